@@ -1,0 +1,189 @@
+/*
+ * katome_gpu.h -- C ABI of the B200 (sm_100a) De Bruijn graph build stage.
+ *
+ * This is the drop-in boundary for katome's GIR producer: every entry point
+ * names the reference interface it replaces (file:line under
+ * /root/reference/src/katome/).  A Rust `GpuGIR` that forwards its
+ * Init/Build/Clean/Standardizable/Stats impls to these symbols is shown in
+ * INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; the handle owns all device memory
+ *   - every function returns 0 (KTG_OK) or a KTG_ERR_* code; the message of
+ *     the last failure on the calling thread is ktg_last_error()
+ *   - one host thread drives one handle (the reference is single-threaded:
+ *     prelude.rs:32-34); the library uses CUDA streams internally
+ *   - there is no CPU fallback: without a CUDA device ktg_create fails
+ *   - k-mers are integers key(w) = sum code(w[j]) * 4^(k-1-j), A0 C1 G2 T3
+ *     (compress.rs:347-378); integer order == the reference's packed-byte
+ *     order.  k <= 32 uses one u64 (lo); 33 <= k <= 64 uses (hi, lo).
+ */
+#ifndef KATOME_GPU_H
+#define KATOME_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KTG_ABI_VERSION 1
+
+enum {
+    KTG_OK = 0,
+    KTG_ERR_SHORT_READ = 1, /* "Read is too short!"          hm_gir.rs:40      */
+    KTG_ERR_BAD_K = 2,      /* assert!(k_size > 1) / len > 2 prelude.rs:35, compress.rs:19 */
+    KTG_ERR_IO = 3,         /* check_files / open panics     builder.rs:57-77,148 */
+    KTG_ERR_BAD_RECORD = 4, /* reader.records() unwrap()     builder.rs:153     */
+    KTG_ERR_DEGENERATE = 5, /* G < k or s == l               standardizer.rs:123-127 */
+    KTG_ERR_TABLE_FULL = 6, /* device table cannot grow further (never silent loss) */
+    KTG_ERR_CUDA = 7,
+    KTG_ERR_INVALID = 8,    /* bad argument / wrong state */
+    KTG_ERR_NO_DEVICE = 9
+};
+
+/* InputFileType (config.rs:5-14); BFCounter input is a "next" row */
+enum { KTG_FASTQ = 0, KTG_FASTA = 1 };
+
+typedef struct ktg_builder ktg_builder;
+
+/* Replaces set_global_k_sizes (prelude.rs:34-43) + Init::init's optional
+ * size hints (builder.rs:19-25).  k is per handle, not a process global. */
+typedef struct ktg_config {
+    uint32_t abi_version;        /* KTG_ABI_VERSION */
+    uint32_t k;                  /* K_SIZE: edge length, 3..=64 */
+    uint32_t reverse_complement; /* Config::reverse_complement (config.rs:33-36) */
+    int32_t device;              /* CUDA device ordinal, -1 = current */
+    uint64_t capacity_hint_edges; /* Init::init(edges_count, ..): expected distinct
+                                     edges as the reference counts them; 0 = grow on demand */
+    uint32_t world_size;         /* hash-sharding: this handle owns keys with */
+    uint32_t rank;               /*   owner(key) == rank; 1/0 = single GPU     */
+    void *stream;                /* cudaStream_t to launch on; NULL = own stream */
+    uint32_t sub_table_log2_bytes; /* 0 = default (L2-resident partition size) */
+    uint32_t flags;              /* KTG_FLAG_* */
+} ktg_config;
+
+#define KTG_FLAG_PROFILE 1u      /* time every kernel launch with CUDA events */
+#define KTG_FLAG_FORCE_DIRECT 2u /* never use the partitioned insert */
+#define KTG_FLAG_FORCE_PARTITION 4u
+
+int ktg_create(const ktg_config *cfg, ktg_builder **out);
+void ktg_destroy(ktg_builder *b);
+const char *ktg_last_error(void);
+int ktg_device_count(void);
+
+/* Build::add_read_fastaq over a batch + the accept/reject rule and byte total
+ * of create_fastq's loop body (builder.rs:152-160, hm_gir.rs:39-87).
+ * bases: concatenated ASCII reads on the HOST, read r = [offsets[r], offsets[r+1]).
+ * A read with any byte outside "ACGT" is dropped whole; an accepted read
+ * shorter than k returns KTG_ERR_SHORT_READ and voids the build.
+ * accepted_* are incremented (not overwritten) when non-NULL. */
+int ktg_add_reads(ktg_builder *b, const uint8_t *bases, const uint64_t *offsets, uint64_t n_reads,
+                  uint64_t *accepted_reads, uint64_t *accepted_bytes);
+
+/* Same, inputs already resident in device memory (d_offsets: n_reads+1 u64).
+ * total_bases == offsets[n_reads].  d_bases must be readable up to the next
+ * 16-byte boundary past its end. */
+int ktg_add_reads_device(ktg_builder *b, const void *d_bases, const void *d_offsets,
+                         uint64_t n_reads, uint64_t total_bases, uint64_t *accepted_reads,
+                         uint64_t *accepted_bytes);
+
+/* Build::create (builder.rs:42-54): check_files + FASTQ/FASTA reader + batcher.
+ * total_bytes = second element of the reference's return tuple. */
+int ktg_create_from_files(ktg_builder *b, const char *const *paths, uint32_t n_paths,
+                          int file_type, uint64_t *total_bytes);
+
+/* Waits for all queued work and surfaces deferred errors (short read, table). */
+int ktg_finalize(ktg_builder *b);
+
+/* Stats<CollectionStats> for HmGIR/HsGIR (stats/collections.rs:170-208):
+ * node_count = |{prefix, suffix of edges}|, edge_count = |edges|. */
+int ktg_counts(ktg_builder *b, uint64_t *nodes, uint64_t *edges);
+
+/* CollectionStats of the converted PtGraph (stats/collections.rs:137-168). */
+typedef struct ktg_stats {
+    uint64_t node_count, edge_count;
+    uint64_t max_edge_weight, sum_edge_weight;
+    uint64_t max_in_degree, max_out_degree;
+    uint64_t incoming_vert_count; /* nodes with in-degree 0  */
+    uint64_t outgoing_vert_count; /* nodes with out-degree 0 */
+} ktg_stats;
+int ktg_collection_stats(ktg_builder *b, ktg_stats *out);
+
+/* Clean::remove_weak_edges / remove_single_vertices for HmGIR
+ * (pruner.rs:95-119, 127-157; edges.rs:51-58): keep edges with w >= threshold;
+ * nodes are implicit (prefix/suffix of surviving edges), so the orphan-node
+ * rule holds by construction and remove_single_vertices is a no-op. */
+int ktg_remove_weak_edges(ktg_builder *b, uint32_t threshold);
+int ktg_remove_single_vertices(ktg_builder *b);
+
+/* Standardizable::standardize_edges (standardizer.rs:42-70, 123-127). */
+int ktg_standardize_edges(ktg_builder *b, uint64_t genome_len, uint64_t k, uint32_t threshold);
+
+/* Edge export = what Convert::create_from consumes (hm_gir.rs:156-226): the
+ * both-strand-expanded edge set with weights, compacted on the device
+ * (stream compaction) and, if sorted != 0, ordered by k-mer.
+ * key_hi may be NULL when k <= 32.  Returns the edge count in *n; copies at
+ * most cap entries. */
+int ktg_export_edges(ktg_builder *b, uint64_t *key_hi, uint64_t *key_lo, uint32_t *weight,
+                     uint64_t cap, int sorted, uint64_t *n);
+
+/* Order-independent digest over the expanded edge set:
+ * out[0] = sum splitmix64(splitmix64(hi)^lo)*(2w+1), out[1] = |E|,
+ * out[2] = sum w, out[3] = max w. */
+int ktg_digest(ktg_builder *b, uint64_t out[4]);
+
+/* ---- hash-sharding across GPUs (world_size > 1): the data path is
+ * extract+partition on the sender, an all-to-all of keys (done by the host
+ * with NCCL), and insert on the owner. ---- */
+uint32_t ktg_key_words(const ktg_builder *b); /* 1 (k<=32) or 2 */
+/* owner rank of a k-mer (after canonicalisation when reverse_complement) */
+uint32_t ktg_owner_of(const ktg_builder *b, uint64_t key_hi, uint64_t key_lo);
+/* Pack + validate + extract the batch's canonical keys, grouped by owner rank.
+ * On return d_keys (device, owned by the handle, valid until the next call)
+ * holds the keys owner-major; counts[world_size] are keys per owner. */
+int ktg_partition_reads_device(ktg_builder *b, const void *d_bases, const void *d_offsets,
+                               uint64_t n_reads, uint64_t total_bases, void **d_keys,
+                               uint64_t *counts, uint64_t *accepted_reads,
+                               uint64_t *accepted_bytes);
+/* Insert n canonical keys (device pointer, ktg_key_words() u64 each, lo first). */
+int ktg_insert_keys_device(ktg_builder *b, const void *d_keys, uint64_t n);
+
+/* ---- pinned host memory for the batcher ---- */
+int ktg_host_alloc(void **p, size_t bytes);
+void ktg_host_free(void *p);
+
+/* ---- synthetic reads on the device (bench workloads; twin of
+ * oracle ko_synth_reads).  Writes (r1-r0)*L ASCII bytes to d_out. */
+int ktg_synth_reads_device(void *d_out, uint64_t seed_g, uint64_t genome_len, uint32_t read_len,
+                           uint32_t err_ppm, uint64_t r0, uint64_t r1, void *stream);
+
+/* ---- random-access roofline probe: n uniformly random 'load key + atomicAdd'
+ * updates over a table of `bytes` bytes; returns elapsed ms. ---- */
+int ktg_random_access_probe(uint64_t bytes, uint64_t n_updates, uint32_t slot_bytes, float *ms);
+
+/* ---- profiling (KTG_FLAG_PROFILE) ---- */
+typedef struct ktg_kernel_profile {
+    char name[32];
+    uint64_t launches;
+    double total_ms;
+    uint64_t units; /* units of work (bases, windows, slots) summed over launches */
+} ktg_kernel_profile;
+int ktg_get_profile(ktg_builder *b, ktg_kernel_profile *out, uint32_t cap, uint32_t *n);
+int ktg_reset_profile(ktg_builder *b);
+
+typedef struct ktg_info {
+    uint64_t capacity_slots, occupied_slots;
+    uint64_t table_bytes;
+    uint32_t n_sub_tables, slot_bytes;
+    uint64_t windows_inserted;
+    uint64_t kernel_launches;
+    uint32_t grow_events, partitioned;
+} ktg_info;
+int ktg_get_info(ktg_builder *b, ktg_info *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,824 @@
+// builder.cuh -- host-side state of one GIR build on one GPU: table sizing and
+// growth, the per-batch kernel schedule, profiling.  Included by ktg_api.cu.
+#pragma once
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/katome_gpu.h"
+#include "kernels.cuh"
+
+namespace ktg {
+
+// ------------------------------------------------------------------ errors
+inline std::string &last_error_ref() {
+    static thread_local std::string s;
+    return s;
+}
+inline int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    last_error_ref() = buf;
+    return code;
+}
+#define KTG_CUDA(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t e_ = (expr);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return ::ktg::fail(KTG_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,                   \
+                               cudaGetErrorString(e_), __FILE__, __LINE__);                    \
+    } while (0)
+#define KTG_TRY(expr)                                                                          \
+    do {                                                                                       \
+        int ktg_try_rc__ = (expr);                                                             \
+        if (ktg_try_rc__ != KTG_OK) return ktg_try_rc__;                                       \
+    } while (0)
+
+// grow-only device buffer
+struct DeviceBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return KTG_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            e = cudaMalloc(&p, bytes);
+            want = bytes;
+        }
+        if (e != cudaSuccess)
+            return fail(KTG_ERR_CUDA, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        cap = want;
+        return KTG_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+// ---------------------------------------------------------------- profiling
+struct Profiler {
+    struct Entry {
+        std::string name;
+        uint64_t launches = 0, units = 0;
+        double ms = 0;
+    };
+    struct Pending {
+        cudaEvent_t a, b;
+        int entry;
+    };
+    bool enabled = false;
+    std::vector<Entry> entries;
+    std::vector<Pending> pending;
+    std::vector<cudaEvent_t> pool;
+    uint64_t total_launches = 0;
+
+    int entry_of(const char *name) {
+        for (size_t i = 0; i < entries.size(); ++i)
+            if (entries[i].name == name) return (int)i;
+        entries.push_back(Entry());
+        entries.back().name = name;
+        return (int)entries.size() - 1;
+    }
+    cudaEvent_t get_event() {
+        if (!pool.empty()) {
+            cudaEvent_t e = pool.back();
+            pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+    void begin(const char *name, uint64_t units, cudaStream_t s) {
+        ++total_launches;
+        if (!enabled) return;
+        Pending p;
+        p.entry = entry_of(name);
+        entries[p.entry].launches++;
+        entries[p.entry].units += units;
+        p.a = get_event();
+        p.b = get_event();
+        cudaEventRecord(p.a, s);
+        pending.push_back(p);
+    }
+    void end(cudaStream_t s) {
+        if (!enabled) return;
+        cudaEventRecord(pending.back().b, s);
+    }
+    void resolve() { // caller has synchronised the stream
+        for (Pending &p : pending) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) entries[p.entry].ms += ms;
+            pool.push_back(p.a);
+            pool.push_back(p.b);
+        }
+        pending.clear();
+    }
+    void reset() {
+        resolve();
+        entries.clear();
+        total_launches = 0;
+    }
+    ~Profiler() {
+        for (Pending &p : pending) {
+            cudaEventDestroy(p.a);
+            cudaEventDestroy(p.b);
+        }
+        for (cudaEvent_t e : pool) cudaEventDestroy(e);
+    }
+};
+
+struct DeviceProps {
+    int sms = 148;
+    size_t l2_bytes = 126u << 20;
+};
+
+constexpr uint32_t MAX_BINS = 2048;      // sub-tables (smem bins of the scatter kernel)
+constexpr double LOAD_MAX = 0.70;        // grow before a batch could exceed this
+constexpr double LOAD_TARGET = 0.50;     // load right after sizing / growing
+constexpr uint64_t OVF_CAP = 1u << 20;   // replay buffer entries
+
+// ------------------------------------------------------------ abstract base
+struct BuilderBase {
+    ktg_config cfg{};
+    uint32_t k = 0;
+    bool rc = false;
+    int device = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    bool own_stream = false;
+    DeviceProps props;
+    Profiler prof;
+    int deferred_error = KTG_OK;
+    uint64_t windows_inserted = 0;
+    uint32_t grow_events = 0;
+
+    virtual ~BuilderBase() {}
+    virtual int init() = 0;
+    virtual int ingest_device(const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t n_reads,
+                              uint64_t total_bases) = 0;
+    virtual int read_counters(uint64_t *reads, uint64_t *bytes) = 0;
+    virtual int finalize() = 0;
+    virtual int edge_stats(uint32_t threshold, EdgeStats *out) = 0;
+    virtual int node_stats(NodeStats *out) = 0;
+    virtual int remove_weak_edges(uint32_t t) = 0;
+    virtual int standardize(uint64_t G, uint64_t k_, uint32_t t) = 0;
+    virtual int export_edges(uint64_t *hi, uint64_t *lo, uint32_t *w, uint64_t cap, int sorted,
+                             uint64_t *n) = 0;
+    virtual int partition_reads(const uint8_t *d_bases, const uint64_t *d_offsets,
+                                uint64_t n_reads, uint64_t total_bases, void **d_keys,
+                                uint64_t *counts) = 0;
+    virtual int insert_keys(const void *d_keys, uint64_t n) = 0;
+    virtual uint32_t owner_of(uint64_t hi, uint64_t lo) = 0;
+    virtual int info(ktg_info *out) = 0;
+};
+
+template <class F> inline int grid_for(F kernel, int block, size_t smem, const DeviceProps &p) {
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem);
+    if (per_sm < 1) per_sm = 1;
+    return p.sms * per_sm; // a whole number of CTAs per SM: one full wave, grid-stride inside
+}
+
+// ---------------------------------------------------------------- the builder
+template <class K> struct Builder : BuilderBase {
+    typedef KeyTraits<K> T;
+    typedef typename T::Slot Slot;
+
+    Table<K> tab{};
+    uint64_t occupied_ub = 0; // upper bound on occupied slots
+    uint64_t hll_base = 0;    // exact occupancy when the sketch was (re)started
+    bool sketch_complete = true; // the sketch covers every key inserted since hll_base
+    DeviceBuf b_hll;
+    DeviceBuf b_packed, b_nstart, b_keys, b_keys2, b_hist, b_ovf_keys, b_ovf_inc, b_small;
+    PackCounters *d_ctr = nullptr;        // accumulates over the whole build
+    unsigned long long *d_ovf_count = nullptr;
+    unsigned long long *d_scratch = nullptr; // 16 u64 of scratch (stats, cursors)
+    // lazily built node ((k-1)-mer) table
+    bool nodes_valid = false;
+    NodeStats node_cache{};
+
+    ~Builder() override {
+        cudaSetDevice(device);
+        if (stream) cudaStreamSynchronize(stream);
+        if (tab.slots) cudaFree(tab.slots);
+        b_packed.release(); b_nstart.release(); b_keys.release(); b_keys2.release();
+        b_hist.release(); b_hll.release(); b_ovf_keys.release(); b_ovf_inc.release(); b_small.release();
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+        if (own_stream && stream) cudaStreamDestroy(stream);
+    }
+
+    // ---- table geometry ------------------------------------------------------
+    static void geometry(uint64_t need_slots, uint32_t sub_log2_bytes, uint32_t *n_sub,
+                         uint32_t *sub_log2) {
+        uint32_t slot_log2 = sizeof(Slot) == 16 ? 4 : 5;
+        uint32_t sl = sub_log2_bytes - slot_log2; // slots per sub-table (log2)
+        if (need_slots < 1024) need_slots = 1024;
+        if (need_slots <= (1ull << sl)) {
+            uint32_t l = 10;
+            while ((1ull << l) < need_slots) ++l;
+            *n_sub = 1;
+            *sub_log2 = l;
+            return;
+        }
+        uint64_t ns = (need_slots + (1ull << sl) - 1) >> sl;
+        while (ns > MAX_BINS) {
+            ++sl;
+            ns = (need_slots + (1ull << sl) - 1) >> sl;
+        }
+        *n_sub = (uint32_t)ns;
+        *sub_log2 = sl;
+    }
+
+    int alloc_table(uint64_t need_slots, Table<K> *out) {
+        Table<K> t = tab;
+        uint32_t slb = cfg.sub_table_log2_bytes ? cfg.sub_table_log2_bytes : 24;
+        geometry(need_slots, slb, &t.n_sub, &t.sub_log2);
+        t.sub_mask = (uint32_t)((1ull << t.sub_log2) - 1);
+        t.max_probe = (uint32_t)std::min<uint64_t>(1ull << t.sub_log2, 2048);
+        size_t bytes = (t.capacity() + 1) * sizeof(Slot);
+        void *p = nullptr;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            return fail(KTG_ERR_TABLE_FULL, "cannot allocate a %zu byte table: %s", bytes,
+                        cudaGetErrorString(e));
+        }
+        t.slots = (Slot *)p;
+        int grid = props.sms * 8;
+        prof.begin("init_table", t.capacity() + 1, stream);
+        init_table_kernel<K><<<grid, 256, 0, stream>>>(t.slots, t.capacity() + 1);
+        prof.end(stream);
+        *out = t;
+        return KTG_OK;
+    }
+
+    int init() override {
+        KTG_CUDA(cudaSetDevice(device));
+        cudaDeviceProp dp;
+        KTG_CUDA(cudaGetDeviceProperties(&dp, device));
+        props.sms = dp.multiProcessorCount;
+        props.l2_bytes = (size_t)dp.l2CacheSize;
+        if (!stream) {
+            KTG_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+            own_stream = true;
+        }
+        KTG_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        KTG_TRY(b_small.ensure(4096));
+        KTG_CUDA(cudaMemsetAsync(b_small.p, 0, 4096, stream));
+        d_ctr = (PackCounters *)b_small.p;
+        d_ovf_count = (unsigned long long *)((char *)b_small.p + 256);
+        d_scratch = (unsigned long long *)((char *)b_small.p + 512);
+        KTG_TRY(b_hll.ensure(HLL_M * 4));
+        KTG_CUDA(cudaMemsetAsync(b_hll.p, 0, HLL_M * 4, stream));
+        KTG_TRY(b_ovf_keys.ensure(OVF_CAP * sizeof(K)));
+        KTG_TRY(b_ovf_inc.ensure(OVF_CAP * sizeof(uint32_t)));
+        tab.world = cfg.world_size ? cfg.world_size : 1;
+        tab.rank = cfg.rank;
+        tab.ovf_keys = (K *)b_ovf_keys.p;
+        tab.ovf_inc = (uint32_t *)b_ovf_inc.p;
+        tab.ovf_count = d_ovf_count;
+        tab.ovf_cap = OVF_CAP;
+        // capacity hint counts edges the way the reference does (both strands)
+        uint64_t entries = cfg.capacity_hint_edges;
+        if (rc) entries = (entries + 1) / 2;
+        entries = (entries + tab.world - 1) / tab.world;
+        uint64_t need = entries ? (uint64_t)((double)entries / LOAD_TARGET) + 1 : (1u << 20);
+        KTG_TRY(alloc_table(need, &tab));
+        // opt in to large dynamic shared memory for the scatter kernels
+        set_smem_attrs();
+        return KTG_OK;
+    }
+
+    size_t scatter_reads_smem(uint32_t n_bins) const {
+        return (size_t)ScatterCfg<K>::TILE_KEYS * (sizeof(K) + 2) + (size_t)(n_bins + (n_bins & 1)) * 8 +
+               (size_t)n_bins * 8;
+    }
+    size_t scatter_keys_smem(uint32_t n_bins) const {
+        return (size_t)4096 * (sizeof(K) + 2) + (size_t)(n_bins + (n_bins & 1)) * 8 + (size_t)n_bins * 8;
+    }
+    void set_smem_attrs() {
+        int mx = (int)scatter_reads_smem(MAX_BINS);
+        cudaFuncSetAttribute(scatter_reads_kernel<K, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(scatter_reads_kernel<K, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(scatter_reads_kernel<K, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(scatter_reads_kernel<K, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        int mk = (int)scatter_keys_smem(MAX_BINS);
+        cudaFuncSetAttribute(scatter_keys_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mk);
+        cudaFuncSetAttribute(scatter_keys_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mk);
+    }
+
+    bool use_partition() const {
+        if (cfg.flags & KTG_FLAG_FORCE_DIRECT) return false;
+        if (cfg.flags & KTG_FLAG_FORCE_PARTITION) return true;
+        return tab.n_sub > 3; // up to ~48 MB of table is L2 resident as a whole
+    }
+
+    int sync() {
+        KTG_CUDA(cudaStreamSynchronize(stream));
+        prof.resolve();
+        return KTG_OK;
+    }
+
+    // ---- growth -----------------------------------------------------------------
+    int count_occupied(uint64_t *out) {
+        KTG_CUDA(cudaMemsetAsync(d_scratch, 0, 8, stream));
+        prof.begin("count_occupied", tab.capacity(), stream);
+        count_occupied_kernel<K><<<props.sms * 8, 256, 0, stream>>>(tab.slots, tab.capacity(), d_scratch);
+        prof.end(stream);
+        unsigned long long v = 0;
+        KTG_CUDA(cudaMemcpyAsync(&v, d_scratch, 8, cudaMemcpyDeviceToHost, stream));
+        KTG_TRY(sync());
+        *out = v;
+        return KTG_OK;
+    }
+
+    int grow_to(uint64_t need_slots) {
+        Table<K> nt;
+        KTG_TRY(alloc_table(need_slots, &nt));
+        prof.begin("rehash", tab.capacity(), stream);
+        rehash_kernel<K><<<props.sms * 8, 256, 0, stream>>>(tab.slots, tab.capacity(), nt);
+        prof.end(stream);
+        KTG_TRY(sync());
+        cudaFree(tab.slots);
+        tab = nt;
+        ++grow_events;
+        return KTG_OK;
+    }
+
+    // replay inserts that did not fit (after growing); void the build if any were dropped
+    int drain_overflow() {
+        unsigned long long n = 0;
+        KTG_CUDA(cudaMemcpyAsync(&n, d_ovf_count, 8, cudaMemcpyDeviceToHost, stream));
+        KTG_TRY(sync());
+        while (n) {
+            if (n > OVF_CAP) {
+                deferred_error = KTG_ERR_TABLE_FULL;
+                return fail(KTG_ERR_TABLE_FULL, "%llu inserts overflowed the replay buffer", n - OVF_CAP);
+            }
+            KTG_TRY(b_keys2.ensure(n * sizeof(K)));
+            DeviceBuf inc;
+            KTG_TRY(inc.ensure(n * 4));
+            KTG_CUDA(cudaMemcpyAsync(b_keys2.p, tab.ovf_keys, n * sizeof(K), cudaMemcpyDeviceToDevice, stream));
+            KTG_CUDA(cudaMemcpyAsync(inc.p, tab.ovf_inc, n * 4, cudaMemcpyDeviceToDevice, stream));
+            KTG_CUDA(cudaMemsetAsync(d_ovf_count, 0, 8, stream));
+            int rc_ = grow_to(tab.capacity() * 2);
+            if (rc_ != KTG_OK) { inc.release(); return rc_; }
+            prof.begin("replay_overflow", n, stream);
+            replay_overflow_kernel<K><<<props.sms * 4, 256, 0, stream>>>((const K *)b_keys2.p, (const uint32_t *)inc.p, n, tab);
+            prof.end(stream);
+            KTG_CUDA(cudaMemcpyAsync(&n, d_ovf_count, 8, cudaMemcpyDeviceToHost, stream));
+            KTG_TRY(sync());
+            inc.release();
+        }
+        return KTG_OK;
+    }
+
+    // HyperLogLog estimate of the distinct keys ever offered to this table
+    // (persistent sketch, see kernels.cuh)
+    int hll_estimate(double *est) {
+        std::vector<uint32_t> regs(HLL_M);
+        KTG_CUDA(cudaMemcpyAsync(regs.data(), b_hll.p, HLL_M * 4, cudaMemcpyDeviceToHost, stream));
+        KTG_TRY(sync());
+        double m = (double)HLL_M, sum = 0;
+        uint32_t zeros = 0;
+        for (uint32_t r : regs) {
+            sum += ldexp(1.0, -(int)r);
+            zeros += r == 0;
+        }
+        double e = (0.7213 / (1.0 + 1.079 / m)) * m * m / sum;
+        if (e <= 2.5 * m && zeros) e = m * log(m / (double)zeros);
+        *est = e;
+        return KTG_OK;
+    }
+
+    // Make sure the coming batch cannot push the load past LOAD_MAX.  `bound`
+    // is a trivial upper bound on its new keys; when that is not enough to
+    // decide, `sketch()` folds the batch into the HyperLogLog sketch and the
+    // table is sized from the estimated number of distinct keys.  Estimate
+    // errors are caught by the overflow/replay path, never lost.
+    template <class F> int reserve(uint64_t bound, F sketch) {
+        if ((double)(occupied_ub + bound) <= LOAD_MAX * (double)tab.capacity()) {
+            occupied_ub += bound;
+            sketch_complete = false; // these keys go in unsketched
+            return KTG_OK;
+        }
+        if (!sketch_complete) {
+            uint64_t exact = 0;
+            KTG_TRY(count_occupied(&exact));
+            occupied_ub = exact;
+            if ((double)(exact + bound) <= LOAD_MAX * (double)tab.capacity()) {
+                occupied_ub += bound;
+                return KTG_OK;
+            }
+            // restart the sketch here: estimate = exact + distinct(batches from now on)
+            hll_base = exact;
+            sketch_complete = true;
+            KTG_CUDA(cudaMemsetAsync(b_hll.p, 0, HLL_M * 4, stream));
+        }
+        KTG_TRY(sketch());
+        double est = 0;
+        KTG_TRY(hll_estimate(&est));
+        uint64_t total = hll_base + (uint64_t)(est * 1.08) + 64;
+        if ((double)total > LOAD_MAX * (double)tab.capacity()) {
+            uint64_t need = (uint64_t)((double)total / LOAD_TARGET) + 1;
+            KTG_TRY(grow_to(need));
+        }
+        occupied_ub = total;
+        return KTG_OK;
+    }
+
+    // ---- K1 ------------------------------------------------------------------------
+    int pack(const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t n_reads,
+             uint64_t total_bases, uint64_t *n_words) {
+        uint64_t nw = total_bases / 32 + n_reads;
+        KTG_TRY(b_packed.ensure((nw + 4) * 8));
+        KTG_TRY(b_nstart.ensure(nw + 4));
+        *n_words = nw;
+        if (n_reads == 0) return KTG_OK;
+        int grid = grid_for(pack_reads_kernel, 256, 0, props);
+        uint64_t want = (n_reads * PACK_GROUP + 255) / 256;
+        if ((uint64_t)grid > want) grid = (int)want;
+        prof.begin("pack_reads", total_bases, stream);
+        pack_reads_kernel<<<grid, 256, 0, stream>>>(d_bases, d_offsets, n_reads, k, (uint64_t *)b_packed.p,
+                                                    (uint8_t *)b_nstart.p, d_ctr);
+        prof.end(stream);
+        nodes_valid = false;
+        return KTG_OK;
+    }
+
+    // ---- partition helpers ----------------------------------------------------------
+    // bins -> exclusive offsets in d_hist[n_bins .. 2n_bins], cursors in [2n_bins+1 ..]
+    unsigned long long *hist_ptr() { return (unsigned long long *)b_hist.p; }
+    unsigned long long *offs_ptr(uint32_t n_bins) { return hist_ptr() + n_bins; }
+    unsigned long long *curs_ptr(uint32_t n_bins) { return hist_ptr() + 2 * n_bins + 1; }
+
+    template <bool BY_OWNER>
+    int partition_from_reads(uint64_t n_words, uint64_t max_keys, uint32_t n_bins, K **out) {
+        KTG_TRY(b_hist.ensure((3 * (size_t)n_bins + 2) * 8));
+        KTG_TRY(b_keys.ensure(max_keys * sizeof(K) + 16));
+        KTG_CUDA(cudaMemsetAsync(b_hist.p, 0, n_bins * 8, stream));
+        const uint64_t *packed = (const uint64_t *)b_packed.p;
+        const uint8_t *nstart = (const uint8_t *)b_nstart.p;
+        size_t hs = (size_t)n_bins * 4;
+        if (rc) {
+            int g = grid_for(hist_reads_kernel<K, true, BY_OWNER>, 256, hs, props);
+            prof.begin("hist_reads", n_words * 32, stream);
+            hist_reads_kernel<K, true, BY_OWNER><<<g, 256, hs, stream>>>(packed, nstart, n_words, k, tab, n_bins, hist_ptr());
+        }
+        else {
+            int g = grid_for(hist_reads_kernel<K, false, BY_OWNER>, 256, hs, props);
+            prof.begin("hist_reads", n_words * 32, stream);
+            hist_reads_kernel<K, false, BY_OWNER><<<g, 256, hs, stream>>>(packed, nstart, n_words, k, tab, n_bins, hist_ptr());
+        }
+        prof.end(stream);
+        prof.begin("scan_bins", n_bins, stream);
+        scan_bins_kernel<<<1, 1024, 0, stream>>>(hist_ptr(), n_bins, offs_ptr(n_bins), curs_ptr(n_bins));
+        prof.end(stream);
+        size_t ss = scatter_reads_smem(n_bins);
+        constexpr int TW = ScatterCfg<K>::TILE_WORDS;
+        uint64_t n_tiles = (n_words + TW - 1) / TW;
+        if (rc) {
+            int g = (int)std::min<uint64_t>(grid_for(scatter_reads_kernel<K, true, BY_OWNER>, TW, ss, props), n_tiles);
+            prof.begin("scatter_reads", n_words * 32, stream);
+            scatter_reads_kernel<K, true, BY_OWNER><<<g, TW, ss, stream>>>(packed, nstart, n_words, k, tab, n_bins, curs_ptr(n_bins), (K *)b_keys.p);
+        }
+        else {
+            int g = (int)std::min<uint64_t>(grid_for(scatter_reads_kernel<K, false, BY_OWNER>, TW, ss, props), n_tiles);
+            prof.begin("scatter_reads", n_words * 32, stream);
+            scatter_reads_kernel<K, false, BY_OWNER><<<g, TW, ss, stream>>>(packed, nstart, n_words, k, tab, n_bins, curs_ptr(n_bins), (K *)b_keys.p);
+        }
+        prof.end(stream);
+        *out = (K *)b_keys.p;
+        return KTG_OK;
+    }
+
+    int partition_from_keys(const K *keys, uint64_t n, uint32_t n_bins, K **out) {
+        KTG_TRY(b_hist.ensure((3 * (size_t)n_bins + 2) * 8));
+        KTG_TRY(b_keys2.ensure(n * sizeof(K) + 16));
+        KTG_CUDA(cudaMemsetAsync(b_hist.p, 0, n_bins * 8, stream));
+        size_t hs = (size_t)n_bins * 4;
+        int g = grid_for(hist_keys_kernel<K, false>, 256, hs, props);
+        prof.begin("hist_keys", n, stream);
+        hist_keys_kernel<K, false><<<g, 256, hs, stream>>>(keys, n, tab, n_bins, hist_ptr());
+        prof.end(stream);
+        prof.begin("scan_bins", n_bins, stream);
+        scan_bins_kernel<<<1, 1024, 0, stream>>>(hist_ptr(), n_bins, offs_ptr(n_bins), curs_ptr(n_bins));
+        prof.end(stream);
+        size_t ss = scatter_keys_smem(n_bins);
+        uint64_t n_tiles = (n + 4095) / 4096;
+        int g2 = (int)std::min<uint64_t>(grid_for(scatter_keys_kernel<K, false>, 256, ss, props), std::max<uint64_t>(n_tiles, 1));
+        prof.begin("scatter_keys", n, stream);
+        scatter_keys_kernel<K, false><<<g2, 256, ss, stream>>>(keys, n, tab, n_bins, curs_ptr(n_bins), (K *)b_keys2.p);
+        prof.end(stream);
+        *out = (K *)b_keys2.p;
+        return KTG_OK;
+    }
+
+    int launch_insert_keys(const K *keys, uint64_t n) {
+        if (n == 0) return KTG_OK;
+        int g = grid_for(insert_keys_kernel<K>, 256, 0, props);
+        g = (int)std::min<uint64_t>(g, (n + 255) / 256);
+        prof.begin("insert_keys", n, stream);
+        insert_keys_kernel<K><<<g, 256, 0, stream>>>(keys, n, k, rc && (k % 2 == 0), tab);
+        prof.end(stream);
+        nodes_valid = false;
+        return KTG_OK;
+    }
+
+    // ---- one batch of reads, all on the device ---------------------------------------
+    int ingest_device(const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t n_reads,
+                      uint64_t total_bases) override {
+        if (deferred_error != KTG_OK) return fail(deferred_error, "build is void after an earlier error");
+        if (tab.world > 1)
+            return fail(KTG_ERR_INVALID, "world_size > 1: use ktg_partition_reads_device + ktg_insert_keys_device");
+        if (n_reads == 0) return KTG_OK;
+        uint64_t n_words = 0;
+        KTG_TRY(pack(d_bases, d_offsets, n_reads, total_bases, &n_words));
+        const uint64_t *packed = (const uint64_t *)b_packed.p;
+        const uint8_t *nstart = (const uint8_t *)b_nstart.p;
+        const uint64_t max_windows = total_bases; // trivial bound on the batch's keys
+        KTG_TRY(reserve(max_windows, [&]() -> int {
+            prof.begin("hll_reads", n_words * 32, stream);
+            if (rc) hll_reads_kernel<K, true><<<props.sms * 4, 256, 0, stream>>>(packed, nstart, n_words, k, (uint32_t *)b_hll.p);
+            else hll_reads_kernel<K, false><<<props.sms * 4, 256, 0, stream>>>(packed, nstart, n_words, k, (uint32_t *)b_hll.p);
+            prof.end(stream);
+            return KTG_OK;
+        }));
+        if (!use_partition()) {
+            if (rc) {
+                int g = grid_for(extract_insert_kernel<K, true>, 256, 0, props);
+                g = (int)std::min<uint64_t>(g, (n_words + 255) / 256);
+                prof.begin("extract_insert", n_words * 32, stream);
+                extract_insert_kernel<K, true><<<g, 256, 0, stream>>>(packed, nstart, n_words, k, tab);
+            }
+            else {
+                int g = grid_for(extract_insert_kernel<K, false>, 256, 0, props);
+                g = (int)std::min<uint64_t>(g, (n_words + 255) / 256);
+                prof.begin("extract_insert", n_words * 32, stream);
+                extract_insert_kernel<K, false><<<g, 256, 0, stream>>>(packed, nstart, n_words, k, tab);
+            }
+            prof.end(stream);
+        }
+        else {
+            K *keys = nullptr;
+            KTG_TRY(partition_from_reads<false>(n_words, max_windows, tab.n_sub, &keys));
+            // the exact key count lives on the device (offsets[n_bins]); read it
+            // back: the insert grid does not depend on it, only the loop bound
+            unsigned long long n_keys = 0;
+            KTG_CUDA(cudaMemcpyAsync(&n_keys, offs_ptr(tab.n_sub) + tab.n_sub, 8, cudaMemcpyDeviceToHost, stream));
+            KTG_CUDA(cudaStreamSynchronize(stream));
+            KTG_TRY(launch_insert_keys(keys, n_keys));
+        }
+        KTG_CUDA(cudaGetLastError());
+        return KTG_OK;
+    }
+
+    int read_counters(uint64_t *reads, uint64_t *bytes) override {
+        PackCounters c;
+        KTG_CUDA(cudaMemcpyAsync(&c, d_ctr, sizeof c, cudaMemcpyDeviceToHost, stream));
+        KTG_TRY(sync());
+        if (reads) *reads = c.accepted_reads;
+        if (bytes) *bytes = c.accepted_bytes;
+        windows_inserted = c.windows;
+        if (c.short_reads) {
+            deferred_error = KTG_ERR_SHORT_READ;
+            return fail(KTG_ERR_SHORT_READ, "Read is too short!");
+        }
+        return KTG_OK;
+    }
+
+    int finalize() override {
+        if (deferred_error != KTG_OK) return fail(deferred_error, "build is void after an earlier error");
+        KTG_TRY(read_counters(nullptr, nullptr));
+        KTG_TRY(drain_overflow());
+        return KTG_OK;
+    }
+
+    // ---- stats ------------------------------------------------------------------------
+    int edge_stats(uint32_t threshold, EdgeStats *out) override {
+        KTG_TRY(finalize());
+        KTG_CUDA(cudaMemsetAsync(d_scratch, 0, sizeof(EdgeStats), stream));
+        uint64_t n = tab.capacity() + 1;
+        prof.begin("edge_stats", n, stream);
+        if (rc) edge_stats_kernel<K, true><<<props.sms * 8, 256, 0, stream>>>(tab.slots, n, k, threshold, (EdgeStats *)d_scratch);
+        else edge_stats_kernel<K, false><<<props.sms * 8, 256, 0, stream>>>(tab.slots, n, k, threshold, (EdgeStats *)d_scratch);
+        prof.end(stream);
+        KTG_CUDA(cudaMemcpyAsync(out, d_scratch, sizeof(EdgeStats), cudaMemcpyDeviceToHost, stream));
+        return sync();
+    }
+
+    template <class KN> int node_stats_t(NodeStats *out) {
+        // distinct canonical nodes <= 2 x live canonical edges
+        uint64_t occ = 0;
+        KTG_TRY(count_occupied(&occ));
+        Table<KN> nt{};
+        uint64_t need = (uint64_t)(2.0 * (double)(occ + 1) / 0.8) + 1024;
+        uint32_t l = 10;
+        while ((1ull << l) < need) ++l;
+        nt.n_sub = 1;
+        nt.sub_log2 = l;
+        nt.sub_mask = (uint32_t)((1ull << l) - 1);
+        nt.max_probe = (uint32_t)std::min<uint64_t>(1ull << l, 1u << 20);
+        nt.world = 1;
+        nt.rank = 0;
+        nt.ovf_keys = nullptr;
+        nt.ovf_inc = nullptr;
+        nt.ovf_count = d_scratch + 15; // count only; nothing is stored (ovf_cap = 0)
+        nt.ovf_cap = 0;
+        typedef typename KeyTraits<KN>::Slot NSlot;
+        void *p = nullptr;
+        size_t bytes = (nt.capacity() + 1) * sizeof(NSlot);
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            return fail(KTG_ERR_CUDA, "cannot allocate %zu bytes for the node table: %s", bytes, cudaGetErrorString(e));
+        }
+        nt.slots = (NSlot *)p;
+        KTG_CUDA(cudaMemsetAsync(d_scratch, 0, 128, stream));
+        prof.begin("init_table", nt.capacity() + 1, stream);
+        init_table_kernel<KN><<<props.sms * 8, 256, 0, stream>>>(nt.slots, nt.capacity() + 1);
+        prof.end(stream);
+        uint64_t n = tab.capacity() + 1;
+        prof.begin("build_nodes", n, stream);
+        if (rc) build_nodes_kernel<K, KN, true><<<props.sms * 8, 256, 0, stream>>>(tab.slots, n, k, nt);
+        else build_nodes_kernel<K, KN, false><<<props.sms * 8, 256, 0, stream>>>(tab.slots, n, k, nt);
+        prof.end(stream);
+        prof.begin("node_stats", nt.capacity() + 1, stream);
+        if (rc) node_stats_kernel<KN, true><<<props.sms * 8, 256, 0, stream>>>(nt.slots, nt.capacity() + 1, (NodeStats *)d_scratch);
+        else node_stats_kernel<KN, false><<<props.sms * 8, 256, 0, stream>>>(nt.slots, nt.capacity() + 1, (NodeStats *)d_scratch);
+        prof.end(stream);
+        unsigned long long host[16];
+        KTG_CUDA(cudaMemcpyAsync(host, d_scratch, sizeof host, cudaMemcpyDeviceToHost, stream));
+        int rc_ = sync();
+        cudaFree(p);
+        KTG_TRY(rc_);
+        if (host[15]) return fail(KTG_ERR_TABLE_FULL, "node table overflow (%llu)", host[15]);
+        memcpy(out, host, sizeof(NodeStats));
+        return KTG_OK;
+    }
+
+    int node_stats(NodeStats *out) override {
+        KTG_TRY(finalize());
+        if (!nodes_valid) {
+            if (k - 1 <= 32) KTG_TRY(node_stats_t<uint64_t>(&node_cache));
+            else KTG_TRY(node_stats_t<u128>(&node_cache));
+            nodes_valid = true;
+        }
+        *out = node_cache;
+        return KTG_OK;
+    }
+
+    // ---- K4 -----------------------------------------------------------------------------
+    int remove_weak_edges(uint32_t t) override {
+        KTG_TRY(finalize());
+        if (t <= 1) return KTG_OK; // every stored edge has w >= 1
+        uint64_t n = tab.capacity() + 1;
+        prof.begin("filter", n, stream);
+        filter_kernel<K><<<props.sms * 8, 256, 0, stream>>>(tab.slots, n, t);
+        prof.end(stream);
+        nodes_valid = false;
+        KTG_CUDA(cudaGetLastError());
+        return KTG_OK;
+    }
+
+    int standardize(uint64_t G, uint64_t k_, uint32_t t) override {
+        EdgeStats es;
+        KTG_TRY(edge_stats(t, &es));
+        if (G < k_ || es.sum_w == es.sum_w_below)
+            return fail(KTG_ERR_DEGENERATE, "degenerate standardization ratio (G=%llu k=%llu s=%llu l=%llu)",
+                        (unsigned long long)G, (unsigned long long)k_, es.sum_w, es.sum_w_below);
+        double p = (double)(G - k_) / (double)(es.sum_w - es.sum_w_below); // standardizer.rs:123-127
+        uint64_t n = tab.capacity() + 1;
+        prof.begin("standardize", n, stream);
+        standardize_kernel<K><<<props.sms * 8, 256, 0, stream>>>(tab.slots, n, p, t);
+        prof.end(stream);
+        nodes_valid = false;
+        KTG_CUDA(cudaGetLastError());
+        return KTG_OK;
+    }
+
+    int export_edges(uint64_t *hi, uint64_t *lo, uint32_t *w, uint64_t cap, int sorted,
+                     uint64_t *n_out) override {
+        EdgeStats es;
+        KTG_TRY(edge_stats(0, &es));
+        uint64_t ne = es.edges;
+        if (n_out) *n_out = ne;
+        uint64_t m = std::min(ne, cap);
+        if (m == 0 || !lo || !w) return KTG_OK;
+        bool wide = T::WORDS == 2;
+        DeviceBuf d_hi, d_lo, d_w;
+        KTG_TRY(d_lo.ensure(ne * 8));
+        KTG_TRY(d_w.ensure(ne * 4));
+        if (wide) KTG_TRY(d_hi.ensure(ne * 8));
+        KTG_CUDA(cudaMemsetAsync(d_scratch, 0, 8, stream));
+        uint64_t n = tab.capacity() + 1;
+        prof.begin("compact_edges", n, stream);
+        if (rc) compact_edges_kernel<K, true><<<props.sms * 8, 256, 0, stream>>>(tab.slots, n, k, 1, (uint64_t *)d_hi.p, (uint64_t *)d_lo.p, (uint32_t *)d_w.p, ne, d_scratch);
+        else compact_edges_kernel<K, false><<<props.sms * 8, 256, 0, stream>>>(tab.slots, n, k, 1, (uint64_t *)d_hi.p, (uint64_t *)d_lo.p, (uint32_t *)d_w.p, ne, d_scratch);
+        prof.end(stream);
+        std::vector<uint64_t> h_hi(wide ? ne : 0), h_lo(ne);
+        std::vector<uint32_t> h_w(ne);
+        KTG_CUDA(cudaMemcpyAsync(h_lo.data(), d_lo.p, ne * 8, cudaMemcpyDeviceToHost, stream));
+        KTG_CUDA(cudaMemcpyAsync(h_w.data(), d_w.p, ne * 4, cudaMemcpyDeviceToHost, stream));
+        if (wide) KTG_CUDA(cudaMemcpyAsync(h_hi.data(), d_hi.p, ne * 8, cudaMemcpyDeviceToHost, stream));
+        int rc_ = sync();
+        d_hi.release(); d_lo.release(); d_w.release();
+        KTG_TRY(rc_);
+        std::vector<uint64_t> perm(ne);
+        for (uint64_t i = 0; i < ne; ++i) perm[i] = i;
+        if (sorted) {
+            std::sort(perm.begin(), perm.end(), [&](uint64_t a, uint64_t b) {
+                if (wide && h_hi[a] != h_hi[b]) return h_hi[a] < h_hi[b];
+                return h_lo[a] < h_lo[b];
+            });
+        }
+        for (uint64_t i = 0; i < m; ++i) {
+            uint64_t j = perm[i];
+            if (hi) hi[i] = wide ? h_hi[j] : 0;
+            lo[i] = h_lo[j];
+            w[i] = h_w[j];
+        }
+        return KTG_OK;
+    }
+
+    // ---- multi-GPU phases -------------------------------------------------------------------
+    int partition_reads(const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t n_reads,
+                        uint64_t total_bases, void **d_keys, uint64_t *counts) override {
+        if (deferred_error != KTG_OK) return fail(deferred_error, "build is void after an earlier error");
+        uint32_t W = tab.world;
+        for (uint32_t i = 0; i < W; ++i) counts[i] = 0;
+        *d_keys = nullptr;
+        if (n_reads == 0) return KTG_OK;
+        uint64_t n_words = 0;
+        KTG_TRY(pack(d_bases, d_offsets, n_reads, total_bases, &n_words));
+        K *keys = nullptr;
+        KTG_TRY(partition_from_reads<true>(n_words, total_bases, W, &keys));
+        std::vector<unsigned long long> h(W);
+        KTG_CUDA(cudaMemcpyAsync(h.data(), hist_ptr(), W * 8, cudaMemcpyDeviceToHost, stream));
+        KTG_TRY(sync());
+        for (uint32_t i = 0; i < W; ++i) counts[i] = h[i];
+        *d_keys = keys;
+        return KTG_OK;
+    }
+
+    int insert_keys(const void *d_keys, uint64_t n) override {
+        if (deferred_error != KTG_OK) return fail(deferred_error, "build is void after an earlier error");
+        if (n == 0) return KTG_OK;
+        const K *keys = (const K *)d_keys;
+        KTG_TRY(reserve(n, [&]() -> int {
+            prof.begin("hll_keys", n, stream);
+            hll_keys_kernel<K><<<props.sms * 4, 256, 0, stream>>>(keys, n, (uint32_t *)b_hll.p);
+            prof.end(stream);
+            return KTG_OK;
+        }));
+        if (use_partition()) {
+            K *sorted = nullptr;
+            KTG_TRY(partition_from_keys(keys, n, tab.n_sub, &sorted));
+            keys = sorted;
+        }
+        KTG_TRY(launch_insert_keys(keys, n));
+        KTG_CUDA(cudaGetLastError());
+        return KTG_OK;
+    }
+
+    uint32_t owner_of(uint64_t hi, uint64_t lo) override {
+        K key = T::make(hi, lo);
+        if (rc) {
+            K r = revcomp(key, k);
+            if (r < key) key = r;
+        }
+        return place_of(T::hash(key), tab.world, tab.n_sub, tab.sub_mask).owner;
+    }
+
+    int info(ktg_info *out) override {
+        memset(out, 0, sizeof *out);
+        uint64_t occ = 0;
+        KTG_TRY(count_occupied(&occ));
+        out->capacity_slots = tab.capacity();
+        out->occupied_slots = occ;
+        out->table_bytes = (tab.capacity() + 1) * sizeof(Slot);
+        out->n_sub_tables = tab.n_sub;
+        out->slot_bytes = sizeof(Slot);
+        out->windows_inserted = windows_inserted;
+        out->kernel_launches = prof.total_launches;
+        out->grow_events = grow_events;
+        out->partitioned = use_partition();
+        return KTG_OK;
+    }
+};
+
+} // namespace ktg

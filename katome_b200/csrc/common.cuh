@@ -1,0 +1,198 @@
+// common.cuh -- key types, hashing and the open-addressing table primitives.
+//
+// Keys are k-mers as integers, first base in the most significant 2 bits
+// (A0 C1 G2 T3; /root/reference/src/katome/compress.rs:347-378), right
+// aligned: k <= 32 in a u64, 33..64 in a u128.  The table replaces katome's
+// HashMap<NodeSlice, Outgoing> (collections/girs/hm_gir.rs:22): instead of a
+// node-keyed map with <=4 outgoing edges per node we key directly on the edge
+// k-mer and keep one u32 weight per edge (create_or_modify_edge,
+// collections/girs/hs_gir.rs:192-203 -> atomicAdd).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace ktg {
+
+typedef unsigned __int128 u128;
+
+// splitmix64 finalizer; also the building block of the digest and of the
+// synthetic read generator (oracle/katome_oracle.c has the CPU twins).
+__host__ __device__ __forceinline__ uint64_t fmix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    return fmix64(x + 0x9E3779B97F4A7C15ull);
+}
+
+// ---- reverse complement on packed integers (compress.rs:153-169 restated as
+// bit tricks: complement = NOT (:164), reversal of 2-bit symbols) ----
+__host__ __device__ __forceinline__ uint64_t rev2_u64(uint64_t x) {
+#ifdef __CUDA_ARCH__
+    x = __brevll(x);
+#else
+    x = ((x >> 32) | (x << 32));
+    x = ((x >> 16) & 0x0000FFFF0000FFFFull) | ((x & 0x0000FFFF0000FFFFull) << 16);
+    x = ((x >> 8) & 0x00FF00FF00FF00FFull) | ((x & 0x00FF00FF00FF00FFull) << 8);
+    x = ((x >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((x & 0x0F0F0F0F0F0F0F0Full) << 4);
+    x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
+    x = ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
+#endif
+    // all 64 bits are reversed; swap the two bits of every symbol back
+    return ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
+}
+
+__host__ __device__ __forceinline__ uint64_t revcomp(uint64_t x, uint32_t k) {
+    return rev2_u64(~x) >> (64 - 2 * k);
+}
+__host__ __device__ __forceinline__ u128 revcomp(u128 x, uint32_t k) {
+    uint64_t lo = (uint64_t)x, hi = (uint64_t)(x >> 64);
+    u128 r = ((u128)rev2_u64(~lo) << 64) | rev2_u64(~hi);
+    return r >> (128 - 2 * k);
+}
+
+template <class K> struct KeyTraits;
+
+template <> struct KeyTraits<uint64_t> {
+    static constexpr int WORDS = 1;
+    struct alignas(16) Slot {
+        uint64_t key;
+        uint32_t w;
+        uint32_t aux;
+    };
+    __host__ __device__ static __forceinline__ uint64_t empty() { return ~0ull; }
+    __host__ __device__ static __forceinline__ uint64_t hash(uint64_t k) {
+        return fmix64(k ^ 0x6b61746f6d65ull);
+    }
+    __host__ __device__ static __forceinline__ uint64_t hi(uint64_t) { return 0; }
+    __host__ __device__ static __forceinline__ uint64_t lo(uint64_t k) { return k; }
+    __host__ __device__ static __forceinline__ uint64_t make(uint64_t, uint64_t lo_) { return lo_; }
+#ifdef __CUDACC__
+    __device__ static __forceinline__ uint64_t load(const Slot *s) {
+        return __ldcg((const unsigned long long *)&s->key);
+    }
+    __device__ static __forceinline__ bool maybe_torn(uint64_t) { return false; }
+    __device__ static __forceinline__ uint64_t cas(Slot *s, uint64_t cmp, uint64_t val) {
+        return atomicCAS((unsigned long long *)&s->key, (unsigned long long)cmp,
+                         (unsigned long long)val);
+    }
+    __device__ static __forceinline__ void store_key(Slot *s, uint64_t k) { s->key = k; }
+#endif
+};
+
+template <> struct KeyTraits<u128> {
+    static constexpr int WORDS = 2;
+    struct alignas(32) Slot {
+        uint64_t lo, hi;
+        uint32_t w;
+        uint32_t aux[3];
+    };
+    __host__ __device__ static __forceinline__ u128 empty() { return ~(u128)0; }
+    __host__ __device__ static __forceinline__ uint64_t hash(u128 k) {
+        return fmix64((uint64_t)k ^ fmix64((uint64_t)(k >> 64) ^ 0x6b61746f6d65ull));
+    }
+    __host__ __device__ static __forceinline__ uint64_t hi(u128 k) { return (uint64_t)(k >> 64); }
+    __host__ __device__ static __forceinline__ uint64_t lo(u128 k) { return (uint64_t)k; }
+    __host__ __device__ static __forceinline__ u128 make(uint64_t hi_, uint64_t lo_) {
+        return ((u128)hi_ << 64) | lo_;
+    }
+#ifdef __CUDACC__
+    __device__ static __forceinline__ u128 load(const Slot *s) {
+        ulonglong2 v = __ldcg((const ulonglong2 *)s);
+        return ((u128)v.y << 64) | v.x;
+    }
+    // A 16-byte vector load is one transaction in practice but is not promised
+    // to be single-copy atomic against the 128-bit CAS; a value with an
+    // all-ones half could be a half-written key, so it is re-read with the CAS.
+    __device__ static __forceinline__ bool maybe_torn(u128 k) {
+        return (uint64_t)k == ~0ull || (uint64_t)(k >> 64) == ~0ull;
+    }
+    __device__ static __forceinline__ u128 cas(Slot *s, u128 cmp, u128 val) {
+        uint64_t olo, ohi;
+        asm volatile(
+            "{\n\t"
+            ".reg .b128 c, v, o;\n\t"
+            "mov.b128 c, {%2, %3};\n\t"
+            "mov.b128 v, {%4, %5};\n\t"
+            "atom.global.relaxed.gpu.cas.b128 o, [%6], c, v;\n\t"
+            "mov.b128 {%0, %1}, o;\n\t"
+            "}\n"
+            : "=l"(olo), "=l"(ohi)
+            : "l"((uint64_t)cmp), "l"((uint64_t)(cmp >> 64)), "l"((uint64_t)val),
+              "l"((uint64_t)(val >> 64)), "l"(s)
+            : "memory");
+        return ((u128)ohi << 64) | olo;
+    }
+    __device__ static __forceinline__ void store_key(Slot *s, u128 k) {
+        s->lo = (uint64_t)k;
+        s->hi = (uint64_t)(k >> 64);
+    }
+#endif
+};
+
+// Where a key lives: owner rank (hash sharding over GPUs), sub-table (the
+// L2-resident partition) and home slot inside it.  Three disjoint pieces of
+// one 64-bit hash, range-reduced by multiply-shift so that world and n_sub
+// need not be powers of two.
+struct Place {
+    uint32_t owner, part, slot;
+};
+__host__ __device__ __forceinline__ Place place_of(uint64_t h, uint32_t world, uint32_t n_sub,
+                                                   uint32_t sub_mask) {
+    uint32_t hi = (uint32_t)(h >> 32), lo = (uint32_t)h;
+    uint64_t t = (uint64_t)hi * world;
+    Place p;
+    p.owner = (uint32_t)(t >> 32);
+    p.part = (uint32_t)(((uint64_t)(uint32_t)t * n_sub) >> 32);
+    p.slot = lo & sub_mask;
+    return p;
+}
+
+template <class K> struct Table {
+    typename KeyTraits<K>::Slot *slots; // n_sub << sub_log2 slots + 1 special slot
+    uint32_t n_sub, sub_log2, sub_mask;
+    uint32_t world, rank;
+    uint32_t max_probe;
+    // inserts that could not be placed (sub-table full): replayed after a grow
+    K *ovf_keys;
+    uint32_t *ovf_inc;
+    unsigned long long *ovf_count;
+    uint64_t ovf_cap;
+    __host__ __device__ uint64_t capacity() const { return (uint64_t)n_sub << sub_log2; }
+};
+
+#ifdef __CUDACC__
+// weight[key] += inc.  The net effect of add_single_edge + create_or_modify_edge
+// (hm_gir.rs:91-153, hs_gir.rs:192-203); u32 wraps like the release build.
+template <class K>
+__device__ __forceinline__ void table_add(const Table<K> &t, K key, uint32_t inc) {
+    typedef KeyTraits<K> T;
+    typedef typename T::Slot Slot;
+    const K EMPTY = T::empty();
+    if (key == EMPTY) { // all-T at full key width (only without canonicalisation)
+        atomicAdd(&t.slots[t.capacity()].w, inc);
+        return;
+    }
+    Place p = place_of(T::hash(key), t.world, t.n_sub, t.sub_mask);
+    Slot *sub = t.slots + ((uint64_t)p.part << t.sub_log2);
+    uint32_t i = p.slot;
+    for (uint32_t n = 0; n < t.max_probe; ++n) {
+        Slot *s = sub + i;
+        K cur = T::load(s);
+        if (cur != key && (cur == EMPTY || T::maybe_torn(cur))) cur = T::cas(s, EMPTY, key);
+        if (cur == key || cur == EMPTY) {
+            atomicAdd(&s->w, inc);
+            return;
+        }
+        i = (i + 1) & t.sub_mask;
+    }
+    unsigned long long pos = atomicAdd(t.ovf_count, 1ull);
+    if (pos < t.ovf_cap) {
+        t.ovf_keys[pos] = key;
+        t.ovf_inc[pos] = inc;
+    }
+}
+#endif
+
+} // namespace ktg

@@ -1,0 +1,859 @@
+// kernels.cuh -- the hand-written sm_100a kernels of the build stage.
+//
+//   K1  pack_reads_kernel        ASCII -> 2-bit words + per-word window counts
+//   K2  extract (rolling k-mer / reverse complement / canonical) fused into
+//   K3  extract_insert_kernel    direct insert into the open-addressing table
+//       hist_*/scatter_* kernels partition keys by sub-table (or owner rank)
+//       insert_keys_kernel       insert an array of keys (partitioned / received)
+//   K4  table scans: stats+digest, filter, standardize, compaction (export)
+//
+// Reference code each one replaces is cited at the kernel.
+#pragma once
+#include "common.cuh"
+
+namespace ktg {
+
+// ------------------------------------------------------------------ helpers
+__device__ __forceinline__ uint64_t warp_sum(uint64_t v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+__device__ __forceinline__ uint64_t warp_max(uint64_t v) {
+    for (int o = 16; o > 0; o >>= 1) {
+        uint64_t x = __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        v = x > v ? x : v;
+    }
+    return v;
+}
+
+// block-wide sum of N counters, one atomicAdd per counter per block
+template <int N>
+__device__ __forceinline__ void block_accumulate(const uint64_t (&v)[N], unsigned long long *out) {
+    __shared__ unsigned long long sh[N];
+    if (threadIdx.x < N) sh[threadIdx.x] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        uint64_t s = warp_sum(v[i]);
+        if ((threadIdx.x & 31) == 0 && s) atomicAdd(&sh[i], (unsigned long long)s);
+    }
+    __syncthreads();
+    if (threadIdx.x < N && sh[threadIdx.x]) atomicAdd(&out[threadIdx.x], sh[threadIdx.x]);
+}
+
+// ======================================================================= K1
+// Replaces encode_fasta_symbol (compress.rs:347-378), compress_node
+// (compress.rs:55-73) and the whole-read ACGT filter + byte total of
+// create_fastq (algorithms/builder.rs:155-158), plus the length assert of
+// add_read_fastaq (collections/girs/hm_gir.rs:40).
+//
+// Layout: read r owns packed words [wo(r), wo(r+1)), wo(r) = (off[r]-off[0])/32 + r
+// (no prefix sum needed; <= 1 spare word per read).  Word j of a read holds
+// bases 32j..32j+31, first base in bits 63:62.  nstart[w] = number of k-mer
+// windows that START in word w (0 for rejected reads and spare words), which
+// is all the extraction kernels need to know about read boundaries.
+struct PackCounters {
+    unsigned long long accepted_reads, accepted_bytes, windows, short_reads;
+};
+
+// four ASCII bases (little endian: first base in the low byte) -> 8 bits, MSB first
+__device__ __forceinline__ uint32_t pack4(uint32_t x, bool &ok) {
+    uint32_t c = ((x >> 1) & 0x03030303u) ^ ((x >> 2) & 0x01010101u);
+    uint32_t sel = (c & 0xFu) | ((c >> 4) & 0xF0u) | ((c >> 8) & 0xF00u) | ((c >> 12) & 0xF000u);
+    ok = ok && (__byte_perm(0x54474341u, 0u, sel) == x); // "ACGT" looked up by code == input
+    return (c * 0x40100401u) >> 24;
+}
+
+// 16 ASCII bases -> 32 bits; bases at index >= cnt are treated as 'A' and not validated
+__device__ __forceinline__ uint32_t pack16(u128 v, int cnt, bool &ok) {
+    uint32_t out = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint32_t x = (uint32_t)(v >> (32 * q));
+        int nv = cnt - 4 * q;
+        if (nv < 4) {
+            uint32_t m = nv <= 0 ? 0u : ((1u << (8 * nv)) - 1u);
+            x = (x & m) | (0x41414141u & ~m);
+        }
+        out = (out << 8) | pack4(x, ok);
+    }
+    return out;
+}
+
+__device__ __forceinline__ u128 ld16(const uint8_t *p) {
+    uint4 v = __ldg((const uint4 *)p);
+    return ((u128)v.w << 96) | ((u128)v.z << 64) | ((u128)v.y << 32) | v.x;
+}
+
+// 32 bases starting at an arbitrary byte address -> one packed word.
+// Only 16-byte blocks that contain a byte of [p, p+cnt) are touched.
+__device__ __forceinline__ uint64_t pack32_unaligned(const uint8_t *p, int cnt, bool &ok) {
+    const uint8_t *a = (const uint8_t *)((uintptr_t)p & ~(uintptr_t)15);
+    int sh = (int)((uintptr_t)p & 15);
+    int span = sh + cnt; // bytes needed counted from a
+    u128 v0 = ld16(a);
+    u128 v1 = span > 16 ? ld16(a + 16) : (u128)0;
+    u128 v2 = span > 32 ? ld16(a + 32) : (u128)0;
+    u128 lo, hi;
+    if (sh == 0) {
+        lo = v0;
+        hi = v1;
+    }
+    else {
+        lo = (v0 >> (8 * sh)) | (v1 << (128 - 8 * sh));
+        hi = (v1 >> (8 * sh)) | (v2 << (128 - 8 * sh));
+    }
+    uint32_t a0 = pack16(lo, cnt, ok);
+    uint32_t a1 = pack16(hi, cnt - 16, ok);
+    return ((uint64_t)a0 << 32) | a1;
+}
+
+constexpr int PACK_GROUP = 8; // lanes cooperating on one read (256 bases / iteration)
+
+__global__ void __launch_bounds__(256)
+pack_reads_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restrict__ offsets,
+                  uint64_t n_reads, uint32_t k, uint64_t *__restrict__ packed,
+                  uint8_t *__restrict__ nstart, PackCounters *ctr) {
+    const int lane = threadIdx.x & 31, gl = lane & (PACK_GROUP - 1);
+    const unsigned gmask = ((1u << PACK_GROUP) - 1u) << (lane & ~(PACK_GROUP - 1));
+    const uint64_t n_groups = (uint64_t)gridDim.x * blockDim.x / PACK_GROUP;
+    const uint64_t off0 = offsets[0];
+    uint64_t acc[4] = {0, 0, 0, 0};
+    for (uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / PACK_GROUP; r < n_reads;
+         r += n_groups) {
+        const uint64_t o0 = offsets[r], o1 = offsets[r + 1];
+        const uint64_t len = o1 - o0;
+        const uint64_t wbase = (o0 - off0) / 32 + r, wend = (o1 - off0) / 32 + r + 1;
+        const uint64_t nwords = (len + 31) / 32;
+        bool ok = true;
+        for (uint64_t j = gl; j < nwords; j += PACK_GROUP) {
+            uint64_t rem = len - 32 * j;
+            packed[wbase + j] = pack32_unaligned(bases + o0 + 32 * j, rem < 32 ? (int)rem : 32, ok);
+        }
+        const bool valid = __ballot_sync(gmask, !ok) == 0;
+        const uint64_t nwin = (valid && len >= k) ? len - k + 1 : 0;
+        for (uint64_t j = gl; wbase + j < wend; j += PACK_GROUP) {
+            uint64_t s = nwin > 32 * j ? nwin - 32 * j : 0;
+            nstart[wbase + j] = (uint8_t)(s < 32 ? s : 32);
+        }
+        if (gl == 0 && valid) {
+            acc[0] += 1;
+            acc[1] += len;
+            acc[2] += nwin;
+            acc[3] += len < k;
+        }
+    }
+    block_accumulate<4>(acc, (unsigned long long *)ctr);
+}
+
+// =================================================================== K2 core
+// Rolling (k)-mer extraction over the windows that start in one packed word.
+// Replaces the per-window re-packing of compress_kmer[_with_rev_compl]
+// (compress.rs:18-48) and reverse_compressed_node (compress.rs:153-169):
+//   fw' = ((fw << 2) | b) & mask        rc' = (rc >> 2) | ((3 - b) << 2(k-1))
+// A lane owns word w and gets the k-1 overlap from its neighbours' words with
+// warp shuffles (only the last lanes of a warp load them).
+template <class K> struct Roller {
+    K fw, rc, mask;
+    u128 nxt; // bases k, k+1, ... of the 96-base span, left aligned
+    uint32_t k, rc_shift;
+
+    __device__ __forceinline__ void init(uint64_t w0, uint64_t w1, uint64_t w2, uint32_t k_) {
+        k = k_;
+        rc_shift = 2 * (k - 1);
+        if (sizeof(K) == 8) {
+            mask = k == 32 ? (K)~0ull : (K)((1ull << (2 * k)) - 1);
+            fw = (K)(w0 >> (64 - 2 * k));
+            nxt = (((u128)w0 << 64) | w1) << (2 * k);
+        }
+        else {
+            mask = k == 64 ? ~(K)0 : (K)((((u128)1) << (2 * k)) - 1);
+            fw = (K)((((u128)w0 << 64) | w1) >> (128 - 2 * k));
+            nxt = (((u128)w1 << 64) | w2) << (2 * (k - 32));
+        }
+        rc = revcomp(fw, k);
+    }
+    __device__ __forceinline__ void step() {
+        uint32_t b = (uint32_t)(nxt >> 126);
+        nxt <<= 2;
+        fw = ((fw << 2) | (K)b) & mask;
+        rc = (rc >> 2) | ((K)(3u - b) << rc_shift);
+    }
+};
+
+// words w+1 / w+2 for every lane of the warp
+__device__ __forceinline__ void neighbour_words(const uint64_t *__restrict__ packed, uint64_t w,
+                                                uint64_t n_words, uint64_t w0, bool need2,
+                                                uint64_t &w1, uint64_t &w2) {
+    const int lane = threadIdx.x & 31;
+    w1 = __shfl_down_sync(0xFFFFFFFFu, w0, 1);
+    w2 = __shfl_down_sync(0xFFFFFFFFu, w0, 2);
+    if (lane == 31) w1 = (w + 1 < n_words) ? packed[w + 1] : 0;
+    if (need2 && lane >= 30) w2 = (w + 2 < n_words) ? packed[w + 2] : 0;
+}
+
+// ======================================================================= K3
+// Fused extract + insert (the single-GPU path when the table is L2 sized):
+// the loop of add_read_fastaq (hm_gir.rs:55-85) with both-strand insertion
+// folded into one canonical update: key = min(fw, rc), +2 if fw == rc
+// (a palindrome is inserted twice by hm_gir.rs:55-74).
+template <class K, bool RC>
+__global__ void __launch_bounds__(256)
+extract_insert_kernel(const uint64_t *__restrict__ packed, const uint8_t *__restrict__ nstart,
+                      uint64_t n_words, uint32_t k, Table<K> t) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n_round = (n_words + 31) & ~(uint64_t)31;
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_round; w += stride) {
+        const bool in = w < n_words;
+        uint64_t w0 = in ? packed[w] : 0, w1, w2;
+        const uint32_t ns = in ? nstart[w] : 0;
+        neighbour_words(packed, w, n_words, w0, sizeof(K) == 16, w1, w2);
+        if (ns == 0) continue;
+        Roller<K> r;
+        r.init(w0, w1, w2, k);
+        for (uint32_t j = 0; j < ns; ++j) {
+            K key = r.fw;
+            uint32_t inc = 1;
+            if (RC) {
+                if (r.rc < key) key = r.rc;
+                if (r.rc == r.fw) inc = 2;
+            }
+            table_add(t, key, inc);
+            r.step();
+        }
+    }
+}
+
+// ============================================================ cardinality
+// HyperLogLog sketch (2^12 registers) of the keys of a batch, merged into a
+// persistent sketch with atomicMax.  The host sizes / grows the table from the
+// estimate, so no capacity hint is needed (create_fastq starts from
+// T::default(), builder.rs:145) and no pessimistic "every window is new" bound
+// is used.  Register index and rank come from a re-mixed hash so they are
+// independent of the bits that place the key in the table.
+constexpr uint32_t HLL_P = 12, HLL_M = 1u << HLL_P;
+
+__device__ __forceinline__ void hll_update(uint32_t *regs, uint64_t h) {
+    uint64_t g = fmix64(h ^ 0x9E3779B97F4A7C15ull);
+    uint32_t idx = (uint32_t)(g >> (64 - HLL_P));
+    uint64_t rest = g << HLL_P;
+    uint32_t rank = rest ? (uint32_t)__clzll((long long)rest) + 1u : 64u - HLL_P + 1u;
+    if (regs[idx] < rank) atomicMax(&regs[idx], rank);
+}
+
+template <class K, bool RC>
+__global__ void __launch_bounds__(256)
+hll_reads_kernel(const uint64_t *__restrict__ packed, const uint8_t *__restrict__ nstart,
+                 uint64_t n_words, uint32_t k, uint32_t *__restrict__ g_regs) {
+    __shared__ uint32_t regs[HLL_M];
+    for (uint32_t i = threadIdx.x; i < HLL_M; i += blockDim.x) regs[i] = 0;
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n_round = (n_words + 31) & ~(uint64_t)31;
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_round; w += stride) {
+        const bool in = w < n_words;
+        uint64_t w0 = in ? packed[w] : 0, w1, w2;
+        const uint32_t ns = in ? nstart[w] : 0;
+        neighbour_words(packed, w, n_words, w0, sizeof(K) == 16, w1, w2);
+        if (ns == 0) continue;
+        Roller<K> r;
+        r.init(w0, w1, w2, k);
+        for (uint32_t j = 0; j < ns; ++j) {
+            K key = (RC && r.rc < r.fw) ? r.rc : r.fw;
+            hll_update(regs, KeyTraits<K>::hash(key));
+            r.step();
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < HLL_M; i += blockDim.x)
+        if (regs[i]) atomicMax(&g_regs[i], regs[i]);
+}
+
+template <class K>
+__global__ void __launch_bounds__(256)
+hll_keys_kernel(const K *__restrict__ keys, uint64_t n, uint32_t *__restrict__ g_regs) {
+    __shared__ uint32_t regs[HLL_M];
+    for (uint32_t i = threadIdx.x; i < HLL_M; i += blockDim.x) regs[i] = 0;
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        hll_update(regs, KeyTraits<K>::hash(keys[i]));
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < HLL_M; i += blockDim.x)
+        if (regs[i]) atomicMax(&g_regs[i], regs[i]);
+}
+
+// ================================================================ partition
+// bin of a key: its owner rank (multi-GPU exchange) or its sub-table
+template <class K, bool BY_OWNER>
+__device__ __forceinline__ uint32_t bin_of(const Table<K> &t, K key) {
+    Place p = place_of(KeyTraits<K>::hash(key), t.world, t.n_sub, t.sub_mask);
+    return BY_OWNER ? p.owner : p.part;
+}
+
+// histogram of bins over all windows of a packed batch
+template <class K, bool RC, bool BY_OWNER>
+__global__ void __launch_bounds__(256)
+hist_reads_kernel(const uint64_t *__restrict__ packed, const uint8_t *__restrict__ nstart,
+                  uint64_t n_words, uint32_t k, Table<K> t, uint32_t n_bins,
+                  unsigned long long *__restrict__ g_hist) {
+    extern __shared__ uint32_t sh_hist[];
+    for (uint32_t i = threadIdx.x; i < n_bins; i += blockDim.x) sh_hist[i] = 0;
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n_round = (n_words + 31) & ~(uint64_t)31;
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_round; w += stride) {
+        const bool in = w < n_words;
+        uint64_t w0 = in ? packed[w] : 0, w1, w2;
+        const uint32_t ns = in ? nstart[w] : 0;
+        neighbour_words(packed, w, n_words, w0, sizeof(K) == 16, w1, w2);
+        if (ns == 0) continue;
+        Roller<K> r;
+        r.init(w0, w1, w2, k);
+        for (uint32_t j = 0; j < ns; ++j) {
+            K key = (RC && r.rc < r.fw) ? r.rc : r.fw;
+            atomicAdd(&sh_hist[bin_of<K, BY_OWNER>(t, key)], 1u);
+            r.step();
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n_bins; i += blockDim.x)
+        if (sh_hist[i]) atomicAdd(&g_hist[i], (unsigned long long)sh_hist[i]);
+}
+
+template <class K, bool BY_OWNER>
+__global__ void __launch_bounds__(256)
+hist_keys_kernel(const K *__restrict__ keys, uint64_t n, Table<K> t, uint32_t n_bins,
+                 unsigned long long *__restrict__ g_hist) {
+    extern __shared__ uint32_t sh_hist[];
+    for (uint32_t i = threadIdx.x; i < n_bins; i += blockDim.x) sh_hist[i] = 0;
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        atomicAdd(&sh_hist[bin_of<K, BY_OWNER>(t, keys[i])], 1u);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n_bins; i += blockDim.x)
+        if (sh_hist[i]) atomicAdd(&g_hist[i], (unsigned long long)sh_hist[i]);
+}
+
+// exclusive scan of the bin histogram (n_bins <= a few thousand): one block
+__global__ void scan_bins_kernel(const unsigned long long *__restrict__ hist, uint32_t n_bins,
+                                 unsigned long long *__restrict__ offsets,
+                                 unsigned long long *__restrict__ cursors) {
+    __shared__ unsigned long long part[1024];
+    const uint32_t per = (n_bins + blockDim.x - 1) / blockDim.x;
+    const uint32_t b0 = threadIdx.x * per;
+    unsigned long long s = 0;
+    for (uint32_t i = b0; i < b0 + per && i < n_bins; ++i) s += hist[i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (uint32_t i = 0; i < blockDim.x; ++i) {
+            unsigned long long v = part[i];
+            part[i] = run;
+            run += v;
+        }
+    }
+    __syncthreads();
+    unsigned long long run = part[threadIdx.x];
+    for (uint32_t i = b0; i < b0 + per && i < n_bins; ++i) {
+        offsets[i] = run;
+        cursors[i] = run;
+        run += hist[i];
+    }
+    if (threadIdx.x == blockDim.x - 1) offsets[n_bins] = run;
+}
+
+// Block-wide exclusive scan of the per-bin counts of one tile.  On return
+// s_loc[b] = tile-local start of bin b, s_cnt[b] = the same (it becomes the
+// local write cursor) and s_glob[b] = the range reserved in HBM for (tile, b)
+// with ONE atomicAdd.  Returns the number of keys in the tile.
+template <int NT>
+__device__ __forceinline__ uint32_t bin_scan_reserve(uint32_t *s_cnt, uint32_t *s_loc,
+                                                     unsigned long long *s_glob,
+                                                     unsigned long long *__restrict__ cursors,
+                                                     uint32_t n_bins) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_total;
+    const uint32_t per = (n_bins + NT - 1) / NT;
+    const uint32_t b0 = threadIdx.x * per;
+    uint32_t s = 0;
+    for (uint32_t i = b0; i < b0 + per && i < n_bins; ++i) s += s_cnt[i];
+    uint32_t incl = s;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t x = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if ((threadIdx.x & 31) >= o) incl += x;
+    }
+    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t v = threadIdx.x < NT / 32 ? s_warp[threadIdx.x] : 0, iv = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t x = __shfl_up_sync(0xFFFFFFFFu, iv, o);
+            if (threadIdx.x >= o) iv += x;
+        }
+        s_warp[threadIdx.x] = iv - v;
+        if (threadIdx.x == 31) s_total = iv;
+    }
+    __syncthreads();
+    uint32_t run = s_warp[threadIdx.x >> 5] + incl - s;
+    for (uint32_t i = b0; i < b0 + per && i < n_bins; ++i) {
+        uint32_t c = s_cnt[i];
+        s_loc[i] = run;
+        s_cnt[i] = run;
+        if (c) s_glob[i] = atomicAdd(&cursors[i], (unsigned long long)c);
+        run += c;
+    }
+    __syncthreads();
+    return s_total;
+}
+
+// Tile-local counting sort in shared memory, then coalesced runs to HBM.
+// One CTA takes TILE_WORDS packed words (<= 32*TILE_WORDS keys), bins them in
+// shared memory and reserves one contiguous range per (tile, bin) with a
+// single atomicAdd, so HBM sees runs instead of scattered 8-byte stores.
+template <class K> struct ScatterCfg {
+    static constexpr int TILE_WORDS = sizeof(K) == 8 ? 256 : 128;
+    static constexpr int TILE_KEYS = TILE_WORDS * 32;
+};
+
+template <class K, bool RC, bool BY_OWNER>
+__global__ void __launch_bounds__(ScatterCfg<K>::TILE_WORDS)
+scatter_reads_kernel(const uint64_t *__restrict__ packed, const uint8_t *__restrict__ nstart,
+                     uint64_t n_words, uint32_t k, Table<K> t, uint32_t n_bins,
+                     unsigned long long *__restrict__ cursors, K *__restrict__ out) {
+    constexpr int TW = ScatterCfg<K>::TILE_WORDS, TK = ScatterCfg<K>::TILE_KEYS;
+    extern __shared__ __align__(16) unsigned char smem[];
+    K *s_keys = (K *)smem;                                   // TK keys
+    uint16_t *s_bin = (uint16_t *)(s_keys + TK);             // TK bins
+    uint32_t *s_cnt = (uint32_t *)(s_bin + TK);              // n_bins: count -> local cursor
+    uint32_t *s_loc = s_cnt + n_bins;                        // n_bins: local start
+    unsigned long long *s_glob = (unsigned long long *)(s_loc + n_bins + (n_bins & 1)); // n_bins
+    const uint64_t n_tiles = (n_words + TW - 1) / TW;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (uint32_t i = threadIdx.x; i < n_bins; i += TW) s_cnt[i] = 0;
+        __syncthreads();
+        const uint64_t w = tile * TW + threadIdx.x;
+        const bool in = w < n_words;
+        uint64_t w0 = in ? packed[w] : 0, w1, w2;
+        const uint32_t ns = in ? nstart[w] : 0;
+        neighbour_words(packed, w, n_words, w0, sizeof(K) == 16, w1, w2);
+        Roller<K> r;
+        // pass A: bin counts
+        if (ns) {
+            r.init(w0, w1, w2, k);
+            for (uint32_t j = 0; j < ns; ++j) {
+                K key = (RC && r.rc < r.fw) ? r.rc : r.fw;
+                atomicAdd(&s_cnt[bin_of<K, BY_OWNER>(t, key)], 1u);
+                r.step();
+            }
+        }
+        __syncthreads();
+        const uint32_t total = bin_scan_reserve<TW>(s_cnt, s_loc, s_glob, cursors, n_bins);
+        // pass B: recompute keys, place them bin-sorted in shared memory
+        if (ns) {
+            r.init(w0, w1, w2, k);
+            for (uint32_t j = 0; j < ns; ++j) {
+                K key = (RC && r.rc < r.fw) ? r.rc : r.fw;
+                uint32_t b = bin_of<K, BY_OWNER>(t, key);
+                uint32_t pos = atomicAdd(&s_cnt[b], 1u);
+                s_keys[pos] = key;
+                s_bin[pos] = (uint16_t)b;
+                r.step();
+            }
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < total; i += TW) {
+            uint32_t b = s_bin[i];
+            out[s_glob[b] + (i - s_loc[b])] = s_keys[i];
+        }
+        __syncthreads();
+    }
+}
+
+// same for an array of keys (receiver side of the multi-GPU exchange)
+template <class K, bool BY_OWNER>
+__global__ void __launch_bounds__(256)
+scatter_keys_kernel(const K *__restrict__ keys, uint64_t n, Table<K> t, uint32_t n_bins,
+                    unsigned long long *__restrict__ cursors, K *__restrict__ out) {
+    constexpr int TK = 4096, NT = 256;
+    extern __shared__ __align__(16) unsigned char smem[];
+    K *s_keys = (K *)smem;
+    uint16_t *s_bin = (uint16_t *)(s_keys + TK);
+    uint32_t *s_cnt = (uint32_t *)(s_bin + TK);
+    uint32_t *s_loc = s_cnt + n_bins;
+    unsigned long long *s_glob = (unsigned long long *)(s_loc + n_bins + (n_bins & 1));
+    const uint64_t n_tiles = (n + TK - 1) / TK;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (uint32_t i = threadIdx.x; i < n_bins; i += NT) s_cnt[i] = 0;
+        __syncthreads();
+        const uint64_t base = tile * TK;
+        const uint32_t cnt = (uint32_t)((n - base) < TK ? (n - base) : TK);
+        K my[TK / NT];
+        uint32_t mb[TK / NT];
+#pragma unroll
+        for (int q = 0; q < TK / NT; ++q) {
+            uint32_t i = q * NT + threadIdx.x;
+            if (i < cnt) {
+                my[q] = keys[base + i];
+                mb[q] = bin_of<K, BY_OWNER>(t, my[q]);
+                atomicAdd(&s_cnt[mb[q]], 1u);
+            }
+        }
+        __syncthreads();
+        bin_scan_reserve<NT>(s_cnt, s_loc, s_glob, cursors, n_bins);
+#pragma unroll
+        for (int q = 0; q < TK / NT; ++q) {
+            uint32_t i = q * NT + threadIdx.x;
+            if (i < cnt) {
+                uint32_t pos = atomicAdd(&s_cnt[mb[q]], 1u);
+                s_keys[pos] = my[q];
+                s_bin[pos] = (uint16_t)mb[q];
+            }
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < cnt; i += NT) {
+            uint32_t b = s_bin[i];
+            out[s_glob[b] + (i - s_loc[b])] = s_keys[i];
+        }
+        __syncthreads();
+    }
+}
+
+// K3 over an array of canonical keys (partitioned locally or received from
+// peers).  Keys arrive grouped by sub-table, so concurrently running CTAs work
+// on one L2-resident slice of the table.
+template <class K>
+__global__ void __launch_bounds__(256)
+insert_keys_kernel(const K *__restrict__ keys, uint64_t n, uint32_t k, bool check_palindrome,
+                   Table<K> t) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        K key = keys[i];
+        uint32_t inc = (check_palindrome && revcomp(key, k) == key) ? 2u : 1u;
+        table_add(t, key, inc);
+    }
+}
+
+// replay of inserts that overflowed a full sub-table, after the table grew
+template <class K>
+__global__ void replay_overflow_kernel(const K *__restrict__ keys, const uint32_t *__restrict__ inc,
+                                       uint64_t n, Table<K> t) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        table_add(t, keys[i], inc[i]);
+}
+
+// ================================================================ table scans
+template <class K>
+__global__ void init_table_kernel(typename KeyTraits<K>::Slot *slots, uint64_t n) {
+    typedef typename KeyTraits<K>::Slot Slot;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    // every 16 bytes of an empty slot: key halves all-ones, weight/aux zero
+    if (sizeof(Slot) == 16) {
+        uint4 e = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+            ((uint4 *)slots)[i] = e;
+    }
+    else {
+        uint4 e0 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+        uint4 e1 = make_uint4(0u, 0u, 0u, 0u);
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n; i += stride)
+            ((uint4 *)slots)[i] = (i & 1) ? e1 : e0;
+    }
+}
+
+template <class K>
+__global__ void count_occupied_kernel(const typename KeyTraits<K>::Slot *slots, uint64_t n,
+                                      unsigned long long *out) {
+    typedef KeyTraits<K> T;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t acc[1] = {0};
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        acc[0] += T::load(&slots[i]) != T::empty();
+    block_accumulate<1>(acc, out);
+}
+
+template <class K>
+__global__ void rehash_kernel(const typename KeyTraits<K>::Slot *old_slots, uint64_t n_old,
+                              Table<K> t) {
+    typedef KeyTraits<K> T;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    // slot n_old is the special all-ones-key slot
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n_old; i += stride) {
+        uint32_t w = old_slots[i].w;
+        if (w == 0) continue; // empty, or an edge removed by the filter
+        K key = i == n_old ? T::empty() : T::load(&old_slots[i]);
+        table_add(t, key, w);
+    }
+}
+
+// Stats over the both-strand expanded edge set: a canonical entry c with
+// weight w stands for edges c and revcomp(c) (one edge if c is a palindrome);
+// see SURVEY Appendix A.5-7.
+struct EdgeStats {
+    unsigned long long edges, sum_w, sum_w_below, max_w, digest;
+};
+
+__device__ __forceinline__ uint64_t digest_term(uint64_t hi, uint64_t lo, uint32_t w) {
+    return splitmix64(splitmix64(hi) ^ lo) * (2ull * w + 1ull);
+}
+
+template <class K, bool RC>
+__global__ void __launch_bounds__(256)
+edge_stats_kernel(const typename KeyTraits<K>::Slot *slots, uint64_t n_slots, uint32_t k,
+                  uint32_t threshold, EdgeStats *out) {
+    typedef KeyTraits<K> T;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t acc[4] = {0, 0, 0, 0}; // edges, sum_w, sum_w_below, digest
+    uint64_t mx = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += stride) {
+        uint32_t w = slots[i].w;
+        if (w == 0) continue;
+        K key = T::load(&slots[i]);
+        uint64_t mult = 1;
+        uint64_t d = digest_term(T::hi(key), T::lo(key), w);
+        if (RC) {
+            K r = revcomp(key, k);
+            if (r != key) {
+                mult = 2;
+                d += digest_term(T::hi(r), T::lo(r), w);
+            }
+        }
+        acc[0] += mult;
+        acc[1] += mult * w;
+        if (w < threshold) acc[2] += mult * w;
+        acc[3] += d;
+        if (w > mx) mx = w;
+    }
+    uint64_t a4[4] = {acc[0], acc[1], acc[2], acc[3]};
+    // EdgeStats layout: edges, sum_w, sum_w_below, max_w, digest
+    __shared__ unsigned long long sh[5];
+    if (threadIdx.x < 5) sh[threadIdx.x] = 0;
+    __syncthreads();
+    for (int i = 0; i < 4; ++i) {
+        uint64_t s = warp_sum(a4[i]);
+        if ((threadIdx.x & 31) == 0 && s) atomicAdd(&sh[i < 3 ? i : 4], (unsigned long long)s);
+    }
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) atomicMax(&sh[3], (unsigned long long)mx);
+    __syncthreads();
+    if (threadIdx.x < 5 && sh[threadIdx.x]) {
+        if (threadIdx.x == 3) atomicMax(&out->max_w, sh[3]);
+        else atomicAdd(((unsigned long long *)out) + threadIdx.x, sh[threadIdx.x]);
+    }
+}
+
+// ======================================================================= K4
+// Clean::remove_weak_edges (pruner.rs:109-118, edges.rs:51-58): keep w >= t.
+// In place: a removed edge keeps its slot (probe chains stay intact) with
+// weight 0 == "not in E".
+template <class K>
+__global__ void filter_kernel(typename KeyTraits<K>::Slot *slots, uint64_t n_slots,
+                              uint32_t threshold) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += stride) {
+        uint32_t w = slots[i].w;
+        if (w != 0 && w < threshold) slots[i].w = 0;
+    }
+}
+
+// standardize_edges (standardizer.rs:56-69): w' = round_half_away(w * p) as
+// u32 (saturating), w' = 1 if it rounded to 0 but w >= t; w' == 0 removes the
+// edge (remove_weak_edges(1)).  p is computed on the host from the device sums.
+__device__ __forceinline__ uint32_t scale_weight(uint32_t w, double p, uint32_t threshold) {
+    double r = round((double)w * p); // round(): half away from zero, like f64::round
+    uint32_t nw;
+    if (!(r >= 0.0)) nw = 0;
+    else if (r >= 4294967295.0) nw = 0xFFFFFFFFu;
+    else nw = (uint32_t)r;
+    if (nw == 0 && w >= threshold) nw = 1;
+    return nw;
+}
+
+template <class K>
+__global__ void standardize_kernel(typename KeyTraits<K>::Slot *slots, uint64_t n_slots, double p,
+                                   uint32_t threshold) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += stride) {
+        uint32_t w = slots[i].w;
+        if (w != 0) slots[i].w = scale_weight(w, p, threshold);
+    }
+}
+
+// Stream compaction of the surviving edges (w >= threshold, threshold >= 1)
+// into dense arrays, expanding both strands.  Block-aggregated: one atomicAdd
+// on the output cursor per CTA iteration.  This is the export that
+// Convert::create_from (hm_gir.rs:156-226) consumes and, with threshold > 1,
+// the fused "filter + compact" of north_star kernel (4).
+template <class K, bool RC>
+__global__ void __launch_bounds__(256)
+compact_edges_kernel(const typename KeyTraits<K>::Slot *slots, uint64_t n_slots, uint32_t k,
+                     uint32_t threshold, uint64_t *__restrict__ out_hi,
+                     uint64_t *__restrict__ out_lo, uint32_t *__restrict__ out_w, uint64_t cap,
+                     unsigned long long *cursor) {
+    typedef KeyTraits<K> T;
+    __shared__ uint32_t s_warp[8];
+    __shared__ unsigned long long s_base;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n_round = (n_slots + blockDim.x - 1) / blockDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        uint32_t w = i < n_slots ? slots[i].w : 0;
+        uint32_t cnt = 0;
+        K key = 0, r = 0;
+        if (w != 0 && w >= threshold) {
+            key = T::load(&slots[i]);
+            cnt = 1;
+            if (RC) {
+                r = revcomp(key, k);
+                if (r != key) cnt = 2;
+            }
+        }
+        // exclusive scan of cnt over the block
+        uint32_t incl = cnt;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t x = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += x;
+        }
+        if (lane == 31) s_warp[wid] = incl;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t run = 0;
+            for (int q = 0; q < 8; ++q) {
+                uint32_t v = s_warp[q];
+                s_warp[q] = run;
+                run += v;
+            }
+            s_base = run ? atomicAdd(cursor, (unsigned long long)run) : 0ull;
+        }
+        __syncthreads();
+        uint64_t pos = s_base + s_warp[wid] + incl - cnt;
+        if (cnt >= 1 && pos < cap) {
+            if (out_hi) out_hi[pos] = T::hi(key);
+            out_lo[pos] = T::lo(key);
+            out_w[pos] = w;
+        }
+        if (cnt == 2 && pos + 1 < cap) {
+            if (out_hi) out_hi[pos + 1] = T::hi(r);
+            out_lo[pos + 1] = T::lo(r);
+            out_w[pos + 1] = w;
+        }
+        __syncthreads();
+    }
+}
+
+// ============================================================ node (k-1)-mers
+// Node set N = {prefix, suffix of every edge} (hm_gir.rs:99-149; sinks are keys
+// with empty Outgoing) and the degree data behind CollectionStats
+// (stats/collections.rs:137-168).  One entry per canonical (k-1)-mer; its u32
+// holds four 8-bit degree counters: out/in of the canonical orientation and
+// out/in of the reverse-complement orientation (each <= 4).
+template <class KE, class KN, bool RC>
+__global__ void __launch_bounds__(256)
+build_nodes_kernel(const typename KeyTraits<KE>::Slot *slots, uint64_t n_slots, uint32_t k,
+                   Table<KN> nt) {
+    typedef KeyTraits<KE> TE;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint32_t k1 = k - 1;
+    const KE nmask = (k1 == 8 * sizeof(KE) / 2) ? ~(KE)0 : (KE)((((KE)1) << (2 * k1)) - 1);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += stride) {
+        if (slots[i].w == 0) continue;
+        KE e = TE::load(&slots[i]);
+        KE er = RC ? revcomp(e, k) : e;
+        const int n_exp = (RC && er != e) ? 2 : 1;
+        for (int x = 0; x < n_exp; ++x) {
+            KE edge = x ? er : e;
+            KN pre = (KN)(edge >> 2), suf = (KN)(edge & nmask);
+#pragma unroll
+            for (int side = 0; side < 2; ++side) { // 0: prefix gains an out-edge, 1: suffix an in-edge
+                KN n = side ? suf : pre;
+                uint32_t field = side;
+                if (RC) {
+                    KN nr = revcomp(n, k1);
+                    if (nr < n) {
+                        n = nr;
+                        field += 2;
+                    }
+                }
+                table_add(nt, n, 1u << (8 * field));
+            }
+        }
+    }
+}
+
+struct NodeStats {
+    unsigned long long nodes, sources, sinks, max_in, max_out;
+};
+
+template <class KN, bool RC>
+__global__ void __launch_bounds__(256)
+node_stats_kernel(const typename KeyTraits<KN>::Slot *slots, uint64_t n_slots, NodeStats *out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t acc[3] = {0, 0, 0};
+    uint64_t mi = 0, mo = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += stride) {
+        uint32_t w = slots[i].w;
+        if (w == 0) continue;
+#pragma unroll
+        for (int o = 0; o < (RC ? 2 : 1); ++o) {
+            uint32_t od = (w >> (16 * o)) & 0xFF, id = (w >> (16 * o + 8)) & 0xFF;
+            if (od + id == 0) continue;
+            acc[0] += 1;
+            acc[1] += id == 0;
+            acc[2] += od == 0;
+            if (id > mi) mi = id;
+            if (od > mo) mo = od;
+        }
+    }
+    block_accumulate<3>(acc, (unsigned long long *)out);
+    mi = warp_max(mi);
+    mo = warp_max(mo);
+    if ((threadIdx.x & 31) == 0) {
+        if (mi) atomicMax(&out->max_in, (unsigned long long)mi);
+        if (mo) atomicMax(&out->max_out, (unsigned long long)mo);
+    }
+}
+
+// ===================================================================== synth
+// Device twin of oracle ko_synth_reads (counter based).
+__global__ void synth_reads_kernel(uint8_t *__restrict__ out, uint64_t seed_g, uint64_t G,
+                                   uint32_t L, uint64_t thr, uint64_t r0, uint64_t n_reads) {
+    const uint64_t seed_r = seed_g ^ 0x5245414453ull, seed_e = seed_g ^ 0x4552524f52ull;
+    const uint32_t chunks = (L + 3) / 4;
+    const uint64_t total = n_reads * chunks, stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const uint64_t r = r0 + i / chunks;
+        const uint32_t j0 = (uint32_t)(i % chunks) * 4;
+        const uint64_t start = splitmix64(seed_r + 2 * r) % (G - L + 1);
+        const bool strand = splitmix64(seed_r + 2 * r + 1) & 1;
+        uint8_t *dst = out + (r - r0) * L;
+        for (uint32_t j = j0; j < j0 + 4 && j < L; ++j) {
+            uint32_t code = strand ? 3u - (uint32_t)(splitmix64(seed_g + start + (L - 1 - j)) & 3)
+                                   : (uint32_t)(splitmix64(seed_g + start + j) & 3);
+            uint64_t h = splitmix64(seed_e + r * L + j);
+            if (h < thr) code = (code + 1 + (uint32_t)(splitmix64(h) % 3)) & 3;
+            dst[j] = (uint8_t)((0x54474341u >> (8 * code)) & 0xFF);
+        }
+    }
+}
+
+// uniformly random "load key + atomicAdd weight" over a table of n_slots
+// (the random-access roofline the insert kernel is compared against)
+template <int SLOT_BYTES>
+__global__ void random_access_probe_kernel(unsigned char *table, uint64_t n_slots,
+                                           uint64_t n_updates, unsigned long long *sink) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long acc = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_updates; i += stride) {
+        uint64_t h = splitmix64(i);
+        uint64_t s = (uint64_t)(((u128)h * n_slots) >> 64);
+        unsigned char *p = table + s * SLOT_BYTES;
+        acc += __ldcg((const unsigned long long *)p);
+        atomicAdd((unsigned int *)(p + (SLOT_BYTES == 16 ? 8 : 16)), 1u);
+    }
+    if (acc == 0x1234567ull) *sink = acc;
+}
+
+} // namespace ktg

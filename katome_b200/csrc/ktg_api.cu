@@ -1,0 +1,362 @@
+// ktg_api.cu -- the extern "C" boundary declared in include/katome_gpu.h.
+#include <fstream>
+#include <memory>
+
+#include "builder.cuh"
+#include "host_reader.h"
+
+using namespace ktg;
+
+struct ktg_builder {
+    std::unique_ptr<BuilderBase> impl;
+    // double-buffered device staging for host batches
+    DeviceBuf st_bases[2], st_offs[2];
+    cudaEvent_t st_free[2] = {nullptr, nullptr}; // staging buffer consumed by the compute stream
+    cudaEvent_t st_ready[2] = {nullptr, nullptr};
+    int st_next = 0;
+};
+
+extern "C" {
+
+const char *ktg_last_error(void) { return last_error_ref().c_str(); }
+
+int ktg_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int ktg_create(const ktg_config *cfg, ktg_builder **out) {
+    if (!cfg || !out) return fail(KTG_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->abi_version != KTG_ABI_VERSION)
+        return fail(KTG_ERR_INVALID, "ABI version %u, library is %u", cfg->abi_version, KTG_ABI_VERSION);
+    // prelude.rs:35 asserts k > 1, compress.rs:19 needs len > 2; 64 is our key width
+    if (cfg->k < 3 || cfg->k > 64) return fail(KTG_ERR_BAD_K, "k_mer_size %u outside 3..=64", cfg->k);
+    if (cfg->world_size > 1 && cfg->rank >= cfg->world_size) return fail(KTG_ERR_INVALID, "rank >= world_size");
+    if (cfg->sub_table_log2_bytes && (cfg->sub_table_log2_bytes < 16 || cfg->sub_table_log2_bytes > 34))
+        return fail(KTG_ERR_INVALID, "sub_table_log2_bytes out of range");
+    if (ktg_device_count() < 1) return fail(KTG_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
+    int dev = cfg->device;
+    if (dev < 0) KTG_CUDA(cudaGetDevice(&dev));
+    std::unique_ptr<BuilderBase> impl;
+    if (cfg->k <= 32) impl.reset(new Builder<uint64_t>());
+    else impl.reset(new Builder<u128>());
+    impl->cfg = *cfg;
+    impl->k = cfg->k;
+    impl->rc = cfg->reverse_complement != 0;
+    impl->device = dev;
+    impl->stream = (cudaStream_t)cfg->stream;
+    impl->prof.enabled = (cfg->flags & KTG_FLAG_PROFILE) != 0;
+    KTG_TRY(impl->init());
+    ktg_builder *b = new ktg_builder();
+    b->impl = std::move(impl);
+    *out = b;
+    return KTG_OK;
+}
+
+void ktg_destroy(ktg_builder *b) {
+    if (!b) return;
+    cudaSetDevice(b->impl->device);
+    cudaStreamSynchronize(b->impl->stream);
+    cudaStreamSynchronize(b->impl->copy_stream);
+    for (int i = 0; i < 2; ++i) {
+        b->st_bases[i].release();
+        b->st_offs[i].release();
+        if (b->st_free[i]) cudaEventDestroy(b->st_free[i]);
+        if (b->st_ready[i]) cudaEventDestroy(b->st_ready[i]);
+    }
+    delete b;
+}
+
+#define KTG_ENTER(b)                                                                           \
+    if (!(b)) return fail(KTG_ERR_INVALID, "null builder");                                    \
+    KTG_CUDA(cudaSetDevice((b)->impl->device));
+
+int ktg_add_reads_device(ktg_builder *b, const void *d_bases, const void *d_offsets,
+                         uint64_t n_reads, uint64_t total_bases, uint64_t *accepted_reads,
+                         uint64_t *accepted_bytes) {
+    KTG_ENTER(b);
+    uint64_t r0 = 0, b0 = 0;
+    if (accepted_reads || accepted_bytes) KTG_TRY(b->impl->read_counters(&r0, &b0));
+    KTG_TRY(b->impl->ingest_device((const uint8_t *)d_bases, (const uint64_t *)d_offsets, n_reads, total_bases));
+    if (accepted_reads || accepted_bytes) {
+        uint64_t r1 = 0, b1 = 0;
+        KTG_TRY(b->impl->read_counters(&r1, &b1));
+        if (accepted_reads) *accepted_reads += r1 - r0;
+        if (accepted_bytes) *accepted_bytes += b1 - b0;
+    }
+    return KTG_OK;
+}
+
+// Host batch: chunked H2D on the copy stream, double buffered against the
+// kernels on the compute stream.
+int ktg_add_reads(ktg_builder *b, const uint8_t *bases, const uint64_t *offsets, uint64_t n_reads,
+                  uint64_t *accepted_reads, uint64_t *accepted_bytes) {
+    KTG_ENTER(b);
+    if (n_reads == 0) return KTG_OK;
+    if (!bases || !offsets) return fail(KTG_ERR_INVALID, "null argument");
+    BuilderBase *impl = b->impl.get();
+    uint64_t r0c = 0, b0c = 0;
+    if (accepted_reads || accepted_bytes) KTG_TRY(impl->read_counters(&r0c, &b0c));
+    const uint64_t CHUNK = 256ull << 20; // bytes of bases per chunk
+    for (int i = 0; i < 2; ++i) {
+        if (!b->st_free[i]) {
+            KTG_CUDA(cudaEventCreateWithFlags(&b->st_free[i], cudaEventDisableTiming));
+            KTG_CUDA(cudaEventCreateWithFlags(&b->st_ready[i], cudaEventDisableTiming));
+        }
+    }
+    uint64_t r = 0;
+    while (r < n_reads) {
+        // largest r1 with offsets[r1] - offsets[r] <= CHUNK (at least one read)
+        uint64_t lo = r + 1, hi = n_reads;
+        while (lo < hi) {
+            uint64_t mid = (lo + hi + 1) / 2;
+            if (offsets[mid] - offsets[r] <= CHUNK) lo = mid;
+            else hi = mid - 1;
+        }
+        const uint64_t r1 = lo, nb = offsets[r1] - offsets[r], nr = r1 - r;
+        const int s = b->st_next;
+        b->st_next ^= 1;
+        // the staging buffer may still be read by kernels of two chunks ago
+        KTG_CUDA(cudaStreamWaitEvent(impl->copy_stream, b->st_free[s], 0));
+        if (b->st_bases[s].cap < nb + 64 || b->st_offs[s].cap < (nr + 1) * 8) {
+            KTG_CUDA(cudaStreamSynchronize(impl->stream)); // reallocation frees the old buffer
+            KTG_TRY(b->st_bases[s].ensure(nb + 64));
+            KTG_TRY(b->st_offs[s].ensure((nr + 1) * 8));
+        }
+        KTG_CUDA(cudaMemcpyAsync(b->st_bases[s].p, bases + offsets[r], nb, cudaMemcpyHostToDevice, impl->copy_stream));
+        KTG_CUDA(cudaMemcpyAsync(b->st_offs[s].p, offsets + r, (nr + 1) * 8, cudaMemcpyHostToDevice, impl->copy_stream));
+        KTG_CUDA(cudaEventRecord(b->st_ready[s], impl->copy_stream));
+        KTG_CUDA(cudaStreamWaitEvent(impl->stream, b->st_ready[s], 0));
+        // offsets stay absolute: bias the base pointer instead (pack kernel subtracts offsets[0])
+        const uint8_t *d_bases = (const uint8_t *)b->st_bases[s].p - offsets[r];
+        KTG_TRY(impl->ingest_device(d_bases, (const uint64_t *)b->st_offs[s].p, nr, nb));
+        KTG_CUDA(cudaEventRecord(b->st_free[s], impl->stream));
+        r = r1;
+    }
+    if (accepted_reads || accepted_bytes) {
+        uint64_t r1c = 0, b1c = 0;
+        KTG_TRY(impl->read_counters(&r1c, &b1c));
+        if (accepted_reads) *accepted_reads += r1c - r0c;
+        if (accepted_bytes) *accepted_bytes += b1c - b0c;
+    }
+    return KTG_OK;
+}
+
+int ktg_create_from_files(ktg_builder *b, const char *const *paths, uint32_t n_paths,
+                          int file_type, uint64_t *total_bytes) {
+    KTG_ENTER(b);
+    if (file_type != KTG_FASTQ && file_type != KTG_FASTA)
+        return fail(KTG_ERR_INVALID, "unsupported input_file_type %d", file_type);
+    uint64_t reads = 0, bytes = 0;
+    // check_files + opening every file up front (builder.rs:57-77, 146-149)
+    std::vector<std::unique_ptr<ReadFile>> files;
+    for (uint32_t i = 0; i < n_paths; ++i) {
+        std::unique_ptr<ReadFile> f(new ReadFile());
+        std::string why;
+        if (!f->open(paths[i], file_type == KTG_FASTA, &why)) return fail(KTG_ERR_IO, "%s", why.c_str());
+        files.push_back(std::move(f));
+    }
+    ReadBatch batch;
+    for (auto &f : files) {
+        for (;;) {
+            std::string why;
+            int st = f->next_batch(&batch, 64u << 20, &why);
+            if (st < 0) return fail(KTG_ERR_BAD_RECORD, "%s", why.c_str());
+            if (batch.n_reads())
+                KTG_TRY(ktg_add_reads(b, batch.bases.data(), batch.offsets.data(), batch.n_reads(), nullptr, nullptr));
+            // the pageable staging vectors are reused by the next batch
+            KTG_CUDA(cudaStreamSynchronize(b->impl->copy_stream));
+            if (st == 0) break;
+        }
+    }
+    KTG_TRY(b->impl->read_counters(&reads, &bytes));
+    if (total_bytes) *total_bytes = bytes;
+    return ktg_finalize(b);
+}
+
+int ktg_finalize(ktg_builder *b) {
+    KTG_ENTER(b);
+    return b->impl->finalize();
+}
+
+int ktg_counts(ktg_builder *b, uint64_t *nodes, uint64_t *edges) {
+    KTG_ENTER(b);
+    if (edges) {
+        EdgeStats es;
+        KTG_TRY(b->impl->edge_stats(0, &es));
+        *edges = es.edges;
+    }
+    if (nodes) {
+        NodeStats ns;
+        KTG_TRY(b->impl->node_stats(&ns));
+        *nodes = ns.nodes;
+    }
+    return KTG_OK;
+}
+
+int ktg_collection_stats(ktg_builder *b, ktg_stats *out) {
+    KTG_ENTER(b);
+    if (!out) return fail(KTG_ERR_INVALID, "null argument");
+    EdgeStats es;
+    NodeStats ns;
+    KTG_TRY(b->impl->edge_stats(0, &es));
+    KTG_TRY(b->impl->node_stats(&ns));
+    out->node_count = ns.nodes;
+    out->edge_count = es.edges;
+    out->max_edge_weight = es.max_w;
+    out->sum_edge_weight = es.sum_w;
+    out->max_in_degree = ns.max_in;
+    out->max_out_degree = ns.max_out;
+    out->incoming_vert_count = ns.sources;
+    out->outgoing_vert_count = ns.sinks;
+    return KTG_OK;
+}
+
+int ktg_remove_weak_edges(ktg_builder *b, uint32_t threshold) {
+    KTG_ENTER(b);
+    return b->impl->remove_weak_edges(threshold);
+}
+
+int ktg_remove_single_vertices(ktg_builder *b) {
+    KTG_ENTER(b);
+    return b->impl->finalize(); // nodes are implicit: nothing to remove
+}
+
+int ktg_standardize_edges(ktg_builder *b, uint64_t genome_len, uint64_t k, uint32_t threshold) {
+    KTG_ENTER(b);
+    return b->impl->standardize(genome_len, k, threshold);
+}
+
+int ktg_export_edges(ktg_builder *b, uint64_t *key_hi, uint64_t *key_lo, uint32_t *weight,
+                     uint64_t cap, int sorted, uint64_t *n) {
+    KTG_ENTER(b);
+    return b->impl->export_edges(key_hi, key_lo, weight, cap, sorted, n);
+}
+
+int ktg_digest(ktg_builder *b, uint64_t out[4]) {
+    KTG_ENTER(b);
+    EdgeStats es;
+    KTG_TRY(b->impl->edge_stats(0, &es));
+    out[0] = es.digest;
+    out[1] = es.edges;
+    out[2] = es.sum_w;
+    out[3] = es.max_w;
+    return KTG_OK;
+}
+
+uint32_t ktg_key_words(const ktg_builder *b) { return b && b->impl->k > 32 ? 2u : 1u; }
+
+uint32_t ktg_owner_of(const ktg_builder *b, uint64_t key_hi, uint64_t key_lo) {
+    return b ? b->impl->owner_of(key_hi, key_lo) : 0;
+}
+
+int ktg_partition_reads_device(ktg_builder *b, const void *d_bases, const void *d_offsets,
+                               uint64_t n_reads, uint64_t total_bases, void **d_keys,
+                               uint64_t *counts, uint64_t *accepted_reads,
+                               uint64_t *accepted_bytes) {
+    KTG_ENTER(b);
+    if (!d_keys || !counts) return fail(KTG_ERR_INVALID, "null argument");
+    uint64_t r0 = 0, b0 = 0;
+    if (accepted_reads || accepted_bytes) KTG_TRY(b->impl->read_counters(&r0, &b0));
+    KTG_TRY(b->impl->partition_reads((const uint8_t *)d_bases, (const uint64_t *)d_offsets, n_reads, total_bases, d_keys, counts));
+    if (accepted_reads || accepted_bytes) {
+        uint64_t r1 = 0, b1 = 0;
+        KTG_TRY(b->impl->read_counters(&r1, &b1));
+        if (accepted_reads) *accepted_reads += r1 - r0;
+        if (accepted_bytes) *accepted_bytes += b1 - b0;
+    }
+    return KTG_OK;
+}
+
+int ktg_insert_keys_device(ktg_builder *b, const void *d_keys, uint64_t n) {
+    KTG_ENTER(b);
+    return b->impl->insert_keys(d_keys, n);
+}
+
+int ktg_host_alloc(void **p, size_t bytes) {
+    if (!p) return fail(KTG_ERR_INVALID, "null argument");
+    KTG_CUDA(cudaHostAlloc(p, bytes, cudaHostAllocDefault));
+    return KTG_OK;
+}
+
+void ktg_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+int ktg_synth_reads_device(void *d_out, uint64_t seed_g, uint64_t genome_len, uint32_t read_len,
+                           uint32_t err_ppm, uint64_t r0, uint64_t r1, void *stream) {
+    if (!d_out || r1 < r0 || read_len == 0 || genome_len < read_len)
+        return fail(KTG_ERR_INVALID, "bad synthetic read configuration");
+    if (r1 == r0) return KTG_OK;
+    const uint64_t thr = (uint64_t)err_ppm * 18446744073709ull; // err_ppm * floor(2^64 / 1e6)
+    uint64_t work = (r1 - r0) * ((read_len + 3) / 4);
+    int grid = (int)std::min<uint64_t>((work + 255) / 256, 148 * 16);
+    synth_reads_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((uint8_t *)d_out, seed_g, genome_len, read_len, thr, r0, r1 - r0);
+    KTG_CUDA(cudaGetLastError());
+    return KTG_OK;
+}
+
+int ktg_random_access_probe(uint64_t bytes, uint64_t n_updates, uint32_t slot_bytes, float *ms) {
+    if (!ms || (slot_bytes != 16 && slot_bytes != 32) || bytes < slot_bytes)
+        return fail(KTG_ERR_INVALID, "bad probe configuration");
+    void *p = nullptr;
+    KTG_CUDA(cudaMalloc(&p, bytes));
+    KTG_CUDA(cudaMemset(p, 0, bytes));
+    unsigned long long *sink = nullptr;
+    KTG_CUDA(cudaMalloc(&sink, 8));
+    cudaEvent_t a, c;
+    cudaEventCreate(&a);
+    cudaEventCreate(&c);
+    uint64_t n_slots = bytes / slot_bytes;
+    int grid = 148 * 8;
+    for (int it = 0; it < 2; ++it) { // first pass warms the cache / TLB
+        cudaEventRecord(a);
+        if (slot_bytes == 16) random_access_probe_kernel<16><<<grid, 256>>>((unsigned char *)p, n_slots, n_updates, sink);
+        else random_access_probe_kernel<32><<<grid, 256>>>((unsigned char *)p, n_slots, n_updates, sink);
+        cudaEventRecord(c);
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaEventElapsedTime(ms, a, c);
+    cudaEventDestroy(a);
+    cudaEventDestroy(c);
+    cudaFree(p);
+    cudaFree(sink);
+    if (e != cudaSuccess) return fail(KTG_ERR_CUDA, "probe failed: %s", cudaGetErrorString(e));
+    return KTG_OK;
+}
+
+int ktg_get_profile(ktg_builder *b, ktg_kernel_profile *out, uint32_t cap, uint32_t *n) {
+    KTG_ENTER(b);
+    KTG_CUDA(cudaStreamSynchronize(b->impl->stream));
+    b->impl->prof.resolve();
+    const auto &es = b->impl->prof.entries;
+    if (n) *n = (uint32_t)es.size();
+    for (uint32_t i = 0; i < es.size() && i < cap; ++i) {
+        memset(&out[i], 0, sizeof out[i]);
+        strncpy(out[i].name, es[i].name.c_str(), sizeof(out[i].name) - 1);
+        out[i].launches = es[i].launches;
+        out[i].total_ms = es[i].ms;
+        out[i].units = es[i].units;
+    }
+    return KTG_OK;
+}
+
+int ktg_reset_profile(ktg_builder *b) {
+    KTG_ENTER(b);
+    KTG_CUDA(cudaStreamSynchronize(b->impl->stream));
+    b->impl->prof.reset();
+    return KTG_OK;
+}
+
+int ktg_get_info(ktg_builder *b, ktg_info *out) {
+    KTG_ENTER(b);
+    if (!out) return fail(KTG_ERR_INVALID, "null argument");
+    return b->impl->info(out);
+}
+
+} // extern "C"

@@ -1,0 +1,287 @@
+"""Host-side mirror of katome's GIR interface for the B200 builder.
+
+`GpuGIR` exposes the operations a katome GIR type implements -- Init / Build
+(algorithms/builder.rs:19-55), Clean (algorithms/pruner.rs:29-34),
+Standardizable::standardize_edges (algorithms/standardizer.rs:33-39),
+Stats<CollectionStats> (stats/collections.rs:170-208) and the edge export that
+Convert::create_from consumes (collections/girs/hm_gir.rs:156-226) -- with the
+same names, argument meaning and error behaviour, by forwarding to the C ABI in
+include/katome_gpu.h.  All file:line references are under
+/root/reference/src/katome/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Iterable, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib as L
+
+
+class KatomeError(RuntimeError):
+    """A panic of the reference, surfaced as an exception with the same message."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(message)
+        self.code = code
+
+
+class ReadTooShort(KatomeError):
+    """`assert!(read.len() >= K_SIZE, "Read is too short!")` (hm_gir.rs:40)."""
+
+
+def _raise(code: int):
+    msg = (L.lib().ktg_last_error() or b"").decode(errors="replace")
+    if code == L.KTG_ERR_SHORT_READ:
+        raise ReadTooShort(code, msg or "Read is too short!")
+    raise KatomeError(code, msg or f"katome_gpu error {code}")
+
+
+def _check(code: int):
+    if code != L.KTG_OK:
+        _raise(code)
+
+
+def _ptr(x) -> int:
+    """device / host pointer of a torch tensor, numpy array or int"""
+    if x is None:
+        return 0
+    if isinstance(x, int):
+        return x
+    if hasattr(x, "data_ptr"):
+        return int(x.data_ptr())
+    if isinstance(x, np.ndarray):
+        return int(x.ctypes.data)
+    raise TypeError(f"cannot take a pointer of {type(x)}")
+
+
+class DeviceArray:
+    """Zero-copy view of `n` 64-bit words at a device pointer owned by a handle, for
+    `torch.as_tensor(view, device="cuda")` (CUDA array interface, dtype int64)."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<i8", "data": (int(ptr), False),
+                                         "version": 2}
+
+
+_FILE_TYPES = {"fastq": L.KTG_FASTQ, "fasta": L.KTG_FASTA}
+
+
+class GpuGIR:
+    """De Bruijn graph intermediate representation built on one B200.
+
+    One handle == one collection; unlike the reference (`static mut K_SIZE`,
+    prelude.rs:21-25) k is per handle, so several can coexist.
+    """
+
+    def __init__(self, k: int = 40, reverse_complement: bool = True, *, edges_count: Optional[int] = None,
+                 device: int = -1, stream: int = 0, world_size: int = 1, rank: int = 0,
+                 profile: bool = False, force_direct: bool = False, force_partition: bool = False,
+                 sub_table_log2_bytes: int = 0):
+        self._L = L.lib()
+        flags = (L.KTG_FLAG_PROFILE if profile else 0) | (L.KTG_FLAG_FORCE_DIRECT if force_direct else 0) | \
+                (L.KTG_FLAG_FORCE_PARTITION if force_partition else 0)
+        cfg = L.KtgConfig(L.KTG_ABI_VERSION, int(k), int(bool(reverse_complement)), int(device),
+                          int(edges_count or 0), int(world_size), int(rank), C.c_void_p(stream or None),
+                          int(sub_table_log2_bytes), flags)
+        h = C.c_void_p()
+        self._h = None
+        _check(self._L.ktg_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+        self.k = int(k)
+        self.reverse_complement = bool(reverse_complement)
+        self.world_size, self.rank = int(world_size), int(rank)
+
+    # ---- Init (builder.rs:19-25) -------------------------------------------------
+    @classmethod
+    def init(cls, edges_count: Optional[int], nodes_count: Optional[int], ft: str = "fastq", *, k: int = 40,
+             reverse_complement: bool = True, **kw) -> "GpuGIR":
+        del nodes_count, ft  # nodes are implicit; the file type does not change the table
+        return cls(k, reverse_complement, edges_count=edges_count, **kw)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.ktg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ---- Build (builder.rs:28-55) ------------------------------------------------
+    def add_read_fastaq(self, read: bytes, reverse_complement: Optional[bool] = None):
+        """One read that already passed the ACGT filter (hm_gir.rs:39-87)."""
+        if reverse_complement is not None and bool(reverse_complement) != self.reverse_complement:
+            raise KatomeError(L.KTG_ERR_INVALID, "reverse_complement is fixed per GpuGIR handle")
+        bases = np.frombuffer(bytes(read), dtype=np.uint8)
+        offsets = np.array([0, len(bases)], dtype=np.uint64)
+        self.add_reads(bases, offsets)
+        _check(self._L.ktg_finalize(self._h))  # a short read panics immediately in the reference
+
+    def add_reads(self, bases: np.ndarray, offsets: np.ndarray) -> Tuple[int, int]:
+        """Batch form of the create_fastq loop body (builder.rs:152-160): drops reads with a
+        byte outside "ACGT", returns (accepted_reads, accepted_bytes) of this batch."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        nr, nb = C.c_uint64(0), C.c_uint64(0)
+        _check(self._L.ktg_add_reads(self._h, bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1,
+                                     C.byref(nr), C.byref(nb)))
+        return nr.value, nb.value
+
+    def add_reads_host_ptr(self, bases_ptr: int, offsets_ptr: int, n_reads: int, want_counts: bool = False):
+        """Same from raw (ideally pinned) host pointers; asynchronous unless counts are requested."""
+        if want_counts:
+            nr, nb = C.c_uint64(0), C.c_uint64(0)
+            _check(self._L.ktg_add_reads(self._h, bases_ptr, offsets_ptr, n_reads, C.byref(nr), C.byref(nb)))
+            return nr.value, nb.value
+        _check(self._L.ktg_add_reads(self._h, bases_ptr, offsets_ptr, n_reads, None, None))
+        return None
+
+    def add_reads_device(self, d_bases, d_offsets, n_reads: int, total_bases: int, want_counts: bool = False):
+        """Inputs resident in HBM (torch tensors or raw device pointers)."""
+        if want_counts:
+            nr, nb = C.c_uint64(0), C.c_uint64(0)
+            _check(self._L.ktg_add_reads_device(self._h, _ptr(d_bases), _ptr(d_offsets), n_reads, total_bases,
+                                                C.byref(nr), C.byref(nb)))
+            return nr.value, nb.value
+        _check(self._L.ktg_add_reads_device(self._h, _ptr(d_bases), _ptr(d_offsets), n_reads, total_bases, None, None))
+        return None
+
+    @classmethod
+    def create(cls, input_files: Sequence[os.PathLike], ft: str = "fastq", reverse_complement: bool = True,
+               minimal_weight_threshold: int = 0, *, k: int = 40, **kw) -> Tuple["GpuGIR", int]:
+        """Build::create (builder.rs:42-54): returns (collection, total accepted bytes).
+        `minimal_weight_threshold` only matters for BFCounter input in the reference
+        (builder.rs:106-108) and is ignored for Fastq/Fasta, as there."""
+        del minimal_weight_threshold
+        if ft.lower() not in _FILE_TYPES:
+            raise KatomeError(L.KTG_ERR_INVALID, f"unsupported input_file_type {ft!r} (BFCounter is out of scope)")
+        g = cls(k, reverse_complement, **kw)
+        arr = (C.c_char_p * len(input_files))(*[os.fsencode(f) for f in input_files])
+        total = C.c_uint64(0)
+        try:
+            _check(g._L.ktg_create_from_files(g._h, arr, len(input_files), _FILE_TYPES[ft.lower()], C.byref(total)))
+        except Exception:
+            g.close()
+            raise
+        return g, total.value
+
+    def finalize(self):
+        _check(self._L.ktg_finalize(self._h))
+
+    # ---- Stats (stats/collections.rs:170-208 and :137-168) -----------------------
+    def counts(self) -> Tuple[int, int]:
+        n, e = C.c_uint64(0), C.c_uint64(0)
+        _check(self._L.ktg_counts(self._h, C.byref(n), C.byref(e)))
+        return n.value, e.value
+
+    def edge_count(self) -> int:
+        e = C.c_uint64(0)
+        _check(self._L.ktg_counts(self._h, None, C.byref(e)))
+        return e.value
+
+    def stats(self) -> dict:
+        n, e = self.counts()
+        return {"node_count": n, "edge_count": e}
+
+    def collection_stats(self) -> dict:
+        s = L.KtgStats()
+        _check(self._L.ktg_collection_stats(self._h, C.byref(s)))
+        d = {name: int(getattr(s, name)) for name, _ in L.KtgStats._fields_}
+        d["avg_edge_weight"] = d["sum_edge_weight"] / d["edge_count"] if d["edge_count"] else float("nan")
+        d["avg_out_degree"] = d["edge_count"] / d["node_count"] if d["node_count"] else float("nan")
+        return d
+
+    # ---- Clean / Standardizable ---------------------------------------------------
+    def remove_weak_edges(self, threshold: int):
+        _check(self._L.ktg_remove_weak_edges(self._h, int(threshold)))
+
+    def remove_single_vertices(self):
+        _check(self._L.ktg_remove_single_vertices(self._h))
+
+    def standardize_edges(self, original_genome_length: int, k_size: int, threshold: int):
+        _check(self._L.ktg_standardize_edges(self._h, int(original_genome_length), int(k_size), int(threshold)))
+
+    # ---- export (what Convert::create_from consumes) -------------------------------
+    def export_edges(self, sorted: bool = True):
+        ne = self.edge_count()
+        hi = np.zeros(ne, np.uint64)
+        lo = np.zeros(ne, np.uint64)
+        w = np.zeros(ne, np.uint32)
+        n = C.c_uint64(0)
+        _check(self._L.ktg_export_edges(self._h, hi.ctypes.data, lo.ctypes.data, w.ctypes.data, ne, int(sorted),
+                                        C.byref(n)))
+        assert n.value == ne
+        return hi, lo, w
+
+    def digest(self) -> Tuple[int, int, int, int]:
+        out = (C.c_uint64 * 4)()
+        _check(self._L.ktg_digest(self._h, out))
+        return tuple(int(x) for x in out)
+
+    def dump(self) -> str:
+        """`sequence <kmer> weight <w>` lines (format of hs_gir.rs:288-290), sorted by k-mer."""
+        hi, lo, w = self.export_edges(sorted=True)
+        sym = "ACGT"
+        lines = []
+        for h, l, wt in zip(hi.tolist(), lo.tolist(), w.tolist()):
+            v = (h << 64) | l
+            kmer = "".join(sym[(v >> (2 * (self.k - 1 - j))) & 3] for j in range(self.k))
+            lines.append(f"sequence {kmer} weight {wt}\n")
+        return "".join(lines)
+
+    # ---- hash sharding (world_size > 1) ----------------------------------------------
+    def key_words(self) -> int:
+        return int(self._L.ktg_key_words(self._h))
+
+    def owner_of(self, hi: int, lo: int) -> int:
+        return int(self._L.ktg_owner_of(self._h, hi, lo))
+
+    def partition_reads_device(self, d_bases, d_offsets, n_reads: int, total_bases: int):
+        """-> (device pointer of the owner-major key array, counts per owner)"""
+        keys = C.c_void_p()
+        counts = (C.c_uint64 * self.world_size)()
+        _check(self._L.ktg_partition_reads_device(self._h, _ptr(d_bases), _ptr(d_offsets), n_reads, total_bases,
+                                                  C.byref(keys), counts, None, None))
+        return int(keys.value or 0), [int(c) for c in counts]
+
+    def insert_keys_device(self, d_keys, n: int):
+        _check(self._L.ktg_insert_keys_device(self._h, _ptr(d_keys), int(n)))
+
+    # ---- observability -----------------------------------------------------------------
+    def profile(self) -> dict:
+        n = C.c_uint32(0)
+        arr = (L.KtgKernelProfile * 64)()
+        _check(self._L.ktg_get_profile(self._h, arr, 64, C.byref(n)))
+        return {arr[i].name.decode(): {"launches": int(arr[i].launches), "ms": float(arr[i].total_ms),
+                                       "units": int(arr[i].units)} for i in range(min(n.value, 64))}
+
+    def reset_profile(self):
+        _check(self._L.ktg_reset_profile(self._h))
+
+    def info(self) -> dict:
+        i = L.KtgInfo()
+        _check(self._L.ktg_get_info(self._h, C.byref(i)))
+        return {name: int(getattr(i, name)) for name, _ in L.KtgInfo._fields_}
+
+
+def synth_reads_device(d_out, seed_g: int, genome_len: int, read_len: int, err_ppm: int, r0: int, r1: int,
+                       stream: int = 0):
+    _check(L.lib().ktg_synth_reads_device(_ptr(d_out), seed_g, genome_len, read_len, err_ppm, r0, r1,
+                                          C.c_void_p(stream or None)))
+
+
+def random_access_probe(table_bytes: int, n_updates: int, slot_bytes: int = 16) -> float:
+    ms = C.c_float(0)
+    _check(L.lib().ktg_random_access_probe(table_bytes, n_updates, slot_bytes, C.byref(ms)))
+    return float(ms.value)

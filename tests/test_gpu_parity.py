@@ -1,0 +1,324 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle.  Bit-exact: identical
+edge sets, weights, node counts and degree statistics, also after filtering/standardizing."""
+import numpy as np
+import pytest
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def K():
+    import katome_b200
+    from katome_b200 import _lib
+    assert _lib.lib().ktg_device_count() > 0, "GPU tests need a CUDA device"
+    return katome_b200
+
+
+def _oracle(seqs, k, rc):
+    from oracle import oracle as O
+    g = O.OracleGIR(k)
+    g.add_reads(*H.batch_of(seqs), rc)
+    return g
+
+
+def _assert_same(gpu, cpu, full_stats=True):
+    assert gpu.digest() == cpu.digest()
+    hi, lo, w = gpu.export_edges(sorted=True)
+    ehi, elo, ew = cpu.export_edges()
+    assert np.array_equal(lo, elo) and np.array_equal(hi, ehi) and np.array_equal(w, ew)
+    assert gpu.counts() == cpu.counts()
+    if full_stats:
+        a, b = gpu.collection_stats(), cpu.collection_stats()
+        for key in b:
+            if isinstance(b[key], float):
+                assert (np.isnan(a[key]) and np.isnan(b[key])) or a[key] == b[key], key
+            else:
+                assert a[key] == b[key], key
+
+
+# ------------------------------------------------------------------ C1: the reference's fixtures
+@pytest.mark.parametrize("name", ["data1", "data2", "data3"])
+def test_reference_fixtures_k40_norc(K, golden, tmp_path, name):
+    """tests/build.rs:27-28,46-89 through Build::create on the GPU"""
+    ref = golden["reference_pinned"][name]
+    fq = H.write_fastq(tmp_path / f"{name}.fastq", H.golden_seqs(name))
+    g, nbytes = K.GpuGIR.create([fq], "fastq", False, 0, k=40)
+    assert nbytes == ref["bytes"]
+    assert g.counts() == (ref["nodes"], ref["edges"])
+    st = g.collection_stats()
+    for key in ("max_edge_weight", "max_in_degree", "max_out_degree", "incoming_vert_count", "outgoing_vert_count"):
+        assert st[key] == ref[key], key
+    assert round(st["avg_edge_weight"], 2) == ref["avg_edge_weight"]
+    assert round(st["avg_out_degree"], 2) == ref["avg_out_degree"]
+
+
+def test_reference_filter_cases(K, golden, tmp_path):
+    """tests/pruner.rs:240-251, 260-262, 272"""
+    for case in golden["reference_pinned_filter"]:
+        fq = H.write_fastq(tmp_path / "f.fastq", H.golden_seqs(case["file"]))
+        g, _ = K.GpuGIR.create([fq], "fastq", False, 0, k=40)
+        g.remove_weak_edges(case["threshold"])
+        assert g.counts() == (case["nodes"], case["edges"]), case
+
+
+@pytest.mark.parametrize("k", [21, 31, 32, 33, 40, 63, 64])
+@pytest.mark.parametrize("rc", [False, True])
+def test_fixtures_against_committed_goldens(K, golden, tmp_path, k, rc):
+    for name in ("data1", "data2", "data3"):
+        exp = golden["oracle_derived"][f"{name}/k{k}/rc{int(rc)}"]
+        fq = H.write_fastq(tmp_path / f"{name}.fastq", H.golden_seqs(name))
+        g, nbytes = K.GpuGIR.create([fq], "fastq", rc, 0, k=k)
+        assert nbytes == exp["bytes"]
+        assert list(g.digest()) == exp["digest"]
+        assert list(g.counts()) == [exp["nodes"], exp["edges"]]
+        st = g.collection_stats()
+        for key, v in exp["stats"].items():
+            assert st[key] == v, (name, key)
+        for t in (2, 3):
+            g2, _ = K.GpuGIR.create([fq], "fastq", rc, 0, k=k)
+            g2.remove_weak_edges(t)
+            assert list(g2.digest()) == exp[f"filter_t{t}"]["digest"]
+            assert list(g2.counts()) == exp[f"filter_t{t}"]["counts"]
+            g2.close()
+        g.close()
+
+
+def test_too_short_read_voids_the_build(K, golden, tmp_path):
+    fq = H.write_fastq(tmp_path / "short.fastq", golden["too_short_seqs"], qual_len=100)
+    with pytest.raises(K.ReadTooShort):
+        K.GpuGIR.create([fq], "fastq", False, 0, k=40)
+    g = K.GpuGIR(40, True)
+    with pytest.raises(K.ReadTooShort):
+        g.add_read_fastaq(b"ACGTACG")
+    with pytest.raises(K.KatomeError):  # the build stays void
+        g.add_read_fastaq(b"A" * 50)
+
+
+def test_file_errors_mirror_check_files(K, tmp_path):
+    with pytest.raises(K.KatomeError) as e:
+        K.GpuGIR.create([str(tmp_path / "nope.fastq")], "fastq", True, 0, k=31)
+    assert "resolve path" in str(e.value)
+    with pytest.raises(K.KatomeError) as e:
+        K.GpuGIR.create([str(tmp_path)], "fastq", True, 0, k=31)
+    assert "is a directory" in str(e.value)
+    bad = tmp_path / "bad.fastq"
+    bad.write_text("ACGT\nACGT\n+\nIIII\n")
+    with pytest.raises(K.KatomeError):
+        K.GpuGIR.create([str(bad)], "fastq", True, 0, k=3)
+    for k in (1, 2, 65):
+        with pytest.raises(K.KatomeError):
+            K.GpuGIR(k)
+
+
+def test_fasta_and_multiple_files(K, tmp_path):
+    seqs = H.golden_seqs("data2")
+    fa = H.write_fasta(tmp_path / "a.fasta", seqs[:50])
+    fq1 = H.write_fastq(tmp_path / "a.fastq", seqs[:50])
+    fq2 = H.write_fastq(tmp_path / "b.fastq", seqs[50:])
+    ga, ba = K.GpuGIR.create([fa], "fasta", True, 0, k=40)
+    gq, bq = K.GpuGIR.create([fq1], "fastq", True, 0, k=40)
+    assert ba == bq and ga.digest() == gq.digest()
+    g2, b2 = K.GpuGIR.create([fq1, fq2], "fastq", True, 0, k=40)
+    cpu = _oracle(seqs, 40, True)
+    assert b2 == cpu.accepted_bytes
+    _assert_same(g2, cpu)
+
+
+# ------------------------------------------------------------------ random / ragged / edge cases
+@pytest.mark.parametrize("k", [3, 4, 5, 16, 17, 31, 32, 33, 34, 40, 47, 48, 63, 64])
+@pytest.mark.parametrize("rc", [False, True])
+def test_random_ragged_reads(K, k, rc):
+    rng = np.random.default_rng(1000 * k + rc)
+    seqs = H.random_reads(rng, 300, k, k + 200, n_rate=0.1)
+    seqs += ["A" * (k + 5), "T" * (k + 40), "ACGT" * 40, "AT" * 70, "", "N"]  # homopolymers, palindromes
+    seqs = [s for s in seqs if len(s) >= k or any(c not in "ACGT" for c in s)]  # short valid reads abort
+    cpu = _oracle(seqs, k, rc)
+    g = K.GpuGIR(k, rc)
+    nr, nb = g.add_reads(*H.batch_of(seqs))
+    assert (nr, nb) == (cpu.accepted_reads, cpu.accepted_bytes)
+    _assert_same(g, cpu)
+    # python set-level twin as a second witness
+    edges, _, _ = H.py_build(seqs, k, rc)
+    assert g.counts() == (len(H.py_nodes(edges)), len(edges))
+    for t in (2, 3):
+        cpu.remove_weak_edges(t)
+        g.remove_weak_edges(t)
+        _assert_same(g, cpu)
+    g.close()
+
+
+@pytest.mark.parametrize("k", [31, 40])
+def test_direct_and_partitioned_paths_agree(K, k):
+    rng = np.random.default_rng(7 + k)
+    genome = "".join(rng.choice(list("ACGT"), size=20000))
+    seqs = H.random_reads(rng, 3000, 100, 150, genome=genome, n_rate=0.02)
+    cpu = _oracle(seqs, k, True)
+    for kw in ({"force_direct": True}, {"force_partition": True}, {"force_partition": True, "sub_table_log2_bytes": 16}):
+        g = K.GpuGIR(k, True, **kw)
+        g.add_reads(*H.batch_of(seqs))
+        _assert_same(g, cpu)
+        assert g.info()["partitioned"] == int("force_partition" in kw)
+        g.close()
+
+
+def test_all_T_at_full_key_width_without_canonicalisation(K):
+    """k=32 / k=64, reverse_complement=false: TTT...T equals the all-ones 'empty' marker"""
+    for k in (32, 64):
+        seqs = ["T" * (k + 10), "ACGT" * 30, "T" * k, "G" + "T" * (k + 3)]
+        for rc in (False, True):
+            cpu = _oracle(seqs, k, rc)
+            g = K.GpuGIR(k, rc)
+            g.add_reads(*H.batch_of(seqs))
+            _assert_same(g, cpu)
+            g.remove_weak_edges(3)
+            cpu.remove_weak_edges(3)
+            _assert_same(g, cpu)
+            g.close()
+
+
+def test_empty_and_minimal_inputs(K):
+    g = K.GpuGIR(31, True)
+    assert g.add_reads(np.zeros(0, np.uint8), np.zeros(1, np.uint64)) == (0, 0)
+    assert g.counts() == (0, 0) and g.digest() == (0, 0, 0, 0)
+    assert g.add_reads(*H.batch_of(["ACGTNACGT" * 10, "acgt" * 20])) == (0, 0)  # all rejected
+    assert g.counts() == (0, 0)
+    s = "ACGTTGCATGCATGCCGATAGCTAGCTAGGA"  # exactly k: one window
+    assert g.add_reads(*H.batch_of([s])) == (1, 31)
+    assert g.counts() == (4, 2)
+    assert g.dump() == _oracle([s], 31, True).dump()
+    g.close()
+
+
+def test_batches_accumulate_and_table_grows_without_a_hint(K):
+    from oracle import oracle as O
+    G, L, k = 300_000, 100, 31
+    n = 12_000
+    reads = O.synth_reads(0xABCDEF, G, L, 5000, 0, n)
+    offsets = (np.arange(n + 1, dtype=np.uint64) * L)
+    cpu = O.OracleGIR(k)
+    cpu.add_reads(reads, offsets, True)
+    g = K.GpuGIR(k, True, sub_table_log2_bytes=16)  # starts at 1 Mi slots, must grow + partition
+    step = 3000
+    for r0 in range(0, n, step):
+        g.add_reads(reads[r0 * L:(r0 + step) * L], offsets[r0:r0 + step + 1] - offsets[r0])
+    _assert_same(g, cpu, full_stats=True)
+    info = g.info()
+    assert info["grow_events"] >= 1 and info["occupied_slots"] * 2 == cpu.counts()[1]
+    # one shot with a capacity hint gives the same table content
+    g2 = K.GpuGIR(k, True, edges_count=cpu.counts()[1])
+    g2.add_reads(reads, offsets)
+    assert g2.digest() == cpu.digest() and g2.info()["grow_events"] == 0
+    g.close(), g2.close()
+
+
+@pytest.mark.parametrize("k,rc", [(31, True), (40, True), (40, False), (63, True)])
+def test_standardize_edges(K, k, rc):
+    rng = np.random.default_rng(k)
+    genome = "".join(rng.choice(list("ACGT"), size=3000))
+    seqs = H.random_reads(rng, 1500, 100, 150, genome=genome)
+    for t in (0, 2, 5):
+        cpu = _oracle(seqs, k, rc)
+        g = K.GpuGIR(k, rc)
+        g.add_reads(*H.batch_of(seqs))
+        cpu.standardize_edges(len(genome), k, t)
+        g.standardize_edges(len(genome), k, t)
+        _assert_same(g, cpu)
+        g.close()
+    g = K.GpuGIR(k, rc)
+    g.add_reads(*H.batch_of(seqs))
+    with pytest.raises(K.KatomeError):
+        g.standardize_edges(k - 1, k, 0)  # G < k: the reference underflows/panics
+
+
+def test_device_resident_inputs_and_synthetic_generator(K):
+    from oracle import oracle as O
+    seed, G, L, n = 0x6B61746F6D65 + 1, 200_000, 100, 5000
+    d = torch.empty(n * L, dtype=torch.uint8, device="cuda")
+    K.synth_reads_device(d, seed, G, L, 5000, 100, 100 + n, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    host = O.synth_reads(seed, G, L, 5000, 100, 100 + n)
+    assert np.array_equal(d.cpu().numpy(), host)
+    offs = torch.arange(0, (n + 1) * L, L, dtype=torch.int64, device="cuda")
+    for k in (31, 63):
+        g = K.GpuGIR(k, True, stream=torch.cuda.current_stream().cuda_stream)
+        assert g.add_reads_device(d, offs, n, n * L, want_counts=True) == (n, n * L)
+        cpu = O.OracleGIR(k)
+        cpu.add_reads(host, np.arange(n + 1, dtype=np.uint64) * L, True)
+        _assert_same(g, cpu)
+        g.close()
+
+
+def test_two_rank_sharding_on_one_gpu(K):
+    """world_size=2 emulated with two handles on one GPU: partition -> exchange -> insert; the
+    union of the shards is the oracle's table and every key sits on its owner."""
+    from oracle import oracle as O
+    seed, G, L, n, k = 77, 150_000, 150, 4000, 31
+    host = O.synth_reads(seed, G, L, 5000, 0, n)
+    cpu = O.OracleGIR(k)
+    cpu.add_reads(host, np.arange(n + 1, dtype=np.uint64) * L, True)
+    W = 2
+    gs = [K.GpuGIR(k, True, world_size=W, rank=r) for r in range(W)]
+    half = n // W
+    recv = [[] for _ in range(W)]
+    for r in range(W):
+        d = torch.from_numpy(host[r * half * L:(r + 1) * half * L]).cuda()
+        offs = torch.arange(0, (half + 1) * L, L, dtype=torch.int64, device="cuda")
+        ptr, counts = gs[r].partition_reads_device(d, offs, half, half * L)
+        assert sum(counts) == half * (L - k + 1)
+        gs[r].finalize()
+        total = sum(counts)
+        buf = torch.as_tensor(K.DeviceArray(ptr, total), device="cuda").clone()
+        o = 0
+        for dst in range(W):
+            recv[dst].append(buf[o:o + counts[dst]].clone())
+            o += counts[dst]
+    parts = []
+    for r in range(W):
+        keys = torch.cat(recv[r])
+        gs[r].insert_keys_device(keys, keys.numel())
+        hi, lo, w = gs[r].export_edges(sorted=True)
+        assert all(gs[r].owner_of(0, int(x)) == r for x in lo[:200].tolist())
+        parts.append((lo, w))
+    lo = np.concatenate([p[0] for p in parts])
+    w = np.concatenate([p[1] for p in parts])
+    order = np.argsort(lo, kind="stable")
+    _, elo, ew = cpu.export_edges()
+    assert np.array_equal(lo[order], elo) and np.array_equal(w[order], ew)
+    d0, d1 = gs[0].digest(), gs[1].digest()
+    cd = cpu.digest()
+    assert ((d0[0] + d1[0]) & (2**64 - 1), d0[1] + d1[1], d0[2] + d1[2], max(d0[3], d1[3])) == cd
+
+
+def test_full_size_properties(K):
+    """Size-independent properties on a run too large for the oracle: weight conservation,
+    batch-split invariance, filter idempotence and monotonicity (BASELINE config 2 shape)."""
+    from katome_b200.workloads import Workload
+    wl = Workload("mini-C2", 1, 1_000_000, 100, 20, 5000, 31)
+    n, L = wl.n_reads, wl.read_len
+    d = torch.empty(n * L, dtype=torch.uint8, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    K.synth_reads_device(d, wl.seed, wl.genome_len, L, wl.err_ppm, 0, n, stream=s)
+    offs = torch.arange(0, (n + 1) * L, L, dtype=torch.int64, device="cuda")
+    g = K.GpuGIR(31, True, stream=s, edges_count=wl.expected_distinct_edges())
+    assert g.add_reads_device(d, offs, n, n * L, want_counts=True) == (n, n * L)
+    D, E, S, M = g.digest()
+    assert S == 2 * wl.n_windows  # every window adds 1 to each strand (2 to a palindrome)
+    assert 0.8 * wl.expected_distinct_edges() < E < 1.2 * wl.expected_distinct_edges()
+    # same reads in two batches, no hint, partitioned path
+    g2 = K.GpuGIR(31, True, stream=s, force_partition=True)
+    h = n // 2
+    g2.add_reads_device(d, offs, h, h * L)
+    g2.add_reads_device(d[h * L:], offs[:n - h + 1], n - h, (n - h) * L)
+    assert g2.digest() == (D, E, S, M)
+    g.remove_weak_edges(3)
+    d3 = g.digest()
+    assert d3[1] < E and d3[2] < S
+    g.remove_weak_edges(3)
+    assert g.digest() == d3
+    g2.remove_weak_edges(2)
+    g2.remove_weak_edges(3)
+    assert g2.digest() == d3

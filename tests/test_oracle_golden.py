@@ -1,0 +1,151 @@
+"""The oracle against every known-answer vector the reference's own tests hold for the
+hot path.  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests import helpers as H
+
+
+@pytest.mark.parametrize("name", ["data1", "data2", "data3"])
+def test_build_counts_pinned_by_reference(golden, tmp_path, name):
+    """tests/build.rs:27-28,46-89 -- k=40, reverse_complement=false, threshold 0"""
+    ref = golden["reference_pinned"][name]
+    fq = H.write_fastq(tmp_path / f"{name}.fastq", H.golden_seqs(name))
+    g, nbytes = O.OracleGIR.create(40, [fq], "fastq", False)
+    assert nbytes == ref["bytes"]
+    assert g.counts() == (ref["nodes"], ref["edges"])
+    st = g.collection_stats()
+    for key in ("max_edge_weight", "max_in_degree", "max_out_degree", "incoming_vert_count", "outgoing_vert_count"):
+        assert st[key] == ref[key], key
+    # CollectionStats equality rounds floats to 2 dp (stats/collections.rs:71-89)
+    assert round(st["avg_edge_weight"], 2) == ref["avg_edge_weight"]
+    assert round(st["avg_out_degree"], 2) == ref["avg_out_degree"]
+
+
+def test_filter_pinned_by_reference(golden, tmp_path):
+    """tests/pruner.rs:240-251, 260-262, 272"""
+    for case in golden["reference_pinned_filter"]:
+        fq = H.write_fastq(tmp_path / "f.fastq", H.golden_seqs(case["file"]))
+        g, _ = O.OracleGIR.create(40, [fq], "fastq", False)
+        g.remove_weak_edges(case["threshold"])
+        assert g.counts() == (case["nodes"], case["edges"]), case
+
+
+def test_too_short_read_aborts(golden, tmp_path):
+    """hm_gir.rs:40: the first read has N's (rejected), the second is 7 bp"""
+    fq = H.write_fastq(tmp_path / "short.fastq", golden["too_short_seqs"], qual_len=100)
+    with pytest.raises(O.OracleError) as e:
+        O.OracleGIR.create(40, [fq], "fastq", False)
+    assert e.value.code == O.KO_ERR_SHORT_READ
+
+
+def test_codec_known_answers(golden):
+    kat = golden["codec_kat"]
+    for s, expect in kat["compress_edge"]:
+        assert list(O.compress_edge(s.encode())) == expect
+        assert O.decompress_edge(bytes(expect)) == s.encode()
+    enc = kat["encode_fasta_symbol"]
+    block = 0
+    for c in "ACGT":
+        assert O.encode_fasta_symbol(ord(c), 0) == enc[c]
+        block = O.encode_fasta_symbol(ord(c), block)
+    assert block == enc["block_ACGT"]
+    for by, expect in kat["shift_right"]["by"]:
+        assert list(O.shift_right_bit_array(bytes(kat["shift_right"]["input"]), by)) == expect
+    for inp, rem, out, s_in, s_out in kat["reverse_compressed_node"]:
+        assert list(O.reverse_compressed_node(bytes(inp), rem)) == out
+        assert list(O.reverse_compressed_node(bytes(out), rem)) == inp  # involution, compress.rs:629
+        assert list(O.compress_node(s_in.encode())) == inp
+        assert list(O.compress_node(s_out.encode())) == out
+        assert H.revcomp(s_in) == s_out
+
+
+def test_standardize_known_answer(golden):
+    """standardizer.rs:254-279: (G,k,t)=(17,3,3) keeps 13 edges, weights 2 at idx 3,4 else 1"""
+    import ctypes as C
+    kat = golden["standardize_kat"]
+    w = np.array(kat["weights"], np.uint32)
+    err = C.c_int(0)
+    m = O.lib().ko_standardize_weights(w.ctypes.data, len(w), kat["G"], kat["k"], kat["t"], C.byref(err))
+    assert err.value == 0 and m == len(kat["expect"])
+    assert w[:m].tolist() == kat["expect"]
+    # ratio (10,0,10,0) -> 1.0 (standardizer.rs:138-141): weights unchanged
+    w = np.array([4, 6], np.uint32)
+    m = O.lib().ko_standardize_weights(w.ctypes.data, 2, 10, 0, 0, C.byref(err))
+    assert err.value == 0 and m == 2 and w.tolist() == [4, 6]
+
+
+@pytest.mark.parametrize("k", [3, 4, 5, 6, 21, 31, 32, 33, 40, 63, 64])
+def test_byte_level_revcomp_equals_string_revcomp(k):
+    """compress_kmer_with_rev_compl (compress.rs:34-48) == packing the reverse-complement string"""
+    rng = np.random.default_rng(k)
+    for _ in range(50):
+        s = "".join(rng.choice(list("ACGT"), size=k))
+        fw, rv = O.compress_kmer_with_rev_compl(s.encode())
+        assert fw == O.compress_kmer(s.encode())
+        assert rv == O.compress_kmer(H.revcomp(s).encode())
+
+
+@pytest.mark.parametrize("k,rc", [(5, False), (5, True), (6, True), (31, True), (32, False), (33, True), (40, True),
+                                  (64, True)])
+def test_oracle_equals_python_set_level_twin(k, rc):
+    """C oracle (node-keyed, chained) vs the 10-line set-level restatement of SURVEY Appendix A"""
+    rng = np.random.default_rng(100 * k + rc)
+    seqs = H.random_reads(rng, 60, k, k + 90, n_rate=0.15)
+    edges, reads, nbytes = H.py_build(seqs, k, rc)
+    g = O.OracleGIR(k)
+    g.add_reads(*H.batch_of(seqs), rc)
+    assert (g.accepted_reads, g.accepted_bytes) == (reads, nbytes)
+    hi, lo, w = g.export_edges()
+    ehi, elo, ew = H.py_sorted_arrays(edges)
+    assert np.array_equal(hi, ehi) and np.array_equal(lo, elo) and np.array_equal(w, ew)
+    assert g.counts() == (len(H.py_nodes(edges)), len(edges))
+    # filter, then the orphan-node rule (pruner.rs:95-119): N' = prefixes/suffixes of E'
+    g.remove_weak_edges(2)
+    kept = {e: x for e, x in edges.items() if x >= 2}
+    assert g.counts() == (len(H.py_nodes(kept)), len(kept))
+
+
+def test_oracle_derived_goldens_are_reproducible(golden, tmp_path):
+    """the committed oracle-derived numbers (rc=true, other k) still come out of the oracle"""
+    for key in ("data1/k40/rc1", "data2/k40/rc1", "data3/k31/rc1", "data3/k63/rc0"):
+        name, ks, rcs = key.split("/")
+        fq = H.write_fastq(tmp_path / "g.fastq", H.golden_seqs(name))
+        g, nbytes = O.OracleGIR.create(int(ks[1:]), [fq], "fastq", rcs == "rc1")
+        exp = golden["oracle_derived"][key]
+        assert nbytes == exp["bytes"] and list(g.counts()) == [exp["nodes"], exp["edges"]]
+        assert list(g.digest()) == exp["digest"]
+    # SURVEY Appendix B (derived, rc=true, k=40)
+    d = golden["oracle_derived"]
+    assert (d["data1/k40/rc1"]["nodes"], d["data1/k40/rc1"]["edges"]) == (124, 122)
+    assert (d["data2/k40/rc1"]["nodes"], d["data2/k40/rc1"]["edges"]) == (11376, 11194)
+    assert (d["data3/k40/rc1"]["nodes"], d["data3/k40/rc1"]["edges"]) == (28892, 28426)
+
+
+def test_fasta_reader_and_multi_file(tmp_path):
+    seqs = H.golden_seqs("data2")[:20]
+    fa = H.write_fasta(tmp_path / "a.fasta", seqs)
+    fq = H.write_fastq(tmp_path / "a.fastq", seqs)
+    ga, ba = O.OracleGIR.create(40, [fa], "fasta", True)
+    gq, bq = O.OracleGIR.create(40, [fq], "fastq", True)
+    assert ba == bq and ga.digest() == gq.digest()
+    fq2 = H.write_fastq(tmp_path / "b.fastq", H.golden_seqs("data2")[20:40])
+    g2, b2 = O.OracleGIR.create(40, [fq, fq2], "fastq", True)
+    g3, b3 = O.OracleGIR.create(40, [H.write_fastq(tmp_path / "c.fastq", H.golden_seqs("data2")[:40])], "fastq", True)
+    assert b2 == b3 and g2.digest() == g3.digest()
+    with pytest.raises(O.OracleError):
+        O.OracleGIR.create(40, [str(tmp_path / "missing.fastq")])
+
+
+def test_synthetic_reads_are_deterministic_and_error_rate_is_right():
+    a = O.synth_reads(0x6B61746F6D65 + 1, 100000, 100, 5000, 10, 2010)
+    b = O.synth_reads(0x6B61746F6D65 + 1, 100000, 100, 5000, 10, 2010)
+    assert np.array_equal(a, b) and set(np.unique(a)) <= set(b"ACGT")
+    clean = O.synth_reads(0x6B61746F6D65 + 1, 100000, 100, 0, 10, 2010)
+    rate = float(np.mean(a != clean))
+    assert 0.003 < rate < 0.007
+    # an error-free forward-strand read is a slice of the genome
+    genome = O.synth_genome(0x6B61746F6D65 + 1, 0, 100000).tobytes().decode()
+    r0 = clean[:100].tobytes().decode()
+    assert r0 in genome or H.revcomp(r0) in genome
