@@ -94,6 +94,10 @@ int ktg_add_reads_device(ktg_builder *b, const void *d_bases, const void *d_offs
 int ktg_create_from_files(ktg_builder *b, const char *const *paths, uint32_t n_paths,
                           int file_type, uint64_t *total_bytes);
 
+/* Default::default() again (builder.rs:145): empties the collection but keeps the
+ * device allocations, so that repeated builds do not pay cudaMalloc. */
+int ktg_reset(ktg_builder *b);
+
 /* Waits for all queued work and surfaces deferred errors (short read, table). */
 int ktg_finalize(ktg_builder *b);
 

@@ -22,7 +22,7 @@ KTG_FLAG_PROFILE, KTG_FLAG_FORCE_DIRECT, KTG_FLAG_FORCE_PARTITION = 1, 2, 4
 # every symbol include/katome_gpu.h declares
 SYMBOLS = (
     "ktg_create", "ktg_destroy", "ktg_last_error", "ktg_device_count", "ktg_add_reads",
-    "ktg_add_reads_device", "ktg_create_from_files", "ktg_finalize", "ktg_counts",
+    "ktg_add_reads_device", "ktg_create_from_files", "ktg_reset", "ktg_finalize", "ktg_counts",
     "ktg_collection_stats", "ktg_remove_weak_edges", "ktg_remove_single_vertices",
     "ktg_standardize_edges", "ktg_export_edges", "ktg_digest", "ktg_key_words", "ktg_owner_of",
     "ktg_partition_reads_device", "ktg_insert_keys_device", "ktg_host_alloc", "ktg_host_free",
@@ -94,6 +94,7 @@ def lib():
     L.ktg_add_reads_device.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, u64p, u64p]
     L.ktg_create_from_files.argtypes = [vp, C.POINTER(C.c_char_p), C.c_uint32, C.c_int, u64p]
     L.ktg_finalize.argtypes = [vp]
+    L.ktg_reset.argtypes = [vp]
     L.ktg_counts.argtypes = [vp, u64p, u64p]
     L.ktg_collection_stats.argtypes = [vp, C.POINTER(KtgStats)]
     L.ktg_remove_weak_edges.argtypes = [vp, C.c_uint32]

@@ -172,6 +172,7 @@ struct BuilderBase {
                               uint64_t total_bases) = 0;
     virtual int read_counters(uint64_t *reads, uint64_t *bytes) = 0;
     virtual int finalize() = 0;
+    virtual int reset() = 0;
     virtual int edge_stats(uint32_t threshold, EdgeStats *out) = 0;
     virtual int node_stats(NodeStats *out) = 0;
     virtual int remove_weak_edges(uint32_t t) = 0;
@@ -461,44 +462,52 @@ template <class K> struct Builder : BuilderBase {
     }
 
     // ---- partition helpers ----------------------------------------------------------
-    // bins -> exclusive offsets in d_hist[n_bins .. 2n_bins], cursors in [2n_bins+1 ..]
+    // b_hist layout: hist[n_bins] | offsets[n_bins + 1] | cursors[n_bins]
     unsigned long long *hist_ptr() { return (unsigned long long *)b_hist.p; }
     unsigned long long *offs_ptr(uint32_t n_bins) { return hist_ptr() + n_bins; }
     unsigned long long *curs_ptr(uint32_t n_bins) { return hist_ptr() + 2 * n_bins + 1; }
 
-    template <bool BY_OWNER>
-    int partition_from_reads(uint64_t n_words, uint64_t max_keys, uint32_t n_bins, K **out) {
+    // bin histogram of the packed batch (optionally folding the keys into the sketch)
+    template <bool BY_OWNER, bool HLL> int hist_reads_pass(uint64_t n_words, uint32_t n_bins) {
         KTG_TRY(b_hist.ensure((3 * (size_t)n_bins + 2) * 8));
-        KTG_TRY(b_keys.ensure(max_keys * sizeof(K) + 16));
         KTG_CUDA(cudaMemsetAsync(b_hist.p, 0, n_bins * 8, stream));
         const uint64_t *packed = (const uint64_t *)b_packed.p;
         const uint8_t *nstart = (const uint8_t *)b_nstart.p;
-        size_t hs = (size_t)n_bins * 4;
+        size_t hs = ((size_t)n_bins + (HLL ? HLL_M : 0)) * 4;
+        prof.begin("hist_reads", n_words * 32, stream);
         if (rc) {
-            int g = grid_for(hist_reads_kernel<K, true, BY_OWNER>, 256, hs, props);
-            prof.begin("hist_reads", n_words * 32, stream);
-            hist_reads_kernel<K, true, BY_OWNER><<<g, 256, hs, stream>>>(packed, nstart, n_words, k, tab, n_bins, hist_ptr());
+            int g = grid_for(hist_reads_kernel<K, true, BY_OWNER, HLL>, 256, hs, props);
+            hist_reads_kernel<K, true, BY_OWNER, HLL><<<g, 256, hs, stream>>>(packed, nstart, n_words, k, tab, n_bins, hist_ptr(), (uint32_t *)b_hll.p);
         }
         else {
-            int g = grid_for(hist_reads_kernel<K, false, BY_OWNER>, 256, hs, props);
-            prof.begin("hist_reads", n_words * 32, stream);
-            hist_reads_kernel<K, false, BY_OWNER><<<g, 256, hs, stream>>>(packed, nstart, n_words, k, tab, n_bins, hist_ptr());
+            int g = grid_for(hist_reads_kernel<K, false, BY_OWNER, HLL>, 256, hs, props);
+            hist_reads_kernel<K, false, BY_OWNER, HLL><<<g, 256, hs, stream>>>(packed, nstart, n_words, k, tab, n_bins, hist_ptr(), (uint32_t *)b_hll.p);
         }
         prof.end(stream);
+        return KTG_OK;
+    }
+
+    int scan_bins_pass(uint32_t n_bins) {
         prof.begin("scan_bins", n_bins, stream);
         scan_bins_kernel<<<1, 1024, 0, stream>>>(hist_ptr(), n_bins, offs_ptr(n_bins), curs_ptr(n_bins));
         prof.end(stream);
+        return KTG_OK;
+    }
+
+    template <bool BY_OWNER> int scatter_reads_pass(uint64_t n_words, uint64_t n_keys, uint32_t n_bins, K **out) {
+        KTG_TRY(b_keys.ensure(n_keys * sizeof(K) + 16));
+        const uint64_t *packed = (const uint64_t *)b_packed.p;
+        const uint8_t *nstart = (const uint8_t *)b_nstart.p;
         size_t ss = scatter_reads_smem(n_bins);
         constexpr int TW = ScatterCfg<K>::TILE_WORDS;
         uint64_t n_tiles = (n_words + TW - 1) / TW;
+        prof.begin("scatter_reads", n_words * 32, stream);
         if (rc) {
             int g = (int)std::min<uint64_t>(grid_for(scatter_reads_kernel<K, true, BY_OWNER>, TW, ss, props), n_tiles);
-            prof.begin("scatter_reads", n_words * 32, stream);
             scatter_reads_kernel<K, true, BY_OWNER><<<g, TW, ss, stream>>>(packed, nstart, n_words, k, tab, n_bins, curs_ptr(n_bins), (K *)b_keys.p);
         }
         else {
             int g = (int)std::min<uint64_t>(grid_for(scatter_reads_kernel<K, false, BY_OWNER>, TW, ss, props), n_tiles);
-            prof.begin("scatter_reads", n_words * 32, stream);
             scatter_reads_kernel<K, false, BY_OWNER><<<g, TW, ss, stream>>>(packed, nstart, n_words, k, tab, n_bins, curs_ptr(n_bins), (K *)b_keys.p);
         }
         prof.end(stream);
@@ -506,18 +515,19 @@ template <class K> struct Builder : BuilderBase {
         return KTG_OK;
     }
 
-    int partition_from_keys(const K *keys, uint64_t n, uint32_t n_bins, K **out) {
+    template <bool HLL> int hist_keys_pass(const K *keys, uint64_t n, uint32_t n_bins) {
         KTG_TRY(b_hist.ensure((3 * (size_t)n_bins + 2) * 8));
-        KTG_TRY(b_keys2.ensure(n * sizeof(K) + 16));
         KTG_CUDA(cudaMemsetAsync(b_hist.p, 0, n_bins * 8, stream));
-        size_t hs = (size_t)n_bins * 4;
-        int g = grid_for(hist_keys_kernel<K, false>, 256, hs, props);
+        size_t hs = ((size_t)n_bins + (HLL ? HLL_M : 0)) * 4;
+        int g = grid_for(hist_keys_kernel<K, false, HLL>, 256, hs, props);
         prof.begin("hist_keys", n, stream);
-        hist_keys_kernel<K, false><<<g, 256, hs, stream>>>(keys, n, tab, n_bins, hist_ptr());
+        hist_keys_kernel<K, false, HLL><<<g, 256, hs, stream>>>(keys, n, tab, n_bins, hist_ptr(), (uint32_t *)b_hll.p);
         prof.end(stream);
-        prof.begin("scan_bins", n_bins, stream);
-        scan_bins_kernel<<<1, 1024, 0, stream>>>(hist_ptr(), n_bins, offs_ptr(n_bins), curs_ptr(n_bins));
-        prof.end(stream);
+        return KTG_OK;
+    }
+
+    int scatter_keys_pass(const K *keys, uint64_t n, uint32_t n_bins, K **out) {
+        KTG_TRY(b_keys2.ensure(n * sizeof(K) + 16));
         size_t ss = scatter_keys_smem(n_bins);
         uint64_t n_tiles = (n + 4095) / 4096;
         int g2 = (int)std::min<uint64_t>(grid_for(scatter_keys_kernel<K, false>, 256, ss, props), std::max<uint64_t>(n_tiles, 1));
@@ -526,6 +536,32 @@ template <class K> struct Builder : BuilderBase {
         prof.end(stream);
         *out = (K *)b_keys2.p;
         return KTG_OK;
+    }
+
+    // Partitioned insert, sizing the table from the sketch that the histogram pass
+    // fills for free.  `hist` runs the histogram (+sketch) for the current geometry.
+    template <class H> int sized_hist(H hist, uint64_t *n_keys) {
+        if (!sketch_complete) { // keys went in unsketched (direct path): restart from the exact count
+            uint64_t exact = 0;
+            KTG_TRY(count_occupied(&exact));
+            hll_base = exact;
+            sketch_complete = true;
+            KTG_CUDA(cudaMemsetAsync(b_hll.p, 0, HLL_M * 4, stream));
+        }
+        for (int attempt = 0;; ++attempt) {
+            KTG_TRY(hist());
+            std::vector<unsigned long long> h(tab.n_sub);
+            KTG_CUDA(cudaMemcpyAsync(h.data(), hist_ptr(), tab.n_sub * 8, cudaMemcpyDeviceToHost, stream));
+            double est = 0;
+            KTG_TRY(hll_estimate(&est)); // synchronises the stream
+            uint64_t total = 0;
+            for (unsigned long long v : h) total += v;
+            *n_keys = total;
+            uint64_t distinct = hll_base + (uint64_t)(est * 1.08) + 64;
+            occupied_ub = distinct;
+            if ((double)distinct <= LOAD_MAX * (double)tab.capacity() || attempt >= 2) return KTG_OK;
+            KTG_TRY(grow_to((uint64_t)((double)distinct / LOAD_TARGET) + 1)); // geometry changed: redo
+        }
     }
 
     int launch_insert_keys(const K *keys, uint64_t n) {
@@ -550,37 +586,36 @@ template <class K> struct Builder : BuilderBase {
         KTG_TRY(pack(d_bases, d_offsets, n_reads, total_bases, &n_words));
         const uint64_t *packed = (const uint64_t *)b_packed.p;
         const uint8_t *nstart = (const uint8_t *)b_nstart.p;
-        const uint64_t max_windows = total_bases; // trivial bound on the batch's keys
-        KTG_TRY(reserve(max_windows, [&]() -> int {
-            prof.begin("hll_reads", n_words * 32, stream);
-            if (rc) hll_reads_kernel<K, true><<<props.sms * 4, 256, 0, stream>>>(packed, nstart, n_words, k, (uint32_t *)b_hll.p);
-            else hll_reads_kernel<K, false><<<props.sms * 4, 256, 0, stream>>>(packed, nstart, n_words, k, (uint32_t *)b_hll.p);
-            prof.end(stream);
-            return KTG_OK;
-        }));
         if (!use_partition()) {
+            const uint64_t max_windows = total_bases; // trivial bound on the batch's new keys
+            KTG_TRY(reserve(max_windows, [&]() -> int {
+                prof.begin("hll_reads", n_words * 32, stream);
+                if (rc) hll_reads_kernel<K, true><<<props.sms * 4, 256, 0, stream>>>(packed, nstart, n_words, k, (uint32_t *)b_hll.p);
+                else hll_reads_kernel<K, false><<<props.sms * 4, 256, 0, stream>>>(packed, nstart, n_words, k, (uint32_t *)b_hll.p);
+                prof.end(stream);
+                return KTG_OK;
+            }));
+        }
+        if (!use_partition()) { // still small after a possible grow: fused extract + insert
+            prof.begin("extract_insert", n_words * 32, stream);
             if (rc) {
                 int g = grid_for(extract_insert_kernel<K, true>, 256, 0, props);
                 g = (int)std::min<uint64_t>(g, (n_words + 255) / 256);
-                prof.begin("extract_insert", n_words * 32, stream);
                 extract_insert_kernel<K, true><<<g, 256, 0, stream>>>(packed, nstart, n_words, k, tab);
             }
             else {
                 int g = grid_for(extract_insert_kernel<K, false>, 256, 0, props);
                 g = (int)std::min<uint64_t>(g, (n_words + 255) / 256);
-                prof.begin("extract_insert", n_words * 32, stream);
                 extract_insert_kernel<K, false><<<g, 256, 0, stream>>>(packed, nstart, n_words, k, tab);
             }
             prof.end(stream);
         }
         else {
+            uint64_t n_keys = 0;
+            KTG_TRY(sized_hist([&]() -> int { return hist_reads_pass<false, true>(n_words, tab.n_sub); }, &n_keys));
+            KTG_TRY(scan_bins_pass(tab.n_sub));
             K *keys = nullptr;
-            KTG_TRY(partition_from_reads<false>(n_words, max_windows, tab.n_sub, &keys));
-            // the exact key count lives on the device (offsets[n_bins]); read it
-            // back: the insert grid does not depend on it, only the loop bound
-            unsigned long long n_keys = 0;
-            KTG_CUDA(cudaMemcpyAsync(&n_keys, offs_ptr(tab.n_sub) + tab.n_sub, 8, cudaMemcpyDeviceToHost, stream));
-            KTG_CUDA(cudaStreamSynchronize(stream));
+            KTG_TRY(scatter_reads_pass<false>(n_words, n_keys, tab.n_sub, &keys));
             KTG_TRY(launch_insert_keys(keys, n_keys));
         }
         KTG_CUDA(cudaGetLastError());
@@ -605,6 +640,22 @@ template <class K> struct Builder : BuilderBase {
         if (deferred_error != KTG_OK) return fail(deferred_error, "build is void after an earlier error");
         KTG_TRY(read_counters(nullptr, nullptr));
         KTG_TRY(drain_overflow());
+        return KTG_OK;
+    }
+
+    int reset() override {
+        prof.begin("init_table", tab.capacity() + 1, stream);
+        init_table_kernel<K><<<props.sms * 8, 256, 0, stream>>>(tab.slots, tab.capacity() + 1);
+        prof.end(stream);
+        KTG_CUDA(cudaMemsetAsync(b_small.p, 0, 4096, stream));
+        KTG_CUDA(cudaMemsetAsync(b_hll.p, 0, HLL_M * 4, stream));
+        occupied_ub = 0;
+        hll_base = 0;
+        sketch_complete = true;
+        deferred_error = KTG_OK;
+        windows_inserted = 0;
+        nodes_valid = false;
+        KTG_CUDA(cudaGetLastError());
         return KTG_OK;
     }
 
@@ -765,12 +816,16 @@ template <class K> struct Builder : BuilderBase {
         if (n_reads == 0) return KTG_OK;
         uint64_t n_words = 0;
         KTG_TRY(pack(d_bases, d_offsets, n_reads, total_bases, &n_words));
-        K *keys = nullptr;
-        KTG_TRY(partition_from_reads<true>(n_words, total_bases, W, &keys));
+        KTG_TRY((hist_reads_pass<true, false>(n_words, W)));
         std::vector<unsigned long long> h(W);
         KTG_CUDA(cudaMemcpyAsync(h.data(), hist_ptr(), W * 8, cudaMemcpyDeviceToHost, stream));
         KTG_TRY(sync());
-        for (uint32_t i = 0; i < W; ++i) counts[i] = h[i];
+        uint64_t n_keys = 0;
+        for (uint32_t i = 0; i < W; ++i) n_keys += (counts[i] = h[i]);
+        KTG_TRY(scan_bins_pass(W));
+        K *keys = nullptr;
+        KTG_TRY(scatter_reads_pass<true>(n_words, n_keys, W, &keys));
+        KTG_TRY(sync()); // the caller hands the buffer to NCCL on its own stream
         *d_keys = keys;
         return KTG_OK;
     }
@@ -779,15 +834,20 @@ template <class K> struct Builder : BuilderBase {
         if (deferred_error != KTG_OK) return fail(deferred_error, "build is void after an earlier error");
         if (n == 0) return KTG_OK;
         const K *keys = (const K *)d_keys;
-        KTG_TRY(reserve(n, [&]() -> int {
-            prof.begin("hll_keys", n, stream);
-            hll_keys_kernel<K><<<props.sms * 4, 256, 0, stream>>>(keys, n, (uint32_t *)b_hll.p);
-            prof.end(stream);
-            return KTG_OK;
-        }));
+        if (!use_partition()) {
+            KTG_TRY(reserve(n, [&]() -> int {
+                prof.begin("hll_keys", n, stream);
+                hll_keys_kernel<K><<<props.sms * 4, 256, 0, stream>>>(keys, n, (uint32_t *)b_hll.p);
+                prof.end(stream);
+                return KTG_OK;
+            }));
+        }
         if (use_partition()) {
+            uint64_t n_keys = 0;
+            KTG_TRY(sized_hist([&]() -> int { return hist_keys_pass<true>(keys, n, tab.n_sub); }, &n_keys));
+            KTG_TRY(scan_bins_pass(tab.n_sub));
             K *sorted = nullptr;
-            KTG_TRY(partition_from_keys(keys, n, tab.n_sub, &sorted));
+            KTG_TRY(scatter_keys_pass(keys, n, tab.n_sub, &sorted));
             keys = sorted;
         }
         KTG_TRY(launch_insert_keys(keys, n));

@@ -292,13 +292,16 @@ __device__ __forceinline__ uint32_t bin_of(const Table<K> &t, K key) {
 }
 
 // histogram of bins over all windows of a packed batch
-template <class K, bool RC, bool BY_OWNER>
+// (with HLL the same pass also folds every key into the cardinality sketch: the
+// hash is already there, so sizing the table costs no extra pass)
+template <class K, bool RC, bool BY_OWNER, bool HLL>
 __global__ void __launch_bounds__(256)
 hist_reads_kernel(const uint64_t *__restrict__ packed, const uint8_t *__restrict__ nstart,
                   uint64_t n_words, uint32_t k, Table<K> t, uint32_t n_bins,
-                  unsigned long long *__restrict__ g_hist) {
-    extern __shared__ uint32_t sh_hist[];
-    for (uint32_t i = threadIdx.x; i < n_bins; i += blockDim.x) sh_hist[i] = 0;
+                  unsigned long long *__restrict__ g_hist, uint32_t *__restrict__ g_regs) {
+    extern __shared__ uint32_t sh_hist[]; // n_bins counters (+ HLL_M registers)
+    uint32_t *regs = sh_hist + n_bins;
+    for (uint32_t i = threadIdx.x; i < n_bins + (HLL ? HLL_M : 0); i += blockDim.x) sh_hist[i] = 0;
     __syncthreads();
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t n_round = (n_words + 31) & ~(uint64_t)31;
@@ -312,28 +315,42 @@ hist_reads_kernel(const uint64_t *__restrict__ packed, const uint8_t *__restrict
         r.init(w0, w1, w2, k);
         for (uint32_t j = 0; j < ns; ++j) {
             K key = (RC && r.rc < r.fw) ? r.rc : r.fw;
-            atomicAdd(&sh_hist[bin_of<K, BY_OWNER>(t, key)], 1u);
+            uint64_t h = KeyTraits<K>::hash(key);
+            Place p = place_of(h, t.world, t.n_sub, t.sub_mask);
+            atomicAdd(&sh_hist[BY_OWNER ? p.owner : p.part], 1u);
+            if (HLL) hll_update(regs, h);
             r.step();
         }
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < n_bins; i += blockDim.x)
         if (sh_hist[i]) atomicAdd(&g_hist[i], (unsigned long long)sh_hist[i]);
+    if (HLL)
+        for (uint32_t i = threadIdx.x; i < HLL_M; i += blockDim.x)
+            if (regs[i]) atomicMax(&g_regs[i], regs[i]);
 }
 
-template <class K, bool BY_OWNER>
+template <class K, bool BY_OWNER, bool HLL>
 __global__ void __launch_bounds__(256)
 hist_keys_kernel(const K *__restrict__ keys, uint64_t n, Table<K> t, uint32_t n_bins,
-                 unsigned long long *__restrict__ g_hist) {
+                 unsigned long long *__restrict__ g_hist, uint32_t *__restrict__ g_regs) {
     extern __shared__ uint32_t sh_hist[];
-    for (uint32_t i = threadIdx.x; i < n_bins; i += blockDim.x) sh_hist[i] = 0;
+    uint32_t *regs = sh_hist + n_bins;
+    for (uint32_t i = threadIdx.x; i < n_bins + (HLL ? HLL_M : 0); i += blockDim.x) sh_hist[i] = 0;
     __syncthreads();
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        atomicAdd(&sh_hist[bin_of<K, BY_OWNER>(t, keys[i])], 1u);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint64_t h = KeyTraits<K>::hash(keys[i]);
+        Place p = place_of(h, t.world, t.n_sub, t.sub_mask);
+        atomicAdd(&sh_hist[BY_OWNER ? p.owner : p.part], 1u);
+        if (HLL) hll_update(regs, h);
+    }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < n_bins; i += blockDim.x)
         if (sh_hist[i]) atomicAdd(&g_hist[i], (unsigned long long)sh_hist[i]);
+    if (HLL)
+        for (uint32_t i = threadIdx.x; i < HLL_M; i += blockDim.x)
+            if (regs[i]) atomicMax(&g_regs[i], regs[i]);
 }
 
 // exclusive scan of the bin histogram (n_bins <= a few thousand): one block
@@ -429,7 +446,7 @@ scatter_reads_kernel(const uint64_t *__restrict__ packed, const uint8_t *__restr
     uint16_t *s_bin = (uint16_t *)(s_keys + TK);             // TK bins
     uint32_t *s_cnt = (uint32_t *)(s_bin + TK);              // n_bins: count -> local cursor
     uint32_t *s_loc = s_cnt + n_bins;                        // n_bins: local start
-    unsigned long long *s_glob = (unsigned long long *)(s_loc + n_bins + (n_bins & 1)); // n_bins
+    unsigned long long *s_glob = (unsigned long long *)(s_loc + n_bins); // n_bins
     const uint64_t n_tiles = (n_words + TW - 1) / TW;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (uint32_t i = threadIdx.x; i < n_bins; i += TW) s_cnt[i] = 0;
@@ -483,7 +500,7 @@ scatter_keys_kernel(const K *__restrict__ keys, uint64_t n, Table<K> t, uint32_t
     uint16_t *s_bin = (uint16_t *)(s_keys + TK);
     uint32_t *s_cnt = (uint32_t *)(s_bin + TK);
     uint32_t *s_loc = s_cnt + n_bins;
-    unsigned long long *s_glob = (unsigned long long *)(s_loc + n_bins + (n_bins & 1));
+    unsigned long long *s_glob = (unsigned long long *)(s_loc + n_bins);
     const uint64_t n_tiles = (n + TK - 1) / TK;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (uint32_t i = threadIdx.x; i < n_bins; i += NT) s_cnt[i] = 0;

@@ -179,6 +179,11 @@ int ktg_create_from_files(ktg_builder *b, const char *const *paths, uint32_t n_p
     return ktg_finalize(b);
 }
 
+int ktg_reset(ktg_builder *b) {
+    KTG_ENTER(b);
+    return b->impl->reset();
+}
+
 int ktg_finalize(ktg_builder *b) {
     KTG_ENTER(b);
     return b->impl->finalize();

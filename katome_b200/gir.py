@@ -179,6 +179,10 @@ class GpuGIR:
     def finalize(self):
         _check(self._L.ktg_finalize(self._h))
 
+    def reset(self):
+        """Back to `Default::default()` (builder.rs:145), keeping the device allocations."""
+        _check(self._L.ktg_reset(self._h))
+
     # ---- Stats (stats/collections.rs:170-208 and :137-168) -----------------------
     def counts(self) -> Tuple[int, int]:
         n, e = C.c_uint64(0), C.c_uint64(0)

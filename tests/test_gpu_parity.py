@@ -195,14 +195,14 @@ def test_empty_and_minimal_inputs(K):
 
 def test_batches_accumulate_and_table_grows_without_a_hint(K):
     from oracle import oracle as O
-    G, L, k = 300_000, 100, 31
-    n = 12_000
+    G, L, k = 1_500_000, 100, 31
+    n = 40_000
     reads = O.synth_reads(0xABCDEF, G, L, 5000, 0, n)
     offsets = (np.arange(n + 1, dtype=np.uint64) * L)
     cpu = O.OracleGIR(k)
     cpu.add_reads(reads, offsets, True)
     g = K.GpuGIR(k, True, sub_table_log2_bytes=16)  # starts at 1 Mi slots, must grow + partition
-    step = 3000
+    step = 10_000
     for r0 in range(0, n, step):
         g.add_reads(reads[r0 * L:(r0 + step) * L], offsets[r0:r0 + step + 1] - offsets[r0])
     _assert_same(g, cpu, full_stats=True)
@@ -212,6 +212,10 @@ def test_batches_accumulate_and_table_grows_without_a_hint(K):
     g2 = K.GpuGIR(k, True, edges_count=cpu.counts()[1])
     g2.add_reads(reads, offsets)
     assert g2.digest() == cpu.digest() and g2.info()["grow_events"] == 0
+    g2.reset()
+    assert g2.counts() == (0, 0)
+    g2.add_reads(reads, offsets)
+    assert g2.digest() == cpu.digest()
     g.close(), g2.close()
 
 
