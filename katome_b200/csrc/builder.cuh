@@ -450,12 +450,19 @@ template <class K> struct Builder : BuilderBase {
         KTG_TRY(b_nstart.ensure(nw + 4));
         *n_words = nw;
         if (n_reads == 0) return KTG_OK;
-        int grid = grid_for(pack_reads_kernel, 256, 0, props);
-        uint64_t want = (n_reads * PACK_GROUP + 255) / 256;
-        if ((uint64_t)grid > want) grid = (int)want;
+        const uint64_t mean_len = total_bases / n_reads;
+        const int group = mean_len <= 128 ? 4 : (mean_len <= 256 ? 8 : 32);
+        auto launch = [&](auto kernel, int G) {
+            int grid = grid_for(kernel, 256, 0, props);
+            uint64_t want = (n_reads * G + 255) / 256;
+            if ((uint64_t)grid > want) grid = (int)want;
+            kernel<<<grid, 256, 0, stream>>>(d_bases, d_offsets, n_reads, k, (uint64_t *)b_packed.p,
+                                             (uint8_t *)b_nstart.p, d_ctr);
+        };
         prof.begin("pack_reads", total_bases, stream);
-        pack_reads_kernel<<<grid, 256, 0, stream>>>(d_bases, d_offsets, n_reads, k, (uint64_t *)b_packed.p,
-                                                    (uint8_t *)b_nstart.p, d_ctr);
+        if (group == 4) launch(pack_reads_kernel<4>, 4);
+        else if (group == 8) launch(pack_reads_kernel<8>, 8);
+        else launch(pack_reads_kernel<32>, 32);
         prof.end(stream);
         nodes_valid = false;
         return KTG_OK;
@@ -567,9 +574,10 @@ template <class K> struct Builder : BuilderBase {
     int launch_insert_keys(const K *keys, uint64_t n) {
         if (n == 0) return KTG_OK;
         int g = grid_for(insert_keys_kernel<K>, 256, 0, props);
-        g = (int)std::min<uint64_t>(g, (n + 255) / 256);
+        g = (int)std::min<uint64_t>(g, (n + 2047) / 2048);
+        KTG_CUDA(cudaMemsetAsync(d_scratch + 14, 0, 8, stream)); // the tile counter
         prof.begin("insert_keys", n, stream);
-        insert_keys_kernel<K><<<g, 256, 0, stream>>>(keys, n, k, rc && (k % 2 == 0), tab);
+        insert_keys_kernel<K><<<g, 256, 0, stream>>>(keys, n, k, rc && (k % 2 == 0), tab, d_scratch + 14);
         prof.end(stream);
         nodes_valid = false;
         return KTG_OK;

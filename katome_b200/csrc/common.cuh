@@ -72,6 +72,9 @@ template <> struct KeyTraits<uint64_t> {
     __device__ static __forceinline__ uint64_t load(const Slot *s) {
         return __ldcg((const unsigned long long *)&s->key);
     }
+    __device__ static __forceinline__ uint64_t load_stream(const uint64_t *p) { // read once
+        return __ldcs((const unsigned long long *)p);
+    }
     __device__ static __forceinline__ bool maybe_torn(uint64_t) { return false; }
     __device__ static __forceinline__ uint64_t cas(Slot *s, uint64_t cmp, uint64_t val) {
         return atomicCAS((unsigned long long *)&s->key, (unsigned long long)cmp,
@@ -100,6 +103,10 @@ template <> struct KeyTraits<u128> {
 #ifdef __CUDACC__
     __device__ static __forceinline__ u128 load(const Slot *s) {
         ulonglong2 v = __ldcg((const ulonglong2 *)s);
+        return ((u128)v.y << 64) | v.x;
+    }
+    __device__ static __forceinline__ u128 load_stream(const u128 *p) {
+        ulonglong2 v = __ldcs((const ulonglong2 *)p);
         return ((u128)v.y << 64) | v.x;
     }
     // A 16-byte vector load is one transaction in practice but is not promised

@@ -64,75 +64,76 @@ __device__ __forceinline__ uint32_t pack4(uint32_t x, bool &ok) {
     return (c * 0x40100401u) >> 24;
 }
 
-// 16 ASCII bases -> 32 bits; bases at index >= cnt are treated as 'A' and not validated
-__device__ __forceinline__ uint32_t pack16(u128 v, int cnt, bool &ok) {
-    uint32_t out = 0;
+// 32 bases starting at an arbitrary byte address -> one packed word.
+// Three aligned 16-byte loads cover the span; only blocks that hold a byte of
+// [p, p+cnt) are touched.  The byte offset inside the first block is removed
+// with selects (whole words) and funnel shifts (bytes), all on 32-bit registers.
+__device__ __forceinline__ uint64_t pack32_unaligned(const uint8_t *p, int cnt, bool &ok) {
+    const uint4 *a = (const uint4 *)((uintptr_t)p & ~(uintptr_t)15);
+    const uint32_t sh = (uint32_t)((uintptr_t)p & 15);
+    const int span = (int)sh + cnt; // bytes needed counted from a
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    uint4 v0 = __ldg(a);
+    uint4 v1 = span > 16 ? __ldg(a + 1) : z;
+    uint4 v2 = span > 32 ? __ldg(a + 2) : z;
+    uint32_t x[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+    if (sh & 8) {
+#pragma unroll
+        for (int i = 0; i < 10; ++i) x[i] = x[i + 2];
+    }
+    if (sh & 4) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) x[i] = x[i + 1];
+    }
+    const uint32_t bs = 8 * (sh & 3);
+    uint32_t y[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) y[i] = __funnelshift_r(x[i], x[i + 1], bs);
+    if (cnt < 32) { // tail word of a read: bases past the end count as 'A', unchecked
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            int nv = cnt - 4 * q;
+            if (nv < 4) {
+                uint32_t m = nv <= 0 ? 0u : ((1u << (8 * nv)) - 1u);
+                y[q] = (y[q] & m) | (0x41414141u & ~m);
+            }
+        }
+    }
+    uint32_t hi = 0, lo = 0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        uint32_t x = (uint32_t)(v >> (32 * q));
-        int nv = cnt - 4 * q;
-        if (nv < 4) {
-            uint32_t m = nv <= 0 ? 0u : ((1u << (8 * nv)) - 1u);
-            x = (x & m) | (0x41414141u & ~m);
-        }
-        out = (out << 8) | pack4(x, ok);
+        hi = (hi << 8) | pack4(y[q], ok);
+        lo = (lo << 8) | pack4(y[q + 4], ok);
     }
-    return out;
+    return ((uint64_t)hi << 32) | lo;
 }
 
-__device__ __forceinline__ u128 ld16(const uint8_t *p) {
-    uint4 v = __ldg((const uint4 *)p);
-    return ((u128)v.w << 96) | ((u128)v.z << 64) | ((u128)v.y << 32) | v.x;
-}
-
-// 32 bases starting at an arbitrary byte address -> one packed word.
-// Only 16-byte blocks that contain a byte of [p, p+cnt) are touched.
-__device__ __forceinline__ uint64_t pack32_unaligned(const uint8_t *p, int cnt, bool &ok) {
-    const uint8_t *a = (const uint8_t *)((uintptr_t)p & ~(uintptr_t)15);
-    int sh = (int)((uintptr_t)p & 15);
-    int span = sh + cnt; // bytes needed counted from a
-    u128 v0 = ld16(a);
-    u128 v1 = span > 16 ? ld16(a + 16) : (u128)0;
-    u128 v2 = span > 32 ? ld16(a + 32) : (u128)0;
-    u128 lo, hi;
-    if (sh == 0) {
-        lo = v0;
-        hi = v1;
-    }
-    else {
-        lo = (v0 >> (8 * sh)) | (v1 << (128 - 8 * sh));
-        hi = (v1 >> (8 * sh)) | (v2 << (128 - 8 * sh));
-    }
-    uint32_t a0 = pack16(lo, cnt, ok);
-    uint32_t a1 = pack16(hi, cnt - 16, ok);
-    return ((uint64_t)a0 << 32) | a1;
-}
-
-constexpr int PACK_GROUP = 8; // lanes cooperating on one read (256 bases / iteration)
-
+// GROUP lanes cooperate on one read (32 * GROUP bases per iteration); the host
+// picks GROUP from the mean read length so that short reads keep all lanes busy.
+template <int GROUP>
 __global__ void __launch_bounds__(256)
 pack_reads_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restrict__ offsets,
                   uint64_t n_reads, uint32_t k, uint64_t *__restrict__ packed,
                   uint8_t *__restrict__ nstart, PackCounters *ctr) {
-    const int lane = threadIdx.x & 31, gl = lane & (PACK_GROUP - 1);
-    const unsigned gmask = ((1u << PACK_GROUP) - 1u) << (lane & ~(PACK_GROUP - 1));
-    const uint64_t n_groups = (uint64_t)gridDim.x * blockDim.x / PACK_GROUP;
+    const int lane = threadIdx.x & 31, gl = lane & (GROUP - 1);
+    const unsigned gmask = GROUP == 32 ? 0xFFFFFFFFu : (((1u << (GROUP & 31)) - 1u) << (lane & ~(GROUP - 1)));
+    const uint64_t n_groups = (uint64_t)gridDim.x * blockDim.x / GROUP;
     const uint64_t off0 = offsets[0];
     uint64_t acc[4] = {0, 0, 0, 0};
-    for (uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / PACK_GROUP; r < n_reads;
+    for (uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / GROUP; r < n_reads;
          r += n_groups) {
         const uint64_t o0 = offsets[r], o1 = offsets[r + 1];
         const uint64_t len = o1 - o0;
         const uint64_t wbase = (o0 - off0) / 32 + r, wend = (o1 - off0) / 32 + r + 1;
         const uint64_t nwords = (len + 31) / 32;
         bool ok = true;
-        for (uint64_t j = gl; j < nwords; j += PACK_GROUP) {
+        for (uint64_t j = gl; j < nwords; j += GROUP) {
             uint64_t rem = len - 32 * j;
             packed[wbase + j] = pack32_unaligned(bases + o0 + 32 * j, rem < 32 ? (int)rem : 32, ok);
         }
         const bool valid = __ballot_sync(gmask, !ok) == 0;
         const uint64_t nwin = (valid && len >= k) ? len - k + 1 : 0;
-        for (uint64_t j = gl; wbase + j < wend; j += PACK_GROUP) {
+        for (uint64_t j = gl; wbase + j < wend; j += GROUP) {
             uint64_t s = nwin > 32 * j ? nwin - 32 * j : 0;
             nstart[wbase + j] = (uint8_t)(s < 32 ? s : 32);
         }
@@ -539,17 +540,40 @@ scatter_keys_kernel(const K *__restrict__ keys, uint64_t n, Table<K> t, uint32_t
 }
 
 // K3 over an array of canonical keys (partitioned locally or received from
-// peers).  Keys arrive grouped by sub-table, so concurrently running CTAs work
-// on one L2-resident slice of the table.
+// peers).  Keys arrive grouped by sub-table.  Tiles are handed out through a
+// global counter (persistent CTAs, dynamic scheduling) instead of a static
+// grid-stride: with a static split the SMs drift apart over the ~1000
+// iterations (near/far L2 latency differs per SM), the in-flight keys end up
+// spread over many sub-tables and the working set falls out of L2 (ncu: 27 GB
+// of DRAM reads for 322 M inserts).  With the counter every CTA works at the
+// global frontier, i.e. on the one or two sub-tables that are L2 resident.
+constexpr int INSERT_TILE_PER_THREAD = 8;
 template <class K>
 __global__ void __launch_bounds__(256)
 insert_keys_kernel(const K *__restrict__ keys, uint64_t n, uint32_t k, bool check_palindrome,
-                   Table<K> t) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        K key = keys[i];
-        uint32_t inc = (check_palindrome && revcomp(key, k) == key) ? 2u : 1u;
-        table_add(t, key, inc);
+                   Table<K> t, unsigned long long *tile_counter) {
+    constexpr uint64_t TILE = 256 * INSERT_TILE_PER_THREAD;
+    __shared__ unsigned long long s_tile;
+    for (;;) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1ull);
+        __syncthreads();
+        const uint64_t base = s_tile * TILE;
+        __syncthreads();
+        if (base >= n) break;
+        K my[INSERT_TILE_PER_THREAD];
+#pragma unroll
+        for (int q = 0; q < INSERT_TILE_PER_THREAD; ++q) {
+            uint64_t i = base + q * 256 + threadIdx.x;
+            my[q] = i < n ? KeyTraits<K>::load_stream(&keys[i]) : KeyTraits<K>::empty(); // read once: evict first
+        }
+#pragma unroll
+        for (int q = 0; q < INSERT_TILE_PER_THREAD; ++q) {
+            uint64_t i = base + q * 256 + threadIdx.x;
+            if (i < n) {
+                uint32_t inc = (check_palindrome && revcomp(my[q], k) == my[q]) ? 2u : 1u;
+                table_add(t, my[q], inc);
+            }
+        }
     }
 }
 
