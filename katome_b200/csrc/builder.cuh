@@ -204,6 +204,7 @@ template <class K> struct Builder : BuilderBase {
     uint64_t hll_base = 0;    // exact occupancy when the sketch was (re)started
     bool sketch_complete = true; // the sketch covers every key inserted since hll_base
     DeviceBuf b_hll;
+    DeviceBuf b_spill;
     DeviceBuf b_packed, b_nstart, b_keys, b_keys2, b_hist, b_ovf_keys, b_ovf_inc, b_small;
     PackCounters *d_ctr = nullptr;        // accumulates over the whole build
     unsigned long long *d_ovf_count = nullptr;
@@ -217,7 +218,7 @@ template <class K> struct Builder : BuilderBase {
         if (stream) cudaStreamSynchronize(stream);
         if (tab.slots) cudaFree(tab.slots);
         b_packed.release(); b_nstart.release(); b_keys.release(); b_keys2.release();
-        b_hist.release(); b_hll.release(); b_ovf_keys.release(); b_ovf_inc.release(); b_small.release();
+        b_hist.release(); b_hll.release(); b_spill.release(); b_ovf_keys.release(); b_ovf_inc.release(); b_small.release();
         if (copy_stream) cudaStreamDestroy(copy_stream);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
@@ -246,7 +247,7 @@ template <class K> struct Builder : BuilderBase {
 
     int alloc_table(uint64_t need_slots, Table<K> *out) {
         Table<K> t = tab;
-        uint32_t slb = cfg.sub_table_log2_bytes ? cfg.sub_table_log2_bytes : 24;
+        uint32_t slb = cfg.sub_table_log2_bytes ? cfg.sub_table_log2_bytes : 25;
         geometry(need_slots, slb, &t.n_sub, &t.sub_log2);
         t.sub_mask = (uint32_t)((1ull << t.sub_log2) - 1);
         t.max_probe = (uint32_t)std::min<uint64_t>(1ull << t.sub_log2, 2048);
@@ -304,22 +305,19 @@ template <class K> struct Builder : BuilderBase {
         return KTG_OK;
     }
 
-    size_t scatter_reads_smem(uint32_t n_bins) const {
-        return (size_t)ScatterCfg<K>::TILE_KEYS * (sizeof(K) + 2) + (size_t)(n_bins + (n_bins & 1)) * 8 +
-               (size_t)n_bins * 8;
-    }
-    size_t scatter_keys_smem(uint32_t n_bins) const {
-        return (size_t)4096 * (sizeof(K) + 2) + (size_t)(n_bins + (n_bins & 1)) * 8 + (size_t)n_bins * 8;
+    template <class F> static void allow_smem(F kernel, size_t bytes) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     }
     void set_smem_attrs() {
-        int mx = (int)scatter_reads_smem(MAX_BINS);
-        cudaFuncSetAttribute(scatter_reads_kernel<K, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-        cudaFuncSetAttribute(scatter_reads_kernel<K, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-        cudaFuncSetAttribute(scatter_reads_kernel<K, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-        cudaFuncSetAttribute(scatter_reads_kernel<K, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-        int mk = (int)scatter_keys_smem(MAX_BINS);
-        cudaFuncSetAttribute(scatter_keys_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mk);
-        cudaFuncSetAttribute(scatter_keys_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mk);
+        const size_t mx = ScatterSmem<K>::bytes(MAX_BINS, true);
+        allow_smem(scatter_reads_kernel<K, true, false, true>, mx);
+        allow_smem(scatter_reads_kernel<K, false, false, true>, mx);
+        allow_smem(scatter_reads_kernel<K, true, false, false>, mx);
+        allow_smem(scatter_reads_kernel<K, false, false, false>, mx);
+        allow_smem(scatter_reads_kernel<K, true, true, false>, mx);
+        allow_smem(scatter_reads_kernel<K, false, true, false>, mx);
+        allow_smem(scatter_keys_kernel<K, false, true>, mx);
+        allow_smem(scatter_keys_kernel<K, false, false>, mx);
     }
 
     bool use_partition() const {
@@ -402,7 +400,7 @@ template <class K> struct Builder : BuilderBase {
         }
         double e = (0.7213 / (1.0 + 1.079 / m)) * m * m / sum;
         if (e <= 2.5 * m && zeros) e = m * log(m / (double)zeros);
-        *est = e;
+        *est = e * HLL_SAMPLE; // only 1/HLL_SAMPLE of the hash space is sketched
         return KTG_OK;
     }
 
@@ -443,13 +441,23 @@ template <class K> struct Builder : BuilderBase {
     }
 
     // ---- K1 ------------------------------------------------------------------------
+    // Packs the batch and returns what the extraction kernels need to know about it:
+    // the exact number of windows and whether all reads share one length.
+    struct Batch {
+        uint64_t n_words = 0, windows = 0;
+        ItemMap im{};
+    };
+    uint64_t windows_seen = 0; // cumulative PackCounters::windows already accounted for
+
     int pack(const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t n_reads,
-             uint64_t total_bases, uint64_t *n_words) {
+             uint64_t total_bases, Batch *bt) {
         uint64_t nw = total_bases / 32 + n_reads;
         KTG_TRY(b_packed.ensure((nw + 4) * 8));
         KTG_TRY(b_nstart.ensure(nw + 4));
-        *n_words = nw;
-        if (n_reads == 0) return KTG_OK;
+        bt->n_words = nw;
+        // per-batch min/max read length
+        KTG_CUDA(cudaMemsetAsync(&d_ctr->min_len, 0xFF, 8, stream));
+        KTG_CUDA(cudaMemsetAsync(&d_ctr->max_len, 0, 8, stream));
         const uint64_t mean_len = total_bases / n_reads;
         const int group = mean_len <= 128 ? 4 : (mean_len <= 256 ? 8 : 32);
         auto launch = [&](auto kernel, int G) {
@@ -465,89 +473,128 @@ template <class K> struct Builder : BuilderBase {
         else launch(pack_reads_kernel<32>, 32);
         prof.end(stream);
         nodes_valid = false;
+        PackCounters c;
+        KTG_CUDA(cudaMemcpyAsync(&c, d_ctr, sizeof c, cudaMemcpyDeviceToHost, stream));
+        KTG_TRY(sync());
+        bt->windows = c.windows - windows_seen;
+        windows_seen = c.windows;
+        if (c.short_reads) { // hm_gir.rs:40: the reference panics, the build is void
+            deferred_error = KTG_ERR_SHORT_READ;
+            return fail(KTG_ERR_SHORT_READ, "Read is too short!");
+        }
+        bt->im = ItemMap{0, 0, nw * ITEMS_PER_WORD};
+        if (c.min_len == c.max_len) { // every read has the same length: closed-form item map
+            const uint32_t L = (uint32_t)c.max_len;
+            const uint32_t ipr = L >= k ? (L - k + 1 + GRAN - 1) / GRAN : 0;
+            bt->im = ItemMap{L, ipr, n_reads * ipr};
+        }
         return KTG_OK;
     }
 
     // ---- partition helpers ----------------------------------------------------------
-    // b_hist layout: hist[n_bins] | offsets[n_bins + 1] | cursors[n_bins]
+    // b_hist layout: hist[n_bins] | offsets[n_bins + 1] | cursors[n_bins] | spill cursor
     unsigned long long *hist_ptr() { return (unsigned long long *)b_hist.p; }
     unsigned long long *offs_ptr(uint32_t n_bins) { return hist_ptr() + n_bins; }
     unsigned long long *curs_ptr(uint32_t n_bins) { return hist_ptr() + 2 * n_bins + 1; }
+    unsigned long long *spill_ptr(uint32_t n_bins) { return hist_ptr() + 3 * n_bins + 1; }
+    int ensure_hist(uint32_t n_bins) { return b_hist.ensure((3 * (size_t)n_bins + 4) * 8); }
 
-    // bin histogram of the packed batch (optionally folding the keys into the sketch)
-    template <bool BY_OWNER, bool HLL> int hist_reads_pass(uint64_t n_words, uint32_t n_bins) {
-        KTG_TRY(b_hist.ensure((3 * (size_t)n_bins + 2) * 8));
-        KTG_CUDA(cudaMemsetAsync(b_hist.p, 0, n_bins * 8, stream));
-        const uint64_t *packed = (const uint64_t *)b_packed.p;
-        const uint8_t *nstart = (const uint8_t *)b_nstart.p;
-        size_t hs = ((size_t)n_bins + (HLL ? HLL_M : 0)) * 4;
-        prof.begin("hist_reads", n_words * 32, stream);
-        if (rc) {
-            int g = grid_for(hist_reads_kernel<K, true, BY_OWNER, HLL>, 256, hs, props);
-            hist_reads_kernel<K, true, BY_OWNER, HLL><<<g, 256, hs, stream>>>(packed, nstart, n_words, k, tab, n_bins, hist_ptr(), (uint32_t *)b_hll.p);
-        }
-        else {
-            int g = grid_for(hist_reads_kernel<K, false, BY_OWNER, HLL>, 256, hs, props);
-            hist_reads_kernel<K, false, BY_OWNER, HLL><<<g, 256, hs, stream>>>(packed, nstart, n_words, k, tab, n_bins, hist_ptr(), (uint32_t *)b_hll.p);
-        }
-        prof.end(stream);
-        return KTG_OK;
+    static uint64_t bucket_cap_for(uint64_t n_keys, uint32_t n_bins) {
+        uint64_t mean = (n_keys + n_bins - 1) / n_bins;
+        uint64_t slack = std::max<uint64_t>(4096, (uint64_t)(10.0 * sqrt((double)mean)) + mean / 64);
+        uint64_t cap = mean + slack;
+        return (cap + INSERT_TILE - 1) / INSERT_TILE * INSERT_TILE;
     }
 
-    int scan_bins_pass(uint32_t n_bins) {
+    int scan_bins_pass(uint32_t n_bins, uint64_t bucket_cap) {
         prof.begin("scan_bins", n_bins, stream);
-        scan_bins_kernel<<<1, 1024, 0, stream>>>(hist_ptr(), n_bins, offs_ptr(n_bins), curs_ptr(n_bins));
+        scan_bins_kernel<<<1, 1024, 0, stream>>>(hist_ptr(), n_bins, bucket_cap, offs_ptr(n_bins), curs_ptr(n_bins));
         prof.end(stream);
+        KTG_CUDA(cudaMemsetAsync(spill_ptr(n_bins), 0, 8, stream));
         return KTG_OK;
     }
 
-    template <bool BY_OWNER> int scatter_reads_pass(uint64_t n_words, uint64_t n_keys, uint32_t n_bins, K **out) {
-        KTG_TRY(b_keys.ensure(n_keys * sizeof(K) + 16));
+    template <bool BY_OWNER> int hist_reads_pass(const Batch &bt, uint32_t n_bins) {
+        KTG_TRY(ensure_hist(n_bins));
+        KTG_CUDA(cudaMemsetAsync(b_hist.p, 0, n_bins * 8, stream));
         const uint64_t *packed = (const uint64_t *)b_packed.p;
         const uint8_t *nstart = (const uint8_t *)b_nstart.p;
-        size_t ss = scatter_reads_smem(n_bins);
-        constexpr int TW = ScatterCfg<K>::TILE_WORDS;
-        uint64_t n_tiles = (n_words + TW - 1) / TW;
-        prof.begin("scatter_reads", n_words * 32, stream);
+        size_t hs = (size_t)n_bins * 4;
+        prof.begin("hist_reads", bt.windows, stream);
         if (rc) {
-            int g = (int)std::min<uint64_t>(grid_for(scatter_reads_kernel<K, true, BY_OWNER>, TW, ss, props), n_tiles);
-            scatter_reads_kernel<K, true, BY_OWNER><<<g, TW, ss, stream>>>(packed, nstart, n_words, k, tab, n_bins, curs_ptr(n_bins), (K *)b_keys.p);
+            int g = grid_for(hist_reads_kernel<K, true, BY_OWNER, false>, 256, hs, props);
+            hist_reads_kernel<K, true, BY_OWNER, false><<<g, 256, hs, stream>>>(packed, nstart, bt.n_words, k, bt.im, tab, n_bins, hist_ptr(), nullptr);
         }
         else {
-            int g = (int)std::min<uint64_t>(grid_for(scatter_reads_kernel<K, false, BY_OWNER>, TW, ss, props), n_tiles);
-            scatter_reads_kernel<K, false, BY_OWNER><<<g, TW, ss, stream>>>(packed, nstart, n_words, k, tab, n_bins, curs_ptr(n_bins), (K *)b_keys.p);
+            int g = grid_for(hist_reads_kernel<K, false, BY_OWNER, false>, 256, hs, props);
+            hist_reads_kernel<K, false, BY_OWNER, false><<<g, 256, hs, stream>>>(packed, nstart, bt.n_words, k, bt.im, tab, n_bins, hist_ptr(), nullptr);
         }
         prof.end(stream);
-        *out = (K *)b_keys.p;
         return KTG_OK;
     }
 
-    template <bool HLL> int hist_keys_pass(const K *keys, uint64_t n, uint32_t n_bins) {
-        KTG_TRY(b_hist.ensure((3 * (size_t)n_bins + 2) * 8));
-        KTG_CUDA(cudaMemsetAsync(b_hist.p, 0, n_bins * 8, stream));
-        size_t hs = ((size_t)n_bins + (HLL ? HLL_M : 0)) * 4;
-        int g = grid_for(hist_keys_kernel<K, false, HLL>, 256, hs, props);
-        prof.begin("hist_keys", n, stream);
-        hist_keys_kernel<K, false, HLL><<<g, 256, hs, stream>>>(keys, n, tab, n_bins, hist_ptr(), (uint32_t *)b_hll.p);
+    ScatterOut scatter_out(uint32_t n_bins, uint64_t bucket_cap, void *out, void *spill, uint64_t spill_cap) {
+        ScatterOut o;
+        o.cursors = curs_ptr(n_bins);
+        o.bucket_cap = bucket_cap;
+        o.out = out;
+        o.spill_out = spill;
+        o.spill_cursor = spill_ptr(n_bins);
+        o.spill_cap = spill_cap;
+        return o;
+    }
+
+    template <bool BY_OWNER, bool HLL>
+    int scatter_reads_pass(const Batch &bt, uint32_t n_bins, const ScatterOut &o) {
+        const uint64_t *packed = (const uint64_t *)b_packed.p;
+        const uint8_t *nstart = (const uint8_t *)b_nstart.p;
+        size_t ss = ScatterSmem<K>::bytes(n_bins, HLL);
+        uint64_t n_tiles = std::max<uint64_t>(1, (bt.im.n_items + SCATTER_THREADS - 1) / SCATTER_THREADS);
+        prof.begin("scatter_reads", bt.windows, stream);
+        if (rc) {
+            int g = (int)std::min<uint64_t>(grid_for(scatter_reads_kernel<K, true, BY_OWNER, HLL>, SCATTER_THREADS, ss, props), n_tiles);
+            scatter_reads_kernel<K, true, BY_OWNER, HLL><<<g, SCATTER_THREADS, ss, stream>>>(packed, nstart, bt.n_words, k, bt.im, tab, n_bins, o, (uint32_t *)b_hll.p);
+        }
+        else {
+            int g = (int)std::min<uint64_t>(grid_for(scatter_reads_kernel<K, false, BY_OWNER, HLL>, SCATTER_THREADS, ss, props), n_tiles);
+            scatter_reads_kernel<K, false, BY_OWNER, HLL><<<g, SCATTER_THREADS, ss, stream>>>(packed, nstart, bt.n_words, k, bt.im, tab, n_bins, o, (uint32_t *)b_hll.p);
+        }
         prof.end(stream);
         return KTG_OK;
     }
 
-    int scatter_keys_pass(const K *keys, uint64_t n, uint32_t n_bins, K **out) {
-        KTG_TRY(b_keys2.ensure(n * sizeof(K) + 16));
-        size_t ss = scatter_keys_smem(n_bins);
-        uint64_t n_tiles = (n + 4095) / 4096;
-        int g2 = (int)std::min<uint64_t>(grid_for(scatter_keys_kernel<K, false>, 256, ss, props), std::max<uint64_t>(n_tiles, 1));
+    template <bool HLL> int scatter_keys_pass(const K *keys, uint64_t n, uint32_t n_bins, const ScatterOut &o) {
+        size_t ss = ScatterSmem<K>::bytes(n_bins, HLL);
+        uint64_t n_tiles = std::max<uint64_t>(1, (n + SCATTER_TILE - 1) / SCATTER_TILE);
+        int g = (int)std::min<uint64_t>(grid_for(scatter_keys_kernel<K, false, HLL>, SCATTER_THREADS, ss, props), n_tiles);
         prof.begin("scatter_keys", n, stream);
-        scatter_keys_kernel<K, false><<<g2, 256, ss, stream>>>(keys, n, tab, n_bins, curs_ptr(n_bins), (K *)b_keys2.p);
+        scatter_keys_kernel<K, false, HLL><<<g, SCATTER_THREADS, ss, stream>>>(keys, n, tab, n_bins, o, (uint32_t *)b_hll.p);
         prof.end(stream);
-        *out = (K *)b_keys2.p;
         return KTG_OK;
     }
 
-    // Partitioned insert, sizing the table from the sketch that the histogram pass
-    // fills for free.  `hist` runs the histogram (+sketch) for the current geometry.
-    template <class H> int sized_hist(H hist, uint64_t *n_keys) {
+    // flat (dense) or bucketed insert
+    int launch_insert(const K *keys, uint64_t n, const unsigned long long *bin_end, uint64_t bucket_cap,
+                      uint32_t n_bins) {
+        uint64_t tiles_per_bin = bin_end ? bucket_cap / INSERT_TILE : 0;
+        uint64_t n_tiles = bin_end ? tiles_per_bin * n_bins : (n + INSERT_TILE - 1) / INSERT_TILE;
+        if (n_tiles == 0) return KTG_OK;
+        int g = grid_for(insert_keys_kernel<K>, 256, 0, props);
+        g = (int)std::min<uint64_t>(g, n_tiles);
+        KTG_CUDA(cudaMemsetAsync(d_scratch + 14, 0, 8, stream)); // the tile counter
+        prof.begin("insert_keys", n, stream);
+        insert_keys_kernel<K><<<g, 256, 0, stream>>>(keys, n, k, rc && (k % 2 == 0), tab, d_scratch + 14, bin_end,
+                                                      bucket_cap, tiles_per_bin, n_tiles);
+        prof.end(stream);
+        nodes_valid = false;
+        return KTG_OK;
+    }
+    int launch_insert_keys(const K *keys, uint64_t n) { return launch_insert(keys, n, nullptr, 0, 0); }
+
+    // One-pass partition by sub-table + insert.  `scatter(o)` runs the scatter kernel
+    // (which also feeds the cardinality sketch) for the current table geometry;
+    // `n_keys` is the exact number of keys it will emit.
+    template <class S> int partitioned_insert(uint64_t n_keys, S scatter) {
         if (!sketch_complete) { // keys went in unsketched (direct path): restart from the exact count
             uint64_t exact = 0;
             KTG_TRY(count_occupied(&exact));
@@ -556,31 +603,30 @@ template <class K> struct Builder : BuilderBase {
             KTG_CUDA(cudaMemsetAsync(b_hll.p, 0, HLL_M * 4, stream));
         }
         for (int attempt = 0;; ++attempt) {
-            KTG_TRY(hist());
-            std::vector<unsigned long long> h(tab.n_sub);
-            KTG_CUDA(cudaMemcpyAsync(h.data(), hist_ptr(), tab.n_sub * 8, cudaMemcpyDeviceToHost, stream));
+            const uint32_t n_bins = tab.n_sub;
+            const uint64_t cap = bucket_cap_for(n_keys, n_bins);
+            const uint64_t spill_cap = std::max<uint64_t>(1u << 20, n_keys / 32);
+            KTG_TRY(ensure_hist(n_bins));
+            KTG_TRY(b_keys.ensure(cap * n_bins * sizeof(K) + 64));
+            KTG_TRY(b_spill.ensure(spill_cap * sizeof(K) + 64));
+            KTG_TRY(scan_bins_pass(n_bins, cap));
+            ScatterOut o = scatter_out(n_bins, cap, b_keys.p, b_spill.p, spill_cap);
+            KTG_TRY(scatter(n_bins, o));
+            unsigned long long spilled = 0;
+            KTG_CUDA(cudaMemcpyAsync(&spilled, spill_ptr(n_bins), 8, cudaMemcpyDeviceToHost, stream));
             double est = 0;
             KTG_TRY(hll_estimate(&est)); // synchronises the stream
-            uint64_t total = 0;
-            for (unsigned long long v : h) total += v;
-            *n_keys = total;
             uint64_t distinct = hll_base + (uint64_t)(est * 1.08) + 64;
             occupied_ub = distinct;
-            if ((double)distinct <= LOAD_MAX * (double)tab.capacity() || attempt >= 2) return KTG_OK;
-            KTG_TRY(grow_to((uint64_t)((double)distinct / LOAD_TARGET) + 1)); // geometry changed: redo
+            if ((double)distinct > LOAD_MAX * (double)tab.capacity() && attempt < 2) {
+                KTG_TRY(grow_to((uint64_t)((double)distinct / LOAD_TARGET) + 1)); // geometry changed: redo
+                continue;
+            }
+            if (spilled > spill_cap) return KTG_ERR_TABLE_FULL + 1000; // caller falls back to the exact path
+            KTG_TRY(launch_insert((const K *)b_keys.p, n_keys, curs_ptr(n_bins), cap, n_bins));
+            if (spilled) KTG_TRY(launch_insert_keys((const K *)b_spill.p, spilled));
+            return KTG_OK;
         }
-    }
-
-    int launch_insert_keys(const K *keys, uint64_t n) {
-        if (n == 0) return KTG_OK;
-        int g = grid_for(insert_keys_kernel<K>, 256, 0, props);
-        g = (int)std::min<uint64_t>(g, (n + 2047) / 2048);
-        KTG_CUDA(cudaMemsetAsync(d_scratch + 14, 0, 8, stream)); // the tile counter
-        prof.begin("insert_keys", n, stream);
-        insert_keys_kernel<K><<<g, 256, 0, stream>>>(keys, n, k, rc && (k % 2 == 0), tab, d_scratch + 14);
-        prof.end(stream);
-        nodes_valid = false;
-        return KTG_OK;
     }
 
     // ---- one batch of reads, all on the device ---------------------------------------
@@ -590,41 +636,47 @@ template <class K> struct Builder : BuilderBase {
         if (tab.world > 1)
             return fail(KTG_ERR_INVALID, "world_size > 1: use ktg_partition_reads_device + ktg_insert_keys_device");
         if (n_reads == 0) return KTG_OK;
-        uint64_t n_words = 0;
-        KTG_TRY(pack(d_bases, d_offsets, n_reads, total_bases, &n_words));
+        Batch bt;
+        KTG_TRY(pack(d_bases, d_offsets, n_reads, total_bases, &bt));
+        if (bt.windows == 0) return KTG_OK;
         const uint64_t *packed = (const uint64_t *)b_packed.p;
         const uint8_t *nstart = (const uint8_t *)b_nstart.p;
         if (!use_partition()) {
-            const uint64_t max_windows = total_bases; // trivial bound on the batch's new keys
-            KTG_TRY(reserve(max_windows, [&]() -> int {
-                prof.begin("hll_reads", n_words * 32, stream);
-                if (rc) hll_reads_kernel<K, true><<<props.sms * 4, 256, 0, stream>>>(packed, nstart, n_words, k, (uint32_t *)b_hll.p);
-                else hll_reads_kernel<K, false><<<props.sms * 4, 256, 0, stream>>>(packed, nstart, n_words, k, (uint32_t *)b_hll.p);
+            KTG_TRY(reserve(bt.windows, [&]() -> int {
+                prof.begin("hll_reads", bt.windows, stream);
+                if (rc) hll_reads_kernel<K, true><<<props.sms * 4, 256, 0, stream>>>(packed, nstart, bt.n_words, k, bt.im, (uint32_t *)b_hll.p);
+                else hll_reads_kernel<K, false><<<props.sms * 4, 256, 0, stream>>>(packed, nstart, bt.n_words, k, bt.im, (uint32_t *)b_hll.p);
                 prof.end(stream);
                 return KTG_OK;
             }));
         }
         if (!use_partition()) { // still small after a possible grow: fused extract + insert
-            prof.begin("extract_insert", n_words * 32, stream);
+            prof.begin("extract_insert", bt.windows, stream);
             if (rc) {
                 int g = grid_for(extract_insert_kernel<K, true>, 256, 0, props);
-                g = (int)std::min<uint64_t>(g, (n_words + 255) / 256);
-                extract_insert_kernel<K, true><<<g, 256, 0, stream>>>(packed, nstart, n_words, k, tab);
+                g = (int)std::min<uint64_t>(g, (bt.n_words + 255) / 256);
+                extract_insert_kernel<K, true><<<g, 256, 0, stream>>>(packed, nstart, bt.n_words, k, tab);
             }
             else {
                 int g = grid_for(extract_insert_kernel<K, false>, 256, 0, props);
-                g = (int)std::min<uint64_t>(g, (n_words + 255) / 256);
-                extract_insert_kernel<K, false><<<g, 256, 0, stream>>>(packed, nstart, n_words, k, tab);
+                g = (int)std::min<uint64_t>(g, (bt.n_words + 255) / 256);
+                extract_insert_kernel<K, false><<<g, 256, 0, stream>>>(packed, nstart, bt.n_words, k, tab);
             }
             prof.end(stream);
         }
         else {
-            uint64_t n_keys = 0;
-            KTG_TRY(sized_hist([&]() -> int { return hist_reads_pass<false, true>(n_words, tab.n_sub); }, &n_keys));
-            KTG_TRY(scan_bins_pass(tab.n_sub));
-            K *keys = nullptr;
-            KTG_TRY(scatter_reads_pass<false>(n_words, n_keys, tab.n_sub, &keys));
-            KTG_TRY(launch_insert_keys(keys, n_keys));
+            int st = partitioned_insert(bt.windows, [&](uint32_t n_bins, const ScatterOut &o) -> int {
+                return scatter_reads_pass<false, true>(bt, n_bins, o);
+            });
+            if (st == KTG_ERR_TABLE_FULL + 1000) { // heavy skew: exact two-pass partition
+                const uint32_t n_bins = tab.n_sub;
+                KTG_TRY(hist_reads_pass<false>(bt, n_bins));
+                KTG_TRY(scan_bins_pass(n_bins, 0));
+                KTG_TRY(b_keys.ensure(bt.windows * sizeof(K) + 64));
+                KTG_TRY((scatter_reads_pass<false, false>(bt, n_bins, scatter_out(n_bins, 0, b_keys.p, nullptr, 0))));
+                KTG_TRY(launch_insert_keys((const K *)b_keys.p, bt.windows));
+            }
+            else KTG_TRY(st);
         }
         KTG_CUDA(cudaGetLastError());
         return KTG_OK;
@@ -662,6 +714,7 @@ template <class K> struct Builder : BuilderBase {
         sketch_complete = true;
         deferred_error = KTG_OK;
         windows_inserted = 0;
+        windows_seen = 0;
         nodes_valid = false;
         KTG_CUDA(cudaGetLastError());
         return KTG_OK;
@@ -822,19 +875,19 @@ template <class K> struct Builder : BuilderBase {
         for (uint32_t i = 0; i < W; ++i) counts[i] = 0;
         *d_keys = nullptr;
         if (n_reads == 0) return KTG_OK;
-        uint64_t n_words = 0;
-        KTG_TRY(pack(d_bases, d_offsets, n_reads, total_bases, &n_words));
-        KTG_TRY((hist_reads_pass<true, false>(n_words, W)));
+        Batch bt;
+        KTG_TRY(pack(d_bases, d_offsets, n_reads, total_bases, &bt));
+        if (bt.windows == 0) return KTG_OK;
+        // NCCL wants dense per-destination ranges: exact two-pass partition by owner
+        KTG_TRY(hist_reads_pass<true>(bt, W));
+        KTG_TRY(scan_bins_pass(W, 0));
+        KTG_TRY(b_keys.ensure(bt.windows * sizeof(K) + 64));
+        KTG_TRY((scatter_reads_pass<true, false>(bt, W, scatter_out(W, 0, b_keys.p, nullptr, 0))));
         std::vector<unsigned long long> h(W);
         KTG_CUDA(cudaMemcpyAsync(h.data(), hist_ptr(), W * 8, cudaMemcpyDeviceToHost, stream));
-        KTG_TRY(sync());
-        uint64_t n_keys = 0;
-        for (uint32_t i = 0; i < W; ++i) n_keys += (counts[i] = h[i]);
-        KTG_TRY(scan_bins_pass(W));
-        K *keys = nullptr;
-        KTG_TRY(scatter_reads_pass<true>(n_words, n_keys, W, &keys));
         KTG_TRY(sync()); // the caller hands the buffer to NCCL on its own stream
-        *d_keys = keys;
+        for (uint32_t i = 0; i < W; ++i) counts[i] = h[i];
+        *d_keys = b_keys.p;
         return KTG_OK;
     }
 
@@ -850,15 +903,21 @@ template <class K> struct Builder : BuilderBase {
                 return KTG_OK;
             }));
         }
-        if (use_partition()) {
-            uint64_t n_keys = 0;
-            KTG_TRY(sized_hist([&]() -> int { return hist_keys_pass<true>(keys, n, tab.n_sub); }, &n_keys));
-            KTG_TRY(scan_bins_pass(tab.n_sub));
-            K *sorted = nullptr;
-            KTG_TRY(scatter_keys_pass(keys, n, tab.n_sub, &sorted));
-            keys = sorted;
+        if (!use_partition()) {
+            KTG_TRY(launch_insert_keys(keys, n));
         }
-        KTG_TRY(launch_insert_keys(keys, n));
+        else {
+            if (keys == (const K *)b_keys.p) { // scatter output must not alias its input
+                KTG_TRY(b_keys2.ensure(n * sizeof(K) + 64));
+                KTG_CUDA(cudaMemcpyAsync(b_keys2.p, keys, n * sizeof(K), cudaMemcpyDeviceToDevice, stream));
+                keys = (const K *)b_keys2.p;
+            }
+            int st = partitioned_insert(n, [&](uint32_t n_bins, const ScatterOut &o) -> int {
+                return scatter_keys_pass<true>(keys, n, n_bins, o);
+            });
+            if (st == KTG_ERR_TABLE_FULL + 1000) KTG_TRY(launch_insert_keys(keys, n)); // skewed: no locality, still exact
+            else KTG_TRY(st);
+        }
         KTG_CUDA(cudaGetLastError());
         return KTG_OK;
     }

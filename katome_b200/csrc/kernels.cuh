@@ -54,6 +54,7 @@ __device__ __forceinline__ void block_accumulate(const uint64_t (&v)[N], unsigne
 // is all the extraction kernels need to know about read boundaries.
 struct PackCounters {
     unsigned long long accepted_reads, accepted_bytes, windows, short_reads;
+    unsigned long long min_len, max_len; // over ALL reads of the build (valid or not)
 };
 
 // four ASCII bases (little endian: first base in the low byte) -> 8 bits, MSB first
@@ -120,10 +121,13 @@ pack_reads_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restrict_
     const uint64_t n_groups = (uint64_t)gridDim.x * blockDim.x / GROUP;
     const uint64_t off0 = offsets[0];
     uint64_t acc[4] = {0, 0, 0, 0};
+    uint64_t lmin = ~0ull, lmax = 0;
     for (uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / GROUP; r < n_reads;
          r += n_groups) {
         const uint64_t o0 = offsets[r], o1 = offsets[r + 1];
         const uint64_t len = o1 - o0;
+        lmin = len < lmin ? len : lmin;
+        lmax = len > lmax ? len : lmax;
         const uint64_t wbase = (o0 - off0) / 32 + r, wend = (o1 - off0) / 32 + r + 1;
         const uint64_t nwords = (len + 31) / 32;
         bool ok = true;
@@ -145,6 +149,12 @@ pack_reads_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restrict_
         }
     }
     block_accumulate<4>(acc, (unsigned long long *)ctr);
+    lmax = warp_max(lmax);
+    lmin = ~warp_max(~lmin);
+    if ((threadIdx.x & 31) == 0) {
+        if (lmax) atomicMax(&ctr->max_len, (unsigned long long)lmax);
+        atomicMin(&ctr->min_len, (unsigned long long)lmin);
+    }
 }
 
 // =================================================================== K2 core
@@ -226,15 +236,18 @@ extract_insert_kernel(const uint64_t *__restrict__ packed, const uint8_t *__rest
 }
 
 // ============================================================ cardinality
-// HyperLogLog sketch (2^12 registers) of the keys of a batch, merged into a
-// persistent sketch with atomicMax.  The host sizes / grows the table from the
-// estimate, so no capacity hint is needed (create_fastq starts from
+// HyperLogLog sketch (2^12 registers) of the keys offered to the table, merged
+// into a persistent sketch with atomicMax.  The host sizes / grows the table
+// from the estimate, so no capacity hint is needed (create_fastq starts from
 // T::default(), builder.rs:145) and no pessimistic "every window is new" bound
-// is used.  Register index and rank come from a re-mixed hash so they are
-// independent of the bits that place the key in the table.
-constexpr uint32_t HLL_P = 12, HLL_M = 1u << HLL_P;
+// is used.  Only keys whose hash falls in a fixed 1/8 of the hash space are
+// sketched (consistent for duplicates, so distinct(sample) * 8 estimates
+// distinct(all)); the sampled keys are re-mixed so that register index and rank
+// are independent of the bits that place the key in the table.
+constexpr uint32_t HLL_P = 12, HLL_M = 1u << HLL_P, HLL_SAMPLE = 8;
 
 __device__ __forceinline__ void hll_update(uint32_t *regs, uint64_t h) {
+    if (((uint32_t)h >> 29) != 0) return; // lo32 bits 29..31: above every slot index we use
     uint64_t g = fmix64(h ^ 0x9E3779B97F4A7C15ull);
     uint32_t idx = (uint32_t)(g >> (64 - HLL_P));
     uint64_t rest = g << HLL_P;
@@ -242,27 +255,100 @@ __device__ __forceinline__ void hll_update(uint32_t *regs, uint64_t h) {
     if (regs[idx] < rank) atomicMax(&regs[idx], rank);
 }
 
+// ================================================================ work items
+// The extraction kernels that feed the partitioner split every packed word
+// into 4 work items of 8 window starts (instead of one lane per word with up
+// to 32 windows): a 100 bp read has 70 windows = 32+32+6+0 per word, i.e. 55 %
+// lane utilisation per word but 97 % per 8-window item.  A warp covers 8
+// consecutive words; lanes 0..9 load them (+2 for the k-1 overlap) once and
+// every lane picks its three words with warp shuffles.
+constexpr int GRAN = 8, ITEMS_PER_WORD = 32 / GRAN;
+
+// When every read of the batch has the same length L (the usual case for
+// short-read sequencers; the pack kernel reports min/max length) items are
+// enumerated in closed form instead -- read r = item / ipr, granule u = item % ipr
+// with ipr = ceil((L-k+1)/8) -- so that no lane is handed an empty item.
+struct ItemMap {
+    uint32_t ulen; // 0: ragged batch, map items through nstart
+    uint32_t ipr;  // items per read (uniform batches)
+    uint64_t n_items;
+};
+
+template <class K> struct ItemWindows {
+    Roller<K> r;
+    uint32_t nwin;
+    // all 32 lanes of the warp must call this with consecutive items
+    __device__ __forceinline__ void load(const uint64_t *__restrict__ packed,
+                                         const uint8_t *__restrict__ nstart, uint64_t n_words,
+                                         uint64_t item, uint32_t k, const ItemMap &m) {
+        uint64_t w0, w1, w2;
+        uint32_t g;
+        if (m.ulen) {
+            uint64_t rd;
+            uint32_t u;
+            if (m.n_items <= 0xFFFFFFFFull) {
+                rd = (uint32_t)item / m.ipr;
+                u = (uint32_t)item - (uint32_t)rd * m.ipr;
+            }
+            else {
+                rd = item / m.ipr;
+                u = (uint32_t)(item - rd * m.ipr);
+            }
+            const bool in = item < m.n_items;
+            const uint64_t wb = (rd * m.ulen) / 32 + rd; // first packed word of read rd
+            const uint64_t w = wb + (GRAN * u) / 32;
+            g = u % ITEMS_PER_WORD;
+            const uint32_t total = m.ulen - k + 1, done = GRAN * u;
+            nwin = (in && nstart[wb] != 0) ? (total - done < GRAN ? total - done : GRAN) : 0;
+            w0 = in ? packed[w] : 0;
+            w1 = in ? packed[w + 1] : 0; // the batch buffer is padded by 4 words
+            w2 = (in && sizeof(K) == 16) ? packed[w + 2] : 0;
+        }
+        else {
+            const int lane = threadIdx.x & 31;
+            const uint64_t warp_word = (item - lane) / ITEMS_PER_WORD; // first word of the warp
+            const uint64_t lw = warp_word + lane;
+            uint64_t v = (lane < 8 + 2 && lw < n_words) ? packed[lw] : 0;
+            const int src = lane / ITEMS_PER_WORD;
+            w0 = __shfl_sync(0xFFFFFFFFu, v, src);
+            w1 = __shfl_sync(0xFFFFFFFFu, v, src + 1);
+            w2 = __shfl_sync(0xFFFFFFFFu, v, src + 2);
+            const uint64_t w = item / ITEMS_PER_WORD;
+            g = (uint32_t)(item % ITEMS_PER_WORD);
+            const uint32_t ns = w < n_words ? nstart[w] : 0;
+            nwin = ns > GRAN * g ? (ns - GRAN * g < GRAN ? ns - GRAN * g : GRAN) : 0;
+        }
+        if (g) { // start at base 8g of the word: shift the 96-base span left
+            const uint32_t sh = 2 * GRAN * g;
+            w0 = (w0 << sh) | (w1 >> (64 - sh));
+            w1 = (w1 << sh) | (w2 >> (64 - sh));
+            w2 <<= sh;
+        }
+        r.init(w0, w1, w2, k);
+    }
+    template <bool RC> __device__ __forceinline__ K key() const {
+        return (RC && r.rc < r.fw) ? r.rc : r.fw;
+    }
+};
+
+// stand-alone sketch passes for the direct (unpartitioned) path, only run when
+// the trivial bound cannot prove that the batch fits
 template <class K, bool RC>
 __global__ void __launch_bounds__(256)
 hll_reads_kernel(const uint64_t *__restrict__ packed, const uint8_t *__restrict__ nstart,
-                 uint64_t n_words, uint32_t k, uint32_t *__restrict__ g_regs) {
+                 uint64_t n_words, uint32_t k, ItemMap im, uint32_t *__restrict__ g_regs) {
     __shared__ uint32_t regs[HLL_M];
     for (uint32_t i = threadIdx.x; i < HLL_M; i += blockDim.x) regs[i] = 0;
     __syncthreads();
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t n_round = (n_words + 31) & ~(uint64_t)31;
-    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_round; w += stride) {
-        const bool in = w < n_words;
-        uint64_t w0 = in ? packed[w] : 0, w1, w2;
-        const uint32_t ns = in ? nstart[w] : 0;
-        neighbour_words(packed, w, n_words, w0, sizeof(K) == 16, w1, w2);
-        if (ns == 0) continue;
-        Roller<K> r;
-        r.init(w0, w1, w2, k);
-        for (uint32_t j = 0; j < ns; ++j) {
-            K key = (RC && r.rc < r.fw) ? r.rc : r.fw;
-            hll_update(regs, KeyTraits<K>::hash(key));
-            r.step();
+    const uint64_t n_items = (im.n_items + 31) & ~(uint64_t)31;
+    for (uint64_t it = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; it < n_items; it += stride) {
+        ItemWindows<K> iw;
+        iw.load(packed, nstart, n_words, it, k, im);
+#pragma unroll
+        for (int j = 0; j < GRAN; ++j) {
+            if (j < (int)iw.nwin) hll_update(regs, KeyTraits<K>::hash(iw.template key<RC>()));
+            iw.r.step();
         }
     }
     __syncthreads();
@@ -285,42 +371,32 @@ hll_keys_kernel(const K *__restrict__ keys, uint64_t n, uint32_t *__restrict__ g
 }
 
 // ================================================================ partition
-// bin of a key: its owner rank (multi-GPU exchange) or its sub-table
-template <class K, bool BY_OWNER>
-__device__ __forceinline__ uint32_t bin_of(const Table<K> &t, K key) {
-    Place p = place_of(KeyTraits<K>::hash(key), t.world, t.n_sub, t.sub_mask);
-    return BY_OWNER ? p.owner : p.part;
-}
-
-// histogram of bins over all windows of a packed batch
-// (with HLL the same pass also folds every key into the cardinality sketch: the
-// hash is already there, so sizing the table costs no extra pass)
+// bin of a key: its owner rank (multi-GPU exchange) or its sub-table.
+// histogram of bins over all windows of a packed batch (exact two-pass mode);
+// with HLL the same pass also folds the keys into the cardinality sketch.
 template <class K, bool RC, bool BY_OWNER, bool HLL>
 __global__ void __launch_bounds__(256)
 hist_reads_kernel(const uint64_t *__restrict__ packed, const uint8_t *__restrict__ nstart,
-                  uint64_t n_words, uint32_t k, Table<K> t, uint32_t n_bins,
+                  uint64_t n_words, uint32_t k, ItemMap im, Table<K> t, uint32_t n_bins,
                   unsigned long long *__restrict__ g_hist, uint32_t *__restrict__ g_regs) {
     extern __shared__ uint32_t sh_hist[]; // n_bins counters (+ HLL_M registers)
     uint32_t *regs = sh_hist + n_bins;
     for (uint32_t i = threadIdx.x; i < n_bins + (HLL ? HLL_M : 0); i += blockDim.x) sh_hist[i] = 0;
     __syncthreads();
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t n_round = (n_words + 31) & ~(uint64_t)31;
-    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_round; w += stride) {
-        const bool in = w < n_words;
-        uint64_t w0 = in ? packed[w] : 0, w1, w2;
-        const uint32_t ns = in ? nstart[w] : 0;
-        neighbour_words(packed, w, n_words, w0, sizeof(K) == 16, w1, w2);
-        if (ns == 0) continue;
-        Roller<K> r;
-        r.init(w0, w1, w2, k);
-        for (uint32_t j = 0; j < ns; ++j) {
-            K key = (RC && r.rc < r.fw) ? r.rc : r.fw;
-            uint64_t h = KeyTraits<K>::hash(key);
-            Place p = place_of(h, t.world, t.n_sub, t.sub_mask);
-            atomicAdd(&sh_hist[BY_OWNER ? p.owner : p.part], 1u);
-            if (HLL) hll_update(regs, h);
-            r.step();
+    const uint64_t n_items = (im.n_items + 31) & ~(uint64_t)31;
+    for (uint64_t it = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; it < n_items; it += stride) {
+        ItemWindows<K> iw;
+        iw.load(packed, nstart, n_words, it, k, im);
+#pragma unroll
+        for (int j = 0; j < GRAN; ++j) {
+            if (j < (int)iw.nwin) {
+                uint64_t h = KeyTraits<K>::hash(iw.template key<RC>());
+                Place p = place_of(h, t.world, t.n_sub, t.sub_mask);
+                atomicAdd(&sh_hist[BY_OWNER ? p.owner : p.part], 1u);
+                if (HLL) hll_update(regs, h);
+            }
+            iw.r.step();
         }
     }
     __syncthreads();
@@ -354,11 +430,21 @@ hist_keys_kernel(const K *__restrict__ keys, uint64_t n, Table<K> t, uint32_t n_
             if (regs[i]) atomicMax(&g_regs[i], regs[i]);
 }
 
-// exclusive scan of the bin histogram (n_bins <= a few thousand): one block
+// exclusive scan of the bin histogram (n_bins <= a few thousand): one block.
+// bucket_cap == 0: cursors = exclusive prefix of hist (exact mode);
+// bucket_cap  > 0: cursors = bin * bucket_cap (one-pass mode, hist unused).
 __global__ void scan_bins_kernel(const unsigned long long *__restrict__ hist, uint32_t n_bins,
+                                 unsigned long long bucket_cap,
                                  unsigned long long *__restrict__ offsets,
                                  unsigned long long *__restrict__ cursors) {
     __shared__ unsigned long long part[1024];
+    if (bucket_cap) {
+        for (uint32_t i = threadIdx.x; i <= n_bins; i += blockDim.x) {
+            offsets[i] = (unsigned long long)i * bucket_cap;
+            if (i < n_bins) cursors[i] = (unsigned long long)i * bucket_cap;
+        }
+        return;
+    }
     const uint32_t per = (n_bins + blockDim.x - 1) / blockDim.x;
     const uint32_t b0 = threadIdx.x * per;
     unsigned long long s = 0;
@@ -383,159 +469,211 @@ __global__ void scan_bins_kernel(const unsigned long long *__restrict__ hist, ui
     if (threadIdx.x == blockDim.x - 1) offsets[n_bins] = run;
 }
 
-// Block-wide exclusive scan of the per-bin counts of one tile.  On return
-// s_loc[b] = tile-local start of bin b, s_cnt[b] = the same (it becomes the
-// local write cursor) and s_glob[b] = the range reserved in HBM for (tile, b)
-// with ONE atomicAdd.  Returns the number of keys in the tile.
-template <int NT>
-__device__ __forceinline__ uint32_t bin_scan_reserve(uint32_t *s_cnt, uint32_t *s_loc,
-                                                     unsigned long long *s_glob,
-                                                     unsigned long long *__restrict__ cursors,
-                                                     uint32_t n_bins) {
-    __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_total;
-    const uint32_t per = (n_bins + NT - 1) / NT;
-    const uint32_t b0 = threadIdx.x * per;
-    uint32_t s = 0;
-    for (uint32_t i = b0; i < b0 + per && i < n_bins; ++i) s += s_cnt[i];
-    uint32_t incl = s;
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t x = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-        if ((threadIdx.x & 31) >= o) incl += x;
-    }
-    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        uint32_t v = threadIdx.x < NT / 32 ? s_warp[threadIdx.x] : 0, iv = v;
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t x = __shfl_up_sync(0xFFFFFFFFu, iv, o);
-            if (threadIdx.x >= o) iv += x;
-        }
-        s_warp[threadIdx.x] = iv - v;
-        if (threadIdx.x == 31) s_total = iv;
-    }
-    __syncthreads();
-    uint32_t run = s_warp[threadIdx.x >> 5] + incl - s;
-    for (uint32_t i = b0; i < b0 + per && i < n_bins; ++i) {
-        uint32_t c = s_cnt[i];
-        s_loc[i] = run;
-        s_cnt[i] = run;
-        if (c) s_glob[i] = atomicAdd(&cursors[i], (unsigned long long)c);
-        run += c;
-    }
-    __syncthreads();
-    return s_total;
-}
+// ---- tile-local counting sort in shared memory, then coalesced runs to HBM.
+// A CTA bins up to SCATTER_TILE keys in shared memory and reserves one
+// contiguous range per (tile, bin) with a single atomicAdd on the bin's
+// cursor, so HBM sees runs instead of scattered 8-byte stores.
+// Two modes share the code:
+//   exact    (bucket_cap == 0): cursors start at the exclusive prefix of a
+//            histogram pass; bins are dense and contiguous.
+//   one-pass (bucket_cap  > 0): bin b owns [b*cap, (b+1)*cap); no histogram
+//            pass.  Keys that do not fit (hash skew / heavy hitters) spill to
+//            an overflow array that the host inserts separately; nothing is
+//            ever dropped silently (the host checks the spill counter).
+constexpr int SCATTER_THREADS = 256, SCATTER_PER = 8, SCATTER_TILE = SCATTER_THREADS * SCATTER_PER;
 
-// Tile-local counting sort in shared memory, then coalesced runs to HBM.
-// One CTA takes TILE_WORDS packed words (<= 32*TILE_WORDS keys), bins them in
-// shared memory and reserves one contiguous range per (tile, bin) with a
-// single atomicAdd, so HBM sees runs instead of scattered 8-byte stores.
-template <class K> struct ScatterCfg {
-    static constexpr int TILE_WORDS = sizeof(K) == 8 ? 256 : 128;
-    static constexpr int TILE_KEYS = TILE_WORDS * 32;
+template <class K> struct ScatterSmem {
+    K *keys;                  // SCATTER_TILE
+    uint16_t *bin;            // SCATTER_TILE
+    uint32_t *cnt, *loc;      // n_bins each
+    unsigned long long *glob; // n_bins: reserved start in the bin's HBM range
+    unsigned long long *spill; // n_bins: reserved start in the overflow array
+    uint32_t *regs;           // HLL_M (only with HLL)
+    __device__ __forceinline__ void carve(unsigned char *base, uint32_t n_bins) {
+        keys = (K *)base;
+        bin = (uint16_t *)(keys + SCATTER_TILE);
+        cnt = (uint32_t *)(bin + SCATTER_TILE);
+        loc = cnt + n_bins;
+        glob = (unsigned long long *)(loc + n_bins); // 2*n_bins u32: 8-byte aligned
+        spill = glob + n_bins;
+        regs = (uint32_t *)(spill + n_bins);
+    }
+    static size_t bytes(uint32_t n_bins, bool hll) {
+        return (size_t)SCATTER_TILE * (sizeof(K) + 2) + (size_t)n_bins * 24 + (hll ? HLL_M * 4 : 0);
+    }
 };
 
-template <class K, bool RC, bool BY_OWNER>
-__global__ void __launch_bounds__(ScatterCfg<K>::TILE_WORDS)
+struct ScatterOut {
+    unsigned long long *cursors;   // per bin
+    unsigned long long bucket_cap; // 0 = exact mode
+    void *out;                     // binned keys
+    void *spill_out;               // overflow keys (one-pass mode)
+    unsigned long long *spill_cursor;
+    unsigned long long spill_cap;
+};
+
+// precondition: sm.cnt zeroed and the block synchronised
+template <class K>
+__device__ __forceinline__ void tile_scatter(const K (&key)[SCATTER_PER],
+                                             const uint32_t (&bin)[SCATTER_PER], int nvalid,
+                                             ScatterSmem<K> &sm, uint32_t n_bins,
+                                             const ScatterOut &o) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_total;
+    uint32_t rank[SCATTER_PER];
+#pragma unroll
+    for (int j = 0; j < SCATTER_PER; ++j)
+        if (j < nvalid) rank[j] = atomicAdd(&sm.cnt[bin[j]], 1u);
+    __syncthreads();
+    // block-wide exclusive scan of the bin counts; reserve HBM ranges
+    {
+        const uint32_t per = (n_bins + SCATTER_THREADS - 1) / SCATTER_THREADS;
+        const uint32_t b0 = threadIdx.x * per;
+        uint32_t s = 0;
+        for (uint32_t i = b0; i < b0 + per && i < n_bins; ++i) s += sm.cnt[i];
+        uint32_t incl = s;
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t x = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if ((threadIdx.x & 31) >= d) incl += x;
+        }
+        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t v = threadIdx.x < SCATTER_THREADS / 32 ? s_warp[threadIdx.x] : 0, iv = v;
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t x = __shfl_up_sync(0xFFFFFFFFu, iv, d);
+                if (threadIdx.x >= d) iv += x;
+            }
+            s_warp[threadIdx.x] = iv - v;
+            if (threadIdx.x == 31) s_total = iv;
+        }
+        __syncthreads();
+        uint32_t run = s_warp[threadIdx.x >> 5] + incl - s;
+        for (uint32_t i = b0; i < b0 + per && i < n_bins; ++i) {
+            const uint32_t c = sm.cnt[i];
+            sm.loc[i] = run;
+            if (c) {
+                const unsigned long long base = atomicAdd(&o.cursors[i], (unsigned long long)c);
+                sm.glob[i] = base;
+                if (o.bucket_cap) {
+                    const unsigned long long lim = (unsigned long long)(i + 1) * o.bucket_cap;
+                    if (base + c > lim) {
+                        const unsigned long long over = base + c - (base > lim ? base : lim);
+                        sm.spill[i] = atomicAdd(o.spill_cursor, over);
+                    }
+                }
+            }
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < SCATTER_PER; ++j)
+        if (j < nvalid) {
+            const uint32_t pos = sm.loc[bin[j]] + rank[j];
+            sm.keys[pos] = key[j];
+            sm.bin[pos] = (uint16_t)bin[j];
+        }
+    __syncthreads();
+    const uint32_t total = s_total;
+    K *out = (K *)o.out;
+    for (uint32_t i = threadIdx.x; i < total; i += SCATTER_THREADS) {
+        const uint32_t b = sm.bin[i];
+        const unsigned long long dst = sm.glob[b] + (i - sm.loc[b]);
+        if (o.bucket_cap == 0) {
+            out[dst] = sm.keys[i];
+        }
+        else {
+            const unsigned long long lim = (unsigned long long)(b + 1) * o.bucket_cap;
+            if (dst < lim) out[dst] = sm.keys[i];
+            else {
+                const unsigned long long first = sm.glob[b] > lim ? sm.glob[b] : lim;
+                const unsigned long long so = sm.spill[b] + (dst - first);
+                if (so < o.spill_cap) ((K *)o.spill_out)[so] = sm.keys[i];
+            }
+        }
+    }
+    __syncthreads();
+}
+
+template <class K, bool RC, bool BY_OWNER, bool HLL>
+__global__ void __launch_bounds__(SCATTER_THREADS)
 scatter_reads_kernel(const uint64_t *__restrict__ packed, const uint8_t *__restrict__ nstart,
-                     uint64_t n_words, uint32_t k, Table<K> t, uint32_t n_bins,
-                     unsigned long long *__restrict__ cursors, K *__restrict__ out) {
-    constexpr int TW = ScatterCfg<K>::TILE_WORDS, TK = ScatterCfg<K>::TILE_KEYS;
+                     uint64_t n_words, uint32_t k, ItemMap im, Table<K> t, uint32_t n_bins,
+                     ScatterOut o, uint32_t *__restrict__ g_regs) {
     extern __shared__ __align__(16) unsigned char smem[];
-    K *s_keys = (K *)smem;                                   // TK keys
-    uint16_t *s_bin = (uint16_t *)(s_keys + TK);             // TK bins
-    uint32_t *s_cnt = (uint32_t *)(s_bin + TK);              // n_bins: count -> local cursor
-    uint32_t *s_loc = s_cnt + n_bins;                        // n_bins: local start
-    unsigned long long *s_glob = (unsigned long long *)(s_loc + n_bins); // n_bins
-    const uint64_t n_tiles = (n_words + TW - 1) / TW;
+    ScatterSmem<K> sm;
+    sm.carve(smem, n_bins);
+    if (HLL) {
+        for (uint32_t i = threadIdx.x; i < HLL_M; i += SCATTER_THREADS) sm.regs[i] = 0;
+    }
+    const uint64_t n_tiles = (im.n_items + SCATTER_THREADS - 1) / SCATTER_THREADS;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (uint32_t i = threadIdx.x; i < n_bins; i += TW) s_cnt[i] = 0;
+        for (uint32_t i = threadIdx.x; i < n_bins; i += SCATTER_THREADS) sm.cnt[i] = 0;
         __syncthreads();
-        const uint64_t w = tile * TW + threadIdx.x;
-        const bool in = w < n_words;
-        uint64_t w0 = in ? packed[w] : 0, w1, w2;
-        const uint32_t ns = in ? nstart[w] : 0;
-        neighbour_words(packed, w, n_words, w0, sizeof(K) == 16, w1, w2);
-        Roller<K> r;
-        // pass A: bin counts
-        if (ns) {
-            r.init(w0, w1, w2, k);
-            for (uint32_t j = 0; j < ns; ++j) {
-                K key = (RC && r.rc < r.fw) ? r.rc : r.fw;
-                atomicAdd(&s_cnt[bin_of<K, BY_OWNER>(t, key)], 1u);
-                r.step();
-            }
+        ItemWindows<K> iw;
+        iw.load(packed, nstart, n_words, tile * SCATTER_THREADS + threadIdx.x, k, im);
+        K key[SCATTER_PER];
+        uint32_t bin[SCATTER_PER];
+#pragma unroll
+        for (int j = 0; j < SCATTER_PER; ++j) {
+            key[j] = iw.template key<RC>();
+            uint64_t h = KeyTraits<K>::hash(key[j]);
+            Place p = place_of(h, t.world, t.n_sub, t.sub_mask);
+            bin[j] = BY_OWNER ? p.owner : p.part;
+            if (HLL && j < (int)iw.nwin) hll_update(sm.regs, h);
+            iw.r.step();
         }
+        tile_scatter<K>(key, bin, (int)iw.nwin, sm, n_bins, o);
+    }
+    if (HLL) {
         __syncthreads();
-        const uint32_t total = bin_scan_reserve<TW>(s_cnt, s_loc, s_glob, cursors, n_bins);
-        // pass B: recompute keys, place them bin-sorted in shared memory
-        if (ns) {
-            r.init(w0, w1, w2, k);
-            for (uint32_t j = 0; j < ns; ++j) {
-                K key = (RC && r.rc < r.fw) ? r.rc : r.fw;
-                uint32_t b = bin_of<K, BY_OWNER>(t, key);
-                uint32_t pos = atomicAdd(&s_cnt[b], 1u);
-                s_keys[pos] = key;
-                s_bin[pos] = (uint16_t)b;
-                r.step();
-            }
-        }
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < total; i += TW) {
-            uint32_t b = s_bin[i];
-            out[s_glob[b] + (i - s_loc[b])] = s_keys[i];
-        }
-        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < HLL_M; i += SCATTER_THREADS)
+            if (sm.regs[i]) atomicMax(&g_regs[i], sm.regs[i]);
     }
 }
 
 // same for an array of keys (receiver side of the multi-GPU exchange)
-template <class K, bool BY_OWNER>
-__global__ void __launch_bounds__(256)
+template <class K, bool BY_OWNER, bool HLL>
+__global__ void __launch_bounds__(SCATTER_THREADS)
 scatter_keys_kernel(const K *__restrict__ keys, uint64_t n, Table<K> t, uint32_t n_bins,
-                    unsigned long long *__restrict__ cursors, K *__restrict__ out) {
-    constexpr int TK = 4096, NT = 256;
+                    ScatterOut o, uint32_t *__restrict__ g_regs) {
     extern __shared__ __align__(16) unsigned char smem[];
-    K *s_keys = (K *)smem;
-    uint16_t *s_bin = (uint16_t *)(s_keys + TK);
-    uint32_t *s_cnt = (uint32_t *)(s_bin + TK);
-    uint32_t *s_loc = s_cnt + n_bins;
-    unsigned long long *s_glob = (unsigned long long *)(s_loc + n_bins);
-    const uint64_t n_tiles = (n + TK - 1) / TK;
+    ScatterSmem<K> sm;
+    sm.carve(smem, n_bins);
+    if (HLL) {
+        for (uint32_t i = threadIdx.x; i < HLL_M; i += SCATTER_THREADS) sm.regs[i] = 0;
+    }
+    const uint64_t n_tiles = (n + SCATTER_TILE - 1) / SCATTER_TILE;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (uint32_t i = threadIdx.x; i < n_bins; i += NT) s_cnt[i] = 0;
+        for (uint32_t i = threadIdx.x; i < n_bins; i += SCATTER_THREADS) sm.cnt[i] = 0;
         __syncthreads();
-        const uint64_t base = tile * TK;
-        const uint32_t cnt = (uint32_t)((n - base) < TK ? (n - base) : TK);
-        K my[TK / NT];
-        uint32_t mb[TK / NT];
+        const uint64_t base = tile * SCATTER_TILE;
+        K key[SCATTER_PER];
+        uint32_t bin[SCATTER_PER];
+        int nvalid = 0;
 #pragma unroll
-        for (int q = 0; q < TK / NT; ++q) {
-            uint32_t i = q * NT + threadIdx.x;
-            if (i < cnt) {
-                my[q] = keys[base + i];
-                mb[q] = bin_of<K, BY_OWNER>(t, my[q]);
-                atomicAdd(&s_cnt[mb[q]], 1u);
+        for (int j = 0; j < SCATTER_PER; ++j) {
+            const uint64_t i = base + (uint64_t)j * SCATTER_THREADS + threadIdx.x;
+            if (i < n) {
+                key[j] = KeyTraits<K>::load_stream(&keys[i]);
+                uint64_t h = KeyTraits<K>::hash(key[j]);
+                Place p = place_of(h, t.world, t.n_sub, t.sub_mask);
+                bin[j] = BY_OWNER ? p.owner : p.part;
+                if (HLL) hll_update(sm.regs, h);
+                nvalid = j + 1;
+            }
+            else {
+                key[j] = 0;
+                bin[j] = 0;
             }
         }
+        tile_scatter<K>(key, bin, nvalid, sm, n_bins, o);
+    }
+    if (HLL) {
         __syncthreads();
-        bin_scan_reserve<NT>(s_cnt, s_loc, s_glob, cursors, n_bins);
-#pragma unroll
-        for (int q = 0; q < TK / NT; ++q) {
-            uint32_t i = q * NT + threadIdx.x;
-            if (i < cnt) {
-                uint32_t pos = atomicAdd(&s_cnt[mb[q]], 1u);
-                s_keys[pos] = my[q];
-                s_bin[pos] = (uint16_t)mb[q];
-            }
-        }
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < cnt; i += NT) {
-            uint32_t b = s_bin[i];
-            out[s_glob[b] + (i - s_loc[b])] = s_keys[i];
-        }
-        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < HLL_M; i += SCATTER_THREADS)
+            if (sm.regs[i]) atomicMax(&g_regs[i], sm.regs[i]);
     }
 }
 
@@ -548,28 +686,45 @@ scatter_keys_kernel(const K *__restrict__ keys, uint64_t n, Table<K> t, uint32_t
 // of DRAM reads for 322 M inserts).  With the counter every CTA works at the
 // global frontier, i.e. on the one or two sub-tables that are L2 resident.
 constexpr int INSERT_TILE_PER_THREAD = 8;
+constexpr uint64_t INSERT_TILE = 256 * INSERT_TILE_PER_THREAD;
+// bin_end == nullptr: keys[0, n) is dense.  Otherwise bin b holds
+// keys[b*bucket_cap, min(bin_end[b], (b+1)*bucket_cap)) (one-pass partitioner)
+// and tile t covers bin t / tiles_per_bin, tile t % tiles_per_bin of that bin.
 template <class K>
 __global__ void __launch_bounds__(256)
 insert_keys_kernel(const K *__restrict__ keys, uint64_t n, uint32_t k, bool check_palindrome,
-                   Table<K> t, unsigned long long *tile_counter) {
-    constexpr uint64_t TILE = 256 * INSERT_TILE_PER_THREAD;
+                   Table<K> t, unsigned long long *tile_counter,
+                   const unsigned long long *__restrict__ bin_end, uint64_t bucket_cap,
+                   uint64_t tiles_per_bin, uint64_t n_tiles) {
     __shared__ unsigned long long s_tile;
     for (;;) {
         if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1ull);
         __syncthreads();
-        const uint64_t base = s_tile * TILE;
+        const uint64_t tile = s_tile;
         __syncthreads();
-        if (base >= n) break;
+        if (tile >= n_tiles) break;
+        uint64_t base, end;
+        if (bin_end) {
+            const uint64_t b = tile / tiles_per_bin;
+            const uint64_t lim = (b + 1) * bucket_cap, fill = bin_end[b];
+            base = b * bucket_cap + (tile % tiles_per_bin) * INSERT_TILE;
+            end = fill < lim ? fill : lim;
+        }
+        else {
+            base = tile * INSERT_TILE;
+            end = n;
+        }
+        if (base >= end) continue;
         K my[INSERT_TILE_PER_THREAD];
 #pragma unroll
         for (int q = 0; q < INSERT_TILE_PER_THREAD; ++q) {
             uint64_t i = base + q * 256 + threadIdx.x;
-            my[q] = i < n ? KeyTraits<K>::load_stream(&keys[i]) : KeyTraits<K>::empty(); // read once: evict first
+            my[q] = i < end ? KeyTraits<K>::load_stream(&keys[i]) : KeyTraits<K>::empty(); // read once
         }
 #pragma unroll
         for (int q = 0; q < INSERT_TILE_PER_THREAD; ++q) {
             uint64_t i = base + q * 256 + threadIdx.x;
-            if (i < n) {
+            if (i < end) {
                 uint32_t inc = (check_palindrome && revcomp(my[q], k) == my[q]) ? 2u : 1u;
                 table_add(t, my[q], inc);
             }
