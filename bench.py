@@ -185,6 +185,8 @@ def run_ours(args):
     info = builder.info()
     launches = info["kernel_launches"] - launches0 - 1  # info() itself launches one scan
     dig = digest()
+    # weight conservation: every window adds 1 to each strand (2 to a palindrome)
+    assert dig[2] == 2 * windows_total, (dig, windows_total)
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

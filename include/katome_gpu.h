@@ -59,7 +59,8 @@ typedef struct ktg_config {
                                      edges as the reference counts them; 0 = grow on demand */
     uint32_t world_size;         /* hash-sharding: this handle owns keys with */
     uint32_t rank;               /*   owner(key) == rank; 1/0 = single GPU     */
-    void *stream;                /* cudaStream_t to launch on; NULL = own stream */
+    void *stream;                /* cudaStream_t to launch on; NULL = own stream (pass
+                                    cudaStreamLegacy for the legacy default stream) */
     uint32_t sub_table_log2_bytes; /* 0 = default (L2-resident partition size) */
     uint32_t flags;              /* KTG_FLAG_* */
 } ktg_config;

@@ -81,7 +81,6 @@ class ShardedGIR:
             keys = torch.empty(0, dtype=torch.int64, device=self.device)
         recv, rcounts = exchange_keys(keys, counts, self.words, self.group)
         self.exchanged_bytes += (n - counts[self.rank]) * 8 * self.words
-        torch.cuda.current_stream().synchronize()
         self.gir.insert_keys_device(recv, sum(rcounts))
         self._keep = recv  # keep the receive buffer alive until the insert has run
 

@@ -77,14 +77,18 @@ class GpuGIR:
     """
 
     def __init__(self, k: int = 40, reverse_complement: bool = True, *, edges_count: Optional[int] = None,
-                 device: int = -1, stream: int = 0, world_size: int = 1, rank: int = 0,
+                 device: int = -1, stream: Optional[int] = None, world_size: int = 1, rank: int = 0,
                  profile: bool = False, force_direct: bool = False, force_partition: bool = False,
                  sub_table_log2_bytes: int = 0):
         self._L = L.lib()
         flags = (L.KTG_FLAG_PROFILE if profile else 0) | (L.KTG_FLAG_FORCE_DIRECT if force_direct else 0) | \
                 (L.KTG_FLAG_FORCE_PARTITION if force_partition else 0)
+        # stream=None: the handle creates its own stream.  A torch stream handle of 0 means the
+        # legacy default stream, which the C ABI spells cudaStreamLegacy (0x1), since NULL = "own".
+        if stream is not None and int(stream) == 0:
+            stream = 1
         cfg = L.KtgConfig(L.KTG_ABI_VERSION, int(k), int(bool(reverse_complement)), int(device),
-                          int(edges_count or 0), int(world_size), int(rank), C.c_void_p(stream or None),
+                          int(edges_count or 0), int(world_size), int(rank), C.c_void_p(stream),
                           int(sub_table_log2_bytes), flags)
         h = C.c_void_p()
         self._h = None
@@ -281,6 +285,7 @@ class GpuGIR:
 
 def synth_reads_device(d_out, seed_g: int, genome_len: int, read_len: int, err_ppm: int, r0: int, r1: int,
                        stream: int = 0):
+    """`stream` is a raw cudaStream_t handle (0 = the legacy default stream)."""
     _check(L.lib().ktg_synth_reads_device(_ptr(d_out), seed_g, genome_len, read_len, err_ppm, r0, r1,
                                           C.c_void_p(stream or None)))
 

@@ -1,0 +1,66 @@
+"""Host-side (numpy) mirror of the device key functions in csrc/common.cuh: canonical form,
+the 64-bit key hash and the owner rank of a k-mer.  Used by the host routing logic and its
+CPU tests; the insert path itself only exists on the GPU."""
+from __future__ import annotations
+
+import numpy as np
+
+M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+_SALT = np.uint64(0x6B61746F6D65)
+
+
+def fmix64(z: np.ndarray) -> np.ndarray:
+    z = np.asarray(z, dtype=np.uint64).copy()
+    with np.errstate(over="ignore"):
+        z ^= z >> np.uint64(30)
+        z *= np.uint64(0xBF58476D1CE4E5B9)
+        z ^= z >> np.uint64(27)
+        z *= np.uint64(0x94D049BB133111EB)
+        z ^= z >> np.uint64(31)
+    return z
+
+
+def _rev2(x: np.ndarray) -> np.ndarray:
+    """reverse the 32 two-bit symbols of every u64"""
+    x = np.asarray(x, dtype=np.uint64)
+    for sh, m in ((2, 0x3333333333333333), (4, 0x0F0F0F0F0F0F0F0F), (8, 0x00FF00FF00FF00FF),
+                  (16, 0x0000FFFF0000FFFF)):
+        x = ((x >> np.uint64(sh)) & np.uint64(m)) | ((x & np.uint64(m)) << np.uint64(sh))
+    return (x >> np.uint64(32)) | (x << np.uint64(32))
+
+
+def revcomp(hi: np.ndarray, lo: np.ndarray, k: int):
+    """reverse complement of k-mers given as (hi, lo) u64 pairs (hi = 0 for k <= 32)"""
+    hi = np.asarray(hi, dtype=np.uint64)
+    lo = np.asarray(lo, dtype=np.uint64)
+    if k <= 32:
+        return np.zeros_like(lo), _rev2(~lo) >> np.uint64(64 - 2 * k)
+    rhi, rlo = _rev2(~lo), _rev2(~hi)  # 128-bit value (rhi:rlo), to be shifted right by 128-2k
+    s = 128 - 2 * k
+    if s == 0:
+        return rhi, rlo
+    out_lo = (rlo >> np.uint64(s)) | (rhi << np.uint64(64 - s))
+    return rhi >> np.uint64(s), out_lo
+
+
+def canonical(hi, lo, k: int):
+    hi = np.asarray(hi, dtype=np.uint64)
+    lo = np.asarray(lo, dtype=np.uint64)
+    rhi, rlo = revcomp(hi, lo, k)
+    less = (rhi < hi) | ((rhi == hi) & (rlo < lo))
+    return np.where(less, rhi, hi), np.where(less, rlo, lo)
+
+
+def key_hash(hi, lo, k: int) -> np.ndarray:
+    lo = np.asarray(lo, dtype=np.uint64)
+    if k <= 32:
+        return fmix64(lo ^ _SALT)
+    return fmix64(lo ^ fmix64(np.asarray(hi, dtype=np.uint64) ^ _SALT))
+
+
+def owner_of(hi, lo, k: int, world: int, reverse_complement: bool = True) -> np.ndarray:
+    """owner rank = top 32 hash bits range-reduced to [0, world) (place_of in common.cuh)"""
+    if reverse_complement:
+        hi, lo = canonical(hi, lo, k)
+    h = key_hash(hi, lo, k)
+    return (((h >> np.uint64(32)) * np.uint64(world)) >> np.uint64(32)).astype(np.int64)

@@ -1,0 +1,64 @@
+"""Hash-sharded build over 2 real GPUs (NCCL): merged result == the oracle's table.
+Skipped on a one-GPU box; the same host logic is covered on CPU by tests/test_dist_cpu.py."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+from tests.helpers import ROOT
+
+pytestmark = pytest.mark.gpu
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, os.environ["KTG_ROOT"])
+import numpy as np, torch, torch.distributed as dist
+from katome_b200.dist import ShardedGIR
+from oracle import oracle as O
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+for k, n, L, G in ((31, 6000, 150, 200_000), (63, 3000, 150, 100_000)):
+    reads = O.synth_reads(99, G, L, 5000, 0, n)
+    cpu = O.OracleGIR(k)
+    cpu.add_reads(reads, np.arange(n + 1, dtype=np.uint64) * L, True)
+    half = n // world
+    mine = torch.from_numpy(reads[rank * half * L:(rank + 1) * half * L]).cuda()
+    offs = torch.arange(0, (half + 1) * L, L, dtype=torch.int64, device="cuda")
+    for kw in ({}, {"force_partition": True, "sub_table_log2_bytes": 16}):
+        sg = ShardedGIR(k, True, **kw)
+        for _ in range(2):  # reset + rebuild gives the same table
+            sg.reset()
+            sg.add_reads_device(mine[: (half // 2) * L], offs[: half // 2 + 1], half // 2, (half // 2) * L)
+            sg.add_reads_device(mine[(half // 2) * L:], offs[: half - half // 2 + 1], half - half // 2, (half - half // 2) * L)
+            sg.finalize()
+            assert sg.digest() == cpu.digest(), (rank, k, kw, sg.digest(), cpu.digest())
+        sg.remove_weak_edges(3)
+        cpu2 = O.OracleGIR(k)
+        cpu2.add_reads(reads, np.arange(n + 1, dtype=np.uint64) * L, True)
+        cpu2.remove_weak_edges(3)
+        assert sg.digest() == cpu2.digest()
+        sg.close()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_two_gpu_sharded_build_matches_oracle(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, KTG_ROOT=ROOT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("ok") == 2

@@ -297,6 +297,21 @@ def test_two_rank_sharding_on_one_gpu(K):
     assert ((d0[0] + d1[0]) & (2**64 - 1), d0[1] + d1[1], d0[2] + d1[2], max(d0[3], d1[3])) == cd
 
 
+def test_host_mirror_of_owner_matches_device(K):
+    from katome_b200 import hashing
+    rng = np.random.default_rng(9)
+    for k, W in ((31, 8), (40, 3), (64, 5)):
+        g = K.GpuGIR(k, True, world_size=W, rank=0)
+        lo = rng.integers(0, 2**63, 300, dtype=np.uint64)
+        hi = rng.integers(0, 2**(2 * k - 64) if k > 32 else 1, 300, dtype=np.uint64) if k > 32 else np.zeros(300, np.uint64)
+        if k <= 32:
+            lo &= np.uint64((1 << (2 * k)) - 1)
+        want = hashing.owner_of(hi, lo, k, W, True)
+        got = [g.owner_of(int(h), int(l)) for h, l in zip(hi.tolist(), lo.tolist())]
+        assert got == want.tolist()
+        g.close()
+
+
 def test_full_size_properties(K):
     """Size-independent properties on a run too large for the oracle: weight conservation,
     batch-split invariance, filter idempotence and monotonicity (BASELINE config 2 shape)."""
