@@ -68,6 +68,8 @@ typedef struct ktg_config {
 #define KTG_FLAG_PROFILE 1u      /* time every kernel launch with CUDA events */
 #define KTG_FLAG_FORCE_DIRECT 2u /* never use the partitioned insert */
 #define KTG_FLAG_FORCE_PARTITION 4u
+#define KTG_FLAG_FORCE_PAGES 8u  /* always partition twice + streaming page update */
+#define KTG_FLAG_NO_PAGES 16u    /* never use the page update (L2 atomics only) */
 
 int ktg_create(const ktg_config *cfg, ktg_builder **out);
 void ktg_destroy(ktg_builder *b);
@@ -185,6 +187,7 @@ typedef struct ktg_info {
     uint64_t windows_inserted;
     uint64_t kernel_launches;
     uint32_t grow_events, partitioned;
+    uint32_t page_updates, n_pages; /* batches inserted by the streaming page update */
 } ktg_info;
 int ktg_get_info(ktg_builder *b, ktg_info *out);
 

@@ -18,6 +18,7 @@ KTG_ABI_VERSION = 1
  KTG_ERR_TABLE_FULL, KTG_ERR_CUDA, KTG_ERR_INVALID, KTG_ERR_NO_DEVICE) = range(10)
 KTG_FASTQ, KTG_FASTA = 0, 1
 KTG_FLAG_PROFILE, KTG_FLAG_FORCE_DIRECT, KTG_FLAG_FORCE_PARTITION = 1, 2, 4
+KTG_FLAG_FORCE_PAGES, KTG_FLAG_NO_PAGES = 8, 16
 
 # every symbol include/katome_gpu.h declares
 SYMBOLS = (
@@ -55,7 +56,8 @@ class KtgInfo(C.Structure):
     _fields_ = [("capacity_slots", C.c_uint64), ("occupied_slots", C.c_uint64),
                 ("table_bytes", C.c_uint64), ("n_sub_tables", C.c_uint32), ("slot_bytes", C.c_uint32),
                 ("windows_inserted", C.c_uint64), ("kernel_launches", C.c_uint64),
-                ("grow_events", C.c_uint32), ("partitioned", C.c_uint32)]
+                ("grow_events", C.c_uint32), ("partitioned", C.c_uint32),
+                ("page_updates", C.c_uint32), ("n_pages", C.c_uint32)]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

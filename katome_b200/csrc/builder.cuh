@@ -148,6 +148,7 @@ struct DeviceProps {
 };
 
 constexpr uint32_t MAX_BINS = 2048;      // sub-tables (smem bins of the scatter kernel)
+constexpr uint32_t MAX_PAGES_PER_SUB = 2048; // smem bins of the level-2 scatter
 constexpr double LOAD_MAX = 0.70;        // grow before a batch could exceed this
 constexpr double LOAD_TARGET = 0.50;     // load right after sizing / growing
 constexpr uint64_t OVF_CAP = 1u << 20;   // replay buffer entries
@@ -200,15 +201,20 @@ template <class K> struct Builder : BuilderBase {
     typedef typename T::Slot Slot;
 
     Table<K> tab{};
+    bool fresh = true;        // the table is logically empty and its memory undefined (see ensure_init)
+    uint32_t page_updates = 0;
     uint64_t occupied_ub = 0; // upper bound on occupied slots
     uint64_t hll_base = 0;    // exact occupancy when the sketch was (re)started
     bool sketch_complete = true; // the sketch covers every key inserted since hll_base
     DeviceBuf b_hll;
     DeviceBuf b_spill;
     DeviceBuf b_packed, b_nstart, b_keys, b_keys2, b_hist, b_ovf_keys, b_ovf_inc, b_small;
+    DeviceBuf b_pkeys, b_pcur, b_pspill; // level-2 (page) buckets, their cursors, their spill list
     PackCounters *d_ctr = nullptr;        // accumulates over the whole build
     unsigned long long *d_ovf_count = nullptr;
     unsigned long long *d_scratch = nullptr; // 16 u64 of scratch (stats, cursors)
+    unsigned long long *d_lost = nullptr;    // keys dropped because a spill list overflowed (voids the build)
+    unsigned long long *d_page_spill = nullptr; // cursor of the page spill list
     // lazily built node ((k-1)-mer) table
     bool nodes_valid = false;
     NodeStats node_cache{};
@@ -219,6 +225,7 @@ template <class K> struct Builder : BuilderBase {
         if (tab.slots) cudaFree(tab.slots);
         b_packed.release(); b_nstart.release(); b_keys.release(); b_keys2.release();
         b_hist.release(); b_hll.release(); b_spill.release(); b_ovf_keys.release(); b_ovf_inc.release(); b_small.release();
+        b_pkeys.release(); b_pcur.release(); b_pspill.release();
         if (copy_stream) cudaStreamDestroy(copy_stream);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
@@ -245,12 +252,15 @@ template <class K> struct Builder : BuilderBase {
         *sub_log2 = sl;
     }
 
-    int alloc_table(uint64_t need_slots, Table<K> *out) {
+    // do_init == false leaves the memory undefined: the caller marks the table `fresh`
+    int alloc_table(uint64_t need_slots, Table<K> *out, bool do_init) {
         Table<K> t = tab;
-        uint32_t slb = cfg.sub_table_log2_bytes ? cfg.sub_table_log2_bytes : 25;
+        uint32_t slb = cfg.sub_table_log2_bytes ? cfg.sub_table_log2_bytes : 24;
         geometry(need_slots, slb, &t.n_sub, &t.sub_log2);
         t.sub_mask = (uint32_t)((1ull << t.sub_log2) - 1);
-        t.max_probe = (uint32_t)std::min<uint64_t>(1ull << t.sub_log2, 2048);
+        t.page_log2 = std::min<uint32_t>(PageGeom<K>::LOG2, t.sub_log2);
+        t.page_mask = (1u << t.page_log2) - 1;
+        t.max_probe = std::min<uint32_t>(1u << t.page_log2, 2048);
         size_t bytes = (t.capacity() + 1) * sizeof(Slot);
         void *p = nullptr;
         cudaError_t e = cudaMalloc(&p, bytes);
@@ -260,11 +270,33 @@ template <class K> struct Builder : BuilderBase {
                         cudaGetErrorString(e));
         }
         t.slots = (Slot *)p;
-        int grid = props.sms * 8;
-        prof.begin("init_table", t.capacity() + 1, stream);
-        init_table_kernel<K><<<grid, 256, 0, stream>>>(t.slots, t.capacity() + 1);
-        prof.end(stream);
+        if (do_init) {
+            prof.begin("init_table", t.capacity() + 1, stream);
+            init_table_kernel<K><<<props.sms * 8, 256, 0, stream>>>(t.slots, t.capacity() + 1);
+            prof.end(stream);
+        }
+        else KTG_TRY(init_special_slot(t));
         *out = t;
+        return KTG_OK;
+    }
+
+    // the one slot past the end (all-ones key at full width) is always kept defined
+    int init_special_slot(const Table<K> &t) {
+        Slot *sp = t.slots + t.capacity();
+        KTG_CUDA(cudaMemsetAsync(sp, 0, sizeof(Slot), stream));
+        KTG_CUDA(cudaMemsetAsync(sp, 0xFF, sizeof(K), stream));
+        return KTG_OK;
+    }
+
+    // A table that was just allocated / reset is only marked `fresh`; the page
+    // update initialises pages in shared memory as it sweeps, every other user of
+    // the table memory (L2-atomic inserts, scans) materialises the empty table first.
+    int ensure_init() {
+        if (!fresh) return KTG_OK;
+        prof.begin("init_table", tab.capacity() + 1, stream);
+        init_table_kernel<K><<<props.sms * 8, 256, 0, stream>>>(tab.slots, tab.capacity() + 1);
+        prof.end(stream);
+        fresh = false;
         return KTG_OK;
     }
 
@@ -284,6 +316,8 @@ template <class K> struct Builder : BuilderBase {
         d_ctr = (PackCounters *)b_small.p;
         d_ovf_count = (unsigned long long *)((char *)b_small.p + 256);
         d_scratch = (unsigned long long *)((char *)b_small.p + 512);
+        d_lost = (unsigned long long *)((char *)b_small.p + 1024);
+        d_page_spill = d_lost + 1;
         KTG_TRY(b_hll.ensure(HLL_M * 4));
         KTG_CUDA(cudaMemsetAsync(b_hll.p, 0, HLL_M * 4, stream));
         KTG_TRY(b_ovf_keys.ensure(OVF_CAP * sizeof(K)));
@@ -299,7 +333,8 @@ template <class K> struct Builder : BuilderBase {
         if (rc) entries = (entries + 1) / 2;
         entries = (entries + tab.world - 1) / tab.world;
         uint64_t need = entries ? (uint64_t)((double)entries / LOAD_TARGET) + 1 : (1u << 20);
-        KTG_TRY(alloc_table(need, &tab));
+        KTG_TRY(alloc_table(need, &tab, false));
+        fresh = true;
         // opt in to large dynamic shared memory for the scatter kernels
         set_smem_attrs();
         return KTG_OK;
@@ -309,7 +344,9 @@ template <class K> struct Builder : BuilderBase {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     }
     void set_smem_attrs() {
-        const size_t mx = ScatterSmem<K>::bytes(MAX_BINS, true);
+        const size_t mx = ScatterSmem<K, SCATTER_TILE>::bytes(MAX_BINS, true);
+        allow_smem(scatter_pages_kernel<K>, ScatterSmem<K, L2S_TILE>::bytes(MAX_PAGES_PER_SUB, false));
+        allow_smem(update_pages_kernel<K>, page_smem_bytes());
         allow_smem(scatter_reads_kernel<K, true, false, true>, mx);
         allow_smem(scatter_reads_kernel<K, false, false, true>, mx);
         allow_smem(scatter_reads_kernel<K, true, false, false>, mx);
@@ -322,8 +359,18 @@ template <class K> struct Builder : BuilderBase {
 
     bool use_partition() const {
         if (cfg.flags & KTG_FLAG_FORCE_DIRECT) return false;
-        if (cfg.flags & KTG_FLAG_FORCE_PARTITION) return true;
+        if (cfg.flags & (KTG_FLAG_FORCE_PARTITION | KTG_FLAG_FORCE_PAGES)) return true;
         return tab.n_sub > 3; // up to ~48 MB of table is L2 resident as a whole
+    }
+    static size_t page_smem_bytes() { return ((size_t)1 << PageGeom<K>::LOG2) * (sizeof(K) + 4); }
+    // Streaming page update or L2 atomics?  The sweep reads and writes every slot
+    // (32 B per slot of traffic), the atomic path costs ~2 L2 transactions per key:
+    // the sweep wins once the batch has about as many keys as the table has slots.
+    bool use_pages(uint64_t n_keys) const {
+        if (cfg.flags & KTG_FLAG_NO_PAGES) return false;
+        if (tab.pages_per_sub() > MAX_PAGES_PER_SUB) return false;
+        if (cfg.flags & KTG_FLAG_FORCE_PAGES) return true;
+        return 2 * n_keys >= tab.capacity();
     }
 
     int sync() {
@@ -334,6 +381,10 @@ template <class K> struct Builder : BuilderBase {
 
     // ---- growth -----------------------------------------------------------------
     int count_occupied(uint64_t *out) {
+        if (fresh) {
+            *out = 0;
+            return KTG_OK;
+        }
         KTG_CUDA(cudaMemsetAsync(d_scratch, 0, 8, stream));
         prof.begin("count_occupied", tab.capacity(), stream);
         count_occupied_kernel<K><<<props.sms * 8, 256, 0, stream>>>(tab.slots, tab.capacity(), d_scratch);
@@ -347,7 +398,15 @@ template <class K> struct Builder : BuilderBase {
 
     int grow_to(uint64_t need_slots) {
         Table<K> nt;
-        KTG_TRY(alloc_table(need_slots, &nt));
+        if (fresh) { // nothing to move
+            KTG_TRY(alloc_table(need_slots, &nt, false));
+            KTG_TRY(sync());
+            cudaFree(tab.slots);
+            tab = nt;
+            ++grow_events;
+            return KTG_OK;
+        }
+        KTG_TRY(alloc_table(need_slots, &nt, true));
         prof.begin("rehash", tab.capacity(), stream);
         rehash_kernel<K><<<props.sms * 8, 256, 0, stream>>>(tab.slots, tab.capacity(), nt);
         prof.end(stream);
@@ -503,7 +562,14 @@ template <class K> struct Builder : BuilderBase {
         uint64_t mean = (n_keys + n_bins - 1) / n_bins;
         uint64_t slack = std::max<uint64_t>(4096, (uint64_t)(10.0 * sqrt((double)mean)) + mean / 64);
         uint64_t cap = mean + slack;
-        return (cap + INSERT_TILE - 1) / INSERT_TILE * INSERT_TILE;
+        return (cap + L2S_TILE - 1) / L2S_TILE * L2S_TILE; // whole tiles of either consumer
+    }
+    // page buckets: a page's key count is a sum over its distinct keys of their
+    // multiplicities, so its spread grows with the coverage; 1/8 + 1024 is ~3.5 sigma
+    // at 100x.  The tail goes to the spill list (exact, just slower).
+    static uint64_t page_bucket_cap_for(uint64_t n_keys, uint64_t n_pages) {
+        uint64_t mean = (n_keys + n_pages - 1) / n_pages;
+        return (mean + mean / 8 + 1024 + 3) & ~3ull;
     }
 
     int scan_bins_pass(uint32_t n_bins, uint64_t bucket_cap) {
@@ -548,7 +614,7 @@ template <class K> struct Builder : BuilderBase {
     int scatter_reads_pass(const Batch &bt, uint32_t n_bins, const ScatterOut &o) {
         const uint64_t *packed = (const uint64_t *)b_packed.p;
         const uint8_t *nstart = (const uint8_t *)b_nstart.p;
-        size_t ss = ScatterSmem<K>::bytes(n_bins, HLL);
+        size_t ss = ScatterSmem<K, SCATTER_TILE>::bytes(n_bins, HLL);
         uint64_t n_tiles = std::max<uint64_t>(1, (bt.im.n_items + SCATTER_THREADS - 1) / SCATTER_THREADS);
         prof.begin("scatter_reads", bt.windows, stream);
         if (rc) {
@@ -564,7 +630,7 @@ template <class K> struct Builder : BuilderBase {
     }
 
     template <bool HLL> int scatter_keys_pass(const K *keys, uint64_t n, uint32_t n_bins, const ScatterOut &o) {
-        size_t ss = ScatterSmem<K>::bytes(n_bins, HLL);
+        size_t ss = ScatterSmem<K, SCATTER_TILE>::bytes(n_bins, HLL);
         uint64_t n_tiles = std::max<uint64_t>(1, (n + SCATTER_TILE - 1) / SCATTER_TILE);
         int g = (int)std::min<uint64_t>(grid_for(scatter_keys_kernel<K, false, HLL>, SCATTER_THREADS, ss, props), n_tiles);
         prof.begin("scatter_keys", n, stream);
@@ -573,23 +639,65 @@ template <class K> struct Builder : BuilderBase {
         return KTG_OK;
     }
 
-    // flat (dense) or bucketed insert
+    // flat (dense) or bucketed insert with L2 atomics; n_dev: the count lives on the device
     int launch_insert(const K *keys, uint64_t n, const unsigned long long *bin_end, uint64_t bucket_cap,
-                      uint32_t n_bins) {
+                      uint32_t n_bins, const unsigned long long *n_dev = nullptr) {
         uint64_t tiles_per_bin = bin_end ? bucket_cap / INSERT_TILE : 0;
         uint64_t n_tiles = bin_end ? tiles_per_bin * n_bins : (n + INSERT_TILE - 1) / INSERT_TILE;
         if (n_tiles == 0) return KTG_OK;
+        KTG_TRY(ensure_init());
         int g = grid_for(insert_keys_kernel<K>, 256, 0, props);
         g = (int)std::min<uint64_t>(g, n_tiles);
         KTG_CUDA(cudaMemsetAsync(d_scratch + 14, 0, 8, stream)); // the tile counter
-        prof.begin("insert_keys", n, stream);
-        insert_keys_kernel<K><<<g, 256, 0, stream>>>(keys, n, k, rc && (k % 2 == 0), tab, d_scratch + 14, bin_end,
+        prof.begin("insert_keys", n_dev ? 0 : n, stream);
+        insert_keys_kernel<K><<<g, 256, 0, stream>>>(keys, n, n_dev, d_lost, k, rc && (k % 2 == 0), tab, d_scratch + 14, bin_end,
                                                       bucket_cap, tiles_per_bin, n_tiles);
         prof.end(stream);
         nodes_valid = false;
         return KTG_OK;
     }
     int launch_insert_keys(const K *keys, uint64_t n) { return launch_insert(keys, n, nullptr, 0, 0); }
+
+    // Level-2 scatter of the level-1 buckets by page, then the streaming page update.
+    // Page-bucket overflow goes to a spill list that is inserted with L2 atomics
+    // afterwards (count stays on the device: no host round trip).
+    int paged_update(uint32_t n_bins, uint64_t cap1, uint64_t n_keys) {
+        const uint64_t n_pages = tab.n_pages();
+        const uint64_t cap2 = page_bucket_cap_for(n_keys, n_pages);
+        const uint64_t spill_cap = std::max<uint64_t>(1u << 20, n_keys / 32);
+        if ((double)n_pages * (double)cap2 >= 4.0e9) return fail(KTG_ERR_INVALID, "batch too large for 32-bit bucket positions");
+        KTG_TRY(b_pkeys.ensure(n_pages * cap2 * sizeof(K) + 64));
+        KTG_TRY(b_pcur.ensure(n_pages * 8));
+        KTG_TRY(b_pspill.ensure(spill_cap * sizeof(K) + 64));
+        unsigned long long *cur2 = (unsigned long long *)b_pcur.p, *spill2 = d_page_spill;
+        KTG_CUDA(cudaMemsetAsync(spill2, 0, 8, stream));
+        init_cursors_kernel<<<(int)std::min<uint64_t>((n_pages + 255) / 256, props.sms * 8), 256, 0, stream>>>(cur2, n_pages, cap2);
+        ScatterOut o;
+        o.cursors = cur2;
+        o.bucket_cap = cap2;
+        o.out = b_pkeys.p;
+        o.spill_out = b_pspill.p;
+        o.spill_cursor = spill2;
+        o.spill_cap = spill_cap;
+        const uint64_t tiles_per_bin = cap1 / L2S_TILE, n_tiles = tiles_per_bin * n_bins;
+        const size_t ss = ScatterSmem<K, L2S_TILE>::bytes(tab.pages_per_sub(), false);
+        int g = (int)std::min<uint64_t>(grid_for(scatter_pages_kernel<K>, L2S_THREADS, ss, props), n_tiles);
+        prof.begin("scatter_pages", n_keys, stream);
+        scatter_pages_kernel<K><<<g, L2S_THREADS, ss, stream>>>((const K *)b_keys.p, curs_ptr(n_bins), cap1, tiles_per_bin, n_tiles, tab, o);
+        prof.end(stream);
+        const size_t ps = ((size_t)1 << tab.page_log2) * (sizeof(K) + 4);
+        g = (int)std::min<uint64_t>(grid_for(update_pages_kernel<K>, PAGE_THREADS, ps, props), n_pages);
+        prof.begin("update_pages", n_keys, stream);
+        update_pages_kernel<K><<<g, PAGE_THREADS, ps, stream>>>((const K *)b_pkeys.p, cur2, cap2, k, rc && (k % 2 == 0), tab, fresh);
+        prof.end(stream);
+        fresh = false;
+        nodes_valid = false;
+        ++page_updates;
+        // page-bucket spill (if any): the kernel reads the count from the device
+        // (keys beyond spill_cap are counted in *d_lost by the kernel and void the build in finalize)
+        KTG_TRY(launch_insert((const K *)b_pspill.p, spill_cap, nullptr, 0, 0, spill2));
+        return KTG_OK;
+    }
 
     // One-pass partition by sub-table + insert.  `scatter(o)` runs the scatter kernel
     // (which also feeds the cardinality sketch) for the current table geometry;
@@ -623,7 +731,8 @@ template <class K> struct Builder : BuilderBase {
                 continue;
             }
             if (spilled > spill_cap) return KTG_ERR_TABLE_FULL + 1000; // caller falls back to the exact path
-            KTG_TRY(launch_insert((const K *)b_keys.p, n_keys, curs_ptr(n_bins), cap, n_bins));
+            if (use_pages(n_keys)) KTG_TRY(paged_update(n_bins, cap, n_keys));
+            else KTG_TRY(launch_insert((const K *)b_keys.p, n_keys, curs_ptr(n_bins), cap, n_bins));
             if (spilled) KTG_TRY(launch_insert_keys((const K *)b_spill.p, spilled));
             return KTG_OK;
         }
@@ -651,6 +760,7 @@ template <class K> struct Builder : BuilderBase {
             }));
         }
         if (!use_partition()) { // still small after a possible grow: fused extract + insert
+            KTG_TRY(ensure_init());
             prof.begin("extract_insert", bt.windows, stream);
             if (rc) {
                 int g = grid_for(extract_insert_kernel<K, true>, 256, 0, props);
@@ -699,14 +809,20 @@ template <class K> struct Builder : BuilderBase {
     int finalize() override {
         if (deferred_error != KTG_OK) return fail(deferred_error, "build is void after an earlier error");
         KTG_TRY(read_counters(nullptr, nullptr));
+        unsigned long long lost = 0;
+        KTG_CUDA(cudaMemcpyAsync(&lost, d_lost, 8, cudaMemcpyDeviceToHost, stream));
+        KTG_TRY(sync());
+        if (lost) {
+            deferred_error = KTG_ERR_TABLE_FULL;
+            return fail(KTG_ERR_TABLE_FULL, "%llu keys overflowed the page spill list", lost);
+        }
         KTG_TRY(drain_overflow());
         return KTG_OK;
     }
 
     int reset() override {
-        prof.begin("init_table", tab.capacity() + 1, stream);
-        init_table_kernel<K><<<props.sms * 8, 256, 0, stream>>>(tab.slots, tab.capacity() + 1);
-        prof.end(stream);
+        fresh = true; // the next user of the table memory initialises it (ensure_init / page update)
+        KTG_TRY(init_special_slot(tab));
         KTG_CUDA(cudaMemsetAsync(b_small.p, 0, 4096, stream));
         KTG_CUDA(cudaMemsetAsync(b_hll.p, 0, HLL_M * 4, stream));
         occupied_ub = 0;
@@ -716,6 +832,7 @@ template <class K> struct Builder : BuilderBase {
         windows_inserted = 0;
         windows_seen = 0;
         nodes_valid = false;
+        page_updates = 0;
         KTG_CUDA(cudaGetLastError());
         return KTG_OK;
     }
@@ -723,6 +840,7 @@ template <class K> struct Builder : BuilderBase {
     // ---- stats ------------------------------------------------------------------------
     int edge_stats(uint32_t threshold, EdgeStats *out) override {
         KTG_TRY(finalize());
+        KTG_TRY(ensure_init());
         KTG_CUDA(cudaMemsetAsync(d_scratch, 0, sizeof(EdgeStats), stream));
         uint64_t n = tab.capacity() + 1;
         prof.begin("edge_stats", n, stream);
@@ -734,6 +852,7 @@ template <class K> struct Builder : BuilderBase {
     }
 
     template <class KN> int node_stats_t(NodeStats *out) {
+        KTG_TRY(ensure_init());
         // distinct canonical nodes <= 2 x live canonical edges
         uint64_t occ = 0;
         KTG_TRY(count_occupied(&occ));
@@ -744,6 +863,8 @@ template <class K> struct Builder : BuilderBase {
         nt.n_sub = 1;
         nt.sub_log2 = l;
         nt.sub_mask = (uint32_t)((1ull << l) - 1);
+        nt.page_log2 = l; // one page: probing wraps around the whole node table
+        nt.page_mask = nt.sub_mask;
         nt.max_probe = (uint32_t)std::min<uint64_t>(1ull << l, 1u << 20);
         nt.world = 1;
         nt.rank = 0;
@@ -798,6 +919,7 @@ template <class K> struct Builder : BuilderBase {
     int remove_weak_edges(uint32_t t) override {
         KTG_TRY(finalize());
         if (t <= 1) return KTG_OK; // every stored edge has w >= 1
+        KTG_TRY(ensure_init());
         uint64_t n = tab.capacity() + 1;
         prof.begin("filter", n, stream);
         filter_kernel<K><<<props.sms * 8, 256, 0, stream>>>(tab.slots, n, t);
@@ -944,6 +1066,8 @@ template <class K> struct Builder : BuilderBase {
         out->kernel_launches = prof.total_launches;
         out->grow_events = grow_events;
         out->partitioned = use_partition();
+        out->page_updates = page_updates;
+        out->n_pages = (uint32_t)std::min<uint64_t>(tab.n_pages(), 0xFFFFFFFFull);
         return KTG_OK;
     }
 };

@@ -25,6 +25,18 @@ __host__ __device__ __forceinline__ uint64_t fmix64(uint64_t z) {
 __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
     return fmix64(x + 0x9E3779B97F4A7C15ull);
 }
+// Placement hash: two multiply / fold rounds (a shift by 32 is a register move,
+// so this is ~8 SASS instructions against ~20 for fmix64, and the hash is
+// computed three times per window: L1 scatter, L2 scatter, page update).  It only
+// decides WHERE a key lives, never a result; its uniformity on sequential, shifted,
+// low-complexity and tandem-repeat key sets is checked in tests/test_hashing.py.
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
+    x *= 0x9E3779B97F4A7C15ull;
+    x ^= x >> 32;
+    x *= 0xD6E8FEB86659FD93ull;
+    x ^= x >> 32;
+    return x;
+}
 
 // ---- reverse complement on packed integers (compress.rs:153-169 restated as
 // bit tricks: complement = NOT (:164), reversal of 2-bit symbols) ----
@@ -62,9 +74,7 @@ template <> struct KeyTraits<uint64_t> {
         uint32_t aux;
     };
     __host__ __device__ static __forceinline__ uint64_t empty() { return ~0ull; }
-    __host__ __device__ static __forceinline__ uint64_t hash(uint64_t k) {
-        return fmix64(k ^ 0x6b61746f6d65ull);
-    }
+    __host__ __device__ static __forceinline__ uint64_t hash(uint64_t k) { return mix64(k); }
     __host__ __device__ static __forceinline__ uint64_t hi(uint64_t) { return 0; }
     __host__ __device__ static __forceinline__ uint64_t lo(uint64_t k) { return k; }
     __host__ __device__ static __forceinline__ uint64_t make(uint64_t, uint64_t lo_) { return lo_; }
@@ -93,7 +103,7 @@ template <> struct KeyTraits<u128> {
     };
     __host__ __device__ static __forceinline__ u128 empty() { return ~(u128)0; }
     __host__ __device__ static __forceinline__ uint64_t hash(u128 k) {
-        return fmix64((uint64_t)k ^ fmix64((uint64_t)(k >> 64) ^ 0x6b61746f6d65ull));
+        return mix64((uint64_t)k ^ ((uint64_t)(k >> 64) * 0xA24BAED4963EE407ull));
     }
     __host__ __device__ static __forceinline__ uint64_t hi(u128 k) { return (uint64_t)(k >> 64); }
     __host__ __device__ static __forceinline__ uint64_t lo(u128 k) { return (uint64_t)k; }
@@ -139,9 +149,11 @@ template <> struct KeyTraits<u128> {
 };
 
 // Where a key lives: owner rank (hash sharding over GPUs), sub-table (the
-// L2-resident partition) and home slot inside it.  Three disjoint pieces of
-// one 64-bit hash, range-reduced by multiply-shift so that world and n_sub
-// need not be powers of two.
+// L2-resident partition, = level-1 bin of the partitioner) and home slot inside
+// it; the high bits of the slot select the PAGE (the shared-memory sized unit of
+// the streaming update, = level-2 bin) and linear probing wraps inside the page.
+// Disjoint pieces of one 64-bit hash, range-reduced by multiply-shift so that
+// world and n_sub need not be powers of two.
 struct Place {
     uint32_t owner, part, slot;
 };
@@ -159,6 +171,7 @@ __host__ __device__ __forceinline__ Place place_of(uint64_t h, uint32_t world, u
 template <class K> struct Table {
     typename KeyTraits<K>::Slot *slots; // n_sub << sub_log2 slots + 1 special slot
     uint32_t n_sub, sub_log2, sub_mask;
+    uint32_t page_log2, page_mask; // page_log2 <= sub_log2; probing wraps inside a page
     uint32_t world, rank;
     uint32_t max_probe;
     // inserts that could not be placed (sub-table full): replayed after a grow
@@ -167,6 +180,8 @@ template <class K> struct Table {
     unsigned long long *ovf_count;
     uint64_t ovf_cap;
     __host__ __device__ uint64_t capacity() const { return (uint64_t)n_sub << sub_log2; }
+    __host__ __device__ uint32_t pages_per_sub() const { return 1u << (sub_log2 - page_log2); }
+    __host__ __device__ uint64_t n_pages() const { return (uint64_t)n_sub << (sub_log2 - page_log2); }
 };
 
 #ifdef __CUDACC__
@@ -182,17 +197,17 @@ __device__ __forceinline__ void table_add(const Table<K> &t, K key, uint32_t inc
         return;
     }
     Place p = place_of(T::hash(key), t.world, t.n_sub, t.sub_mask);
-    Slot *sub = t.slots + ((uint64_t)p.part << t.sub_log2);
-    uint32_t i = p.slot;
+    Slot *page = t.slots + ((uint64_t)p.part << t.sub_log2) + (p.slot & ~t.page_mask);
+    uint32_t i = p.slot & t.page_mask;
     for (uint32_t n = 0; n < t.max_probe; ++n) {
-        Slot *s = sub + i;
+        Slot *s = page + i;
         K cur = T::load(s);
         if (cur != key && (cur == EMPTY || T::maybe_torn(cur))) cur = T::cas(s, EMPTY, key);
         if (cur == key || cur == EMPTY) {
             atomicAdd(&s->w, inc);
             return;
         }
-        i = (i + 1) & t.sub_mask;
+        i = (i + 1) & t.page_mask;
     }
     unsigned long long pos = atomicAdd(t.ovf_count, 1ull);
     if (pos < t.ovf_cap) {

@@ -240,19 +240,26 @@ extract_insert_kernel(const uint64_t *__restrict__ packed, const uint8_t *__rest
 // into a persistent sketch with atomicMax.  The host sizes / grows the table
 // from the estimate, so no capacity hint is needed (create_fastq starts from
 // T::default(), builder.rs:145) and no pessimistic "every window is new" bound
-// is used.  Only keys whose hash falls in a fixed 1/8 of the hash space are
-// sketched (consistent for duplicates, so distinct(sample) * 8 estimates
+// is used.  Only keys whose hash falls in a fixed 1/128 of the hash space are
+// sketched (consistent for duplicates, so distinct(sample) * 128 estimates
 // distinct(all)); the sampled keys are re-mixed so that register index and rank
-// are independent of the bits that place the key in the table.
-constexpr uint32_t HLL_P = 12, HLL_M = 1u << HLL_P, HLL_SAMPLE = 8;
+// are independent of the bits that place the key in the table.  The warp vote
+// turns the update into a real branch that ~4 of 5 warps skip (as straight-line
+// predicated code it was 20 % of the scatter kernel's instructions).
+constexpr uint32_t HLL_P = 12, HLL_M = 1u << HLL_P, HLL_SAMPLE = 128;
 
-__device__ __forceinline__ void hll_update(uint32_t *regs, uint64_t h) {
-    if (((uint32_t)h >> 29) != 0) return; // lo32 bits 29..31: above every slot index we use
+__device__ __forceinline__ void hll_insert(uint32_t *regs, uint64_t h) {
     uint64_t g = fmix64(h ^ 0x9E3779B97F4A7C15ull);
     uint32_t idx = (uint32_t)(g >> (64 - HLL_P));
     uint64_t rest = g << HLL_P;
     uint32_t rank = rest ? (uint32_t)__clzll((long long)rest) + 1u : 64u - HLL_P + 1u;
     if (regs[idx] < rank) atomicMax(&regs[idx], rank);
+}
+__device__ __forceinline__ void hll_update(uint32_t *regs, uint64_t h, bool valid = true) {
+    const bool s = valid && ((uint32_t)h >> 25) == 0; // lo32 bits 25..31: above every slot index we use
+    if (__any_sync(__activemask(), s)) {
+        if (s) hll_insert(regs, h);
+    }
 }
 
 // ================================================================ work items
@@ -347,7 +354,7 @@ hll_reads_kernel(const uint64_t *__restrict__ packed, const uint8_t *__restrict_
         iw.load(packed, nstart, n_words, it, k, im);
 #pragma unroll
         for (int j = 0; j < GRAN; ++j) {
-            if (j < (int)iw.nwin) hll_update(regs, KeyTraits<K>::hash(iw.template key<RC>()));
+            hll_update(regs, KeyTraits<K>::hash(iw.template key<RC>()), j < (int)iw.nwin);
             iw.r.step();
         }
     }
@@ -470,36 +477,38 @@ __global__ void scan_bins_kernel(const unsigned long long *__restrict__ hist, ui
 }
 
 // ---- tile-local counting sort in shared memory, then coalesced runs to HBM.
-// A CTA bins up to SCATTER_TILE keys in shared memory and reserves one
-// contiguous range per (tile, bin) with a single atomicAdd on the bin's
-// cursor, so HBM sees runs instead of scattered 8-byte stores.
-// Two modes share the code:
+// A CTA bins one tile of keys in shared memory and reserves one contiguous
+// range per (tile, bin) with a single atomicAdd on the bin's cursor, so HBM
+// sees runs instead of scattered 8-byte stores.  Cursors are absolute positions
+// in the output array.  Two modes share the code:
 //   exact    (bucket_cap == 0): cursors start at the exclusive prefix of a
 //            histogram pass; bins are dense and contiguous.
-//   one-pass (bucket_cap  > 0): bin b owns [b*cap, (b+1)*cap); no histogram
-//            pass.  Keys that do not fit (hash skew / heavy hitters) spill to
-//            an overflow array that the host inserts separately; nothing is
-//            ever dropped silently (the host checks the spill counter).
-constexpr int SCATTER_THREADS = 256, SCATTER_PER = 8, SCATTER_TILE = SCATTER_THREADS * SCATTER_PER;
-
-template <class K> struct ScatterSmem {
-    K *keys;                  // SCATTER_TILE
-    uint16_t *bin;            // SCATTER_TILE
-    uint32_t *cnt, *loc;      // n_bins each
-    unsigned long long *glob; // n_bins: reserved start in the bin's HBM range
+//   one-pass (bucket_cap  > 0): bin b owns [(bin_off+b)*cap, (bin_off+b+1)*cap);
+//            no histogram pass.  Keys that do not fit (hash skew / heavy
+//            hitters) spill to an overflow array that the host inserts
+//            separately; nothing is ever dropped silently (the host checks the
+//            spill counter).
+// The same routine serves both partition levels: level 1 bins by sub-table (or
+// owner rank), level 2 bins the keys of one sub-table by page.
+// Output positions must fit 32 bits (the host splits larger batches).
+template <class K, int TILE> struct ScatterSmem {
+    K *keys;                   // TILE
+    uint32_t *delta;           // TILE: output position minus position in the sorted tile
+    uint32_t *cnt, *loc;       // 2 x n_bins (double buffered), n_bins
+    unsigned long long *glob;  // n_bins: reserved start in the bin's HBM range
     unsigned long long *spill; // n_bins: reserved start in the overflow array
-    uint32_t *regs;           // HLL_M (only with HLL)
+    uint32_t *regs;            // HLL_M (only with HLL)
     __device__ __forceinline__ void carve(unsigned char *base, uint32_t n_bins) {
         keys = (K *)base;
-        bin = (uint16_t *)(keys + SCATTER_TILE);
-        cnt = (uint32_t *)(bin + SCATTER_TILE);
-        loc = cnt + n_bins;
-        glob = (unsigned long long *)(loc + n_bins); // 2*n_bins u32: 8-byte aligned
+        glob = (unsigned long long *)(keys + TILE);
         spill = glob + n_bins;
-        regs = (uint32_t *)(spill + n_bins);
+        delta = (uint32_t *)(spill + n_bins);
+        cnt = delta + TILE;
+        loc = cnt + 2 * n_bins;
+        regs = loc + n_bins;
     }
     static size_t bytes(uint32_t n_bins, bool hll) {
-        return (size_t)SCATTER_TILE * (sizeof(K) + 2) + (size_t)n_bins * 24 + (hll ? HLL_M * 4 : 0);
+        return (size_t)TILE * (sizeof(K) + 4) + (size_t)n_bins * 28 + (hll ? HLL_M * 4 : 0);
     }
 };
 
@@ -512,25 +521,28 @@ struct ScatterOut {
     unsigned long long spill_cap;
 };
 
-// precondition: sm.cnt zeroed and the block synchronised
-template <class K>
-__device__ __forceinline__ void tile_scatter(const K (&key)[SCATTER_PER],
-                                             const uint32_t (&bin)[SCATTER_PER], int nvalid,
-                                             ScatterSmem<K> &sm, uint32_t n_bins,
-                                             const ScatterOut &o) {
+// Preconditions: sm.cnt[parity] is zero, s_ovf == 0, the block is synchronised.
+// Leaves sm.cnt[parity ^ 1] zeroed and the block synchronised.
+template <class K, int THREADS, int PER>
+__device__ __forceinline__ void tile_scatter(const K (&key)[PER], const uint32_t (&bin)[PER],
+                                             int nvalid, ScatterSmem<K, THREADS * PER> &sm,
+                                             uint32_t n_bins, unsigned long long *cursors,
+                                             uint64_t bin_off, const ScatterOut &o, uint32_t parity) {
     __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_total;
-    uint32_t rank[SCATTER_PER];
+    __shared__ uint32_t s_total, s_ovf;
+    uint32_t *cnt = sm.cnt + parity * n_bins;
+    uint32_t rank[PER];
 #pragma unroll
-    for (int j = 0; j < SCATTER_PER; ++j)
-        if (j < nvalid) rank[j] = atomicAdd(&sm.cnt[bin[j]], 1u);
+    for (int j = 0; j < PER; ++j)
+        if (j < nvalid) rank[j] = atomicAdd(&cnt[bin[j]], 1u);
+    if (threadIdx.x == 0) s_ovf = 0;
     __syncthreads();
     // block-wide exclusive scan of the bin counts; reserve HBM ranges
     {
-        const uint32_t per = (n_bins + SCATTER_THREADS - 1) / SCATTER_THREADS;
+        const uint32_t per = (n_bins + THREADS - 1) / THREADS;
         const uint32_t b0 = threadIdx.x * per;
         uint32_t s = 0;
-        for (uint32_t i = b0; i < b0 + per && i < n_bins; ++i) s += sm.cnt[i];
+        for (uint32_t i = b0; i < b0 + per && i < n_bins; ++i) s += cnt[i];
         uint32_t incl = s;
         for (int d = 1; d < 32; d <<= 1) {
             uint32_t x = __shfl_up_sync(0xFFFFFFFFu, incl, d);
@@ -539,7 +551,7 @@ __device__ __forceinline__ void tile_scatter(const K (&key)[SCATTER_PER],
         if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
         __syncthreads();
         if (threadIdx.x < 32) {
-            uint32_t v = threadIdx.x < SCATTER_THREADS / 32 ? s_warp[threadIdx.x] : 0, iv = v;
+            uint32_t v = threadIdx.x < THREADS / 32 ? s_warp[threadIdx.x] : 0, iv = v;
             for (int d = 1; d < 32; d <<= 1) {
                 uint32_t x = __shfl_up_sync(0xFFFFFFFFu, iv, d);
                 if (threadIdx.x >= d) iv += x;
@@ -550,16 +562,17 @@ __device__ __forceinline__ void tile_scatter(const K (&key)[SCATTER_PER],
         __syncthreads();
         uint32_t run = s_warp[threadIdx.x >> 5] + incl - s;
         for (uint32_t i = b0; i < b0 + per && i < n_bins; ++i) {
-            const uint32_t c = sm.cnt[i];
+            const uint32_t c = cnt[i];
             sm.loc[i] = run;
             if (c) {
-                const unsigned long long base = atomicAdd(&o.cursors[i], (unsigned long long)c);
+                const unsigned long long base = atomicAdd(&cursors[i], (unsigned long long)c);
                 sm.glob[i] = base;
                 if (o.bucket_cap) {
-                    const unsigned long long lim = (unsigned long long)(i + 1) * o.bucket_cap;
+                    const unsigned long long lim = (bin_off + i + 1) * o.bucket_cap;
                     if (base + c > lim) {
                         const unsigned long long over = base + c - (base > lim ? base : lim);
                         sm.spill[i] = atomicAdd(o.spill_cursor, over);
+                        s_ovf = 1;
                     }
                 }
             }
@@ -568,23 +581,33 @@ __device__ __forceinline__ void tile_scatter(const K (&key)[SCATTER_PER],
     }
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < SCATTER_PER; ++j)
+    for (int j = 0; j < PER; ++j)
         if (j < nvalid) {
-            const uint32_t pos = sm.loc[bin[j]] + rank[j];
+            const uint32_t l = sm.loc[bin[j]], pos = l + rank[j];
             sm.keys[pos] = key[j];
-            sm.bin[pos] = (uint16_t)bin[j];
+            sm.delta[pos] = (uint32_t)sm.glob[bin[j]] - l;
         }
+    {   // the other counter buffer is free now: zero it for the next tile
+        uint32_t *nxt = sm.cnt + (parity ^ 1u) * n_bins;
+        for (uint32_t i = threadIdx.x; i < n_bins; i += THREADS) nxt[i] = 0;
+    }
     __syncthreads();
     const uint32_t total = s_total;
     K *out = (K *)o.out;
-    for (uint32_t i = threadIdx.x; i < total; i += SCATTER_THREADS) {
-        const uint32_t b = sm.bin[i];
-        const unsigned long long dst = sm.glob[b] + (i - sm.loc[b]);
-        if (o.bucket_cap == 0) {
-            out[dst] = sm.keys[i];
-        }
-        else {
-            const unsigned long long lim = (unsigned long long)(b + 1) * o.bucket_cap;
+    if (!s_ovf) {
+        for (uint32_t i = threadIdx.x; i < total; i += THREADS) out[(uint32_t)(sm.delta[i] + i)] = sm.keys[i];
+    }
+    else { // some bin of this tile ran past its bucket: find each key's bin again (rare)
+        for (uint32_t i = threadIdx.x; i < total; i += THREADS) {
+            uint32_t lo = 0, hi = n_bins - 1; // last bin with loc <= i and a non-empty count
+            while (lo < hi) {
+                uint32_t mid = (lo + hi + 1) >> 1;
+                if (sm.loc[mid] <= i) lo = mid;
+                else hi = mid - 1;
+            }
+            const uint32_t b = lo;
+            const unsigned long long lim = (bin_off + b + 1) * o.bucket_cap;
+            const unsigned long long dst = sm.glob[b] + (i - sm.loc[b]);
             if (dst < lim) out[dst] = sm.keys[i];
             else {
                 const unsigned long long first = sm.glob[b] > lim ? sm.glob[b] : lim;
@@ -596,21 +619,25 @@ __device__ __forceinline__ void tile_scatter(const K (&key)[SCATTER_PER],
     __syncthreads();
 }
 
+constexpr int SCATTER_THREADS = 256, SCATTER_PER = 8, SCATTER_TILE = SCATTER_THREADS * SCATTER_PER;
+
+// Level 1 from packed reads: extraction (K2) + partition by sub-table or owner.
 template <class K, bool RC, bool BY_OWNER, bool HLL>
-__global__ void __launch_bounds__(SCATTER_THREADS)
+__global__ void __launch_bounds__(SCATTER_THREADS, 3)
 scatter_reads_kernel(const uint64_t *__restrict__ packed, const uint8_t *__restrict__ nstart,
                      uint64_t n_words, uint32_t k, ItemMap im, Table<K> t, uint32_t n_bins,
                      ScatterOut o, uint32_t *__restrict__ g_regs) {
     extern __shared__ __align__(16) unsigned char smem[];
-    ScatterSmem<K> sm;
+    ScatterSmem<K, SCATTER_TILE> sm;
     sm.carve(smem, n_bins);
     if (HLL) {
         for (uint32_t i = threadIdx.x; i < HLL_M; i += SCATTER_THREADS) sm.regs[i] = 0;
     }
+    for (uint32_t i = threadIdx.x; i < 2 * n_bins; i += SCATTER_THREADS) sm.cnt[i] = 0;
+    __syncthreads();
     const uint64_t n_tiles = (im.n_items + SCATTER_THREADS - 1) / SCATTER_THREADS;
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (uint32_t i = threadIdx.x; i < n_bins; i += SCATTER_THREADS) sm.cnt[i] = 0;
-        __syncthreads();
+    uint32_t parity = 0;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, parity ^= 1u) {
         ItemWindows<K> iw;
         iw.load(packed, nstart, n_words, tile * SCATTER_THREADS + threadIdx.x, k, im);
         K key[SCATTER_PER];
@@ -621,10 +648,10 @@ scatter_reads_kernel(const uint64_t *__restrict__ packed, const uint8_t *__restr
             uint64_t h = KeyTraits<K>::hash(key[j]);
             Place p = place_of(h, t.world, t.n_sub, t.sub_mask);
             bin[j] = BY_OWNER ? p.owner : p.part;
-            if (HLL && j < (int)iw.nwin) hll_update(sm.regs, h);
+            if (HLL) hll_update(sm.regs, h, j < (int)iw.nwin);
             iw.r.step();
         }
-        tile_scatter<K>(key, bin, (int)iw.nwin, sm, n_bins, o);
+        tile_scatter<K, SCATTER_THREADS, SCATTER_PER>(key, bin, (int)iw.nwin, sm, n_bins, o.cursors, 0, o, parity);
     }
     if (HLL) {
         __syncthreads();
@@ -633,21 +660,22 @@ scatter_reads_kernel(const uint64_t *__restrict__ packed, const uint8_t *__restr
     }
 }
 
-// same for an array of keys (receiver side of the multi-GPU exchange)
+// Level 1 for an array of keys (receiver side of the multi-GPU exchange)
 template <class K, bool BY_OWNER, bool HLL>
 __global__ void __launch_bounds__(SCATTER_THREADS)
 scatter_keys_kernel(const K *__restrict__ keys, uint64_t n, Table<K> t, uint32_t n_bins,
                     ScatterOut o, uint32_t *__restrict__ g_regs) {
     extern __shared__ __align__(16) unsigned char smem[];
-    ScatterSmem<K> sm;
+    ScatterSmem<K, SCATTER_TILE> sm;
     sm.carve(smem, n_bins);
     if (HLL) {
         for (uint32_t i = threadIdx.x; i < HLL_M; i += SCATTER_THREADS) sm.regs[i] = 0;
     }
+    for (uint32_t i = threadIdx.x; i < 2 * n_bins; i += SCATTER_THREADS) sm.cnt[i] = 0;
+    __syncthreads();
     const uint64_t n_tiles = (n + SCATTER_TILE - 1) / SCATTER_TILE;
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (uint32_t i = threadIdx.x; i < n_bins; i += SCATTER_THREADS) sm.cnt[i] = 0;
-        __syncthreads();
+    uint32_t parity = 0;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, parity ^= 1u) {
         const uint64_t base = tile * SCATTER_TILE;
         K key[SCATTER_PER];
         uint32_t bin[SCATTER_PER];
@@ -655,20 +683,15 @@ scatter_keys_kernel(const K *__restrict__ keys, uint64_t n, Table<K> t, uint32_t
 #pragma unroll
         for (int j = 0; j < SCATTER_PER; ++j) {
             const uint64_t i = base + (uint64_t)j * SCATTER_THREADS + threadIdx.x;
-            if (i < n) {
-                key[j] = KeyTraits<K>::load_stream(&keys[i]);
-                uint64_t h = KeyTraits<K>::hash(key[j]);
-                Place p = place_of(h, t.world, t.n_sub, t.sub_mask);
-                bin[j] = BY_OWNER ? p.owner : p.part;
-                if (HLL) hll_update(sm.regs, h);
-                nvalid = j + 1;
-            }
-            else {
-                key[j] = 0;
-                bin[j] = 0;
-            }
+            const bool in = i < n;
+            key[j] = in ? KeyTraits<K>::load_stream(&keys[i]) : (K)0;
+            uint64_t h = KeyTraits<K>::hash(key[j]);
+            Place p = place_of(h, t.world, t.n_sub, t.sub_mask);
+            bin[j] = BY_OWNER ? p.owner : p.part;
+            if (HLL) hll_update(sm.regs, h, in);
+            if (in) nvalid = j + 1;
         }
-        tile_scatter<K>(key, bin, nvalid, sm, n_bins, o);
+        tile_scatter<K, SCATTER_THREADS, SCATTER_PER>(key, bin, nvalid, sm, n_bins, o.cursors, 0, o, parity);
     }
     if (HLL) {
         __syncthreads();
@@ -677,26 +700,209 @@ scatter_keys_kernel(const K *__restrict__ keys, uint64_t n, Table<K> t, uint32_t
     }
 }
 
-// K3 over an array of canonical keys (partitioned locally or received from
-// peers).  Keys arrive grouped by sub-table.  Tiles are handed out through a
-// global counter (persistent CTAs, dynamic scheduling) instead of a static
-// grid-stride: with a static split the SMs drift apart over the ~1000
-// iterations (near/far L2 latency differs per SM), the in-flight keys end up
-// spread over many sub-tables and the working set falls out of L2 (ncu: 27 GB
-// of DRAM reads for 322 M inserts).  With the counter every CTA works at the
-// global frontier, i.e. on the one or two sub-tables that are L2 resident.
+// ---- level 2: the keys of sub-table b (level-1 bucket b) grouped by page.
+// Tile t covers level-1 bin t / tiles_per_bin; page p of sub-table b owns
+// keys2[(b*n2+p)*cap2, +cap2) and cursors2[b*n2+p] starts at (b*n2+p)*cap2.
+constexpr int L2S_THREADS = 512, L2S_PER = 8, L2S_TILE = L2S_THREADS * L2S_PER;
+
+__global__ void init_cursors_kernel(unsigned long long *cursors, uint64_t n, uint64_t cap) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) cursors[i] = i * cap;
+}
+
+template <class K>
+__global__ void __launch_bounds__(L2S_THREADS, 2)
+scatter_pages_kernel(const K *__restrict__ keys1, const unsigned long long *__restrict__ fill1,
+                     uint64_t cap1, uint64_t tiles_per_bin, uint64_t n_tiles, Table<K> t,
+                     ScatterOut o) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const uint32_t n2 = t.pages_per_sub();
+    ScatterSmem<K, L2S_TILE> sm;
+    sm.carve(smem, n2);
+    for (uint32_t i = threadIdx.x; i < 2 * n2; i += L2S_THREADS) sm.cnt[i] = 0;
+    __syncthreads();
+    uint32_t parity = 0;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t b = tile / tiles_per_bin;
+        const uint64_t lim = (b + 1) * cap1, fill = fill1[b];
+        const uint64_t base = b * cap1 + (tile - b * tiles_per_bin) * L2S_TILE;
+        const uint64_t end = fill < lim ? fill : lim;
+        if (base >= end) continue;
+        K key[L2S_PER];
+        uint32_t bin[L2S_PER];
+        int nvalid = 0;
+#pragma unroll
+        for (int j = 0; j < L2S_PER; ++j) {
+            const uint64_t i = base + (uint64_t)j * L2S_THREADS + threadIdx.x;
+            const bool in = i < end;
+            key[j] = in ? KeyTraits<K>::load_stream(&keys1[i]) : (K)0;
+            bin[j] = ((uint32_t)KeyTraits<K>::hash(key[j]) & t.sub_mask) >> t.page_log2;
+            if (in) nvalid = j + 1;
+        }
+        tile_scatter<K, L2S_THREADS, L2S_PER>(key, bin, nvalid, sm, n2, o.cursors + b * n2, b * n2, o, parity);
+        parity ^= 1u;
+    }
+}
+
+// ======================================================================= K3
+// Streaming page update: the table is swept once, page by page.  A CTA loads
+// one page (2^page_log2 slots) into shared memory, inserts the page's keys with
+// shared-memory CAS / atomicAdd (add_single_edge + create_or_modify_edge,
+// hm_gir.rs:91-153, hs_gir.rs:192-203), and writes the page back.  No L2
+// atomics: HBM sees one coalesced read of the keys and one read + write of the
+// table.  `fresh`: the table is logically empty and its memory undefined (right
+// after ktg_reset), so pages are initialised in shared memory instead of loaded.
+constexpr int PAGE_THREADS = 512, PAGE_UNROLL = 4;
+template <class K> struct PageGeom;
+template <> struct PageGeom<uint64_t> { static constexpr uint32_t LOG2 = 13; }; // 8192 x (8+4) B =  96 KB
+template <> struct PageGeom<u128> { static constexpr uint32_t LOG2 = 12; };     // 4096 x (16+4) B = 80 KB
+
+__device__ __forceinline__ uint64_t smem_cas(uint64_t *p, uint64_t cmp, uint64_t val) {
+    return atomicCAS((unsigned long long *)p, (unsigned long long)cmp, (unsigned long long)val);
+}
+__device__ __forceinline__ u128 smem_cas(u128 *p, u128 cmp, u128 val) {
+    uint64_t olo, ohi;
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile(
+        "{\n\t"
+        ".reg .b128 c, v, o;\n\t"
+        "mov.b128 c, {%2, %3};\n\t"
+        "mov.b128 v, {%4, %5};\n\t"
+        "atom.shared.relaxed.cta.cas.b128 o, [%6], c, v;\n\t"
+        "mov.b128 {%0, %1}, o;\n\t"
+        "}\n"
+        : "=l"(olo), "=l"(ohi)
+        : "l"((uint64_t)cmp), "l"((uint64_t)(cmp >> 64)), "l"((uint64_t)val), "l"((uint64_t)(val >> 64)), "r"(addr)
+        : "memory");
+    return ((u128)ohi << 64) | olo;
+}
+__device__ __forceinline__ uint64_t smem_load(const uint64_t *p) { return *(const volatile uint64_t *)p; }
+__device__ __forceinline__ u128 smem_load(const u128 *p) {
+    uint64_t lo, hi;
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "r"(addr) : "memory");
+    return ((u128)hi << 64) | lo;
+}
+
+template <class K>
+__device__ __forceinline__ void page_add(K *sk, uint32_t *sw, uint32_t page_mask, const Table<K> &t,
+                                         K key, uint32_t inc) {
+    typedef KeyTraits<K> T;
+    const K EMPTY = T::empty();
+    if (key == EMPTY) { // all-T at full key width (only without canonicalisation)
+        atomicAdd(&t.slots[t.capacity()].w, inc);
+        return;
+    }
+    uint32_t i = (uint32_t)T::hash(key) & page_mask;
+    for (uint32_t n = 0; n <= page_mask; ++n) {
+        K cur = smem_load(&sk[i]);
+        if (cur != key && (cur == EMPTY || T::maybe_torn(cur))) cur = smem_cas(&sk[i], EMPTY, key);
+        if (cur == key || cur == EMPTY) {
+            atomicAdd(&sw[i], inc);
+            return;
+        }
+        i = (i + 1) & page_mask;
+    }
+    unsigned long long pos = atomicAdd(t.ovf_count, 1ull); // page full: replayed after a grow
+    if (pos < t.ovf_cap) {
+        t.ovf_keys[pos] = key;
+        t.ovf_inc[pos] = inc;
+    }
+}
+
+__device__ __forceinline__ void slot_to_smem(const KeyTraits<uint64_t>::Slot *g, uint64_t *sk, uint32_t *sw) {
+    uint4 v = __ldcs((const uint4 *)g);
+    *sk = ((uint64_t)v.y << 32) | v.x;
+    *sw = v.z;
+}
+__device__ __forceinline__ void slot_to_smem(const KeyTraits<u128>::Slot *g, u128 *sk, uint32_t *sw) {
+    uint4 a = __ldcs((const uint4 *)g), b = __ldcs((const uint4 *)g + 1);
+    *(uint4 *)sk = a;
+    *sw = b.x;
+}
+__device__ __forceinline__ void smem_to_slot(KeyTraits<uint64_t>::Slot *g, const uint64_t *sk, const uint32_t *sw) {
+    const uint64_t key = *sk;
+    *(uint4 *)g = make_uint4((uint32_t)key, (uint32_t)(key >> 32), *sw, 0u);
+}
+__device__ __forceinline__ void smem_to_slot(KeyTraits<u128>::Slot *g, const u128 *sk, const uint32_t *sw) {
+    ((uint4 *)g)[0] = *(const uint4 *)sk;
+    ((uint4 *)g)[1] = make_uint4(*sw, 0u, 0u, 0u);
+}
+
+template <class K>
+__global__ void __launch_bounds__(PAGE_THREADS)
+update_pages_kernel(const K *__restrict__ keys2, const unsigned long long *__restrict__ cursors2,
+                    uint64_t cap2, uint32_t k, bool check_palindrome, Table<K> t, bool fresh) {
+    typedef KeyTraits<K> T;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const uint32_t P = 1u << t.page_log2, page_mask = t.page_mask;
+    K *sk = (K *)smem;
+    uint32_t *sw = (uint32_t *)(sk + P);
+    const uint64_t n_pages = t.n_pages();
+    for (uint64_t g = blockIdx.x; g < n_pages; g += gridDim.x) {
+        typename T::Slot *gs = t.slots + g * P;
+        if (fresh) {
+            for (uint32_t i = threadIdx.x; i < P; i += PAGE_THREADS) {
+                sk[i] = T::empty();
+                sw[i] = 0;
+            }
+        }
+        else {
+            for (uint32_t i = threadIdx.x; i < P; i += PAGE_THREADS) slot_to_smem(gs + i, sk + i, sw + i);
+        }
+        __syncthreads();
+        const uint64_t beg = g * cap2, lim = beg + cap2, cur = cursors2[g];
+        const uint32_t n = (uint32_t)((cur < lim ? cur : lim) - beg);
+        const K *src = keys2 + beg;
+        for (uint32_t i0 = threadIdx.x; i0 < n; i0 += PAGE_THREADS * PAGE_UNROLL) {
+            K my[PAGE_UNROLL];
+#pragma unroll
+            for (int q = 0; q < PAGE_UNROLL; ++q) {
+                const uint32_t i = i0 + q * PAGE_THREADS;
+                my[q] = i < n ? T::load_stream(&src[i]) : T::empty();
+            }
+#pragma unroll
+            for (int q = 0; q < PAGE_UNROLL; ++q) {
+                const uint32_t i = i0 + q * PAGE_THREADS;
+                if (i < n) {
+                    const uint32_t inc = (check_palindrome && revcomp(my[q], k) == my[q]) ? 2u : 1u;
+                    page_add(sk, sw, page_mask, t, my[q], inc);
+                }
+            }
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < P; i += PAGE_THREADS) smem_to_slot(gs + i, sk + i, sw + i);
+        __syncthreads();
+    }
+}
+
+// K3 with L2 atomics over an array of canonical keys (small batches against a
+// large table, spill lists, keys received from peers).  Keys arrive grouped by
+// sub-table.  Tiles are handed out through a global counter (persistent CTAs,
+// dynamic scheduling) instead of a static grid-stride: with a static split the
+// SMs drift apart over the ~1000 iterations (near/far L2 latency differs per
+// SM), the in-flight keys end up spread over many sub-tables and the working
+// set falls out of L2 (ncu: 27 GB of DRAM reads for 322 M inserts).  With the
+// counter every CTA works at the global frontier, i.e. on the one or two
+// sub-tables that are L2 resident.
 constexpr int INSERT_TILE_PER_THREAD = 8;
 constexpr uint64_t INSERT_TILE = 256 * INSERT_TILE_PER_THREAD;
-// bin_end == nullptr: keys[0, n) is dense.  Otherwise bin b holds
-// keys[b*bucket_cap, min(bin_end[b], (b+1)*bucket_cap)) (one-pass partitioner)
-// and tile t covers bin t / tiles_per_bin, tile t % tiles_per_bin of that bin.
+// bin_end == nullptr: keys[0, n) is dense (n_dev != nullptr: n = min(*n_dev, n)).
+// Otherwise bin b holds keys[b*bucket_cap, min(bin_end[b], (b+1)*bucket_cap))
+// (one-pass partitioner) and tile t covers bin t / tiles_per_bin.
 template <class K>
 __global__ void __launch_bounds__(256)
-insert_keys_kernel(const K *__restrict__ keys, uint64_t n, uint32_t k, bool check_palindrome,
-                   Table<K> t, unsigned long long *tile_counter,
+insert_keys_kernel(const K *__restrict__ keys, uint64_t n, const unsigned long long *__restrict__ n_dev,
+                   unsigned long long *lost, uint32_t k, bool check_palindrome, Table<K> t, unsigned long long *tile_counter,
                    const unsigned long long *__restrict__ bin_end, uint64_t bucket_cap,
                    uint64_t tiles_per_bin, uint64_t n_tiles) {
     __shared__ unsigned long long s_tile;
+    if (n_dev) {
+        const uint64_t m = *n_dev;
+        if (m > n && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(lost, (unsigned long long)(m - n));
+        n = m < n ? m : n;
+        n_tiles = (n + INSERT_TILE - 1) / INSERT_TILE;
+    }
     for (;;) {
         if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1ull);
         __syncthreads();

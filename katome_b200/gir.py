@@ -79,10 +79,11 @@ class GpuGIR:
     def __init__(self, k: int = 40, reverse_complement: bool = True, *, edges_count: Optional[int] = None,
                  device: int = -1, stream: Optional[int] = None, world_size: int = 1, rank: int = 0,
                  profile: bool = False, force_direct: bool = False, force_partition: bool = False,
-                 sub_table_log2_bytes: int = 0):
+                 force_pages: bool = False, no_pages: bool = False, sub_table_log2_bytes: int = 0):
         self._L = L.lib()
         flags = (L.KTG_FLAG_PROFILE if profile else 0) | (L.KTG_FLAG_FORCE_DIRECT if force_direct else 0) | \
-                (L.KTG_FLAG_FORCE_PARTITION if force_partition else 0)
+                (L.KTG_FLAG_FORCE_PARTITION if force_partition else 0) | \
+                (L.KTG_FLAG_FORCE_PAGES if force_pages else 0) | (L.KTG_FLAG_NO_PAGES if no_pages else 0)
         # stream=None: the handle creates its own stream.  A torch stream handle of 0 means the
         # legacy default stream, which the C ABI spells cudaStreamLegacy (0x1), since NULL = "own".
         if stream is not None and int(stream) == 0:

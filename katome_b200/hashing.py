@@ -51,11 +51,23 @@ def canonical(hi, lo, k: int):
     return np.where(less, rhi, hi), np.where(less, rlo, lo)
 
 
+def mix64(x: np.ndarray) -> np.ndarray:
+    """placement hash of common.cuh: two multiply / fold-by-32 rounds"""
+    x = np.asarray(x, dtype=np.uint64).copy()
+    with np.errstate(over="ignore"):
+        x *= np.uint64(0x9E3779B97F4A7C15)
+        x ^= x >> np.uint64(32)
+        x *= np.uint64(0xD6E8FEB86659FD93)
+        x ^= x >> np.uint64(32)
+    return x
+
+
 def key_hash(hi, lo, k: int) -> np.ndarray:
     lo = np.asarray(lo, dtype=np.uint64)
     if k <= 32:
-        return fmix64(lo ^ _SALT)
-    return fmix64(lo ^ fmix64(np.asarray(hi, dtype=np.uint64) ^ _SALT))
+        return mix64(lo)
+    with np.errstate(over="ignore"):
+        return mix64(lo ^ (np.asarray(hi, dtype=np.uint64) * np.uint64(0xA24BAED4963EE407)))
 
 
 def owner_of(hi, lo, k: int, world: int, reverse_complement: bool = True) -> np.ndarray:

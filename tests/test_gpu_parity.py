@@ -165,6 +165,58 @@ def test_direct_and_partitioned_paths_agree(K, k):
         g.close()
 
 
+@pytest.mark.parametrize("k", [4, 21, 31, 32, 33, 40, 63, 64])
+@pytest.mark.parametrize("rc", [False, True])
+def test_paged_update_path(K, k, rc):
+    """two-level partition + streaming page update (shared-memory inserts), several batches,
+    fresh and non-fresh tables, palindromes (even k) and the all-T key at full width"""
+    rng = np.random.default_rng(31 * k + rc)
+    genome = "".join(rng.choice(list("ACGT"), size=30000))
+    seqs = H.random_reads(rng, 4000, max(k, 60), 160, genome=genome, n_rate=0.02)
+    seqs += ["T" * (k + 20), "A" * (k + 7), "AT" * 60, "ACGT" * 40]
+    cpu = _oracle(seqs, k, rc)
+    for kw in ({}, {"sub_table_log2_bytes": 18}, {"edges_count": 2 * 30000 * 3}):
+        g = K.GpuGIR(k, rc, force_pages=True, **kw)
+        third = len(seqs) // 3
+        for part in (seqs[:third], seqs[third:2 * third], seqs[2 * third:]):
+            g.add_reads(*H.batch_of(part))
+        _assert_same(g, cpu)
+        info = g.info()
+        assert info["page_updates"] == 3 and info["partitioned"] == 1
+        g.reset()
+        g.add_reads(*H.batch_of(seqs))
+        _assert_same(g, cpu, full_stats=False)
+        g.close()
+
+
+def test_paged_and_atomic_paths_agree_at_scale(K):
+    """mini-C2 shape, default path selection (page update) against L2 atomics only"""
+    from katome_b200.workloads import Workload
+    wl = Workload("mini-C2", 1, 1_000_000, 100, 40, 5000, 31)
+    n, L = wl.n_reads, wl.read_len
+    d = torch.empty(n * L, dtype=torch.uint8, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    K.synth_reads_device(d, wl.seed, wl.genome_len, L, wl.err_ppm, 0, n, stream=s)
+    offs = torch.arange(0, (n + 1) * L, L, dtype=torch.int64, device="cuda")
+    res = []
+    for kw in ({}, {"no_pages": True}, {"sub_table_log2_bytes": 20}):
+        g = K.GpuGIR(31, True, stream=s, edges_count=wl.expected_distinct_edges(), **kw)
+        g.add_reads_device(d, offs, n, n * L)
+        res.append((g.digest(), g.counts()))
+        assert g.info()["page_updates"] == (0 if "no_pages" in kw else 1)
+        assert g.digest()[2] == 2 * wl.n_windows
+        g.close()
+    assert res[0] == res[1] == res[2]
+    # k = 63: u128 keys, 128-bit shared-memory CAS
+    res = []
+    for kw in ({}, {"no_pages": True}):
+        g = K.GpuGIR(63, True, stream=s, **kw)
+        g.add_reads_device(d, offs, n, n * L)
+        res.append((g.digest(), g.counts()))
+        g.close()
+    assert res[0] == res[1] and res[0][0][2] == 2 * n * (L - 63 + 1)
+
+
 def test_all_T_at_full_key_width_without_canonicalisation(K):
     """k=32 / k=64, reverse_complement=false: TTT...T equals the all-ones 'empty' marker"""
     for k in (32, 64):
