@@ -362,7 +362,9 @@ template <class K> struct Builder : BuilderBase {
         if (cfg.flags & (KTG_FLAG_FORCE_PARTITION | KTG_FLAG_FORCE_PAGES)) return true;
         return tab.n_sub > 3; // up to ~48 MB of table is L2 resident as a whole
     }
-    static size_t page_smem_bytes() { return ((size_t)1 << PageGeom<K>::LOG2) * (sizeof(K) + 4); }
+    static size_t page_smem_bytes(uint32_t page_log2 = PageGeom<K>::LOG2) {
+        return (((size_t)1 << page_log2) + (PAGE_THREADS / 32) * PQ_CAP) * (sizeof(K) + 4);
+    }
     // Streaming page update or L2 atomics?  The sweep reads and writes every slot
     // (32 B per slot of traffic), the atomic path costs ~2 L2 transactions per key:
     // the sweep wins once the batch has about as many keys as the table has slots.
@@ -685,7 +687,7 @@ template <class K> struct Builder : BuilderBase {
         prof.begin("scatter_pages", n_keys, stream);
         scatter_pages_kernel<K><<<g, L2S_THREADS, ss, stream>>>((const K *)b_keys.p, curs_ptr(n_bins), cap1, tiles_per_bin, n_tiles, tab, o);
         prof.end(stream);
-        const size_t ps = ((size_t)1 << tab.page_log2) * (sizeof(K) + 4);
+        const size_t ps = page_smem_bytes(tab.page_log2);
         g = (int)std::min<uint64_t>(grid_for(update_pages_kernel<K>, PAGE_THREADS, ps, props), n_pages);
         prof.begin("update_pages", n_keys, stream);
         update_pages_kernel<K><<<g, PAGE_THREADS, ps, stream>>>((const K *)b_pkeys.p, cur2, cap2, k, rc && (k % 2 == 0), tab, fresh);

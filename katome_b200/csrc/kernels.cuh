@@ -494,7 +494,8 @@ __global__ void scan_bins_kernel(const unsigned long long *__restrict__ hist, ui
 template <class K, int TILE> struct ScatterSmem {
     K *keys;                   // TILE
     uint32_t *delta;           // TILE: output position minus position in the sorted tile
-    uint32_t *cnt, *loc;       // 2 x n_bins (double buffered), n_bins
+    uint32_t *cnt;             // 2 x n_bins (double buffered)
+    uint2 *ld;                 // n_bins: {start in the sorted tile, output position minus that start}
     unsigned long long *glob;  // n_bins: reserved start in the bin's HBM range
     unsigned long long *spill; // n_bins: reserved start in the overflow array
     uint32_t *regs;            // HLL_M (only with HLL)
@@ -502,13 +503,13 @@ template <class K, int TILE> struct ScatterSmem {
         keys = (K *)base;
         glob = (unsigned long long *)(keys + TILE);
         spill = glob + n_bins;
-        delta = (uint32_t *)(spill + n_bins);
+        ld = (uint2 *)(spill + n_bins);
+        delta = (uint32_t *)(ld + n_bins);
         cnt = delta + TILE;
-        loc = cnt + 2 * n_bins;
-        regs = loc + n_bins;
+        regs = cnt + 2 * n_bins;
     }
     static size_t bytes(uint32_t n_bins, bool hll) {
-        return (size_t)TILE * (sizeof(K) + 4) + (size_t)n_bins * 28 + (hll ? HLL_M * 4 : 0);
+        return (size_t)TILE * (sizeof(K) + 4) + (size_t)n_bins * 32 + (hll ? HLL_M * 4 : 0);
     }
 };
 
@@ -563,9 +564,9 @@ __device__ __forceinline__ void tile_scatter(const K (&key)[PER], const uint32_t
         uint32_t run = s_warp[threadIdx.x >> 5] + incl - s;
         for (uint32_t i = b0; i < b0 + per && i < n_bins; ++i) {
             const uint32_t c = cnt[i];
-            sm.loc[i] = run;
+            unsigned long long base = 0;
             if (c) {
-                const unsigned long long base = atomicAdd(&cursors[i], (unsigned long long)c);
+                base = atomicAdd(&cursors[i], (unsigned long long)c);
                 sm.glob[i] = base;
                 if (o.bucket_cap) {
                     const unsigned long long lim = (bin_off + i + 1) * o.bucket_cap;
@@ -576,6 +577,7 @@ __device__ __forceinline__ void tile_scatter(const K (&key)[PER], const uint32_t
                     }
                 }
             }
+            sm.ld[i] = make_uint2(run, (uint32_t)base - run);
             run += c;
         }
     }
@@ -583,9 +585,10 @@ __device__ __forceinline__ void tile_scatter(const K (&key)[PER], const uint32_t
 #pragma unroll
     for (int j = 0; j < PER; ++j)
         if (j < nvalid) {
-            const uint32_t l = sm.loc[bin[j]], pos = l + rank[j];
+            const uint2 v = sm.ld[bin[j]];
+            const uint32_t pos = v.x + rank[j];
             sm.keys[pos] = key[j];
-            sm.delta[pos] = (uint32_t)sm.glob[bin[j]] - l;
+            sm.delta[pos] = v.y;
         }
     {   // the other counter buffer is free now: zero it for the next tile
         uint32_t *nxt = sm.cnt + (parity ^ 1u) * n_bins;
@@ -602,12 +605,12 @@ __device__ __forceinline__ void tile_scatter(const K (&key)[PER], const uint32_t
             uint32_t lo = 0, hi = n_bins - 1; // last bin with loc <= i and a non-empty count
             while (lo < hi) {
                 uint32_t mid = (lo + hi + 1) >> 1;
-                if (sm.loc[mid] <= i) lo = mid;
+                if (sm.ld[mid].x <= i) lo = mid;
                 else hi = mid - 1;
             }
             const uint32_t b = lo;
             const unsigned long long lim = (bin_off + b + 1) * o.bucket_cap;
-            const unsigned long long dst = sm.glob[b] + (i - sm.loc[b]);
+            const unsigned long long dst = sm.glob[b] + (i - sm.ld[b].x);
             if (dst < lim) out[dst] = sm.keys[i];
             else {
                 const unsigned long long first = sm.glob[b] > lim ? sm.glob[b] : lim;
@@ -722,10 +725,10 @@ scatter_pages_kernel(const K *__restrict__ keys1, const unsigned long long *__re
     for (uint32_t i = threadIdx.x; i < 2 * n2; i += L2S_THREADS) sm.cnt[i] = 0;
     __syncthreads();
     uint32_t parity = 0;
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint64_t b = tile / tiles_per_bin;
+    for (uint32_t tile = blockIdx.x; tile < (uint32_t)n_tiles; tile += gridDim.x) {
+        const uint64_t b = tile / (uint32_t)tiles_per_bin;
         const uint64_t lim = (b + 1) * cap1, fill = fill1[b];
-        const uint64_t base = b * cap1 + (tile - b * tiles_per_bin) * L2S_TILE;
+        const uint64_t base = b * cap1 + (uint64_t)(tile - (uint32_t)b * (uint32_t)tiles_per_bin) * L2S_TILE;
         const uint64_t end = fill < lim ? fill : lim;
         if (base >= end) continue;
         K key[L2S_PER];
@@ -784,29 +787,80 @@ __device__ __forceinline__ u128 smem_load(const u128 *p) {
     return ((u128)hi << 64) | lo;
 }
 
+// One probe step for a whole warp.  Divergent per-lane probe loops cost the
+// MAXIMUM chain length of the 32 lanes per row (ncu: 138 warp instructions per
+// row of 32 keys, 58 % of them in the loop); instead every lane probes exactly
+// one slot, and the keys that are not resolved yet go to a warp-private retry
+// queue in shared memory that is drained in full rows of 32, so the work is the
+// SUM of the chain lengths.  Queue entry: key + (slot | probes << 13.. | inc2 << 31).
+constexpr uint32_t PQ_CAP = 64; // < 32 left over + <= 32 pushed per step
+constexpr uint32_t PQ_INC2 = 0x80000000u, PQ_SLOT_BITS = 13, PQ_SLOT_MASK = (1u << PQ_SLOT_BITS) - 1;
+
+template <class K> struct PageCtx {
+    K *sk;
+    uint32_t *sw;
+    K *qk;        // this warp's queue
+    uint32_t *qi;
+    uint32_t qn;  // warp-uniform
+    uint32_t page_mask;
+};
+
+// all 32 lanes call this together; `active` lanes carry (key, st)
 template <class K>
-__device__ __forceinline__ void page_add(K *sk, uint32_t *sw, uint32_t page_mask, const Table<K> &t,
-                                         K key, uint32_t inc) {
+__device__ __forceinline__ void page_probe_rows(PageCtx<K> &c, const Table<K> &t, K key, uint32_t st, bool active) {
     typedef KeyTraits<K> T;
     const K EMPTY = T::empty();
-    if (key == EMPTY) { // all-T at full key width (only without canonicalisation)
-        atomicAdd(&t.slots[t.capacity()].w, inc);
-        return;
-    }
-    uint32_t i = (uint32_t)T::hash(key) & page_mask;
-    for (uint32_t n = 0; n <= page_mask; ++n) {
-        K cur = smem_load(&sk[i]);
-        if (cur != key && (cur == EMPTY || T::maybe_torn(cur))) cur = smem_cas(&sk[i], EMPTY, key);
-        if (cur == key || cur == EMPTY) {
-            atomicAdd(&sw[i], inc);
-            return;
+    const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
+    for (;;) {
+        bool pending = false;
+        if (active) {
+            const uint32_t i = st & PQ_SLOT_MASK, inc = (st & PQ_INC2) ? 2u : 1u;
+            K cur = smem_load(&c.sk[i]);
+            if (cur != key && (cur == EMPTY || T::maybe_torn(cur))) cur = smem_cas(&c.sk[i], EMPTY, key);
+            if (cur == key || cur == EMPTY) atomicAdd(&c.sw[i], inc);
+            else {
+                const uint32_t probes = ((st & ~PQ_INC2) >> PQ_SLOT_BITS) + 1;
+                if (probes > c.page_mask) { // every slot of the page holds another key: replay after a grow
+                    unsigned long long pos = atomicAdd(t.ovf_count, 1ull);
+                    if (pos < t.ovf_cap) {
+                        t.ovf_keys[pos] = key;
+                        t.ovf_inc[pos] = inc;
+                    }
+                }
+                else {
+                    st = (st & PQ_INC2) | (probes << PQ_SLOT_BITS) | ((i + 1) & c.page_mask);
+                    pending = true;
+                }
+            }
         }
-        i = (i + 1) & page_mask;
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, pending);
+        if (pending) {
+            const uint32_t pos = c.qn + __popc(m & lt);
+            c.qk[pos] = key;
+            c.qi[pos] = st;
+        }
+        c.qn += __popc(m);
+        __syncwarp();
+        if (c.qn < 32) return;
+        c.qn -= 32;
+        key = c.qk[c.qn + lane];
+        st = c.qi[c.qn + lane];
+        active = true;
+        __syncwarp();
     }
-    unsigned long long pos = atomicAdd(t.ovf_count, 1ull); // page full: replayed after a grow
-    if (pos < t.ovf_cap) {
-        t.ovf_keys[pos] = key;
-        t.ovf_inc[pos] = inc;
+}
+
+// the partial row left in the queue at the end of a page
+template <class K> __device__ __forceinline__ void page_drain(PageCtx<K> &c, const Table<K> &t) {
+    const uint32_t lane = threadIdx.x & 31;
+    while (c.qn) {
+        const uint32_t cnt = c.qn; // < 32
+        const bool active = lane < cnt;
+        K key = active ? c.qk[lane] : KeyTraits<K>::empty();
+        uint32_t st = active ? c.qi[lane] : 0;
+        c.qn = 0;
+        __syncwarp();
+        page_probe_rows(c, t, key, st, active);
     }
 }
 
@@ -835,43 +889,55 @@ update_pages_kernel(const K *__restrict__ keys2, const unsigned long long *__res
                     uint64_t cap2, uint32_t k, bool check_palindrome, Table<K> t, bool fresh) {
     typedef KeyTraits<K> T;
     extern __shared__ __align__(16) unsigned char smem[];
-    const uint32_t P = 1u << t.page_log2, page_mask = t.page_mask;
-    K *sk = (K *)smem;
-    uint32_t *sw = (uint32_t *)(sk + P);
+    const uint32_t P = 1u << t.page_log2;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    PageCtx<K> c;
+    c.sk = (K *)smem;
+    c.qk = c.sk + P + wid * PQ_CAP;
+    c.sw = (uint32_t *)(c.sk + P + (PAGE_THREADS / 32) * PQ_CAP);
+    c.qi = c.sw + P + wid * PQ_CAP;
+    c.qn = 0;
+    c.page_mask = t.page_mask;
     const uint64_t n_pages = t.n_pages();
     for (uint64_t g = blockIdx.x; g < n_pages; g += gridDim.x) {
         typename T::Slot *gs = t.slots + g * P;
         if (fresh) {
             for (uint32_t i = threadIdx.x; i < P; i += PAGE_THREADS) {
-                sk[i] = T::empty();
-                sw[i] = 0;
+                c.sk[i] = T::empty();
+                c.sw[i] = 0;
             }
         }
         else {
-            for (uint32_t i = threadIdx.x; i < P; i += PAGE_THREADS) slot_to_smem(gs + i, sk + i, sw + i);
+            for (uint32_t i = threadIdx.x; i < P; i += PAGE_THREADS) slot_to_smem(gs + i, c.sk + i, c.sw + i);
         }
         __syncthreads();
         const uint64_t beg = g * cap2, lim = beg + cap2, cur = cursors2[g];
         const uint32_t n = (uint32_t)((cur < lim ? cur : lim) - beg);
         const K *src = keys2 + beg;
-        for (uint32_t i0 = threadIdx.x; i0 < n; i0 += PAGE_THREADS * PAGE_UNROLL) {
+        // a warp takes PAGE_UNROLL consecutive rows of 32 keys at a time
+        for (uint32_t r0 = wid * 32 * PAGE_UNROLL; r0 < n; r0 += PAGE_THREADS * PAGE_UNROLL) {
             K my[PAGE_UNROLL];
 #pragma unroll
             for (int q = 0; q < PAGE_UNROLL; ++q) {
-                const uint32_t i = i0 + q * PAGE_THREADS;
+                const uint32_t i = r0 + q * 32 + lane;
                 my[q] = i < n ? T::load_stream(&src[i]) : T::empty();
             }
 #pragma unroll
             for (int q = 0; q < PAGE_UNROLL; ++q) {
-                const uint32_t i = i0 + q * PAGE_THREADS;
-                if (i < n) {
-                    const uint32_t inc = (check_palindrome && revcomp(my[q], k) == my[q]) ? 2u : 1u;
-                    page_add(sk, sw, page_mask, t, my[q], inc);
+                const uint32_t i = r0 + q * 32 + lane;
+                bool active = i < n;
+                if (active && my[q] == T::empty()) { // all-T at full key width (only without canonicalisation)
+                    atomicAdd(&t.slots[t.capacity()].w, 1u);
+                    active = false;
                 }
+                uint32_t st = (uint32_t)T::hash(my[q]) & c.page_mask;
+                if (check_palindrome && revcomp(my[q], k) == my[q]) st |= PQ_INC2;
+                page_probe_rows(c, t, my[q], st, active);
             }
         }
+        page_drain(c, t);
         __syncthreads();
-        for (uint32_t i = threadIdx.x; i < P; i += PAGE_THREADS) smem_to_slot(gs + i, sk + i, sw + i);
+        for (uint32_t i = threadIdx.x; i < P; i += PAGE_THREADS) smem_to_slot(gs + i, c.sk + i, c.sw + i);
         __syncthreads();
     }
 }
