@@ -215,7 +215,15 @@ def run_ours(args):
                 return sg.digest()
         estep()
         barrier()
-        t0 = time.perf_counter()
+        # the PCIe floor of this step: the same bytes, copy only
+        e0.record()
+        for _ in range(3):
+            d_bases[: n_local * L].copy_(h_bases, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        h2d_ms = e0.elapsed_time(e1) / 3
+        barrier()
+        builder.reset_profile()
         e0.record()
         for _ in range(args.steps):
             edig = estep()
@@ -227,9 +235,13 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ems = float(t.item())
         assert edig == dig, (edig, dig)
+        eprof = builder.profile()
         e2e = {"value": windows_total / (ems / args.steps * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": (n_local * L + (n_local + 1) * 8) * world, "d2h_bytes_per_step": 40 * world,
-               "ms_per_step": ems / args.steps}
+               "ms_per_step": ems / args.steps, "h2d_copy_only_ms": h2d_ms,
+               "h2d_gbs": n_local * L / h2d_ms / 1e6,
+               "kernels": {n: {"launches": p["launches"], "ms_per_step": p["ms"] / args.steps}
+                           for n, p in eprof.items() if p["launches"]}}
 
     if rank != 0:
         if world > 1:

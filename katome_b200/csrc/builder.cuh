@@ -5,7 +5,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <string>
 #include <vector>
 
@@ -40,6 +42,18 @@ inline int fail(int code, const char *fmt, ...) {
         int ktg_try_rc__ = (expr);                                                             \
         if (ktg_try_rc__ != KTG_OK) return ktg_try_rc__;                                       \
     } while (0)
+
+// host-side timeline for tuning (KTG_TRACE=1): label + microseconds since the first event
+inline void trace(const char *label, uint64_t v = 0) {
+    static const bool on = getenv("KTG_TRACE") != nullptr;
+    if (!on) return;
+    static timespec t0{};
+    timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    if (t0.tv_sec == 0 && t0.tv_nsec == 0) t0 = t;
+    fprintf(stderr, "[ktg %9.1f us] %s %llu\n", (t.tv_sec - t0.tv_sec) * 1e6 + (t.tv_nsec - t0.tv_nsec) * 1e-3, label,
+            (unsigned long long)v);
+}
 
 // grow-only device buffer
 struct DeviceBuf {
@@ -164,6 +178,9 @@ struct BuilderBase {
     DeviceProps props;
     Profiler prof;
     int deferred_error = KTG_OK;
+    // recorded on the compute stream as soon as the pack kernel has consumed the caller's
+    // read buffer (the host batcher reuses its staging buffer then, not a whole flush later)
+    cudaEvent_t input_consumed = nullptr;
     uint64_t windows_inserted = 0;
     uint32_t grow_events = 0;
 
@@ -225,7 +242,7 @@ template <class K> struct Builder : BuilderBase {
         if (tab.slots) cudaFree(tab.slots);
         b_packed.release(); b_nstart.release(); b_keys.release(); b_keys2.release();
         b_hist.release(); b_hll.release(); b_spill.release(); b_ovf_keys.release(); b_ovf_inc.release(); b_small.release();
-        b_pkeys.release(); b_pcur.release(); b_pspill.release();
+        b_pkeys.release(); b_pcur.release(); b_pspill.release(); b_stage_cur.release();
         if (copy_stream) cudaStreamDestroy(copy_stream);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
@@ -258,7 +275,9 @@ template <class K> struct Builder : BuilderBase {
         uint32_t slb = cfg.sub_table_log2_bytes ? cfg.sub_table_log2_bytes : 24;
         geometry(need_slots, slb, &t.n_sub, &t.sub_log2);
         t.sub_mask = (uint32_t)((1ull << t.sub_log2) - 1);
-        t.page_log2 = std::min<uint32_t>(PageGeom<K>::LOG2, t.sub_log2);
+        uint32_t pl = PageGeom<K>::LOG2;
+        if (const char *e = getenv("KTG_PAGE_LOG2")) pl = std::min<uint32_t>(pl, std::max(8, atoi(e))); // tuning knob
+        t.page_log2 = std::min<uint32_t>(pl, t.sub_log2);
         t.page_mask = (1u << t.page_log2) - 1;
         t.max_probe = std::min<uint32_t>(1u << t.page_log2, 2048);
         size_t bytes = (t.capacity() + 1) * sizeof(Slot);
@@ -376,7 +395,9 @@ template <class K> struct Builder : BuilderBase {
     }
 
     int sync() {
+        trace("sync>");
         KTG_CUDA(cudaStreamSynchronize(stream));
+        trace("sync<");
         prof.resolve();
         return KTG_OK;
     }
@@ -533,6 +554,7 @@ template <class K> struct Builder : BuilderBase {
         else if (group == 8) launch(pack_reads_kernel<8>, 8);
         else launch(pack_reads_kernel<32>, 32);
         prof.end(stream);
+        if (input_consumed) KTG_CUDA(cudaEventRecord(input_consumed, stream));
         nodes_valid = false;
         PackCounters c;
         KTG_CUDA(cudaMemcpyAsync(&c, d_ctr, sizeof c, cudaMemcpyDeviceToHost, stream));
@@ -663,7 +685,7 @@ template <class K> struct Builder : BuilderBase {
     // Level-2 scatter of the level-1 buckets by page, then the streaming page update.
     // Page-bucket overflow goes to a spill list that is inserted with L2 atomics
     // afterwards (count stays on the device: no host round trip).
-    int paged_update(uint32_t n_bins, uint64_t cap1, uint64_t n_keys) {
+    int paged_update(uint32_t n_bins, uint64_t cap1, uint64_t n_keys, const unsigned long long *fill1) {
         const uint64_t n_pages = tab.n_pages();
         const uint64_t cap2 = page_bucket_cap_for(n_keys, n_pages);
         const uint64_t spill_cap = std::max<uint64_t>(1u << 20, n_keys / 32);
@@ -685,7 +707,7 @@ template <class K> struct Builder : BuilderBase {
         const size_t ss = ScatterSmem<K, L2S_TILE>::bytes(tab.pages_per_sub(), false);
         int g = (int)std::min<uint64_t>(grid_for(scatter_pages_kernel<K>, L2S_THREADS, ss, props), n_tiles);
         prof.begin("scatter_pages", n_keys, stream);
-        scatter_pages_kernel<K><<<g, L2S_THREADS, ss, stream>>>((const K *)b_keys.p, curs_ptr(n_bins), cap1, tiles_per_bin, n_tiles, tab, o);
+        scatter_pages_kernel<K><<<g, L2S_THREADS, ss, stream>>>((const K *)b_keys.p, fill1, cap1, tiles_per_bin, n_tiles, tab, o);
         prof.end(stream);
         const size_t ps = page_smem_bytes(tab.page_log2);
         g = (int)std::min<uint64_t>(grid_for(update_pages_kernel<K>, PAGE_THREADS, ps, props), n_pages);
@@ -701,10 +723,32 @@ template <class K> struct Builder : BuilderBase {
         return KTG_OK;
     }
 
-    // One-pass partition by sub-table + insert.  `scatter(o)` runs the scatter kernel
-    // (which also feeds the cardinality sketch) for the current table geometry;
-    // `n_keys` is the exact number of keys it will emit.
-    template <class S> int partitioned_insert(uint64_t n_keys, S scatter) {
+    // ---- staging -------------------------------------------------------------------
+    // Batches are not inserted one by one: their keys are partitioned by sub-table
+    // (level 1) into buckets that persist across batches, and the buckets are flushed
+    // into the table when about as many keys are staged as the table has slots (one
+    // sweep of the table then serves all of them), when the next batch would not fit,
+    // or when the build is finalised / queried.  With host input this also lets the
+    // H2D copy of the following chunks overlap the flush.
+    uint32_t stage_bins = 0;      // n_sub the buckets are laid out for (0: no open stage)
+    uint32_t stage_sub_log2 = 0;
+    uint64_t stage_cap1 = 0;      // bucket capacity per sub-table
+    uint64_t stage_room = 0;      // keys the open stage was sized for
+    uint64_t stage_target = 0;    // flush once this many keys are staged
+    uint64_t stage_spill_cap = 0;
+    uint64_t staged_keys = 0;     // keys in the buckets + spill list
+    uint64_t staged_spilled = 0;  // of which in the spill list
+    DeviceBuf b_stage_cur;        // cursors[n_bins] | spill cursor | backup of both
+    unsigned long long *stage_cursors() { return (unsigned long long *)b_stage_cur.p; }
+    unsigned long long *stage_spill_cursor() { return stage_cursors() + stage_bins; }
+
+    uint64_t stage_max_keys() const {
+        const char *e = getenv("KTG_STAGE_MAX_KEYS"); // tuning knob
+        if (e) return std::max<uint64_t>(1u << 16, strtoull(e, nullptr, 10));
+        return sizeof(K) == 8 ? (1ull << 30) : (1ull << 29); // 8 GiB of staged keys
+    }
+
+    int stage_open(uint64_t batch_keys) {
         if (!sketch_complete) { // keys went in unsketched (direct path): restart from the exact count
             uint64_t exact = 0;
             KTG_TRY(count_occupied(&exact));
@@ -712,32 +756,86 @@ template <class K> struct Builder : BuilderBase {
             sketch_complete = true;
             KTG_CUDA(cudaMemsetAsync(b_hll.p, 0, HLL_M * 4, stream));
         }
-        for (int attempt = 0;; ++attempt) {
-            const uint32_t n_bins = tab.n_sub;
-            const uint64_t cap = bucket_cap_for(n_keys, n_bins);
-            const uint64_t spill_cap = std::max<uint64_t>(1u << 20, n_keys / 32);
-            KTG_TRY(ensure_hist(n_bins));
-            KTG_TRY(b_keys.ensure(cap * n_bins * sizeof(K) + 64));
-            KTG_TRY(b_spill.ensure(spill_cap * sizeof(K) + 64));
-            KTG_TRY(scan_bins_pass(n_bins, cap));
-            ScatterOut o = scatter_out(n_bins, cap, b_keys.p, b_spill.p, spill_cap);
-            KTG_TRY(scatter(n_bins, o));
-            unsigned long long spilled = 0;
-            KTG_CUDA(cudaMemcpyAsync(&spilled, spill_ptr(n_bins), 8, cudaMemcpyDeviceToHost, stream));
-            double est = 0;
-            KTG_TRY(hll_estimate(&est)); // synchronises the stream
-            uint64_t distinct = hll_base + (uint64_t)(est * 1.08) + 64;
-            occupied_ub = distinct;
-            if ((double)distinct > LOAD_MAX * (double)tab.capacity() && attempt < 2) {
-                KTG_TRY(grow_to((uint64_t)((double)distinct / LOAD_TARGET) + 1)); // geometry changed: redo
-                continue;
-            }
-            if (spilled > spill_cap) return KTG_ERR_TABLE_FULL + 1000; // caller falls back to the exact path
-            if (use_pages(n_keys)) KTG_TRY(paged_update(n_bins, cap, n_keys));
-            else KTG_TRY(launch_insert((const K *)b_keys.p, n_keys, curs_ptr(n_bins), cap, n_bins));
-            if (spilled) KTG_TRY(launch_insert_keys((const K *)b_spill.p, spilled));
+        const uint32_t n_bins = tab.n_sub;
+        double factor = 1.0;
+        if (const char *e = getenv("KTG_STAGE_FACTOR")) factor = atof(e); // tuning knob
+        stage_target = std::min<uint64_t>((uint64_t)(factor * (double)tab.capacity()), stage_max_keys());
+        stage_room = batch_keys >= stage_target ? batch_keys : stage_target + batch_keys;
+        stage_cap1 = bucket_cap_for(stage_room, n_bins);
+        stage_spill_cap = std::max<uint64_t>(1u << 20, stage_room / 16);
+        if ((double)stage_cap1 * n_bins >= 4.0e9) return fail(KTG_ERR_INVALID, "batch too large: split it (32-bit bucket positions)");
+        KTG_TRY(b_keys.ensure(stage_cap1 * n_bins * sizeof(K) + 64));
+        KTG_TRY(b_spill.ensure(stage_spill_cap * sizeof(K) + 64));
+        KTG_TRY(b_stage_cur.ensure(2 * ((size_t)n_bins + 1) * 8));
+        stage_bins = n_bins;
+        stage_sub_log2 = tab.sub_log2;
+        init_cursors_kernel<<<(n_bins + 255) / 256, 256, 0, stream>>>(stage_cursors(), n_bins, stage_cap1);
+        KTG_CUDA(cudaMemsetAsync(stage_spill_cursor(), 0, 8, stream));
+        staged_keys = staged_spilled = 0;
+        return KTG_OK;
+    }
+
+    // Adds one batch to the stage.  `scatter(n_bins, o)` runs the level-1 scatter kernel
+    // (which also feeds the cardinality sketch); `n_keys` is the exact number of keys it
+    // emits.  Returns KTG_ERR_TABLE_FULL + 1000 if the batch is too skewed for the spill
+    // list; the stage is then exactly as before the call and the caller takes the exact path.
+    template <class S> int stage_add(uint64_t n_keys, S scatter) {
+        if (stage_bins != tab.n_sub || stage_sub_log2 != tab.sub_log2 || staged_keys + n_keys > stage_room) {
+            KTG_TRY(flush_staged());
+            KTG_TRY(stage_open(n_keys));
+        }
+        const size_t cur_bytes = ((size_t)stage_bins + 1) * 8;
+        KTG_CUDA(cudaMemcpyAsync(stage_cursors() + stage_bins + 1, stage_cursors(), cur_bytes, cudaMemcpyDeviceToDevice, stream));
+        ScatterOut o;
+        o.cursors = stage_cursors();
+        o.bucket_cap = stage_cap1;
+        o.out = b_keys.p;
+        o.spill_out = b_spill.p;
+        o.spill_cursor = stage_spill_cursor();
+        o.spill_cap = stage_spill_cap;
+        KTG_TRY(scatter(stage_bins, o));
+        unsigned long long spilled = 0;
+        KTG_CUDA(cudaMemcpyAsync(&spilled, stage_spill_cursor(), 8, cudaMemcpyDeviceToHost, stream));
+        KTG_TRY(sync());
+        if (spilled > stage_spill_cap) { // roll the stage back; nothing of this batch stays in it
+            KTG_CUDA(cudaMemcpyAsync(stage_cursors(), stage_cursors() + stage_bins + 1, cur_bytes, cudaMemcpyDeviceToDevice, stream));
+            return KTG_ERR_TABLE_FULL + 1000;
+        }
+        staged_spilled = spilled;
+        staged_keys += n_keys;
+        nodes_valid = false;
+        if (staged_keys >= stage_target) KTG_TRY(flush_staged());
+        return KTG_OK;
+    }
+
+    // Size the table for everything offered so far, then move the staged keys into it.
+    int flush_staged() {
+        if (staged_keys == 0) {
+            stage_bins = 0;
             return KTG_OK;
         }
+        trace("flush", staged_keys);
+        double est = 0;
+        KTG_TRY(hll_estimate(&est)); // synchronises the stream
+        const uint64_t distinct = hll_base + (uint64_t)(est * 1.08) + 64;
+        occupied_ub = distinct;
+        bool moved = false;
+        if ((double)distinct > LOAD_MAX * (double)tab.capacity()) {
+            // at least double, so that a stream of small batches grows O(log) times
+            const uint64_t need = std::max<uint64_t>((uint64_t)((double)distinct / LOAD_TARGET) + 1, 2 * tab.capacity());
+            KTG_TRY(grow_to(need));
+            moved = tab.n_sub != stage_bins || tab.sub_log2 != stage_sub_log2;
+        }
+        const uint64_t n = staged_keys, spilled = staged_spilled;
+        const uint32_t bins = stage_bins;
+        staged_keys = staged_spilled = 0;
+        stage_bins = 0; // the next batch opens a new stage (sized for the table as it is then)
+        // After a change of geometry the buckets no longer match the sub-tables: the keys are
+        // still all there, they just lose their L2 locality for this one flush.
+        if (!moved && use_pages(n)) KTG_TRY(paged_update(bins, stage_cap1, n, stage_cursors()));
+        else KTG_TRY(launch_insert((const K *)b_keys.p, n, stage_cursors(), stage_cap1, bins));
+        if (spilled) KTG_TRY(launch_insert_keys((const K *)b_spill.p, spilled));
+        return KTG_OK;
     }
 
     // ---- one batch of reads, all on the device ---------------------------------------
@@ -748,6 +846,7 @@ template <class K> struct Builder : BuilderBase {
             return fail(KTG_ERR_INVALID, "world_size > 1: use ktg_partition_reads_device + ktg_insert_keys_device");
         if (n_reads == 0) return KTG_OK;
         Batch bt;
+        trace("ingest", n_reads);
         KTG_TRY(pack(d_bases, d_offsets, n_reads, total_bases, &bt));
         if (bt.windows == 0) return KTG_OK;
         const uint64_t *packed = (const uint64_t *)b_packed.p;
@@ -777,16 +876,17 @@ template <class K> struct Builder : BuilderBase {
             prof.end(stream);
         }
         else {
-            int st = partitioned_insert(bt.windows, [&](uint32_t n_bins, const ScatterOut &o) -> int {
+            int st = stage_add(bt.windows, [&](uint32_t n_bins, const ScatterOut &o) -> int {
                 return scatter_reads_pass<false, true>(bt, n_bins, o);
             });
-            if (st == KTG_ERR_TABLE_FULL + 1000) { // heavy skew: exact two-pass partition
+            if (st == KTG_ERR_TABLE_FULL + 1000) { // heavy skew: exact two-pass partition, inserted at once
+                KTG_TRY(flush_staged()); // also sizes the table for this batch (it is in the sketch already)
                 const uint32_t n_bins = tab.n_sub;
                 KTG_TRY(hist_reads_pass<false>(bt, n_bins));
                 KTG_TRY(scan_bins_pass(n_bins, 0));
-                KTG_TRY(b_keys.ensure(bt.windows * sizeof(K) + 64));
-                KTG_TRY((scatter_reads_pass<false, false>(bt, n_bins, scatter_out(n_bins, 0, b_keys.p, nullptr, 0))));
-                KTG_TRY(launch_insert_keys((const K *)b_keys.p, bt.windows));
+                KTG_TRY(b_keys2.ensure(bt.windows * sizeof(K) + 64));
+                KTG_TRY((scatter_reads_pass<false, false>(bt, n_bins, scatter_out(n_bins, 0, b_keys2.p, nullptr, 0))));
+                KTG_TRY(launch_insert_keys((const K *)b_keys2.p, bt.windows));
             }
             else KTG_TRY(st);
         }
@@ -810,6 +910,7 @@ template <class K> struct Builder : BuilderBase {
 
     int finalize() override {
         if (deferred_error != KTG_OK) return fail(deferred_error, "build is void after an earlier error");
+        KTG_TRY(flush_staged());
         KTG_TRY(read_counters(nullptr, nullptr));
         unsigned long long lost = 0;
         KTG_CUDA(cudaMemcpyAsync(&lost, d_lost, 8, cudaMemcpyDeviceToHost, stream));
@@ -823,6 +924,9 @@ template <class K> struct Builder : BuilderBase {
     }
 
     int reset() override {
+        trace("reset");
+        staged_keys = staged_spilled = 0;
+        stage_bins = 0;
         fresh = true; // the next user of the table memory initialises it (ensure_init / page update)
         KTG_TRY(init_special_slot(tab));
         KTG_CUDA(cudaMemsetAsync(b_small.p, 0, 4096, stream));
@@ -841,6 +945,7 @@ template <class K> struct Builder : BuilderBase {
 
     // ---- stats ------------------------------------------------------------------------
     int edge_stats(uint32_t threshold, EdgeStats *out) override {
+        trace("edge_stats");
         KTG_TRY(finalize());
         KTG_TRY(ensure_init());
         KTG_CUDA(cudaMemsetAsync(d_scratch, 0, sizeof(EdgeStats), stream));
@@ -1005,13 +1110,13 @@ template <class K> struct Builder : BuilderBase {
         // NCCL wants dense per-destination ranges: exact two-pass partition by owner
         KTG_TRY(hist_reads_pass<true>(bt, W));
         KTG_TRY(scan_bins_pass(W, 0));
-        KTG_TRY(b_keys.ensure(bt.windows * sizeof(K) + 64));
-        KTG_TRY((scatter_reads_pass<true, false>(bt, W, scatter_out(W, 0, b_keys.p, nullptr, 0))));
+        KTG_TRY(b_keys2.ensure(bt.windows * sizeof(K) + 64));
+        KTG_TRY((scatter_reads_pass<true, false>(bt, W, scatter_out(W, 0, b_keys2.p, nullptr, 0))));
         std::vector<unsigned long long> h(W);
         KTG_CUDA(cudaMemcpyAsync(h.data(), hist_ptr(), W * 8, cudaMemcpyDeviceToHost, stream));
         KTG_TRY(sync()); // the caller hands the buffer to NCCL on its own stream
         for (uint32_t i = 0; i < W; ++i) counts[i] = h[i];
-        *d_keys = b_keys.p;
+        *d_keys = b_keys2.p;
         return KTG_OK;
     }
 
@@ -1031,15 +1136,13 @@ template <class K> struct Builder : BuilderBase {
             KTG_TRY(launch_insert_keys(keys, n));
         }
         else {
-            if (keys == (const K *)b_keys.p) { // scatter output must not alias its input
-                KTG_TRY(b_keys2.ensure(n * sizeof(K) + 64));
-                KTG_CUDA(cudaMemcpyAsync(b_keys2.p, keys, n * sizeof(K), cudaMemcpyDeviceToDevice, stream));
-                keys = (const K *)b_keys2.p;
-            }
-            int st = partitioned_insert(n, [&](uint32_t n_bins, const ScatterOut &o) -> int {
+            int st = stage_add(n, [&](uint32_t n_bins, const ScatterOut &o) -> int {
                 return scatter_keys_pass<true>(keys, n, n_bins, o);
             });
-            if (st == KTG_ERR_TABLE_FULL + 1000) KTG_TRY(launch_insert_keys(keys, n)); // skewed: no locality, still exact
+            if (st == KTG_ERR_TABLE_FULL + 1000) { // skewed: no locality, still exact
+                KTG_TRY(flush_staged());
+                KTG_TRY(launch_insert_keys(keys, n));
+            }
             else KTG_TRY(st);
         }
         KTG_CUDA(cudaGetLastError());
@@ -1052,11 +1155,12 @@ template <class K> struct Builder : BuilderBase {
             K r = revcomp(key, k);
             if (r < key) key = r;
         }
-        return place_of(T::hash(key), tab.world, tab.n_sub, tab.sub_mask).owner;
+        return place_of(T::hash(key), tab.world, tab.n_sub).owner;
     }
 
     int info(ktg_info *out) override {
         memset(out, 0, sizeof *out);
+        KTG_TRY(flush_staged());
         uint64_t occ = 0;
         KTG_TRY(count_occupied(&occ));
         out->capacity_slots = tab.capacity();

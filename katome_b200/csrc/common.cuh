@@ -64,6 +64,20 @@ __host__ __device__ __forceinline__ u128 revcomp(u128 x, uint32_t k) {
     return r >> (128 - 2 * k);
 }
 
+// Slot hash: murmur3's 32-bit finalizer over a multiplicative fold of the key
+// words.  Owner rank and sub-table come from the top bits of mix64; the slot
+// (and with it the page) comes from this cheaper, independent function, because
+// the level-2 scatter and the page update need nothing else (9 instructions
+// instead of 17 per key and pass).
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16;
+    x *= 0x85EBCA6Bu;
+    x ^= x >> 13;
+    x *= 0xC2B2AE35u;
+    x ^= x >> 16;
+    return x;
+}
+
 template <class K> struct KeyTraits;
 
 template <> struct KeyTraits<uint64_t> {
@@ -75,6 +89,9 @@ template <> struct KeyTraits<uint64_t> {
     };
     __host__ __device__ static __forceinline__ uint64_t empty() { return ~0ull; }
     __host__ __device__ static __forceinline__ uint64_t hash(uint64_t k) { return mix64(k); }
+    __host__ __device__ static __forceinline__ uint32_t slot_hash(uint64_t k) {
+        return mix32((uint32_t)k + (uint32_t)(k >> 32) * 0x9E3779B1u);
+    }
     __host__ __device__ static __forceinline__ uint64_t hi(uint64_t) { return 0; }
     __host__ __device__ static __forceinline__ uint64_t lo(uint64_t k) { return k; }
     __host__ __device__ static __forceinline__ uint64_t make(uint64_t, uint64_t lo_) { return lo_; }
@@ -104,6 +121,10 @@ template <> struct KeyTraits<u128> {
     __host__ __device__ static __forceinline__ u128 empty() { return ~(u128)0; }
     __host__ __device__ static __forceinline__ uint64_t hash(u128 k) {
         return mix64((uint64_t)k ^ ((uint64_t)(k >> 64) * 0xA24BAED4963EE407ull));
+    }
+    __host__ __device__ static __forceinline__ uint32_t slot_hash(u128 k) {
+        return mix32((uint32_t)k + (uint32_t)(k >> 32) * 0x9E3779B1u + (uint32_t)(k >> 64) * 0x85EBCA77u +
+                     (uint32_t)(k >> 96) * 0xC2B2AE3Du);
     }
     __host__ __device__ static __forceinline__ uint64_t hi(u128 k) { return (uint64_t)(k >> 64); }
     __host__ __device__ static __forceinline__ uint64_t lo(u128 k) { return (uint64_t)k; }
@@ -150,21 +171,19 @@ template <> struct KeyTraits<u128> {
 
 // Where a key lives: owner rank (hash sharding over GPUs), sub-table (the
 // L2-resident partition, = level-1 bin of the partitioner) and home slot inside
-// it; the high bits of the slot select the PAGE (the shared-memory sized unit of
+// it (slot_hash & sub_mask); the high bits of the slot select the PAGE (the shared-memory sized unit of
 // the streaming update, = level-2 bin) and linear probing wraps inside the page.
 // Disjoint pieces of one 64-bit hash, range-reduced by multiply-shift so that
 // world and n_sub need not be powers of two.
 struct Place {
-    uint32_t owner, part, slot;
+    uint32_t owner, part;
 };
-__host__ __device__ __forceinline__ Place place_of(uint64_t h, uint32_t world, uint32_t n_sub,
-                                                   uint32_t sub_mask) {
-    uint32_t hi = (uint32_t)(h >> 32), lo = (uint32_t)h;
+__host__ __device__ __forceinline__ Place place_of(uint64_t h, uint32_t world, uint32_t n_sub) {
+    uint32_t hi = (uint32_t)(h >> 32);
     uint64_t t = (uint64_t)hi * world;
     Place p;
     p.owner = (uint32_t)(t >> 32);
     p.part = (uint32_t)(((uint64_t)(uint32_t)t * n_sub) >> 32);
-    p.slot = lo & sub_mask;
     return p;
 }
 
@@ -196,9 +215,10 @@ __device__ __forceinline__ void table_add(const Table<K> &t, K key, uint32_t inc
         atomicAdd(&t.slots[t.capacity()].w, inc);
         return;
     }
-    Place p = place_of(T::hash(key), t.world, t.n_sub, t.sub_mask);
-    Slot *page = t.slots + ((uint64_t)p.part << t.sub_log2) + (p.slot & ~t.page_mask);
-    uint32_t i = p.slot & t.page_mask;
+    const Place p = place_of(T::hash(key), t.world, t.n_sub);
+    const uint32_t slot = T::slot_hash(key) & t.sub_mask;
+    Slot *page = t.slots + ((uint64_t)p.part << t.sub_log2) + (slot & ~t.page_mask);
+    uint32_t i = slot & t.page_mask;
     for (uint32_t n = 0; n < t.max_probe; ++n) {
         Slot *s = page + i;
         K cur = T::load(s);

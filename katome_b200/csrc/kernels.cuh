@@ -255,10 +255,20 @@ __device__ __forceinline__ void hll_insert(uint32_t *regs, uint64_t h) {
     uint32_t rank = rest ? (uint32_t)__clzll((long long)rest) + 1u : 64u - HLL_P + 1u;
     if (regs[idx] < rank) atomicMax(&regs[idx], rank);
 }
+__device__ __forceinline__ bool hll_sampled(uint64_t h) { return ((uint32_t)h >> 25) == 0; }
 __device__ __forceinline__ void hll_update(uint32_t *regs, uint64_t h, bool valid = true) {
-    const bool s = valid && ((uint32_t)h >> 25) == 0; // lo32 bits 25..31: above every slot index we use
+    const bool s = valid && hll_sampled(h);
     if (__any_sync(__activemask(), s)) {
         if (s) hll_insert(regs, h);
+    }
+}
+// one vote for the PER keys a lane handles in a tile; mask bit j = key j is sampled
+template <class K, int PER>
+__device__ __forceinline__ void hll_update_tile(uint32_t *regs, const K (&key)[PER], uint32_t mask) {
+    if (__any_sync(0xFFFFFFFFu, mask != 0)) {
+#pragma unroll
+        for (int j = 0; j < PER; ++j)
+            if (mask & (1u << j)) hll_insert(regs, KeyTraits<K>::hash(key[j]));
     }
 }
 
@@ -399,7 +409,7 @@ hist_reads_kernel(const uint64_t *__restrict__ packed, const uint8_t *__restrict
         for (int j = 0; j < GRAN; ++j) {
             if (j < (int)iw.nwin) {
                 uint64_t h = KeyTraits<K>::hash(iw.template key<RC>());
-                Place p = place_of(h, t.world, t.n_sub, t.sub_mask);
+                Place p = place_of(h, t.world, t.n_sub);
                 atomicAdd(&sh_hist[BY_OWNER ? p.owner : p.part], 1u);
                 if (HLL) hll_update(regs, h);
             }
@@ -425,7 +435,7 @@ hist_keys_kernel(const K *__restrict__ keys, uint64_t n, Table<K> t, uint32_t n_
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         uint64_t h = KeyTraits<K>::hash(keys[i]);
-        Place p = place_of(h, t.world, t.n_sub, t.sub_mask);
+        Place p = place_of(h, t.world, t.n_sub);
         atomicAdd(&sh_hist[BY_OWNER ? p.owner : p.part], 1u);
         if (HLL) hll_update(regs, h);
     }
@@ -645,15 +655,17 @@ scatter_reads_kernel(const uint64_t *__restrict__ packed, const uint8_t *__restr
         iw.load(packed, nstart, n_words, tile * SCATTER_THREADS + threadIdx.x, k, im);
         K key[SCATTER_PER];
         uint32_t bin[SCATTER_PER];
+        uint32_t sampled = 0;
 #pragma unroll
         for (int j = 0; j < SCATTER_PER; ++j) {
             key[j] = iw.template key<RC>();
             uint64_t h = KeyTraits<K>::hash(key[j]);
-            Place p = place_of(h, t.world, t.n_sub, t.sub_mask);
+            Place p = place_of(h, t.world, t.n_sub);
             bin[j] = BY_OWNER ? p.owner : p.part;
-            if (HLL) hll_update(sm.regs, h, j < (int)iw.nwin);
+            if (HLL && hll_sampled(h) && j < (int)iw.nwin) sampled |= 1u << j;
             iw.r.step();
         }
+        if (HLL) hll_update_tile<K, SCATTER_PER>(sm.regs, key, sampled);
         tile_scatter<K, SCATTER_THREADS, SCATTER_PER>(key, bin, (int)iw.nwin, sm, n_bins, o.cursors, 0, o, parity);
     }
     if (HLL) {
@@ -682,6 +694,7 @@ scatter_keys_kernel(const K *__restrict__ keys, uint64_t n, Table<K> t, uint32_t
         const uint64_t base = tile * SCATTER_TILE;
         K key[SCATTER_PER];
         uint32_t bin[SCATTER_PER];
+        uint32_t sampled = 0;
         int nvalid = 0;
 #pragma unroll
         for (int j = 0; j < SCATTER_PER; ++j) {
@@ -689,11 +702,12 @@ scatter_keys_kernel(const K *__restrict__ keys, uint64_t n, Table<K> t, uint32_t
             const bool in = i < n;
             key[j] = in ? KeyTraits<K>::load_stream(&keys[i]) : (K)0;
             uint64_t h = KeyTraits<K>::hash(key[j]);
-            Place p = place_of(h, t.world, t.n_sub, t.sub_mask);
+            Place p = place_of(h, t.world, t.n_sub);
             bin[j] = BY_OWNER ? p.owner : p.part;
-            if (HLL) hll_update(sm.regs, h, in);
+            if (HLL && hll_sampled(h) && in) sampled |= 1u << j;
             if (in) nvalid = j + 1;
         }
+        if (HLL) hll_update_tile<K, SCATTER_PER>(sm.regs, key, sampled);
         tile_scatter<K, SCATTER_THREADS, SCATTER_PER>(key, bin, nvalid, sm, n_bins, o.cursors, 0, o, parity);
     }
     if (HLL) {
@@ -739,7 +753,7 @@ scatter_pages_kernel(const K *__restrict__ keys1, const unsigned long long *__re
             const uint64_t i = base + (uint64_t)j * L2S_THREADS + threadIdx.x;
             const bool in = i < end;
             key[j] = in ? KeyTraits<K>::load_stream(&keys1[i]) : (K)0;
-            bin[j] = ((uint32_t)KeyTraits<K>::hash(key[j]) & t.sub_mask) >> t.page_log2;
+            bin[j] = (KeyTraits<K>::slot_hash(key[j]) & t.sub_mask) >> t.page_log2;
             if (in) nvalid = j + 1;
         }
         tile_scatter<K, L2S_THREADS, L2S_PER>(key, bin, nvalid, sm, n2, o.cursors + b * n2, b * n2, o, parity);
@@ -794,7 +808,8 @@ __device__ __forceinline__ u128 smem_load(const u128 *p) {
 // queue in shared memory that is drained in full rows of 32, so the work is the
 // SUM of the chain lengths.  Queue entry: key + (slot | probes << 13.. | inc2 << 31).
 constexpr uint32_t PQ_CAP = 64; // < 32 left over + <= 32 pushed per step
-constexpr uint32_t PQ_INC2 = 0x80000000u, PQ_SLOT_BITS = 13, PQ_SLOT_MASK = (1u << PQ_SLOT_BITS) - 1;
+// queue state word: slot in bits 0..15, probes done in bits 16..30, "+2" flag in bit 31
+constexpr uint32_t PQ_INC2 = 0x80000000u, PQ_STEP = 0x00010001u, PQ_PROBE_SHIFT = 16;
 
 template <class K> struct PageCtx {
     K *sk;
@@ -811,29 +826,29 @@ __device__ __forceinline__ void page_probe_rows(PageCtx<K> &c, const Table<K> &t
     typedef KeyTraits<K> T;
     const K EMPTY = T::empty();
     const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
+    const uint32_t keep = 0xFFFF0000u | c.page_mask;
     for (;;) {
         bool pending = false;
         if (active) {
-            const uint32_t i = st & PQ_SLOT_MASK, inc = (st & PQ_INC2) ? 2u : 1u;
+            const uint32_t i = st & 0xFFFFu;
             K cur = smem_load(&c.sk[i]);
             if (cur != key && (cur == EMPTY || T::maybe_torn(cur))) cur = smem_cas(&c.sk[i], EMPTY, key);
-            if (cur == key || cur == EMPTY) atomicAdd(&c.sw[i], inc);
+            if (cur == key || cur == EMPTY) atomicAdd(&c.sw[i], 1u + (st >> 31));
             else {
-                const uint32_t probes = ((st & ~PQ_INC2) >> PQ_SLOT_BITS) + 1;
-                if (probes > c.page_mask) { // every slot of the page holds another key: replay after a grow
-                    unsigned long long pos = atomicAdd(t.ovf_count, 1ull);
+                st = (st + PQ_STEP) & keep; // next slot (wraps inside the page), one more probe
+                pending = true;
+                if (((st & ~PQ_INC2) >> PQ_PROBE_SHIFT) > c.page_mask) { // every slot holds another key
+                    pending = false;
+                    unsigned long long pos = atomicAdd(t.ovf_count, 1ull); // replayed after a grow
                     if (pos < t.ovf_cap) {
                         t.ovf_keys[pos] = key;
-                        t.ovf_inc[pos] = inc;
+                        t.ovf_inc[pos] = 1u + (st >> 31);
                     }
-                }
-                else {
-                    st = (st & PQ_INC2) | (probes << PQ_SLOT_BITS) | ((i + 1) & c.page_mask);
-                    pending = true;
                 }
             }
         }
         const uint32_t m = __ballot_sync(0xFFFFFFFFu, pending);
+        if (m == 0 && c.qn < 32) return; // the common case: nothing to queue, nothing to drain
         if (pending) {
             const uint32_t pos = c.qn + __popc(m & lt);
             c.qk[pos] = key;
@@ -930,7 +945,7 @@ update_pages_kernel(const K *__restrict__ keys2, const unsigned long long *__res
                     atomicAdd(&t.slots[t.capacity()].w, 1u);
                     active = false;
                 }
-                uint32_t st = (uint32_t)T::hash(my[q]) & c.page_mask;
+                uint32_t st = T::slot_hash(my[q]) & c.page_mask;
                 if (check_palindrome && revcomp(my[q], k) == my[q]) st |= PQ_INC2;
                 page_probe_rows(c, t, my[q], st, active);
             }

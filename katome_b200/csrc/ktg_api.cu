@@ -13,7 +13,6 @@ struct ktg_builder {
     DeviceBuf st_bases[2], st_offs[2];
     cudaEvent_t st_free[2] = {nullptr, nullptr}; // staging buffer consumed by the compute stream
     cudaEvent_t st_ready[2] = {nullptr, nullptr};
-    int st_next = 0;
 };
 
 extern "C" {
@@ -102,41 +101,61 @@ int ktg_add_reads(ktg_builder *b, const uint8_t *bases, const uint64_t *offsets,
     BuilderBase *impl = b->impl.get();
     uint64_t r0c = 0, b0c = 0;
     if (accepted_reads || accepted_bytes) KTG_TRY(impl->read_counters(&r0c, &b0c));
-    const uint64_t CHUNK = 256ull << 20; // bytes of bases per chunk
+    // bytes of bases per chunk: small enough that the H2D copy of chunk i+1 hides the kernels of
+    // chunk i and only one chunk's kernels are exposed at the end
+    uint64_t CHUNK = 64ull << 20;
+    if (const char *e = getenv("KTG_CHUNK_MB")) CHUNK = (uint64_t)std::max(1, atoi(e)) << 20; // tuning knob
     for (int i = 0; i < 2; ++i) {
         if (!b->st_free[i]) {
             KTG_CUDA(cudaEventCreateWithFlags(&b->st_free[i], cudaEventDisableTiming));
             KTG_CUDA(cudaEventCreateWithFlags(&b->st_ready[i], cudaEventDisableTiming));
         }
     }
-    uint64_t r = 0;
-    while (r < n_reads) {
-        // largest r1 with offsets[r1] - offsets[r] <= CHUNK (at least one read)
+    // chunk boundaries: largest r1 with offsets[r1] - offsets[r] <= CHUNK (at least one read)
+    std::vector<uint64_t> cut{0};
+    while (cut.back() < n_reads) {
+        const uint64_t r = cut.back();
         uint64_t lo = r + 1, hi = n_reads;
         while (lo < hi) {
             uint64_t mid = (lo + hi + 1) / 2;
             if (offsets[mid] - offsets[r] <= CHUNK) lo = mid;
             else hi = mid - 1;
         }
-        const uint64_t r1 = lo, nb = offsets[r1] - offsets[r], nr = r1 - r;
-        const int s = b->st_next;
-        b->st_next ^= 1;
-        // the staging buffer may still be read by kernels of two chunks ago
+        cut.push_back(lo);
+    }
+    const size_t n_chunks = cut.size() - 1;
+    // The copy of chunk i+1 is queued BEFORE the kernels of chunk i are launched: ingest_device
+    // synchronises the compute stream (counters, table sizing), and the copy engine must not
+    // sit idle meanwhile.
+    auto issue_copy = [&](size_t c) -> int {
+        const uint64_t r = cut[c], r1 = cut[c + 1], nb = offsets[r1] - offsets[r], nr = r1 - r;
+        const int s = (int)(c & 1);
+        // the staging buffer may still be read by the kernels of two chunks ago
         KTG_CUDA(cudaStreamWaitEvent(impl->copy_stream, b->st_free[s], 0));
         if (b->st_bases[s].cap < nb + 64 || b->st_offs[s].cap < (nr + 1) * 8) {
             KTG_CUDA(cudaStreamSynchronize(impl->stream)); // reallocation frees the old buffer
-            KTG_TRY(b->st_bases[s].ensure(nb + 64));
+            KTG_CUDA(cudaStreamSynchronize(impl->copy_stream));
+            KTG_TRY(b->st_bases[s].ensure(std::max<uint64_t>(nb, CHUNK) + 64));
             KTG_TRY(b->st_offs[s].ensure((nr + 1) * 8));
         }
         KTG_CUDA(cudaMemcpyAsync(b->st_bases[s].p, bases + offsets[r], nb, cudaMemcpyHostToDevice, impl->copy_stream));
         KTG_CUDA(cudaMemcpyAsync(b->st_offs[s].p, offsets + r, (nr + 1) * 8, cudaMemcpyHostToDevice, impl->copy_stream));
         KTG_CUDA(cudaEventRecord(b->st_ready[s], impl->copy_stream));
+        trace("copy queued", c);
+        return KTG_OK;
+    };
+    KTG_TRY(issue_copy(0));
+    for (size_t c = 0; c < n_chunks; ++c) {
+        if (c + 1 < n_chunks) KTG_TRY(issue_copy(c + 1));
+        const uint64_t r = cut[c], r1 = cut[c + 1], nb = offsets[r1] - offsets[r], nr = r1 - r;
+        const int s = (int)(c & 1);
         KTG_CUDA(cudaStreamWaitEvent(impl->stream, b->st_ready[s], 0));
         // offsets stay absolute: bias the base pointer instead (pack kernel subtracts offsets[0])
         const uint8_t *d_bases = (const uint8_t *)b->st_bases[s].p - offsets[r];
-        KTG_TRY(impl->ingest_device(d_bases, (const uint64_t *)b->st_offs[s].p, nr, nb));
-        KTG_CUDA(cudaEventRecord(b->st_free[s], impl->stream));
-        r = r1;
+        impl->input_consumed = b->st_free[s];
+        int rc_ = impl->ingest_device(d_bases, (const uint64_t *)b->st_offs[s].p, nr, nb);
+        impl->input_consumed = nullptr;
+        KTG_TRY(rc_);
     }
     if (accepted_reads || accepted_bytes) {
         uint64_t r1c = 0, b1c = 0;

@@ -175,18 +175,25 @@ def test_paged_update_path(K, k, rc):
     seqs = H.random_reads(rng, 4000, max(k, 60), 160, genome=genome, n_rate=0.02)
     seqs += ["T" * (k + 20), "A" * (k + 7), "AT" * 60, "ACGT" * 40]
     cpu = _oracle(seqs, k, rc)
-    for kw in ({}, {"sub_table_log2_bytes": 18}, {"edges_count": 2 * 30000 * 3}):
-        g = K.GpuGIR(k, rc, force_pages=True, **kw)
-        third = len(seqs) // 3
-        for part in (seqs[:third], seqs[third:2 * third], seqs[2 * third:]):
-            g.add_reads(*H.batch_of(part))
-        _assert_same(g, cpu)
-        info = g.info()
-        assert info["page_updates"] == 3 and info["partitioned"] == 1
-        g.reset()
-        g.add_reads(*H.batch_of(seqs))
-        _assert_same(g, cpu, full_stats=False)
-        g.close()
+    import os
+    for kw, factor in (({}, None), ({"sub_table_log2_bytes": 18}, "0.001"), ({"edges_count": 2 * 30000 * 3}, "0.001")):
+        # KTG_STAGE_FACTOR: flush the staged buckets after every batch instead of once at the end
+        if factor:
+            os.environ["KTG_STAGE_FACTOR"] = factor
+        try:
+            g = K.GpuGIR(k, rc, force_pages=True, **kw)
+            third = len(seqs) // 3
+            for part in (seqs[:third], seqs[third:2 * third], seqs[2 * third:]):
+                g.add_reads(*H.batch_of(part))
+            _assert_same(g, cpu)
+            info = g.info()
+            assert info["page_updates"] == (3 if factor else 1) and info["partitioned"] == 1
+            g.reset()
+            g.add_reads(*H.batch_of(seqs))
+            _assert_same(g, cpu, full_stats=False)
+            g.close()
+        finally:
+            os.environ.pop("KTG_STAGE_FACTOR", None)
 
 
 def test_paged_and_atomic_paths_agree_at_scale(K):
