@@ -201,6 +201,17 @@ struct BuilderBase {
                                 uint64_t n_reads, uint64_t total_bases, void **d_keys,
                                 uint64_t *counts) = 0;
     virtual int insert_keys(const void *d_keys, uint64_t n) = 0;
+    virtual int partition_keys(const void *d_keys, uint64_t n, void **d_out, uint64_t *counts) = 0;
+    virtual int mg_plan(uint64_t max_windows, int *needs_realloc) = 0;
+    virtual int mg_prepare(uint64_t max_windows, void **rx_base, uint64_t *rx_bytes, uint64_t *bucket_cap,
+                           uint32_t *n_sub) = 0;
+    virtual int mg_insert_spill(const void *d_keys, uint64_t n) = 0;
+    virtual int mg_scatter_reads(const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t n_reads,
+                                 uint64_t total_bases, void *const *peer_rx, void **d_cursors) = 0;
+    virtual int mg_insert_buckets(const void *d_bucket_ends, uint64_t n_keys_estimate) = 0;
+    virtual int mg_sketch(void **d_regs, uint32_t *n_regs) = 0;
+    virtual int mg_plan_growth(int *grew) = 0;
+    virtual int mg_spill(void **d_keys, uint64_t *n) = 0;
     virtual uint32_t owner_of(uint64_t hi, uint64_t lo) = 0;
     virtual int info(ktg_info *out) = 0;
 };
@@ -243,6 +254,7 @@ template <class K> struct Builder : BuilderBase {
         b_packed.release(); b_nstart.release(); b_keys.release(); b_keys2.release();
         b_hist.release(); b_hll.release(); b_spill.release(); b_ovf_keys.release(); b_ovf_inc.release(); b_small.release();
         b_pkeys.release(); b_pcur.release(); b_pspill.release(); b_stage_cur.release();
+        b_rx.release(); b_mg_cur.release(); b_mg_spill.release();
         if (copy_stream) cudaStreamDestroy(copy_stream);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
@@ -366,12 +378,15 @@ template <class K> struct Builder : BuilderBase {
         const size_t mx = ScatterSmem<K, SCATTER_TILE>::bytes(MAX_BINS, true);
         allow_smem(scatter_pages_kernel<K>, ScatterSmem<K, L2S_TILE>::bytes(MAX_PAGES_PER_SUB, false));
         allow_smem(update_pages_kernel<K>, page_smem_bytes());
-        allow_smem(scatter_reads_kernel<K, true, false, true>, mx);
-        allow_smem(scatter_reads_kernel<K, false, false, true>, mx);
-        allow_smem(scatter_reads_kernel<K, true, false, false>, mx);
-        allow_smem(scatter_reads_kernel<K, false, false, false>, mx);
-        allow_smem(scatter_reads_kernel<K, true, true, false>, mx);
-        allow_smem(scatter_reads_kernel<K, false, true, false>, mx);
+        allow_smem(scatter_reads_kernel<K, true, BIN_PART, true>, mx);
+        allow_smem(scatter_reads_kernel<K, false, BIN_PART, true>, mx);
+        allow_smem(scatter_reads_kernel<K, true, BIN_PART, false>, mx);
+        allow_smem(scatter_reads_kernel<K, false, BIN_PART, false>, mx);
+        allow_smem(scatter_reads_kernel<K, true, BIN_OWNER, false>, mx);
+        allow_smem(scatter_reads_kernel<K, false, BIN_OWNER, false>, mx);
+        allow_smem(scatter_reads_kernel<K, true, BIN_OWNER_PART, true>, mx);
+        allow_smem(scatter_reads_kernel<K, false, BIN_OWNER_PART, true>, mx);
+        allow_smem(scatter_keys_kernel<K, true, false>, mx);
         allow_smem(scatter_keys_kernel<K, false, true>, mx);
         allow_smem(scatter_keys_kernel<K, false, false>, mx);
     }
@@ -634,31 +649,33 @@ template <class K> struct Builder : BuilderBase {
         return o;
     }
 
-    template <bool BY_OWNER, bool HLL>
-    int scatter_reads_pass(const Batch &bt, uint32_t n_bins, const ScatterOut &o) {
+    template <int BINS, bool HLL>
+    int scatter_reads_pass(const Batch &bt, uint32_t n_bins, const ScatterOut &o, const PeerOut *po = nullptr) {
         const uint64_t *packed = (const uint64_t *)b_packed.p;
         const uint8_t *nstart = (const uint8_t *)b_nstart.p;
         size_t ss = ScatterSmem<K, SCATTER_TILE>::bytes(n_bins, HLL);
         uint64_t n_tiles = std::max<uint64_t>(1, (bt.im.n_items + SCATTER_THREADS - 1) / SCATTER_THREADS);
-        prof.begin("scatter_reads", bt.windows, stream);
+        PeerOut peers{};
+        if (po) peers = *po;
+        prof.begin(BINS == BIN_OWNER_PART ? "scatter_reads_p2p" : "scatter_reads", bt.windows, stream);
         if (rc) {
-            int g = (int)std::min<uint64_t>(grid_for(scatter_reads_kernel<K, true, BY_OWNER, HLL>, SCATTER_THREADS, ss, props), n_tiles);
-            scatter_reads_kernel<K, true, BY_OWNER, HLL><<<g, SCATTER_THREADS, ss, stream>>>(packed, nstart, bt.n_words, k, bt.im, tab, n_bins, o, (uint32_t *)b_hll.p);
+            int g = (int)std::min<uint64_t>(grid_for(scatter_reads_kernel<K, true, BINS, HLL>, SCATTER_THREADS, ss, props), n_tiles);
+            scatter_reads_kernel<K, true, BINS, HLL><<<g, SCATTER_THREADS, ss, stream>>>(packed, nstart, bt.n_words, k, bt.im, tab, n_bins, o, (uint32_t *)b_hll.p, peers);
         }
         else {
-            int g = (int)std::min<uint64_t>(grid_for(scatter_reads_kernel<K, false, BY_OWNER, HLL>, SCATTER_THREADS, ss, props), n_tiles);
-            scatter_reads_kernel<K, false, BY_OWNER, HLL><<<g, SCATTER_THREADS, ss, stream>>>(packed, nstart, bt.n_words, k, bt.im, tab, n_bins, o, (uint32_t *)b_hll.p);
+            int g = (int)std::min<uint64_t>(grid_for(scatter_reads_kernel<K, false, BINS, HLL>, SCATTER_THREADS, ss, props), n_tiles);
+            scatter_reads_kernel<K, false, BINS, HLL><<<g, SCATTER_THREADS, ss, stream>>>(packed, nstart, bt.n_words, k, bt.im, tab, n_bins, o, (uint32_t *)b_hll.p, peers);
         }
         prof.end(stream);
         return KTG_OK;
     }
 
-    template <bool HLL> int scatter_keys_pass(const K *keys, uint64_t n, uint32_t n_bins, const ScatterOut &o) {
+    template <bool BY_OWNER, bool HLL> int scatter_keys_pass(const K *keys, uint64_t n, uint32_t n_bins, const ScatterOut &o) {
         size_t ss = ScatterSmem<K, SCATTER_TILE>::bytes(n_bins, HLL);
         uint64_t n_tiles = std::max<uint64_t>(1, (n + SCATTER_TILE - 1) / SCATTER_TILE);
-        int g = (int)std::min<uint64_t>(grid_for(scatter_keys_kernel<K, false, HLL>, SCATTER_THREADS, ss, props), n_tiles);
+        int g = (int)std::min<uint64_t>(grid_for(scatter_keys_kernel<K, BY_OWNER, HLL>, SCATTER_THREADS, ss, props), n_tiles);
         prof.begin("scatter_keys", n, stream);
-        scatter_keys_kernel<K, false, HLL><<<g, SCATTER_THREADS, ss, stream>>>(keys, n, tab, n_bins, o, (uint32_t *)b_hll.p);
+        scatter_keys_kernel<K, BY_OWNER, HLL><<<g, SCATTER_THREADS, ss, stream>>>(keys, n, tab, n_bins, o, (uint32_t *)b_hll.p);
         prof.end(stream);
         return KTG_OK;
     }
@@ -685,7 +702,11 @@ template <class K> struct Builder : BuilderBase {
     // Level-2 scatter of the level-1 buckets by page, then the streaming page update.
     // Page-bucket overflow goes to a spill list that is inserted with L2 atomics
     // afterwards (count stays on the device: no host round trip).
-    int paged_update(uint32_t n_bins, uint64_t cap1, uint64_t n_keys, const unsigned long long *fill1) {
+    // keys1: level-1 buckets (n_bins of cap1 keys, ends in fill1); sub_mod != 0: bucket q
+    // belongs to sub-table q % sub_mod (receive buckets, one set per source rank)
+    int paged_update(uint32_t n_bins, uint64_t cap1, uint64_t n_keys, const unsigned long long *fill1,
+                     const K *keys1 = nullptr, uint32_t sub_mod = 0) {
+        if (!keys1) keys1 = (const K *)b_keys.p;
         const uint64_t n_pages = tab.n_pages();
         const uint64_t cap2 = page_bucket_cap_for(n_keys, n_pages);
         const uint64_t spill_cap = std::max<uint64_t>(1u << 20, n_keys / 32);
@@ -707,7 +728,7 @@ template <class K> struct Builder : BuilderBase {
         const size_t ss = ScatterSmem<K, L2S_TILE>::bytes(tab.pages_per_sub(), false);
         int g = (int)std::min<uint64_t>(grid_for(scatter_pages_kernel<K>, L2S_THREADS, ss, props), n_tiles);
         prof.begin("scatter_pages", n_keys, stream);
-        scatter_pages_kernel<K><<<g, L2S_THREADS, ss, stream>>>((const K *)b_keys.p, fill1, cap1, tiles_per_bin, n_tiles, tab, o);
+        scatter_pages_kernel<K><<<g, L2S_THREADS, ss, stream>>>(keys1, fill1, cap1, tiles_per_bin, n_tiles, sub_mod, tab, o);
         prof.end(stream);
         const size_t ps = page_smem_bytes(tab.page_log2);
         g = (int)std::min<uint64_t>(grid_for(update_pages_kernel<K>, PAGE_THREADS, ps, props), n_pages);
@@ -877,7 +898,7 @@ template <class K> struct Builder : BuilderBase {
         }
         else {
             int st = stage_add(bt.windows, [&](uint32_t n_bins, const ScatterOut &o) -> int {
-                return scatter_reads_pass<false, true>(bt, n_bins, o);
+                return scatter_reads_pass<BIN_PART, true>(bt, n_bins, o);
             });
             if (st == KTG_ERR_TABLE_FULL + 1000) { // heavy skew: exact two-pass partition, inserted at once
                 KTG_TRY(flush_staged()); // also sizes the table for this batch (it is in the sketch already)
@@ -885,7 +906,7 @@ template <class K> struct Builder : BuilderBase {
                 KTG_TRY(hist_reads_pass<false>(bt, n_bins));
                 KTG_TRY(scan_bins_pass(n_bins, 0));
                 KTG_TRY(b_keys2.ensure(bt.windows * sizeof(K) + 64));
-                KTG_TRY((scatter_reads_pass<false, false>(bt, n_bins, scatter_out(n_bins, 0, b_keys2.p, nullptr, 0))));
+                KTG_TRY((scatter_reads_pass<BIN_PART, false>(bt, n_bins, scatter_out(n_bins, 0, b_keys2.p, nullptr, 0))));
                 KTG_TRY(launch_insert_keys((const K *)b_keys2.p, bt.windows));
             }
             else KTG_TRY(st);
@@ -1111,7 +1132,7 @@ template <class K> struct Builder : BuilderBase {
         KTG_TRY(hist_reads_pass<true>(bt, W));
         KTG_TRY(scan_bins_pass(W, 0));
         KTG_TRY(b_keys2.ensure(bt.windows * sizeof(K) + 64));
-        KTG_TRY((scatter_reads_pass<true, false>(bt, W, scatter_out(W, 0, b_keys2.p, nullptr, 0))));
+        KTG_TRY((scatter_reads_pass<BIN_OWNER, false>(bt, W, scatter_out(W, 0, b_keys2.p, nullptr, 0))));
         std::vector<unsigned long long> h(W);
         KTG_CUDA(cudaMemcpyAsync(h.data(), hist_ptr(), W * 8, cudaMemcpyDeviceToHost, stream));
         KTG_TRY(sync()); // the caller hands the buffer to NCCL on its own stream
@@ -1137,7 +1158,7 @@ template <class K> struct Builder : BuilderBase {
         }
         else {
             int st = stage_add(n, [&](uint32_t n_bins, const ScatterOut &o) -> int {
-                return scatter_keys_pass<true>(keys, n, n_bins, o);
+                return scatter_keys_pass<false, true>(keys, n, n_bins, o);
             });
             if (st == KTG_ERR_TABLE_FULL + 1000) { // skewed: no locality, still exact
                 KTG_TRY(flush_staged());
@@ -1146,6 +1167,165 @@ template <class K> struct Builder : BuilderBase {
             else KTG_TRY(st);
         }
         KTG_CUDA(cudaGetLastError());
+        return KTG_OK;
+    }
+
+    // exact partition of an array of keys by owner rank (spill lists of the fused path)
+    int partition_keys(const void *d_keys, uint64_t n, void **d_out, uint64_t *counts) override {
+        if (deferred_error != KTG_OK) return fail(deferred_error, "build is void after an earlier error");
+        const uint32_t W = tab.world;
+        for (uint32_t i = 0; i < W; ++i) counts[i] = 0;
+        *d_out = nullptr;
+        if (n == 0) return KTG_OK;
+        KTG_TRY(ensure_hist(W));
+        KTG_CUDA(cudaMemsetAsync(b_hist.p, 0, W * 8, stream));
+        prof.begin("hist_keys", n, stream);
+        hist_keys_kernel<K, true, false><<<props.sms * 4, 256, W * 4, stream>>>((const K *)d_keys, n, tab, W, hist_ptr(), nullptr);
+        prof.end(stream);
+        KTG_TRY(scan_bins_pass(W, 0));
+        KTG_TRY(b_keys2.ensure(n * sizeof(K) + 64));
+        KTG_TRY((scatter_keys_pass<true, false>((const K *)d_keys, n, W, scatter_out(W, 0, b_keys2.p, nullptr, 0))));
+        std::vector<unsigned long long> h(W);
+        KTG_CUDA(cudaMemcpyAsync(h.data(), hist_ptr(), W * 8, cudaMemcpyDeviceToHost, stream));
+        KTG_TRY(sync());
+        for (uint32_t i = 0; i < W; ++i) counts[i] = h[i];
+        *d_out = b_keys2.p;
+        return KTG_OK;
+    }
+
+    // ---- multi-GPU, fused: the level-1 scatter writes straight into the owners' HBM ------
+    // Rank r reserves world * n_sub receive buckets of mg_cap keys: bucket (s, p) takes the
+    // keys of sub-table p that rank s extracts.  Only rank s writes it (cursors are local to
+    // the sender: no remote atomics), so after the senders' kernels have completed the owner
+    // runs the level-2 scatter + page update over its buckets exactly as on one GPU.
+    DeviceBuf b_rx, b_mg_cur, b_mg_spill;
+    uint64_t mg_cap = 0, mg_spill_cap = 0;
+    uint32_t mg_bins = 0, mg_sub_log2 = 0;
+
+    int mg_geometry(uint64_t max_windows, uint32_t *bins, uint64_t *cap) {
+        const uint32_t W = tab.world;
+        if (W > (uint32_t)MAX_P2P_WORLD || (uint64_t)W * tab.n_sub > MAX_BINS)
+            return fail(KTG_ERR_INVALID, "fused exchange needs world <= %d and world * sub-tables <= %u", MAX_P2P_WORLD, MAX_BINS);
+        *bins = W * tab.n_sub;
+        *cap = bucket_cap_for(std::max<uint64_t>(max_windows, 1), *bins);
+        if ((double)*cap * *bins >= 4.0e9) return fail(KTG_ERR_INVALID, "batch too large: split it (32-bit bucket positions)");
+        return KTG_OK;
+    }
+    // would mg_prepare(max_windows) replace the receive buffer?  (peers must unmap it first)
+    int mg_plan(uint64_t max_windows, int *needs_realloc) override {
+        uint32_t bins = 0;
+        uint64_t cap = 0;
+        KTG_TRY(mg_geometry(max_windows, &bins, &cap));
+        *needs_realloc = bins != mg_bins || tab.sub_log2 != mg_sub_log2 || cap > mg_cap || !b_rx.p;
+        return KTG_OK;
+    }
+    int mg_prepare(uint64_t max_windows, void **rx_base, uint64_t *rx_bytes, uint64_t *bucket_cap,
+                   uint32_t *n_sub) override {
+        uint32_t bins = 0;
+        uint64_t cap = 0;
+        KTG_TRY(mg_geometry(max_windows, &bins, &cap));
+        if (bins != mg_bins || tab.sub_log2 != mg_sub_log2 || cap > mg_cap || !b_rx.p) {
+            KTG_TRY(sync());
+            b_rx.release();
+            KTG_TRY(b_rx.ensure((size_t)cap * bins * sizeof(K) + 64));
+            mg_cap = cap;
+            mg_bins = bins;
+            mg_sub_log2 = tab.sub_log2;
+            mg_spill_cap = std::max<uint64_t>(1u << 20, max_windows / 16);
+            KTG_TRY(b_mg_spill.ensure(mg_spill_cap * sizeof(K) + 64));
+            KTG_TRY(b_mg_cur.ensure(((size_t)bins + 2) * 8));
+        }
+        *rx_base = b_rx.p;
+        *rx_bytes = (size_t)mg_cap * mg_bins * sizeof(K);
+        *bucket_cap = mg_cap;
+        *n_sub = tab.n_sub;
+        return KTG_OK;
+    }
+    // keys of the exchange spill list that this rank owns: they are in the (global) sketch
+    // already, so they bypass staging and sizing
+    int mg_insert_spill(const void *d_keys, uint64_t n) override {
+        if (deferred_error != KTG_OK) return fail(deferred_error, "build is void after an earlier error");
+        if (n == 0) return KTG_OK;
+        return launch_insert_keys((const K *)d_keys, n);
+    }
+
+    int mg_scatter_reads(const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t n_reads,
+                         uint64_t total_bases, void *const *peer_rx, void **d_cursors) override {
+        if (deferred_error != KTG_OK) return fail(deferred_error, "build is void after an earlier error");
+        if (!mg_bins || mg_bins != tab.world * tab.n_sub) return fail(KTG_ERR_INVALID, "ktg_mg_prepare first");
+        unsigned long long *cur = (unsigned long long *)b_mg_cur.p;
+        *d_cursors = cur;
+        init_cursors_kernel<<<(mg_bins + 255) / 256, 256, 0, stream>>>(cur, mg_bins, mg_cap);
+        KTG_CUDA(cudaMemsetAsync(cur + mg_bins, 0, 8, stream)); // spill cursor
+        if (n_reads == 0) return KTG_OK;
+        Batch bt;
+        KTG_TRY(pack(d_bases, d_offsets, n_reads, total_bases, &bt));
+        if (bt.windows == 0) return KTG_OK;
+        PeerOut po{};
+        po.world = tab.world;
+        po.bins_per_owner = tab.n_sub;
+        const int64_t region = (int64_t)tab.n_sub * (int64_t)mg_cap; // keys per (source, owner) region
+        for (uint32_t o = 0; o < tab.world; ++o)
+            po.rxb[o] = (K *)peer_rx[o] + ((int64_t)tab.rank - (int64_t)o) * region;
+        ScatterOut so;
+        so.cursors = cur;
+        so.bucket_cap = mg_cap;
+        so.out = nullptr;
+        so.spill_out = b_mg_spill.p;
+        so.spill_cursor = cur + mg_bins;
+        so.spill_cap = mg_spill_cap;
+        KTG_TRY((scatter_reads_pass<BIN_OWNER_PART, true>(bt, mg_bins, so, &po)));
+        KTG_CUDA(cudaGetLastError());
+        return KTG_OK;
+    }
+
+    // d_bucket_ends[s * n_sub + p]: absolute end (in keys, inside the own receive buffer) of
+    // bucket (s, p), i.e. (s * n_sub + p) * mg_cap + fill, as published by rank s
+    int mg_insert_buckets(const void *d_bucket_ends, uint64_t n_keys_estimate) override {
+        if (deferred_error != KTG_OK) return fail(deferred_error, "build is void after an earlier error");
+        const unsigned long long *ends = (const unsigned long long *)d_bucket_ends;
+        if (n_keys_estimate == 0) return KTG_OK;
+        if (use_pages(n_keys_estimate))
+            KTG_TRY(paged_update(mg_bins, mg_cap, n_keys_estimate, ends, (const K *)b_rx.p, tab.n_sub));
+        else KTG_TRY(launch_insert((const K *)b_rx.p, n_keys_estimate, ends, mg_cap, mg_bins));
+        KTG_CUDA(cudaGetLastError());
+        return KTG_OK;
+    }
+
+    int mg_sketch(void **d_regs, uint32_t *n_regs) override {
+        *d_regs = b_hll.p;
+        *n_regs = HLL_M;
+        return KTG_OK;
+    }
+
+    // The caller has all-reduced (max) the sketch, so it describes the keys of ALL ranks;
+    // this shard holds 1/world of them.  Every rank reaches the same decision.
+    int mg_plan_growth(int *grew) override {
+        *grew = 0;
+        double est = 0;
+        KTG_TRY(hll_estimate(&est));
+        const uint64_t distinct = hll_base + (uint64_t)(est * 1.10 / tab.world) + 64;
+        occupied_ub = distinct;
+        if ((double)distinct > LOAD_MAX * (double)tab.capacity()) {
+            const uint64_t need = std::max<uint64_t>((uint64_t)((double)distinct / LOAD_TARGET) + 1, 2 * tab.capacity());
+            KTG_TRY(grow_to(need));
+            *grew = 1;
+        }
+        return KTG_OK;
+    }
+
+    int mg_spill(void **d_keys, uint64_t *n) override {
+        unsigned long long v = 0;
+        *d_keys = b_mg_spill.p;
+        *n = 0;
+        if (!b_mg_cur.p || !mg_bins) return KTG_OK;
+        KTG_CUDA(cudaMemcpyAsync(&v, (unsigned long long *)b_mg_cur.p + mg_bins, 8, cudaMemcpyDeviceToHost, stream));
+        KTG_TRY(sync());
+        if (v > mg_spill_cap) {
+            deferred_error = KTG_ERR_TABLE_FULL;
+            return fail(KTG_ERR_TABLE_FULL, "%llu keys overflowed the exchange spill list", v - mg_spill_cap);
+        }
+        *n = v;
         return KTG_OK;
     }
 

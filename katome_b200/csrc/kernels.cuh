@@ -523,6 +523,16 @@ template <class K, int TILE> struct ScatterSmem {
     }
 };
 
+// Multi-GPU fused scatter: bins are (owner rank, sub-table) pairs and the bucket of
+// bin (o, p) lives in the HBM of rank o (mapped peer memory, NVLink), in the region
+// that rank reserves for this sender.  rxb[o] is rank o's receive base biased so that
+// the sender's virtual position v = bin * cap + fill is also the index into it.
+constexpr int MAX_P2P_WORLD = 8;
+struct PeerOut {
+    void *rxb[MAX_P2P_WORLD];
+    uint32_t world, bins_per_owner; // world == 0: single destination (ScatterOut::out)
+};
+
 struct ScatterOut {
     unsigned long long *cursors;   // per bin
     unsigned long long bucket_cap; // 0 = exact mode
@@ -538,7 +548,8 @@ template <class K, int THREADS, int PER>
 __device__ __forceinline__ void tile_scatter(const K (&key)[PER], const uint32_t (&bin)[PER],
                                              int nvalid, ScatterSmem<K, THREADS * PER> &sm,
                                              uint32_t n_bins, unsigned long long *cursors,
-                                             uint64_t bin_off, const ScatterOut &o, uint32_t parity) {
+                                             uint64_t bin_off, const ScatterOut &o, uint32_t parity,
+                                             const PeerOut *po = nullptr) {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_total, s_ovf;
     uint32_t *cnt = sm.cnt + parity * n_bins;
@@ -607,7 +618,15 @@ __device__ __forceinline__ void tile_scatter(const K (&key)[PER], const uint32_t
     __syncthreads();
     const uint32_t total = s_total;
     K *out = (K *)o.out;
-    if (!s_ovf) {
+    if (!s_ovf && po) { // bins are owner-major: one contiguous range of the sorted tile per destination GPU
+        for (uint32_t w = 0; w < po->world; ++w) {
+            const uint32_t beg = sm.ld[w * po->bins_per_owner].x;
+            const uint32_t end = w + 1 < po->world ? sm.ld[(w + 1) * po->bins_per_owner].x : total;
+            K *dst = (K *)po->rxb[w];
+            for (uint32_t i = beg + threadIdx.x; i < end; i += THREADS) dst[(uint32_t)(sm.delta[i] + i)] = sm.keys[i];
+        }
+    }
+    else if (!s_ovf) {
         for (uint32_t i = threadIdx.x; i < total; i += THREADS) out[(uint32_t)(sm.delta[i] + i)] = sm.keys[i];
     }
     else { // some bin of this tile ran past its bucket: find each key's bin again (rare)
@@ -621,6 +640,7 @@ __device__ __forceinline__ void tile_scatter(const K (&key)[PER], const uint32_t
             const uint32_t b = lo;
             const unsigned long long lim = (bin_off + b + 1) * o.bucket_cap;
             const unsigned long long dst = sm.glob[b] + (i - sm.ld[b].x);
+            if (po) out = (K *)po->rxb[b / po->bins_per_owner];
             if (dst < lim) out[dst] = sm.keys[i];
             else {
                 const unsigned long long first = sm.glob[b] > lim ? sm.glob[b] : lim;
@@ -634,12 +654,15 @@ __device__ __forceinline__ void tile_scatter(const K (&key)[PER], const uint32_t
 
 constexpr int SCATTER_THREADS = 256, SCATTER_PER = 8, SCATTER_TILE = SCATTER_THREADS * SCATTER_PER;
 
-// Level 1 from packed reads: extraction (K2) + partition by sub-table or owner.
-template <class K, bool RC, bool BY_OWNER, bool HLL>
+// Level 1 from packed reads: extraction (K2) + partition.  BINS: 0 = by sub-table,
+// 1 = by owner rank (keys for an NCCL exchange), 2 = by (owner, sub-table) straight into
+// the owners' receive buckets over NVLink (po).
+constexpr int BIN_PART = 0, BIN_OWNER = 1, BIN_OWNER_PART = 2;
+template <class K, bool RC, int BINS, bool HLL>
 __global__ void __launch_bounds__(SCATTER_THREADS, 3)
 scatter_reads_kernel(const uint64_t *__restrict__ packed, const uint8_t *__restrict__ nstart,
                      uint64_t n_words, uint32_t k, ItemMap im, Table<K> t, uint32_t n_bins,
-                     ScatterOut o, uint32_t *__restrict__ g_regs) {
+                     ScatterOut o, uint32_t *__restrict__ g_regs, PeerOut po) {
     extern __shared__ __align__(16) unsigned char smem[];
     ScatterSmem<K, SCATTER_TILE> sm;
     sm.carve(smem, n_bins);
@@ -661,12 +684,13 @@ scatter_reads_kernel(const uint64_t *__restrict__ packed, const uint8_t *__restr
             key[j] = iw.template key<RC>();
             uint64_t h = KeyTraits<K>::hash(key[j]);
             Place p = place_of(h, t.world, t.n_sub);
-            bin[j] = BY_OWNER ? p.owner : p.part;
+            bin[j] = BINS == BIN_OWNER ? p.owner : (BINS == BIN_PART ? p.part : p.owner * t.n_sub + p.part);
             if (HLL && hll_sampled(h) && j < (int)iw.nwin) sampled |= 1u << j;
             iw.r.step();
         }
         if (HLL) hll_update_tile<K, SCATTER_PER>(sm.regs, key, sampled);
-        tile_scatter<K, SCATTER_THREADS, SCATTER_PER>(key, bin, (int)iw.nwin, sm, n_bins, o.cursors, 0, o, parity);
+        tile_scatter<K, SCATTER_THREADS, SCATTER_PER>(key, bin, (int)iw.nwin, sm, n_bins, o.cursors, 0, o, parity,
+                                                      BINS == BIN_OWNER_PART ? &po : nullptr);
     }
     if (HLL) {
         __syncthreads();
@@ -730,8 +754,8 @@ __global__ void init_cursors_kernel(unsigned long long *cursors, uint64_t n, uin
 template <class K>
 __global__ void __launch_bounds__(L2S_THREADS, 2)
 scatter_pages_kernel(const K *__restrict__ keys1, const unsigned long long *__restrict__ fill1,
-                     uint64_t cap1, uint64_t tiles_per_bin, uint64_t n_tiles, Table<K> t,
-                     ScatterOut o) {
+                     uint64_t cap1, uint64_t tiles_per_bin, uint64_t n_tiles, uint32_t sub_mod,
+                     Table<K> t, ScatterOut o) {
     extern __shared__ __align__(16) unsigned char smem[];
     const uint32_t n2 = t.pages_per_sub();
     ScatterSmem<K, L2S_TILE> sm;
@@ -740,9 +764,12 @@ scatter_pages_kernel(const K *__restrict__ keys1, const unsigned long long *__re
     __syncthreads();
     uint32_t parity = 0;
     for (uint32_t tile = blockIdx.x; tile < (uint32_t)n_tiles; tile += gridDim.x) {
-        const uint64_t b = tile / (uint32_t)tiles_per_bin;
-        const uint64_t lim = (b + 1) * cap1, fill = fill1[b];
-        const uint64_t base = b * cap1 + (uint64_t)(tile - (uint32_t)b * (uint32_t)tiles_per_bin) * L2S_TILE;
+        // level-1 bucket q holds keys of sub-table q (local buckets) or q % n_sub (receive
+        // buckets of the multi-GPU path: one set of n_sub buckets per source rank)
+        const uint64_t q = tile / (uint32_t)tiles_per_bin;
+        const uint64_t b = sub_mod ? q % sub_mod : q;
+        const uint64_t lim = (q + 1) * cap1, fill = fill1[q];
+        const uint64_t base = q * cap1 + (uint64_t)(tile - (uint32_t)q * (uint32_t)tiles_per_bin) * L2S_TILE;
         const uint64_t end = fill < lim ? fill : lim;
         if (base >= end) continue;
         K key[L2S_PER];

@@ -302,6 +302,84 @@ int ktg_insert_keys_device(ktg_builder *b, const void *d_keys, uint64_t n) {
     return b->impl->insert_keys(d_keys, n);
 }
 
+int ktg_partition_keys_device(ktg_builder *b, const void *d_keys, uint64_t n, void **d_out, uint64_t *counts) {
+    KTG_ENTER(b);
+    if (!d_out || !counts) return fail(KTG_ERR_INVALID, "null argument");
+    return b->impl->partition_keys(d_keys, n, d_out, counts);
+}
+
+int ktg_mg_plan(ktg_builder *b, uint64_t max_windows, int *needs_realloc) {
+    KTG_ENTER(b);
+    if (!needs_realloc) return fail(KTG_ERR_INVALID, "null argument");
+    return b->impl->mg_plan(max_windows, needs_realloc);
+}
+
+int ktg_mg_prepare(ktg_builder *b, uint64_t max_windows, void **rx_base, uint64_t *rx_bytes,
+                   uint64_t *bucket_cap, uint32_t *n_sub) {
+    KTG_ENTER(b);
+    if (!rx_base || !rx_bytes || !bucket_cap || !n_sub) return fail(KTG_ERR_INVALID, "null argument");
+    return b->impl->mg_prepare(max_windows, rx_base, rx_bytes, bucket_cap, n_sub);
+}
+
+int ktg_mg_scatter_reads_device(ktg_builder *b, const void *d_bases, const void *d_offsets, uint64_t n_reads,
+                                uint64_t total_bases, void *const *peer_rx, void **d_cursors) {
+    KTG_ENTER(b);
+    if (!peer_rx || !d_cursors) return fail(KTG_ERR_INVALID, "null argument");
+    return b->impl->mg_scatter_reads((const uint8_t *)d_bases, (const uint64_t *)d_offsets, n_reads, total_bases,
+                                     peer_rx, d_cursors);
+}
+
+int ktg_mg_insert_buckets(ktg_builder *b, const void *d_bucket_ends, uint64_t n_keys_estimate) {
+    KTG_ENTER(b);
+    return b->impl->mg_insert_buckets(d_bucket_ends, n_keys_estimate);
+}
+
+int ktg_mg_sketch(ktg_builder *b, void **d_regs, uint32_t *n_regs) {
+    KTG_ENTER(b);
+    if (!d_regs || !n_regs) return fail(KTG_ERR_INVALID, "null argument");
+    return b->impl->mg_sketch(d_regs, n_regs);
+}
+
+int ktg_mg_plan_growth(ktg_builder *b, int *grew) {
+    KTG_ENTER(b);
+    if (!grew) return fail(KTG_ERR_INVALID, "null argument");
+    return b->impl->mg_plan_growth(grew);
+}
+
+int ktg_mg_spill(ktg_builder *b, void **d_keys, uint64_t *n) {
+    KTG_ENTER(b);
+    if (!d_keys || !n) return fail(KTG_ERR_INVALID, "null argument");
+    return b->impl->mg_spill(d_keys, n);
+}
+
+int ktg_mg_insert_spill(ktg_builder *b, const void *d_keys, uint64_t n) {
+    KTG_ENTER(b);
+    return b->impl->mg_insert_spill(d_keys, n);
+}
+
+int ktg_ipc_get_handle(const void *dev_ptr, uint8_t handle[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    if (!dev_ptr || !handle) return fail(KTG_ERR_INVALID, "null argument");
+    cudaIpcMemHandle_t h;
+    KTG_CUDA(cudaIpcGetMemHandle(&h, (void *)dev_ptr));
+    memcpy(handle, &h, 64);
+    return KTG_OK;
+}
+
+int ktg_ipc_open(const uint8_t handle[64], void **dev_ptr) {
+    if (!dev_ptr || !handle) return fail(KTG_ERR_INVALID, "null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    KTG_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return KTG_OK;
+}
+
+int ktg_ipc_close(void *dev_ptr) {
+    if (!dev_ptr) return KTG_OK;
+    KTG_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+    return KTG_OK;
+}
+
 int ktg_host_alloc(void **p, size_t bytes) {
     if (!p) return fail(KTG_ERR_INVALID, "null argument");
     KTG_CUDA(cudaHostAlloc(p, bytes, cudaHostAllocDefault));

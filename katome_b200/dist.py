@@ -1,11 +1,17 @@
 """Hash-sharded build across GPUs: one process per GPU, `torch.distributed` for the plumbing.
 
 The table is sharded by owner(key) = hash(canonical k-mer) range-reduced to [0, world)
-(SURVEY 8e).  Every rank extracts the keys of its own reads grouped by owner
-(`ktg_partition_reads_device`), the groups are routed with one all-to-all over
-NVLink, and every rank inserts what it received into its shard
-(`ktg_insert_keys_device`).  Shards are disjoint by construction, so the merged GIR
-is their concatenation and all whole-graph statistics are plain reductions.
+(SURVEY 8e).  Shards are disjoint by construction, so the merged GIR is their
+concatenation and all whole-graph statistics are plain reductions.
+
+Two data paths:
+  fused (default on one node, world <= 8): the level-1 scatter kernel of every rank writes
+      its keys straight into the owners' HBM over NVLink (CUDA IPC mapped peer memory),
+      grouped by (source rank, sub-table), so the owner continues with the level-2 scatter
+      and the page update as on one GPU.  NCCL only carries the small control messages
+      (batch size, sketch, bucket fills) and doubles as the ordering between ranks.
+  nccl: every rank groups its keys by owner (`ktg_partition_reads_device`), one all-to-all
+      routes them, every rank inserts what it received (`ktg_insert_keys_device`).
 
 `exchange_keys` is device agnostic on purpose: with the gloo backend and CPU tensors
 it runs the same routing logic in the world_size-2 CPU tests.
@@ -17,7 +23,9 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 import torch.distributed as dist
 
-from .gir import DeviceArray, GpuGIR
+import os
+
+from .gir import DeviceArray, GpuGIR, ipc_close, ipc_get_handle, ipc_open
 
 MASK64 = (1 << 64) - 1
 
@@ -62,17 +70,87 @@ class ShardedGIR:
     """One shard of a GIR that is hash-partitioned over the ranks of a process group."""
 
     def __init__(self, k: int = 40, reverse_complement: bool = True, *, group=None, edges_count: Optional[int] = None,
-                 **kw):
+                 fused: Optional[bool] = None, **kw):
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.device = torch.device("cuda", torch.cuda.current_device())
+        if fused is None:
+            fused = self.world <= 8 and os.environ.get("KTG_EXCHANGE", "fused") != "nccl"
+        self.fused = bool(fused)
+        if self.fused:
+            kw.setdefault("force_partition", True)  # the fused path has no unpartitioned mode
         self.gir = GpuGIR(k, reverse_complement, edges_count=edges_count, world_size=self.world, rank=self.rank,
                           stream=torch.cuda.current_stream().cuda_stream, **kw)
+        self.k = int(k)
         self.words = self.gir.key_words()
         self.exchanged_bytes = 0
+        self._peers: List[int] = []   # receive buffer of every rank, mapped here (own rank: own pointer)
+        self._cap = self._n_sub = 0
+
+    # ---- fused path ------------------------------------------------------------------------
+    def _unmap_peers(self):
+        for r, p in enumerate(self._peers):
+            if r != self.rank and p:
+                ipc_close(p)
+        self._peers = []
+
+    def _map_peers(self, gmax: int):
+        """(re)allocate the receive buffer for batches of up to gmax windows per rank and map
+        everybody's buffer; collective."""
+        self._unmap_peers()
+        dist.barrier(self.group)  # nobody still has the old buffer mapped when it is freed
+        base, nbytes, self._cap, self._n_sub = self.gir.mg_prepare(gmax)
+        mine = torch.frombuffer(bytearray(ipc_get_handle(base)), dtype=torch.uint8).to(self.device)
+        allh = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(allh, mine, group=self.group)
+        self._peers = [base if r == self.rank else ipc_open(bytes(allh[r].cpu().numpy().tobytes()))
+                       for r in range(self.world)]
+
+    def _add_reads_fused(self, d_bases, d_offsets, n_reads: int, total_bases: int):
+        W, dev = self.world, self.device
+        ub = max(int(total_bases) - int(n_reads) * (self.k - 1), 0)  # windows if every read is accepted
+        t = torch.tensor([ub], dtype=torch.int64, device=dev)
+        # also orders "every rank has finished reading its receive buffer" before anybody writes
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        gmax = int(t.item())
+        if gmax == 0:
+            return
+        while True:
+            if not self._peers or self.gir.mg_plan(gmax):
+                self._map_peers(gmax)
+            cur_ptr = self.gir.mg_scatter_reads_device(d_bases, d_offsets, n_reads, total_bases, self._peers)
+            sk_ptr, sk_n = self.gir.mg_sketch()
+            regs = torch.as_tensor(DeviceArray(sk_ptr, sk_n, "<i4"), device=dev)
+            dist.all_reduce(regs, op=dist.ReduceOp.MAX, group=self.group)
+            if not self.gir.mg_plan_growth():
+                break  # (after a growth the geometry changed: map new buffers and redo the batch)
+        n_sub, cap = self._n_sub, self._cap
+        cur = torch.as_tensor(DeviceArray(cur_ptr, W * n_sub), device=dev)
+        got = torch.empty_like(cur)
+        dist.all_to_all_single(got, cur, group=self.group)  # also: the writers' kernels have completed
+        part = torch.arange(n_sub, dtype=torch.int64, device=dev)
+        fill = (got.view(W, n_sub) - (self.rank * n_sub + part) * cap).clamp_(max=cap)
+        ends = (torch.arange(W, dtype=torch.int64, device=dev)[:, None] * n_sub + part[None, :]) * cap + fill
+        self.gir.mg_insert_buckets(ends.contiguous(), gmax)
+        self._keep = (ends, got)
+        self.exchanged_bytes += int(ub * 8 * self.words * (W - 1) / W)
+        # keys that did not fit their bucket (skew): routed the slow way
+        sp_ptr, n_sp = self.gir.mg_spill()
+        tot = torch.tensor([n_sp], dtype=torch.int64, device=dev)
+        dist.all_reduce(tot, group=self.group)
+        if int(tot.item()):
+            ptr, counts = self.gir.partition_keys_device(sp_ptr, n_sp)
+            n = sum(counts)
+            keys = torch.as_tensor(DeviceArray(ptr, n * self.words), device=dev) if n else \
+                torch.empty(0, dtype=torch.int64, device=dev)
+            recv, rcounts = exchange_keys(keys, counts, self.words, self.group)
+            self.gir.mg_insert_spill(recv, sum(rcounts))
+            self._keep = (ends, got, recv)
 
     def add_reads_device(self, d_bases, d_offsets, n_reads: int, total_bases: int):
+        if self.fused:
+            return self._add_reads_fused(d_bases, d_offsets, n_reads, total_bases)
         ptr, counts = self.gir.partition_reads_device(d_bases, d_offsets, n_reads, total_bases)
         n = sum(counts)
         if n:
@@ -104,4 +182,8 @@ class ShardedGIR:
         raise NotImplementedError("multi-GPU standardize_edges needs the all-reduced sums (next round)")
 
     def close(self):
+        if self._peers:
+            torch.cuda.synchronize()
+            self._unmap_peers()
+            dist.barrier(self.group)
         self.gir.close()

@@ -58,11 +58,11 @@ def _ptr(x) -> int:
 
 
 class DeviceArray:
-    """Zero-copy view of `n` 64-bit words at a device pointer owned by a handle, for
-    `torch.as_tensor(view, device="cuda")` (CUDA array interface, dtype int64)."""
+    """Zero-copy view of `n` words at a device pointer owned by a handle, for
+    `torch.as_tensor(view, device="cuda")` (CUDA array interface; int64 unless `typestr`)."""
 
-    def __init__(self, ptr: int, n: int):
-        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<i8", "data": (int(ptr), False),
+    def __init__(self, ptr: int, n: int, typestr: str = "<i8"):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False),
                                          "version": 2}
 
 
@@ -267,6 +267,55 @@ class GpuGIR:
     def insert_keys_device(self, d_keys, n: int):
         _check(self._L.ktg_insert_keys_device(self._h, _ptr(d_keys), int(n)))
 
+    def partition_keys_device(self, d_keys, n: int):
+        """-> (device pointer of the owner-major copy of the keys, counts per owner)"""
+        out = C.c_void_p()
+        counts = (C.c_uint64 * self.world_size)()
+        _check(self._L.ktg_partition_keys_device(self._h, _ptr(d_keys), int(n), C.byref(out), counts))
+        return int(out.value or 0), [int(c) for c in counts]
+
+    # ---- fused multi-GPU exchange (include/katome_gpu.h, "fused exchange") -----------------
+    def mg_plan(self, max_windows: int) -> bool:
+        need = C.c_int(0)
+        _check(self._L.ktg_mg_plan(self._h, int(max_windows), C.byref(need)))
+        return bool(need.value)
+
+    def mg_prepare(self, max_windows: int):
+        """-> (receive buffer pointer, bytes, bucket capacity in keys, sub-tables)"""
+        base, nbytes, cap, n_sub = C.c_void_p(), C.c_uint64(), C.c_uint64(), C.c_uint32()
+        _check(self._L.ktg_mg_prepare(self._h, int(max_windows), C.byref(base), C.byref(nbytes), C.byref(cap),
+                                      C.byref(n_sub)))
+        return int(base.value), int(nbytes.value), int(cap.value), int(n_sub.value)
+
+    def mg_scatter_reads_device(self, d_bases, d_offsets, n_reads: int, total_bases: int, peer_rx) -> int:
+        """peer_rx: receive buffer pointers of all ranks (own rank included); -> cursors pointer"""
+        arr = (C.c_void_p * self.world_size)(*[C.c_void_p(int(p)) for p in peer_rx])
+        cur = C.c_void_p()
+        _check(self._L.ktg_mg_scatter_reads_device(self._h, _ptr(d_bases), _ptr(d_offsets), int(n_reads),
+                                                   int(total_bases), arr, C.byref(cur)))
+        return int(cur.value)
+
+    def mg_insert_buckets(self, d_bucket_ends, n_keys_estimate: int):
+        _check(self._L.ktg_mg_insert_buckets(self._h, _ptr(d_bucket_ends), int(n_keys_estimate)))
+
+    def mg_sketch(self):
+        p, n = C.c_void_p(), C.c_uint32()
+        _check(self._L.ktg_mg_sketch(self._h, C.byref(p), C.byref(n)))
+        return int(p.value), int(n.value)
+
+    def mg_plan_growth(self) -> bool:
+        g = C.c_int(0)
+        _check(self._L.ktg_mg_plan_growth(self._h, C.byref(g)))
+        return bool(g.value)
+
+    def mg_spill(self):
+        p, n = C.c_void_p(), C.c_uint64()
+        _check(self._L.ktg_mg_spill(self._h, C.byref(p), C.byref(n)))
+        return int(p.value or 0), int(n.value)
+
+    def mg_insert_spill(self, d_keys, n: int):
+        _check(self._L.ktg_mg_insert_spill(self._h, _ptr(d_keys), int(n)))
+
     # ---- observability -----------------------------------------------------------------
     def profile(self) -> dict:
         n = C.c_uint32(0)
@@ -282,6 +331,22 @@ class GpuGIR:
         i = L.KtgInfo()
         _check(self._L.ktg_get_info(self._h, C.byref(i)))
         return {name: int(getattr(i, name)) for name, _ in L.KtgInfo._fields_}
+
+
+def ipc_get_handle(dev_ptr: int) -> bytes:
+    buf = C.create_string_buffer(64)
+    _check(L.lib().ktg_ipc_get_handle(C.c_void_p(int(dev_ptr)), buf))
+    return buf.raw
+
+
+def ipc_open(handle: bytes) -> int:
+    p = C.c_void_p()
+    _check(L.lib().ktg_ipc_open(C.create_string_buffer(bytes(handle), 64), C.byref(p)))
+    return int(p.value)
+
+
+def ipc_close(dev_ptr: int):
+    _check(L.lib().ktg_ipc_close(C.c_void_p(int(dev_ptr))))
 
 
 def synth_reads_device(d_out, seed_g: int, genome_len: int, read_len: int, err_ppm: int, r0: int, r1: int,

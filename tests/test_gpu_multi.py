@@ -27,7 +27,7 @@ for k, n, L, G in ((31, 6000, 150, 200_000), (63, 3000, 150, 100_000)):
     half = n // world
     mine = torch.from_numpy(reads[rank * half * L:(rank + 1) * half * L]).cuda()
     offs = torch.arange(0, (half + 1) * L, L, dtype=torch.int64, device="cuda")
-    for kw in ({}, {"force_partition": True, "sub_table_log2_bytes": 16}):
+    for kw in ({}, {"fused": False}, {"force_pages": True}, {"fused": False, "force_partition": True, "sub_table_log2_bytes": 16}):
         sg = ShardedGIR(k, True, **kw)
         for _ in range(2):  # reset + rebuild gives the same table
             sg.reset()

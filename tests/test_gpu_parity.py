@@ -356,6 +356,93 @@ def test_two_rank_sharding_on_one_gpu(K):
     assert ((d0[0] + d1[0]) & (2**64 - 1), d0[1] + d1[1], d0[2] + d1[2], max(d0[3], d1[3])) == cd
 
 
+def _fused_exchange_emulated(K, gs, batches, k):
+    """The protocol of katome_b200.dist.ShardedGIR._add_reads_fused with all ranks in one process on
+    one GPU: peers' receive buffers are plain device pointers, collectives are torch ops."""
+    W = len(gs)
+    gmax = max(max(nb - n * (k - 1), 0) for (_, _, n, nb) in batches)
+    while True:
+        prep = [g.mg_prepare(gmax) for g in gs]
+        peers = [p[0] for p in prep]
+        cap, n_sub = prep[0][2], prep[0][3]
+        assert all(p[2] == cap and p[3] == n_sub for p in prep)
+        curs = [torch.as_tensor(K.DeviceArray(g.mg_scatter_reads_device(d, o, n, nb, peers), W * n_sub), device="cuda")
+                for g, (d, o, n, nb) in zip(gs, batches)]
+        regs = [torch.as_tensor(K.DeviceArray(*g.mg_sketch(), "<i4"), device="cuda") for g in gs]
+        m = torch.stack(regs).max(dim=0).values
+        for r in regs:
+            r.copy_(m)
+        grew = [g.mg_plan_growth() for g in gs]
+        assert len(set(grew)) == 1  # every rank reaches the same decision
+        if not grew[0]:
+            break
+    part = torch.arange(n_sub, dtype=torch.int64, device="cuda")
+    for r, g in enumerate(gs):
+        got = torch.stack([c.view(W, n_sub)[r] for c in curs])  # what the all-to-all delivers to rank r
+        fill = (got - (r * n_sub + part) * cap).clamp_(max=cap)
+        ends = (torch.arange(W, dtype=torch.int64, device="cuda")[:, None] * n_sub + part[None, :]) * cap + fill
+        g.mg_insert_buckets(ends.contiguous(), gmax)
+        torch.cuda.synchronize()
+    words = gs[0].key_words()
+    routed = [[] for _ in range(W)]
+    n_spilled = 0
+    for g in gs:
+        ptr, n = g.mg_spill()
+        n_spilled += n
+        if n:
+            out, counts = g.partition_keys_device(ptr, n)
+            buf = torch.as_tensor(K.DeviceArray(out, n * words), device="cuda").clone()
+            o = 0
+            for dst in range(W):
+                routed[dst].append(buf[o:o + counts[dst] * words])
+                o += counts[dst] * words
+    for r, g in enumerate(gs):
+        if routed[r]:
+            keys = torch.cat(routed[r])
+            g.mg_insert_spill(keys, keys.numel() // words)
+            torch.cuda.synchronize()
+    return n_spilled
+
+
+@pytest.mark.parametrize("k,W", [(31, 2), (31, 3), (40, 2), (63, 4)])
+def test_fused_exchange_ranks_emulated_on_one_gpu(K, k, W):
+    """fused multi-GPU path: scatter into the owners' receive buckets, level-2 scatter + page update
+    from them; two batches, a skewed one (bucket overflow -> spill list) and growth without a hint"""
+    from oracle import oracle as O
+    seed, G, L, n = 1234 + k, 120_000, 150, 3000 * W
+    host = O.synth_reads(seed, G, L, 5000, 0, n)
+    skew = np.frombuffer((b"A" * L) * (2500 * W), dtype=np.uint8)  # one key, 2500*W*(L-k+1) times
+    cpu = O.OracleGIR(k)
+    cpu.add_reads(host, np.arange(n + 1, dtype=np.uint64) * L, True)
+    cpu.add_reads(skew, np.arange(2500 * W + 1, dtype=np.uint64) * L, True)
+    s = torch.cuda.current_stream().cuda_stream
+    gs = [K.GpuGIR(k, True, world_size=W, rank=r, force_pages=True, stream=s) for r in range(W)]
+    spilled = 0
+    for data, per in ((host, n // W), (skew, 2500)):
+        batches = []
+        for r in range(W):
+            d = torch.from_numpy(data[r * per * L:(r + 1) * per * L].copy()).cuda()
+            offs = torch.arange(0, (per + 1) * L, L, dtype=torch.int64, device="cuda")
+            batches.append((d, offs, per, per * L))
+        spilled += _fused_exchange_emulated(K, gs, batches, k)
+    assert spilled > 0  # the skewed batch must have exercised the spill route
+    digs = [g.digest() for g in gs]
+    cd = cpu.digest()
+    assert (sum(d[0] for d in digs) & (2**64 - 1), sum(d[1] for d in digs), sum(d[2] for d in digs),
+            max(d[3] for d in digs)) == cd
+    parts = [g.export_edges(sorted=True) for g in gs]
+    for r, (hi, lo, w) in enumerate(parts):
+        assert all(gs[r].owner_of(int(h), int(x)) == r for h, x in list(zip(hi.tolist(), lo.tolist()))[:100])
+    hi = np.concatenate([p[0] for p in parts]); lo = np.concatenate([p[1] for p in parts])
+    w = np.concatenate([p[2] for p in parts])
+    order = np.lexsort((lo, hi))
+    ehi, elo, ew = cpu.export_edges()
+    assert np.array_equal(hi[order], ehi) and np.array_equal(lo[order], elo) and np.array_equal(w[order], ew)
+    assert sum(g.info()["page_updates"] for g in gs) > 0
+    for g in gs:
+        g.close()
+
+
 def test_host_mirror_of_owner_matches_device(K):
     from katome_b200 import hashing
     rng = np.random.default_rng(9)
