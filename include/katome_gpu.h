@@ -160,20 +160,21 @@ int ktg_insert_keys_device(ktg_builder *b, const void *d_keys, uint64_t n);
 /* Same grouping for an array of keys (the spill list of the fused exchange below). */
 int ktg_partition_keys_device(ktg_builder *b, const void *d_keys, uint64_t n, void **d_out, uint64_t *counts);
 
-/* ---- fused exchange (one node, world_size <= 8): the level-1 scatter kernel of every
- * rank writes its keys straight into the owners' HBM over NVLink (mapped peer memory),
- * already grouped by (source rank, sub-table); there is no separate all-to-all of keys.
- * Per batch, on every rank and in this order:
- *   1. ktg_mg_plan / ktg_mg_prepare size the receive buffer for the largest per-rank batch
- *      (all ranks pass the same max_windows); when it is replaced, peers unmap the old one
- *      first and the new ktg_ipc_get_handle is exchanged (ktg_ipc_open on the peers);
+/* ---- fused exchange (one node, world_size <= 8): the extraction kernel of every rank
+ * writes its keys, grouped by owner, straight into the owners' HBM over NVLink (mapped peer
+ * memory); there is no separate all-to-all of keys.  Per batch, on every rank and in this order:
+ *   1. ktg_mg_plan / ktg_mg_prepare size the receive buffer (one bucket per source rank) for
+ *      the largest per-rank batch (all ranks pass the same max_windows); when it is replaced,
+ *      peers unmap the old one first and the new ktg_ipc_get_handle is exchanged
+ *      (ktg_ipc_open on the peers);
  *   2. a collective orders "everybody finished reading its receive buffer" before
  *   3. ktg_mg_scatter_reads_device(peer_rx[world]) - pack + extract + scatter into the
- *      peers' buckets; *d_cursors (device, world * n_sub u64) are the bucket ends it reached;
- *   4. the sketch (ktg_mg_sketch) is all-reduced with MAX, ktg_mg_plan_growth sizes the shard
- *      from it (same decision on every rank; if it grew, go back to 1 and redo the batch);
+ *      peers' buckets; *d_cursors (device, world u64) are the bucket ends it reached
+ *      (owner * bucket_cap + fill);
+ *   4. the sketch (ktg_mg_sketch) is all-reduced with MAX so that every shard can size itself;
  *   5. an all-to-all of the cursors tells every owner how full its buckets are (and that the
- *      writers are done); ktg_mg_insert_buckets runs level-2 scatter + page update over them;
+ *      writers are done); ktg_mg_insert_buckets partitions them by sub-table into the staged
+ *      buckets, from where they are flushed like any other batch;
  *   6. keys that did not fit a bucket (ktg_mg_spill) are grouped with
  *      ktg_partition_keys_device, exchanged with NCCL and added with ktg_mg_insert_spill. */
 int ktg_mg_plan(ktg_builder *b, uint64_t max_windows, int *needs_realloc);
@@ -181,9 +182,8 @@ int ktg_mg_prepare(ktg_builder *b, uint64_t max_windows, void **rx_base, uint64_
                    uint64_t *bucket_cap, uint32_t *n_sub);
 int ktg_mg_scatter_reads_device(ktg_builder *b, const void *d_bases, const void *d_offsets, uint64_t n_reads,
                                 uint64_t total_bases, void *const *peer_rx, void **d_cursors);
-int ktg_mg_insert_buckets(ktg_builder *b, const void *d_bucket_ends, uint64_t n_keys_estimate);
+int ktg_mg_insert_buckets(ktg_builder *b, const void *d_bucket_ends, uint64_t n_keys);
 int ktg_mg_sketch(ktg_builder *b, void **d_regs, uint32_t *n_regs);
-int ktg_mg_plan_growth(ktg_builder *b, int *grew);
 int ktg_mg_spill(ktg_builder *b, void **d_keys, uint64_t *n);
 int ktg_mg_insert_spill(ktg_builder *b, const void *d_keys, uint64_t n);
 /* CUDA IPC handles of device allocations (cudaIpcGetMemHandle / OpenMemHandle / CloseMemHandle) */

@@ -210,7 +210,6 @@ struct BuilderBase {
                                  uint64_t total_bases, void *const *peer_rx, void **d_cursors) = 0;
     virtual int mg_insert_buckets(const void *d_bucket_ends, uint64_t n_keys_estimate) = 0;
     virtual int mg_sketch(void **d_regs, uint32_t *n_regs) = 0;
-    virtual int mg_plan_growth(int *grew) = 0;
     virtual int mg_spill(void **d_keys, uint64_t *n) = 0;
     virtual uint32_t owner_of(uint64_t hi, uint64_t lo) = 0;
     virtual int info(ktg_info *out) = 0;
@@ -376,7 +375,8 @@ template <class K> struct Builder : BuilderBase {
     }
     void set_smem_attrs() {
         const size_t mx = ScatterSmem<K, SCATTER_TILE>::bytes(MAX_BINS, true);
-        allow_smem(scatter_pages_kernel<K>, ScatterSmem<K, L2S_TILE>::bytes(MAX_PAGES_PER_SUB, false));
+        allow_smem(scatter_buckets_kernel<K, 2>, ScatterSmem<K, L2S_TILE>::bytes(MAX_PAGES_PER_SUB, false));
+        allow_smem(scatter_buckets_kernel<K, 1>, ScatterSmem<K, L2S_TILE>::bytes(MAX_BINS, false));
         allow_smem(update_pages_kernel<K>, page_smem_bytes());
         allow_smem(scatter_reads_kernel<K, true, BIN_PART, true>, mx);
         allow_smem(scatter_reads_kernel<K, false, BIN_PART, true>, mx);
@@ -384,8 +384,8 @@ template <class K> struct Builder : BuilderBase {
         allow_smem(scatter_reads_kernel<K, false, BIN_PART, false>, mx);
         allow_smem(scatter_reads_kernel<K, true, BIN_OWNER, false>, mx);
         allow_smem(scatter_reads_kernel<K, false, BIN_OWNER, false>, mx);
-        allow_smem(scatter_reads_kernel<K, true, BIN_OWNER_PART, true>, mx);
-        allow_smem(scatter_reads_kernel<K, false, BIN_OWNER_PART, true>, mx);
+        allow_smem(scatter_reads_kernel<K, true, BIN_OWNER, true>, mx);
+        allow_smem(scatter_reads_kernel<K, false, BIN_OWNER, true>, mx);
         allow_smem(scatter_keys_kernel<K, true, false>, mx);
         allow_smem(scatter_keys_kernel<K, false, true>, mx);
         allow_smem(scatter_keys_kernel<K, false, false>, mx);
@@ -657,7 +657,7 @@ template <class K> struct Builder : BuilderBase {
         uint64_t n_tiles = std::max<uint64_t>(1, (bt.im.n_items + SCATTER_THREADS - 1) / SCATTER_THREADS);
         PeerOut peers{};
         if (po) peers = *po;
-        prof.begin(BINS == BIN_OWNER_PART ? "scatter_reads_p2p" : "scatter_reads", bt.windows, stream);
+        prof.begin(po ? "scatter_reads_p2p" : "scatter_reads", bt.windows, stream);
         if (rc) {
             int g = (int)std::min<uint64_t>(grid_for(scatter_reads_kernel<K, true, BINS, HLL>, SCATTER_THREADS, ss, props), n_tiles);
             scatter_reads_kernel<K, true, BINS, HLL><<<g, SCATTER_THREADS, ss, stream>>>(packed, nstart, bt.n_words, k, bt.im, tab, n_bins, o, (uint32_t *)b_hll.p, peers);
@@ -726,9 +726,9 @@ template <class K> struct Builder : BuilderBase {
         o.spill_cap = spill_cap;
         const uint64_t tiles_per_bin = cap1 / L2S_TILE, n_tiles = tiles_per_bin * n_bins;
         const size_t ss = ScatterSmem<K, L2S_TILE>::bytes(tab.pages_per_sub(), false);
-        int g = (int)std::min<uint64_t>(grid_for(scatter_pages_kernel<K>, L2S_THREADS, ss, props), n_tiles);
+        int g = (int)std::min<uint64_t>(grid_for(scatter_buckets_kernel<K, 2>, L2S_THREADS, ss, props), n_tiles);
         prof.begin("scatter_pages", n_keys, stream);
-        scatter_pages_kernel<K><<<g, L2S_THREADS, ss, stream>>>(keys1, fill1, cap1, tiles_per_bin, n_tiles, sub_mod, tab, o);
+        scatter_buckets_kernel<K, 2><<<g, L2S_THREADS, ss, stream>>>(keys1, fill1, cap1, tiles_per_bin, n_tiles, sub_mod, tab, o);
         prof.end(stream);
         const size_t ps = page_smem_bytes(tab.page_log2);
         g = (int)std::min<uint64_t>(grid_for(update_pages_kernel<K>, PAGE_THREADS, ps, props), n_pages);
@@ -838,7 +838,8 @@ template <class K> struct Builder : BuilderBase {
         trace("flush", staged_keys);
         double est = 0;
         KTG_TRY(hll_estimate(&est)); // synchronises the stream
-        const uint64_t distinct = hll_base + (uint64_t)(est * 1.08) + 64;
+        // fused multi-GPU mode: the sketch was all-reduced, it describes the keys of ALL ranks
+        const uint64_t distinct = hll_base + (uint64_t)(est * (mg_mode ? 1.10 / tab.world : 1.08)) + 64;
         occupied_ub = distinct;
         bool moved = false;
         if ((double)distinct > LOAD_MAX * (double)tab.capacity()) {
@@ -1193,50 +1194,47 @@ template <class K> struct Builder : BuilderBase {
         return KTG_OK;
     }
 
-    // ---- multi-GPU, fused: the level-1 scatter writes straight into the owners' HBM ------
-    // Rank r reserves world * n_sub receive buckets of mg_cap keys: bucket (s, p) takes the
-    // keys of sub-table p that rank s extracts.  Only rank s writes it (cursors are local to
-    // the sender: no remote atomics), so after the senders' kernels have completed the owner
-    // runs the level-2 scatter + page update over its buckets exactly as on one GPU.
+    // ---- multi-GPU, fused: the extraction kernel writes straight into the owners' HBM ------
+    // Rank r reserves one receive bucket of mg_cap keys per source rank.  Only rank s writes
+    // bucket s (cursors are local to the sender: no remote atomics), in runs of tile / world
+    // keys, so NVLink sees kilobyte-sized writes.  After the senders' kernels have completed the
+    // owner partitions what it received by sub-table (level 1) into its staged buckets and
+    // carries on exactly as on one GPU.  Nothing here depends on the table geometry, so ranks
+    // may grow their shards independently.
     DeviceBuf b_rx, b_mg_cur, b_mg_spill;
     uint64_t mg_cap = 0, mg_spill_cap = 0;
-    uint32_t mg_bins = 0, mg_sub_log2 = 0;
+    bool mg_mode = false;
 
-    int mg_geometry(uint64_t max_windows, uint32_t *bins, uint64_t *cap) {
+    int mg_geometry(uint64_t max_windows, uint64_t *cap) {
         const uint32_t W = tab.world;
-        if (W > (uint32_t)MAX_P2P_WORLD || (uint64_t)W * tab.n_sub > MAX_BINS)
-            return fail(KTG_ERR_INVALID, "fused exchange needs world <= %d and world * sub-tables <= %u", MAX_P2P_WORLD, MAX_BINS);
-        *bins = W * tab.n_sub;
-        *cap = bucket_cap_for(std::max<uint64_t>(max_windows, 1), *bins);
-        if ((double)*cap * *bins >= 4.0e9) return fail(KTG_ERR_INVALID, "batch too large: split it (32-bit bucket positions)");
+        if (W > (uint32_t)MAX_P2P_WORLD) return fail(KTG_ERR_INVALID, "fused exchange needs world <= %d", MAX_P2P_WORLD);
+        *cap = bucket_cap_for(std::max<uint64_t>(max_windows, 1), W);
+        if ((double)*cap * W >= 4.0e9) return fail(KTG_ERR_INVALID, "batch too large: split it (32-bit bucket positions)");
         return KTG_OK;
     }
     // would mg_prepare(max_windows) replace the receive buffer?  (peers must unmap it first)
     int mg_plan(uint64_t max_windows, int *needs_realloc) override {
-        uint32_t bins = 0;
         uint64_t cap = 0;
-        KTG_TRY(mg_geometry(max_windows, &bins, &cap));
-        *needs_realloc = bins != mg_bins || tab.sub_log2 != mg_sub_log2 || cap > mg_cap || !b_rx.p;
+        KTG_TRY(mg_geometry(max_windows, &cap));
+        *needs_realloc = cap > mg_cap || !b_rx.p;
         return KTG_OK;
     }
     int mg_prepare(uint64_t max_windows, void **rx_base, uint64_t *rx_bytes, uint64_t *bucket_cap,
                    uint32_t *n_sub) override {
-        uint32_t bins = 0;
         uint64_t cap = 0;
-        KTG_TRY(mg_geometry(max_windows, &bins, &cap));
-        if (bins != mg_bins || tab.sub_log2 != mg_sub_log2 || cap > mg_cap || !b_rx.p) {
+        KTG_TRY(mg_geometry(max_windows, &cap));
+        const uint32_t W = tab.world;
+        if (cap > mg_cap || !b_rx.p) {
             KTG_TRY(sync());
             b_rx.release();
-            KTG_TRY(b_rx.ensure((size_t)cap * bins * sizeof(K) + 64));
+            KTG_TRY(b_rx.ensure((size_t)cap * W * sizeof(K) + 64));
             mg_cap = cap;
-            mg_bins = bins;
-            mg_sub_log2 = tab.sub_log2;
             mg_spill_cap = std::max<uint64_t>(1u << 20, max_windows / 16);
             KTG_TRY(b_mg_spill.ensure(mg_spill_cap * sizeof(K) + 64));
-            KTG_TRY(b_mg_cur.ensure(((size_t)bins + 2) * 8));
+            KTG_TRY(b_mg_cur.ensure(((size_t)W + 2) * 8));
         }
         *rx_base = b_rx.p;
-        *rx_bytes = (size_t)mg_cap * mg_bins * sizeof(K);
+        *rx_bytes = (size_t)mg_cap * W * sizeof(K);
         *bucket_cap = mg_cap;
         *n_sub = tab.n_sub;
         return KTG_OK;
@@ -1252,42 +1250,60 @@ template <class K> struct Builder : BuilderBase {
     int mg_scatter_reads(const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t n_reads,
                          uint64_t total_bases, void *const *peer_rx, void **d_cursors) override {
         if (deferred_error != KTG_OK) return fail(deferred_error, "build is void after an earlier error");
-        if (!mg_bins || mg_bins != tab.world * tab.n_sub) return fail(KTG_ERR_INVALID, "ktg_mg_prepare first");
+        if (!b_rx.p) return fail(KTG_ERR_INVALID, "ktg_mg_prepare first");
+        const uint32_t W = tab.world;
+        mg_mode = true;
         unsigned long long *cur = (unsigned long long *)b_mg_cur.p;
         *d_cursors = cur;
-        init_cursors_kernel<<<(mg_bins + 255) / 256, 256, 0, stream>>>(cur, mg_bins, mg_cap);
-        KTG_CUDA(cudaMemsetAsync(cur + mg_bins, 0, 8, stream)); // spill cursor
+        init_cursors_kernel<<<1, 32, 0, stream>>>(cur, W, mg_cap);
+        KTG_CUDA(cudaMemsetAsync(cur + W, 0, 8, stream)); // spill cursor
         if (n_reads == 0) return KTG_OK;
         Batch bt;
         KTG_TRY(pack(d_bases, d_offsets, n_reads, total_bases, &bt));
         if (bt.windows == 0) return KTG_OK;
         PeerOut po{};
-        po.world = tab.world;
-        po.bins_per_owner = tab.n_sub;
-        const int64_t region = (int64_t)tab.n_sub * (int64_t)mg_cap; // keys per (source, owner) region
-        for (uint32_t o = 0; o < tab.world; ++o)
-            po.rxb[o] = (K *)peer_rx[o] + ((int64_t)tab.rank - (int64_t)o) * region;
+        po.world = W;
+        po.bins_per_owner = 1;
+        // the sender's virtual position is v = owner * cap + fill; bucket `rank` of the owner
+        // starts at rank * cap, so bias the base by (rank - owner) * cap
+        for (uint32_t o = 0; o < W; ++o)
+            po.rxb[o] = (K *)peer_rx[o] + ((int64_t)tab.rank - (int64_t)o) * (int64_t)mg_cap;
         ScatterOut so;
         so.cursors = cur;
         so.bucket_cap = mg_cap;
         so.out = nullptr;
         so.spill_out = b_mg_spill.p;
-        so.spill_cursor = cur + mg_bins;
+        so.spill_cursor = cur + W;
         so.spill_cap = mg_spill_cap;
-        KTG_TRY((scatter_reads_pass<BIN_OWNER_PART, true>(bt, mg_bins, so, &po)));
+        KTG_TRY((scatter_reads_pass<BIN_OWNER, true>(bt, W, so, &po)));
         KTG_CUDA(cudaGetLastError());
         return KTG_OK;
     }
 
-    // d_bucket_ends[s * n_sub + p]: absolute end (in keys, inside the own receive buffer) of
-    // bucket (s, p), i.e. (s * n_sub + p) * mg_cap + fill, as published by rank s
-    int mg_insert_buckets(const void *d_bucket_ends, uint64_t n_keys_estimate) override {
+    // d_bucket_ends[s]: absolute end (in keys, inside the own receive buffer) of the bucket that
+    // rank s filled, i.e. s * mg_cap + fill; n_keys: the exact total.  The caller has
+    // all-reduced (max) the sketch before this call.
+    int mg_insert_buckets(const void *d_bucket_ends, uint64_t n_keys) override {
         if (deferred_error != KTG_OK) return fail(deferred_error, "build is void after an earlier error");
         const unsigned long long *ends = (const unsigned long long *)d_bucket_ends;
-        if (n_keys_estimate == 0) return KTG_OK;
-        if (use_pages(n_keys_estimate))
-            KTG_TRY(paged_update(mg_bins, mg_cap, n_keys_estimate, ends, (const K *)b_rx.p, tab.n_sub));
-        else KTG_TRY(launch_insert((const K *)b_rx.p, n_keys_estimate, ends, mg_cap, mg_bins));
+        if (n_keys == 0) return KTG_OK;
+        const uint32_t W = tab.world;
+        const uint64_t cap = mg_cap;
+        const K *rx = (const K *)b_rx.p;
+        int st = stage_add(n_keys, [&](uint32_t n_bins, const ScatterOut &o) -> int {
+            const uint64_t tiles_per_bin = cap / L2S_TILE, n_tiles = tiles_per_bin * W;
+            const size_t ss = ScatterSmem<K, L2S_TILE>::bytes(n_bins, false);
+            int g = (int)std::min<uint64_t>(grid_for(scatter_buckets_kernel<K, 1>, L2S_THREADS, ss, props), n_tiles);
+            prof.begin("scatter_received", n_keys, stream);
+            scatter_buckets_kernel<K, 1><<<g, L2S_THREADS, ss, stream>>>(rx, ends, cap, tiles_per_bin, n_tiles, 0, tab, o);
+            prof.end(stream);
+            return KTG_OK;
+        });
+        if (st == KTG_ERR_TABLE_FULL + 1000) { // skewed: L2 atomics straight from the receive buckets
+            KTG_TRY(flush_staged());
+            KTG_TRY(launch_insert(rx, n_keys, ends, cap, W));
+        }
+        else KTG_TRY(st);
         KTG_CUDA(cudaGetLastError());
         return KTG_OK;
     }
@@ -1298,28 +1314,12 @@ template <class K> struct Builder : BuilderBase {
         return KTG_OK;
     }
 
-    // The caller has all-reduced (max) the sketch, so it describes the keys of ALL ranks;
-    // this shard holds 1/world of them.  Every rank reaches the same decision.
-    int mg_plan_growth(int *grew) override {
-        *grew = 0;
-        double est = 0;
-        KTG_TRY(hll_estimate(&est));
-        const uint64_t distinct = hll_base + (uint64_t)(est * 1.10 / tab.world) + 64;
-        occupied_ub = distinct;
-        if ((double)distinct > LOAD_MAX * (double)tab.capacity()) {
-            const uint64_t need = std::max<uint64_t>((uint64_t)((double)distinct / LOAD_TARGET) + 1, 2 * tab.capacity());
-            KTG_TRY(grow_to(need));
-            *grew = 1;
-        }
-        return KTG_OK;
-    }
-
     int mg_spill(void **d_keys, uint64_t *n) override {
         unsigned long long v = 0;
         *d_keys = b_mg_spill.p;
         *n = 0;
-        if (!b_mg_cur.p || !mg_bins) return KTG_OK;
-        KTG_CUDA(cudaMemcpyAsync(&v, (unsigned long long *)b_mg_cur.p + mg_bins, 8, cudaMemcpyDeviceToHost, stream));
+        if (!b_mg_cur.p) return KTG_OK;
+        KTG_CUDA(cudaMemcpyAsync(&v, (unsigned long long *)b_mg_cur.p + tab.world, 8, cudaMemcpyDeviceToHost, stream));
         KTG_TRY(sync());
         if (v > mg_spill_cap) {
             deferred_error = KTG_ERR_TABLE_FULL;

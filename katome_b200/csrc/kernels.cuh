@@ -523,10 +523,10 @@ template <class K, int TILE> struct ScatterSmem {
     }
 };
 
-// Multi-GPU fused scatter: bins are (owner rank, sub-table) pairs and the bucket of
-// bin (o, p) lives in the HBM of rank o (mapped peer memory, NVLink), in the region
-// that rank reserves for this sender.  rxb[o] is rank o's receive base biased so that
-// the sender's virtual position v = bin * cap + fill is also the index into it.
+// Multi-GPU fused scatter: bins are owner ranks and the bucket of owner o lives in the
+// HBM of rank o (mapped peer memory, NVLink), in the region that rank reserves for this
+// sender.  rxb[o] is rank o's receive base biased so that the sender's virtual position
+// v = o * cap + fill is also the index into it.
 constexpr int MAX_P2P_WORLD = 8;
 struct PeerOut {
     void *rxb[MAX_P2P_WORLD];
@@ -654,10 +654,10 @@ __device__ __forceinline__ void tile_scatter(const K (&key)[PER], const uint32_t
 
 constexpr int SCATTER_THREADS = 256, SCATTER_PER = 8, SCATTER_TILE = SCATTER_THREADS * SCATTER_PER;
 
-// Level 1 from packed reads: extraction (K2) + partition.  BINS: 0 = by sub-table,
-// 1 = by owner rank (keys for an NCCL exchange), 2 = by (owner, sub-table) straight into
-// the owners' receive buckets over NVLink (po).
-constexpr int BIN_PART = 0, BIN_OWNER = 1, BIN_OWNER_PART = 2;
+// Level 1 from packed reads: extraction (K2) + partition.  BINS: by sub-table, or by owner
+// rank -- into a local array for an NCCL exchange (po.world == 0) or straight into the
+// owners' receive buckets over NVLink (po).
+constexpr int BIN_PART = 0, BIN_OWNER = 1;
 template <class K, bool RC, int BINS, bool HLL>
 __global__ void __launch_bounds__(SCATTER_THREADS, 3)
 scatter_reads_kernel(const uint64_t *__restrict__ packed, const uint8_t *__restrict__ nstart,
@@ -684,13 +684,13 @@ scatter_reads_kernel(const uint64_t *__restrict__ packed, const uint8_t *__restr
             key[j] = iw.template key<RC>();
             uint64_t h = KeyTraits<K>::hash(key[j]);
             Place p = place_of(h, t.world, t.n_sub);
-            bin[j] = BINS == BIN_OWNER ? p.owner : (BINS == BIN_PART ? p.part : p.owner * t.n_sub + p.part);
+            bin[j] = BINS == BIN_OWNER ? p.owner : p.part;
             if (HLL && hll_sampled(h) && j < (int)iw.nwin) sampled |= 1u << j;
             iw.r.step();
         }
         if (HLL) hll_update_tile<K, SCATTER_PER>(sm.regs, key, sampled);
         tile_scatter<K, SCATTER_THREADS, SCATTER_PER>(key, bin, (int)iw.nwin, sm, n_bins, o.cursors, 0, o, parity,
-                                                      BINS == BIN_OWNER_PART ? &po : nullptr);
+                                                      (BINS == BIN_OWNER && po.world) ? &po : nullptr);
     }
     if (HLL) {
         __syncthreads();
@@ -751,23 +751,24 @@ __global__ void init_cursors_kernel(unsigned long long *cursors, uint64_t n, uin
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) cursors[i] = i * cap;
 }
 
-template <class K>
+// LEVEL 2: bucket q holds keys of sub-table q (or q % sub_mod); they are grouped by page.
+// LEVEL 1: bucket q holds keys of this shard in no particular order (what source rank q sent
+//          in the fused multi-GPU exchange); they are grouped by sub-table.
+template <class K, int LEVEL>
 __global__ void __launch_bounds__(L2S_THREADS, 2)
-scatter_pages_kernel(const K *__restrict__ keys1, const unsigned long long *__restrict__ fill1,
-                     uint64_t cap1, uint64_t tiles_per_bin, uint64_t n_tiles, uint32_t sub_mod,
-                     Table<K> t, ScatterOut o) {
+scatter_buckets_kernel(const K *__restrict__ keys1, const unsigned long long *__restrict__ fill1,
+                       uint64_t cap1, uint64_t tiles_per_bin, uint64_t n_tiles, uint32_t sub_mod,
+                       Table<K> t, ScatterOut o) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const uint32_t n2 = t.pages_per_sub();
+    const uint32_t n2 = LEVEL == 2 ? t.pages_per_sub() : t.n_sub;
     ScatterSmem<K, L2S_TILE> sm;
     sm.carve(smem, n2);
     for (uint32_t i = threadIdx.x; i < 2 * n2; i += L2S_THREADS) sm.cnt[i] = 0;
     __syncthreads();
     uint32_t parity = 0;
     for (uint32_t tile = blockIdx.x; tile < (uint32_t)n_tiles; tile += gridDim.x) {
-        // level-1 bucket q holds keys of sub-table q (local buckets) or q % n_sub (receive
-        // buckets of the multi-GPU path: one set of n_sub buckets per source rank)
         const uint64_t q = tile / (uint32_t)tiles_per_bin;
-        const uint64_t b = sub_mod ? q % sub_mod : q;
+        const uint64_t b = LEVEL == 2 ? (sub_mod ? q % sub_mod : q) : 0;
         const uint64_t lim = (q + 1) * cap1, fill = fill1[q];
         const uint64_t base = q * cap1 + (uint64_t)(tile - (uint32_t)q * (uint32_t)tiles_per_bin) * L2S_TILE;
         const uint64_t end = fill < lim ? fill : lim;
@@ -780,7 +781,8 @@ scatter_pages_kernel(const K *__restrict__ keys1, const unsigned long long *__re
             const uint64_t i = base + (uint64_t)j * L2S_THREADS + threadIdx.x;
             const bool in = i < end;
             key[j] = in ? KeyTraits<K>::load_stream(&keys1[i]) : (K)0;
-            bin[j] = (KeyTraits<K>::slot_hash(key[j]) & t.sub_mask) >> t.page_log2;
+            if (LEVEL == 2) bin[j] = (KeyTraits<K>::slot_hash(key[j]) & t.sub_mask) >> t.page_log2;
+            else bin[j] = place_of(KeyTraits<K>::hash(key[j]), t.world, t.n_sub).part;
             if (in) nvalid = j + 1;
         }
         tile_scatter<K, L2S_THREADS, L2S_PER>(key, bin, nvalid, sm, n2, o.cursors + b * n2, b * n2, o, parity);

@@ -340,12 +340,6 @@ int ktg_mg_sketch(ktg_builder *b, void **d_regs, uint32_t *n_regs) {
     return b->impl->mg_sketch(d_regs, n_regs);
 }
 
-int ktg_mg_plan_growth(ktg_builder *b, int *grew) {
-    KTG_ENTER(b);
-    if (!grew) return fail(KTG_ERR_INVALID, "null argument");
-    return b->impl->mg_plan_growth(grew);
-}
-
 int ktg_mg_spill(ktg_builder *b, void **d_keys, uint64_t *n) {
     KTG_ENTER(b);
     if (!d_keys || !n) return fail(KTG_ERR_INVALID, "null argument");

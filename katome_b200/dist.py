@@ -5,11 +5,11 @@ The table is sharded by owner(key) = hash(canonical k-mer) range-reduced to [0, 
 concatenation and all whole-graph statistics are plain reductions.
 
 Two data paths:
-  fused (default on one node, world <= 8): the level-1 scatter kernel of every rank writes
-      its keys straight into the owners' HBM over NVLink (CUDA IPC mapped peer memory),
-      grouped by (source rank, sub-table), so the owner continues with the level-2 scatter
-      and the page update as on one GPU.  NCCL only carries the small control messages
-      (batch size, sketch, bucket fills) and doubles as the ordering between ranks.
+  fused (default on one node, world <= 8): the extraction kernel of every rank writes its
+      keys, grouped by owner, straight into the owners' HBM over NVLink (CUDA IPC mapped peer
+      memory); the owner partitions what it received by sub-table and carries on as on one
+      GPU.  NCCL only carries the small control messages (batch size, sketch, bucket fills)
+      and doubles as the ordering between ranks.
   nccl: every rank groups its keys by owner (`ktg_partition_reads_device`), one all-to-all
       routes them, every rank inserts what it received (`ktg_insert_keys_device`).
 
@@ -116,23 +116,19 @@ class ShardedGIR:
         gmax = int(t.item())
         if gmax == 0:
             return
-        while True:
-            if not self._peers or self.gir.mg_plan(gmax):
-                self._map_peers(gmax)
-            cur_ptr = self.gir.mg_scatter_reads_device(d_bases, d_offsets, n_reads, total_bases, self._peers)
-            sk_ptr, sk_n = self.gir.mg_sketch()
-            regs = torch.as_tensor(DeviceArray(sk_ptr, sk_n, "<i4"), device=dev)
-            dist.all_reduce(regs, op=dist.ReduceOp.MAX, group=self.group)
-            if not self.gir.mg_plan_growth():
-                break  # (after a growth the geometry changed: map new buffers and redo the batch)
-        n_sub, cap = self._n_sub, self._cap
-        cur = torch.as_tensor(DeviceArray(cur_ptr, W * n_sub), device=dev)
+        if not self._peers or self.gir.mg_plan(gmax):
+            self._map_peers(gmax)
+        cur_ptr = self.gir.mg_scatter_reads_device(d_bases, d_offsets, n_reads, total_bases, self._peers)
+        sk_ptr, sk_n = self.gir.mg_sketch()
+        regs = torch.as_tensor(DeviceArray(sk_ptr, sk_n, "<i4"), device=dev)
+        dist.all_reduce(regs, op=dist.ReduceOp.MAX, group=self.group)  # every shard sizes itself from it
+        cap = self._cap
+        cur = torch.as_tensor(DeviceArray(cur_ptr, W), device=dev)
         got = torch.empty_like(cur)
         dist.all_to_all_single(got, cur, group=self.group)  # also: the writers' kernels have completed
-        part = torch.arange(n_sub, dtype=torch.int64, device=dev)
-        fill = (got.view(W, n_sub) - (self.rank * n_sub + part) * cap).clamp_(max=cap)
-        ends = (torch.arange(W, dtype=torch.int64, device=dev)[:, None] * n_sub + part[None, :]) * cap + fill
-        self.gir.mg_insert_buckets(ends.contiguous(), gmax)
+        fill = (got - self.rank * cap).clamp_(max=cap)
+        ends = torch.arange(W, dtype=torch.int64, device=dev) * cap + fill
+        self.gir.mg_insert_buckets(ends, int(fill.sum().item()))
         self._keep = (ends, got)
         self.exchanged_bytes += int(ub * 8 * self.words * (W - 1) / W)
         # keys that did not fit their bucket (skew): routed the slow way

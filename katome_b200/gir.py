@@ -295,18 +295,13 @@ class GpuGIR:
                                                    int(total_bases), arr, C.byref(cur)))
         return int(cur.value)
 
-    def mg_insert_buckets(self, d_bucket_ends, n_keys_estimate: int):
-        _check(self._L.ktg_mg_insert_buckets(self._h, _ptr(d_bucket_ends), int(n_keys_estimate)))
+    def mg_insert_buckets(self, d_bucket_ends, n_keys: int):
+        _check(self._L.ktg_mg_insert_buckets(self._h, _ptr(d_bucket_ends), int(n_keys)))
 
     def mg_sketch(self):
         p, n = C.c_void_p(), C.c_uint32()
         _check(self._L.ktg_mg_sketch(self._h, C.byref(p), C.byref(n)))
         return int(p.value), int(n.value)
-
-    def mg_plan_growth(self) -> bool:
-        g = C.c_int(0)
-        _check(self._L.ktg_mg_plan_growth(self._h, C.byref(g)))
-        return bool(g.value)
 
     def mg_spill(self):
         p, n = C.c_void_p(), C.c_uint64()

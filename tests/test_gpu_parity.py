@@ -361,27 +361,21 @@ def _fused_exchange_emulated(K, gs, batches, k):
     one GPU: peers' receive buffers are plain device pointers, collectives are torch ops."""
     W = len(gs)
     gmax = max(max(nb - n * (k - 1), 0) for (_, _, n, nb) in batches)
-    while True:
-        prep = [g.mg_prepare(gmax) for g in gs]
-        peers = [p[0] for p in prep]
-        cap, n_sub = prep[0][2], prep[0][3]
-        assert all(p[2] == cap and p[3] == n_sub for p in prep)
-        curs = [torch.as_tensor(K.DeviceArray(g.mg_scatter_reads_device(d, o, n, nb, peers), W * n_sub), device="cuda")
-                for g, (d, o, n, nb) in zip(gs, batches)]
-        regs = [torch.as_tensor(K.DeviceArray(*g.mg_sketch(), "<i4"), device="cuda") for g in gs]
-        m = torch.stack(regs).max(dim=0).values
-        for r in regs:
-            r.copy_(m)
-        grew = [g.mg_plan_growth() for g in gs]
-        assert len(set(grew)) == 1  # every rank reaches the same decision
-        if not grew[0]:
-            break
-    part = torch.arange(n_sub, dtype=torch.int64, device="cuda")
+    prep = [g.mg_prepare(gmax) for g in gs]
+    peers = [p[0] for p in prep]
+    cap = prep[0][2]
+    assert all(p[2] == cap for p in prep)
+    curs = [torch.as_tensor(K.DeviceArray(g.mg_scatter_reads_device(d, o, n, nb, peers), W), device="cuda")
+            for g, (d, o, n, nb) in zip(gs, batches)]
+    regs = [torch.as_tensor(K.DeviceArray(*g.mg_sketch(), "<i4"), device="cuda") for g in gs]
+    m = torch.stack(regs).max(dim=0).values
+    for r in regs:
+        r.copy_(m)
     for r, g in enumerate(gs):
-        got = torch.stack([c.view(W, n_sub)[r] for c in curs])  # what the all-to-all delivers to rank r
-        fill = (got - (r * n_sub + part) * cap).clamp_(max=cap)
-        ends = (torch.arange(W, dtype=torch.int64, device="cuda")[:, None] * n_sub + part[None, :]) * cap + fill
-        g.mg_insert_buckets(ends.contiguous(), gmax)
+        got = torch.stack([c[r] for c in curs])  # what the all-to-all delivers to rank r
+        fill = (got - r * cap).clamp_(max=cap)
+        ends = torch.arange(W, dtype=torch.int64, device="cuda") * cap + fill
+        g.mg_insert_buckets(ends, int(fill.sum().item()))
         torch.cuda.synchronize()
     words = gs[0].key_words()
     routed = [[] for _ in range(W)]
