@@ -17,6 +17,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+_OUT = sys.stdout
 METRIC = "kmers_inserted_per_sec"
 UNIT = "k-mers/s"
 
@@ -70,7 +71,8 @@ def run_reference(args):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "reads_per_sec": v / wl.windows_per_read,
     }
-    print(json.dumps(line))
+    _OUT.write(json.dumps(line) + "\n")
+    _OUT.flush()
 
 
 # --------------------------------------------------------------------------- clocks
@@ -296,12 +298,19 @@ def run_ours(args):
         n_upd = 1 << 28
         line["random_access"] = {
             f"{mb}MB": n_upd / (random_access_probe(mb << 20, n_upd, 16) * 1e-3) for mb in (16, 64, 256, 2048)}
-    print(json.dumps(line))
+    _OUT.write(json.dumps(line) + "\n")
+    _OUT.flush()
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
+    # Libraries (NCCL prints its version) write to the C-level stdout; the contract is ONE JSON
+    # line there, so everything else goes to stderr and the line is written to the saved fd.
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

@@ -726,12 +726,27 @@ template <class K> struct Builder : BuilderBase {
         o.spill_cap = spill_cap;
         const uint64_t tiles_per_bin = cap1 / L2S_TILE, n_tiles = tiles_per_bin * n_bins;
         const size_t ss = ScatterSmem<K, L2S_TILE>::bytes(tab.pages_per_sub(), false);
-        int g = (int)std::min<uint64_t>(grid_for(scatter_buckets_kernel<K, 2>, L2S_THREADS, ss, props), n_tiles);
+        int variant = 0;
+        if (const char *e = getenv("KTG_L2S_VARIANT")) variant = atoi(e); // tuning knob
         prof.begin("scatter_pages", n_keys, stream);
-        scatter_buckets_kernel<K, 2><<<g, L2S_THREADS, ss, stream>>>(keys1, fill1, cap1, tiles_per_bin, n_tiles, sub_mod, tab, o);
+        auto launch_v = [&](auto kern, int threads, int per) {
+            const uint64_t tile = (uint64_t)threads * per, tpb = cap1 / tile, nt = tpb * n_bins;
+            const size_t sb = (size_t)tile * (sizeof(K) + 4) + (size_t)tab.pages_per_sub() * 32;
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);
+            int gg = (int)std::min<uint64_t>(grid_for(kern, threads, sb, props), nt);
+            kern<<<gg, threads, sb, stream>>>(keys1, fill1, cap1, tpb, nt, sub_mod, tab, o);
+        };
+        if (variant == 1) launch_v(scatter_buckets_kernel<K, 2, 256, 8, 4>, 256, 8);
+        else if (variant == 2) launch_v(scatter_buckets_kernel<K, 2, 512, 4, 3>, 512, 4);
+        else if (variant == 3) launch_v(scatter_buckets_kernel<K, 2, 1024, 4, 2>, 1024, 4);
+        else if (variant == 4) launch_v(scatter_buckets_kernel<K, 2, 256, 16, 2>, 256, 16);
+        else {
+            int g = (int)std::min<uint64_t>(grid_for(scatter_buckets_kernel<K, 2>, L2S_THREADS, ss, props), n_tiles);
+            scatter_buckets_kernel<K, 2><<<g, L2S_THREADS, ss, stream>>>(keys1, fill1, cap1, tiles_per_bin, n_tiles, sub_mod, tab, o);
+        }
         prof.end(stream);
         const size_t ps = page_smem_bytes(tab.page_log2);
-        g = (int)std::min<uint64_t>(grid_for(update_pages_kernel<K>, PAGE_THREADS, ps, props), n_pages);
+        int g = (int)std::min<uint64_t>(grid_for(update_pages_kernel<K>, PAGE_THREADS, ps, props), n_pages);
         prof.begin("update_pages", n_keys, stream);
         update_pages_kernel<K><<<g, PAGE_THREADS, ps, stream>>>((const K *)b_pkeys.p, cur2, cap2, k, rc && (k % 2 == 0), tab, fresh);
         prof.end(stream);

@@ -501,6 +501,28 @@ __global__ void scan_bins_kernel(const unsigned long long *__restrict__ hist, ui
 // The same routine serves both partition levels: level 1 bins by sub-table (or
 // owner rank), level 2 bins the keys of one sub-table by page.
 // Output positions must fit 32 bits (the host splits larger batches).
+// Per-phase cycle counters of the tile scatter (debug builds with -DKTG_PHASE_TIMERS only).
+#ifdef KTG_PHASE_TIMERS
+__device__ unsigned long long g_phase_cycles[8];
+#define KTG_PHASE(i)                                                                  \
+    do {                                                                              \
+        if (threadIdx.x == 0) {                                                       \
+            long long now_ = clock64();                                               \
+            atomicAdd(&g_phase_cycles[i], (unsigned long long)(now_ - phase_t0_));    \
+            phase_t0_ = now_;                                                         \
+        }                                                                             \
+    } while (0)
+#define KTG_PHASE_BEGIN() long long phase_t0_ = clock64()
+#define KTG_PHASE_RESET()                                                             \
+    do {                                                                              \
+        if (threadIdx.x == 0) phase_t0_ = clock64();                                  \
+    } while (0)
+#else
+#define KTG_PHASE(i)
+#define KTG_PHASE_BEGIN()
+#define KTG_PHASE_RESET()
+#endif
+
 template <class K, int TILE> struct ScatterSmem {
     K *keys;                   // TILE
     uint32_t *delta;           // TILE: output position minus position in the sorted tile
@@ -554,17 +576,30 @@ __device__ __forceinline__ void tile_scatter(const K (&key)[PER], const uint32_t
     __shared__ uint32_t s_total, s_ovf;
     uint32_t *cnt = sm.cnt + parity * n_bins;
     uint32_t rank[PER];
+    KTG_PHASE_BEGIN();
 #pragma unroll
     for (int j = 0; j < PER; ++j)
         if (j < nvalid) rank[j] = atomicAdd(&cnt[bin[j]], 1u);
     if (threadIdx.x == 0) s_ovf = 0;
     __syncthreads();
-    // block-wide exclusive scan of the bin counts; reserve HBM ranges
+    KTG_PHASE(1);
+    // block-wide exclusive scan of the bin counts; reserve HBM ranges.  The global atomicAdd
+    // that reserves a bin's range is issued BEFORE the scan so that its round trip to L2
+    // (~1 us, the longest single latency of a tile) overlaps the scan's barriers.
     {
         const uint32_t per = (n_bins + THREADS - 1) / THREADS;
         const uint32_t b0 = threadIdx.x * per;
-        uint32_t s = 0;
-        for (uint32_t i = b0; i < b0 + per && i < n_bins; ++i) s += cnt[i];
+        const bool one = per == 1; // the usual case: at most one bin per thread
+        uint32_t s = 0, c1 = 0;
+        unsigned long long base1 = 0;
+        if (one) {
+            if (b0 < n_bins) c1 = cnt[b0];
+            if (c1) base1 = atomicAdd(&cursors[b0], (unsigned long long)c1);
+            s = c1;
+        }
+        else {
+            for (uint32_t i = b0; i < b0 + per && i < n_bins; ++i) s += cnt[i];
+        }
         uint32_t incl = s;
         for (int d = 1; d < 32; d <<= 1) {
             uint32_t x = __shfl_up_sync(0xFFFFFFFFu, incl, d);
@@ -584,10 +619,10 @@ __device__ __forceinline__ void tile_scatter(const K (&key)[PER], const uint32_t
         __syncthreads();
         uint32_t run = s_warp[threadIdx.x >> 5] + incl - s;
         for (uint32_t i = b0; i < b0 + per && i < n_bins; ++i) {
-            const uint32_t c = cnt[i];
-            unsigned long long base = 0;
+            const uint32_t c = one ? c1 : cnt[i];
+            unsigned long long base = base1;
             if (c) {
-                base = atomicAdd(&cursors[i], (unsigned long long)c);
+                if (!one) base = atomicAdd(&cursors[i], (unsigned long long)c);
                 sm.glob[i] = base;
                 if (o.bucket_cap) {
                     const unsigned long long lim = (bin_off + i + 1) * o.bucket_cap;
@@ -603,6 +638,7 @@ __device__ __forceinline__ void tile_scatter(const K (&key)[PER], const uint32_t
         }
     }
     __syncthreads();
+    KTG_PHASE(2);
 #pragma unroll
     for (int j = 0; j < PER; ++j)
         if (j < nvalid) {
@@ -616,6 +652,7 @@ __device__ __forceinline__ void tile_scatter(const K (&key)[PER], const uint32_t
         for (uint32_t i = threadIdx.x; i < n_bins; i += THREADS) nxt[i] = 0;
     }
     __syncthreads();
+    KTG_PHASE(3);
     const uint32_t total = s_total;
     K *out = (K *)o.out;
     if (!s_ovf && po) { // bins are owner-major: one contiguous range of the sorted tile per destination GPU
@@ -650,6 +687,7 @@ __device__ __forceinline__ void tile_scatter(const K (&key)[PER], const uint32_t
         }
     }
     __syncthreads();
+    KTG_PHASE(4);
 }
 
 constexpr int SCATTER_THREADS = 256, SCATTER_PER = 8, SCATTER_TILE = SCATTER_THREADS * SCATTER_PER;
@@ -754,12 +792,13 @@ __global__ void init_cursors_kernel(unsigned long long *cursors, uint64_t n, uin
 // LEVEL 2: bucket q holds keys of sub-table q (or q % sub_mod); they are grouped by page.
 // LEVEL 1: bucket q holds keys of this shard in no particular order (what source rank q sent
 //          in the fused multi-GPU exchange); they are grouped by sub-table.
-template <class K, int LEVEL>
-__global__ void __launch_bounds__(L2S_THREADS, 2)
+template <class K, int LEVEL, int L2S_THREADS = ktg::L2S_THREADS, int L2S_PER = ktg::L2S_PER, int MINB = 2>
+__global__ void __launch_bounds__(L2S_THREADS, MINB)
 scatter_buckets_kernel(const K *__restrict__ keys1, const unsigned long long *__restrict__ fill1,
                        uint64_t cap1, uint64_t tiles_per_bin, uint64_t n_tiles, uint32_t sub_mod,
                        Table<K> t, ScatterOut o) {
     extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int L2S_TILE = L2S_THREADS * L2S_PER;
     const uint32_t n2 = LEVEL == 2 ? t.pages_per_sub() : t.n_sub;
     ScatterSmem<K, L2S_TILE> sm;
     sm.carve(smem, n2);
@@ -776,6 +815,7 @@ scatter_buckets_kernel(const K *__restrict__ keys1, const unsigned long long *__
         K key[L2S_PER];
         uint32_t bin[L2S_PER];
         int nvalid = 0;
+        KTG_PHASE_BEGIN();
 #pragma unroll
         for (int j = 0; j < L2S_PER; ++j) {
             const uint64_t i = base + (uint64_t)j * L2S_THREADS + threadIdx.x;
@@ -785,6 +825,10 @@ scatter_buckets_kernel(const K *__restrict__ keys1, const unsigned long long *__
             else bin[j] = place_of(KeyTraits<K>::hash(key[j]), t.world, t.n_sub).part;
             if (in) nvalid = j + 1;
         }
+#ifdef KTG_PHASE_TIMERS
+        if (threadIdx.x == 0 && key[L2S_PER - 1] == (K)12345) g_phase_cycles[7] = 1; // wait for the loads
+#endif
+        KTG_PHASE(0);
         tile_scatter<K, L2S_THREADS, L2S_PER>(key, bin, nvalid, sm, n2, o.cursors + b * n2, b * n2, o, parity);
         parity ^= 1u;
     }

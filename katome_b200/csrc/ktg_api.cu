@@ -429,6 +429,15 @@ int ktg_random_access_probe(uint64_t bytes, uint64_t n_updates, uint32_t slot_by
 int ktg_get_profile(ktg_builder *b, ktg_kernel_profile *out, uint32_t cap, uint32_t *n) {
     KTG_ENTER(b);
     KTG_CUDA(cudaStreamSynchronize(b->impl->stream));
+#ifdef KTG_PHASE_TIMERS
+    {
+        unsigned long long h[8];
+        cudaMemcpyFromSymbol(h, g_phase_cycles, sizeof h);
+        fprintf(stderr, "[ktg phases] load %llu rank %llu scan %llu place %llu copy %llu\n", h[0], h[1], h[2], h[3], h[4]);
+        memset(h, 0, sizeof h);
+        cudaMemcpyToSymbol(g_phase_cycles, h, sizeof h);
+    }
+#endif
     b->impl->prof.resolve();
     const auto &es = b->impl->prof.entries;
     if (n) *n = (uint32_t)es.size();
