@@ -86,8 +86,9 @@ int ktg_add_reads(ktg_builder *b, const uint8_t *bases, const uint64_t *offsets,
                   uint64_t *accepted_reads, uint64_t *accepted_bytes);
 
 /* Same, inputs already resident in device memory (d_offsets: n_reads+1 u64).
- * total_bases == offsets[n_reads].  d_bases must be readable up to the next
- * 16-byte boundary past its end. */
+ * total_bases == offsets[n_reads] - offsets[0].  The packer reads whole aligned 32-byte
+ * chunks: d_bases must be readable from the 32-byte boundary at or below its first base to
+ * the one at or above its end (true for any sub-range of a cudaMalloc allocation). */
 int ktg_add_reads_device(ktg_builder *b, const void *d_bases, const void *d_offsets,
                          uint64_t n_reads, uint64_t total_bases, uint64_t *accepted_reads,
                          uint64_t *accepted_bytes);

@@ -235,7 +235,7 @@ template <class K> struct Builder : BuilderBase {
     bool sketch_complete = true; // the sketch covers every key inserted since hll_base
     DeviceBuf b_hll;
     DeviceBuf b_spill;
-    DeviceBuf b_packed, b_nstart, b_keys, b_keys2, b_hist, b_ovf_keys, b_ovf_inc, b_small;
+    DeviceBuf b_packed, b_keys, b_keys2, b_hist, b_ovf_keys, b_ovf_inc, b_small;
     DeviceBuf b_pkeys, b_pcur, b_pspill; // level-2 (page) buckets, their cursors, their spill list
     PackCounters *d_ctr = nullptr;        // accumulates over the whole build
     unsigned long long *d_ovf_count = nullptr;
@@ -250,7 +250,7 @@ template <class K> struct Builder : BuilderBase {
         cudaSetDevice(device);
         if (stream) cudaStreamSynchronize(stream);
         if (tab.slots) cudaFree(tab.slots);
-        b_packed.release(); b_nstart.release(); b_keys.release(); b_keys2.release();
+        b_packed.release(); b_bad.release(); b_valid.release(); b_wstart.release(); b_keys.release(); b_keys2.release();
         b_hist.release(); b_hll.release(); b_spill.release(); b_ovf_keys.release(); b_ovf_inc.release(); b_small.release();
         b_pkeys.release(); b_pcur.release(); b_pspill.release(); b_stage_cur.release();
         b_rx.release(); b_mg_cur.release(); b_mg_spill.release();
@@ -541,35 +541,36 @@ template <class K> struct Builder : BuilderBase {
     // Packs the batch and returns what the extraction kernels need to know about it:
     // the exact number of windows and whether all reads share one length.
     struct Batch {
-        uint64_t n_words = 0, windows = 0;
-        ItemMap im{};
+        uint64_t windows = 0;
+        ReadView v{};
     };
     uint64_t windows_seen = 0; // cumulative PackCounters::windows already accounted for
+    DeviceBuf b_bad, b_valid, b_wstart;
 
     int pack(const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t n_reads,
              uint64_t total_bases, Batch *bt) {
-        uint64_t nw = total_bases / 32 + n_reads;
-        KTG_TRY(b_packed.ensure((nw + 4) * 8));
-        KTG_TRY(b_nstart.ensure(nw + 4));
-        bt->n_words = nw;
+        const uint64_t nw_max = (total_bases + 31 + 31) / 32 + 1; // whatever the alignment of the first base
+        KTG_TRY(b_packed.ensure((nw_max + 4) * 8));
+        KTG_TRY(b_bad.ensure(nw_max * 4));
+        KTG_TRY(b_valid.ensure(n_reads + 1));
         // per-batch min/max read length
         KTG_CUDA(cudaMemsetAsync(&d_ctr->min_len, 0xFF, 8, stream));
         KTG_CUDA(cudaMemsetAsync(&d_ctr->max_len, 0, 8, stream));
-        const uint64_t mean_len = total_bases / n_reads;
-        const int group = mean_len <= 128 ? 4 : (mean_len <= 256 ? 8 : 32);
-        auto launch = [&](auto kernel, int G) {
-            int grid = grid_for(kernel, 256, 0, props);
-            uint64_t want = (n_reads * G + 255) / 256;
-            if ((uint64_t)grid > want) grid = (int)want;
-            kernel<<<grid, 256, 0, stream>>>(d_bases, d_offsets, n_reads, k, (uint64_t *)b_packed.p,
-                                             (uint8_t *)b_nstart.p, d_ctr);
-        };
         prof.begin("pack_reads", total_bases, stream);
-        if (group == 4) launch(pack_reads_kernel<4>, 4);
-        else if (group == 8) launch(pack_reads_kernel<8>, 8);
-        else launch(pack_reads_kernel<32>, 32);
+        {
+            int grid = (int)std::min<uint64_t>((nw_max + 255) / 256, (uint64_t)props.sms * 16);
+            pack_flat_kernel<<<grid, 256, 0, stream>>>(d_bases, d_offsets, total_bases, (uint64_t *)b_packed.p,
+                                                       (uint32_t *)b_bad.p, d_ctr);
+        }
         prof.end(stream);
         if (input_consumed) KTG_CUDA(cudaEventRecord(input_consumed, stream));
+        prof.begin("check_reads", n_reads, stream);
+        {
+            int grid = (int)std::min<uint64_t>((n_reads + 255) / 256, (uint64_t)props.sms * 16);
+            check_reads_kernel<<<grid, 256, 0, stream>>>(d_offsets, n_reads, d_bases, k, (const uint32_t *)b_bad.p,
+                                                         (uint8_t *)b_valid.p, d_ctr);
+        }
+        prof.end(stream);
         nodes_valid = false;
         PackCounters c;
         KTG_CUDA(cudaMemcpyAsync(&c, d_ctr, sizeof c, cudaMemcpyDeviceToHost, stream));
@@ -580,11 +581,29 @@ template <class K> struct Builder : BuilderBase {
             deferred_error = KTG_ERR_SHORT_READ;
             return fail(KTG_ERR_SHORT_READ, "Read is too short!");
         }
-        bt->im = ItemMap{0, 0, nw * ITEMS_PER_WORD};
+        ReadView &v = bt->v;
+        v.packed = (const uint64_t *)b_packed.p;
+        v.valid = (const uint8_t *)b_valid.p;
+        v.wstart = nullptr;
+        v.shift0 = (uint32_t)c.shift0;
+        v.n_words = (total_bases + v.shift0 + 31) / 32;
         if (c.min_len == c.max_len) { // every read has the same length: closed-form item map
             const uint32_t L = (uint32_t)c.max_len;
-            const uint32_t ipr = L >= k ? (L - k + 1 + GRAN - 1) / GRAN : 0;
-            bt->im = ItemMap{L, ipr, n_reads * ipr};
+            v.ulen = L;
+            v.ipr = L >= k ? (L - k + 1 + GRAN - 1) / GRAN : 0;
+            v.n_items = n_reads * v.ipr;
+        }
+        else if (bt->windows) { // ragged: mark the window starts, items are (word, granule) pairs
+            KTG_TRY(b_wstart.ensure(nw_max * 4));
+            KTG_CUDA(cudaMemsetAsync(b_wstart.p, 0, v.n_words * 4, stream));
+            prof.begin("mark_starts", n_reads, stream);
+            int grid = (int)std::min<uint64_t>((n_reads + 255) / 256, (uint64_t)props.sms * 16);
+            mark_starts_kernel<<<grid, 256, 0, stream>>>(d_offsets, n_reads, d_bases, k, (const uint8_t *)b_valid.p,
+                                                         (uint32_t *)b_wstart.p);
+            prof.end(stream);
+            v.wstart = (const uint32_t *)b_wstart.p;
+            v.ulen = v.ipr = 0;
+            v.n_items = v.n_words * ITEMS_PER_WORD;
         }
         return KTG_OK;
     }
@@ -622,17 +641,15 @@ template <class K> struct Builder : BuilderBase {
     template <bool BY_OWNER> int hist_reads_pass(const Batch &bt, uint32_t n_bins) {
         KTG_TRY(ensure_hist(n_bins));
         KTG_CUDA(cudaMemsetAsync(b_hist.p, 0, n_bins * 8, stream));
-        const uint64_t *packed = (const uint64_t *)b_packed.p;
-        const uint8_t *nstart = (const uint8_t *)b_nstart.p;
         size_t hs = (size_t)n_bins * 4;
         prof.begin("hist_reads", bt.windows, stream);
         if (rc) {
             int g = grid_for(hist_reads_kernel<K, true, BY_OWNER, false>, 256, hs, props);
-            hist_reads_kernel<K, true, BY_OWNER, false><<<g, 256, hs, stream>>>(packed, nstart, bt.n_words, k, bt.im, tab, n_bins, hist_ptr(), nullptr);
+            hist_reads_kernel<K, true, BY_OWNER, false><<<g, 256, hs, stream>>>(bt.v, k, tab, n_bins, hist_ptr(), nullptr);
         }
         else {
             int g = grid_for(hist_reads_kernel<K, false, BY_OWNER, false>, 256, hs, props);
-            hist_reads_kernel<K, false, BY_OWNER, false><<<g, 256, hs, stream>>>(packed, nstart, bt.n_words, k, bt.im, tab, n_bins, hist_ptr(), nullptr);
+            hist_reads_kernel<K, false, BY_OWNER, false><<<g, 256, hs, stream>>>(bt.v, k, tab, n_bins, hist_ptr(), nullptr);
         }
         prof.end(stream);
         return KTG_OK;
@@ -651,20 +668,18 @@ template <class K> struct Builder : BuilderBase {
 
     template <int BINS, bool HLL>
     int scatter_reads_pass(const Batch &bt, uint32_t n_bins, const ScatterOut &o, const PeerOut *po = nullptr) {
-        const uint64_t *packed = (const uint64_t *)b_packed.p;
-        const uint8_t *nstart = (const uint8_t *)b_nstart.p;
         size_t ss = ScatterSmem<K, SCATTER_TILE>::bytes(n_bins, HLL);
-        uint64_t n_tiles = std::max<uint64_t>(1, (bt.im.n_items + SCATTER_THREADS - 1) / SCATTER_THREADS);
+        uint64_t n_tiles = std::max<uint64_t>(1, (bt.v.n_items + SCATTER_THREADS - 1) / SCATTER_THREADS);
         PeerOut peers{};
         if (po) peers = *po;
         prof.begin(po ? "scatter_reads_p2p" : "scatter_reads", bt.windows, stream);
         if (rc) {
             int g = (int)std::min<uint64_t>(grid_for(scatter_reads_kernel<K, true, BINS, HLL>, SCATTER_THREADS, ss, props), n_tiles);
-            scatter_reads_kernel<K, true, BINS, HLL><<<g, SCATTER_THREADS, ss, stream>>>(packed, nstart, bt.n_words, k, bt.im, tab, n_bins, o, (uint32_t *)b_hll.p, peers);
+            scatter_reads_kernel<K, true, BINS, HLL><<<g, SCATTER_THREADS, ss, stream>>>(bt.v, k, tab, n_bins, o, (uint32_t *)b_hll.p, peers);
         }
         else {
             int g = (int)std::min<uint64_t>(grid_for(scatter_reads_kernel<K, false, BINS, HLL>, SCATTER_THREADS, ss, props), n_tiles);
-            scatter_reads_kernel<K, false, BINS, HLL><<<g, SCATTER_THREADS, ss, stream>>>(packed, nstart, bt.n_words, k, bt.im, tab, n_bins, o, (uint32_t *)b_hll.p, peers);
+            scatter_reads_kernel<K, false, BINS, HLL><<<g, SCATTER_THREADS, ss, stream>>>(bt.v, k, tab, n_bins, o, (uint32_t *)b_hll.p, peers);
         }
         prof.end(stream);
         return KTG_OK;
@@ -886,13 +901,11 @@ template <class K> struct Builder : BuilderBase {
         trace("ingest", n_reads);
         KTG_TRY(pack(d_bases, d_offsets, n_reads, total_bases, &bt));
         if (bt.windows == 0) return KTG_OK;
-        const uint64_t *packed = (const uint64_t *)b_packed.p;
-        const uint8_t *nstart = (const uint8_t *)b_nstart.p;
         if (!use_partition()) {
             KTG_TRY(reserve(bt.windows, [&]() -> int {
                 prof.begin("hll_reads", bt.windows, stream);
-                if (rc) hll_reads_kernel<K, true><<<props.sms * 4, 256, 0, stream>>>(packed, nstart, bt.n_words, k, bt.im, (uint32_t *)b_hll.p);
-                else hll_reads_kernel<K, false><<<props.sms * 4, 256, 0, stream>>>(packed, nstart, bt.n_words, k, bt.im, (uint32_t *)b_hll.p);
+                if (rc) hll_reads_kernel<K, true><<<props.sms * 4, 256, 0, stream>>>(bt.v, k, (uint32_t *)b_hll.p);
+                else hll_reads_kernel<K, false><<<props.sms * 4, 256, 0, stream>>>(bt.v, k, (uint32_t *)b_hll.p);
                 prof.end(stream);
                 return KTG_OK;
             }));
@@ -902,13 +915,13 @@ template <class K> struct Builder : BuilderBase {
             prof.begin("extract_insert", bt.windows, stream);
             if (rc) {
                 int g = grid_for(extract_insert_kernel<K, true>, 256, 0, props);
-                g = (int)std::min<uint64_t>(g, (bt.n_words + 255) / 256);
-                extract_insert_kernel<K, true><<<g, 256, 0, stream>>>(packed, nstart, bt.n_words, k, tab);
+                g = (int)std::min<uint64_t>(g, (bt.v.n_items + 255) / 256);
+                extract_insert_kernel<K, true><<<g, 256, 0, stream>>>(bt.v, k, tab);
             }
             else {
                 int g = grid_for(extract_insert_kernel<K, false>, 256, 0, props);
-                g = (int)std::min<uint64_t>(g, (bt.n_words + 255) / 256);
-                extract_insert_kernel<K, false><<<g, 256, 0, stream>>>(packed, nstart, bt.n_words, k, tab);
+                g = (int)std::min<uint64_t>(g, (bt.v.n_items + 255) / 256);
+                extract_insert_kernel<K, false><<<g, 256, 0, stream>>>(bt.v, k, tab);
             }
             prof.end(stream);
         }

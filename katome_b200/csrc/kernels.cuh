@@ -47,101 +47,86 @@ __device__ __forceinline__ void block_accumulate(const uint64_t (&v)[N], unsigne
 // create_fastq (algorithms/builder.rs:155-158), plus the length assert of
 // add_read_fastaq (collections/girs/hm_gir.rs:40).
 //
-// Layout: read r owns packed words [wo(r), wo(r+1)), wo(r) = (off[r]-off[0])/32 + r
-// (no prefix sum needed; <= 1 spare word per read).  Word j of a read holds
-// bases 32j..32j+31, first base in bits 63:62.  nstart[w] = number of k-mer
-// windows that START in word w (0 for rejected reads and spare words), which
-// is all the extraction kernels need to know about read boundaries.
+// Layout: the batch is ONE flat 2-bit stream.  Word w holds the bases at byte
+// positions [32w, 32w+32) counted from the 32-byte aligned address at or below the
+// first read, first base in bits 63:62 (the MSB-first order of compress_node).  A
+// second stream has one bit per byte: "not one of A C G T".  Packing is therefore a
+// pure streaming kernel over aligned 32-byte chunks, with no per-read control flow;
+// read boundaries only matter to check_reads_kernel (validity, counters) and to the
+// extraction kernels, which address the stream at 2-bit granularity.
 struct PackCounters {
     unsigned long long accepted_reads, accepted_bytes, windows, short_reads;
-    unsigned long long min_len, max_len; // over ALL reads of the build (valid or not)
+    unsigned long long min_len, max_len; // over ALL reads of the batch (valid or not)
+    unsigned long long shift0;           // flat position of the batch's first base (0..31)
 };
 
-// four ASCII bases (little endian: first base in the low byte) -> 8 bits, MSB first
-__device__ __forceinline__ uint32_t pack4(uint32_t x, bool &ok) {
+// four ASCII bases (little endian: first base in the low byte) -> 8 bits, MSB first;
+// bad: bit q set iff byte q is not one of "ACGT"
+__device__ __forceinline__ uint32_t pack4(uint32_t x, uint32_t &bad) {
     uint32_t c = ((x >> 1) & 0x03030303u) ^ ((x >> 2) & 0x01010101u);
     uint32_t sel = (c & 0xFu) | ((c >> 4) & 0xF0u) | ((c >> 8) & 0xF00u) | ((c >> 12) & 0xF000u);
-    ok = ok && (__byte_perm(0x54474341u, 0u, sel) == x); // "ACGT" looked up by code == input
+    uint32_t d = __byte_perm(0x54474341u, 0u, sel) ^ x; // "ACGT" looked up by code, against the input
+    uint32_t nz = (((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) & 0x80808080u; // 0x80 in every non-zero byte
+    bad = (((nz >> 7) * 0x00204081u) >> 21) & 0xFu; // bits 0, 8, 16, 24 gathered into a nibble
     return (c * 0x40100401u) >> 24;
 }
 
-// 32 bases starting at an arbitrary byte address -> one packed word.
-// Three aligned 16-byte loads cover the span; only blocks that hold a byte of
-// [p, p+cnt) are touched.  The byte offset inside the first block is removed
-// with selects (whole words) and funnel shifts (bytes), all on 32-bit registers.
-__device__ __forceinline__ uint64_t pack32_unaligned(const uint8_t *p, int cnt, bool &ok) {
-    const uint4 *a = (const uint4 *)((uintptr_t)p & ~(uintptr_t)15);
-    const uint32_t sh = (uint32_t)((uintptr_t)p & 15);
-    const int span = (int)sh + cnt; // bytes needed counted from a
-    const uint4 z = make_uint4(0, 0, 0, 0);
-    uint4 v0 = __ldg(a);
-    uint4 v1 = span > 16 ? __ldg(a + 1) : z;
-    uint4 v2 = span > 32 ? __ldg(a + 2) : z;
-    uint32_t x[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
-    if (sh & 8) {
+__global__ void __launch_bounds__(256)
+pack_flat_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restrict__ offsets,
+                 uint64_t total_bases, uint64_t *__restrict__ packed, uint32_t *__restrict__ bad,
+                 PackCounters *ctr) {
+    const uintptr_t first = (uintptr_t)(bases + offsets[0]);
+    const uint4 *src = (const uint4 *)(first & ~(uintptr_t)31);
+    const uint32_t shift0 = (uint32_t)(first & 31);
+    const uint64_t n_words = (total_bases + shift0 + 31) / 32;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctr->shift0 = shift0;
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) {
+        const uint4 v0 = __ldcs(src + 2 * w), v1 = __ldcs(src + 2 * w + 1);
+        const uint32_t x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        uint32_t hi = 0, lo = 0, bm = 0;
 #pragma unroll
-        for (int i = 0; i < 10; ++i) x[i] = x[i + 2];
-    }
-    if (sh & 4) {
-#pragma unroll
-        for (int i = 0; i < 9; ++i) x[i] = x[i + 1];
-    }
-    const uint32_t bs = 8 * (sh & 3);
-    uint32_t y[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) y[i] = __funnelshift_r(x[i], x[i + 1], bs);
-    if (cnt < 32) { // tail word of a read: bases past the end count as 'A', unchecked
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            int nv = cnt - 4 * q;
-            if (nv < 4) {
-                uint32_t m = nv <= 0 ? 0u : ((1u << (8 * nv)) - 1u);
-                y[q] = (y[q] & m) | (0x41414141u & ~m);
-            }
+        for (int q = 0; q < 4; ++q) {
+            uint32_t b0, b1;
+            hi = (hi << 8) | pack4(x[q], b0);
+            lo = (lo << 8) | pack4(x[q + 4], b1);
+            bm |= (b0 << (4 * q)) | (b1 << (4 * q + 16));
         }
+        packed[w] = ((uint64_t)hi << 32) | lo;
+        bad[w] = bm;
     }
-    uint32_t hi = 0, lo = 0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        hi = (hi << 8) | pack4(y[q], ok);
-        lo = (lo << 8) | pack4(y[q + 4], ok);
-    }
-    return ((uint64_t)hi << 32) | lo;
 }
 
-// GROUP lanes cooperate on one read (32 * GROUP bases per iteration); the host
-// picks GROUP from the mean read length so that short reads keep all lanes busy.
-template <int GROUP>
+// One thread per read: accept / reject (any bad byte rejects the whole read), counters, and
+// valid[r] = 1 iff the read contributes windows (accepted and len >= k).
 __global__ void __launch_bounds__(256)
-pack_reads_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restrict__ offsets,
-                  uint64_t n_reads, uint32_t k, uint64_t *__restrict__ packed,
-                  uint8_t *__restrict__ nstart, PackCounters *ctr) {
-    const int lane = threadIdx.x & 31, gl = lane & (GROUP - 1);
-    const unsigned gmask = GROUP == 32 ? 0xFFFFFFFFu : (((1u << (GROUP & 31)) - 1u) << (lane & ~(GROUP - 1)));
-    const uint64_t n_groups = (uint64_t)gridDim.x * blockDim.x / GROUP;
+check_reads_kernel(const uint64_t *__restrict__ offsets, uint64_t n_reads,
+                   const uint8_t *__restrict__ bases, uint32_t k, const uint32_t *__restrict__ bad,
+                   uint8_t *__restrict__ valid, PackCounters *ctr) {
     const uint64_t off0 = offsets[0];
+    const uint32_t shift0 = (uint32_t)((uintptr_t)(bases + off0) & 31);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     uint64_t acc[4] = {0, 0, 0, 0};
     uint64_t lmin = ~0ull, lmax = 0;
-    for (uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / GROUP; r < n_reads;
-         r += n_groups) {
-        const uint64_t o0 = offsets[r], o1 = offsets[r + 1];
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += stride) {
+        const uint64_t o0 = offsets[r] - off0 + shift0, o1 = offsets[r + 1] - off0 + shift0;
         const uint64_t len = o1 - o0;
         lmin = len < lmin ? len : lmin;
         lmax = len > lmax ? len : lmax;
-        const uint64_t wbase = (o0 - off0) / 32 + r, wend = (o1 - off0) / 32 + r + 1;
-        const uint64_t nwords = (len + 31) / 32;
-        bool ok = true;
-        for (uint64_t j = gl; j < nwords; j += GROUP) {
-            uint64_t rem = len - 32 * j;
-            packed[wbase + j] = pack32_unaligned(bases + o0 + 32 * j, rem < 32 ? (int)rem : 32, ok);
+        uint32_t any = 0;
+        if (len) {
+            const uint64_t wf = o0 >> 5, wl = (o1 - 1) >> 5;
+            for (uint64_t w = wf; w <= wl; ++w) {
+                uint32_t m = bad[w];
+                if (w == wf) m &= 0xFFFFFFFFu << (o0 & 31);
+                if (w == wl) m &= 0xFFFFFFFFu >> (31 - ((o1 - 1) & 31));
+                any |= m;
+            }
         }
-        const bool valid = __ballot_sync(gmask, !ok) == 0;
-        const uint64_t nwin = (valid && len >= k) ? len - k + 1 : 0;
-        for (uint64_t j = gl; wbase + j < wend; j += GROUP) {
-            uint64_t s = nwin > 32 * j ? nwin - 32 * j : 0;
-            nstart[wbase + j] = (uint8_t)(s < 32 ? s : 32);
-        }
-        if (gl == 0 && valid) {
+        const bool ok = any == 0;
+        const uint64_t nwin = (ok && len >= k) ? len - k + 1 : 0;
+        valid[r] = nwin != 0;
+        if (ok) {
             acc[0] += 1;
             acc[1] += len;
             acc[2] += nwin;
@@ -154,6 +139,30 @@ pack_reads_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restrict_
     if ((threadIdx.x & 31) == 0) {
         if (lmax) atomicMax(&ctr->max_len, (unsigned long long)lmax);
         atomicMin(&ctr->min_len, (unsigned long long)lmin);
+    }
+}
+
+// Ragged batches only: wstart bit i of word w <=> a window starts at flat base 32w + i,
+// i.e. the base belongs to an accepted read and the window ends inside it.  (Batches whose
+// reads all have one length enumerate their windows in closed form and skip this.)
+__global__ void __launch_bounds__(256)
+mark_starts_kernel(const uint64_t *__restrict__ offsets, uint64_t n_reads, const uint8_t *__restrict__ bases,
+                   uint32_t k, const uint8_t *__restrict__ valid, uint32_t *__restrict__ wstart) {
+    const uint64_t off0 = offsets[0];
+    const uint32_t shift0 = (uint32_t)((uintptr_t)(bases + off0) & 31);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += stride) {
+        if (!valid[r]) continue;
+        const uint64_t o0 = offsets[r] - off0 + shift0, o1 = offsets[r + 1] - off0 + shift0;
+        const uint64_t last = o1 - k; // last window start (valid[r] implies len >= k)
+        const uint64_t wf = o0 >> 5, wl = last >> 5;
+        for (uint64_t w = wf; w <= wl; ++w) {
+            uint32_t m = 0xFFFFFFFFu;
+            if (w == wf) m &= 0xFFFFFFFFu << (o0 & 31);
+            if (w == wl) m &= 0xFFFFFFFFu >> (31 - (last & 31));
+            if (w == wf || w == wl) atomicOr(&wstart[w], m); // boundary words are shared with neighbours
+            else wstart[w] = m;
+        }
     }
 }
 
@@ -191,49 +200,6 @@ template <class K> struct Roller {
         rc = (rc >> 2) | ((K)(3u - b) << rc_shift);
     }
 };
-
-// words w+1 / w+2 for every lane of the warp
-__device__ __forceinline__ void neighbour_words(const uint64_t *__restrict__ packed, uint64_t w,
-                                                uint64_t n_words, uint64_t w0, bool need2,
-                                                uint64_t &w1, uint64_t &w2) {
-    const int lane = threadIdx.x & 31;
-    w1 = __shfl_down_sync(0xFFFFFFFFu, w0, 1);
-    w2 = __shfl_down_sync(0xFFFFFFFFu, w0, 2);
-    if (lane == 31) w1 = (w + 1 < n_words) ? packed[w + 1] : 0;
-    if (need2 && lane >= 30) w2 = (w + 2 < n_words) ? packed[w + 2] : 0;
-}
-
-// ======================================================================= K3
-// Fused extract + insert (the single-GPU path when the table is L2 sized):
-// the loop of add_read_fastaq (hm_gir.rs:55-85) with both-strand insertion
-// folded into one canonical update: key = min(fw, rc), +2 if fw == rc
-// (a palindrome is inserted twice by hm_gir.rs:55-74).
-template <class K, bool RC>
-__global__ void __launch_bounds__(256)
-extract_insert_kernel(const uint64_t *__restrict__ packed, const uint8_t *__restrict__ nstart,
-                      uint64_t n_words, uint32_t k, Table<K> t) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t n_round = (n_words + 31) & ~(uint64_t)31;
-    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_round; w += stride) {
-        const bool in = w < n_words;
-        uint64_t w0 = in ? packed[w] : 0, w1, w2;
-        const uint32_t ns = in ? nstart[w] : 0;
-        neighbour_words(packed, w, n_words, w0, sizeof(K) == 16, w1, w2);
-        if (ns == 0) continue;
-        Roller<K> r;
-        r.init(w0, w1, w2, k);
-        for (uint32_t j = 0; j < ns; ++j) {
-            K key = r.fw;
-            uint32_t inc = 1;
-            if (RC) {
-                if (r.rc < key) key = r.rc;
-                if (r.rc == r.fw) inc = 2;
-            }
-            table_add(t, key, inc);
-            r.step();
-        }
-    }
-}
 
 // ============================================================ cardinality
 // HyperLogLog sketch (2^12 registers) of the keys offered to the table, merged
@@ -273,73 +239,80 @@ __device__ __forceinline__ void hll_update_tile(uint32_t *regs, const K (&key)[P
 }
 
 // ================================================================ work items
-// The extraction kernels that feed the partitioner split every packed word
-// into 4 work items of 8 window starts (instead of one lane per word with up
-// to 32 windows): a 100 bp read has 70 windows = 32+32+6+0 per word, i.e. 55 %
-// lane utilisation per word but 97 % per 8-window item.  A warp covers 8
-// consecutive words; lanes 0..9 load them (+2 for the k-1 overlap) once and
-// every lane picks its three words with warp shuffles.
+// The extraction kernels hand every lane a work item of 8 consecutive window start
+// positions of the flat stream (instead of one lane per 32-base word: a 100 bp read has
+// 70 windows = 32+32+6+0 per word, i.e. 55 % lane utilisation per word but 97 % per
+// 8-window item).
+//   uniform batch (all reads have length ulen; the usual case for short-read sequencers):
+//       items are enumerated in closed form, read r = item / ipr, granule u = item % ipr
+//       with ipr = ceil((ulen-k+1)/8), so no lane is handed an empty item;
+//   ragged batch: item = (flat word, granule of 8 positions) and the window starts are the
+//       set bits of wstart; a warp covers 8 consecutive words, lanes 0..10 load them once
+//       and every lane picks its words with warp shuffles.
 constexpr int GRAN = 8, ITEMS_PER_WORD = 32 / GRAN;
 
-// When every read of the batch has the same length L (the usual case for
-// short-read sequencers; the pack kernel reports min/max length) items are
-// enumerated in closed form instead -- read r = item / ipr, granule u = item % ipr
-// with ipr = ceil((L-k+1)/8) -- so that no lane is handed an empty item.
-struct ItemMap {
-    uint32_t ulen; // 0: ragged batch, map items through nstart
-    uint32_t ipr;  // items per read (uniform batches)
+struct ReadView {
+    const uint64_t *packed; // flat 2-bit stream (+4 words of padding)
+    const uint8_t *valid;   // uniform: valid[r]
+    const uint32_t *wstart; // ragged: window start bits
+    uint64_t n_words;
     uint64_t n_items;
+    uint32_t shift0; // flat position of the first base of the batch
+    uint32_t ulen;   // 0: ragged
+    uint32_t ipr;    // items per read (uniform)
 };
 
 template <class K> struct ItemWindows {
     Roller<K> r;
-    uint32_t nwin;
+    uint32_t mask; // bit j: the j-th position of the item starts a window
     // all 32 lanes of the warp must call this with consecutive items
-    __device__ __forceinline__ void load(const uint64_t *__restrict__ packed,
-                                         const uint8_t *__restrict__ nstart, uint64_t n_words,
-                                         uint64_t item, uint32_t k, const ItemMap &m) {
-        uint64_t w0, w1, w2;
-        uint32_t g;
-        if (m.ulen) {
-            uint64_t rd;
+    __device__ __forceinline__ void load(const ReadView &v, uint64_t item, uint32_t k) {
+        constexpr bool WIDE = sizeof(K) == 16;
+        uint64_t w0, w1, w2, w3 = 0;
+        uint32_t s;
+        if (v.ulen) {
+            uint64_t rd, pos;
             uint32_t u;
-            if (m.n_items <= 0xFFFFFFFFull) {
-                rd = (uint32_t)item / m.ipr;
-                u = (uint32_t)item - (uint32_t)rd * m.ipr;
+            if (v.n_items <= 0xFFFFFFFFull) {
+                rd = (uint32_t)item / v.ipr;
+                u = (uint32_t)item - (uint32_t)rd * v.ipr;
             }
             else {
-                rd = item / m.ipr;
-                u = (uint32_t)(item - rd * m.ipr);
+                rd = item / v.ipr;
+                u = (uint32_t)(item - rd * v.ipr);
             }
-            const bool in = item < m.n_items;
-            const uint64_t wb = (rd * m.ulen) / 32 + rd; // first packed word of read rd
-            const uint64_t w = wb + (GRAN * u) / 32;
-            g = u % ITEMS_PER_WORD;
-            const uint32_t total = m.ulen - k + 1, done = GRAN * u;
-            nwin = (in && nstart[wb] != 0) ? (total - done < GRAN ? total - done : GRAN) : 0;
-            w0 = in ? packed[w] : 0;
-            w1 = in ? packed[w + 1] : 0; // the batch buffer is padded by 4 words
-            w2 = (in && sizeof(K) == 16) ? packed[w + 2] : 0;
+            const bool in = item < v.n_items;
+            pos = rd * v.ulen + GRAN * u + v.shift0;
+            const uint64_t w = pos >> 5;
+            s = (uint32_t)pos & 31;
+            const uint32_t total = v.ulen - k + 1, done = GRAN * u;
+            const uint32_t nwin = total - done < GRAN ? total - done : GRAN;
+            mask = (in && v.valid[rd]) ? (1u << nwin) - 1u : 0u;
+            w0 = in ? v.packed[w] : 0;
+            w1 = in ? v.packed[w + 1] : 0; // the packed buffer is padded by 4 words
+            w2 = in ? v.packed[w + 2] : 0;
+            if (WIDE) w3 = in ? v.packed[w + 3] : 0;
         }
         else {
             const int lane = threadIdx.x & 31;
             const uint64_t warp_word = (item - lane) / ITEMS_PER_WORD; // first word of the warp
             const uint64_t lw = warp_word + lane;
-            uint64_t v = (lane < 8 + 2 && lw < n_words) ? packed[lw] : 0;
+            uint64_t x = (lane < 8 + 3 && lw < v.n_words) ? v.packed[lw] : 0;
             const int src = lane / ITEMS_PER_WORD;
-            w0 = __shfl_sync(0xFFFFFFFFu, v, src);
-            w1 = __shfl_sync(0xFFFFFFFFu, v, src + 1);
-            w2 = __shfl_sync(0xFFFFFFFFu, v, src + 2);
+            w0 = __shfl_sync(0xFFFFFFFFu, x, src);
+            w1 = __shfl_sync(0xFFFFFFFFu, x, src + 1);
+            w2 = __shfl_sync(0xFFFFFFFFu, x, src + 2);
+            if (WIDE) w3 = __shfl_sync(0xFFFFFFFFu, x, src + 3);
             const uint64_t w = item / ITEMS_PER_WORD;
-            g = (uint32_t)(item % ITEMS_PER_WORD);
-            const uint32_t ns = w < n_words ? nstart[w] : 0;
-            nwin = ns > GRAN * g ? (ns - GRAN * g < GRAN ? ns - GRAN * g : GRAN) : 0;
+            const uint32_t g = (uint32_t)(item % ITEMS_PER_WORD);
+            s = GRAN * g;
+            mask = w < v.n_words ? (v.wstart[w] >> s) & 0xFFu : 0u;
         }
-        if (g) { // start at base 8g of the word: shift the 96-base span left
-            const uint32_t sh = 2 * GRAN * g;
+        if (s) { // left-align the span at the item's first base
+            const uint32_t sh = 2 * s;
             w0 = (w0 << sh) | (w1 >> (64 - sh));
             w1 = (w1 << sh) | (w2 >> (64 - sh));
-            w2 <<= sh;
+            w2 = (w2 << sh) | (WIDE ? (w3 >> (64 - sh)) : 0);
         }
         r.init(w0, w1, w2, k);
     }
@@ -348,23 +321,51 @@ template <class K> struct ItemWindows {
     }
 };
 
-// stand-alone sketch passes for the direct (unpartitioned) path, only run when
+// ======================================================================= K3 (direct)
+// Fused extract + insert with L2 atomics (the single-GPU path while the whole table is
+// L2 sized): the loop of add_read_fastaq (hm_gir.rs:55-85) with both-strand insertion
+// folded into one canonical update: key = min(fw, rc), +2 if fw == rc (a palindrome is
+// inserted twice by hm_gir.rs:55-74).
+template <class K, bool RC>
+__global__ void __launch_bounds__(256)
+extract_insert_kernel(ReadView v, uint32_t k, Table<K> t) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n_items = (v.n_items + 31) & ~(uint64_t)31;
+    for (uint64_t it = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; it < n_items; it += stride) {
+        ItemWindows<K> iw;
+        iw.load(v, it, k);
+#pragma unroll
+        for (int j = 0; j < GRAN; ++j) {
+            if (iw.mask & (1u << j)) {
+                K key = iw.r.fw;
+                uint32_t inc = 1;
+                if (RC) {
+                    if (iw.r.rc < key) key = iw.r.rc;
+                    if (iw.r.rc == iw.r.fw) inc = 2;
+                }
+                table_add(t, key, inc);
+            }
+            iw.r.step();
+        }
+    }
+}
+
+// stand-alone sketch pass for the direct (unpartitioned) path, only run when
 // the trivial bound cannot prove that the batch fits
 template <class K, bool RC>
 __global__ void __launch_bounds__(256)
-hll_reads_kernel(const uint64_t *__restrict__ packed, const uint8_t *__restrict__ nstart,
-                 uint64_t n_words, uint32_t k, ItemMap im, uint32_t *__restrict__ g_regs) {
+hll_reads_kernel(ReadView v, uint32_t k, uint32_t *__restrict__ g_regs) {
     __shared__ uint32_t regs[HLL_M];
     for (uint32_t i = threadIdx.x; i < HLL_M; i += blockDim.x) regs[i] = 0;
     __syncthreads();
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t n_items = (im.n_items + 31) & ~(uint64_t)31;
+    const uint64_t n_items = (v.n_items + 31) & ~(uint64_t)31;
     for (uint64_t it = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; it < n_items; it += stride) {
         ItemWindows<K> iw;
-        iw.load(packed, nstart, n_words, it, k, im);
+        iw.load(v, it, k);
 #pragma unroll
         for (int j = 0; j < GRAN; ++j) {
-            hll_update(regs, KeyTraits<K>::hash(iw.template key<RC>()), j < (int)iw.nwin);
+            hll_update(regs, KeyTraits<K>::hash(iw.template key<RC>()), (iw.mask >> j) & 1u);
             iw.r.step();
         }
     }
@@ -393,21 +394,20 @@ hll_keys_kernel(const K *__restrict__ keys, uint64_t n, uint32_t *__restrict__ g
 // with HLL the same pass also folds the keys into the cardinality sketch.
 template <class K, bool RC, bool BY_OWNER, bool HLL>
 __global__ void __launch_bounds__(256)
-hist_reads_kernel(const uint64_t *__restrict__ packed, const uint8_t *__restrict__ nstart,
-                  uint64_t n_words, uint32_t k, ItemMap im, Table<K> t, uint32_t n_bins,
+hist_reads_kernel(ReadView v, uint32_t k, Table<K> t, uint32_t n_bins,
                   unsigned long long *__restrict__ g_hist, uint32_t *__restrict__ g_regs) {
     extern __shared__ uint32_t sh_hist[]; // n_bins counters (+ HLL_M registers)
     uint32_t *regs = sh_hist + n_bins;
     for (uint32_t i = threadIdx.x; i < n_bins + (HLL ? HLL_M : 0); i += blockDim.x) sh_hist[i] = 0;
     __syncthreads();
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t n_items = (im.n_items + 31) & ~(uint64_t)31;
+    const uint64_t n_items = (v.n_items + 31) & ~(uint64_t)31;
     for (uint64_t it = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; it < n_items; it += stride) {
         ItemWindows<K> iw;
-        iw.load(packed, nstart, n_words, it, k, im);
+        iw.load(v, it, k);
 #pragma unroll
         for (int j = 0; j < GRAN; ++j) {
-            if (j < (int)iw.nwin) {
+            if (iw.mask & (1u << j)) {
                 uint64_t h = KeyTraits<K>::hash(iw.template key<RC>());
                 Place p = place_of(h, t.world, t.n_sub);
                 atomicAdd(&sh_hist[BY_OWNER ? p.owner : p.part], 1u);
@@ -568,7 +568,7 @@ struct ScatterOut {
 // Leaves sm.cnt[parity ^ 1] zeroed and the block synchronised.
 template <class K, int THREADS, int PER>
 __device__ __forceinline__ void tile_scatter(const K (&key)[PER], const uint32_t (&bin)[PER],
-                                             int nvalid, ScatterSmem<K, THREADS * PER> &sm,
+                                             uint32_t vmask, ScatterSmem<K, THREADS * PER> &sm,
                                              uint32_t n_bins, unsigned long long *cursors,
                                              uint64_t bin_off, const ScatterOut &o, uint32_t parity,
                                              const PeerOut *po = nullptr) {
@@ -579,7 +579,7 @@ __device__ __forceinline__ void tile_scatter(const K (&key)[PER], const uint32_t
     KTG_PHASE_BEGIN();
 #pragma unroll
     for (int j = 0; j < PER; ++j)
-        if (j < nvalid) rank[j] = atomicAdd(&cnt[bin[j]], 1u);
+        if (vmask & (1u << j)) rank[j] = atomicAdd(&cnt[bin[j]], 1u);
     if (threadIdx.x == 0) s_ovf = 0;
     __syncthreads();
     KTG_PHASE(1);
@@ -641,7 +641,7 @@ __device__ __forceinline__ void tile_scatter(const K (&key)[PER], const uint32_t
     KTG_PHASE(2);
 #pragma unroll
     for (int j = 0; j < PER; ++j)
-        if (j < nvalid) {
+        if (vmask & (1u << j)) {
             const uint2 v = sm.ld[bin[j]];
             const uint32_t pos = v.x + rank[j];
             sm.keys[pos] = key[j];
@@ -698,9 +698,8 @@ constexpr int SCATTER_THREADS = 256, SCATTER_PER = 8, SCATTER_TILE = SCATTER_THR
 constexpr int BIN_PART = 0, BIN_OWNER = 1;
 template <class K, bool RC, int BINS, bool HLL>
 __global__ void __launch_bounds__(SCATTER_THREADS, 3)
-scatter_reads_kernel(const uint64_t *__restrict__ packed, const uint8_t *__restrict__ nstart,
-                     uint64_t n_words, uint32_t k, ItemMap im, Table<K> t, uint32_t n_bins,
-                     ScatterOut o, uint32_t *__restrict__ g_regs, PeerOut po) {
+scatter_reads_kernel(ReadView v, uint32_t k, Table<K> t, uint32_t n_bins, ScatterOut o,
+                     uint32_t *__restrict__ g_regs, PeerOut po) {
     extern __shared__ __align__(16) unsigned char smem[];
     ScatterSmem<K, SCATTER_TILE> sm;
     sm.carve(smem, n_bins);
@@ -709,11 +708,11 @@ scatter_reads_kernel(const uint64_t *__restrict__ packed, const uint8_t *__restr
     }
     for (uint32_t i = threadIdx.x; i < 2 * n_bins; i += SCATTER_THREADS) sm.cnt[i] = 0;
     __syncthreads();
-    const uint64_t n_tiles = (im.n_items + SCATTER_THREADS - 1) / SCATTER_THREADS;
+    const uint64_t n_tiles = (v.n_items + SCATTER_THREADS - 1) / SCATTER_THREADS;
     uint32_t parity = 0;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, parity ^= 1u) {
         ItemWindows<K> iw;
-        iw.load(packed, nstart, n_words, tile * SCATTER_THREADS + threadIdx.x, k, im);
+        iw.load(v, tile * SCATTER_THREADS + threadIdx.x, k);
         K key[SCATTER_PER];
         uint32_t bin[SCATTER_PER];
         uint32_t sampled = 0;
@@ -723,11 +722,11 @@ scatter_reads_kernel(const uint64_t *__restrict__ packed, const uint8_t *__restr
             uint64_t h = KeyTraits<K>::hash(key[j]);
             Place p = place_of(h, t.world, t.n_sub);
             bin[j] = BINS == BIN_OWNER ? p.owner : p.part;
-            if (HLL && hll_sampled(h) && j < (int)iw.nwin) sampled |= 1u << j;
+            if (HLL && hll_sampled(h)) sampled |= 1u << j;
             iw.r.step();
         }
-        if (HLL) hll_update_tile<K, SCATTER_PER>(sm.regs, key, sampled);
-        tile_scatter<K, SCATTER_THREADS, SCATTER_PER>(key, bin, (int)iw.nwin, sm, n_bins, o.cursors, 0, o, parity,
+        if (HLL) hll_update_tile<K, SCATTER_PER>(sm.regs, key, sampled & iw.mask);
+        tile_scatter<K, SCATTER_THREADS, SCATTER_PER>(key, bin, iw.mask, sm, n_bins, o.cursors, 0, o, parity,
                                                       (BINS == BIN_OWNER && po.world) ? &po : nullptr);
     }
     if (HLL) {
@@ -756,8 +755,7 @@ scatter_keys_kernel(const K *__restrict__ keys, uint64_t n, Table<K> t, uint32_t
         const uint64_t base = tile * SCATTER_TILE;
         K key[SCATTER_PER];
         uint32_t bin[SCATTER_PER];
-        uint32_t sampled = 0;
-        int nvalid = 0;
+        uint32_t sampled = 0, vmask = 0;
 #pragma unroll
         for (int j = 0; j < SCATTER_PER; ++j) {
             const uint64_t i = base + (uint64_t)j * SCATTER_THREADS + threadIdx.x;
@@ -767,10 +765,10 @@ scatter_keys_kernel(const K *__restrict__ keys, uint64_t n, Table<K> t, uint32_t
             Place p = place_of(h, t.world, t.n_sub);
             bin[j] = BY_OWNER ? p.owner : p.part;
             if (HLL && hll_sampled(h) && in) sampled |= 1u << j;
-            if (in) nvalid = j + 1;
+            if (in) vmask |= 1u << j;
         }
         if (HLL) hll_update_tile<K, SCATTER_PER>(sm.regs, key, sampled);
-        tile_scatter<K, SCATTER_THREADS, SCATTER_PER>(key, bin, nvalid, sm, n_bins, o.cursors, 0, o, parity);
+        tile_scatter<K, SCATTER_THREADS, SCATTER_PER>(key, bin, vmask, sm, n_bins, o.cursors, 0, o, parity);
     }
     if (HLL) {
         __syncthreads();
@@ -814,7 +812,7 @@ scatter_buckets_kernel(const K *__restrict__ keys1, const unsigned long long *__
         if (base >= end) continue;
         K key[L2S_PER];
         uint32_t bin[L2S_PER];
-        int nvalid = 0;
+        uint32_t vmask = 0;
         KTG_PHASE_BEGIN();
 #pragma unroll
         for (int j = 0; j < L2S_PER; ++j) {
@@ -823,13 +821,13 @@ scatter_buckets_kernel(const K *__restrict__ keys1, const unsigned long long *__
             key[j] = in ? KeyTraits<K>::load_stream(&keys1[i]) : (K)0;
             if (LEVEL == 2) bin[j] = (KeyTraits<K>::slot_hash(key[j]) & t.sub_mask) >> t.page_log2;
             else bin[j] = place_of(KeyTraits<K>::hash(key[j]), t.world, t.n_sub).part;
-            if (in) nvalid = j + 1;
+            if (in) vmask |= 1u << j;
         }
 #ifdef KTG_PHASE_TIMERS
         if (threadIdx.x == 0 && key[L2S_PER - 1] == (K)12345) g_phase_cycles[7] = 1; // wait for the loads
 #endif
         KTG_PHASE(0);
-        tile_scatter<K, L2S_THREADS, L2S_PER>(key, bin, nvalid, sm, n2, o.cursors + b * n2, b * n2, o, parity);
+        tile_scatter<K, L2S_THREADS, L2S_PER>(key, bin, vmask, sm, n2, o.cursors + b * n2, b * n2, o, parity);
         parity ^= 1u;
     }
 }
