@@ -377,7 +377,9 @@ template <class K> struct Builder : BuilderBase {
         const size_t mx = ScatterSmem<K, SCATTER_TILE>::bytes(MAX_BINS, true);
         allow_smem(scatter_buckets_kernel<K, 2>, ScatterSmem<K, L2S_TILE>::bytes(MAX_PAGES_PER_SUB, false));
         allow_smem(scatter_buckets_kernel<K, 1>, ScatterSmem<K, L2S_TILE>::bytes(MAX_BINS, false));
-        allow_smem(update_pages_kernel<K>, page_smem_bytes());
+        allow_smem(update_pages_kernel<K, 512>, page_smem_bytes(512));
+        allow_smem(update_pages_kernel<K, 640>, page_smem_bytes(640));
+        allow_smem(update_pages_kernel<K, 704>, page_smem_bytes(704));
         allow_smem(scatter_reads_kernel<K, true, BIN_PART, true>, mx);
         allow_smem(scatter_reads_kernel<K, false, BIN_PART, true>, mx);
         allow_smem(scatter_reads_kernel<K, true, BIN_PART, false>, mx);
@@ -396,8 +398,8 @@ template <class K> struct Builder : BuilderBase {
         if (cfg.flags & (KTG_FLAG_FORCE_PARTITION | KTG_FLAG_FORCE_PAGES)) return true;
         return tab.n_sub > 3; // up to ~48 MB of table is L2 resident as a whole
     }
-    static size_t page_smem_bytes(uint32_t page_log2 = PageGeom<K>::LOG2) {
-        return (((size_t)1 << page_log2) + (PAGE_THREADS / 32) * PQ_CAP) * (sizeof(K) + 4);
+    static size_t page_smem_bytes(int threads, uint32_t page_log2 = PageGeom<K>::LOG2) {
+        return (((size_t)1 << page_log2) + (threads / 32) * PQ_CAP) * (sizeof(K) + 4);
     }
     // Streaming page update or L2 atomics?  The sweep reads and writes every slot
     // (32 B per slot of traffic), the atomic path costs ~2 L2 transactions per key:
@@ -760,10 +762,18 @@ template <class K> struct Builder : BuilderBase {
             scatter_buckets_kernel<K, 2><<<g, L2S_THREADS, ss, stream>>>(keys1, fill1, cap1, tiles_per_bin, n_tiles, sub_mod, tab, o);
         }
         prof.end(stream);
-        const size_t ps = page_smem_bytes(tab.page_log2);
-        int g = (int)std::min<uint64_t>(grid_for(update_pages_kernel<K>, PAGE_THREADS, ps, props), n_pages);
+        int pt = sizeof(K) == 8 ? 704 : 512; // u128 keys need the registers of the smaller block
+        if (const char *e = getenv("KTG_PAGE_THREADS")) pt = atoi(e); // tuning knob: 512, 640 or 704
+        const bool palin = rc && (k % 2 == 0), special = !rc && 2 * k == 8 * sizeof(K);
         prof.begin("update_pages", n_keys, stream);
-        update_pages_kernel<K><<<g, PAGE_THREADS, ps, stream>>>((const K *)b_pkeys.p, cur2, cap2, k, rc && (k % 2 == 0), tab, fresh);
+        auto launch_p = [&](auto kern, int threads) {
+            const size_t ps = page_smem_bytes(threads, tab.page_log2);
+            int g = (int)std::min<uint64_t>(grid_for(kern, threads, ps, props), n_pages);
+            kern<<<g, threads, ps, stream>>>((const K *)b_pkeys.p, cur2, cap2, k, palin, special, tab, fresh);
+        };
+        if (pt == 640) launch_p(update_pages_kernel<K, 640>, 640);
+        else if (pt == 704) launch_p(update_pages_kernel<K, 704>, 704);
+        else launch_p(update_pages_kernel<K, 512>, 512);
         prof.end(stream);
         fresh = false;
         nodes_valid = false;

@@ -891,47 +891,55 @@ template <class K> struct PageCtx {
     uint32_t page_mask;
 };
 
-// all 32 lanes call this together; `active` lanes carry (key, st)
+// One probe of one slot: resolves the key (claim / add) or advances st to the next slot and
+// returns true ("still pending").  `cur` is the slot content loaded by the caller, so that
+// several independent loads can be in flight before the first one is used.
 template <class K>
-__device__ __forceinline__ void page_probe_rows(PageCtx<K> &c, const Table<K> &t, K key, uint32_t st, bool active) {
+__device__ __forceinline__ bool page_probe_once(PageCtx<K> &c, const Table<K> &t, K key, uint32_t &st, K cur) {
     typedef KeyTraits<K> T;
     const K EMPTY = T::empty();
-    const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
-    const uint32_t keep = 0xFFFF0000u | c.page_mask;
-    for (;;) {
-        bool pending = false;
-        if (active) {
-            const uint32_t i = st & 0xFFFFu;
-            K cur = smem_load(&c.sk[i]);
-            if (cur != key && (cur == EMPTY || T::maybe_torn(cur))) cur = smem_cas(&c.sk[i], EMPTY, key);
-            if (cur == key || cur == EMPTY) atomicAdd(&c.sw[i], 1u + (st >> 31));
-            else {
-                st = (st + PQ_STEP) & keep; // next slot (wraps inside the page), one more probe
-                pending = true;
-                if (((st & ~PQ_INC2) >> PQ_PROBE_SHIFT) > c.page_mask) { // every slot holds another key
-                    pending = false;
-                    unsigned long long pos = atomicAdd(t.ovf_count, 1ull); // replayed after a grow
-                    if (pos < t.ovf_cap) {
-                        t.ovf_keys[pos] = key;
-                        t.ovf_inc[pos] = 1u + (st >> 31);
-                    }
-                }
-            }
+    const uint32_t i = st & 0xFFFFu;
+    if (cur != key && (cur == EMPTY || T::maybe_torn(cur))) cur = smem_cas(&c.sk[i], EMPTY, key);
+    if (cur == key || cur == EMPTY) {
+        atomicAdd(&c.sw[i], 1u + (st >> 31));
+        return false;
+    }
+    st = (st + PQ_STEP) & (0xFFFF0000u | c.page_mask); // next slot (wraps inside the page), one more probe
+    if (((st & ~PQ_INC2) >> PQ_PROBE_SHIFT) > c.page_mask) { // every slot holds another key
+        unsigned long long pos = atomicAdd(t.ovf_count, 1ull); // replayed after a grow
+        if (pos < t.ovf_cap) {
+            t.ovf_keys[pos] = key;
+            t.ovf_inc[pos] = 1u + (st >> 31);
         }
-        const uint32_t m = __ballot_sync(0xFFFFFFFFu, pending);
-        if (m == 0 && c.qn < 32) return; // the common case: nothing to queue, nothing to drain
-        if (pending) {
-            const uint32_t pos = c.qn + __popc(m & lt);
-            c.qk[pos] = key;
-            c.qi[pos] = st;
-        }
-        c.qn += __popc(m);
-        __syncwarp();
-        if (c.qn < 32) return;
+        return false;
+    }
+    return true;
+}
+
+// all 32 lanes: append the pending lanes' (key, st) to the warp queue
+template <class K>
+__device__ __forceinline__ void page_push(PageCtx<K> &c, K key, uint32_t st, bool pending) {
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, pending);
+    if (m == 0) return;
+    if (pending) {
+        const uint32_t pos = c.qn + __popc(m & ((1u << (threadIdx.x & 31)) - 1u));
+        c.qk[pos] = key;
+        c.qi[pos] = st;
+    }
+    c.qn += __popc(m);
+}
+
+// all 32 lanes: retry full rows of 32 queued keys until fewer than 32 are left
+template <class K> __device__ __forceinline__ void page_retry_rows(PageCtx<K> &c, const Table<K> &t) {
+    const uint32_t lane = threadIdx.x & 31;
+    __syncwarp();
+    while (c.qn >= 32) {
         c.qn -= 32;
-        key = c.qk[c.qn + lane];
-        st = c.qi[c.qn + lane];
-        active = true;
+        const K key = c.qk[c.qn + lane];
+        uint32_t st = c.qi[c.qn + lane];
+        __syncwarp();
+        const bool pending = page_probe_once(c, t, key, st, smem_load(&c.sk[st & 0xFFFFu]));
+        page_push(c, key, st, pending);
         __syncwarp();
     }
 }
@@ -939,14 +947,17 @@ __device__ __forceinline__ void page_probe_rows(PageCtx<K> &c, const Table<K> &t
 // the partial row left in the queue at the end of a page
 template <class K> __device__ __forceinline__ void page_drain(PageCtx<K> &c, const Table<K> &t) {
     const uint32_t lane = threadIdx.x & 31;
+    __syncwarp();
     while (c.qn) {
         const uint32_t cnt = c.qn; // < 32
         const bool active = lane < cnt;
-        K key = active ? c.qk[lane] : KeyTraits<K>::empty();
+        const K key = active ? c.qk[lane] : KeyTraits<K>::empty();
         uint32_t st = active ? c.qi[lane] : 0;
         c.qn = 0;
         __syncwarp();
-        page_probe_rows(c, t, key, st, active);
+        const bool pending = active && page_probe_once(c, t, key, st, smem_load(&c.sk[st & 0xFFFFu]));
+        page_push(c, key, st, pending);
+        __syncwarp();
     }
 }
 
@@ -969,10 +980,10 @@ __device__ __forceinline__ void smem_to_slot(KeyTraits<u128>::Slot *g, const u12
     ((uint4 *)g)[1] = make_uint4(*sw, 0u, 0u, 0u);
 }
 
-template <class K>
-__global__ void __launch_bounds__(PAGE_THREADS)
+template <class K, int THREADS>
+__global__ void __launch_bounds__(THREADS, 2)
 update_pages_kernel(const K *__restrict__ keys2, const unsigned long long *__restrict__ cursors2,
-                    uint64_t cap2, uint32_t k, bool check_palindrome, Table<K> t, bool fresh) {
+                    uint64_t cap2, uint32_t k, bool check_palindrome, bool has_special, Table<K> t, bool fresh) {
     typedef KeyTraits<K> T;
     extern __shared__ __align__(16) unsigned char smem[];
     const uint32_t P = 1u << t.page_log2;
@@ -980,7 +991,7 @@ update_pages_kernel(const K *__restrict__ keys2, const unsigned long long *__res
     PageCtx<K> c;
     c.sk = (K *)smem;
     c.qk = c.sk + P + wid * PQ_CAP;
-    c.sw = (uint32_t *)(c.sk + P + (PAGE_THREADS / 32) * PQ_CAP);
+    c.sw = (uint32_t *)(c.sk + P + (THREADS / 32) * PQ_CAP);
     c.qi = c.sw + P + wid * PQ_CAP;
     c.qn = 0;
     c.page_mask = t.page_mask;
@@ -988,42 +999,51 @@ update_pages_kernel(const K *__restrict__ keys2, const unsigned long long *__res
     for (uint64_t g = blockIdx.x; g < n_pages; g += gridDim.x) {
         typename T::Slot *gs = t.slots + g * P;
         if (fresh) {
-            for (uint32_t i = threadIdx.x; i < P; i += PAGE_THREADS) {
+            for (uint32_t i = threadIdx.x; i < P; i += THREADS) {
                 c.sk[i] = T::empty();
                 c.sw[i] = 0;
             }
         }
         else {
-            for (uint32_t i = threadIdx.x; i < P; i += PAGE_THREADS) slot_to_smem(gs + i, c.sk + i, c.sw + i);
+            for (uint32_t i = threadIdx.x; i < P; i += THREADS) slot_to_smem(gs + i, c.sk + i, c.sw + i);
         }
         __syncthreads();
         const uint64_t beg = g * cap2, lim = beg + cap2, cur = cursors2[g];
         const uint32_t n = (uint32_t)((cur < lim ? cur : lim) - beg);
         const K *src = keys2 + beg;
         // a warp takes PAGE_UNROLL consecutive rows of 32 keys at a time
-        for (uint32_t r0 = wid * 32 * PAGE_UNROLL; r0 < n; r0 += PAGE_THREADS * PAGE_UNROLL) {
+        for (uint32_t r0 = wid * 32 * PAGE_UNROLL; r0 < n; r0 += THREADS * PAGE_UNROLL) {
             K my[PAGE_UNROLL];
 #pragma unroll
             for (int q = 0; q < PAGE_UNROLL; ++q) {
                 const uint32_t i = r0 + q * 32 + lane;
                 my[q] = i < n ? T::load_stream(&src[i]) : T::empty();
             }
+            // first probes of the PAGE_UNROLL keys: independent shared-memory loads in flight together
+            uint32_t st[PAGE_UNROLL];
+            K cur[PAGE_UNROLL];
+            bool active[PAGE_UNROLL];
 #pragma unroll
             for (int q = 0; q < PAGE_UNROLL; ++q) {
-                const uint32_t i = r0 + q * 32 + lane;
-                bool active = i < n;
-                if (active && my[q] == T::empty()) { // all-T at full key width (only without canonicalisation)
+                active[q] = r0 + q * 32 + lane < n;
+                if (has_special && active[q] && my[q] == T::empty()) { // all-T at full key width, no canonicalisation
                     atomicAdd(&t.slots[t.capacity()].w, 1u);
-                    active = false;
+                    active[q] = false;
                 }
-                uint32_t st = T::slot_hash(my[q]) & c.page_mask;
-                if (check_palindrome && revcomp(my[q], k) == my[q]) st |= PQ_INC2;
-                page_probe_rows(c, t, my[q], st, active);
+                st[q] = T::slot_hash(my[q]) & c.page_mask;
+                if (check_palindrome && revcomp(my[q], k) == my[q]) st[q] |= PQ_INC2;
+                cur[q] = smem_load(&c.sk[st[q] & 0xFFFFu]);
+            }
+#pragma unroll
+            for (int q = 0; q < PAGE_UNROLL; ++q) {
+                const bool pending = active[q] && page_probe_once(c, t, my[q], st[q], cur[q]);
+                page_push(c, my[q], st[q], pending);
+                page_retry_rows(c, t);
             }
         }
         page_drain(c, t);
         __syncthreads();
-        for (uint32_t i = threadIdx.x; i < P; i += PAGE_THREADS) smem_to_slot(gs + i, c.sk + i, c.sw + i);
+        for (uint32_t i = threadIdx.x; i < P; i += THREADS) smem_to_slot(gs + i, c.sk + i, c.sw + i);
         __syncthreads();
     }
 }
