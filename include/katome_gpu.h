@@ -177,14 +177,21 @@ int ktg_partition_keys_device(ktg_builder *b, const void *d_keys, uint64_t n, vo
  *      writers are done); ktg_mg_insert_buckets partitions them by sub-table into the staged
  *      buckets, from where they are flushed like any other batch;
  *   6. keys that did not fit a bucket (ktg_mg_spill) are grouped with
- *      ktg_partition_keys_device, exchanged with NCCL and added with ktg_mg_insert_spill. */
+ *      ktg_partition_keys_device, exchanged with NCCL and added with ktg_mg_insert_spill.
+ * A large batch is sent in chunks: the receive buffer has two slots (slot s starts rx_bytes * s
+ * after rx_base), chunk c uses slot c % 2, and steps 3 (on send_stream) and 5 (on the handle's
+ * stream) of consecutive chunks overlap.  first_of_batch resets the spill list. */
 int ktg_mg_plan(ktg_builder *b, uint64_t max_windows, int *needs_realloc);
 int ktg_mg_prepare(ktg_builder *b, uint64_t max_windows, void **rx_base, uint64_t *rx_bytes,
                    uint64_t *bucket_cap, uint32_t *n_sub);
 int ktg_mg_scatter_reads_device(ktg_builder *b, const void *d_bases, const void *d_offsets, uint64_t n_reads,
-                                uint64_t total_bases, void *const *peer_rx, void **d_cursors);
-int ktg_mg_insert_buckets(ktg_builder *b, const void *d_bucket_ends, uint64_t n_keys);
+                                uint64_t total_bases, void *const *peer_rx, uint32_t slot, int first_of_batch,
+                                void *send_stream, void **d_cursors);
+int ktg_mg_insert_buckets(ktg_builder *b, const void *d_bucket_ends, uint64_t n_keys, uint32_t slot);
 int ktg_mg_sketch(ktg_builder *b, void **d_regs, uint32_t *n_regs);
+/* fold an all-reduced COPY of the sketch back in (atomic max; the live sketch may be written
+ * by the next chunk's scatter at the same time, so it is never all-reduced in place) */
+int ktg_mg_merge_sketch(ktg_builder *b, const void *d_regs);
 int ktg_mg_spill(ktg_builder *b, void **d_keys, uint64_t *n);
 int ktg_mg_insert_spill(ktg_builder *b, const void *d_keys, uint64_t n);
 /* CUDA IPC handles of device allocations (cudaIpcGetMemHandle / OpenMemHandle / CloseMemHandle) */

@@ -29,7 +29,7 @@ SYMBOLS = (
     "ktg_partition_reads_device", "ktg_insert_keys_device", "ktg_host_alloc", "ktg_host_free",
     "ktg_synth_reads_device", "ktg_random_access_probe", "ktg_get_profile", "ktg_reset_profile",
     "ktg_get_info", "ktg_partition_keys_device", "ktg_mg_plan", "ktg_mg_prepare",
-    "ktg_mg_scatter_reads_device", "ktg_mg_insert_buckets", "ktg_mg_sketch", "ktg_mg_spill", "ktg_mg_insert_spill", "ktg_ipc_get_handle", "ktg_ipc_open", "ktg_ipc_close",
+    "ktg_mg_scatter_reads_device", "ktg_mg_insert_buckets", "ktg_mg_sketch", "ktg_mg_merge_sketch", "ktg_mg_spill", "ktg_mg_insert_spill", "ktg_ipc_get_handle", "ktg_ipc_open", "ktg_ipc_close",
 )
 
 
@@ -123,9 +123,11 @@ def lib():
     L.ktg_partition_keys_device.argtypes = [vp, vp, C.c_uint64, C.POINTER(vp), u64p]
     L.ktg_mg_plan.argtypes = [vp, C.c_uint64, intp]
     L.ktg_mg_prepare.argtypes = [vp, C.c_uint64, C.POINTER(vp), u64p, u64p, u32p]
-    L.ktg_mg_scatter_reads_device.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, C.POINTER(vp), C.POINTER(vp)]
-    L.ktg_mg_insert_buckets.argtypes = [vp, vp, C.c_uint64]
+    L.ktg_mg_scatter_reads_device.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, C.POINTER(vp), C.c_uint32, C.c_int,
+                                              vp, C.POINTER(vp)]
+    L.ktg_mg_insert_buckets.argtypes = [vp, vp, C.c_uint64, C.c_uint32]
     L.ktg_mg_sketch.argtypes = [vp, C.POINTER(vp), u32p]
+    L.ktg_mg_merge_sketch.argtypes = [vp, vp]
     L.ktg_mg_spill.argtypes = [vp, C.POINTER(vp), u64p]
     L.ktg_mg_insert_spill.argtypes = [vp, vp, C.c_uint64]
     L.ktg_ipc_get_handle.argtypes = [vp, C.c_char_p]

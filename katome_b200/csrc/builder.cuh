@@ -207,9 +207,11 @@ struct BuilderBase {
                            uint32_t *n_sub) = 0;
     virtual int mg_insert_spill(const void *d_keys, uint64_t n) = 0;
     virtual int mg_scatter_reads(const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t n_reads,
-                                 uint64_t total_bases, void *const *peer_rx, void **d_cursors) = 0;
-    virtual int mg_insert_buckets(const void *d_bucket_ends, uint64_t n_keys_estimate) = 0;
+                                 uint64_t total_bases, void *const *peer_rx, uint32_t slot, int first_of_batch,
+                                 cudaStream_t send_stream, void **d_cursors) = 0;
+    virtual int mg_insert_buckets(const void *d_bucket_ends, uint64_t n_keys, uint32_t slot) = 0;
     virtual int mg_sketch(void **d_regs, uint32_t *n_regs) = 0;
+    virtual int mg_merge_sketch(const void *d_regs) = 0;
     virtual int mg_spill(void **d_keys, uint64_t *n) = 0;
     virtual uint32_t owner_of(uint64_t hi, uint64_t lo) = 0;
     virtual int info(ktg_info *out) = 0;
@@ -674,7 +676,12 @@ template <class K> struct Builder : BuilderBase {
         uint64_t n_tiles = std::max<uint64_t>(1, (bt.v.n_items + SCATTER_THREADS - 1) / SCATTER_THREADS);
         PeerOut peers{};
         if (po) peers = *po;
+        // tuning knobs: CTAs per SM (the fused exchange kernel may share the SMs with the
+        // owner-side kernels of the previous chunk when a batch is sent in chunks)
+        int cap_ctas = 0;
+        if (const char *e = getenv(po ? "KTG_P2P_CTAS" : "KTG_L1_CTAS")) cap_ctas = atoi(e);
         prof.begin(po ? "scatter_reads_p2p" : "scatter_reads", bt.windows, stream);
+        if (cap_ctas > 0) n_tiles = std::min<uint64_t>(n_tiles, (uint64_t)props.sms * cap_ctas);
         if (rc) {
             int g = (int)std::min<uint64_t>(grid_for(scatter_reads_kernel<K, true, BINS, HLL>, SCATTER_THREADS, ss, props), n_tiles);
             scatter_reads_kernel<K, true, BINS, HLL><<<g, SCATTER_THREADS, ss, stream>>>(bt.v, k, tab, n_bins, o, (uint32_t *)b_hll.p, peers);
@@ -1239,9 +1246,15 @@ template <class K> struct Builder : BuilderBase {
     // owner partitions what it received by sub-table (level 1) into its staged buckets and
     // carries on exactly as on one GPU.  Nothing here depends on the table geometry, so ranks
     // may grow their shards independently.
+    // MG_SLOTS receive buffers (one allocation, one IPC handle): chunk c of a batch goes to slot
+    // c % MG_SLOTS, so that the owner can consume one chunk while the senders write the next.
+    static constexpr uint32_t MG_SLOTS = 2;
     DeviceBuf b_rx, b_mg_cur, b_mg_spill;
     uint64_t mg_cap = 0, mg_spill_cap = 0;
     bool mg_mode = false;
+    size_t mg_slot_keys() const { return (size_t)mg_cap * tab.world; }
+    unsigned long long *mg_cursors(uint32_t slot) { return (unsigned long long *)b_mg_cur.p + (size_t)slot * tab.world; }
+    unsigned long long *mg_spill_cursor() { return (unsigned long long *)b_mg_cur.p + (size_t)MG_SLOTS * tab.world; }
 
     int mg_geometry(uint64_t max_windows, uint64_t *cap) {
         const uint32_t W = tab.world;
@@ -1265,14 +1278,14 @@ template <class K> struct Builder : BuilderBase {
         if (cap > mg_cap || !b_rx.p) {
             KTG_TRY(sync());
             b_rx.release();
-            KTG_TRY(b_rx.ensure((size_t)cap * W * sizeof(K) + 64));
+            KTG_TRY(b_rx.ensure((size_t)cap * W * MG_SLOTS * sizeof(K) + 64));
             mg_cap = cap;
-            mg_spill_cap = std::max<uint64_t>(1u << 20, max_windows / 16);
+            mg_spill_cap = std::max<uint64_t>(1u << 20, max_windows / 4); // per batch of several chunks
             KTG_TRY(b_mg_spill.ensure(mg_spill_cap * sizeof(K) + 64));
-            KTG_TRY(b_mg_cur.ensure(((size_t)W + 2) * 8));
+            KTG_TRY(b_mg_cur.ensure(((size_t)W * MG_SLOTS + 2) * 8));
         }
         *rx_base = b_rx.p;
-        *rx_bytes = (size_t)mg_cap * W * sizeof(K);
+        *rx_bytes = (size_t)mg_cap * W * sizeof(K); // of ONE slot; slot s starts at rx_base + s * rx_bytes
         *bucket_cap = mg_cap;
         *n_sub = tab.n_sub;
         return KTG_OK;
@@ -1285,16 +1298,25 @@ template <class K> struct Builder : BuilderBase {
         return launch_insert_keys((const K *)d_keys, n);
     }
 
+    // Runs on send_stream (nullptr: the handle's stream), so that it can overlap the owner-side
+    // work of the previous chunk; peer_rx are the slot-0 bases of all ranks.
     int mg_scatter_reads(const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t n_reads,
-                         uint64_t total_bases, void *const *peer_rx, void **d_cursors) override {
+                         uint64_t total_bases, void *const *peer_rx, uint32_t slot, int first_of_batch,
+                         cudaStream_t send_stream, void **d_cursors) override {
         if (deferred_error != KTG_OK) return fail(deferred_error, "build is void after an earlier error");
         if (!b_rx.p) return fail(KTG_ERR_INVALID, "ktg_mg_prepare first");
+        if (slot >= MG_SLOTS) return fail(KTG_ERR_INVALID, "slot out of range");
+        struct StreamSwap { // pack() and the scatter pass launch on `stream`
+            cudaStream_t &ref, saved;
+            StreamSwap(cudaStream_t &r, cudaStream_t s) : ref(r), saved(r) { if (s) ref = s; }
+            ~StreamSwap() { ref = saved; }
+        } swap(stream, send_stream);
         const uint32_t W = tab.world;
         mg_mode = true;
-        unsigned long long *cur = (unsigned long long *)b_mg_cur.p;
+        unsigned long long *cur = mg_cursors(slot);
         *d_cursors = cur;
         init_cursors_kernel<<<1, 32, 0, stream>>>(cur, W, mg_cap);
-        KTG_CUDA(cudaMemsetAsync(cur + W, 0, 8, stream)); // spill cursor
+        if (first_of_batch) KTG_CUDA(cudaMemsetAsync(mg_spill_cursor(), 0, 8, stream));
         if (n_reads == 0) return KTG_OK;
         Batch bt;
         KTG_TRY(pack(d_bases, d_offsets, n_reads, total_bases, &bt));
@@ -1302,32 +1324,34 @@ template <class K> struct Builder : BuilderBase {
         PeerOut po{};
         po.world = W;
         po.bins_per_owner = 1;
-        // the sender's virtual position is v = owner * cap + fill; bucket `rank` of the owner
-        // starts at rank * cap, so bias the base by (rank - owner) * cap
+        // the sender's virtual position is v = owner * cap + fill; bucket `rank` of the owner's
+        // slot starts at slot_base + rank * cap, so bias the base by (rank - owner) * cap
         for (uint32_t o = 0; o < W; ++o)
-            po.rxb[o] = (K *)peer_rx[o] + ((int64_t)tab.rank - (int64_t)o) * (int64_t)mg_cap;
+            po.rxb[o] = (K *)peer_rx[o] + (int64_t)slot * (int64_t)mg_slot_keys() +
+                        ((int64_t)tab.rank - (int64_t)o) * (int64_t)mg_cap;
         ScatterOut so;
         so.cursors = cur;
         so.bucket_cap = mg_cap;
         so.out = nullptr;
         so.spill_out = b_mg_spill.p;
-        so.spill_cursor = cur + W;
+        so.spill_cursor = mg_spill_cursor();
         so.spill_cap = mg_spill_cap;
         KTG_TRY((scatter_reads_pass<BIN_OWNER, true>(bt, W, so, &po)));
         KTG_CUDA(cudaGetLastError());
         return KTG_OK;
     }
 
-    // d_bucket_ends[s]: absolute end (in keys, inside the own receive buffer) of the bucket that
-    // rank s filled, i.e. s * mg_cap + fill; n_keys: the exact total.  The caller has
-    // all-reduced (max) the sketch before this call.
-    int mg_insert_buckets(const void *d_bucket_ends, uint64_t n_keys) override {
+    // d_bucket_ends[s]: absolute end (in keys, inside the slot) of the bucket that rank s
+    // filled, i.e. s * mg_cap + fill; n_keys: the exact total.  The caller has all-reduced
+    // (max) the sketch before this call, so that a flush can size the shard.
+    int mg_insert_buckets(const void *d_bucket_ends, uint64_t n_keys, uint32_t slot) override {
         if (deferred_error != KTG_OK) return fail(deferred_error, "build is void after an earlier error");
+        if (slot >= MG_SLOTS) return fail(KTG_ERR_INVALID, "slot out of range");
         const unsigned long long *ends = (const unsigned long long *)d_bucket_ends;
         if (n_keys == 0) return KTG_OK;
         const uint32_t W = tab.world;
         const uint64_t cap = mg_cap;
-        const K *rx = (const K *)b_rx.p;
+        const K *rx = (const K *)b_rx.p + (size_t)slot * mg_slot_keys();
         int st = stage_add(n_keys, [&](uint32_t n_bins, const ScatterOut &o) -> int {
             const uint64_t tiles_per_bin = cap / L2S_TILE, n_tiles = tiles_per_bin * W;
             const size_t ss = ScatterSmem<K, L2S_TILE>::bytes(n_bins, false);
@@ -1351,13 +1375,20 @@ template <class K> struct Builder : BuilderBase {
         *n_regs = HLL_M;
         return KTG_OK;
     }
+    // fold an (all-reduced) copy of the sketch back in; atomic, because the sender-side
+    // kernel of the next chunk may be updating the sketch at the same time
+    int mg_merge_sketch(const void *d_regs) override {
+        hll_merge_kernel<<<HLL_M / 256, 256, 0, stream>>>((uint32_t *)b_hll.p, (const uint32_t *)d_regs);
+        KTG_CUDA(cudaGetLastError());
+        return KTG_OK;
+    }
 
     int mg_spill(void **d_keys, uint64_t *n) override {
         unsigned long long v = 0;
         *d_keys = b_mg_spill.p;
         *n = 0;
         if (!b_mg_cur.p) return KTG_OK;
-        KTG_CUDA(cudaMemcpyAsync(&v, (unsigned long long *)b_mg_cur.p + tab.world, 8, cudaMemcpyDeviceToHost, stream));
+        KTG_CUDA(cudaMemcpyAsync(&v, mg_spill_cursor(), 8, cudaMemcpyDeviceToHost, stream));
         KTG_TRY(sync());
         if (v > mg_spill_cap) {
             deferred_error = KTG_ERR_TABLE_FULL;

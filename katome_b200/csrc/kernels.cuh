@@ -221,6 +221,10 @@ __device__ __forceinline__ void hll_insert(uint32_t *regs, uint64_t h) {
     uint32_t rank = rest ? (uint32_t)__clzll((long long)rest) + 1u : 64u - HLL_P + 1u;
     if (regs[idx] < rank) atomicMax(&regs[idx], rank);
 }
+__global__ void hll_merge_kernel(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < HLL_M && src[i] > dst[i]) atomicMax(&dst[i], src[i]);
+}
 __device__ __forceinline__ bool hll_sampled(uint64_t h) { return ((uint32_t)h >> 25) == 0; }
 __device__ __forceinline__ void hll_update(uint32_t *regs, uint64_t h, bool valid = true) {
     const bool s = valid && hll_sampled(h);
@@ -697,7 +701,7 @@ constexpr int SCATTER_THREADS = 256, SCATTER_PER = 8, SCATTER_TILE = SCATTER_THR
 // owners' receive buckets over NVLink (po).
 constexpr int BIN_PART = 0, BIN_OWNER = 1;
 template <class K, bool RC, int BINS, bool HLL>
-__global__ void __launch_bounds__(SCATTER_THREADS, 3)
+__global__ void __launch_bounds__(SCATTER_THREADS, BINS == BIN_OWNER ? 4 : 3) // the remote stores need more warps in flight
 scatter_reads_kernel(ReadView v, uint32_t k, Table<K> t, uint32_t n_bins, ScatterOut o,
                      uint32_t *__restrict__ g_regs, PeerOut po) {
     extern __shared__ __align__(16) unsigned char smem[];

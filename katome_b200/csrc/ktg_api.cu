@@ -322,22 +322,29 @@ int ktg_mg_prepare(ktg_builder *b, uint64_t max_windows, void **rx_base, uint64_
 }
 
 int ktg_mg_scatter_reads_device(ktg_builder *b, const void *d_bases, const void *d_offsets, uint64_t n_reads,
-                                uint64_t total_bases, void *const *peer_rx, void **d_cursors) {
+                                uint64_t total_bases, void *const *peer_rx, uint32_t slot, int first_of_batch,
+                                void *send_stream, void **d_cursors) {
     KTG_ENTER(b);
     if (!peer_rx || !d_cursors) return fail(KTG_ERR_INVALID, "null argument");
     return b->impl->mg_scatter_reads((const uint8_t *)d_bases, (const uint64_t *)d_offsets, n_reads, total_bases,
-                                     peer_rx, d_cursors);
+                                     peer_rx, slot, first_of_batch, (cudaStream_t)send_stream, d_cursors);
 }
 
-int ktg_mg_insert_buckets(ktg_builder *b, const void *d_bucket_ends, uint64_t n_keys_estimate) {
+int ktg_mg_insert_buckets(ktg_builder *b, const void *d_bucket_ends, uint64_t n_keys, uint32_t slot) {
     KTG_ENTER(b);
-    return b->impl->mg_insert_buckets(d_bucket_ends, n_keys_estimate);
+    return b->impl->mg_insert_buckets(d_bucket_ends, n_keys, slot);
 }
 
 int ktg_mg_sketch(ktg_builder *b, void **d_regs, uint32_t *n_regs) {
     KTG_ENTER(b);
     if (!d_regs || !n_regs) return fail(KTG_ERR_INVALID, "null argument");
     return b->impl->mg_sketch(d_regs, n_regs);
+}
+
+int ktg_mg_merge_sketch(ktg_builder *b, const void *d_regs) {
+    KTG_ENTER(b);
+    if (!d_regs) return fail(KTG_ERR_INVALID, "null argument");
+    return b->impl->mg_merge_sketch(d_regs);
 }
 
 int ktg_mg_spill(ktg_builder *b, void **d_keys, uint64_t *n) {

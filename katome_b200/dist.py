@@ -86,9 +86,18 @@ class ShardedGIR:
         self.words = self.gir.key_words()
         self.exchanged_bytes = 0
         self._peers: List[int] = []   # receive buffer of every rank, mapped here (own rank: own pointer)
-        self._cap = self._n_sub = 0
+        self._cap = self._slot_bytes = 0
+        self._send_stream = None
+        self._send_group = None
 
     # ---- fused path ------------------------------------------------------------------------
+    # A batch can be sent in several chunks (two receive slots, sender on its own stream) so that the
+    # owner-side work of chunk c overlaps the exchange of chunk c+1.  Measured on 2 B200s it does not
+    # pay (the extra table sweeps and collectives cost more than the overlap gains), so the default
+    # is one chunk; KTG_MG_CHUNKS overrides it.
+    CHUNKS = 1
+    MIN_CHUNK_READS = 1 << 16
+
     def _unmap_peers(self):
         for r, p in enumerate(self._peers):
             if r != self.rank and p:
@@ -96,11 +105,11 @@ class ShardedGIR:
         self._peers = []
 
     def _map_peers(self, gmax: int):
-        """(re)allocate the receive buffer for batches of up to gmax windows per rank and map
-        everybody's buffer; collective."""
+        """(re)allocate the receive buffer (two slots) for chunks of up to gmax windows per rank and
+        map everybody's buffer; collective."""
         self._unmap_peers()
         dist.barrier(self.group)  # nobody still has the old buffer mapped when it is freed
-        base, nbytes, self._cap, self._n_sub = self.gir.mg_prepare(gmax)
+        base, self._slot_bytes, self._cap, _ = self.gir.mg_prepare(gmax)
         mine = torch.frombuffer(bytearray(ipc_get_handle(base)), dtype=torch.uint8).to(self.device)
         allh = [torch.empty_like(mine) for _ in range(self.world)]
         dist.all_gather(allh, mine, group=self.group)
@@ -108,29 +117,79 @@ class ShardedGIR:
                        for r in range(self.world)]
 
     def _add_reads_fused(self, d_bases, d_offsets, n_reads: int, total_bases: int):
-        W, dev = self.world, self.device
-        ub = max(int(total_bases) - int(n_reads) * (self.k - 1), 0)  # windows if every read is accepted
-        t = torch.tensor([ub], dtype=torch.int64, device=dev)
-        # also orders "every rank has finished reading its receive buffer" before anybody writes
+        W, dev, k = self.world, self.device, self.k
+        main = torch.cuda.current_stream()
+        if self._send_stream is None:
+            self._send_stream = torch.cuda.Stream()
+            # a second communicator: collectives of the two streams must not queue behind each other
+            ranks = None if self.group is None else dist.get_process_group_ranks(self.group)
+            self._send_group = dist.new_group(ranks=ranks, backend="nccl")
+        send, sgroup = self._send_stream, self._send_group
+        # chunks of whole reads; the offsets stay absolute (the kernels subtract offsets[chunk start])
+        want = int(os.environ.get("KTG_MG_CHUNKS", self.CHUNKS))  # tuning knob
+        n_chunks = want if n_reads >= want * self.MIN_CHUNK_READS else 1
+        per = -(-n_reads // n_chunks) if n_reads else 0
+        bounds = [min(i * per, n_reads) for i in range(n_chunks + 1)]
+        offs_host = d_offsets[bounds].tolist() if n_reads else [0] * (n_chunks + 1)
+        ubs = [max((offs_host[i + 1] - offs_host[i]) - (bounds[i + 1] - bounds[i]) * (k - 1), 0)
+               for i in range(n_chunks)]  # windows of a chunk if every read is accepted
+        t = torch.tensor([max(ubs), n_chunks], dtype=torch.int64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
-        gmax = int(t.item())
+        gmax, n_chunks_all = (int(x) for x in t.tolist())
         if gmax == 0:
             return
         if not self._peers or self.gir.mg_plan(gmax):
             self._map_peers(gmax)
-        cur_ptr = self.gir.mg_scatter_reads_device(d_bases, d_offsets, n_reads, total_bases, self._peers)
+        cap = self._cap
+        send.wait_stream(main)  # the inputs are ready; the previous batch has been consumed
         sk_ptr, sk_n = self.gir.mg_sketch()
         regs = torch.as_tensor(DeviceArray(sk_ptr, sk_n, "<i4"), device=dev)
-        dist.all_reduce(regs, op=dist.ReduceOp.MAX, group=self.group)  # every shard sizes itself from it
-        cap = self._cap
-        cur = torch.as_tensor(DeviceArray(cur_ptr, W), device=dev)
-        got = torch.empty_like(cur)
-        dist.all_to_all_single(got, cur, group=self.group)  # also: the writers' kernels have completed
-        fill = (got - self.rank * cap).clamp_(max=cap)
-        ends = torch.arange(W, dtype=torch.int64, device=dev) * cap + fill
-        self.gir.mg_insert_buckets(ends, int(fill.sum().item()))
-        self._keep = (ends, got)
-        self.exchanged_bytes += int(ub * 8 * self.words * (W - 1) / W)
+        slot_free = [None, None]   # event: every rank has finished reading that slot
+        sent = [None] * n_chunks_all
+        keep = []
+
+        def send_chunk(c):
+            slot = c % 2
+            if c < n_chunks and bounds[c + 1] > bounds[c]:
+                lo, hi, nbases = bounds[c], bounds[c + 1], offs_host[c + 1] - offs_host[c]
+            else:  # other ranks have more chunks than this one: take part with an empty chunk
+                lo, hi, nbases = 0, 0, 0
+            with torch.cuda.stream(send):
+                if slot_free[slot] is not None:
+                    send.wait_event(slot_free[slot])
+                cur_ptr = self.gir.mg_scatter_reads_device(d_bases, d_offsets[lo:hi + 1], hi - lo, nbases,
+                                                           self._peers, slot, c == 0, send.cuda_stream)
+                cur = torch.as_tensor(DeviceArray(cur_ptr, W), device=dev)
+                got = torch.empty_like(cur)
+                dist.all_to_all_single(got, cur, group=sgroup)  # also: the writers' kernels have completed
+                ev = torch.cuda.Event()
+                ev.record(send)
+            sent[c] = (got, ev, slot)
+
+        def receive_chunk(c):
+            got, ev, slot = sent[c]
+            main.wait_event(ev)
+            tmp = regs.clone()
+            dist.all_reduce(tmp, op=dist.ReduceOp.MAX, group=self.group)  # every shard sizes itself from it
+            self.gir.mg_merge_sketch(tmp)
+            fill = (got - self.rank * cap).clamp_(max=cap)
+            ends = torch.arange(W, dtype=torch.int64, device=dev) * cap + fill
+            self.gir.mg_insert_buckets(ends, int(fill.sum().item()), slot)
+            token = torch.zeros(1, dtype=torch.int32, device=dev)
+            dist.all_reduce(token, group=self.group)  # every rank is done with this slot
+            done = torch.cuda.Event()
+            done.record(main)
+            slot_free[slot] = done
+            keep.append((tmp, ends, got, token))
+
+        for c in range(n_chunks_all):
+            send_chunk(c)
+            if c > 0:
+                receive_chunk(c - 1)
+        receive_chunk(n_chunks_all - 1)
+        main.wait_stream(send)
+        self._keep = keep
+        self.exchanged_bytes += int(sum(ubs) * 8 * self.words * (W - 1) / W)
         # keys that did not fit their bucket (skew): routed the slow way
         sp_ptr, n_sp = self.gir.mg_spill()
         tot = torch.tensor([n_sp], dtype=torch.int64, device=dev)
@@ -142,7 +201,7 @@ class ShardedGIR:
                 torch.empty(0, dtype=torch.int64, device=dev)
             recv, rcounts = exchange_keys(keys, counts, self.words, self.group)
             self.gir.mg_insert_spill(recv, sum(rcounts))
-            self._keep = (ends, got, recv)
+            self._keep = (keep, recv)
 
     def add_reads_device(self, d_bases, d_offsets, n_reads: int, total_bases: int):
         if self.fused:

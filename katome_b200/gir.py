@@ -287,21 +287,26 @@ class GpuGIR:
                                       C.byref(n_sub)))
         return int(base.value), int(nbytes.value), int(cap.value), int(n_sub.value)
 
-    def mg_scatter_reads_device(self, d_bases, d_offsets, n_reads: int, total_bases: int, peer_rx) -> int:
+    def mg_scatter_reads_device(self, d_bases, d_offsets, n_reads: int, total_bases: int, peer_rx, slot: int = 0,
+                                first_of_batch: bool = True, send_stream: Optional[int] = None) -> int:
         """peer_rx: receive buffer pointers of all ranks (own rank included); -> cursors pointer"""
         arr = (C.c_void_p * self.world_size)(*[C.c_void_p(int(p)) for p in peer_rx])
         cur = C.c_void_p()
         _check(self._L.ktg_mg_scatter_reads_device(self._h, _ptr(d_bases), _ptr(d_offsets), int(n_reads),
-                                                   int(total_bases), arr, C.byref(cur)))
+                                                   int(total_bases), arr, int(slot), int(bool(first_of_batch)),
+                                                   C.c_void_p(send_stream or None), C.byref(cur)))
         return int(cur.value)
 
-    def mg_insert_buckets(self, d_bucket_ends, n_keys: int):
-        _check(self._L.ktg_mg_insert_buckets(self._h, _ptr(d_bucket_ends), int(n_keys)))
+    def mg_insert_buckets(self, d_bucket_ends, n_keys: int, slot: int = 0):
+        _check(self._L.ktg_mg_insert_buckets(self._h, _ptr(d_bucket_ends), int(n_keys), int(slot)))
 
     def mg_sketch(self):
         p, n = C.c_void_p(), C.c_uint32()
         _check(self._L.ktg_mg_sketch(self._h, C.byref(p), C.byref(n)))
         return int(p.value), int(n.value)
+
+    def mg_merge_sketch(self, d_regs):
+        _check(self._L.ktg_mg_merge_sketch(self._h, _ptr(d_regs)))
 
     def mg_spill(self):
         p, n = C.c_void_p(), C.c_uint64()
