@@ -261,10 +261,22 @@ template <class K> struct Builder : BuilderBase {
     }
 
     // ---- table geometry ------------------------------------------------------
-    static void geometry(uint64_t need_slots, uint32_t sub_log2_bytes, uint32_t *n_sub,
+    // balance == true (no explicit sub-table size): sub-tables start at 16 MiB (they stay L2
+    // resident for the atomic path) and double until there are no more sub-tables (level-1 bins)
+    // than pages per sub-table (level-2 bins).  A table of P pages then costs two scatter passes
+    // with about sqrt(P) bins each instead of one pass with P / 128 bins, whose runs would shrink
+    // to a few keys (C3: 632 sub-tables made the level-1 scatter 3x slower per key).
+    static void geometry(uint64_t need_slots, uint32_t sub_log2_bytes, bool balance, uint32_t *n_sub,
                          uint32_t *sub_log2) {
         uint32_t slot_log2 = sizeof(Slot) == 16 ? 4 : 5;
         uint32_t sl = sub_log2_bytes - slot_log2; // slots per sub-table (log2)
+        if (balance) {
+            while (sl < 28 && sl > PageGeom<K>::LOG2) {
+                const uint64_t ns = (need_slots + (1ull << sl) - 1) >> sl;
+                if (ns <= 128 || ns <= (1ull << (sl - PageGeom<K>::LOG2))) break;
+                ++sl;
+            }
+        }
         if (need_slots < 1024) need_slots = 1024;
         if (need_slots <= (1ull << sl)) {
             uint32_t l = 10;
@@ -286,7 +298,7 @@ template <class K> struct Builder : BuilderBase {
     int alloc_table(uint64_t need_slots, Table<K> *out, bool do_init) {
         Table<K> t = tab;
         uint32_t slb = cfg.sub_table_log2_bytes ? cfg.sub_table_log2_bytes : 24;
-        geometry(need_slots, slb, &t.n_sub, &t.sub_log2);
+        geometry(need_slots, slb, cfg.sub_table_log2_bytes == 0, &t.n_sub, &t.sub_log2);
         t.sub_mask = (uint32_t)((1ull << t.sub_log2) - 1);
         uint32_t pl = PageGeom<K>::LOG2;
         if (const char *e = getenv("KTG_PAGE_LOG2")) pl = std::min<uint32_t>(pl, std::max(8, atoi(e))); // tuning knob
