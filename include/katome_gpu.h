@@ -158,6 +158,17 @@ int ktg_partition_reads_device(ktg_builder *b, const void *d_bases, const void *
 /* Insert n canonical keys (device pointer, ktg_key_words() u64 each, lo first). */
 int ktg_insert_keys_device(ktg_builder *b, const void *d_keys, uint64_t n);
 
+/* Whole-graph node statistics and standardize_edges of a SHARDED table.  A node's edges may live on
+ * several shards: every shard exports the (canonical (k-1)-mer, degree word) pairs of its own edges
+ * (device arrays owned by the handle; keys are key_words u64 each, lo first), the host routes
+ * them to an owner of its choice (any function of the key) and the owner merges what it received;
+ * node_count / degrees / sources / sinks of the shards then add up (max for the maxima).
+ * standardize_edges: all-reduce the two sums, compute p = (G-k)/(s-l) once, scale every shard. */
+int ktg_nodes_export_device(ktg_builder *b, void **d_keys, void **d_degrees, uint64_t *n, uint32_t *key_words);
+int ktg_nodes_stats_from_device(ktg_builder *b, const void *d_keys, const void *d_degrees, uint64_t n, ktg_stats *out);
+int ktg_edge_sums(ktg_builder *b, uint32_t threshold, uint64_t *sum_w, uint64_t *sum_w_below);
+int ktg_scale_weights(ktg_builder *b, double ratio, uint32_t threshold);
+
 /* Same grouping for an array of keys (the spill list of the fused exchange below). */
 int ktg_partition_keys_device(ktg_builder *b, const void *d_keys, uint64_t n, void **d_out, uint64_t *counts);
 

@@ -30,6 +30,7 @@ SYMBOLS = (
     "ktg_synth_reads_device", "ktg_random_access_probe", "ktg_get_profile", "ktg_reset_profile",
     "ktg_get_info", "ktg_partition_keys_device", "ktg_mg_plan", "ktg_mg_prepare",
     "ktg_mg_scatter_reads_device", "ktg_mg_insert_buckets", "ktg_mg_sketch", "ktg_mg_merge_sketch", "ktg_mg_spill", "ktg_mg_insert_spill", "ktg_ipc_get_handle", "ktg_ipc_open", "ktg_ipc_close",
+    "ktg_nodes_export_device", "ktg_nodes_stats_from_device", "ktg_edge_sums", "ktg_scale_weights",
 )
 
 
@@ -133,5 +134,9 @@ def lib():
     L.ktg_ipc_get_handle.argtypes = [vp, C.c_char_p]
     L.ktg_ipc_open.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.ktg_ipc_close.argtypes = [vp]
+    L.ktg_nodes_export_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), u64p, u32p]
+    L.ktg_nodes_stats_from_device.argtypes = [vp, vp, vp, C.c_uint64, C.POINTER(KtgStats)]
+    L.ktg_edge_sums.argtypes = [vp, C.c_uint32, u64p, u64p]
+    L.ktg_scale_weights.argtypes = [vp, C.c_double, C.c_uint32]
     _lib = L
     return L

@@ -193,6 +193,10 @@ struct BuilderBase {
     virtual int reset() = 0;
     virtual int edge_stats(uint32_t threshold, EdgeStats *out) = 0;
     virtual int node_stats(NodeStats *out) = 0;
+    virtual int nodes_export(void **d_keys, void **d_deg, uint64_t *n, uint32_t *key_words) = 0;
+    virtual int nodes_stats_from(const void *d_keys, const void *d_deg, uint64_t n, NodeStats *out) = 0;
+    virtual int edge_sums(uint32_t threshold, uint64_t *sum_w, uint64_t *sum_below) = 0;
+    virtual int scale_weights(double p, uint32_t t) = 0;
     virtual int remove_weak_edges(uint32_t t) = 0;
     virtual int standardize(uint64_t G, uint64_t k_, uint32_t t) = 0;
     virtual int export_edges(uint64_t *hi, uint64_t *lo, uint32_t *w, uint64_t cap, int sorted,
@@ -255,7 +259,7 @@ template <class K> struct Builder : BuilderBase {
         b_packed.release(); b_bad.release(); b_valid.release(); b_wstart.release(); b_keys.release(); b_keys2.release();
         b_hist.release(); b_hll.release(); b_spill.release(); b_ovf_keys.release(); b_ovf_inc.release(); b_small.release();
         b_pkeys.release(); b_pcur.release(); b_pspill.release(); b_stage_cur.release();
-        b_rx.release(); b_mg_cur.release(); b_mg_spill.release();
+        b_rx.release(); b_mg_cur.release(); b_mg_spill.release(); b_node_keys.release(); b_node_deg.release();
         if (copy_stream) cudaStreamDestroy(copy_stream);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
@@ -1037,13 +1041,10 @@ template <class K> struct Builder : BuilderBase {
         return sync();
     }
 
-    template <class KN> int node_stats_t(NodeStats *out) {
-        KTG_TRY(ensure_init());
-        // distinct canonical nodes <= 2 x live canonical edges
-        uint64_t occ = 0;
-        KTG_TRY(count_occupied(&occ));
+    // an empty node table for up to max_entries canonical (k-1)-mers (the caller frees nt->slots)
+    template <class KN> int make_node_table(uint64_t max_entries, Table<KN> *out) {
         Table<KN> nt{};
-        uint64_t need = (uint64_t)(2.0 * (double)(occ + 1) / 0.8) + 1024;
+        uint64_t need = (uint64_t)((double)(max_entries + 1) / 0.8) + 1024;
         uint32_t l = 10;
         while ((1ull << l) < need) ++l;
         nt.n_sub = 1;
@@ -1071,11 +1072,25 @@ template <class K> struct Builder : BuilderBase {
         prof.begin("init_table", nt.capacity() + 1, stream);
         init_table_kernel<KN><<<props.sms * 8, 256, 0, stream>>>(nt.slots, nt.capacity() + 1);
         prof.end(stream);
+        *out = nt;
+        return KTG_OK;
+    }
+
+    // node table of this shard's edges: prefix and suffix of every (both-strand expanded) edge
+    template <class KN> int build_node_table(Table<KN> *nt) {
+        KTG_TRY(ensure_init());
+        uint64_t occ = 0;
+        KTG_TRY(count_occupied(&occ));
+        KTG_TRY(make_node_table<KN>(2 * occ, nt)); // distinct canonical nodes <= 2 x live canonical edges
         uint64_t n = tab.capacity() + 1;
         prof.begin("build_nodes", n, stream);
-        if (rc) build_nodes_kernel<K, KN, true><<<props.sms * 8, 256, 0, stream>>>(tab.slots, n, k, nt);
-        else build_nodes_kernel<K, KN, false><<<props.sms * 8, 256, 0, stream>>>(tab.slots, n, k, nt);
+        if (rc) build_nodes_kernel<K, KN, true><<<props.sms * 8, 256, 0, stream>>>(tab.slots, n, k, *nt);
+        else build_nodes_kernel<K, KN, false><<<props.sms * 8, 256, 0, stream>>>(tab.slots, n, k, *nt);
         prof.end(stream);
+        return KTG_OK;
+    }
+
+    template <class KN> int node_table_stats(const Table<KN> &nt, NodeStats *out) {
         prof.begin("node_stats", nt.capacity() + 1, stream);
         if (rc) node_stats_kernel<KN, true><<<props.sms * 8, 256, 0, stream>>>(nt.slots, nt.capacity() + 1, (NodeStats *)d_scratch);
         else node_stats_kernel<KN, false><<<props.sms * 8, 256, 0, stream>>>(nt.slots, nt.capacity() + 1, (NodeStats *)d_scratch);
@@ -1083,10 +1098,92 @@ template <class K> struct Builder : BuilderBase {
         unsigned long long host[16];
         KTG_CUDA(cudaMemcpyAsync(host, d_scratch, sizeof host, cudaMemcpyDeviceToHost, stream));
         int rc_ = sync();
-        cudaFree(p);
+        cudaFree(nt.slots);
         KTG_TRY(rc_);
         if (host[15]) return fail(KTG_ERR_TABLE_FULL, "node table overflow (%llu)", host[15]);
         memcpy(out, host, sizeof(NodeStats));
+        return KTG_OK;
+    }
+
+    template <class KN> int node_stats_t(NodeStats *out) {
+        Table<KN> nt{};
+        KTG_TRY(build_node_table<KN>(&nt));
+        return node_table_stats<KN>(nt, out);
+    }
+
+    // ---- nodes of a sharded table: a node's edges may live on several shards -----------------
+    DeviceBuf b_node_keys, b_node_deg;
+    template <class KN> int nodes_export_t(void **d_keys, void **d_deg, uint64_t *n_out) {
+        Table<KN> nt{};
+        KTG_TRY(build_node_table<KN>(&nt));
+        uint64_t occ = 0; // exact number of entries: one more scan, this is not a hot path
+        {
+            KTG_CUDA(cudaMemsetAsync(d_scratch, 0, 8, stream));
+            count_occupied_kernel<KN><<<props.sms * 8, 256, 0, stream>>>(nt.slots, nt.capacity() + 1, d_scratch);
+            unsigned long long v = 0;
+            KTG_CUDA(cudaMemcpyAsync(&v, d_scratch, 8, cudaMemcpyDeviceToHost, stream));
+            int rc_ = sync();
+            if (rc_ != KTG_OK) { cudaFree(nt.slots); return rc_; }
+            occ = v;
+        }
+        int rc_ = b_node_keys.ensure(occ * sizeof(KN) + 64);
+        if (rc_ == KTG_OK) rc_ = b_node_deg.ensure(occ * 4 + 64);
+        if (rc_ != KTG_OK) { cudaFree(nt.slots); return rc_; }
+        KTG_CUDA(cudaMemsetAsync(d_scratch, 0, 8, stream));
+        prof.begin("compact_nodes", nt.capacity() + 1, stream);
+        compact_nodes_kernel<KN><<<props.sms * 8, 256, 0, stream>>>(nt.slots, nt.capacity() + 1, (KN *)b_node_keys.p,
+                                                                    (uint32_t *)b_node_deg.p, d_scratch);
+        prof.end(stream);
+        unsigned long long host[16];
+        KTG_CUDA(cudaMemcpyAsync(host, d_scratch, sizeof host, cudaMemcpyDeviceToHost, stream));
+        rc_ = sync();
+        cudaFree(nt.slots);
+        KTG_TRY(rc_);
+        if (host[15]) return fail(KTG_ERR_TABLE_FULL, "node table overflow (%llu)", host[15]);
+        *d_keys = b_node_keys.p;
+        *d_deg = b_node_deg.p;
+        *n_out = host[0];
+        return KTG_OK;
+    }
+    int nodes_export(void **d_keys, void **d_deg, uint64_t *n, uint32_t *key_words) override {
+        KTG_TRY(finalize());
+        *key_words = k - 1 <= 32 ? 1 : 2;
+        if (k - 1 <= 32) return nodes_export_t<uint64_t>(d_keys, d_deg, n);
+        return nodes_export_t<u128>(d_keys, d_deg, n);
+    }
+    template <class KN> int nodes_stats_from_t(const void *d_keys, const void *d_deg, uint64_t n, NodeStats *out) {
+        Table<KN> nt{};
+        KTG_TRY(make_node_table<KN>(n, &nt));
+        if (n) {
+            prof.begin("merge_nodes", n, stream);
+            merge_nodes_kernel<KN><<<props.sms * 8, 256, 0, stream>>>((const KN *)d_keys, (const uint32_t *)d_deg, n, nt);
+            prof.end(stream);
+        }
+        return node_table_stats<KN>(nt, out);
+    }
+    int nodes_stats_from(const void *d_keys, const void *d_deg, uint64_t n, NodeStats *out) override {
+        if (k - 1 <= 32) return nodes_stats_from_t<uint64_t>(d_keys, d_deg, n, out);
+        return nodes_stats_from_t<u128>(d_keys, d_deg, n, out);
+    }
+
+    // sums behind standardize_edges and the scaling itself, split so that the sums can be
+    // all-reduced over the shards in between (standardizer.rs:42-70,123-127)
+    int edge_sums(uint32_t threshold, uint64_t *sum_w, uint64_t *sum_below) override {
+        EdgeStats es;
+        KTG_TRY(edge_stats(threshold, &es));
+        *sum_w = es.sum_w;
+        *sum_below = es.sum_w_below;
+        return KTG_OK;
+    }
+    int scale_weights(double p, uint32_t t) override {
+        KTG_TRY(finalize());
+        KTG_TRY(ensure_init());
+        uint64_t n = tab.capacity() + 1;
+        prof.begin("standardize", n, stream);
+        standardize_kernel<K><<<props.sms * 8, 256, 0, stream>>>(tab.slots, n, p, t);
+        prof.end(stream);
+        nodes_valid = false;
+        KTG_CUDA(cudaGetLastError());
         return KTG_OK;
     }
 

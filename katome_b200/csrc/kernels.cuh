@@ -1365,6 +1365,40 @@ struct NodeStats {
     unsigned long long nodes, sources, sinks, max_in, max_out;
 };
 
+// (key, degree word) of every occupied node-table entry, warp-aggregated compaction: what a shard
+// sends to the owners of its nodes when the table is sharded over GPUs
+template <class KN>
+__global__ void __launch_bounds__(256)
+compact_nodes_kernel(const typename KeyTraits<KN>::Slot *slots, uint64_t n_slots, KN *__restrict__ out_keys,
+                     uint32_t *__restrict__ out_deg, unsigned long long *cursor) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n_round = (n_slots + 31) & ~(uint64_t)31;
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        const uint32_t w = i < n_slots ? slots[i].w : 0;
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, w != 0);
+        if (m == 0) continue;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(cursor, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (w) {
+            const unsigned long long pos = base + __popc(m & ((1u << lane) - 1u));
+            out_keys[pos] = KeyTraits<KN>::load(&slots[i]);
+            out_deg[pos] = w;
+        }
+    }
+}
+
+// merge (key, degree word) pairs received from all shards: the degree fields are disjoint
+// counters (<= 4 each in total), so adding the words adds the degrees
+template <class KN>
+__global__ void __launch_bounds__(256)
+merge_nodes_kernel(const KN *__restrict__ keys, const uint32_t *__restrict__ deg, uint64_t n, Table<KN> nt) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        table_add(nt, keys[i], deg[i]);
+}
+
 template <class KN, bool RC>
 __global__ void __launch_bounds__(256)
 node_stats_kernel(const typename KeyTraits<KN>::Slot *slots, uint64_t n_slots, NodeStats *out) {

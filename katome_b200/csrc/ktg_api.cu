@@ -241,6 +241,37 @@ int ktg_collection_stats(ktg_builder *b, ktg_stats *out) {
     return KTG_OK;
 }
 
+int ktg_nodes_export_device(ktg_builder *b, void **d_keys, void **d_degrees, uint64_t *n, uint32_t *key_words) {
+    KTG_ENTER(b);
+    if (!d_keys || !d_degrees || !n || !key_words) return fail(KTG_ERR_INVALID, "null argument");
+    return b->impl->nodes_export(d_keys, d_degrees, n, key_words);
+}
+
+int ktg_nodes_stats_from_device(ktg_builder *b, const void *d_keys, const void *d_degrees, uint64_t n, ktg_stats *out) {
+    KTG_ENTER(b);
+    if (!out) return fail(KTG_ERR_INVALID, "null argument");
+    NodeStats ns;
+    KTG_TRY(b->impl->nodes_stats_from(d_keys, d_degrees, n, &ns));
+    memset(out, 0, sizeof *out);
+    out->node_count = ns.nodes;
+    out->max_in_degree = ns.max_in;
+    out->max_out_degree = ns.max_out;
+    out->incoming_vert_count = ns.sources;
+    out->outgoing_vert_count = ns.sinks;
+    return KTG_OK;
+}
+
+int ktg_edge_sums(ktg_builder *b, uint32_t threshold, uint64_t *sum_w, uint64_t *sum_w_below) {
+    KTG_ENTER(b);
+    if (!sum_w || !sum_w_below) return fail(KTG_ERR_INVALID, "null argument");
+    return b->impl->edge_sums(threshold, sum_w, sum_w_below);
+}
+
+int ktg_scale_weights(ktg_builder *b, double ratio, uint32_t threshold) {
+    KTG_ENTER(b);
+    return b->impl->scale_weights(ratio, threshold);
+}
+
 int ktg_remove_weak_edges(ktg_builder *b, uint32_t threshold) {
     KTG_ENTER(b);
     return b->impl->remove_weak_edges(threshold);

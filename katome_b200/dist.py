@@ -234,7 +234,63 @@ class ShardedGIR:
         return self.digest()[1]
 
     def standardize_edges(self, genome_len: int, k: int, t: int):
-        raise NotImplementedError("multi-GPU standardize_edges needs the all-reduced sums (next round)")
+        """standardize_edges (standardizer.rs:42-70,123-127) over all shards: the two sums are
+        all-reduced, every rank computes the same f64 ratio and scales its shard."""
+        s, l = self.gir.edge_sums(t)
+        tot = torch.tensor([s, l], dtype=torch.int64, device=self.device)
+        dist.all_reduce(tot, group=self.group)
+        s, l = (int(x) for x in tot.tolist())
+        if genome_len < k or s == l:
+            from .gir import KatomeError
+            from . import _lib as L
+            raise KatomeError(L.KTG_ERR_DEGENERATE, f"degenerate standardization ratio (G={genome_len} k={k} s={s} l={l})")
+        self.gir.scale_weights(float(genome_len - k) / float(s - l), t)
+
+    # ---- whole-graph statistics ---------------------------------------------------------------
+    @staticmethod
+    def node_owner(keys: torch.Tensor, world: int) -> torch.Tensor:
+        """owner rank of canonical (k-1)-mers given as int64 rows [n, words]; any deterministic
+        function of the key will do (it only decides where a node's degree words are merged)"""
+        def lsr(x, n):  # logical shift right on int64
+            return (x >> n) & ((1 << (64 - n)) - 1)
+        h = keys[:, 0] * -7046029254386353131          # 0x9E3779B97F4A7C15 as int64; wraps
+        if keys.shape[1] == 2:
+            h = h ^ (keys[:, 1] * -4417276706812531889)  # 0xC2B2AE3D27D4EB4F
+        h = h ^ lsr(h, 29)
+        h = h * -4658895280553007687                   # 0xBF58476D1CE4E5B9
+        return (lsr(h, 33) * world) >> 31
+
+    def collection_stats(self) -> dict:
+        """CollectionStats of the whole (sharded) graph, stats/collections.rs:137-208.  Edges are
+        disjoint over the shards; nodes are not, so every shard sends the (node, degree word) pairs
+        of its edges to the node's owner, which merges them."""
+        W, dev = self.world, self.device
+        pk, pd, n, kw = self.gir.nodes_export_device()
+        keys = torch.as_tensor(DeviceArray(pk, n * kw), device=dev).view(n, kw) if n else \
+            torch.empty((0, kw), dtype=torch.int64, device=dev)
+        deg = torch.as_tensor(DeviceArray(pd, n, "<i4"), device=dev) if n else torch.empty(0, dtype=torch.int32, device=dev)
+        own = self.node_owner(keys, W)
+        order = torch.argsort(own)
+        counts = torch.bincount(own, minlength=W).tolist()
+        rk, rcounts = exchange_keys(keys[order].reshape(-1).contiguous(), counts, kw, self.group)
+        rd, _ = exchange_keys(deg[order].contiguous(), counts, 1, self.group, recv_counts=rcounts)
+        st = self.gir.nodes_stats_from_device(rk, rd, sum(rcounts))
+        D, E, S, M = self.digest()
+        sums = torch.tensor([st["node_count"], st["incoming_vert_count"], st["outgoing_vert_count"]],
+                            dtype=torch.int64, device=dev)
+        mx = torch.tensor([st["max_in_degree"], st["max_out_degree"]], dtype=torch.int64, device=dev)
+        dist.all_reduce(sums, group=self.group)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.group)
+        nodes, sources, sinks = (int(x) for x in sums.tolist())
+        return {"node_count": nodes, "edge_count": E, "max_edge_weight": M, "sum_edge_weight": S,
+                "max_in_degree": int(mx[0].item()), "max_out_degree": int(mx[1].item()),
+                "incoming_vert_count": sources, "outgoing_vert_count": sinks,
+                "avg_edge_weight": S / E if E else float("nan"),
+                "avg_out_degree": E / nodes if nodes else float("nan")}
+
+    def counts(self) -> Tuple[int, int]:
+        st = self.collection_stats()
+        return st["node_count"], st["edge_count"]
 
     def close(self):
         if self._peers:

@@ -267,6 +267,26 @@ class GpuGIR:
     def insert_keys_device(self, d_keys, n: int):
         _check(self._L.ktg_insert_keys_device(self._h, _ptr(d_keys), int(n)))
 
+    # ---- whole-graph statistics of a sharded table ---------------------------------------------
+    def nodes_export_device(self):
+        """-> (keys pointer, degree-word pointer, n, u64 words per key) of this shard's nodes"""
+        pk, pd, n, kw = C.c_void_p(), C.c_void_p(), C.c_uint64(), C.c_uint32()
+        _check(self._L.ktg_nodes_export_device(self._h, C.byref(pk), C.byref(pd), C.byref(n), C.byref(kw)))
+        return int(pk.value or 0), int(pd.value or 0), int(n.value), int(kw.value)
+
+    def nodes_stats_from_device(self, d_keys, d_degrees, n: int) -> dict:
+        st = L.KtgStats()
+        _check(self._L.ktg_nodes_stats_from_device(self._h, _ptr(d_keys), _ptr(d_degrees), int(n), C.byref(st)))
+        return {name: int(getattr(st, name)) for name, _ in L.KtgStats._fields_}
+
+    def edge_sums(self, threshold: int):
+        s, l = C.c_uint64(), C.c_uint64()
+        _check(self._L.ktg_edge_sums(self._h, int(threshold), C.byref(s), C.byref(l)))
+        return int(s.value), int(l.value)
+
+    def scale_weights(self, ratio: float, threshold: int):
+        _check(self._L.ktg_scale_weights(self._h, float(ratio), int(threshold)))
+
     def partition_keys_device(self, d_keys, n: int):
         """-> (device pointer of the owner-major copy of the keys, counts per owner)"""
         out = C.c_void_p()

@@ -35,11 +35,19 @@ for k, n, L, G in ((31, 6000, 150, 200_000), (63, 3000, 150, 100_000)):
             sg.add_reads_device(mine[(half // 2) * L:], offs[: half - half // 2 + 1], half - half // 2, (half - half // 2) * L)
             sg.finalize()
             assert sg.digest() == cpu.digest(), (rank, k, kw, sg.digest(), cpu.digest())
+        a, b = sg.collection_stats(), cpu.collection_stats()
+        for key in b:
+            assert a[key] == b[key] or (a[key] != a[key] and b[key] != b[key]), (rank, k, key, a[key], b[key])
+        assert sg.counts() == cpu.counts()
         sg.remove_weak_edges(3)
         cpu2 = O.OracleGIR(k)
         cpu2.add_reads(reads, np.arange(n + 1, dtype=np.uint64) * L, True)
         cpu2.remove_weak_edges(3)
         assert sg.digest() == cpu2.digest()
+        assert sg.counts() == cpu2.counts()
+        sg.standardize_edges(G, k, 3)
+        cpu2.standardize_edges(G, k, 3)
+        assert sg.digest() == cpu2.digest() and sg.counts() == cpu2.counts()
         sg.close()
 dist.destroy_process_group()
 print("rank", rank, "ok")
