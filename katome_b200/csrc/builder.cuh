@@ -722,7 +722,7 @@ template <class K> struct Builder : BuilderBase {
 
     // flat (dense) or bucketed insert with L2 atomics; n_dev: the count lives on the device
     int launch_insert(const K *keys, uint64_t n, const unsigned long long *bin_end, uint64_t bucket_cap,
-                      uint32_t n_bins, const unsigned long long *n_dev = nullptr) {
+                      uint32_t n_bins, const unsigned long long *n_dev = nullptr, bool skip_empty = false) {
         uint64_t tiles_per_bin = bin_end ? bucket_cap / INSERT_TILE : 0;
         uint64_t n_tiles = bin_end ? tiles_per_bin * n_bins : (n + INSERT_TILE - 1) / INSERT_TILE;
         if (n_tiles == 0) return KTG_OK;
@@ -731,7 +731,7 @@ template <class K> struct Builder : BuilderBase {
         g = (int)std::min<uint64_t>(g, n_tiles);
         KTG_CUDA(cudaMemsetAsync(d_scratch + 14, 0, 8, stream)); // the tile counter
         prof.begin("insert_keys", n_dev ? 0 : n, stream);
-        insert_keys_kernel<K><<<g, 256, 0, stream>>>(keys, n, n_dev, d_lost, k, rc && (k % 2 == 0), tab, d_scratch + 14, bin_end,
+        insert_keys_kernel<K><<<g, 256, 0, stream>>>(keys, n, n_dev, d_lost, k, rc && (k % 2 == 0), skip_empty, tab, d_scratch + 14, bin_end,
                                                       bucket_cap, tiles_per_bin, n_tiles);
         prof.end(stream);
         nodes_valid = false;
@@ -774,7 +774,7 @@ template <class K> struct Builder : BuilderBase {
             const size_t sb = (size_t)tile * (sizeof(K) + 4) + (size_t)tab.pages_per_sub() * 32;
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);
             int gg = (int)std::min<uint64_t>(grid_for(kern, threads, sb, props), nt);
-            kern<<<gg, threads, sb, stream>>>(keys1, fill1, cap1, tpb, nt, sub_mod, tab, o);
+            kern<<<gg, threads, sb, stream>>>(keys1, fill1, cap1, tpb, nt, sub_mod, false, tab, o);
         };
         if (variant == 1) launch_v(scatter_buckets_kernel<K, 2, 256, 8, 4>, 256, 8);
         else if (variant == 2) launch_v(scatter_buckets_kernel<K, 2, 512, 4, 3>, 512, 4);
@@ -782,7 +782,7 @@ template <class K> struct Builder : BuilderBase {
         else if (variant == 4) launch_v(scatter_buckets_kernel<K, 2, 256, 16, 2>, 256, 16);
         else {
             int g = (int)std::min<uint64_t>(grid_for(scatter_buckets_kernel<K, 2>, L2S_THREADS, ss, props), n_tiles);
-            scatter_buckets_kernel<K, 2><<<g, L2S_THREADS, ss, stream>>>(keys1, fill1, cap1, tiles_per_bin, n_tiles, sub_mod, tab, o);
+            scatter_buckets_kernel<K, 2><<<g, L2S_THREADS, ss, stream>>>(keys1, fill1, cap1, tiles_per_bin, n_tiles, sub_mod, false, tab, o);
         }
         prof.end(stream);
         int pt = sizeof(K) == 8 ? 704 : 512; // u128 keys need the registers of the smaller block
@@ -1362,13 +1362,21 @@ template <class K> struct Builder : BuilderBase {
     uint64_t mg_cap = 0, mg_spill_cap = 0;
     bool mg_mode = false;
     size_t mg_slot_keys() const { return (size_t)mg_cap * tab.world; }
+    // run padding of the exchange (PeerOut::pad), in keys: 128 bytes, unless all-ones is a real key
+    uint32_t mg_pad() const {
+        if (!rc && 2 * k == 8 * sizeof(K)) return 1;
+        if (getenv("KTG_MG_NOPAD")) return 1; // tuning knob
+        return 128 / sizeof(K);
+    }
     unsigned long long *mg_cursors(uint32_t slot) { return (unsigned long long *)b_mg_cur.p + (size_t)slot * tab.world; }
     unsigned long long *mg_spill_cursor() { return (unsigned long long *)b_mg_cur.p + (size_t)MG_SLOTS * tab.world; }
 
     int mg_geometry(uint64_t max_windows, uint64_t *cap) {
         const uint32_t W = tab.world;
         if (W > (uint32_t)MAX_P2P_WORLD) return fail(KTG_ERR_INVALID, "fused exchange needs world <= %d", MAX_P2P_WORLD);
-        *cap = bucket_cap_for(std::max<uint64_t>(max_windows, 1), W);
+        // every (tile, owner) run may be rounded up by pad - 1 filler keys
+        const uint64_t fillers = (max_windows / SCATTER_TILE + 1) * W * (mg_pad() - 1);
+        *cap = bucket_cap_for(std::max<uint64_t>(max_windows + fillers, 1), W);
         if ((double)*cap * W >= 4.0e9) return fail(KTG_ERR_INVALID, "batch too large: split it (32-bit bucket positions)");
         return KTG_OK;
     }
@@ -1433,6 +1441,7 @@ template <class K> struct Builder : BuilderBase {
         PeerOut po{};
         po.world = W;
         po.bins_per_owner = 1;
+        po.pad = mg_pad();
         // the sender's virtual position is v = owner * cap + fill; bucket `rank` of the owner's
         // slot starts at slot_base + rank * cap, so bias the base by (rank - owner) * cap
         for (uint32_t o = 0; o < W; ++o)
@@ -1466,13 +1475,13 @@ template <class K> struct Builder : BuilderBase {
             const size_t ss = ScatterSmem<K, L2S_TILE>::bytes(n_bins, false);
             int g = (int)std::min<uint64_t>(grid_for(scatter_buckets_kernel<K, 1>, L2S_THREADS, ss, props), n_tiles);
             prof.begin("scatter_received", n_keys, stream);
-            scatter_buckets_kernel<K, 1><<<g, L2S_THREADS, ss, stream>>>(rx, ends, cap, tiles_per_bin, n_tiles, 0, tab, o);
+            scatter_buckets_kernel<K, 1><<<g, L2S_THREADS, ss, stream>>>(rx, ends, cap, tiles_per_bin, n_tiles, 0, mg_pad() > 1, tab, o);
             prof.end(stream);
             return KTG_OK;
         });
         if (st == KTG_ERR_TABLE_FULL + 1000) { // skewed: L2 atomics straight from the receive buckets
             KTG_TRY(flush_staged());
-            KTG_TRY(launch_insert(rx, n_keys, ends, cap, W));
+            KTG_TRY(launch_insert(rx, n_keys, ends, cap, W, nullptr, mg_pad() > 1));
         }
         else KTG_TRY(st);
         KTG_CUDA(cudaGetLastError());
