@@ -586,7 +586,7 @@ template <class K> struct Builder : BuilderBase {
         if (input_consumed) KTG_CUDA(cudaEventRecord(input_consumed, stream));
         prof.begin("check_reads", n_reads, stream);
         {
-            int grid = (int)std::min<uint64_t>((n_reads + 255) / 256, (uint64_t)props.sms * 16);
+            int grid = (int)std::min<uint64_t>((n_reads + 255) / 256, (uint64_t)props.sms * 4);
             check_reads_kernel<<<grid, 256, 0, stream>>>(d_offsets, n_reads, d_bases, k, (const uint32_t *)b_bad.p,
                                                          (uint8_t *)b_valid.p, d_ctr);
         }

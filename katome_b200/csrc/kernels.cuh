@@ -134,11 +134,23 @@ check_reads_kernel(const uint64_t *__restrict__ offsets, uint64_t n_reads,
         }
     }
     block_accumulate<4>(acc, (unsigned long long *)ctr);
+    // one atomic per block (one per warp on a single address was a fixed 50 us per launch)
+    __shared__ unsigned long long s_min, s_max;
+    if (threadIdx.x == 0) {
+        s_min = ~0ull;
+        s_max = 0;
+    }
+    __syncthreads();
     lmax = warp_max(lmax);
     lmin = ~warp_max(~lmin);
     if ((threadIdx.x & 31) == 0) {
-        if (lmax) atomicMax(&ctr->max_len, (unsigned long long)lmax);
-        atomicMin(&ctr->min_len, (unsigned long long)lmin);
+        atomicMax(&s_max, (unsigned long long)lmax);
+        atomicMin(&s_min, (unsigned long long)lmin);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_max) atomicMax(&ctr->max_len, s_max);
+        atomicMin(&ctr->min_len, s_min);
     }
 }
 
@@ -175,26 +187,28 @@ mark_starts_kernel(const uint64_t *__restrict__ offsets, uint64_t n_reads, const
 // warp shuffles (only the last lanes of a warp load them).
 template <class K> struct Roller {
     K fw, rc, mask;
-    u128 nxt; // bases k, k+1, ... of the 96-base span, left aligned
+    uint32_t nxt; // the 16 bases after the first window, left aligned (a work item takes 7 steps)
     uint32_t k, rc_shift;
 
     __device__ __forceinline__ void init(uint64_t w0, uint64_t w1, uint64_t w2, uint32_t k_) {
         k = k_;
         rc_shift = 2 * (k - 1);
+        uint64_t t;
         if (sizeof(K) == 8) {
             mask = k == 32 ? (K)~0ull : (K)((1ull << (2 * k)) - 1);
             fw = (K)(w0 >> (64 - 2 * k));
-            nxt = (((u128)w0 << 64) | w1) << (2 * k);
+            t = k == 32 ? w1 : ((w0 << (2 * k)) | (w1 >> (64 - 2 * k)));
         }
         else {
             mask = k == 64 ? ~(K)0 : (K)((((u128)1) << (2 * k)) - 1);
             fw = (K)((((u128)w0 << 64) | w1) >> (128 - 2 * k));
-            nxt = (((u128)w1 << 64) | w2) << (2 * (k - 32));
+            t = k == 64 ? w2 : ((w1 << (2 * k - 64)) | (w2 >> (128 - 2 * k)));
         }
+        nxt = (uint32_t)(t >> 32);
         rc = revcomp(fw, k);
     }
     __device__ __forceinline__ void step() {
-        uint32_t b = (uint32_t)(nxt >> 126);
+        const uint32_t b = nxt >> 30;
         nxt <<= 2;
         fw = ((fw << 2) | (K)b) & mask;
         rc = (rc >> 2) | ((K)(3u - b) << rc_shift);
@@ -206,13 +220,15 @@ template <class K> struct Roller {
 // into a persistent sketch with atomicMax.  The host sizes / grows the table
 // from the estimate, so no capacity hint is needed (create_fastq starts from
 // T::default(), builder.rs:145) and no pessimistic "every window is new" bound
-// is used.  Only keys whose hash falls in a fixed 1/128 of the hash space are
-// sketched (consistent for duplicates, so distinct(sample) * 128 estimates
-// distinct(all)); the sampled keys are re-mixed so that register index and rank
-// are independent of the bits that place the key in the table.  The warp vote
-// turns the update into a real branch that ~4 of 5 warps skip (as straight-line
-// predicated code it was 20 % of the scatter kernel's instructions).
-constexpr uint32_t HLL_P = 12, HLL_M = 1u << HLL_P, HLL_SAMPLE = 128;
+// is used.  Only keys whose hash falls in a fixed 1/512 of the hash space are
+// sketched (consistent for duplicates, so distinct(sample) * 512 estimates
+// distinct(all); at the smallest table that ever needs an estimate, 1 Mi slots,
+// that is still ~700 samples, and an underestimate only means a replayed overflow);
+// the sampled keys are re-mixed so that register index and rank are independent of
+// the bits that place the key in the table.  The warp vote turns the update into a
+// real branch that most warps skip (as straight-line predicated code it was 20 % of
+// the scatter kernel's instructions).
+constexpr uint32_t HLL_P = 12, HLL_M = 1u << HLL_P, HLL_SAMPLE = 512;
 
 __device__ __forceinline__ void hll_insert(uint32_t *regs, uint64_t h) {
     uint64_t g = fmix64(h ^ 0x9E3779B97F4A7C15ull);
@@ -225,7 +241,7 @@ __global__ void hll_merge_kernel(uint32_t *__restrict__ dst, const uint32_t *__r
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < HLL_M && src[i] > dst[i]) atomicMax(&dst[i], src[i]);
 }
-__device__ __forceinline__ bool hll_sampled(uint64_t h) { return ((uint32_t)h >> 25) == 0; }
+__device__ __forceinline__ bool hll_sampled(uint64_t h) { return ((uint32_t)h >> 23) == 0; } // 1 / HLL_SAMPLE
 __device__ __forceinline__ void hll_update(uint32_t *regs, uint64_t h, bool valid = true) {
     const bool s = valid && hll_sampled(h);
     if (__any_sync(__activemask(), s)) {
@@ -1201,27 +1217,46 @@ __global__ void __launch_bounds__(256)
 edge_stats_kernel(const typename KeyTraits<K>::Slot *slots, uint64_t n_slots, uint32_t k,
                   uint32_t threshold, EdgeStats *out) {
     typedef KeyTraits<K> T;
+    typedef typename T::Slot Slot;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     uint64_t acc[4] = {0, 0, 0, 0}; // edges, sum_w, sum_w_below, digest
     uint64_t mx = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += stride) {
-        uint32_t w = slots[i].w;
-        if (w == 0) continue;
-        K key = T::load(&slots[i]);
-        uint64_t mult = 1;
-        uint64_t d = digest_term(T::hi(key), T::lo(key), w);
-        if (RC) {
-            K r = revcomp(key, k);
-            if (r != key) {
-                mult = 2;
-                d += digest_term(T::hi(r), T::lo(r), w);
+    // whole slots with 16-byte loads, four in flight per thread (a pure HBM stream)
+    constexpr int U = 4;
+    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n_slots; i0 += U * stride) {
+        uint4 v[U], v2[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t i = i0 + u * stride;
+            v[u] = make_uint4(0, 0, 0, 0);
+            v2[u] = make_uint4(0, 0, 0, 0);
+            if (i < n_slots) {
+                v[u] = __ldcs((const uint4 *)&slots[i]);
+                if (sizeof(Slot) == 32) v2[u] = __ldcs((const uint4 *)&slots[i] + 1);
             }
         }
-        acc[0] += mult;
-        acc[1] += mult * w;
-        if (w < threshold) acc[2] += mult * w;
-        acc[3] += d;
-        if (w > mx) mx = w;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t w = sizeof(Slot) == 32 ? v2[u].x : v[u].z;
+            if (w == 0) continue;
+            const uint64_t lo = ((uint64_t)v[u].y << 32) | v[u].x;
+            const uint64_t hi = sizeof(Slot) == 32 ? (((uint64_t)v[u].w << 32) | v[u].z) : 0;
+            const K key = T::make(hi, lo);
+            uint64_t mult = 1;
+            uint64_t d = digest_term(T::hi(key), T::lo(key), w);
+            if (RC) {
+                K r = revcomp(key, k);
+                if (r != key) {
+                    mult = 2;
+                    d += digest_term(T::hi(r), T::lo(r), w);
+                }
+            }
+            acc[0] += mult;
+            acc[1] += mult * w;
+            if (w < threshold) acc[2] += mult * w;
+            acc[3] += d;
+            if (w > mx) mx = w;
+        }
     }
     uint64_t a4[4] = {acc[0], acc[1], acc[2], acc[3]};
     // EdgeStats layout: edges, sum_w, sum_w_below, max_w, digest
