@@ -167,6 +167,13 @@ constexpr double LOAD_MAX = 0.70;        // grow before a batch could exceed thi
 constexpr double LOAD_TARGET = 0.50;     // load right after sizing / growing
 constexpr uint64_t OVF_CAP = 1u << 20;   // replay buffer entries
 
+// What the host batcher already knows about a batch from its host-side offsets.  With it a
+// batch is queued without any host<->device round trip (the counters are read at finalize).
+struct BatchHint {
+    uint32_t ulen = 0;       // every read has this length (0: ragged)
+    uint64_t windows_ub = 0; // windows if every read is accepted
+};
+
 // ------------------------------------------------------------ abstract base
 struct BuilderBase {
     ktg_config cfg{};
@@ -178,6 +185,7 @@ struct BuilderBase {
     DeviceProps props;
     Profiler prof;
     int deferred_error = KTG_OK;
+    uint32_t hint_shift0 = 0; // flat position of the first base of a hinted batch (set by the host batcher)
     // recorded on the compute stream as soon as the pack kernel has consumed the caller's
     // read buffer (the host batcher reuses its staging buffer then, not a whole flush later)
     cudaEvent_t input_consumed = nullptr;
@@ -187,7 +195,7 @@ struct BuilderBase {
     virtual ~BuilderBase() {}
     virtual int init() = 0;
     virtual int ingest_device(const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t n_reads,
-                              uint64_t total_bases) = 0;
+                              uint64_t total_bases, const BatchHint *hint = nullptr) = 0;
     virtual int read_counters(uint64_t *reads, uint64_t *bytes) = 0;
     virtual int finalize() = 0;
     virtual int reset() = 0;
@@ -567,8 +575,17 @@ template <class K> struct Builder : BuilderBase {
     uint64_t windows_seen = 0; // cumulative PackCounters::windows already accounted for
     DeviceBuf b_bad, b_valid, b_wstart;
 
+    bool counters_stale = false; // batches were queued without reading the counters back
+
     int pack(const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t n_reads,
-             uint64_t total_bases, Batch *bt) {
+             uint64_t total_bases, Batch *bt, const BatchHint *hint = nullptr, uint32_t shift0_hint = 0) {
+        if (!hint && counters_stale) { // the per-batch window count below is a difference of totals
+            PackCounters c0;
+            KTG_CUDA(cudaMemcpyAsync(&c0, d_ctr, sizeof c0, cudaMemcpyDeviceToHost, stream));
+            KTG_TRY(sync());
+            windows_seen = c0.windows;
+            counters_stale = false;
+        }
         const uint64_t nw_max = (total_bases + 31 + 31) / 32 + 1; // whatever the alignment of the first base
         KTG_TRY(b_packed.ensure((nw_max + 4) * 8));
         KTG_TRY(b_bad.ensure(nw_max * 4));
@@ -592,14 +609,23 @@ template <class K> struct Builder : BuilderBase {
         }
         prof.end(stream);
         nodes_valid = false;
-        PackCounters c;
-        KTG_CUDA(cudaMemcpyAsync(&c, d_ctr, sizeof c, cudaMemcpyDeviceToHost, stream));
-        KTG_TRY(sync());
-        bt->windows = c.windows - windows_seen;
-        windows_seen = c.windows;
-        if (c.short_reads) { // hm_gir.rs:40: the reference panics, the build is void
-            deferred_error = KTG_ERR_SHORT_READ;
-            return fail(KTG_ERR_SHORT_READ, "Read is too short!");
+        PackCounters c{};
+        if (hint) { // no round trip: an upper bound on the windows is all the staging needs
+            counters_stale = true;
+            bt->windows = hint->windows_ub;
+            c.shift0 = shift0_hint;
+            c.min_len = c.max_len = hint->ulen;
+            if (!hint->ulen) c.max_len = 1; // ragged
+        }
+        else {
+            KTG_CUDA(cudaMemcpyAsync(&c, d_ctr, sizeof c, cudaMemcpyDeviceToHost, stream));
+            KTG_TRY(sync());
+            bt->windows = c.windows - windows_seen;
+            windows_seen = c.windows;
+            if (c.short_reads) { // hm_gir.rs:40: the reference panics, the build is void
+                deferred_error = KTG_ERR_SHORT_READ;
+                return fail(KTG_ERR_SHORT_READ, "Read is too short!");
+            }
         }
         ReadView &v = bt->v;
         v.packed = (const uint64_t *)b_packed.p;
@@ -841,16 +867,18 @@ template <class K> struct Builder : BuilderBase {
             KTG_CUDA(cudaMemsetAsync(b_hll.p, 0, HLL_M * 4, stream));
         }
         const uint32_t n_bins = tab.n_sub;
-        double factor = 1.0;
+        double factor = 0.75; // with host input: flushes small enough to hide under the following copies
         if (const char *e = getenv("KTG_STAGE_FACTOR")) factor = atof(e); // tuning knob
         stage_target = std::min<uint64_t>((uint64_t)(factor * (double)tab.capacity()), stage_max_keys());
         stage_room = batch_keys >= stage_target ? batch_keys : stage_target + batch_keys;
         stage_cap1 = bucket_cap_for(stage_room, n_bins);
-        stage_spill_cap = std::max<uint64_t>(1u << 20, stage_room / 16);
+        // as large as the stage itself: even a batch made of one key cannot overflow it, so a
+        // batch is staged without looking at the spill cursor (it is read when the stage is flushed)
+        stage_spill_cap = stage_room + 64;
         if ((double)stage_cap1 * n_bins >= 4.0e9) return fail(KTG_ERR_INVALID, "batch too large: split it (32-bit bucket positions)");
         KTG_TRY(b_keys.ensure(stage_cap1 * n_bins * sizeof(K) + 64));
         KTG_TRY(b_spill.ensure(stage_spill_cap * sizeof(K) + 64));
-        KTG_TRY(b_stage_cur.ensure(2 * ((size_t)n_bins + 1) * 8));
+        KTG_TRY(b_stage_cur.ensure(((size_t)n_bins + 1) * 8));
         stage_bins = n_bins;
         stage_sub_log2 = tab.sub_log2;
         init_cursors_kernel<<<(n_bins + 255) / 256, 256, 0, stream>>>(stage_cursors(), n_bins, stage_cap1);
@@ -860,16 +888,13 @@ template <class K> struct Builder : BuilderBase {
     }
 
     // Adds one batch to the stage.  `scatter(n_bins, o)` runs the level-1 scatter kernel
-    // (which also feeds the cardinality sketch); `n_keys` is the exact number of keys it
-    // emits.  Returns KTG_ERR_TABLE_FULL + 1000 if the batch is too skewed for the spill
-    // list; the stage is then exactly as before the call and the caller takes the exact path.
+    // (which also feeds the cardinality sketch); `n_keys` is the number of keys it emits (or an
+    // upper bound).  Nothing here waits for the device unless the stage has to be flushed.
     template <class S> int stage_add(uint64_t n_keys, S scatter) {
         if (stage_bins != tab.n_sub || stage_sub_log2 != tab.sub_log2 || staged_keys + n_keys > stage_room) {
             KTG_TRY(flush_staged());
             KTG_TRY(stage_open(n_keys));
         }
-        const size_t cur_bytes = ((size_t)stage_bins + 1) * 8;
-        KTG_CUDA(cudaMemcpyAsync(stage_cursors() + stage_bins + 1, stage_cursors(), cur_bytes, cudaMemcpyDeviceToDevice, stream));
         ScatterOut o;
         o.cursors = stage_cursors();
         o.bucket_cap = stage_cap1;
@@ -878,14 +903,6 @@ template <class K> struct Builder : BuilderBase {
         o.spill_cursor = stage_spill_cursor();
         o.spill_cap = stage_spill_cap;
         KTG_TRY(scatter(stage_bins, o));
-        unsigned long long spilled = 0;
-        KTG_CUDA(cudaMemcpyAsync(&spilled, stage_spill_cursor(), 8, cudaMemcpyDeviceToHost, stream));
-        KTG_TRY(sync());
-        if (spilled > stage_spill_cap) { // roll the stage back; nothing of this batch stays in it
-            KTG_CUDA(cudaMemcpyAsync(stage_cursors(), stage_cursors() + stage_bins + 1, cur_bytes, cudaMemcpyDeviceToDevice, stream));
-            return KTG_ERR_TABLE_FULL + 1000;
-        }
-        staged_spilled = spilled;
         staged_keys += n_keys;
         nodes_valid = false;
         if (staged_keys >= stage_target) KTG_TRY(flush_staged());
@@ -899,8 +916,11 @@ template <class K> struct Builder : BuilderBase {
             return KTG_OK;
         }
         trace("flush", staged_keys);
+        unsigned long long spilled_now = 0;
+        KTG_CUDA(cudaMemcpyAsync(&spilled_now, stage_spill_cursor(), 8, cudaMemcpyDeviceToHost, stream));
         double est = 0;
         KTG_TRY(hll_estimate(&est)); // synchronises the stream
+        staged_spilled = std::min<uint64_t>(spilled_now, stage_spill_cap);
         // fused multi-GPU mode: the sketch was all-reduced, it describes the keys of ALL ranks
         const uint64_t distinct = hll_base + (uint64_t)(est * (mg_mode ? 1.10 / tab.world : 1.08)) + 64;
         occupied_ub = distinct;
@@ -925,14 +945,15 @@ template <class K> struct Builder : BuilderBase {
 
     // ---- one batch of reads, all on the device ---------------------------------------
     int ingest_device(const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t n_reads,
-                      uint64_t total_bases) override {
+                      uint64_t total_bases, const BatchHint *hint = nullptr) override {
         if (deferred_error != KTG_OK) return fail(deferred_error, "build is void after an earlier error");
         if (tab.world > 1)
             return fail(KTG_ERR_INVALID, "world_size > 1: use ktg_partition_reads_device + ktg_insert_keys_device");
         if (n_reads == 0) return KTG_OK;
         Batch bt;
         trace("ingest", n_reads);
-        KTG_TRY(pack(d_bases, d_offsets, n_reads, total_bases, &bt));
+        if (!use_partition()) hint = nullptr; // the direct path sizes the table from the exact counts
+        KTG_TRY(pack(d_bases, d_offsets, n_reads, total_bases, &bt, hint, hint_shift0));
         if (bt.windows == 0) return KTG_OK;
         if (!use_partition()) {
             KTG_TRY(reserve(bt.windows, [&]() -> int {
@@ -959,19 +980,9 @@ template <class K> struct Builder : BuilderBase {
             prof.end(stream);
         }
         else {
-            int st = stage_add(bt.windows, [&](uint32_t n_bins, const ScatterOut &o) -> int {
+            KTG_TRY(stage_add(bt.windows, [&](uint32_t n_bins, const ScatterOut &o) -> int {
                 return scatter_reads_pass<BIN_PART, true>(bt, n_bins, o);
-            });
-            if (st == KTG_ERR_TABLE_FULL + 1000) { // heavy skew: exact two-pass partition, inserted at once
-                KTG_TRY(flush_staged()); // also sizes the table for this batch (it is in the sketch already)
-                const uint32_t n_bins = tab.n_sub;
-                KTG_TRY(hist_reads_pass<false>(bt, n_bins));
-                KTG_TRY(scan_bins_pass(n_bins, 0));
-                KTG_TRY(b_keys2.ensure(bt.windows * sizeof(K) + 64));
-                KTG_TRY((scatter_reads_pass<BIN_PART, false>(bt, n_bins, scatter_out(n_bins, 0, b_keys2.p, nullptr, 0))));
-                KTG_TRY(launch_insert_keys((const K *)b_keys2.p, bt.windows));
-            }
-            else KTG_TRY(st);
+            }));
         }
         KTG_CUDA(cudaGetLastError());
         return KTG_OK;
@@ -984,6 +995,8 @@ template <class K> struct Builder : BuilderBase {
         if (reads) *reads = c.accepted_reads;
         if (bytes) *bytes = c.accepted_bytes;
         windows_inserted = c.windows;
+        windows_seen = c.windows;
+        counters_stale = false;
         if (c.short_reads) {
             deferred_error = KTG_ERR_SHORT_READ;
             return fail(KTG_ERR_SHORT_READ, "Read is too short!");
@@ -1312,14 +1325,10 @@ template <class K> struct Builder : BuilderBase {
             KTG_TRY(launch_insert_keys(keys, n));
         }
         else {
-            int st = stage_add(n, [&](uint32_t n_bins, const ScatterOut &o) -> int {
+            KTG_TRY(stage_add(n, [&](uint32_t n_bins, const ScatterOut &o) -> int {
                 return scatter_keys_pass<false, true>(keys, n, n_bins, o);
-            });
-            if (st == KTG_ERR_TABLE_FULL + 1000) { // skewed: no locality, still exact
-                KTG_TRY(flush_staged());
-                KTG_TRY(launch_insert_keys(keys, n));
-            }
-            else KTG_TRY(st);
+            }));
+            KTG_TRY(sync()); // the caller may reuse its key buffer
         }
         KTG_CUDA(cudaGetLastError());
         return KTG_OK;
@@ -1470,7 +1479,7 @@ template <class K> struct Builder : BuilderBase {
         const uint32_t W = tab.world;
         const uint64_t cap = mg_cap;
         const K *rx = (const K *)b_rx.p + (size_t)slot * mg_slot_keys();
-        int st = stage_add(n_keys, [&](uint32_t n_bins, const ScatterOut &o) -> int {
+        KTG_TRY(stage_add(n_keys, [&](uint32_t n_bins, const ScatterOut &o) -> int {
             const uint64_t tiles_per_bin = cap / L2S_TILE, n_tiles = tiles_per_bin * W;
             const size_t ss = ScatterSmem<K, L2S_TILE>::bytes(n_bins, false);
             int g = (int)std::min<uint64_t>(grid_for(scatter_buckets_kernel<K, 1>, L2S_THREADS, ss, props), n_tiles);
@@ -1478,12 +1487,8 @@ template <class K> struct Builder : BuilderBase {
             scatter_buckets_kernel<K, 1><<<g, L2S_THREADS, ss, stream>>>(rx, ends, cap, tiles_per_bin, n_tiles, 0, mg_pad() > 1, tab, o);
             prof.end(stream);
             return KTG_OK;
-        });
-        if (st == KTG_ERR_TABLE_FULL + 1000) { // skewed: L2 atomics straight from the receive buckets
-            KTG_TRY(flush_staged());
-            KTG_TRY(launch_insert(rx, n_keys, ends, cap, W, nullptr, mg_pad() > 1));
-        }
-        else KTG_TRY(st);
+        }));
+        KTG_TRY(sync()); // the receive slot may be written again
         KTG_CUDA(cudaGetLastError());
         return KTG_OK;
     }

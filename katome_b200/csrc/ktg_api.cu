@@ -144,7 +144,24 @@ int ktg_add_reads(ktg_builder *b, const uint8_t *bases, const uint64_t *offsets,
         trace("copy queued", c);
         return KTG_OK;
     };
+    // What the offsets on the host already tell about a chunk: one read length or ragged, and how
+    // many windows at most; with that the chunk is queued without a device round trip.
+    auto hint_of = [&](size_t c) {
+        BatchHint h;
+        const uint64_t r = cut[c], r1 = cut[c + 1], kk = impl->k, len0 = offsets[r + 1] - offsets[r];
+        bool uniform = true;
+        uint64_t wub = 0;
+        for (uint64_t i = r; i < r1; ++i) {
+            const uint64_t len = offsets[i + 1] - offsets[i];
+            uniform &= len == len0;
+            wub += len >= kk ? len - kk + 1 : 0;
+        }
+        h.ulen = (uniform && len0 <= 0xFFFFFFFFull) ? (uint32_t)len0 : 0;
+        h.windows_ub = wub;
+        return h;
+    };
     KTG_TRY(issue_copy(0));
+    BatchHint next_hint = hint_of(0);
     for (size_t c = 0; c < n_chunks; ++c) {
         if (c + 1 < n_chunks) KTG_TRY(issue_copy(c + 1));
         const uint64_t r = cut[c], r1 = cut[c + 1], nb = offsets[r1] - offsets[r], nr = r1 - r;
@@ -152,10 +169,13 @@ int ktg_add_reads(ktg_builder *b, const uint8_t *bases, const uint64_t *offsets,
         KTG_CUDA(cudaStreamWaitEvent(impl->stream, b->st_ready[s], 0));
         // offsets stay absolute: bias the base pointer instead (pack kernel subtracts offsets[0])
         const uint8_t *d_bases = (const uint8_t *)b->st_bases[s].p - offsets[r];
+        const BatchHint hint = next_hint; // computed while the previous chunk was being queued
+        impl->hint_shift0 = (uint32_t)((uintptr_t)b->st_bases[s].p & 31);
         impl->input_consumed = b->st_free[s];
-        int rc_ = impl->ingest_device(d_bases, (const uint64_t *)b->st_offs[s].p, nr, nb);
+        int rc_ = impl->ingest_device(d_bases, (const uint64_t *)b->st_offs[s].p, nr, nb, &hint);
         impl->input_consumed = nullptr;
         KTG_TRY(rc_);
+        if (c + 1 < n_chunks) next_hint = hint_of(c + 1); // host work hidden behind the queued kernels
     }
     if (accepted_reads || accepted_bytes) {
         uint64_t r1c = 0, b1c = 0;
