@@ -137,6 +137,20 @@ int ktg_standardize_edges(ktg_builder *b, uint64_t genome_len, uint64_t k, uint3
 int ktg_export_edges(ktg_builder *b, uint64_t *key_hi, uint64_t *key_lo, uint32_t *weight,
                      uint64_t cap, int sorted, uint64_t *n);
 
+/* The graph Convert::create_from builds (hm_gir.rs:156-226, hs_gir.rs:205-262), in a canonical
+ * numbering, assembled on the device so that the host only bulk-loads it:
+ *   nodes       the n_nodes distinct (k-1)-mers, sorted ascending (node_hi may be NULL for k <= 33);
+ *               the reference numbers nodes in HashMap iteration order (hm_gir.rs:160-171), which
+ *               is outside the parity contract
+ *   edges       sorted by k-mer; edge e goes from node src[e] (its prefix) to node dst[e] (its
+ *               suffix) with weight[e] -- the (usize, usize, (EdgeSlice, u32)) of graph.add_edge
+ *   edge_bytes  every edge in compress_edge format (compress.rs:250-271), ktg_edge_record_bytes()
+ *               = 1 + ceil(k/4) bytes each: what SEQUENCES holds after kmer_to_edge
+ * n_nodes / n_edges must be the values of ktg_counts; any output pointer may be NULL. */
+int ktg_export_graph(ktg_builder *b, uint64_t *node_hi, uint64_t *node_lo, uint64_t n_nodes, uint64_t *src,
+                     uint64_t *dst, uint32_t *weight, uint8_t *edge_bytes, uint64_t n_edges);
+uint32_t ktg_edge_record_bytes(const ktg_builder *b);
+
 /* Order-independent digest over the expanded edge set:
  * out[0] = sum splitmix64(splitmix64(hi)^lo)*(2w+1), out[1] = |E|,
  * out[2] = sum w, out[3] = max w. */

@@ -30,7 +30,7 @@ SYMBOLS = (
     "ktg_synth_reads_device", "ktg_random_access_probe", "ktg_get_profile", "ktg_reset_profile",
     "ktg_get_info", "ktg_partition_keys_device", "ktg_mg_plan", "ktg_mg_prepare",
     "ktg_mg_scatter_reads_device", "ktg_mg_insert_buckets", "ktg_mg_sketch", "ktg_mg_merge_sketch", "ktg_mg_spill", "ktg_mg_insert_spill", "ktg_ipc_get_handle", "ktg_ipc_open", "ktg_ipc_close",
-    "ktg_nodes_export_device", "ktg_nodes_stats_from_device", "ktg_edge_sums", "ktg_scale_weights",
+    "ktg_export_graph", "ktg_edge_record_bytes", "ktg_nodes_export_device", "ktg_nodes_stats_from_device", "ktg_edge_sums", "ktg_scale_weights",
 )
 
 
@@ -106,6 +106,9 @@ def lib():
     L.ktg_standardize_edges.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint32]
     L.ktg_export_edges.argtypes = [vp, vp, vp, vp, C.c_uint64, C.c_int, u64p]
     L.ktg_digest.argtypes = [vp, u64p]
+    L.ktg_export_graph.argtypes = [vp, vp, vp, C.c_uint64, vp, vp, vp, vp, C.c_uint64]
+    L.ktg_edge_record_bytes.argtypes = [vp]
+    L.ktg_edge_record_bytes.restype = C.c_uint32
     L.ktg_key_words.argtypes = [vp]
     L.ktg_key_words.restype = C.c_uint32
     L.ktg_owner_of.argtypes = [vp, C.c_uint64, C.c_uint64]

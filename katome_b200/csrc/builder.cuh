@@ -43,6 +43,10 @@ inline int fail(int code, const char *fmt, ...) {
         if (ktg_try_rc__ != KTG_OK) return ktg_try_rc__;                                       \
     } while (0)
 
+} // namespace ktg
+#include "export.cuh"
+namespace ktg {
+
 // host-side timeline for tuning (KTG_TRACE=1): label + microseconds since the first event
 inline void trace(const char *label, uint64_t v = 0) {
     static const bool on = getenv("KTG_TRACE") != nullptr;
@@ -209,6 +213,8 @@ struct BuilderBase {
     virtual int standardize(uint64_t G, uint64_t k_, uint32_t t) = 0;
     virtual int export_edges(uint64_t *hi, uint64_t *lo, uint32_t *w, uint64_t cap, int sorted,
                              uint64_t *n) = 0;
+    virtual int export_graph(uint64_t *node_hi, uint64_t *node_lo, uint64_t n_nodes, uint64_t *src, uint64_t *dst,
+                             uint32_t *weight, uint8_t *edge_bytes, uint64_t n_edges) = 0;
     virtual int partition_reads(const uint8_t *d_bases, const uint64_t *d_offsets,
                                 uint64_t n_reads, uint64_t total_bases, void **d_keys,
                                 uint64_t *counts) = 0;
@@ -1241,48 +1247,123 @@ template <class K> struct Builder : BuilderBase {
         return KTG_OK;
     }
 
-    int export_edges(uint64_t *hi, uint64_t *lo, uint32_t *w, uint64_t cap, int sorted,
-                     uint64_t *n_out) override {
+    // both-strand expanded (key, weight) arrays on the device, optionally sorted by k-mer
+    int device_edges(bool sorted, Scratch &sc, KeyArr *keys, uint32_t **weights, uint64_t *n_out) {
         EdgeStats es;
         KTG_TRY(edge_stats(0, &es));
-        uint64_t ne = es.edges;
-        if (n_out) *n_out = ne;
-        uint64_t m = std::min(ne, cap);
-        if (m == 0 || !lo || !w) return KTG_OK;
-        bool wide = T::WORDS == 2;
-        DeviceBuf d_hi, d_lo, d_w;
-        KTG_TRY(d_lo.ensure(ne * 8));
-        KTG_TRY(d_w.ensure(ne * 4));
-        if (wide) KTG_TRY(d_hi.ensure(ne * 8));
+        const uint64_t ne = es.edges;
+        *n_out = ne;
+        const bool wide = T::WORDS == 2;
+        uint64_t *d_hi = nullptr, *d_lo;
+        uint32_t *d_w;
+        KTG_TRY(sc.alloc(&d_lo, ne));
+        KTG_TRY(sc.alloc(&d_w, ne));
+        if (wide) KTG_TRY(sc.alloc(&d_hi, ne));
         KTG_CUDA(cudaMemsetAsync(d_scratch, 0, 8, stream));
-        uint64_t n = tab.capacity() + 1;
+        const uint64_t n = tab.capacity() + 1;
         prof.begin("compact_edges", n, stream);
-        if (rc) compact_edges_kernel<K, true><<<props.sms * 8, 256, 0, stream>>>(tab.slots, n, k, 1, (uint64_t *)d_hi.p, (uint64_t *)d_lo.p, (uint32_t *)d_w.p, ne, d_scratch);
-        else compact_edges_kernel<K, false><<<props.sms * 8, 256, 0, stream>>>(tab.slots, n, k, 1, (uint64_t *)d_hi.p, (uint64_t *)d_lo.p, (uint32_t *)d_w.p, ne, d_scratch);
+        if (rc) compact_edges_kernel<K, true><<<props.sms * 8, 256, 0, stream>>>(tab.slots, n, k, 1, d_hi, d_lo, d_w, ne, d_scratch);
+        else compact_edges_kernel<K, false><<<props.sms * 8, 256, 0, stream>>>(tab.slots, n, k, 1, d_hi, d_lo, d_w, ne, d_scratch);
         prof.end(stream);
-        std::vector<uint64_t> h_hi(wide ? ne : 0), h_lo(ne);
-        std::vector<uint32_t> h_w(ne);
-        KTG_CUDA(cudaMemcpyAsync(h_lo.data(), d_lo.p, ne * 8, cudaMemcpyDeviceToHost, stream));
-        KTG_CUDA(cudaMemcpyAsync(h_w.data(), d_w.p, ne * 4, cudaMemcpyDeviceToHost, stream));
-        if (wide) KTG_CUDA(cudaMemcpyAsync(h_hi.data(), d_hi.p, ne * 8, cudaMemcpyDeviceToHost, stream));
-        int rc_ = sync();
-        d_hi.release(); d_lo.release(); d_w.release();
-        KTG_TRY(rc_);
-        std::vector<uint64_t> perm(ne);
-        for (uint64_t i = 0; i < ne; ++i) perm[i] = i;
-        if (sorted) {
-            std::sort(perm.begin(), perm.end(), [&](uint64_t a, uint64_t b) {
-                if (wide && h_hi[a] != h_hi[b]) return h_hi[a] < h_hi[b];
-                return h_lo[a] < h_lo[b];
-            });
+        keys->hi = d_hi;
+        keys->lo = d_lo;
+        *weights = d_w;
+        if (sorted && ne) {
+            uint32_t *perm;
+            KeyArr s;
+            prof.begin("sort_edges", ne, stream);
+            KTG_TRY(sort_keys(*keys, ne, 2 * k, sc, stream, &perm, &s));
+            uint32_t *w_s;
+            KTG_TRY(sc.alloc(&w_s, ne));
+            gather_kernel<uint32_t><<<export_grid(ne), 256, 0, stream>>>(d_w, perm, w_s, ne);
+            prof.end(stream);
+            *keys = s;
+            *weights = w_s;
         }
-        for (uint64_t i = 0; i < m; ++i) {
-            uint64_t j = perm[i];
-            if (hi) hi[i] = wide ? h_hi[j] : 0;
-            lo[i] = h_lo[j];
-            w[i] = h_w[j];
-        }
+        KTG_CUDA(cudaGetLastError());
         return KTG_OK;
+    }
+
+    int export_edges(uint64_t *hi, uint64_t *lo, uint32_t *w, uint64_t cap, int sorted,
+                     uint64_t *n_out) override {
+        if (!lo || !w || cap == 0) { // size query
+            EdgeStats es;
+            KTG_TRY(edge_stats(0, &es));
+            if (n_out) *n_out = es.edges;
+            return KTG_OK;
+        }
+        Scratch sc;
+        KeyArr keys;
+        uint32_t *d_w;
+        uint64_t ne = 0;
+        KTG_TRY(device_edges(sorted != 0, sc, &keys, &d_w, &ne));
+        if (n_out) *n_out = ne;
+        const uint64_t m = std::min(ne, cap);
+        if (m == 0) return sync();
+        KTG_CUDA(cudaMemcpyAsync(lo, keys.lo, m * 8, cudaMemcpyDeviceToHost, stream));
+        KTG_CUDA(cudaMemcpyAsync(w, d_w, m * 4, cudaMemcpyDeviceToHost, stream));
+        if (hi) {
+            if (keys.hi) KTG_CUDA(cudaMemcpyAsync(hi, keys.hi, m * 8, cudaMemcpyDeviceToHost, stream));
+            else memset(hi, 0, m * 8);
+        }
+        return sync();
+    }
+
+    // The input of Convert::create_from in a canonical numbering (export.cuh): sorted nodes,
+    // sorted edges with the node indices of their prefix and suffix, edges as compress_edge bytes.
+    int export_graph(uint64_t *node_hi, uint64_t *node_lo, uint64_t n_nodes, uint64_t *src, uint64_t *dst,
+                     uint32_t *weight, uint8_t *edge_bytes, uint64_t n_edges) override {
+        Scratch sc;
+        KeyArr edges;
+        uint32_t *d_w;
+        uint64_t ne = 0;
+        KTG_TRY(device_edges(true, sc, &edges, &d_w, &ne));
+        if (ne != n_edges) return fail(KTG_ERR_INVALID, "n_edges is %llu, the graph has %llu edges (ktg_counts)",
+                                       (unsigned long long)n_edges, (unsigned long long)ne);
+        const bool wide_nodes = k - 1 > 32;
+        KeyArr nodes{nullptr, nullptr};
+        uint64_t nn = 0;
+        if (ne) {
+            KeyArr cand{nullptr, nullptr}, cand_sorted;
+            KTG_TRY(sc.alloc(&cand.lo, 2 * ne));
+            if (wide_nodes) KTG_TRY(sc.alloc(&cand.hi, 2 * ne));
+            prof.begin("graph_nodes", ne, stream);
+            split_nodes_kernel<<<export_grid(ne), 256, 0, stream>>>(edges.hi, edges.lo, ne, k, cand.hi, cand.lo);
+            uint32_t *perm;
+            KTG_TRY(sort_keys(cand, 2 * ne, 2 * (k - 1), sc, stream, &perm, &cand_sorted));
+            KTG_TRY(unique_sorted(cand_sorted, 2 * ne, sc, stream, &nodes, &nn));
+            prof.end(stream);
+        }
+        if (nn != n_nodes) return fail(KTG_ERR_INVALID, "n_nodes is %llu, the graph has %llu nodes (ktg_counts)",
+                                       (unsigned long long)n_nodes, (unsigned long long)nn);
+        if (ne == 0) return sync();
+        if (src || dst) {
+            uint64_t *d_src, *d_dst;
+            KTG_TRY(sc.alloc(&d_src, ne));
+            KTG_TRY(sc.alloc(&d_dst, ne));
+            prof.begin("graph_ids", ne, stream);
+            node_ids_kernel<<<export_grid(ne), 256, 0, stream>>>(edges.hi, edges.lo, ne, k, nodes.hi, nodes.lo, nn, d_src, d_dst);
+            prof.end(stream);
+            if (src) KTG_CUDA(cudaMemcpyAsync(src, d_src, ne * 8, cudaMemcpyDeviceToHost, stream));
+            if (dst) KTG_CUDA(cudaMemcpyAsync(dst, d_dst, ne * 8, cudaMemcpyDeviceToHost, stream));
+        }
+        if (edge_bytes) {
+            const size_t rec = (k + 3) / 4 + 1;
+            uint8_t *d_b;
+            KTG_TRY(sc.alloc(&d_b, ne * rec));
+            prof.begin("edge_bytes", ne, stream);
+            edge_bytes_kernel<<<export_grid(ne), 256, 0, stream>>>(edges.hi, edges.lo, ne, k, d_b);
+            prof.end(stream);
+            KTG_CUDA(cudaMemcpyAsync(edge_bytes, d_b, ne * rec, cudaMemcpyDeviceToHost, stream));
+        }
+        if (weight) KTG_CUDA(cudaMemcpyAsync(weight, d_w, ne * 4, cudaMemcpyDeviceToHost, stream));
+        if (node_lo) KTG_CUDA(cudaMemcpyAsync(node_lo, nodes.lo, nn * 8, cudaMemcpyDeviceToHost, stream));
+        if (node_hi) {
+            if (nodes.hi) KTG_CUDA(cudaMemcpyAsync(node_hi, nodes.hi, nn * 8, cudaMemcpyDeviceToHost, stream));
+            else memset(node_hi, 0, nn * 8);
+        }
+        KTG_CUDA(cudaGetLastError());
+        return sync(); // before the scratch buffers are freed
     }
 
     // ---- multi-GPU phases -------------------------------------------------------------------

@@ -313,6 +313,14 @@ int ktg_export_edges(ktg_builder *b, uint64_t *key_hi, uint64_t *key_lo, uint32_
     return b->impl->export_edges(key_hi, key_lo, weight, cap, sorted, n);
 }
 
+int ktg_export_graph(ktg_builder *b, uint64_t *node_hi, uint64_t *node_lo, uint64_t n_nodes, uint64_t *src,
+                     uint64_t *dst, uint32_t *weight, uint8_t *edge_bytes, uint64_t n_edges) {
+    KTG_ENTER(b);
+    return b->impl->export_graph(node_hi, node_lo, n_nodes, src, dst, weight, edge_bytes, n_edges);
+}
+
+uint32_t ktg_edge_record_bytes(const ktg_builder *b) { return b ? (b->impl->k + 3) / 4 + 1 : 0; }
+
 int ktg_digest(ktg_builder *b, uint64_t out[4]) {
     KTG_ENTER(b);
     EdgeStats es;

@@ -233,6 +233,19 @@ class GpuGIR:
         assert n.value == ne
         return hi, lo, w
 
+    def export_graph(self) -> dict:
+        """What Convert::create_from builds (hm_gir.rs:156-226), canonical numbering: sorted
+        nodes, sorted edges as (src index, dst index, weight) and in compress_edge bytes."""
+        nn, ne = self.counts()
+        rec = int(self._L.ktg_edge_record_bytes(self._h))
+        out = {"node_hi": np.zeros(nn, np.uint64), "node_lo": np.zeros(nn, np.uint64),
+               "src": np.zeros(ne, np.uint64), "dst": np.zeros(ne, np.uint64), "weight": np.zeros(ne, np.uint32),
+               "edge_bytes": np.zeros((ne, rec), np.uint8)}
+        _check(self._L.ktg_export_graph(self._h, out["node_hi"].ctypes.data, out["node_lo"].ctypes.data, nn,
+                                        out["src"].ctypes.data, out["dst"].ctypes.data, out["weight"].ctypes.data,
+                                        out["edge_bytes"].ctypes.data, ne))
+        return out
+
     def digest(self) -> Tuple[int, int, int, int]:
         out = (C.c_uint64 * 4)()
         _check(self._L.ktg_digest(self._h, out))

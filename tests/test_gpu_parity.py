@@ -224,6 +224,35 @@ def test_paged_and_atomic_paths_agree_at_scale(K):
     assert res[0] == res[1] and res[0][0][2] == 2 * n * (L - 63 + 1)
 
 
+@pytest.mark.parametrize("k,rc", [(4, True), (31, True), (32, False), (33, True), (34, False), (40, True), (63, True), (64, True)])
+def test_graph_export_for_convert(K, k, rc):
+    """SURVEY 8f-1: the hand-off to Convert::create_from -- sorted node set, edges with the indices
+    of their prefix / suffix nodes, weights, and the edges in compress_edge bytes (compress.rs:250-271)"""
+    from oracle import oracle as O
+    rng = np.random.default_rng(5 * k + rc)
+    genome = "".join(rng.choice(list("ACGT"), size=4000))
+    seqs = H.random_reads(rng, 600, max(k, 50), 140, genome=genome, n_rate=0.02) + ["T" * (k + 9), "ACGT" * 30]
+    cpu = _oracle(seqs, k, rc)
+    g = K.GpuGIR(k, rc)
+    g.add_reads(*H.batch_of(seqs))
+    out = g.export_graph()
+    nhi, nlo = cpu.export_nodes()
+    ehi, elo, ew = cpu.export_edges()
+    assert np.array_equal(out["node_hi"], nhi) and np.array_equal(out["node_lo"], nlo)
+    assert np.array_equal(out["weight"], ew)
+    nodes = [(int(h) << 64) | int(l) for h, l in zip(nhi.tolist(), nlo.tolist())]
+    index = {v: i for i, v in enumerate(nodes)}
+    mask = (1 << (2 * (k - 1))) - 1
+    for e, (h, l) in enumerate(zip(ehi.tolist(), elo.tolist())):
+        edge = (h << 64) | l
+        assert out["src"][e] == index[edge >> 2] and out["dst"][e] == index[edge & mask]
+        if e % 7 == 0:  # the byte string of every 7th edge against the oracle's compress_edge
+            text = "".join("ACGT"[(edge >> (2 * (k - 1 - j))) & 3] for j in range(k)).encode()
+            assert bytes(out["edge_bytes"][e]) == O.compress_edge(text)
+    assert O.compress_edge(b"AGGTCG") == bytes([2, 0b00101011, 0b01100000])  # compress.rs:244-248
+    g.close()
+
+
 def test_all_T_at_full_key_width_without_canonicalisation(K):
     """k=32 / k=64, reverse_complement=false: TTT...T equals the all-ones 'empty' marker"""
     for k in (32, 64):
