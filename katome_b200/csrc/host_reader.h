@@ -17,6 +17,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <cuda_runtime.h>
 #include <limits.h>
 #include <string>
 #include <sys/stat.h>
@@ -24,27 +26,65 @@
 
 namespace ktg {
 
+// One batch of raw sequences.  The bases live in pinned host memory when it can be had, so
+// that ktg_add_reads copies them at PCIe speed and asynchronously.
 struct ReadBatch {
-    std::vector<uint8_t> bases;
+    uint8_t *bases = nullptr;
+    size_t size = 0, cap = 0;
+    bool pinned = false;
     std::vector<uint64_t> offsets; // n_reads + 1
+    ReadBatch() = default;
+    ReadBatch(const ReadBatch &) = delete;
+    ReadBatch &operator=(const ReadBatch &) = delete;
+    ~ReadBatch() { release(); }
     uint64_t n_reads() const { return offsets.empty() ? 0 : offsets.size() - 1; }
+    void release() {
+        if (bases) {
+            if (pinned) cudaFreeHost(bases);
+            else free(bases);
+        }
+        bases = nullptr;
+        size = cap = 0;
+    }
+    bool reserve(size_t want) {
+        if (want <= cap) return true;
+        size_t ncap = cap ? cap : (1u << 20);
+        while (ncap < want) ncap *= 2;
+        uint8_t *nb = nullptr;
+        bool np = cudaHostAlloc((void **)&nb, ncap, cudaHostAllocDefault) == cudaSuccess;
+        if (!np) {
+            (void)cudaGetLastError();
+            nb = (uint8_t *)malloc(ncap);
+            if (!nb) return false;
+        }
+        if (size) memcpy(nb, bases, size);
+        const size_t keep = size;
+        release();
+        bases = nb;
+        cap = ncap;
+        size = keep;
+        pinned = np;
+        return true;
+    }
     void clear() {
-        bases.clear();
+        size = 0;
         offsets.clear();
         offsets.push_back(0);
     }
-    void push(const char *s, size_t n) {
-        bases.insert(bases.end(), (const uint8_t *)s, (const uint8_t *)s + n);
-        offsets.push_back(bases.size());
+    bool append(const char *s, size_t n) { // part of the current read
+        if (size + n > cap && !reserve(size + n)) return false;
+        memcpy(bases + size, s, n);
+        size += n;
+        return true;
     }
+    void end_read() { offsets.push_back(size); }
 };
 
 class ReadFile {
   public:
     ~ReadFile() {
         if (f_) fclose(f_);
-        free(line_);
-        free(aux_);
+        free(buf_);
     }
 
     // check_files: canonicalize, reject directories and missing files
@@ -68,6 +108,7 @@ class ReadFile {
             *why = std::string("Couldn't open all files: ") + real;
             return false;
         }
+        setvbuf(f_, nullptr, _IONBF, 0); // we do our own (large) buffering
         fasta_ = fasta;
         return true;
     }
@@ -76,6 +117,10 @@ class ReadFile {
     // Returns 1 if more records may follow, 0 at end of file, -1 on a malformed record.
     int next_batch(ReadBatch *out, size_t max_bytes, std::string *why) {
         out->clear();
+        if (!out->reserve(max_bytes + (1u << 16))) {
+            *why = "out of host memory";
+            return -1;
+        }
         return fasta_ ? next_fasta(out, max_bytes, why) : next_fastq(out, max_bytes, why);
     }
 
@@ -89,22 +134,59 @@ class ReadFile {
         return n;
     }
 
+    // Next line (with its newline, like getline) as a view into the block buffer; false at end of
+    // file.  Lines are found with memchr over 8 MiB blocks instead of one getline call per line.
+    bool next_line(const char **p, size_t *n) {
+        for (;;) {
+            if (pos_ < end_) {
+                const char *nl = (const char *)memchr(buf_ + pos_, '\n', end_ - pos_);
+                if (nl) {
+                    *p = buf_ + pos_;
+                    *n = (size_t)(nl - (buf_ + pos_)) + 1;
+                    pos_ += *n;
+                    return true;
+                }
+                if (eof_) { // last line without a newline
+                    *p = buf_ + pos_;
+                    *n = end_ - pos_;
+                    pos_ = end_;
+                    return true;
+                }
+            }
+            else if (eof_) return false;
+            // keep the partial line, refill behind it
+            const size_t keep = end_ - pos_;
+            if (keep && pos_) memmove(buf_, buf_ + pos_, keep);
+            pos_ = 0;
+            end_ = keep;
+            if (end_ + BLOCK > bcap_) {
+                bcap_ = end_ + BLOCK;
+                buf_ = (char *)realloc(buf_, bcap_);
+            }
+            const size_t got = fread(buf_ + end_, 1, BLOCK, f_);
+            end_ += got;
+            if (got < BLOCK) eof_ = true;
+        }
+    }
+
     int next_fastq(ReadBatch *out, size_t max_bytes, std::string *why) {
-        while (out->bases.size() < max_bytes) {
-            ssize_t lh = getline(&line_, &cap_, f_);
-            if (lh <= 0) return 0;
-            if (line_[0] != '@') {
+        const char *p;
+        size_t n;
+        while (out->size < max_bytes) {
+            if (!next_line(&p, &n) || n == 0) return 0;
+            if (p[0] != '@') {
                 *why = "Expected @ at record start.";
                 return -1;
             }
-            ssize_t ls = getline(&line_, &cap_, f_);
-            if (ls < 0) ls = 0;
-            size_t len = rtrim(line_, (size_t)ls);
-            out->push(line_, len);
-            ssize_t lp = getline(&aux_, &aux_cap_, f_);
-            (void)lp;
-            ssize_t lq = getline(&aux_, &aux_cap_, f_);
-            if (lq <= 0) {
+            if (next_line(&p, &n)) {
+                if (!out->append(p, rtrim(p, n))) {
+                    *why = "out of host memory";
+                    return -1;
+                }
+            }
+            out->end_read();
+            next_line(&p, &n); // the '+' line is not looked at (rust-bio 0.10 reads and drops it)
+            if (!next_line(&p, &n) || n == 0) {
                 *why = "Incomplete record. Each FastQ record has to consist of 4 lines.";
                 return -1;
             }
@@ -114,33 +196,35 @@ class ReadFile {
 
     int next_fasta(ReadBatch *out, size_t max_bytes, std::string *why) {
         if (!primed_) {
-            have_ = getline(&line_, &cap_, f_);
+            have_ = next_line(&line_, &line_n_);
             primed_ = true;
         }
-        while (out->bases.size() < max_bytes) {
-            if (have_ <= 0) return 0;
+        while (out->size < max_bytes) {
+            if (!have_ || line_n_ == 0) return 0;
             if (line_[0] != '>') {
                 *why = "Expected > at record start.";
                 return -1;
             }
-            size_t start = out->bases.size();
             for (;;) {
-                have_ = getline(&line_, &cap_, f_);
-                if (have_ <= 0 || line_[0] == '>') break;
-                size_t m = rtrim(line_, (size_t)have_);
-                out->bases.insert(out->bases.end(), (const uint8_t *)line_, (const uint8_t *)line_ + m);
+                have_ = next_line(&line_, &line_n_);
+                if (!have_ || line_n_ == 0 || line_[0] == '>') break;
+                if (!out->append(line_, rtrim(line_, line_n_))) {
+                    *why = "out of host memory";
+                    return -1;
+                }
             }
-            (void)start;
-            out->offsets.push_back(out->bases.size());
+            out->end_read();
         }
         return 1;
     }
 
+    static constexpr size_t BLOCK = 8u << 20;
     FILE *f_ = nullptr;
-    bool fasta_ = false, primed_ = false;
-    char *line_ = nullptr, *aux_ = nullptr;
-    size_t cap_ = 0, aux_cap_ = 0;
-    ssize_t have_ = 0;
+    bool fasta_ = false, primed_ = false, eof_ = false, have_ = false;
+    char *buf_ = nullptr;
+    size_t bcap_ = 0, pos_ = 0, end_ = 0;
+    const char *line_ = nullptr;
+    size_t line_n_ = 0;
 };
 
 } // namespace ktg

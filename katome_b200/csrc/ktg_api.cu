@@ -200,19 +200,36 @@ int ktg_create_from_files(ktg_builder *b, const char *const *paths, uint32_t n_p
         if (!f->open(paths[i], file_type == KTG_FASTA, &why)) return fail(KTG_ERR_IO, "%s", why.c_str());
         files.push_back(std::move(f));
     }
-    ReadBatch batch;
+    // Two pinned batches: the parser fills one while the copy / kernels of the other are in flight.
+    ReadBatch batch[2];
+    cudaEvent_t copied[2] = {nullptr, nullptr};
+    int cur = 0, rc_ = KTG_OK;
     for (auto &f : files) {
         for (;;) {
+            if (copied[cur]) { // the previous contents of this batch must have left the host
+                cudaEventSynchronize(copied[cur]);
+            }
             std::string why;
-            int st = f->next_batch(&batch, 64u << 20, &why);
-            if (st < 0) return fail(KTG_ERR_BAD_RECORD, "%s", why.c_str());
-            if (batch.n_reads())
-                KTG_TRY(ktg_add_reads(b, batch.bases.data(), batch.offsets.data(), batch.n_reads(), nullptr, nullptr));
-            // the pageable staging vectors are reused by the next batch
-            KTG_CUDA(cudaStreamSynchronize(b->impl->copy_stream));
+            int st = f->next_batch(&batch[cur], 64u << 20, &why);
+            if (st < 0) {
+                rc_ = fail(KTG_ERR_BAD_RECORD, "%s", why.c_str());
+                break;
+            }
+            if (batch[cur].n_reads()) {
+                rc_ = ktg_add_reads(b, batch[cur].bases, batch[cur].offsets.data(), batch[cur].n_reads(), nullptr, nullptr);
+                if (rc_ != KTG_OK) break;
+                if (!copied[cur]) cudaEventCreateWithFlags(&copied[cur], cudaEventDisableTiming);
+                cudaEventRecord(copied[cur], b->impl->copy_stream);
+                cur ^= 1;
+            }
             if (st == 0) break;
         }
+        if (rc_ != KTG_OK) break;
     }
+    cudaStreamSynchronize(b->impl->copy_stream); // the batches are freed below
+    for (int i = 0; i < 2; ++i)
+        if (copied[i]) cudaEventDestroy(copied[i]);
+    KTG_TRY(rc_);
     KTG_TRY(b->impl->read_counters(&reads, &bytes));
     if (total_bytes) *total_bytes = bytes;
     return ktg_finalize(b);
