@@ -412,6 +412,9 @@ template <class K> struct Builder : BuilderBase {
         allow_smem(update_pages_kernel<K, 512>, page_smem_bytes(512));
         allow_smem(update_pages_kernel<K, 640>, page_smem_bytes(640));
         allow_smem(update_pages_kernel<K, 704>, page_smem_bytes(704));
+        allow_smem(update_pages_kernel<K, 704, 2>, page_smem_bytes(704));
+        allow_smem(update_pages_kernel<K, 704, 6>, page_smem_bytes(704));
+        allow_smem(update_pages_kernel<K, 704, 8>, page_smem_bytes(704));
         allow_smem(scatter_reads_kernel<K, true, BIN_PART, true>, mx);
         allow_smem(scatter_reads_kernel<K, false, BIN_PART, true>, mx);
         allow_smem(scatter_reads_kernel<K, true, BIN_PART, false>, mx);
@@ -798,7 +801,9 @@ template <class K> struct Builder : BuilderBase {
         o.spill_cap = spill_cap;
         const uint64_t tiles_per_bin = cap1 / L2S_TILE, n_tiles = tiles_per_bin * n_bins;
         const size_t ss = ScatterSmem<K, L2S_TILE>::bytes(tab.pages_per_sub(), false);
-        int variant = 0;
+        // 256-thread CTAs (four per SM) overlap the phases of a tile better than 512-thread ones
+        // (1.51 vs 1.60 ms on C2); u128 keys need the registers of the larger block
+        int variant = sizeof(K) == 8 ? 1 : 0;
         if (const char *e = getenv("KTG_L2S_VARIANT")) variant = atoi(e); // tuning knob
         prof.begin("scatter_pages", n_keys, stream);
         auto launch_v = [&](auto kern, int threads, int per) {
@@ -826,7 +831,12 @@ template <class K> struct Builder : BuilderBase {
             int g = (int)std::min<uint64_t>(grid_for(kern, threads, ps, props), n_pages);
             kern<<<g, threads, ps, stream>>>((const K *)b_pkeys.p, cur2, cap2, k, palin, special, tab, fresh);
         };
-        if (pt == 640) launch_p(update_pages_kernel<K, 640>, 640);
+        int pu = 4;
+        if (const char *e = getenv("KTG_PAGE_UNROLL")) pu = atoi(e); // tuning knob: 2, 4, 6, 8 (704 threads)
+        if (pt == 704 && pu == 2) launch_p(update_pages_kernel<K, 704, 2>, 704);
+        else if (pt == 704 && pu == 6) launch_p(update_pages_kernel<K, 704, 6>, 704);
+        else if (pt == 704 && pu == 8) launch_p(update_pages_kernel<K, 704, 8>, 704);
+        else if (pt == 640) launch_p(update_pages_kernel<K, 640>, 640);
         else if (pt == 704) launch_p(update_pages_kernel<K, 704>, 704);
         else launch_p(update_pages_kernel<K, 512>, 512);
         prof.end(stream);
@@ -1561,10 +1571,11 @@ template <class K> struct Builder : BuilderBase {
         const uint64_t cap = mg_cap;
         const K *rx = (const K *)b_rx.p + (size_t)slot * mg_slot_keys();
         KTG_TRY(stage_add(n_keys, [&](uint32_t n_bins, const ScatterOut &o) -> int {
+            prof.begin("scatter_received", n_keys, stream);
+            // (the 256-thread tile that wins for level 2 is slower here: 1.97 vs 1.62 ms)
             const uint64_t tiles_per_bin = cap / L2S_TILE, n_tiles = tiles_per_bin * W;
             const size_t ss = ScatterSmem<K, L2S_TILE>::bytes(n_bins, false);
             int g = (int)std::min<uint64_t>(grid_for(scatter_buckets_kernel<K, 1>, L2S_THREADS, ss, props), n_tiles);
-            prof.begin("scatter_received", n_keys, stream);
             scatter_buckets_kernel<K, 1><<<g, L2S_THREADS, ss, stream>>>(rx, ends, cap, tiles_per_bin, n_tiles, 0, mg_pad() > 1, tab, o);
             prof.end(stream);
             return KTG_OK;

@@ -1018,7 +1018,7 @@ __device__ __forceinline__ void smem_to_slot(KeyTraits<u128>::Slot *g, const u12
     ((uint4 *)g)[1] = make_uint4(*sw, 0u, 0u, 0u);
 }
 
-template <class K, int THREADS>
+template <class K, int THREADS, int PAGE_UNROLL = ktg::PAGE_UNROLL>
 __global__ void __launch_bounds__(THREADS, 2)
 update_pages_kernel(const K *__restrict__ keys2, const unsigned long long *__restrict__ cursors2,
                     uint64_t cap2, uint32_t k, bool check_palindrome, bool has_special, Table<K> t, bool fresh) {
