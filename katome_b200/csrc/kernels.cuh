@@ -735,7 +735,7 @@ constexpr int SCATTER_THREADS = 256, SCATTER_PER = 8, SCATTER_TILE = SCATTER_THR
 // owners' receive buckets over NVLink (po).
 constexpr int BIN_PART = 0, BIN_OWNER = 1;
 template <class K, bool RC, int BINS, bool HLL>
-__global__ void __launch_bounds__(SCATTER_THREADS, BINS == BIN_OWNER ? 4 : 3) // the remote stores need more warps in flight
+__global__ void __launch_bounds__(SCATTER_THREADS, (BINS == BIN_OWNER || sizeof(K) == 8) ? 4 : 3)
 scatter_reads_kernel(ReadView v, uint32_t k, Table<K> t, uint32_t n_bins, ScatterOut o,
                      uint32_t *__restrict__ g_regs, PeerOut po) {
     extern __shared__ __align__(16) unsigned char smem[];
