@@ -212,12 +212,9 @@ def run_ours(args):
                 g.add_reads_host_ptr(h_bases.data_ptr(), h_offs.data_ptr(), n_local)
                 return g.digest()
         else:
-            stage = torch.empty_like(d_bases)
             def estep():
                 sg.reset()
-                stage[: n_local * L].copy_(h_bases, non_blocking=True)
-                so = h_offs.to(dev, non_blocking=True)
-                sg.add_reads_device(stage, so, n_local, n_local * L)
+                sg.add_reads_host(h_bases, h_offs, n_local)
                 return sg.digest()
         estep()
         barrier()

@@ -89,6 +89,8 @@ class ShardedGIR:
         self._cap = self._slot_bytes = 0
         self._send_stream = None
         self._send_group = None
+        self._copy_stream = None
+        self._stage = None
 
     # ---- fused path ------------------------------------------------------------------------
     # A batch can be sent in several chunks (two receive slots, sender on its own stream) so that the
@@ -202,6 +204,50 @@ class ShardedGIR:
             recv, rcounts = exchange_keys(keys, counts, self.words, self.group)
             self.gir.mg_insert_spill(recv, sum(rcounts))
             self._keep = (keep, recv)
+
+    def add_reads_host(self, h_bases: torch.Tensor, h_offsets: torch.Tensor, n_reads: int, chunks: int = 4):
+        """Reads in (pinned) host memory: h_bases uint8, h_offsets int64 [n_reads + 1].  The batch is
+        copied in chunks on a copy stream, chunk i+1 while chunk i is exchanged and inserted."""
+        dev, main = self.device, torch.cuda.current_stream()
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+        copy = self._copy_stream
+        offs = h_offsets[: n_reads + 1]
+        n_chunks = max(1, min(chunks, n_reads // self.MIN_CHUNK_READS)) if n_reads else 1
+        per = -(-n_reads // n_chunks) if n_reads else 0
+        bounds = [min(i * per, n_reads) for i in range(n_chunks + 1)]
+        ob = [int(offs[b]) for b in bounds]
+        max_b = max(ob[i + 1] - ob[i] for i in range(n_chunks)) + 64
+        max_r = max(bounds[i + 1] - bounds[i] for i in range(n_chunks)) + 1
+        if self._stage is None or self._stage[0][0].numel() < max_b or self._stage[0][1].numel() < max_r:
+            torch.cuda.synchronize()
+            self._stage = [(torch.empty(max_b, dtype=torch.uint8, device=dev),
+                            torch.empty(max_r, dtype=torch.int64, device=dev)) for _ in range(2)]
+            self._stage_ev = [[torch.cuda.Event(), torch.cuda.Event()] for _ in range(2)]  # (ready, free)
+            self._stage_used = [False, False]
+
+        def issue(c):
+            s = c & 1
+            lo, hi = bounds[c], bounds[c + 1]
+            with torch.cuda.stream(copy):
+                if self._stage_used[s]:
+                    copy.wait_event(self._stage_ev[s][1])
+                self._stage[s][0][: ob[c + 1] - ob[c]].copy_(h_bases[ob[c]: ob[c + 1]], non_blocking=True)
+                self._stage[s][1][: hi - lo + 1].copy_(offs[lo: hi + 1], non_blocking=True)
+                self._stage_ev[s][0].record(copy)
+
+        issue(0)
+        for c in range(n_chunks):
+            if c + 1 < n_chunks:
+                issue(c + 1)
+            s = c & 1
+            lo, hi = bounds[c], bounds[c + 1]
+            main.wait_event(self._stage_ev[s][0])
+            # the offsets stay absolute: bias the base pointer instead
+            self.add_reads_device(int(self._stage[s][0].data_ptr()) - ob[c], self._stage[s][1][: hi - lo + 1],
+                                  hi - lo, ob[c + 1] - ob[c])
+            self._stage_ev[s][1].record(main)
+            self._stage_used[s] = True
 
     def add_reads_device(self, d_bases, d_offsets, n_reads: int, total_bases: int):
         if self.fused:

@@ -35,6 +35,14 @@ for k, n, L, G in ((31, 6000, 150, 200_000), (63, 3000, 150, 100_000)):
             sg.add_reads_device(mine[(half // 2) * L:], offs[: half - half // 2 + 1], half - half // 2, (half - half // 2) * L)
             sg.finalize()
             assert sg.digest() == cpu.digest(), (rank, k, kw, sg.digest(), cpu.digest())
+        # the same reads from pinned host memory, copied in chunks behind the exchange
+        sg.reset()
+        hb = torch.from_numpy(reads[rank * half * L:(rank + 1) * half * L].copy()).pin_memory()
+        ho = torch.arange(0, (half + 1) * L, L, dtype=torch.int64).pin_memory()
+        sg.MIN_CHUNK_READS = 500
+        sg.add_reads_host(hb, ho, half, chunks=3)
+        sg.finalize()
+        assert sg.digest() == cpu.digest(), (rank, k, kw, "host path")
         a, b = sg.collection_stats(), cpu.collection_stats()
         for key in b:
             assert a[key] == b[key] or (a[key] != a[key] and b[key] != b[key]), (rank, k, key, a[key], b[key])
