@@ -510,3 +510,42 @@ def test_full_size_properties(K):
     g2.remove_weak_edges(2)
     g2.remove_weak_edges(3)
     assert g2.digest() == d3
+
+
+def test_baseline_config2_full_size(K):
+    """BASELINE config 2 at its full size (4.6 Mbp, 100 bp, 100x, 0.5 % errors, k=31: 322 M windows),
+    far beyond what the oracle can run: size-independent properties only."""
+    from katome_b200.workloads import C2 as wl
+    n, L = wl.n_reads, wl.read_len
+    d = torch.empty(n * L + 64, dtype=torch.uint8, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    K.synth_reads_device(d, wl.seed, wl.genome_len, L, wl.err_ppm, 0, n, stream=s)
+    offs = torch.arange(0, (n + 1) * L, L, dtype=torch.int64, device="cuda")
+    g = K.GpuGIR(wl.k, True, stream=s)  # no capacity hint: sized from the sketch
+    assert g.add_reads_device(d, offs, n, n * L, want_counts=True) == (n, n * L)
+    D, E, S, M = g.digest()
+    assert S == 2 * wl.n_windows                      # every window adds 1 to each strand
+    assert 0.8 * wl.expected_distinct_edges() < E < 1.1 * wl.expected_distinct_edges()  # 97.7 M of ~109 M predicted
+    assert g.info()["page_updates"] >= 1
+    # the same reads in three uneven batches through L2 atomics only: identical table
+    g2 = K.GpuGIR(wl.k, True, stream=s, no_pages=True, edges_count=wl.expected_distinct_edges())
+    cuts = [0, n // 7, n // 2, n]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        g2.add_reads_device(d[a * L:], offs[: b - a + 1], b - a, (b - a) * L)
+    assert g2.digest() == (D, E, S, M) and g2.info()["page_updates"] == 0
+    # reverse_complement = false: the windows of one strand only
+    g3 = K.GpuGIR(wl.k, False, stream=s)
+    g3.add_reads_device(d, offs, n, n * L)
+    assert g3.digest()[2] == wl.n_windows
+    g3.close()
+    # filter: idempotent, monotone, and what survives is what the weights say
+    g.remove_weak_edges(5)
+    d5 = g.digest()
+    g2.remove_weak_edges(3)
+    g2.remove_weak_edges(5)
+    assert g2.digest() == d5 and d5[1] < E and d5[2] < S
+    g.remove_weak_edges(5)
+    assert g.digest() == d5
+    nodes, edges = g.counts()
+    assert edges == d5[1] and 0 < nodes <= edges + 2 * 4_600_000
+    g.close(), g2.close()
