@@ -609,7 +609,6 @@ template <class K> struct Builder : BuilderBase {
                                                        (uint32_t *)b_bad.p, d_ctr);
         }
         prof.end(stream);
-        if (input_consumed) KTG_CUDA(cudaEventRecord(input_consumed, stream));
         prof.begin("check_reads", n_reads, stream);
         {
             int grid = (int)std::min<uint64_t>((n_reads + 255) / 256, (uint64_t)props.sms * 4);
@@ -660,6 +659,8 @@ template <class K> struct Builder : BuilderBase {
             v.ulen = v.ipr = 0;
             v.n_items = v.n_words * ITEMS_PER_WORD;
         }
+        // nothing after this point reads the caller's bases or offsets
+        if (input_consumed) KTG_CUDA(cudaEventRecord(input_consumed, stream));
         return KTG_OK;
     }
 

@@ -113,6 +113,10 @@ class ReadFile {
         return true;
     }
 
+    bool is_fasta() const { return fasta_; }
+    // raw bytes for the device-side parser (must not be mixed with next_batch on one file)
+    size_t read_raw(void *dst, size_t n) { return fread(dst, 1, n, f_); }
+
     // Appends records to a cleared batch until it holds >= max_bytes of bases.
     // Returns 1 if more records may follow, 0 at end of file, -1 on a malformed record.
     int next_batch(ReadBatch *out, size_t max_bytes, std::string *why) {

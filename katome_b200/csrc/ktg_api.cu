@@ -3,6 +3,7 @@
 #include <memory>
 
 #include "builder.cuh"
+#include "fastq_device.cuh"
 #include "host_reader.h"
 
 using namespace ktg;
@@ -186,6 +187,136 @@ int ktg_add_reads(ktg_builder *b, const uint8_t *bases, const uint64_t *offsets,
     return KTG_OK;
 }
 
+// ---- FASTQ parsed on the device (fastq_device.cuh): the host only moves raw file bytes ----------
+namespace {
+
+struct FastqDeviceParser {
+    ktg_builder *b;
+    BuilderBase *impl;
+    size_t chunk;                     // raw bytes per chunk
+    uint8_t *pinned[2] = {nullptr, nullptr};
+    DeviceBuf raw[2], dense[2], offs[2], nl, bcount, bstart, sstart, slen, tmp, info;
+    cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
+    bool used[2] = {false, false};
+
+    FastqDeviceParser(ktg_builder *b_, size_t chunk_) : b(b_), impl(b_->impl.get()), chunk(chunk_) {}
+    ~FastqDeviceParser() {
+        cudaStreamSynchronize(impl->stream);
+        cudaStreamSynchronize(impl->copy_stream);
+        for (int i = 0; i < 2; ++i) {
+            if (pinned[i]) cudaFreeHost(pinned[i]);
+            if (copied[i]) cudaEventDestroy(copied[i]);
+            if (consumed[i]) cudaEventDestroy(consumed[i]);
+            raw[i].release(); dense[i].release(); offs[i].release();
+        }
+        nl.release(); bcount.release(); bstart.release(); sstart.release(); slen.release(); tmp.release(); info.release();
+    }
+    int init() {
+        for (int i = 0; i < 2; ++i) {
+            KTG_CUDA(cudaHostAlloc((void **)&pinned[i], chunk + 64, cudaHostAllocDefault));
+            KTG_CUDA(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
+            KTG_CUDA(cudaEventCreateWithFlags(&consumed[i], cudaEventDisableTiming));
+            KTG_TRY(raw[i].ensure(chunk + 64));
+        }
+        KTG_TRY(info.ensure(sizeof(FastqChunkInfo)));
+        return KTG_OK;
+    }
+
+    // One file.  Mirrors next_fastq of host_reader.h record for record.
+    int parse(ReadFile &f) {
+        cudaStream_t st = impl->stream;
+        size_t carry = 0; // bytes of an unfinished record at the front of pinned[cur]
+        int cur = 0;
+        bool eof = false;
+        while (!eof) {
+            uint8_t *h = pinned[cur];
+            if (used[cur]) KTG_CUDA(cudaEventSynchronize(copied[cur])); // (the carry was written after this wait)
+            size_t got = f.read_raw(h + carry, chunk - carry);
+            size_t n = carry + got;
+            eof = got < chunk - carry;
+            if (eof && n && h[n - 1] != '\n') h[n++] = '\n'; // a last line without newline is a line
+            if (n == 0) break;
+            // raw bytes to the device (the device buffer of two chunks ago has been consumed)
+            if (used[cur]) KTG_CUDA(cudaStreamWaitEvent(impl->copy_stream, consumed[cur], 0));
+            KTG_CUDA(cudaMemcpyAsync(raw[cur].p, h, n, cudaMemcpyHostToDevice, impl->copy_stream));
+            KTG_CUDA(cudaEventRecord(copied[cur], impl->copy_stream));
+            KTG_CUDA(cudaStreamWaitEvent(st, copied[cur], 0));
+            used[cur] = true;
+            const uint8_t *d_raw = (const uint8_t *)raw[cur].p;
+            // newline index
+            const uint32_t n_blocks = (uint32_t)((n + FQ_BLOCK_BYTES - 1) / FQ_BLOCK_BYTES);
+            KTG_TRY(bcount.ensure(((size_t)n_blocks + 1) * 4));
+            KTG_TRY(bstart.ensure(((size_t)n_blocks + 1) * 4));
+            KTG_CUDA(cudaMemsetAsync((uint32_t *)bcount.p + n_blocks, 0, 4, st));
+            fq_count_kernel<<<n_blocks, 256, 0, st>>>(d_raw, n, (uint32_t *)bcount.p);
+            size_t tb = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, tb, (uint32_t *)bcount.p, (uint32_t *)bstart.p, (int)n_blocks + 1, st);
+            KTG_TRY(tmp.ensure(tb));
+            KTG_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, (uint32_t *)bcount.p, (uint32_t *)bstart.p, (int)n_blocks + 1, st));
+            uint32_t n_lines = 0;
+            KTG_CUDA(cudaMemcpyAsync(&n_lines, (uint32_t *)bstart.p + n_blocks, 4, cudaMemcpyDeviceToHost, st));
+            KTG_CUDA(cudaStreamSynchronize(st));
+            const uint64_t n_rec = n_lines / 4;
+            FastqChunkInfo ci{};
+            ci.bad_header = ~0ull;
+            if (n_rec) {
+                KTG_TRY(nl.ensure((size_t)n_lines * 4));
+                fq_positions_kernel<<<n_blocks, 256, 0, st>>>(d_raw, n, (const uint32_t *)bstart.p, (uint32_t *)nl.p);
+                KTG_TRY(sstart.ensure(n_rec * 4));
+                KTG_TRY(slen.ensure((n_rec + 1) * 8));
+                KTG_TRY(offs[cur].ensure((n_rec + 1) * 8));
+                FastqChunkInfo init{};
+                init.bad_header = ~0ull;
+                init.min_len = ~0ull;
+                KTG_CUDA(cudaMemcpyAsync(info.p, &init, sizeof init, cudaMemcpyHostToDevice, st));
+                KTG_CUDA(cudaMemsetAsync((uint64_t *)slen.p + n_rec, 0, 8, st));
+                const int grid = (int)std::min<uint64_t>((n_rec + 255) / 256, 148 * 8);
+                fq_records_kernel<<<grid, 256, 0, st>>>(d_raw, (const uint32_t *)nl.p, n_rec, impl->k, (uint32_t *)sstart.p,
+                                                       (uint64_t *)slen.p, (FastqChunkInfo *)info.p);
+                size_t tb2 = 0;
+                cub::DeviceScan::ExclusiveSum(nullptr, tb2, (uint64_t *)slen.p, (uint64_t *)offs[cur].p, (int)n_rec + 1, st);
+                KTG_TRY(tmp.ensure(tb2));
+                KTG_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb2, (uint64_t *)slen.p, (uint64_t *)offs[cur].p, (int)n_rec + 1, st));
+                uint64_t total_bases = 0;
+                KTG_CUDA(cudaMemcpyAsync(&ci, info.p, sizeof ci, cudaMemcpyDeviceToHost, st));
+                KTG_CUDA(cudaMemcpyAsync(&total_bases, (uint64_t *)offs[cur].p + n_rec, 8, cudaMemcpyDeviceToHost, st));
+                KTG_CUDA(cudaStreamSynchronize(st));
+                if (ci.bad_header != ~0ull) return fail(KTG_ERR_BAD_RECORD, "Expected @ at record start.");
+                KTG_TRY(dense[cur].ensure(total_bases + 64));
+                fq_gather_kernel<<<148 * 8, 256, 0, st>>>(d_raw, (const uint32_t *)sstart.p, (const uint64_t *)offs[cur].p,
+                                                         n_rec, (uint8_t *)dense[cur].p);
+                BatchHint hint;
+                hint.ulen = (ci.min_len == ci.max_len && ci.max_len <= 0xFFFFFFFFull) ? (uint32_t)ci.max_len : 0;
+                hint.windows_ub = ci.windows_ub;
+                impl->hint_shift0 = (uint32_t)((uintptr_t)dense[cur].p & 31);
+                impl->input_consumed = consumed[cur]; // dense, offsets and raw of this slot are free after the pack
+                int rc_ = impl->ingest_device((const uint8_t *)dense[cur].p, (const uint64_t *)offs[cur].p, n_rec, total_bases, &hint);
+                impl->input_consumed = nullptr;
+                KTG_TRY(rc_);
+            }
+            // what follows the last complete record
+            const size_t done = n_rec ? (size_t)ci.consumed : 0;
+            const size_t rest = n - done;
+            if (eof) {
+                if (rest) { // lines of an unfinished record: the reader fails on its header or on its missing lines
+                    if (h[done] != '@') return fail(KTG_ERR_BAD_RECORD, "Expected @ at record start.");
+                    return fail(KTG_ERR_BAD_RECORD, "Incomplete record. Each FastQ record has to consist of 4 lines.");
+                }
+                break;
+            }
+            if (rest >= chunk) return fail(KTG_ERR_BAD_RECORD, "a FASTQ record is larger than %zu bytes", chunk);
+            const int nxt = cur ^ 1;
+            if (used[nxt]) KTG_CUDA(cudaEventSynchronize(copied[nxt]));
+            memcpy(pinned[nxt], h + done, rest);
+            carry = rest;
+            cur = nxt;
+        }
+        return KTG_OK;
+    }
+};
+
+} // namespace
+
 int ktg_create_from_files(ktg_builder *b, const char *const *paths, uint32_t n_paths,
                           int file_type, uint64_t *total_bytes) {
     KTG_ENTER(b);
@@ -199,6 +330,17 @@ int ktg_create_from_files(ktg_builder *b, const char *const *paths, uint32_t n_p
         std::string why;
         if (!f->open(paths[i], file_type == KTG_FASTA, &why)) return fail(KTG_ERR_IO, "%s", why.c_str());
         files.push_back(std::move(f));
+    }
+    // FASTQ: records are cut on the device (KTG_HOST_PARSE=1 keeps the host reader, its twin)
+    if (file_type == KTG_FASTQ && !getenv("KTG_HOST_PARSE")) {
+        size_t chunk = 16u << 20; // small: the two pinned buffers are allocated per call (0.3 ms / MiB)
+        if (const char *e = getenv("KTG_FASTQ_CHUNK_KB")) chunk = (size_t)std::max(1, atoi(e)) << 10; // test knob
+        FastqDeviceParser parser(b, chunk);
+        KTG_TRY(parser.init());
+        for (auto &f : files) KTG_TRY(parser.parse(*f));
+        KTG_TRY(b->impl->read_counters(&reads, &bytes));
+        if (total_bytes) *total_bytes = bytes;
+        return ktg_finalize(b);
     }
     // Two pinned batches: the parser fills one while the copy / kernels of the other are in flight.
     ReadBatch batch[2];

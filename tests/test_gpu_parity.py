@@ -549,3 +549,63 @@ def test_baseline_config2_full_size(K):
     nodes, edges = g.counts()
     assert edges == d5[1] and 0 < nodes <= edges + 2 * 4_600_000
     g.close(), g2.close()
+
+
+def _both_fastq_parsers(K, path, k, rc, chunk_kb=None):
+    """Build::create through the device-side FASTQ parser and through the host reader (its twin)."""
+    import os
+    out = []
+    for host in (False, True):
+        env = {"KTG_HOST_PARSE": "1"} if host else ({"KTG_FASTQ_CHUNK_KB": str(chunk_kb)} if chunk_kb else {})
+        os.environ.update(env)
+        try:
+            try:
+                g, nbytes = K.GpuGIR.create([path] if isinstance(path, str) else path, "fastq", rc, 0, k=k)
+                out.append(("ok", nbytes, g.digest(), g.counts()))
+                g.close()
+            except K.KatomeError as e:
+                out.append(("error", str(e)))
+        finally:
+            for key in env:
+                os.environ.pop(key, None)
+    return out
+
+
+def test_device_fastq_parser_matches_host_reader(K, tmp_path):
+    """FASTQ records cut on the device == the host reader (rust-bio 0.10 semantics:
+    strict 4-line records, '@' header, sequence line trimmed on the right, EOF inside a record fails)"""
+    rng = np.random.default_rng(77)
+    seqs = H.golden_seqs("data2")  # 125 reads, 33 with an N
+    ragged = H.random_reads(rng, 400, 45, 160, n_rate=0.05)
+
+    def fastq(reads, nl="\n", final_nl=True, pad=""):
+        recs = []
+        for i, sq in enumerate(reads):
+            qual = "@" * len(sq) if i % 3 == 0 else "I" * len(sq)  # a quality line may start with '@'
+            recs.append(f"@read{i} some/description{nl}{sq}{pad}{nl}+{'read%d' % i if i % 2 else ''}{nl}{qual}{nl}")
+        text = "".join(recs)
+        return text if final_nl else text[: -len(nl)]
+
+    files = {
+        "plain": fastq(seqs), "crlf": fastq(seqs, nl="\r\n"), "no_final_newline": fastq(seqs, final_nl=False),
+        "trailing_blanks": fastq(seqs, pad=" \t"), "ragged": fastq(ragged), "empty": "",
+        "one_record": fastq(seqs[:1]),
+    }
+    bad = {
+        "no_at_first": "read0\nACGT\n+\nIIII\n", "no_at_later": fastq(seqs[:5]) + "read5\nACGT\n+\nIIII\n",
+        "cut_after_header": fastq(seqs[:4]) + "@x\n", "cut_after_seq": fastq(seqs[:4]) + "@x\nACGT\n",
+        "cut_after_plus": fastq(seqs[:4]) + "@x\nACGT\n+\n", "blank_line_at_end": fastq(seqs[:4]) + "\n",
+        "garbage_tail": fastq(seqs[:4]) + "xyz",
+    }
+    for name, text in {**files, **bad}.items():
+        p = tmp_path / f"{name}.fastq"
+        p.write_bytes(text.encode())
+        for chunk_kb in (None, 1, 3):  # tiny chunks: records carried across chunk boundaries
+            dev, host = _both_fastq_parsers(K, str(p), 40, True, chunk_kb)
+            assert dev == host, (name, chunk_kb, dev, host)
+            assert (dev[0] == "error") == (name in bad), (name, dev)
+    # against the oracle, and several files in one build
+    cpu = _oracle(seqs + ragged, 40, True)
+    p1, p2 = tmp_path / "plain.fastq", tmp_path / "ragged.fastq"
+    dev, host = _both_fastq_parsers(K, [str(p1), str(p2)], 40, True, 2)
+    assert dev == host and dev[2] == cpu.digest() and dev[1] == cpu.accepted_bytes and dev[3] == cpu.counts()
