@@ -219,6 +219,37 @@ int ktg_mg_sketch(ktg_builder *b, void **d_regs, uint32_t *n_regs);
 int ktg_mg_merge_sketch(ktg_builder *b, const void *d_regs);
 int ktg_mg_spill(ktg_builder *b, void **d_keys, uint64_t *n);
 int ktg_mg_insert_spill(ktg_builder *b, const void *d_keys, uint64_t n);
+/* ---- the fused exchange in SUPER-K-MER records (23 <= k <= 31).  The owner of a k-mer is a
+ * function of its minimizer (smallest hashed canonical (k-15)-mer inside it); consecutive windows
+ * of a read mostly share it, so a run of n <= 16 windows travels over NVLink as ONE 16-byte
+ * record holding its n+k-1 bases (about 2.8 bytes per window instead of 8), and the owner unrolls
+ * records into canonical k-mers while it partitions them by sub-table.  Same protocol as above:
+ *   ktg_mg_skm_plan / ktg_mg_skm_prepare   bucket_cap is in records (16 bytes each);
+ *   ktg_mg_skm_scatter_reads_device        *d_cursors: world u64 bucket ends (owner * bucket_cap
+ *       + fill, in records); *d_key_counts: world u64, the k-mers sent to every owner;
+ *   all-to-all of both; no sketch exchange (the owner sketches the keys it unrolls);
+ *   ktg_mg_skm_insert_buckets(ends, sum of the received key counts);
+ *   records that did not fit a bucket: ktg_mg_skm_spill -> ktg_mg_skm_partition_records ->
+ *       all-to-all (2 u64 per record, lo first) -> ktg_mg_skm_insert_records.
+ * The two exchanges assign k-mers to shards differently; use one per build. */
+int ktg_mg_skm_supported(uint32_t k);
+int ktg_mg_skm_plan(ktg_builder *b, uint64_t max_windows, int *needs_realloc);
+int ktg_mg_skm_prepare(ktg_builder *b, uint64_t max_windows, void **rx_base, uint64_t *rx_bytes, uint64_t *bucket_cap);
+int ktg_mg_skm_scatter_reads_device(ktg_builder *b, const void *d_bases, const void *d_offsets, uint64_t n_reads,
+                                    uint64_t total_bases, void *const *peer_rx, uint32_t slot, int first_of_batch,
+                                    void *send_stream, void **d_cursors, void **d_key_counts);
+int ktg_mg_skm_insert_buckets(ktg_builder *b, const void *d_bucket_ends, uint64_t n_keys_ub, uint32_t slot);
+int ktg_mg_skm_spill(ktg_builder *b, void **d_records, uint64_t *n);
+int ktg_mg_skm_partition_records(ktg_builder *b, const void *d_records, uint64_t n, void **d_out, uint64_t *counts);
+int ktg_mg_skm_insert_records(ktg_builder *b, const void *d_records, uint64_t n);
+/* owner rank of a k-mer in this exchange (after canonicalisation it is the same for both strands) */
+uint32_t ktg_mg_skm_owner_of(const ktg_builder *b, uint64_t key_hi, uint64_t key_lo);
+/* Host-only twins of the record cutter (no device needed; used by the CPU tests): work item i is
+ * the 16 window starts from flat base position pos[i] of the 2-bit stream `packed` (first base of
+ * word j in bits 63:62), valid[i] bit j = window j exists.  Records come back as (lo, hi) pairs. */
+int ktg_skm_items_host(const uint64_t *packed, const uint64_t *pos, const uint32_t *valid, uint64_t n_items, uint32_t k,
+                       uint32_t world, uint64_t *records_lo_hi, uint64_t cap, uint64_t *n_records);
+uint32_t ktg_skm_owner_of_kmer(uint64_t kmer, uint32_t k, uint32_t world);
 /* CUDA IPC handles of device allocations (cudaIpcGetMemHandle / OpenMemHandle / CloseMemHandle) */
 int ktg_ipc_get_handle(const void *dev_ptr, uint8_t handle[64]);
 int ktg_ipc_open(const uint8_t handle[64], void **dev_ptr);

@@ -30,6 +30,9 @@ SYMBOLS = (
     "ktg_synth_reads_device", "ktg_random_access_probe", "ktg_get_profile", "ktg_reset_profile",
     "ktg_get_info", "ktg_partition_keys_device", "ktg_mg_plan", "ktg_mg_prepare",
     "ktg_mg_scatter_reads_device", "ktg_mg_insert_buckets", "ktg_mg_sketch", "ktg_mg_merge_sketch", "ktg_mg_spill", "ktg_mg_insert_spill", "ktg_ipc_get_handle", "ktg_ipc_open", "ktg_ipc_close",
+    "ktg_mg_skm_supported", "ktg_mg_skm_plan", "ktg_mg_skm_prepare", "ktg_mg_skm_scatter_reads_device",
+    "ktg_mg_skm_insert_buckets", "ktg_mg_skm_spill", "ktg_mg_skm_partition_records", "ktg_mg_skm_insert_records",
+    "ktg_mg_skm_owner_of", "ktg_skm_items_host", "ktg_skm_owner_of_kmer",
     "ktg_export_graph", "ktg_edge_record_bytes", "ktg_nodes_export_device", "ktg_nodes_stats_from_device", "ktg_edge_sums", "ktg_scale_weights",
 )
 
@@ -134,6 +137,20 @@ def lib():
     L.ktg_mg_merge_sketch.argtypes = [vp, vp]
     L.ktg_mg_spill.argtypes = [vp, C.POINTER(vp), u64p]
     L.ktg_mg_insert_spill.argtypes = [vp, vp, C.c_uint64]
+    L.ktg_mg_skm_supported.argtypes = [C.c_uint32]
+    L.ktg_mg_skm_plan.argtypes = [vp, C.c_uint64, intp]
+    L.ktg_mg_skm_prepare.argtypes = [vp, C.c_uint64, C.POINTER(vp), u64p, u64p]
+    L.ktg_mg_skm_scatter_reads_device.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, C.POINTER(vp), C.c_uint32,
+                                                  C.c_int, vp, C.POINTER(vp), C.POINTER(vp)]
+    L.ktg_mg_skm_insert_buckets.argtypes = [vp, vp, C.c_uint64, C.c_uint32]
+    L.ktg_mg_skm_spill.argtypes = [vp, C.POINTER(vp), u64p]
+    L.ktg_mg_skm_partition_records.argtypes = [vp, vp, C.c_uint64, C.POINTER(vp), u64p]
+    L.ktg_mg_skm_insert_records.argtypes = [vp, vp, C.c_uint64]
+    L.ktg_mg_skm_owner_of.argtypes = [vp, C.c_uint64, C.c_uint64]
+    L.ktg_mg_skm_owner_of.restype = C.c_uint32
+    L.ktg_skm_items_host.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, vp, C.c_uint64, u64p]
+    L.ktg_skm_owner_of_kmer.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32]
+    L.ktg_skm_owner_of_kmer.restype = C.c_uint32
     L.ktg_ipc_get_handle.argtypes = [vp, C.c_char_p]
     L.ktg_ipc_open.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.ktg_ipc_close.argtypes = [vp]

@@ -13,6 +13,7 @@
 
 #include "../../include/katome_gpu.h"
 #include "kernels.cuh"
+#include "superkmer.cuh"
 
 namespace ktg {
 
@@ -231,6 +232,17 @@ struct BuilderBase {
     virtual int mg_sketch(void **d_regs, uint32_t *n_regs) = 0;
     virtual int mg_merge_sketch(const void *d_regs) = 0;
     virtual int mg_spill(void **d_keys, uint64_t *n) = 0;
+    // the same exchange in super-k-mer records (superkmer.cuh); 23 <= k <= 31 only
+    virtual int mg_skm_plan(uint64_t max_windows, int *needs_realloc) = 0;
+    virtual int mg_skm_prepare(uint64_t max_windows, void **rx_base, uint64_t *rx_bytes, uint64_t *bucket_cap) = 0;
+    virtual int mg_skm_scatter_reads(const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t n_reads,
+                                     uint64_t total_bases, void *const *peer_rx, uint32_t slot, int first_of_batch,
+                                     cudaStream_t send_stream, void **d_cursors, void **d_key_counts) = 0;
+    virtual int mg_skm_insert_buckets(const void *d_bucket_ends, uint64_t n_keys_ub, uint32_t slot) = 0;
+    virtual int mg_skm_spill(void **d_records, uint64_t *n) = 0;
+    virtual int mg_skm_partition_records(const void *d_records, uint64_t n, void **d_out, uint64_t *counts) = 0;
+    virtual int mg_skm_insert_records(const void *d_records, uint64_t n) = 0;
+    virtual uint32_t skm_owner_of(uint64_t hi, uint64_t lo) = 0;
     virtual uint32_t owner_of(uint64_t hi, uint64_t lo) = 0;
     virtual int info(ktg_info *out) = 0;
 };
@@ -273,7 +285,7 @@ template <class K> struct Builder : BuilderBase {
         b_packed.release(); b_bad.release(); b_valid.release(); b_wstart.release(); b_keys.release(); b_keys2.release();
         b_hist.release(); b_hll.release(); b_spill.release(); b_ovf_keys.release(); b_ovf_inc.release(); b_small.release();
         b_pkeys.release(); b_pcur.release(); b_pspill.release(); b_stage_cur.release();
-        b_rx.release(); b_mg_cur.release(); b_mg_spill.release(); b_node_keys.release(); b_node_deg.release();
+        b_rx.release(); b_mg_cur.release(); b_mg_spill.release(); b_skm_cnt.release(); b_skm_part.release(); b_skm_keys.release(); b_node_keys.release(); b_node_deg.release();
         if (copy_stream) cudaStreamDestroy(copy_stream);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
@@ -812,7 +824,7 @@ template <class K> struct Builder : BuilderBase {
             const size_t sb = (size_t)tile * (sizeof(K) + 4) + (size_t)tab.pages_per_sub() * 32;
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);
             int gg = (int)std::min<uint64_t>(grid_for(kern, threads, sb, props), nt);
-            kern<<<gg, threads, sb, stream>>>(keys1, fill1, cap1, tpb, nt, sub_mod, false, tab, o);
+            kern<<<gg, threads, sb, stream>>>(keys1, fill1, cap1, tpb, nt, sub_mod, false, tab, o, nullptr);
         };
         if (variant == 1) launch_v(scatter_buckets_kernel<K, 2, 256, 8, 4>, 256, 8);
         else if (variant == 2) launch_v(scatter_buckets_kernel<K, 2, 512, 4, 3>, 512, 4);
@@ -939,7 +951,8 @@ template <class K> struct Builder : BuilderBase {
         KTG_TRY(hll_estimate(&est)); // synchronises the stream
         staged_spilled = std::min<uint64_t>(spilled_now, stage_spill_cap);
         // fused multi-GPU mode: the sketch was all-reduced, it describes the keys of ALL ranks
-        const uint64_t distinct = hll_base + (uint64_t)(est * (mg_mode ? 1.10 / tab.world : 1.08)) + 64;
+        // (super-k-mer exchange: the owner sketches what it receives, i.e. its own shard)
+        const uint64_t distinct = hll_base + (uint64_t)(est * (mg_mode && !mg_local_sketch ? 1.10 / tab.world : 1.08)) + 64;
         occupied_ub = distinct;
         bool moved = false;
         if ((double)distinct > LOAD_MAX * (double)tab.capacity()) {
@@ -1498,6 +1511,7 @@ template <class K> struct Builder : BuilderBase {
             b_rx.release();
             KTG_TRY(b_rx.ensure((size_t)cap * W * MG_SLOTS * sizeof(K) + 64));
             mg_cap = cap;
+            skm_cap = 0; // the super-k-mer exchange has to size the buffer again
             mg_spill_cap = std::max<uint64_t>(1u << 20, max_windows / 4); // per batch of several chunks
             KTG_TRY(b_mg_spill.ensure(mg_spill_cap * sizeof(K) + 64));
             KTG_TRY(b_mg_cur.ensure(((size_t)W * MG_SLOTS + 2) * 8));
@@ -1531,6 +1545,7 @@ template <class K> struct Builder : BuilderBase {
         } swap(stream, send_stream);
         const uint32_t W = tab.world;
         mg_mode = true;
+        mg_local_sketch = false;
         unsigned long long *cur = mg_cursors(slot);
         *d_cursors = cur;
         init_cursors_kernel<<<1, 32, 0, stream>>>(cur, W, mg_cap);
@@ -1612,6 +1627,250 @@ template <class K> struct Builder : BuilderBase {
         }
         *n = v;
         return KTG_OK;
+    }
+
+    // ---- multi-GPU, fused, in super-k-mer records (superkmer.cuh) ---------------------------
+    // Same protocol as above with 16-byte records instead of keys: the receive buffer (same
+    // allocation, same two slots) holds one bucket of skm_cap RECORDS per source rank, the sender
+    // also counts the k-mers it sent to every owner (the owner needs an upper bound to stage
+    // them), and the owner sketches the keys itself while it unrolls the records, so no sketch
+    // is exchanged.  Owner of a k-mer = skm_owner(minimizer), see skm_owner_of.
+    DeviceBuf b_skm_cnt, b_skm_part;
+    uint64_t skm_cap = 0, skm_spill_cap = 0;
+    bool mg_local_sketch = false;
+    static constexpr uint32_t SKM_PAD = 128 / sizeof(u128);
+    size_t skm_slot_records() const { return (size_t)skm_cap * tab.world; }
+    static constexpr uint32_t SKM_CNT_STRIDE = MAX_P2P_WORLD + 8; // key counts per owner, then the spill count
+    unsigned long long *skm_key_counts(uint32_t slot) { return (unsigned long long *)b_skm_cnt.p + (size_t)slot * SKM_CNT_STRIDE; }
+    unsigned long long *skm_scalar(uint32_t i) { return (unsigned long long *)b_skm_cnt.p + (size_t)MG_SLOTS * SKM_CNT_STRIDE + i; }
+
+    int skm_check() {
+        if (sizeof(K) != 8 || !skm_supported(k))
+            return fail(KTG_ERR_INVALID, "the super-k-mer exchange needs %u <= k <= %u", SKM_K_MIN, SKM_K_MAX);
+        if (tab.world > (uint32_t)MAX_P2P_WORLD) return fail(KTG_ERR_INVALID, "fused exchange needs world <= %d", MAX_P2P_WORLD);
+        return KTG_OK;
+    }
+    int skm_geometry(uint64_t max_windows, uint64_t *cap) {
+        KTG_TRY(skm_check());
+        const uint32_t W = tab.world;
+        // random sequence cuts 2.8 records per 16 windows (0.17 per window); 0.25 leaves a third
+        // of headroom, low-complexity reads need fewer, and whatever does not fit takes the
+        // spill route.  Every (tile, owner) run may be rounded up by SKM_PAD - 1 fillers.
+        const uint64_t fillers = (max_windows / (SKM_W * SCATTER_THREADS) + 1) * W * (SKM_PAD - 1);
+        *cap = bucket_cap_for(std::max<uint64_t>(max_windows / 4 + fillers, 1), W);
+        if ((double)*cap * W >= 4.0e9) return fail(KTG_ERR_INVALID, "batch too large: split it (32-bit bucket positions)");
+        return KTG_OK;
+    }
+    int mg_skm_plan(uint64_t max_windows, int *needs_realloc) override {
+        uint64_t cap = 0;
+        KTG_TRY(skm_geometry(max_windows, &cap));
+        *needs_realloc = cap > skm_cap || !b_rx.p;
+        return KTG_OK;
+    }
+    int mg_skm_prepare(uint64_t max_windows, void **rx_base, uint64_t *rx_bytes, uint64_t *bucket_cap) override {
+        uint64_t cap = 0;
+        KTG_TRY(skm_geometry(max_windows, &cap));
+        const uint32_t W = tab.world;
+        if (cap > skm_cap || !b_rx.p) {
+            KTG_TRY(sync());
+            b_rx.release();
+            KTG_TRY(b_rx.ensure((size_t)cap * W * MG_SLOTS * sizeof(u128) + 64));
+            skm_cap = cap;
+            mg_cap = 0; // the key exchange has to size the buffer again
+            skm_spill_cap = std::max<uint64_t>(1u << 20, max_windows / 16);
+            KTG_TRY(b_mg_spill.ensure(skm_spill_cap * sizeof(u128) + 64));
+            KTG_TRY(b_mg_cur.ensure(((size_t)W * MG_SLOTS + 2) * 8));
+            KTG_TRY(b_skm_cnt.ensure(((size_t)MG_SLOTS * SKM_CNT_STRIDE + 4) * 8));
+        }
+        *rx_base = b_rx.p;
+        *rx_bytes = (size_t)skm_cap * W * sizeof(u128); // of ONE slot
+        *bucket_cap = skm_cap;
+        return KTG_OK;
+    }
+
+    int mg_skm_scatter_reads(const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t n_reads,
+                             uint64_t total_bases, void *const *peer_rx, uint32_t slot, int first_of_batch,
+                             cudaStream_t send_stream, void **d_cursors, void **d_key_counts) override {
+        if (deferred_error != KTG_OK) return fail(deferred_error, "build is void after an earlier error");
+        KTG_TRY(skm_check());
+        if (!b_rx.p || !skm_cap) return fail(KTG_ERR_INVALID, "ktg_mg_skm_prepare first");
+        if (slot >= MG_SLOTS) return fail(KTG_ERR_INVALID, "slot out of range");
+        struct StreamSwap {
+            cudaStream_t &ref, saved;
+            StreamSwap(cudaStream_t &r, cudaStream_t s) : ref(r), saved(r) { if (s) ref = s; }
+            ~StreamSwap() { ref = saved; }
+        } swap(stream, send_stream);
+        const uint32_t W = tab.world;
+        mg_mode = true;
+        mg_local_sketch = true;
+        unsigned long long *cur = mg_cursors(slot), *kc = skm_key_counts(slot);
+        *d_cursors = cur;
+        *d_key_counts = kc;
+        init_cursors_kernel<<<1, 32, 0, stream>>>(cur, W, skm_cap);
+        KTG_CUDA(cudaMemsetAsync(kc, 0, SKM_CNT_STRIDE * 8, stream));
+        if (first_of_batch) KTG_CUDA(cudaMemsetAsync(mg_spill_cursor(), 0, 8, stream));
+        if (n_reads == 0) return KTG_OK;
+        Batch bt;
+        KTG_TRY(pack(d_bases, d_offsets, n_reads, total_bases, &bt));
+        if (bt.windows == 0) return KTG_OK;
+        SkmView sv{};
+        sv.v = bt.v;
+        if (bt.v.ulen) {
+            sv.ipr = (bt.v.ulen - k + 1 + SKM_W - 1) / SKM_W;
+            sv.n_items = n_reads * sv.ipr;
+        }
+        else sv.n_items = bt.v.n_words * 2;
+        PeerOut po{};
+        po.world = W;
+        po.bins_per_owner = 1;
+        po.pad = SKM_PAD;
+        for (uint32_t o = 0; o < W; ++o)
+            po.rxb[o] = (u128 *)peer_rx[o] + (int64_t)slot * (int64_t)skm_slot_records() +
+                        ((int64_t)tab.rank - (int64_t)o) * (int64_t)skm_cap;
+        ScatterOut so;
+        so.cursors = cur;
+        so.bucket_cap = skm_cap;
+        so.out = nullptr;
+        so.spill_out = b_mg_spill.p;
+        so.spill_cursor = mg_spill_cursor();
+        so.spill_cap = skm_spill_cap;
+        const size_t ss = ScatterSmem<u128, SCATTER_TILE>::bytes(W, false);
+        const uint64_t n_tiles = std::max<uint64_t>(1, (sv.n_items + SCATTER_THREADS * SKM_IPL - 1) / (SCATTER_THREADS * SKM_IPL));
+        int g = (int)std::min<uint64_t>(grid_for(scatter_superkmers_kernel, SCATTER_THREADS, ss, props), n_tiles);
+        if (const char *e = getenv("KTG_P2P_CTAS")) // tuning knob
+            if (atoi(e) > 0) g = (int)std::min<uint64_t>(g, (uint64_t)props.sms * atoi(e));
+        prof.begin("scatter_superkmers_p2p", bt.windows, stream);
+        scatter_superkmers_kernel<<<g, SCATTER_THREADS, ss, stream>>>(sv, k, W, so, po, kc);
+        prof.end(stream);
+        KTG_CUDA(cudaGetLastError());
+        // key_counts[world]: the records this rank has spilled so far in this batch
+        KTG_CUDA(cudaMemcpyAsync(kc + W, mg_spill_cursor(), 8, cudaMemcpyDeviceToDevice, stream));
+        return KTG_OK;
+    }
+
+    // records [q*cap, ends[q]) for q < n_buckets -> flat keys -> staged by sub-table (+ sketch)
+    DeviceBuf b_skm_keys;
+    int skm_unroll(const u128 *rx, const unsigned long long *ends, uint64_t cap, uint32_t n_buckets, uint64_t n_keys_ub) {
+        if constexpr (sizeof(K) == 8) {
+            const uint64_t tiles_per_bucket = cap / UNROLL_THREADS, n_rtiles = tiles_per_bucket * n_buckets;
+            if ((double)n_rtiles >= 4.0e9) return fail(KTG_ERR_INVALID, "batch too large: split it");
+            // every warp leaves half a chunk of fillers behind on average: no more CTAs than it takes
+            int ug = (int)std::min<uint64_t>((uint64_t)props.sms * 8, std::max<uint64_t>(n_rtiles, 1));
+            // fillers included (see unroll_records_kernel), in whole tiles of the scatter
+            const uint64_t cap1 = (unroll_out_cap(n_keys_ub, (uint64_t)ug * (UNROLL_THREADS / 32)) + L2S_TILE - 1) / L2S_TILE * L2S_TILE;
+            if ((double)cap1 >= 4.0e9) return fail(KTG_ERR_INVALID, "batch too large: split it (32-bit bucket positions)");
+            KTG_TRY(b_skm_keys.ensure(cap1 * sizeof(K) + 64));
+            unsigned long long *n_keys = skm_scalar(2);
+            KTG_CUDA(cudaMemsetAsync(n_keys, 0, 8, stream));
+            prof.begin("unroll_records", n_keys_ub, stream);
+            if (rc)
+                unroll_records_kernel<true><<<ug, UNROLL_THREADS, 0, stream>>>(rx, ends, cap, n_buckets, k,
+                                                                              (uint64_t *)b_skm_keys.p, n_keys, cap1);
+            else
+                unroll_records_kernel<false><<<ug, UNROLL_THREADS, 0, stream>>>(rx, ends, cap, n_buckets, k,
+                                                                               (uint64_t *)b_skm_keys.p, n_keys, cap1);
+            prof.end(stream);
+            KTG_TRY(stage_add(n_keys_ub, [&](uint32_t n_bins, const ScatterOut &o) -> int {
+                // the flat array is ONE level-1 bucket whose fill is the device-side key count
+                const uint64_t n_tiles = cap1 / L2S_TILE;
+                const size_t ss = ScatterSmem<K, L2S_TILE>::bytes(n_bins, false);
+                auto kern = scatter_buckets_kernel<K, 1, L2S_THREADS, L2S_PER, 2, true>;
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ScatterSmem<K, L2S_TILE>::bytes(MAX_BINS, false));
+                int g = (int)std::min<uint64_t>(grid_for(kern, L2S_THREADS, ss, props), n_tiles);
+                prof.begin("scatter_received", n_keys_ub, stream);
+                kern<<<g, L2S_THREADS, ss, stream>>>((const K *)b_skm_keys.p, n_keys, cap1, n_tiles, n_tiles, 0, true, tab, o,
+                                                     (uint32_t *)b_hll.p);
+                prof.end(stream);
+                return KTG_OK;
+            }));
+            KTG_CUDA(cudaGetLastError());
+            return KTG_OK;
+        }
+        else return fail(KTG_ERR_INVALID, "super-k-mer records need k <= 31");
+    }
+
+    // d_bucket_ends[s]: absolute end (in records, inside the slot) of the bucket that rank s
+    // filled; n_keys_ub: the k-mers they hold (the sum of what the senders counted)
+    int mg_skm_insert_buckets(const void *d_bucket_ends, uint64_t n_keys_ub, uint32_t slot) override {
+        if (deferred_error != KTG_OK) return fail(deferred_error, "build is void after an earlier error");
+        KTG_TRY(skm_check());
+        if (slot >= MG_SLOTS) return fail(KTG_ERR_INVALID, "slot out of range");
+        if (n_keys_ub == 0) return KTG_OK;
+        mg_mode = mg_local_sketch = true;
+        const u128 *rx = (const u128 *)b_rx.p + (size_t)slot * skm_slot_records();
+        KTG_TRY(skm_unroll(rx, (const unsigned long long *)d_bucket_ends, skm_cap, tab.world, n_keys_ub));
+        KTG_TRY(sync()); // the receive slot may be written again
+        return KTG_OK;
+    }
+
+    int mg_skm_spill(void **d_records, uint64_t *n) override {
+        unsigned long long v = 0;
+        *d_records = b_mg_spill.p;
+        *n = 0;
+        if (!b_mg_cur.p) return KTG_OK;
+        KTG_CUDA(cudaMemcpyAsync(&v, mg_spill_cursor(), 8, cudaMemcpyDeviceToHost, stream));
+        KTG_TRY(sync());
+        if (v > skm_spill_cap) {
+            deferred_error = KTG_ERR_TABLE_FULL;
+            return fail(KTG_ERR_TABLE_FULL, "%llu records overflowed the exchange spill list", v - skm_spill_cap);
+        }
+        *n = v;
+        return KTG_OK;
+    }
+
+    // group n records by owner (owner-major copy in a buffer of the handle), counts[world]
+    int mg_skm_partition_records(const void *d_records, uint64_t n, void **d_out, uint64_t *counts) override {
+        KTG_TRY(skm_check());
+        const uint32_t W = tab.world;
+        for (uint32_t i = 0; i < W; ++i) counts[i] = 0;
+        *d_out = nullptr;
+        if (n == 0) return KTG_OK;
+        KTG_TRY(b_skm_part.ensure(n * sizeof(u128) + (size_t)2 * MAX_P2P_WORLD * 8 + 64));
+        u128 *out = (u128 *)b_skm_part.p;
+        unsigned long long *cnt = (unsigned long long *)(out + n), *cur = cnt + MAX_P2P_WORLD;
+        KTG_CUDA(cudaMemsetAsync(cnt, 0, MAX_P2P_WORLD * 8, stream));
+        const int g = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)props.sms * 8);
+        count_record_owners_kernel<<<g, 256, 0, stream>>>((const u128 *)d_records, n, k, W, cnt);
+        unsigned long long h[MAX_P2P_WORLD], start[MAX_P2P_WORLD];
+        KTG_CUDA(cudaMemcpyAsync(h, cnt, MAX_P2P_WORLD * 8, cudaMemcpyDeviceToHost, stream));
+        KTG_TRY(sync());
+        unsigned long long run = 0;
+        for (uint32_t i = 0; i < (uint32_t)MAX_P2P_WORLD; ++i) {
+            start[i] = run;
+            if (i < W) {
+                counts[i] = h[i];
+                run += h[i];
+            }
+        }
+        KTG_CUDA(cudaMemcpyAsync(cur, start, MAX_P2P_WORLD * 8, cudaMemcpyHostToDevice, stream));
+        scatter_record_owners_kernel<<<g, 256, 0, stream>>>((const u128 *)d_records, n, k, W, cur, out);
+        KTG_CUDA(cudaGetLastError());
+        KTG_TRY(sync()); // `start` is on this stack frame
+        *d_out = out;
+        return KTG_OK;
+    }
+
+    // a flat array of records this rank owns (what the spill route delivered)
+    int mg_skm_insert_records(const void *d_records, uint64_t n) override {
+        if (deferred_error != KTG_OK) return fail(deferred_error, "build is void after an earlier error");
+        KTG_TRY(skm_check());
+        if (n == 0) return KTG_OK;
+        KTG_TRY(b_skm_cnt.ensure(((size_t)MG_SLOTS * SKM_CNT_STRIDE + 4) * 8));
+        mg_mode = mg_local_sketch = true;
+        const unsigned long long end = n;
+        KTG_CUDA(cudaMemcpyAsync(skm_scalar(1), &end, 8, cudaMemcpyHostToDevice, stream));
+        KTG_TRY(sync()); // `end` is on this stack frame
+        const uint64_t cap = (n + UNROLL_THREADS - 1) / UNROLL_THREADS * UNROLL_THREADS;
+        KTG_TRY(skm_unroll((const u128 *)d_records, skm_scalar(1), cap, 1, n * SKM_W));
+        KTG_TRY(sync()); // the caller may free the records
+        return KTG_OK;
+    }
+
+    // owner of a k-mer in the super-k-mer exchange
+    uint32_t skm_owner_of(uint64_t hi, uint64_t lo) override {
+        (void)hi;
+        if (sizeof(K) != 8 || !skm_supported(k)) return 0;
+        return skm_owner(skm_minimizer_of_kmer(lo, k), tab.world);
     }
 
     uint32_t owner_of(uint64_t hi, uint64_t lo) override {

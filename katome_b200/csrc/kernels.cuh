@@ -828,11 +828,13 @@ __global__ void init_cursors_kernel(unsigned long long *cursors, uint64_t n, uin
 // LEVEL 2: bucket q holds keys of sub-table q (or q % sub_mod); they are grouped by page.
 // LEVEL 1: bucket q holds keys of this shard in no particular order (what source rank q sent
 //          in the fused multi-GPU exchange); they are grouped by sub-table.
-template <class K, int LEVEL, int L2S_THREADS = ktg::L2S_THREADS, int L2S_PER = ktg::L2S_PER, int MINB = 2>
+// HLL (level 1 only): the keys also feed the cardinality sketch g_regs (the super-k-mer exchange
+// sketches on the owner's side; sampled keys go straight to the global registers).
+template <class K, int LEVEL, int L2S_THREADS = ktg::L2S_THREADS, int L2S_PER = ktg::L2S_PER, int MINB = 2, bool HLL = false>
 __global__ void __launch_bounds__(L2S_THREADS, MINB)
 scatter_buckets_kernel(const K *__restrict__ keys1, const unsigned long long *__restrict__ fill1,
                        uint64_t cap1, uint64_t tiles_per_bin, uint64_t n_tiles, uint32_t sub_mod,
-                       bool skip_empty, Table<K> t, ScatterOut o) {
+                       bool skip_empty, Table<K> t, ScatterOut o, uint32_t *__restrict__ g_regs = nullptr) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int L2S_TILE = L2S_THREADS * L2S_PER;
     const uint32_t n2 = LEVEL == 2 ? t.pages_per_sub() : t.n_sub;
@@ -850,7 +852,7 @@ scatter_buckets_kernel(const K *__restrict__ keys1, const unsigned long long *__
         if (base >= end) continue;
         K key[L2S_PER];
         uint32_t bin[L2S_PER];
-        uint32_t vmask = 0;
+        uint32_t vmask = 0, sampled = 0;
         KTG_PHASE_BEGIN();
 #pragma unroll
         for (int j = 0; j < L2S_PER; ++j) {
@@ -858,9 +860,14 @@ scatter_buckets_kernel(const K *__restrict__ keys1, const unsigned long long *__
             const bool in = i < end;
             key[j] = in ? KeyTraits<K>::load_stream(&keys1[i]) : (K)0;
             if (LEVEL == 2) bin[j] = (KeyTraits<K>::slot_hash(key[j]) & t.sub_mask) >> t.page_log2;
-            else bin[j] = place_of(KeyTraits<K>::hash(key[j]), t.world, t.n_sub).part;
+            else {
+                const uint64_t h = KeyTraits<K>::hash(key[j]);
+                bin[j] = place_of(h, t.world, t.n_sub).part;
+                if (HLL && hll_sampled(h)) sampled |= 1u << j;
+            }
             if (in && !(skip_empty && key[j] == KeyTraits<K>::empty())) vmask |= 1u << j; // padding of the exchange
         }
+        if (HLL) hll_update_tile<K, L2S_PER>(g_regs, key, sampled & vmask);
 #ifdef KTG_PHASE_TIMERS
         if (threadIdx.x == 0 && key[L2S_PER - 1] == (K)12345) g_phase_cycles[7] = 1; // wait for the loads
 #endif

@@ -576,6 +576,85 @@ int ktg_mg_insert_spill(ktg_builder *b, const void *d_keys, uint64_t n) {
     return b->impl->mg_insert_spill(d_keys, n);
 }
 
+// ---- the same exchange in super-k-mer records (superkmer.cuh) ----
+int ktg_mg_skm_supported(uint32_t k) { return ktg::skm_supported(k) ? 1 : 0; }
+
+int ktg_mg_skm_plan(ktg_builder *b, uint64_t max_windows, int *needs_realloc) {
+    KTG_ENTER(b);
+    if (!needs_realloc) return fail(KTG_ERR_INVALID, "null argument");
+    return b->impl->mg_skm_plan(max_windows, needs_realloc);
+}
+
+int ktg_mg_skm_prepare(ktg_builder *b, uint64_t max_windows, void **rx_base, uint64_t *rx_bytes, uint64_t *bucket_cap) {
+    KTG_ENTER(b);
+    if (!rx_base || !rx_bytes || !bucket_cap) return fail(KTG_ERR_INVALID, "null argument");
+    return b->impl->mg_skm_prepare(max_windows, rx_base, rx_bytes, bucket_cap);
+}
+
+int ktg_mg_skm_scatter_reads_device(ktg_builder *b, const void *d_bases, const void *d_offsets, uint64_t n_reads,
+                                    uint64_t total_bases, void *const *peer_rx, uint32_t slot, int first_of_batch,
+                                    void *send_stream, void **d_cursors, void **d_key_counts) {
+    KTG_ENTER(b);
+    if (!peer_rx || !d_cursors || !d_key_counts) return fail(KTG_ERR_INVALID, "null argument");
+    return b->impl->mg_skm_scatter_reads((const uint8_t *)d_bases, (const uint64_t *)d_offsets, n_reads, total_bases,
+                                         peer_rx, slot, first_of_batch, (cudaStream_t)send_stream, d_cursors,
+                                         d_key_counts);
+}
+
+int ktg_mg_skm_insert_buckets(ktg_builder *b, const void *d_bucket_ends, uint64_t n_keys_ub, uint32_t slot) {
+    KTG_ENTER(b);
+    if (!d_bucket_ends) return fail(KTG_ERR_INVALID, "null argument");
+    return b->impl->mg_skm_insert_buckets(d_bucket_ends, n_keys_ub, slot);
+}
+
+int ktg_mg_skm_spill(ktg_builder *b, void **d_records, uint64_t *n) {
+    KTG_ENTER(b);
+    if (!d_records || !n) return fail(KTG_ERR_INVALID, "null argument");
+    return b->impl->mg_skm_spill(d_records, n);
+}
+
+int ktg_mg_skm_partition_records(ktg_builder *b, const void *d_records, uint64_t n, void **d_out, uint64_t *counts) {
+    KTG_ENTER(b);
+    if (!d_out || !counts) return fail(KTG_ERR_INVALID, "null argument");
+    return b->impl->mg_skm_partition_records(d_records, n, d_out, counts);
+}
+
+int ktg_mg_skm_insert_records(ktg_builder *b, const void *d_records, uint64_t n) {
+    KTG_ENTER(b);
+    return b->impl->mg_skm_insert_records(d_records, n);
+}
+
+uint32_t ktg_mg_skm_owner_of(const ktg_builder *b, uint64_t key_hi, uint64_t key_lo) {
+    if (!b || !b->impl) return 0;
+    return b->impl->skm_owner_of(key_hi, key_lo);
+}
+
+// Host-only twin of the sending kernel's per-item logic (no device needed): cuts the windows
+// of n_items work items into super-k-mer records.
+int ktg_skm_items_host(const uint64_t *packed, const uint64_t *pos, const uint32_t *valid, uint64_t n_items, uint32_t k,
+                       uint32_t world, uint64_t *records_lo_hi, uint64_t cap, uint64_t *n_records) {
+    if (!packed || !pos || !valid || !records_lo_hi || !n_records) return fail(KTG_ERR_INVALID, "null argument");
+    if (!ktg::skm_supported(k) || world == 0 || world > (uint32_t)ktg::MAX_P2P_WORLD)
+        return fail(KTG_ERR_INVALID, "unsupported k or world");
+    uint64_t n = 0;
+    for (uint64_t i = 0; i < n_items; ++i) {
+        ktg::u128 out[ktg::SKM_W];
+        const uint32_t c = ktg::skm_item_host(packed, pos[i], valid[i] & 0xFFFFu, k, world, out);
+        for (uint32_t j = 0; j < c; ++j, ++n) {
+            if (n >= cap) return fail(KTG_ERR_INVALID, "record buffer too small");
+            records_lo_hi[2 * n] = (uint64_t)out[j];
+            records_lo_hi[2 * n + 1] = (uint64_t)(out[j] >> 64);
+        }
+    }
+    *n_records = n;
+    return KTG_OK;
+}
+
+uint32_t ktg_skm_owner_of_kmer(uint64_t kmer, uint32_t k, uint32_t world) {
+    if (!ktg::skm_supported(k) || world == 0) return 0;
+    return ktg::skm_owner(ktg::skm_minimizer_of_kmer(kmer, k), world);
+}
+
 int ktg_ipc_get_handle(const void *dev_ptr, uint8_t handle[64]) {
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
     if (!dev_ptr || !handle) return fail(KTG_ERR_INVALID, "null argument");

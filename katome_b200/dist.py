@@ -4,8 +4,13 @@ The table is sharded by owner(key) = hash(canonical k-mer) range-reduced to [0, 
 (SURVEY 8e).  Shards are disjoint by construction, so the merged GIR is their
 concatenation and all whole-graph statistics are plain reductions.
 
-Two data paths:
-  fused (default on one node, world <= 8): the extraction kernel of every rank writes its
+Three data paths:
+  fused, super-k-mers (default on one node, world <= 8, 23 <= k <= 31): owner(k-mer) is a
+      function of its minimizer; the sending kernel cuts every read into runs of windows that
+      share a minimizer and writes each run as ONE 16-byte record straight into the owner's HBM
+      over NVLink (2.9 bytes per window instead of 8); the owner unrolls the records into
+      canonical k-mers while it partitions them by sub-table (csrc/superkmer.cuh).
+  fused, keys (other k): the extraction kernel of every rank writes its
       keys, grouped by owner, straight into the owners' HBM over NVLink (CUDA IPC mapped peer
       memory); the owner partitions what it received by sub-table and carries on as on one
       GPU.  NCCL only carries the small control messages (batch size, sketch, bucket fills)
@@ -25,7 +30,7 @@ import torch.distributed as dist
 
 import os
 
-from .gir import DeviceArray, GpuGIR, ipc_close, ipc_get_handle, ipc_open
+from .gir import DeviceArray, GpuGIR, ipc_close, ipc_get_handle, ipc_open, skm_supported
 
 MASK64 = (1 << 64) - 1
 
@@ -70,14 +75,22 @@ class ShardedGIR:
     """One shard of a GIR that is hash-partitioned over the ranks of a process group."""
 
     def __init__(self, k: int = 40, reverse_complement: bool = True, *, group=None, edges_count: Optional[int] = None,
-                 fused: Optional[bool] = None, **kw):
+                 fused: Optional[bool] = None, exchange: Optional[str] = None, **kw):
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.device = torch.device("cuda", torch.cuda.current_device())
+        mode = exchange or os.environ.get("KTG_EXCHANGE", "fused")  # fused | skm | keys | nccl
         if fused is None:
-            fused = self.world <= 8 and os.environ.get("KTG_EXCHANGE", "fused") != "nccl"
+            fused = self.world <= 8 and mode != "nccl"
         self.fused = bool(fused)
+        # Which fused exchange.  Super-k-mer records cost the owner one more pass (unrolling them)
+        # and save the sender 5 of every 8 NVLink bytes: measured on B200s that loses at 2 GPUs
+        # (74.7 vs 82.3 G k-mers/s on C2) and pays once the key exchange is NVLink bound, so it
+        # is the default from SKM_MIN_WORLD ranks on ("skm" / "keys" force one).
+        want_skm = mode == "skm" or (mode == "fused" and self.world >= self.SKM_MIN_WORLD)
+        self.exchange = "nccl" if not self.fused else ("skm" if skm_supported(k) and want_skm else "keys")
+        self._mapped_for = None
         if self.fused:
             kw.setdefault("force_partition", True)  # the fused path has no unpartitioned mode
         self.gir = GpuGIR(k, reverse_complement, edges_count=edges_count, world_size=self.world, rank=self.rank,
@@ -99,6 +112,7 @@ class ShardedGIR:
     # is one chunk; KTG_MG_CHUNKS overrides it.
     CHUNKS = 1
     MIN_CHUNK_READS = 1 << 16
+    SKM_MIN_WORLD = int(os.environ.get("KTG_SKM_MIN_WORLD", 8))
 
     def _unmap_peers(self):
         for r, p in enumerate(self._peers):
@@ -111,7 +125,11 @@ class ShardedGIR:
         map everybody's buffer; collective."""
         self._unmap_peers()
         dist.barrier(self.group)  # nobody still has the old buffer mapped when it is freed
-        base, self._slot_bytes, self._cap, _ = self.gir.mg_prepare(gmax)
+        if self.exchange == "skm":
+            base, self._slot_bytes, self._cap = self.gir.mg_skm_prepare(gmax)
+        else:
+            base, self._slot_bytes, self._cap, _ = self.gir.mg_prepare(gmax)
+        self._mapped_for = self.exchange
         mine = torch.frombuffer(bytearray(ipc_get_handle(base)), dtype=torch.uint8).to(self.device)
         allh = [torch.empty_like(mine) for _ in range(self.world)]
         dist.all_gather(allh, mine, group=self.group)
@@ -140,7 +158,7 @@ class ShardedGIR:
         gmax, n_chunks_all = (int(x) for x in t.tolist())
         if gmax == 0:
             return
-        if not self._peers or self.gir.mg_plan(gmax):
+        if not self._peers or self._mapped_for != "keys" or self.gir.mg_plan(gmax):
             self._map_peers(gmax)
         cap = self._cap
         send.wait_stream(main)  # the inputs are ready; the previous batch has been consumed
@@ -205,6 +223,41 @@ class ShardedGIR:
             self.gir.mg_insert_spill(recv, sum(rcounts))
             self._keep = (keep, recv)
 
+    def _add_reads_skm(self, d_bases, d_offsets, n_reads: int, total_bases: int):
+        """One batch through the super-k-mer exchange (one chunk, everything on the current stream)."""
+        W, dev, k = self.world, self.device, self.k
+        ub = max(int(total_bases) - n_reads * (k - 1), 0)  # windows if every read is accepted
+        t = torch.tensor([ub], dtype=torch.int64, device=dev)
+        # also orders "every rank has finished reading its receive buffer" before anybody writes again
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        gmax = int(t.item())
+        if gmax == 0:
+            return
+        if not self._peers or self._mapped_for != "skm" or self.gir.mg_skm_plan(gmax):
+            self._map_peers(gmax)
+        cap = self._cap
+        cur_ptr, kc_ptr = self.gir.mg_skm_scatter_reads_device(d_bases, d_offsets, n_reads, total_bases, self._peers)
+        cur = torch.as_tensor(DeviceArray(cur_ptr, W), device=dev)
+        kc = torch.as_tensor(DeviceArray(kc_ptr, W + 1), device=dev)  # [W]: records this rank spilled
+        send = torch.stack([cur, kc[:W], kc[W:].expand(W)], dim=1).contiguous()
+        got = torch.empty_like(send)
+        dist.all_to_all_single(got, send, group=self.group)  # also: the writers' kernels have completed
+        fill = (got[:, 0] - self.rank * cap).clamp_(max=cap)
+        ends = torch.arange(W, dtype=torch.int64, device=dev) * cap + fill
+        n_rec, n_keys, n_spilled = (int(x) for x in torch.stack([fill.sum(), got[:, 1].sum(), got[:, 2].sum()]).tolist())
+        self.gir.mg_skm_insert_buckets(ends, n_keys, 0)
+        self._keep = (send, got, ends)
+        self.exchanged_bytes += n_rec * 16 * (W - 1) // W
+        if n_spilled:  # records that did not fit their bucket (skew), on any rank: routed the slow way
+            sp_ptr, n_sp = self.gir.mg_skm_spill()
+            ptr, counts = self.gir.mg_skm_partition_records(sp_ptr, n_sp)
+            n = sum(counts)
+            recs = torch.as_tensor(DeviceArray(ptr, n * 2), device=dev) if n else \
+                torch.empty(0, dtype=torch.int64, device=dev)
+            recv, rcounts = exchange_keys(recs, counts, 2, self.group)
+            self.gir.mg_skm_insert_records(recv, sum(rcounts))
+            self._keep = (send, got, ends, recv)
+
     def add_reads_host(self, h_bases: torch.Tensor, h_offsets: torch.Tensor, n_reads: int, chunks: int = 4):
         """Reads in (pinned) host memory: h_bases uint8, h_offsets int64 [n_reads + 1].  The batch is
         copied in chunks on a copy stream, chunk i+1 while chunk i is exchanged and inserted."""
@@ -250,6 +303,8 @@ class ShardedGIR:
             self._stage_used[s] = True
 
     def add_reads_device(self, d_bases, d_offsets, n_reads: int, total_bases: int):
+        if self.exchange == "skm":
+            return self._add_reads_skm(d_bases, d_offsets, n_reads, total_bases)
         if self.fused:
             return self._add_reads_fused(d_bases, d_offsets, n_reads, total_bases)
         ptr, counts = self.gir.partition_reads_device(d_bases, d_offsets, n_reads, total_bases)

@@ -349,6 +349,48 @@ class GpuGIR:
     def mg_insert_spill(self, d_keys, n: int):
         _check(self._L.ktg_mg_insert_spill(self._h, _ptr(d_keys), int(n)))
 
+    # ---- the same exchange in super-k-mer records (include/katome_gpu.h) ---------------------
+    def mg_skm_plan(self, max_windows: int) -> bool:
+        need = C.c_int(0)
+        _check(self._L.ktg_mg_skm_plan(self._h, int(max_windows), C.byref(need)))
+        return bool(need.value)
+
+    def mg_skm_prepare(self, max_windows: int):
+        """-> (receive buffer pointer, bytes of one slot, bucket capacity in records)"""
+        base, nbytes, cap = C.c_void_p(), C.c_uint64(), C.c_uint64()
+        _check(self._L.ktg_mg_skm_prepare(self._h, int(max_windows), C.byref(base), C.byref(nbytes), C.byref(cap)))
+        return int(base.value), int(nbytes.value), int(cap.value)
+
+    def mg_skm_scatter_reads_device(self, d_bases, d_offsets, n_reads: int, total_bases: int, peer_rx, slot: int = 0,
+                                    first_of_batch: bool = True, send_stream: Optional[int] = None):
+        """-> (bucket ends pointer, key counts pointer): world u64 each"""
+        arr = (C.c_void_p * self.world_size)(*[C.c_void_p(int(p)) for p in peer_rx])
+        cur, kc = C.c_void_p(), C.c_void_p()
+        _check(self._L.ktg_mg_skm_scatter_reads_device(self._h, _ptr(d_bases), _ptr(d_offsets), int(n_reads),
+                                                       int(total_bases), arr, int(slot), int(bool(first_of_batch)),
+                                                       C.c_void_p(send_stream or None), C.byref(cur), C.byref(kc)))
+        return int(cur.value), int(kc.value)
+
+    def mg_skm_insert_buckets(self, d_bucket_ends, n_keys_ub: int, slot: int = 0):
+        _check(self._L.ktg_mg_skm_insert_buckets(self._h, _ptr(d_bucket_ends), int(n_keys_ub), int(slot)))
+
+    def mg_skm_spill(self):
+        p, n = C.c_void_p(), C.c_uint64()
+        _check(self._L.ktg_mg_skm_spill(self._h, C.byref(p), C.byref(n)))
+        return int(p.value or 0), int(n.value)
+
+    def mg_skm_partition_records(self, d_records, n: int):
+        out = C.c_void_p()
+        counts = (C.c_uint64 * self.world_size)()
+        _check(self._L.ktg_mg_skm_partition_records(self._h, _ptr(d_records), int(n), C.byref(out), counts))
+        return int(out.value or 0), [int(c) for c in counts]
+
+    def mg_skm_insert_records(self, d_records, n: int):
+        _check(self._L.ktg_mg_skm_insert_records(self._h, _ptr(d_records), int(n)))
+
+    def mg_skm_owner_of(self, hi: int, lo: int) -> int:
+        return int(self._L.ktg_mg_skm_owner_of(self._h, hi, lo))
+
     # ---- observability -----------------------------------------------------------------
     def profile(self) -> dict:
         n = C.c_uint32(0)
@@ -364,6 +406,11 @@ class GpuGIR:
         i = L.KtgInfo()
         _check(self._L.ktg_get_info(self._h, C.byref(i)))
         return {name: int(getattr(i, name)) for name, _ in L.KtgInfo._fields_}
+
+
+def skm_supported(k: int) -> bool:
+    """can the multi-GPU exchange of this k run in super-k-mer records?"""
+    return bool(L.lib().ktg_mg_skm_supported(int(k)))
 
 
 def ipc_get_handle(dev_ptr: int) -> bytes:

@@ -27,8 +27,11 @@ for k, n, L, G in ((31, 6000, 150, 200_000), (63, 3000, 150, 100_000)):
     half = n // world
     mine = torch.from_numpy(reads[rank * half * L:(rank + 1) * half * L]).cuda()
     offs = torch.arange(0, (half + 1) * L, L, dtype=torch.int64, device="cuda")
-    for kw in ({}, {"fused": False}, {"force_pages": True}, {"fused": False, "force_partition": True, "sub_table_log2_bytes": 16}):
+    for kw in ({}, {"exchange": "skm"}, {"fused": False}, {"force_pages": True, "exchange": "skm"},
+               {"fused": False, "force_partition": True, "sub_table_log2_bytes": 16}):
         sg = ShardedGIR(k, True, **kw)
+        # super-k-mer records need 23 <= k <= 31; below 8 ranks they are opt-in
+        assert sg.exchange == ("nccl" if kw.get("fused") is False else "skm" if k <= 31 and "exchange" in kw else "keys")
         for _ in range(2):  # reset + rebuild gives the same table
             sg.reset()
             sg.add_reads_device(mine[: (half // 2) * L], offs[: half // 2 + 1], half // 2, (half // 2) * L)

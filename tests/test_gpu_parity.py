@@ -466,6 +466,125 @@ def test_fused_exchange_ranks_emulated_on_one_gpu(K, k, W):
         g.close()
 
 
+def _skm_exchange_emulated(K, gs, batches, k, claim=None):
+    """The protocol of ShardedGIR._add_reads_skm with all ranks in one process on one GPU.  `claim`
+    under-provisions the receive buckets on purpose (forces the spill route).  -> spilled records"""
+    W = len(gs)
+    gmax = claim or max(max(nb - n * (k - 1), 0) for (_, _, n, nb) in batches)
+    prep = [g.mg_skm_prepare(gmax) for g in gs]
+    peers = [p[0] for p in prep]
+    cap = prep[0][2]
+    assert all(p[2] == cap for p in prep)
+    outs = [g.mg_skm_scatter_reads_device(d, o, n, nb, peers) for g, (d, o, n, nb) in zip(gs, batches)]
+    curs = [torch.as_tensor(K.DeviceArray(c, W), device="cuda") for c, _ in outs]
+    kcs = [torch.as_tensor(K.DeviceArray(kc, W), device="cuda") for _, kc in outs]
+    torch.cuda.synchronize()
+    for r, g in enumerate(gs):
+        got = torch.stack([c[r] for c in curs])  # what the all-to-all delivers to rank r
+        n_keys = int(sum(int(kc[r]) for kc in kcs))
+        fill = (got - r * cap).clamp_(max=cap)
+        ends = torch.arange(W, dtype=torch.int64, device="cuda") * cap + fill
+        g.mg_skm_insert_buckets(ends, n_keys)
+        torch.cuda.synchronize()
+    routed = [[] for _ in range(W)]
+    n_spilled = 0
+    for g in gs:
+        ptr, n = g.mg_skm_spill()
+        n_spilled += n
+        if n:
+            out, counts = g.mg_skm_partition_records(ptr, n)
+            assert sum(counts) == n
+            buf = torch.as_tensor(K.DeviceArray(out, n * 2), device="cuda").clone()
+            o = 0
+            for dst in range(W):
+                routed[dst].append(buf[o:o + counts[dst] * 2])
+                o += counts[dst] * 2
+    for r, g in enumerate(gs):
+        if routed[r]:
+            recs = torch.cat(routed[r])
+            g.mg_skm_insert_records(recs, recs.numel() // 2)
+            torch.cuda.synchronize()
+    return n_spilled, [int(sum(int(kc[r]) for kc in kcs)) for r in range(W)]
+
+
+def _assert_shards_equal_oracle(gs, cpu, owner):
+    digs = [g.digest() for g in gs]
+    cd = cpu.digest()
+    assert (sum(d[0] for d in digs) & (2**64 - 1), sum(d[1] for d in digs), sum(d[2] for d in digs),
+            max(d[3] for d in digs)) == cd
+    parts = [g.export_edges(sorted=True) for g in gs]
+    for r, (hi, lo, w) in enumerate(parts):
+        assert all(owner(gs[r], int(h), int(x)) == r for h, x in list(zip(hi.tolist(), lo.tolist()))[:200])
+    hi = np.concatenate([p[0] for p in parts]); lo = np.concatenate([p[1] for p in parts])
+    w = np.concatenate([p[2] for p in parts])
+    order = np.lexsort((lo, hi))
+    ehi, elo, ew = cpu.export_edges()
+    assert np.array_equal(hi[order], ehi) and np.array_equal(lo[order], elo) and np.array_equal(w[order], ew)
+
+
+@pytest.mark.parametrize("k,W,rc", [(31, 2, True), (31, 8, True), (23, 3, True), (27, 4, False), (31, 1, True)])
+def test_superkmer_exchange_ranks_emulated_on_one_gpu(K, k, W, rc):
+    """super-k-mer exchange: records into the owners' receive buckets, unrolled there into the staged
+    sub-table buckets; a uniform batch, a ragged one with rejected reads, and a low-complexity one"""
+    from oracle import oracle as O
+    seed, G, L, n = 4321 + k, 120_000, 150, 3000 * W
+    host = O.synth_reads(seed, G, L, 5000, 0, n)
+    rng = np.random.default_rng(k * 10 + W)
+    ragged = H.random_reads(rng, 400 * W, k, k + 200, n_rate=0.1) + ["ACGT" * 40, "AT" * 70, "A" * (k + 3)] * W
+    ragged = ragged[: len(ragged) // W * W]
+    low = np.frombuffer((b"A" * L) * (500 * W), dtype=np.uint8)
+    cpu = O.OracleGIR(k)
+    cpu.add_reads(host, np.arange(n + 1, dtype=np.uint64) * L, rc)
+    cpu.add_reads(*H.batch_of(ragged), rc)
+    cpu.add_reads(low, np.arange(500 * W + 1, dtype=np.uint64) * L, rc)
+    s = torch.cuda.current_stream().cuda_stream
+    gs = [K.GpuGIR(k, rc, world_size=W, rank=r, force_pages=True, stream=s) for r in range(W)]
+    sent = 0
+    for data, per in ((host, n // W), (low, 500)):
+        batches = []
+        for r in range(W):
+            d = torch.from_numpy(data[r * per * L:(r + 1) * per * L].copy()).cuda()
+            offs = torch.arange(0, (per + 1) * L, L, dtype=torch.int64, device="cuda")
+            batches.append((d, offs, per, per * L))
+        _, keys = _skm_exchange_emulated(K, gs, batches, k)
+        sent += sum(keys)
+    assert sent == (n + 500 * W) * (L - k + 1)  # the senders' key counts are exact
+    per = len(ragged) // W
+    batches = []
+    for r in range(W):
+        b, o = H.batch_of(ragged[r * per:(r + 1) * per])
+        batches.append((torch.from_numpy(b).cuda(), torch.from_numpy(o.astype(np.int64)).cuda(), per, int(o[-1])))
+    _skm_exchange_emulated(K, gs, batches, k)
+    _assert_shards_equal_oracle(gs, cpu, lambda g, h, x: g.mg_skm_owner_of(h, x))
+    assert sum(g.info()["page_updates"] for g in gs) > 0
+    for g in gs:
+        g.close()
+
+
+def test_superkmer_exchange_spill_route(K):
+    """receive buckets sized for a tenth of the batch: most records take the spill route (grouped by
+    owner, delivered as flat arrays); growth without a hint on the way"""
+    from oracle import oracle as O
+    k, W, L = 31, 3, 100
+    n = 6000 * W
+    host = O.synth_reads(99, 80_000, L, 10000, 0, n)
+    cpu = O.OracleGIR(k)
+    cpu.add_reads(host, np.arange(n + 1, dtype=np.uint64) * L, True)
+    s = torch.cuda.current_stream().cuda_stream
+    gs = [K.GpuGIR(k, True, world_size=W, rank=r, force_partition=True, stream=s) for r in range(W)]
+    per = n // W
+    batches = []
+    for r in range(W):
+        d = torch.from_numpy(host[r * per * L:(r + 1) * per * L].copy()).cuda()
+        offs = torch.arange(0, (per + 1) * L, L, dtype=torch.int64, device="cuda")
+        batches.append((d, offs, per, per * L))
+    spilled, _ = _skm_exchange_emulated(K, gs, batches, k, claim=1000)
+    assert spilled > 0
+    _assert_shards_equal_oracle(gs, cpu, lambda g, h, x: g.mg_skm_owner_of(h, x))
+    for g in gs:
+        g.close()
+
+
 def test_host_mirror_of_owner_matches_device(K):
     from katome_b200 import hashing
     rng = np.random.default_rng(9)
