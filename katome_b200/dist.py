@@ -86,7 +86,8 @@ class ShardedGIR:
         self.fused = bool(fused)
         # Which fused exchange.  Super-k-mer records cost the owner one more pass (unrolling them)
         # and save the sender 5 of every 8 NVLink bytes: measured on B200s that loses at 2 GPUs
-        # (74.7 vs 82.3 G k-mers/s on C2) and pays once the key exchange is NVLink bound, so it
+        # (74.7 vs 82.3 G k-mers/s on C2), ties at 4 (147.5 vs 142.7) and wins at 8 (288 vs 262), where
+        # the key exchange is NVLink bound, so it
         # is the default from SKM_MIN_WORLD ranks on ("skm" / "keys" force one).
         want_skm = mode == "skm" or (mode == "fused" and self.world >= self.SKM_MIN_WORLD)
         self.exchange = "nccl" if not self.fused else ("skm" if skm_supported(k) and want_skm else "keys")
@@ -112,7 +113,7 @@ class ShardedGIR:
     # is one chunk; KTG_MG_CHUNKS overrides it.
     CHUNKS = 1
     MIN_CHUNK_READS = 1 << 16
-    SKM_MIN_WORLD = int(os.environ.get("KTG_SKM_MIN_WORLD", 8))
+    SKM_MIN_WORLD = int(os.environ.get("KTG_SKM_MIN_WORLD", 4))
 
     def _unmap_peers(self):
         for r, p in enumerate(self._peers):

@@ -8,7 +8,7 @@ for N in $1; do
   for X in keys skm; do
     P=$((P+1))
     KTG_EXCHANGE=$X timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
-      --master-port $P bench.py --gpus $N --steps 5 --warmup 3 --no-cpu > gpurun_out/mg_n${N}_$X.json 2> gpurun_out/mg_n${N}_$X.err
+      --master-port $P bench.py --gpus $N --steps 5 --warmup 3 --no-cpu --no-e2e > gpurun_out/mg_n${N}_$X.json 2> gpurun_out/mg_n${N}_$X.err
     echo "N=$N $X rc=$?"; python - <<PY
 import json
 try:
