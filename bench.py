@@ -254,7 +254,9 @@ def run_ours(args):
         assert edig == dig, (edig, dig)
         eprof = builder.profile()
         e2e = {"value": windows_total / (ems / args.steps * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": (n_local * L + (n_local + 1) * 8) * world, "d2h_bytes_per_step": 40 * world,
+               # one GPU: equally long reads need no offsets on the device (generated there); N > 1 copies both
+               "h2d_bytes_per_step": (n_local * L + ((n_local + 1) * 8 if world > 1 else 0)) * world,
+               "d2h_bytes_per_step": 40 * world,
                "ms_per_step": ems / args.steps, "h2d_copy_only_ms": h2d_ms,
                "h2d_gbs": n_local * L / h2d_ms / 1e6,
                "kernels": {n: {"launches": p["launches"], "ms_per_step": p["ms"] / args.steps}

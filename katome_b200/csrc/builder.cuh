@@ -196,6 +196,10 @@ struct BuilderBase {
     cudaEvent_t input_consumed = nullptr;
     uint64_t windows_inserted = 0;
     uint32_t grow_events = 0;
+    // set by the host batcher for the duration of one large ktg_add_reads call: the keys the call
+    // will offer, and "keep staging until flush_hint() or the stage is full"
+    uint64_t call_keys_hint = 0;
+    bool hold_flush = false;
 
     virtual ~BuilderBase() {}
     virtual int init() = 0;
@@ -203,6 +207,8 @@ struct BuilderBase {
                               uint64_t total_bases, const BatchHint *hint = nullptr) = 0;
     virtual int read_counters(uint64_t *reads, uint64_t *bytes) = 0;
     virtual int finalize() = 0;
+    // the host batcher knows that little input is left: a good moment to empty the stage
+    virtual int flush_hint() = 0;
     virtual int reset() = 0;
     virtual int edge_stats(uint32_t threshold, EdgeStats *out) = 0;
     virtual int node_stats(NodeStats *out) = 0;
@@ -449,13 +455,14 @@ template <class K> struct Builder : BuilderBase {
         return (((size_t)1 << page_log2) + (threads / 32) * PQ_CAP) * (sizeof(K) + 4);
     }
     // Streaming page update or L2 atomics?  The sweep reads and writes every slot
-    // (32 B per slot of traffic), the atomic path costs ~2 L2 transactions per key:
-    // the sweep wins once the batch has about as many keys as the table has slots.
+    // (32 B per slot of traffic) and then absorbs ~120 G keys/s, the atomic path runs at
+    // ~34 G keys/s whatever the table size: measured on C2 (109 M slots, sweep 0.55 ms) they
+    // break even at 26 M keys, a quarter of the slots.
     bool use_pages(uint64_t n_keys) const {
         if (cfg.flags & KTG_FLAG_NO_PAGES) return false;
         if (tab.pages_per_sub() > MAX_PAGES_PER_SUB) return false;
         if (cfg.flags & KTG_FLAG_FORCE_PAGES) return true;
-        return 2 * n_keys >= tab.capacity();
+        return 4 * n_keys >= tab.capacity();
     }
 
     int sync() {
@@ -900,6 +907,8 @@ template <class K> struct Builder : BuilderBase {
         if (const char *e = getenv("KTG_STAGE_FACTOR")) factor = atof(e); // tuning knob
         stage_target = std::min<uint64_t>((uint64_t)(factor * (double)tab.capacity()), stage_max_keys());
         stage_room = batch_keys >= stage_target ? batch_keys : stage_target + batch_keys;
+        if (hold_flush && call_keys_hint) // the batcher flushes once, after ~60 % of its input
+            stage_room = std::max(stage_room, std::min<uint64_t>(call_keys_hint / 4 * 3 + batch_keys, stage_max_keys()));
         stage_cap1 = bucket_cap_for(stage_room, n_bins);
         // as large as the stage itself: even a batch made of one key cannot overflow it, so a
         // batch is staged without looking at the spill cursor (it is read when the stage is flushed)
@@ -934,7 +943,7 @@ template <class K> struct Builder : BuilderBase {
         KTG_TRY(scatter(stage_bins, o));
         staged_keys += n_keys;
         nodes_valid = false;
-        if (staged_keys >= stage_target) KTG_TRY(flush_staged());
+        if (staged_keys >= stage_target && !hold_flush) KTG_TRY(flush_staged());
         return KTG_OK;
     }
 
@@ -1032,6 +1041,11 @@ template <class K> struct Builder : BuilderBase {
             return fail(KTG_ERR_SHORT_READ, "Read is too short!");
         }
         return KTG_OK;
+    }
+
+    int flush_hint() override {
+        if (deferred_error != KTG_OK || 4 * staged_keys < tab.capacity()) return KTG_OK;
+        return flush_staged();
     }
 
     int finalize() override {

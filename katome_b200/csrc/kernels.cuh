@@ -820,6 +820,13 @@ scatter_keys_kernel(const K *__restrict__ keys, uint64_t n, Table<K> t, uint32_t
 // keys2[(b*n2+p)*cap2, +cap2) and cursors2[b*n2+p] starts at (b*n2+p)*cap2.
 constexpr int L2S_THREADS = 512, L2S_PER = 8, L2S_TILE = L2S_THREADS * L2S_PER;
 
+// offsets of a batch of equally long reads: out[i] = first + i * len (the host batcher does not
+// copy 8 bytes per read over PCIe when it has seen that they are all the same)
+__global__ void fill_offsets_kernel(uint64_t *__restrict__ out, uint64_t n, uint64_t first, uint64_t len) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = first + i * len;
+}
+
 __global__ void init_cursors_kernel(unsigned long long *cursors, uint64_t n, uint64_t cap) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) cursors[i] = i * cap;

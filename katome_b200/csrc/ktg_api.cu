@@ -10,10 +10,12 @@ using namespace ktg;
 
 struct ktg_builder {
     std::unique_ptr<BuilderBase> impl;
-    // double-buffered device staging for host batches
-    DeviceBuf st_bases[2], st_offs[2];
-    cudaEvent_t st_free[2] = {nullptr, nullptr}; // staging buffer consumed by the compute stream
-    cudaEvent_t st_ready[2] = {nullptr, nullptr};
+    // device staging for host batches: two buffers for the full chunks, four small ones for the
+    // short chunks a large batch ends in (all of those are copied while the last flush runs)
+    static constexpr int N_STAGE = 6;
+    DeviceBuf st_bases[N_STAGE], st_offs[N_STAGE];
+    cudaEvent_t st_free[N_STAGE] = {}; // staging buffer consumed by the compute stream
+    cudaEvent_t st_ready[N_STAGE] = {};
 };
 
 extern "C" {
@@ -63,7 +65,7 @@ void ktg_destroy(ktg_builder *b) {
     cudaSetDevice(b->impl->device);
     cudaStreamSynchronize(b->impl->stream);
     cudaStreamSynchronize(b->impl->copy_stream);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < ktg_builder::N_STAGE; ++i) {
         b->st_bases[i].release();
         b->st_offs[i].release();
         if (b->st_free[i]) cudaEventDestroy(b->st_free[i]);
@@ -106,49 +108,77 @@ int ktg_add_reads(ktg_builder *b, const uint8_t *bases, const uint64_t *offsets,
     // chunk i and only one chunk's kernels are exposed at the end
     uint64_t CHUNK = 64ull << 20;
     if (const char *e = getenv("KTG_CHUNK_MB")) CHUNK = (uint64_t)std::max(1, atoi(e)) << 20; // tuning knob
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < ktg_builder::N_STAGE; ++i) {
         if (!b->st_free[i]) {
             KTG_CUDA(cudaEventCreateWithFlags(&b->st_free[i], cudaEventDisableTiming));
             KTG_CUDA(cudaEventCreateWithFlags(&b->st_ready[i], cudaEventDisableTiming));
         }
     }
     // chunk boundaries: largest r1 with offsets[r1] - offsets[r] <= CHUNK (at least one read)
+    // Only what cannot start before the LAST copy has landed is exposed: the last chunk's kernels,
+    // the flush of whatever is staged then, the caller's first query.  So a large batch (>= 3 chunks)
+    //   * ends in four short chunks (the last 0.5-1.5 CHUNK), each with its own staging buffer, all
+    //     queued on the copy engine as soon as the last full chunk is;
+    //   * is flushed once on the way, after ~55 % of its bytes (the builder's own cadence, a flush per
+    //     0.75 x capacity keys, is held back: every extra sweep of the table is GPU time that queues
+    //     up behind the copies), which leaves the final flush ~40 % of the keys.
     std::vector<uint64_t> cut{0};
+    const uint64_t total = offsets[n_reads] - offsets[0];
+    const bool large = total >= 3 * CHUNK && !getenv("KTG_NO_TAPER");
+    size_t tail_first = (size_t)-1; // first of the short chunks
     while (cut.back() < n_reads) {
         const uint64_t r = cut.back();
+        uint64_t limit = CHUNK;
+        if (large) {
+            const uint64_t left = offsets[n_reads] - offsets[r];
+            if (left <= CHUNK + CHUNK / 2) {
+                if (tail_first == (size_t)-1) tail_first = cut.size() - 1;
+                limit = std::max<uint64_t>(left / (4 - std::min<size_t>(3, cut.size() - 1 - tail_first)), 1u << 20);
+            }
+        }
         uint64_t lo = r + 1, hi = n_reads;
         while (lo < hi) {
             uint64_t mid = (lo + hi + 1) / 2;
-            if (offsets[mid] - offsets[r] <= CHUNK) lo = mid;
+            if (offsets[mid] - offsets[r] <= limit) lo = mid;
             else hi = mid - 1;
         }
         cut.push_back(lo);
     }
     const size_t n_chunks = cut.size() - 1;
-    // The copy of chunk i+1 is queued BEFORE the kernels of chunk i are launched: ingest_device
-    // synchronises the compute stream (counters, table sizing), and the copy engine must not
-    // sit idle meanwhile.
-    auto issue_copy = [&](size_t c) -> int {
-        const uint64_t r = cut[c], r1 = cut[c + 1], nb = offsets[r1] - offsets[r], nr = r1 - r;
-        const int s = (int)(c & 1);
-        // the staging buffer may still be read by the kernels of two chunks ago
-        KTG_CUDA(cudaStreamWaitEvent(impl->copy_stream, b->st_free[s], 0));
-        if (b->st_bases[s].cap < nb + 64 || b->st_offs[s].cap < (nr + 1) * 8) {
-            KTG_CUDA(cudaStreamSynchronize(impl->stream)); // reallocation frees the old buffer
-            KTG_CUDA(cudaStreamSynchronize(impl->copy_stream));
-            KTG_TRY(b->st_bases[s].ensure(std::max<uint64_t>(nb, CHUNK) + 64));
-            KTG_TRY(b->st_offs[s].ensure((nr + 1) * 8));
+    // One flush on the way, after ~55 % of the bytes: it hides behind the remaining copies and leaves
+    // the final one ~40 % of the keys.  Measured on C2 (8.3 ms of copies): the builder's own cadence
+    // (4 flushes) 12.55 ms per build, one flush at 73 % 12.8, at 58 % 11.8, two (44 %, 73 %) 11.9.
+    std::vector<char> flush_here(n_chunks, 0);
+    if (large) {
+        const size_t last_full = tail_first != (size_t)-1 ? tail_first - 1 : n_chunks - 1;
+        for (uint64_t pct : {55u}) {
+            size_t c = 0;
+            while (c + 1 < n_chunks && offsets[cut[c + 1]] - offsets[0] < total / 100 * pct) ++c;
+            flush_here[std::min(c, last_full)] = 1;
         }
-        KTG_CUDA(cudaMemcpyAsync(b->st_bases[s].p, bases + offsets[r], nb, cudaMemcpyHostToDevice, impl->copy_stream));
-        KTG_CUDA(cudaMemcpyAsync(b->st_offs[s].p, offsets + r, (nr + 1) * 8, cudaMemcpyHostToDevice, impl->copy_stream));
-        KTG_CUDA(cudaEventRecord(b->st_ready[s], impl->copy_stream));
-        trace("copy queued", c);
-        return KTG_OK;
+    }
+    struct Hold { // the builder keeps its stage until flush_hint() / the end of this call
+        BuilderBase *p;
+        ~Hold() { p->hold_flush = false; p->call_keys_hint = 0; }
+    } hold{impl};
+    if (large) {
+        impl->hold_flush = true;
+        impl->call_keys_hint = total > n_reads * (uint64_t)(impl->k - 1) ? total - n_reads * (uint64_t)(impl->k - 1) : 0;
+    }
+    // staging buffer of chunk c: the full chunks alternate between 0 and 1, the short ones at
+    // the end have one each
+    auto slot_of = [&](size_t c) -> int {
+        return c >= tail_first ? 2 + (int)std::min<size_t>(c - tail_first, ktg_builder::N_STAGE - 3) : (int)(c & 1);
     };
     // What the offsets on the host already tell about a chunk: one read length or ragged, and how
-    // many windows at most; with that the chunk is queued without a device round trip.
-    auto hint_of = [&](size_t c) {
-        BatchHint h;
+    // many windows at most; with that the chunk is queued without a device round trip, and the
+    // offsets of a uniform chunk are generated on the device instead of copied (8 bytes per read:
+    // 8 % of the PCIe traffic of 100 bp reads).
+    std::vector<BatchHint> hints(n_chunks);
+    std::vector<char> have_hint(n_chunks, 0);
+    auto hint_of = [&](size_t c) -> const BatchHint & {
+        if (have_hint[c]) return hints[c];
+        BatchHint &h = hints[c];
         const uint64_t r = cut[c], r1 = cut[c + 1], kk = impl->k, len0 = offsets[r + 1] - offsets[r];
         bool uniform = true;
         uint64_t wub = 0;
@@ -159,24 +189,53 @@ int ktg_add_reads(ktg_builder *b, const uint8_t *bases, const uint64_t *offsets,
         }
         h.ulen = (uniform && len0 <= 0xFFFFFFFFull) ? (uint32_t)len0 : 0;
         h.windows_ub = wub;
+        have_hint[c] = 1;
         return h;
     };
-    KTG_TRY(issue_copy(0));
-    BatchHint next_hint = hint_of(0);
-    for (size_t c = 0; c < n_chunks; ++c) {
-        if (c + 1 < n_chunks) KTG_TRY(issue_copy(c + 1));
+    auto issue_copy = [&](size_t c) -> int {
         const uint64_t r = cut[c], r1 = cut[c + 1], nb = offsets[r1] - offsets[r], nr = r1 - r;
-        const int s = (int)(c & 1);
+        const int s = slot_of(c);
+        // the staging buffer may still be read by the kernels of two chunks ago
+        KTG_CUDA(cudaStreamWaitEvent(impl->copy_stream, b->st_free[s], 0));
+        if (b->st_bases[s].cap < nb + 64 || b->st_offs[s].cap < (nr + 1) * 8) {
+            KTG_CUDA(cudaStreamSynchronize(impl->stream)); // reallocation frees the old buffer
+            KTG_CUDA(cudaStreamSynchronize(impl->copy_stream));
+            KTG_TRY(b->st_bases[s].ensure((s < 2 ? std::max<uint64_t>(nb, CHUNK) : nb + nb / 4) + 64));
+            KTG_TRY(b->st_offs[s].ensure((nr + 1) * 8));
+        }
+        KTG_CUDA(cudaMemcpyAsync(b->st_bases[s].p, bases + offsets[r], nb, cudaMemcpyHostToDevice, impl->copy_stream));
+        // (the pass over the offsets is 0.6-0.8 ms of host time per 64 MiB of 100 bp reads: behind the copy)
+        const uint32_t ulen = hint_of(c).ulen;
+        if (ulen) {
+            const int g = (int)std::min<uint64_t>((nr + 1 + 255) / 256, 4096);
+            fill_offsets_kernel<<<g, 256, 0, impl->copy_stream>>>((uint64_t *)b->st_offs[s].p, nr + 1, offsets[r], ulen);
+            KTG_CUDA(cudaGetLastError());
+        }
+        else KTG_CUDA(cudaMemcpyAsync(b->st_offs[s].p, offsets + r, (nr + 1) * 8, cudaMemcpyHostToDevice, impl->copy_stream));
+        KTG_CUDA(cudaEventRecord(b->st_ready[s], impl->copy_stream));
+        trace("copy queued", c);
+        return KTG_OK;
+    };
+    // The copy of chunk i+1 is queued BEFORE the kernels of chunk i are launched: ingest_device
+    // may synchronise the compute stream (table sizing at a flush), and the copy engine must not
+    // sit idle meanwhile.
+    KTG_TRY(issue_copy(0));
+    size_t issued = 1;
+    for (size_t c = 0; c < n_chunks; ++c) {
+        const size_t ahead = (tail_first != (size_t)-1 && c + 1 >= tail_first) ? n_chunks : std::min(c + 2, n_chunks);
+        for (; issued < ahead; ++issued) KTG_TRY(issue_copy(issued));
+        const uint64_t r = cut[c], r1 = cut[c + 1], nb = offsets[r1] - offsets[r], nr = r1 - r;
+        const int s = slot_of(c);
+        const BatchHint hint = hint_of(c);
         KTG_CUDA(cudaStreamWaitEvent(impl->stream, b->st_ready[s], 0));
         // offsets stay absolute: bias the base pointer instead (pack kernel subtracts offsets[0])
         const uint8_t *d_bases = (const uint8_t *)b->st_bases[s].p - offsets[r];
-        const BatchHint hint = next_hint; // computed while the previous chunk was being queued
         impl->hint_shift0 = (uint32_t)((uintptr_t)b->st_bases[s].p & 31);
         impl->input_consumed = b->st_free[s];
         int rc_ = impl->ingest_device(d_bases, (const uint64_t *)b->st_offs[s].p, nr, nb, &hint);
         impl->input_consumed = nullptr;
         KTG_TRY(rc_);
-        if (c + 1 < n_chunks) next_hint = hint_of(c + 1); // host work hidden behind the queued kernels
+        if (flush_here[c]) KTG_TRY(impl->flush_hint());
     }
     if (accepted_reads || accepted_bytes) {
         uint64_t r1c = 0, b1c = 0;
