@@ -151,6 +151,19 @@ int ktg_export_graph(ktg_builder *b, uint64_t *node_hi, uint64_t *node_lo, uint6
                      uint64_t *dst, uint32_t *weight, uint8_t *edge_bytes, uint64_t n_edges);
 uint32_t ktg_edge_record_bytes(const ktg_builder *b);
 
+/* ---- BFCounter input (builder.rs:79-115, pt_graph.rs:201-213,318-329).  The
+ * reference implements it for PtGraph only (add_read_bfc is unreachable!() on its GIR types,
+ * builder.rs:32-36); here the same table takes it: for every k-mer (exactly k ASCII bases, n*k
+ * contiguous bytes) with count >= minimal_weight_threshold (builder.rs:106-108),
+ * weight[kmer] += count, and weight[revcomp(kmer)] += count with reverse_complement.
+ * *accepted_bytes += k per accepted k-mer (builder.rs:109).  BFCounter's k-mers are unique
+ * (pt_graph.rs:78); a repeated one adds up here where petgraph would hold parallel edges.
+ * Single GPU.  ktg_create_from_bfc_files reads "<k-mer>\t<count>" lines and finalizes. */
+int ktg_add_weighted_kmers(ktg_builder *b, const uint8_t *kmers, const uint32_t *weights, uint64_t n,
+                           uint32_t minimal_weight_threshold, uint64_t *accepted_kmers, uint64_t *accepted_bytes);
+int ktg_create_from_bfc_files(ktg_builder *b, const char *const *paths, uint32_t n_paths,
+                              uint32_t minimal_weight_threshold, uint64_t *total_bytes);
+
 /* Order-independent digest over the expanded edge set:
  * out[0] = sum splitmix64(splitmix64(hi)^lo)*(2w+1), out[1] = |E|,
  * out[2] = sum w, out[3] = max w. */

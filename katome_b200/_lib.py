@@ -33,6 +33,7 @@ SYMBOLS = (
     "ktg_mg_skm_supported", "ktg_mg_skm_plan", "ktg_mg_skm_prepare", "ktg_mg_skm_scatter_reads_device",
     "ktg_mg_skm_insert_buckets", "ktg_mg_skm_spill", "ktg_mg_skm_partition_records", "ktg_mg_skm_insert_records",
     "ktg_mg_skm_owner_of", "ktg_skm_items_host", "ktg_skm_owner_of_kmer",
+    "ktg_add_weighted_kmers", "ktg_create_from_bfc_files",
     "ktg_export_graph", "ktg_edge_record_bytes", "ktg_nodes_export_device", "ktg_nodes_stats_from_device", "ktg_edge_sums", "ktg_scale_weights",
 )
 
@@ -100,6 +101,8 @@ def lib():
     L.ktg_add_reads.argtypes = [vp, vp, vp, C.c_uint64, u64p, u64p]
     L.ktg_add_reads_device.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, u64p, u64p]
     L.ktg_create_from_files.argtypes = [vp, C.POINTER(C.c_char_p), C.c_uint32, C.c_int, u64p]
+    L.ktg_add_weighted_kmers.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint32, u64p, u64p]
+    L.ktg_create_from_bfc_files.argtypes = [vp, C.POINTER(C.c_char_p), C.c_uint32, C.c_uint32, u64p]
     L.ktg_finalize.argtypes = [vp]
     L.ktg_reset.argtypes = [vp]
     L.ktg_counts.argtypes = [vp, u64p, u64p]

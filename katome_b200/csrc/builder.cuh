@@ -226,6 +226,8 @@ struct BuilderBase {
                                 uint64_t n_reads, uint64_t total_bases, void **d_keys,
                                 uint64_t *counts) = 0;
     virtual int insert_keys(const void *d_keys, uint64_t n) = 0;
+    virtual int add_weighted_kmers(const uint8_t *d_kmers, const uint32_t *d_weights, uint64_t n, uint32_t threshold,
+                                   uint64_t *accepted) = 0;
     virtual int partition_keys(const void *d_keys, uint64_t n, void **d_out, uint64_t *counts) = 0;
     virtual int mg_plan(uint64_t max_windows, int *needs_realloc) = 0;
     virtual int mg_prepare(uint64_t max_windows, void **rx_base, uint64_t *rx_bytes, uint64_t *bucket_cap,
@@ -291,7 +293,7 @@ template <class K> struct Builder : BuilderBase {
         b_packed.release(); b_bad.release(); b_valid.release(); b_wstart.release(); b_keys.release(); b_keys2.release();
         b_hist.release(); b_hll.release(); b_spill.release(); b_ovf_keys.release(); b_ovf_inc.release(); b_small.release();
         b_pkeys.release(); b_pcur.release(); b_pspill.release(); b_stage_cur.release();
-        b_rx.release(); b_mg_cur.release(); b_mg_spill.release(); b_skm_cnt.release(); b_skm_part.release(); b_skm_keys.release(); b_node_keys.release(); b_node_deg.release();
+        b_rx.release(); b_mg_cur.release(); b_mg_spill.release(); b_skm_cnt.release(); b_skm_part.release(); b_skm_keys.release(); b_bfc_ctr.release(); b_node_keys.release(); b_node_deg.release();
         if (copy_stream) cudaStreamDestroy(copy_stream);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
@@ -1450,6 +1452,45 @@ template <class K> struct Builder : BuilderBase {
             KTG_TRY(sync()); // the caller may reuse its key buffer
         }
         KTG_CUDA(cudaGetLastError());
+        return KTG_OK;
+    }
+
+    // BFCounter input: pre-counted k-mers (device arrays), weight[kmer] += weight
+    DeviceBuf b_bfc_ctr;
+    int add_weighted_kmers(const uint8_t *d_kmers, const uint32_t *d_weights, uint64_t n, uint32_t threshold,
+                           uint64_t *accepted) override {
+        if (deferred_error != KTG_OK) return fail(deferred_error, "build is void after an earlier error");
+        if (tab.world > 1) return fail(KTG_ERR_INVALID, "BFCounter input is single-GPU");
+        if (accepted) *accepted = 0;
+        if (n == 0) return KTG_OK;
+        KTG_TRY(flush_staged());
+        KTG_TRY(ensure_init());
+        if ((double)(occupied_ub + n) > LOAD_MAX * (double)tab.capacity()) { // every line may be a new edge
+            uint64_t exact = 0;
+            KTG_TRY(count_occupied(&exact));
+            occupied_ub = exact;
+            if ((double)(exact + n) > LOAD_MAX * (double)tab.capacity())
+                KTG_TRY(grow_to((uint64_t)((double)(exact + n) / LOAD_TARGET) + 1));
+        }
+        occupied_ub += n;
+        sketch_complete = false; // these keys go in unsketched
+        KTG_TRY(b_bfc_ctr.ensure(16));
+        KTG_CUDA(cudaMemsetAsync(b_bfc_ctr.p, 0, 16, stream));
+        const int g = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)props.sms * 8);
+        prof.begin("insert_weighted_kmers", n, stream);
+        if (rc) insert_weighted_kmers_kernel<K, true><<<g, 256, 0, stream>>>(d_kmers, d_weights, n, k, threshold, tab, (unsigned long long *)b_bfc_ctr.p);
+        else insert_weighted_kmers_kernel<K, false><<<g, 256, 0, stream>>>(d_kmers, d_weights, n, k, threshold, tab, (unsigned long long *)b_bfc_ctr.p);
+        prof.end(stream);
+        KTG_CUDA(cudaGetLastError());
+        nodes_valid = false;
+        unsigned long long c[2] = {0, 0};
+        KTG_CUDA(cudaMemcpyAsync(c, b_bfc_ctr.p, 16, cudaMemcpyDeviceToHost, stream));
+        KTG_TRY(sync());
+        if (c[1]) {
+            deferred_error = KTG_ERR_BAD_RECORD;
+            return fail(KTG_ERR_BAD_RECORD, "%llu BFCounter k-mers with a symbol outside ACGT", c[1]);
+        }
+        if (accepted) *accepted = c[0];
         return KTG_OK;
     }
 

@@ -1163,6 +1163,51 @@ insert_keys_kernel(const K *__restrict__ keys, uint64_t n, const unsigned long l
 }
 
 // replay of inserts that overflowed a full sub-table, after the table grew
+// ---- BFCounter input: n pre-counted k-mers of exactly k ASCII bases each.
+// add_read_bfc (/root/reference/src/katome/collections/graphs/pt_graph.rs:318-329): the k-mer and,
+// with reverse_complement, its reverse complement get an edge of the line's weight; lines below
+// the threshold are skipped (algorithms/builder.rs:106-108).  On the canonical table that is one
+// update of min(kmer, revcomp) by the weight (twice the weight for a palindrome, which the
+// reference inserts twice).  counters[0] += accepted lines, counters[1] += lines with a byte
+// outside ACGT (the build is void then).
+template <class K, bool RC>
+__global__ void __launch_bounds__(256)
+insert_weighted_kmers_kernel(const uint8_t *__restrict__ kmers, const uint32_t *__restrict__ weights, uint64_t n,
+                             uint32_t k, uint32_t threshold, Table<K> t, unsigned long long *__restrict__ counters) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long ok = 0, bad = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t w = weights[i];
+        if (w < threshold) continue;
+        const uint8_t *p = kmers + i * k;
+        K key = 0;
+        bool valid = true;
+        for (uint32_t j = 0; j < k; ++j) {
+            const uint32_t c = p[j];
+            valid &= c == 'A' || c == 'C' || c == 'G' || c == 'T';
+            key = (key << 2) | (K)(((c >> 1) & 3u) ^ ((c >> 2) & 1u)); // A0 C1 G2 T3 (compress.rs:347-378)
+        }
+        if (!valid) {
+            ++bad;
+            continue;
+        }
+        uint32_t inc = w;
+        if (RC) {
+            const K r = revcomp(key, k);
+            if (r == key) inc = 2u * w;
+            else if (r < key) key = r;
+        }
+        table_add(t, key, inc);
+        ++ok;
+    }
+    ok = warp_sum(ok);
+    bad = warp_sum(bad);
+    if ((threadIdx.x & 31) == 0) {
+        if (ok) atomicAdd(&counters[0], ok);
+        if (bad) atomicAdd(&counters[1], bad);
+    }
+}
+
 template <class K>
 __global__ void replay_overflow_kernel(const K *__restrict__ keys, const uint32_t *__restrict__ inc,
                                        uint64_t n, Table<K> t) {

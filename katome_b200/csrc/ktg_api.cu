@@ -436,6 +436,97 @@ int ktg_create_from_files(ktg_builder *b, const char *const *paths, uint32_t n_p
     return ktg_finalize(b);
 }
 
+// ---- BFCounter input --------------------------------------------------------
+// Host arrays: n k-mers of exactly k ASCII bases each (contiguous) and their counts.
+int ktg_add_weighted_kmers(ktg_builder *b, const uint8_t *kmers, const uint32_t *weights, uint64_t n,
+                           uint32_t minimal_weight_threshold, uint64_t *accepted_kmers, uint64_t *accepted_bytes) {
+    KTG_ENTER(b);
+    if (n == 0) return KTG_OK;
+    if (!kmers || !weights) return fail(KTG_ERR_INVALID, "null argument");
+    BuilderBase *impl = b->impl.get();
+    const uint64_t k = impl->k, step = std::max<uint64_t>(1, (64ull << 20) / k); // 64 MiB of bases at a time
+    DeviceBuf d_k, d_w;
+    int rc_ = KTG_OK;
+    for (uint64_t i = 0; i < n && rc_ == KTG_OK; i += step) {
+        const uint64_t m = std::min(step, n - i);
+        uint64_t got = 0;
+        if ((rc_ = d_k.ensure(m * k)) != KTG_OK || (rc_ = d_w.ensure(m * 4)) != KTG_OK) break;
+        if (cudaMemcpyAsync(d_k.p, kmers + i * k, m * k, cudaMemcpyHostToDevice, impl->stream) != cudaSuccess ||
+            cudaMemcpyAsync(d_w.p, weights + i, m * 4, cudaMemcpyHostToDevice, impl->stream) != cudaSuccess) {
+            rc_ = fail(KTG_ERR_CUDA, "copying BFCounter k-mers failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        rc_ = impl->add_weighted_kmers((const uint8_t *)d_k.p, (const uint32_t *)d_w.p, m, minimal_weight_threshold, &got);
+        if (accepted_kmers) *accepted_kmers += got;
+        if (accepted_bytes) *accepted_bytes += got * k; // total += edge.len() (builder.rs:109)
+    }
+    cudaStreamSynchronize(impl->stream);
+    d_k.release();
+    d_w.release();
+    return rc_;
+}
+
+// create_bfc (builder.rs:79-115): lines "<k-mer>\t<count>".  Errors mirror the reference's panics:
+// unopenable file (:88-91), missing field / unparsable count (:100-105), k-mer shorter than k
+// ("Read is too short!", pt_graph.rs:319).  A k-mer longer than k is rejected as a bad record
+// (the reference would pack it as a longer edge against k-wide nodes).
+int ktg_create_from_bfc_files(ktg_builder *b, const char *const *paths, uint32_t n_paths,
+                              uint32_t minimal_weight_threshold, uint64_t *total_bytes) {
+    KTG_ENTER(b);
+    if (!paths && n_paths) return fail(KTG_ERR_INVALID, "null argument");
+    const uint64_t k = b->impl->k;
+    std::vector<FILE *> fs;
+    auto close_all = [&]() { for (FILE *f : fs) if (f) fclose(f); };
+    for (uint32_t i = 0; i < n_paths; ++i) {
+        FILE *f = fopen(paths[i], "rb");
+        if (!f) {
+            close_all();
+            return fail(KTG_ERR_IO, "Couldn't open all files: %s", paths[i]);
+        }
+        fs.push_back(f);
+    }
+    std::vector<uint8_t> kmers;
+    std::vector<uint32_t> weights;
+    uint64_t total = 0;
+    int rc_ = KTG_OK;
+    auto flush = [&]() -> int {
+        if (weights.empty()) return KTG_OK;
+        int r = ktg_add_weighted_kmers(b, kmers.data(), weights.data(), weights.size(), 0, nullptr, nullptr);
+        kmers.clear();
+        weights.clear();
+        return r;
+    };
+    char line[4096];
+    for (FILE *f : fs) {
+        while (rc_ == KTG_OK && fgets(line, sizeof line, f)) {
+            size_t n = strlen(line);
+            while (n && (line[n - 1] == '\n' || line[n - 1] == '\r')) line[--n] = 0;
+            char *tab = (char *)memchr(line, '\t', n);
+            if (!tab) { rc_ = fail(KTG_ERR_BAD_RECORD, "BFCounter line without a count"); break; }
+            char *endp = nullptr;
+            const unsigned long long w = strtoull(tab + 1, &endp, 10);
+            if (endp == tab + 1 || (*endp && *endp != '\t') || w > 0xFFFFFFFFull || tab[1] == '-' || tab[1] == '+') {
+                rc_ = fail(KTG_ERR_BAD_RECORD, "Parse int error in a BFCounter line");
+                break;
+            }
+            if ((uint32_t)w < minimal_weight_threshold) continue; // builder.rs:106-108, before total += len
+            const uint64_t len = (uint64_t)(tab - line);
+            if (len < k) { rc_ = fail(KTG_ERR_SHORT_READ, "Read is too short!"); break; }
+            if (len != k) { rc_ = fail(KTG_ERR_BAD_RECORD, "BFCounter k-mer of %llu bases, k is %llu", (unsigned long long)len, (unsigned long long)k); break; }
+            total += len;
+            kmers.insert(kmers.end(), (const uint8_t *)line, (const uint8_t *)line + len);
+            weights.push_back((uint32_t)w);
+            if (weights.size() >= (1u << 20)) rc_ = flush();
+        }
+        if (rc_ != KTG_OK) break;
+    }
+    if (rc_ == KTG_OK) rc_ = flush();
+    close_all();
+    KTG_TRY(rc_);
+    if (total_bytes) *total_bytes = total;
+    return ktg_finalize(b);
+}
+
 int ktg_reset(ktg_builder *b) {
     KTG_ENTER(b);
     return b->impl->reset();

@@ -133,6 +133,26 @@ class GpuGIR:
         self.add_reads(bases, offsets)
         _check(self._L.ktg_finalize(self._h))  # a short read panics immediately in the reference
 
+    def add_read_bfc(self, read: bytes, weight: int, reverse_complement: Optional[bool] = None):
+        """One BFCounter line (builder.rs:30-36, pt_graph.rs:318-329): a k-mer with its count."""
+        if reverse_complement is not None and bool(reverse_complement) != self.reverse_complement:
+            raise KatomeError(L.KTG_ERR_INVALID, "reverse_complement is fixed per GpuGIR handle")
+        if len(read) < self.k:
+            raise ReadTooShort(L.KTG_ERR_SHORT_READ, "Read is too short!")
+        self.add_weighted_kmers(np.frombuffer(bytes(read), dtype=np.uint8), np.array([weight], dtype=np.uint32))
+
+    def add_weighted_kmers(self, kmers: np.ndarray, weights: np.ndarray, minimal_weight_threshold: int = 0):
+        """Batch of BFCounter lines: `kmers` is n*k ASCII bytes, `weights` n counts; lines below the
+        threshold are skipped (builder.rs:106-108).  -> (accepted k-mers, accepted bytes)"""
+        kmers = np.ascontiguousarray(kmers, dtype=np.uint8)
+        weights = np.ascontiguousarray(weights, dtype=np.uint32)
+        if kmers.size != weights.size * self.k:
+            raise KatomeError(L.KTG_ERR_BAD_RECORD, f"{kmers.size} bases for {weights.size} k-mers of {self.k}")
+        nk, nb = C.c_uint64(0), C.c_uint64(0)
+        _check(self._L.ktg_add_weighted_kmers(self._h, kmers.ctypes.data, weights.ctypes.data, weights.size,
+                                              int(minimal_weight_threshold), C.byref(nk), C.byref(nb)))
+        return nk.value, nb.value
+
     def add_reads(self, bases: np.ndarray, offsets: np.ndarray) -> Tuple[int, int]:
         """Batch form of the create_fastq loop body (builder.rs:152-160): drops reads with a
         byte outside "ACGT", returns (accepted_reads, accepted_bytes) of this batch."""
@@ -166,16 +186,20 @@ class GpuGIR:
     def create(cls, input_files: Sequence[os.PathLike], ft: str = "fastq", reverse_complement: bool = True,
                minimal_weight_threshold: int = 0, *, k: int = 40, **kw) -> Tuple["GpuGIR", int]:
         """Build::create (builder.rs:42-54): returns (collection, total accepted bytes).
-        `minimal_weight_threshold` only matters for BFCounter input in the reference
-        (builder.rs:106-108) and is ignored for Fastq/Fasta, as there."""
-        del minimal_weight_threshold
-        if ft.lower() not in _FILE_TYPES:
-            raise KatomeError(L.KTG_ERR_INVALID, f"unsupported input_file_type {ft!r} (BFCounter is out of scope)")
+        `minimal_weight_threshold` only matters for BFCounter input (`ft="bfcounter"`,
+        builder.rs:106-108) and is ignored for Fastq/Fasta, as in the reference."""
+        bfc = ft.lower() in ("bfcounter", "bfc")
+        if ft.lower() not in _FILE_TYPES and not bfc:
+            raise KatomeError(L.KTG_ERR_INVALID, f"unsupported input_file_type {ft!r}")
         g = cls(k, reverse_complement, **kw)
         arr = (C.c_char_p * len(input_files))(*[os.fsencode(f) for f in input_files])
         total = C.c_uint64(0)
         try:
-            _check(g._L.ktg_create_from_files(g._h, arr, len(input_files), _FILE_TYPES[ft.lower()], C.byref(total)))
+            if bfc:  # create_bfc (builder.rs:79-115)
+                _check(g._L.ktg_create_from_bfc_files(g._h, arr, len(input_files), int(minimal_weight_threshold),
+                                                      C.byref(total)))
+            else:
+                _check(g._L.ktg_create_from_files(g._h, arr, len(input_files), _FILE_TYPES[ft.lower()], C.byref(total)))
         except Exception:
             g.close()
             raise

@@ -206,15 +206,18 @@ static uint32_t find_or_insert_node(ko_gir *g, const uint8_t *key) {
 }
 
 /* hs_gir.rs:192-203 */
-static void create_or_modify_edge(ko_node *src, uint32_t to, uint8_t last_char) {
+static void create_or_modify_edge_w(ko_node *src, uint32_t to, uint8_t last_char, uint32_t inc) {
     for (int i = 0; i < src->nout; ++i) {
         if (src->out[i].target == to) {
-            src->out[i].weight += 1; /* u32, wrapping in release (Cargo.toml:56) */
+            src->out[i].weight += inc; /* u32, wrapping in release (Cargo.toml:56) */
             return;
         }
     }
-    ko_edge e = {to, 1, last_char};
+    ko_edge e = {to, inc, last_char};
     src->out[src->nout++] = e; /* at most 4 distinct successors exist */
+}
+static void create_or_modify_edge(ko_node *src, uint32_t to, uint8_t last_char) {
+    create_or_modify_edge_w(src, to, last_char, 1);
 }
 
 /* hm_gir.rs:91-153.  `kmer` = [start node | end node] packed. */
@@ -404,6 +407,68 @@ int ko_create_from_files(ko_gir *g, const char *const *paths, int n_paths, int f
         if (fs[i]) fclose(fs[i]);
     free(fs);
     if (accepted_reads) *accepted_reads = nr;
+    if (accepted_bytes) *accepted_bytes = nb;
+    return err;
+}
+
+/* ---- BFCounter input.  add_read_bfc (pt_graph.rs:318-329) + add_single_edge_bfc
+ * (pt_graph.rs:201-213): one edge of the given weight per line, plus its reverse complement with
+ * reverse_complement.  The reference implements it for PtGraph only (GIR types: unreachable!(),
+ * builder.rs:32-36) and never merges: BFCounter's k-mers are unique (pt_graph.rs:78).  Restated on
+ * the GIR's map, a k-mer that does come twice adds its weight to the one edge (the petgraph
+ * multigraph would hold parallel edges; that case is outside the parity contract).  The line's
+ * k-mer must be exactly k long: compress_kmer packs the whole string (compress.rs:18-28) while
+ * the node width is the global k (prelude.rs:21-25). */
+int ko_add_read_bfc(ko_gir *g, const uint8_t *kmer, size_t len, uint32_t weight, int reverse_complement) {
+    if (len < (size_t)g->k) return KO_ERR_SHORT_READ; /* pt_graph.rs:319 */
+    if (len != (size_t)g->k || !all_acgt(kmer, len)) return KO_ERR_BAD_RECORD;
+    uint8_t fw[2 * KO_MAXC], rv[2 * KO_MAXC];
+    ko_compress_kmer_with_rev_compl(kmer, len, fw, rv);
+    const uint8_t *both[2] = {fw, rv};
+    for (int i = 0; i < (reverse_complement ? 2 : 1); ++i) {
+        uint32_t source = find_or_insert_node(g, both[i]);
+        uint32_t target = find_or_insert_node(g, both[i] + g->c);
+        create_or_modify_edge_w(&g->nodes[source], target, kmer[len - 1], weight);
+    }
+    return KO_OK;
+}
+
+/* create_bfc (builder.rs:79-115): lines "<k-mer>\t<count>"; count < minimal_weight_threshold is
+ * skipped BEFORE total += len (:106-109). */
+int ko_create_from_bfc_files(ko_gir *g, const char *const *paths, int n_paths, int reverse_complement,
+                             uint32_t minimal_weight_threshold, uint64_t *accepted_kmers,
+                             uint64_t *accepted_bytes) {
+    uint64_t nk = 0, nb = 0;
+    int err = KO_OK;
+    FILE **fs = (FILE **)calloc((size_t)n_paths, sizeof(FILE *));
+    for (int i = 0; i < n_paths; ++i) { /* all readers are created up front: builder.rs:88-91 */
+        fs[i] = fopen(paths[i], "rb");
+        if (!fs[i]) { err = KO_ERR_IO; break; }
+    }
+    char line[4096];
+    for (int i = 0; i < n_paths && err == KO_OK; ++i) {
+        while (err == KO_OK && fgets(line, sizeof line, fs[i])) {
+            size_t n = strlen(line);
+            while (n && (line[n - 1] == '\n' || line[n - 1] == '\r')) line[--n] = 0;
+            char *tab = strchr(line, '\t');
+            if (!tab) { err = KO_ERR_BAD_RECORD; break; } /* iter.next().unwrap() :100 */
+            *tab = 0;
+            char *endp = NULL;
+            unsigned long long w = strtoull(tab + 1, &endp, 10);
+            if (endp == tab + 1 || (*endp && *endp != '\t') || w > 0xFFFFFFFFull || tab[1] == '-' || tab[1] == '+') {
+                err = KO_ERR_BAD_RECORD; /* parse::<EdgeWeight>() error :100-105 */
+                break;
+            }
+            if ((uint32_t)w < minimal_weight_threshold) continue; /* :106-108 */
+            nb += (uint64_t)(tab - line);                        /* :109 */
+            err = ko_add_read_bfc(g, (const uint8_t *)line, (size_t)(tab - line), (uint32_t)w, reverse_complement);
+            if (err == KO_OK) ++nk;
+        }
+    }
+    for (int i = 0; i < n_paths; ++i)
+        if (fs[i]) fclose(fs[i]);
+    free(fs);
+    if (accepted_kmers) *accepted_kmers = nk;
     if (accepted_bytes) *accepted_bytes = nb;
     return err;
 }

@@ -55,6 +55,12 @@ int ko_create_from_files(ko_gir *g, const char *const *paths, int n_paths, int f
                          int reverse_complement, uint64_t *accepted_reads,
                          uint64_t *accepted_bytes);
 
+/* BFCounter input (builder.rs:79-115, pt_graph.rs:201-213,318-329): one pre-counted k-mer. */
+int ko_add_read_bfc(ko_gir *g, const uint8_t *kmer, size_t len, uint32_t weight, int reverse_complement);
+int ko_create_from_bfc_files(ko_gir *g, const char *const *paths, int n_paths, int reverse_complement,
+                             uint32_t minimal_weight_threshold, uint64_t *accepted_kmers,
+                             uint64_t *accepted_bytes);
+
 /* ---- Stats (stats/collections.rs:190-208) ---- */
 void ko_counts(const ko_gir *g, uint64_t *nodes, uint64_t *edges);
 

@@ -47,6 +47,8 @@ def lib():
         L.ko_add_read_fastaq.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
         L.ko_add_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, u64p, u64p]
         L.ko_create_from_files.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int, u64p, u64p]
+        L.ko_add_read_bfc.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_uint32, C.c_int]
+        L.ko_create_from_bfc_files.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_uint32, u64p, u64p]
         L.ko_counts.argtypes = [C.c_void_p, u64p, u64p]
         L.ko_collection_stats.argtypes = [C.c_void_p, u64p]
         L.ko_remove_weak_edges.argtypes = [C.c_void_p, C.c_uint32]
@@ -131,6 +133,22 @@ class OracleGIR:
         code = g._L.ko_create_from_files(g._h, arr, len(files), 1 if file_type.lower() == "fasta" else 0,
                                          int(reverse_complement), C.byref(nr), C.byref(nb))
         g.accepted_reads, g.accepted_bytes = nr.value, nb.value
+        _check(code)
+        return g, nb.value
+
+    def add_read_bfc(self, kmer: bytes, weight: int, reverse_complement: bool):
+        """one BFCounter line (pt_graph.rs:318-329)"""
+        _check(self._L.ko_add_read_bfc(self._h, kmer, len(kmer), int(weight), int(reverse_complement)))
+
+    @classmethod
+    def create_bfc(cls, k: int, files, reverse_complement: bool = False, minimal_weight_threshold: int = 0):
+        """create_bfc (builder.rs:79-115) -> (collection, total accepted bytes)"""
+        g = cls(k)
+        arr = (C.c_char_p * len(files))(*[os.fsencode(f) for f in files])
+        nk, nb = C.c_uint64(0), C.c_uint64(0)
+        code = g._L.ko_create_from_bfc_files(g._h, arr, len(files), int(reverse_complement),
+                                             int(minimal_weight_threshold), C.byref(nk), C.byref(nb))
+        g.accepted_reads, g.accepted_bytes = nk.value, nb.value
         _check(code)
         return g, nb.value
 

@@ -728,3 +728,53 @@ def test_device_fastq_parser_matches_host_reader(K, tmp_path):
     p1, p2 = tmp_path / "plain.fastq", tmp_path / "ragged.fastq"
     dev, host = _both_fastq_parsers(K, [str(p1), str(p2)], 40, True, 2)
     assert dev == host and dev[2] == cpu.digest() and dev[1] == cpu.accepted_bytes and dev[3] == cpu.counts()
+
+
+# ------------------------------------------------------------------ BFCounter input
+@pytest.mark.parametrize("k,rc,t", [(31, True, 0), (40, False, 3), (6, True, 2), (63, True, 5), (32, False, 0)])
+def test_bfcounter_input(K, tmp_path, k, rc, t):
+    """create_bfc / add_read_bfc on the GPU table == the oracle's restatement: weights, threshold
+    pre-filter, accepted bytes, a palindrome, the all-T k-mer at full key width; then reads on top"""
+    from oracle import oracle as O
+    from tests.test_oracle_golden import _bfc_lines
+    rng = np.random.default_rng(100 + k)
+    lines = _bfc_lines(rng, k, 2000)
+    if k % 2 == 0 and rc:
+        lines.append(("ACG" * (k // 6) + "CGT" * (k // 6), 7))
+    if not rc:
+        lines.append(("T" * k, 9))
+    path = tmp_path / "bfc.txt"
+    path.write_text("".join(f"{s}\t{w}\n" for s, w in lines))
+    cpu, total = O.OracleGIR.create_bfc(k, [str(path)], rc, t)
+    g, gtotal = K.GpuGIR.create([str(path)], "bfcounter", rc, t, k=k)
+    assert gtotal == total
+    _assert_same(g, cpu)
+    # the batch entry point, with the threshold applied on the device, and reads mixed in
+    g2 = K.GpuGIR(k, rc)
+    kmers = np.frombuffer("".join(s for s, _ in lines).encode(), dtype=np.uint8)
+    weights = np.array([w for _, w in lines], dtype=np.uint32)
+    nk, nb = g2.add_weighted_kmers(kmers, weights, t)
+    assert (nk, nb) == (sum(w >= t for _, w in lines), total)
+    _assert_same(g2, cpu)
+    reads = H.random_reads(rng, 50, k, k + 60)
+    g2.add_reads(*H.batch_of(reads))
+    cpu.add_reads(*H.batch_of(reads), rc)
+    g2.add_read_bfc(lines[0][0].encode(), 5)
+    cpu.add_read_bfc(lines[0][0].encode(), 5, rc)
+    _assert_same(g2, cpu)
+    g.close()
+    g2.close()
+
+
+def test_bfcounter_input_errors(K, tmp_path):
+    for body, code in (("ACGT\t3\n", K._lib.KTG_ERR_SHORT_READ), ("A" * 31 + "\n", K._lib.KTG_ERR_BAD_RECORD),
+                       ("A" * 31 + "\tx\n", K._lib.KTG_ERR_BAD_RECORD), ("A" * 30 + "N\t2\n", K._lib.KTG_ERR_BAD_RECORD),
+                       ("A" * 33 + "\t2\n", K._lib.KTG_ERR_BAD_RECORD)):
+        p = tmp_path / "bad.txt"
+        p.write_text(body)
+        with pytest.raises(K.KatomeError) as e:
+            K.GpuGIR.create([str(p)], "bfcounter", True, 0, k=31)
+        assert e.value.code == code, body
+    with pytest.raises(K.KatomeError) as e:
+        K.GpuGIR.create([str(tmp_path / "missing.txt")], "bfcounter", True, 0, k=31)
+    assert e.value.code == K._lib.KTG_ERR_IO

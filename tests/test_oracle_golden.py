@@ -149,3 +149,59 @@ def test_synthetic_reads_are_deterministic_and_error_rate_is_right():
     genome = O.synth_genome(0x6B61746F6D65 + 1, 0, 100000).tobytes().decode()
     r0 = clean[:100].tobytes().decode()
     assert r0 in genome or H.revcomp(r0) in genome
+
+
+# ------------------------------------------------------------------ BFCounter input
+def _bfc_lines(rng, k, n):
+    """unique canonical k-mers with counts, the shape of BFCounter's output"""
+    from tests.helpers import kmer_int, revcomp
+    seen, out = set(), []
+    while len(out) < n:
+        s = "".join(rng.choice(list("ACGT"), size=k))
+        c = min(s, revcomp(s), key=kmer_int)
+        if c not in seen:
+            seen.add(c)
+            out.append((c, int(rng.integers(1, 40))))
+    return out
+
+
+def test_bfcounter_input_matches_the_set_level_twin(tmp_path):
+    """create_bfc (builder.rs:79-115) + add_read_bfc (pt_graph.rs:318-329) restated on the GIR:
+    every line is one edge of its count, plus the reverse complement with rc; counts below the
+    threshold are skipped before `total += len`.  The reference holds no fixture for this input
+    (parity unpinned by reference tests); the witness is the set-level twin."""
+    import numpy as np
+    from collections import Counter
+    from oracle import oracle as O
+    from tests.helpers import kmer_int, py_nodes, revcomp
+    rng = np.random.default_rng(11)
+    for k, rc, t in ((31, True, 0), (40, False, 3), (6, True, 2), (63, True, 5)):
+        lines = _bfc_lines(rng, k, 300)
+        if k % 2 == 0 and rc:
+            lines.append(("ACG" * (k // 6) + "CGT" * (k // 6), 7))  # a palindrome: both strands are one edge
+            assert revcomp(lines[-1][0]) == lines[-1][0]
+        path = tmp_path / f"bfc_{k}.txt"
+        path.write_text("".join(f"{s}\t{w}\n" for s, w in lines))
+        g, total = O.OracleGIR.create_bfc(k, [str(path)], rc, t)
+        want = Counter()
+        for s, w in lines:
+            if w < t:
+                continue
+            want[s] += w
+            if rc:
+                want[revcomp(s)] += w
+        assert total == sum(len(s) for s, w in lines if w >= t)
+        hi, lo, wt = g.export_edges()
+        got = {(int(h) << 64) | int(l): int(x) for h, l, x in zip(hi, lo, wt)}
+        assert got == {kmer_int(s): w & 0xFFFFFFFF for s, w in want.items()}
+        assert g.counts() == (len(py_nodes(want)), len(want))
+    # errors: short k-mer, missing count, unparsable count, missing file
+    for body, code in (("ACGT\t3\n", O.KO_ERR_SHORT_READ), ("A" * 31 + "\n", O.KO_ERR_BAD_RECORD),
+                       ("A" * 31 + "\tx\n", O.KO_ERR_BAD_RECORD), ("A" * 30 + "N\t2\n", O.KO_ERR_BAD_RECORD)):
+        p = tmp_path / "bad.txt"
+        p.write_text(body)
+        with pytest.raises(O.OracleError) as e:
+            O.OracleGIR.create_bfc(31, [str(p)], True, 0)
+        assert e.value.code == code
+    with pytest.raises(O.OracleError):
+        O.OracleGIR.create_bfc(31, [str(tmp_path / "missing.txt")], True, 0)
