@@ -780,7 +780,7 @@ template <class K> struct Builder : BuilderBase {
     // flat (dense) or bucketed insert with L2 atomics; n_dev: the count lives on the device
     int launch_insert(const K *keys, uint64_t n, const unsigned long long *bin_end, uint64_t bucket_cap,
                       uint32_t n_bins, const unsigned long long *n_dev = nullptr, bool skip_empty = false) {
-        uint64_t tiles_per_bin = bin_end ? bucket_cap / INSERT_TILE : 0;
+        uint64_t tiles_per_bin = bin_end ? (bucket_cap + INSERT_TILE - 1) / INSERT_TILE : 0; // the kernel clips a tile at its bin's end
         uint64_t n_tiles = bin_end ? tiles_per_bin * n_bins : (n + INSERT_TILE - 1) / INSERT_TILE;
         if (n_tiles == 0) return KTG_OK;
         KTG_TRY(ensure_init());
@@ -799,28 +799,36 @@ template <class K> struct Builder : BuilderBase {
     // Level-2 scatter of the level-1 buckets by page, then the streaming page update.
     // Page-bucket overflow goes to a spill list that is inserted with L2 atomics
     // afterwards (count stays on the device: no host round trip).
-    // keys1: level-1 buckets (n_bins of cap1 keys, ends in fill1); sub_mod != 0: bucket q
-    // belongs to sub-table q % sub_mod (receive buckets, one set per source rank)
-    int paged_update(uint32_t n_bins, uint64_t cap1, uint64_t n_keys, const unsigned long long *fill1,
-                     const K *keys1 = nullptr, uint32_t sub_mod = 0) {
-        if (!keys1) keys1 = (const K *)b_keys.p;
+    // Three steps, so that the host batcher can run the scatter chunk by chunk while the
+    // copies are still coming in and leave only the page sweep for the flush (pages_drain):
+    //   pages_open    page buckets + cursors for up to `room` keys
+    //   pages_scatter level-1 buckets (n_bins of cap1 keys, ends in fill1) -> page buckets;
+    //                 sub_mod != 0: bucket q belongs to sub-table q % sub_mod (receive buckets,
+    //                 one set per source rank)
+    //   pages_update  the sweep + the spill list
+    uint64_t pg_cap2 = 0, pg_spill_cap = 0;
+    int pages_open(uint64_t room) {
         const uint64_t n_pages = tab.n_pages();
-        const uint64_t cap2 = page_bucket_cap_for(n_keys, n_pages);
-        const uint64_t spill_cap = std::max<uint64_t>(1u << 20, n_keys / 32);
-        if ((double)n_pages * (double)cap2 >= 4.0e9) return fail(KTG_ERR_INVALID, "batch too large for 32-bit bucket positions");
-        KTG_TRY(b_pkeys.ensure(n_pages * cap2 * sizeof(K) + 64));
+        pg_cap2 = page_bucket_cap_for(room, n_pages);
+        pg_spill_cap = std::max<uint64_t>(1u << 20, room / 32);
+        if ((double)n_pages * (double)pg_cap2 >= 4.0e9) return fail(KTG_ERR_INVALID, "batch too large for 32-bit bucket positions");
+        KTG_TRY(b_pkeys.ensure(n_pages * pg_cap2 * sizeof(K) + 64));
         KTG_TRY(b_pcur.ensure(n_pages * 8));
-        KTG_TRY(b_pspill.ensure(spill_cap * sizeof(K) + 64));
-        unsigned long long *cur2 = (unsigned long long *)b_pcur.p, *spill2 = d_page_spill;
-        KTG_CUDA(cudaMemsetAsync(spill2, 0, 8, stream));
-        init_cursors_kernel<<<(int)std::min<uint64_t>((n_pages + 255) / 256, props.sms * 8), 256, 0, stream>>>(cur2, n_pages, cap2);
+        KTG_TRY(b_pspill.ensure(pg_spill_cap * sizeof(K) + 64));
+        KTG_CUDA(cudaMemsetAsync(d_page_spill, 0, 8, stream));
+        init_cursors_kernel<<<(int)std::min<uint64_t>((n_pages + 255) / 256, props.sms * 8), 256, 0, stream>>>(
+            (unsigned long long *)b_pcur.p, n_pages, pg_cap2);
+        return KTG_OK;
+    }
+    int pages_scatter(uint32_t n_bins, uint64_t cap1, uint64_t n_keys, const unsigned long long *fill1,
+                      const K *keys1, uint32_t sub_mod) {
         ScatterOut o;
-        o.cursors = cur2;
-        o.bucket_cap = cap2;
+        o.cursors = (unsigned long long *)b_pcur.p;
+        o.bucket_cap = pg_cap2;
         o.out = b_pkeys.p;
         o.spill_out = b_pspill.p;
-        o.spill_cursor = spill2;
-        o.spill_cap = spill_cap;
+        o.spill_cursor = d_page_spill;
+        o.spill_cap = pg_spill_cap;
         const uint64_t tiles_per_bin = cap1 / L2S_TILE, n_tiles = tiles_per_bin * n_bins;
         const size_t ss = ScatterSmem<K, L2S_TILE>::bytes(tab.pages_per_sub(), false);
         // 256-thread CTAs (four per SM) overlap the phases of a tile better than 512-thread ones
@@ -846,6 +854,12 @@ template <class K> struct Builder : BuilderBase {
             scatter_buckets_kernel<K, 2><<<g, L2S_THREADS, ss, stream>>>(keys1, fill1, cap1, tiles_per_bin, n_tiles, sub_mod, false, tab, o);
         }
         prof.end(stream);
+        KTG_CUDA(cudaGetLastError());
+        return KTG_OK;
+    }
+    int pages_update(uint64_t n_keys) {
+        const uint64_t n_pages = tab.n_pages(), cap2 = pg_cap2;
+        unsigned long long *cur2 = (unsigned long long *)b_pcur.p;
         int pt = sizeof(K) == 8 ? 704 : 512; // u128 keys need the registers of the smaller block
         if (const char *e = getenv("KTG_PAGE_THREADS")) pt = atoi(e); // tuning knob: 512, 640 or 704
         const bool palin = rc && (k % 2 == 0), special = !rc && 2 * k == 8 * sizeof(K);
@@ -869,8 +883,15 @@ template <class K> struct Builder : BuilderBase {
         ++page_updates;
         // page-bucket spill (if any): the kernel reads the count from the device
         // (keys beyond spill_cap are counted in *d_lost by the kernel and void the build in finalize)
-        KTG_TRY(launch_insert((const K *)b_pspill.p, spill_cap, nullptr, 0, 0, spill2));
+        KTG_TRY(launch_insert((const K *)b_pspill.p, pg_spill_cap, nullptr, 0, 0, d_page_spill));
         return KTG_OK;
+    }
+    int paged_update(uint32_t n_bins, uint64_t cap1, uint64_t n_keys, const unsigned long long *fill1,
+                     const K *keys1 = nullptr, uint32_t sub_mod = 0) {
+        if (!keys1) keys1 = (const K *)b_keys.p;
+        KTG_TRY(pages_open(n_keys));
+        KTG_TRY(pages_scatter(n_bins, cap1, n_keys, fill1, keys1, sub_mod));
+        return pages_update(n_keys);
     }
 
     // ---- staging -------------------------------------------------------------------
@@ -886,8 +907,24 @@ template <class K> struct Builder : BuilderBase {
     uint64_t stage_room = 0;      // keys the open stage was sized for
     uint64_t stage_target = 0;    // flush once this many keys are staged
     uint64_t stage_spill_cap = 0;
-    uint64_t staged_keys = 0;     // keys in the buckets + spill list
+    uint64_t staged_keys = 0;     // keys in the buckets + spill list (+ page buckets, see below)
     uint64_t staged_spilled = 0;  // of which in the spill list
+    // Eager page stage (host batcher, large batches).  With hold_flush the batcher has announced how
+    // many keys its call will offer (call_keys_hint) and flushes on its own schedule.  Then every
+    // chunk's level-1 buckets are moved on to page buckets right away (pages_drain): the level-2
+    // scatter runs while the copies are still coming in, when the GPU has time to spare, and a flush
+    // is only the page sweep.  The level-1 buckets then hold one chunk; the spill list stays as large
+    // as everything the page stage may take, so it still cannot overflow.
+    bool pstage_open = false;
+    uint64_t l1_keys = 0;         // keys in the level-1 buckets + spill list since the last drain
+    uint64_t pstage_room = 0;     // keys the page buckets were sized for
+    uint64_t pstaged_keys = 0;    // keys moved to page buckets (upper bound: includes spilled ones)
+    uint32_t pstage_n_sub = 0, pstage_sub_log2 = 0, pstage_page_log2 = 0;
+    uint64_t pstage_pages = 0;
+    bool eager_pages() const {
+        if (!hold_flush || !call_keys_hint || getenv("KTG_NO_EAGER")) return false; // (tuning knob)
+        return use_partition() && use_pages(call_keys_hint);
+    }
     DeviceBuf b_stage_cur;        // cursors[n_bins] | spill cursor | backup of both
     unsigned long long *stage_cursors() { return (unsigned long long *)b_stage_cur.p; }
     unsigned long long *stage_spill_cursor() { return stage_cursors() + stage_bins; }
@@ -911,12 +948,17 @@ template <class K> struct Builder : BuilderBase {
         if (const char *e = getenv("KTG_STAGE_FACTOR")) factor = atof(e); // tuning knob
         stage_target = std::min<uint64_t>((uint64_t)(factor * (double)tab.capacity()), stage_max_keys());
         stage_room = batch_keys >= stage_target ? batch_keys : stage_target + batch_keys;
-        if (hold_flush && call_keys_hint) // the batcher flushes once, after ~60 % of its input
+        const bool eager = eager_pages();
+        if (eager) { // level-1 buckets are drained after every chunk; the page stage takes the whole call
+            stage_room = batch_keys;
+            pstage_room = std::min<uint64_t>(std::max(call_keys_hint, batch_keys), stage_max_keys());
+        }
+        else if (hold_flush && call_keys_hint) // the batcher flushes once, after ~60 % of its input
             stage_room = std::max(stage_room, std::min<uint64_t>(call_keys_hint / 4 * 3 + batch_keys, stage_max_keys()));
         stage_cap1 = bucket_cap_for(stage_room, n_bins);
         // as large as the stage itself: even a batch made of one key cannot overflow it, so a
         // batch is staged without looking at the spill cursor (it is read when the stage is flushed)
-        stage_spill_cap = stage_room + 64;
+        stage_spill_cap = (eager ? pstage_room + batch_keys : stage_room) + 64;
         if ((double)stage_cap1 * n_bins >= 4.0e9) return fail(KTG_ERR_INVALID, "batch too large: split it (32-bit bucket positions)");
         KTG_TRY(b_keys.ensure(stage_cap1 * n_bins * sizeof(K) + 64));
         KTG_TRY(b_spill.ensure(stage_spill_cap * sizeof(K) + 64));
@@ -926,6 +968,27 @@ template <class K> struct Builder : BuilderBase {
         init_cursors_kernel<<<(n_bins + 255) / 256, 256, 0, stream>>>(stage_cursors(), n_bins, stage_cap1);
         KTG_CUDA(cudaMemsetAsync(stage_spill_cursor(), 0, 8, stream));
         staged_keys = staged_spilled = 0;
+        l1_keys = pstaged_keys = 0;
+        pstage_open = false;
+        if (eager) {
+            KTG_TRY(pages_open(pstage_room));
+            pstage_open = true;
+            pstage_n_sub = tab.n_sub;
+            pstage_sub_log2 = tab.sub_log2;
+            pstage_page_log2 = tab.page_log2;
+            pstage_pages = tab.n_pages();
+        }
+        return KTG_OK;
+    }
+
+    // eager page stage: level-1 buckets -> page buckets; the level-1 buckets are empty again
+    // afterwards (the spill list is not touched: its keys wait for the flush)
+    int pages_drain() {
+        if (!pstage_open || l1_keys == 0) return KTG_OK;
+        KTG_TRY(pages_scatter(stage_bins, stage_cap1, l1_keys, stage_cursors(), (const K *)b_keys.p, 0));
+        init_cursors_kernel<<<(stage_bins + 255) / 256, 256, 0, stream>>>(stage_cursors(), stage_bins, stage_cap1);
+        pstaged_keys += l1_keys;
+        l1_keys = 0;
         return KTG_OK;
     }
 
@@ -933,7 +996,8 @@ template <class K> struct Builder : BuilderBase {
     // (which also feeds the cardinality sketch); `n_keys` is the number of keys it emits (or an
     // upper bound).  Nothing here waits for the device unless the stage has to be flushed.
     template <class S> int stage_add(uint64_t n_keys, S scatter) {
-        if (stage_bins != tab.n_sub || stage_sub_log2 != tab.sub_log2 || staged_keys + n_keys > stage_room) {
+        if (stage_bins != tab.n_sub || stage_sub_log2 != tab.sub_log2 || l1_keys + n_keys > stage_room ||
+            (pstage_open && pstaged_keys + l1_keys + n_keys > pstage_room) || (!pstage_open && stage_bins && eager_pages())) {
             KTG_TRY(flush_staged());
             KTG_TRY(stage_open(n_keys));
         }
@@ -946,7 +1010,9 @@ template <class K> struct Builder : BuilderBase {
         o.spill_cap = stage_spill_cap;
         KTG_TRY(scatter(stage_bins, o));
         staged_keys += n_keys;
+        l1_keys += n_keys;
         nodes_valid = false;
+        KTG_TRY(pages_drain());
         if (staged_keys >= stage_target && !hold_flush) KTG_TRY(flush_staged());
         return KTG_OK;
     }
@@ -955,6 +1021,7 @@ template <class K> struct Builder : BuilderBase {
     int flush_staged() {
         if (staged_keys == 0) {
             stage_bins = 0;
+            pstage_open = false;
             return KTG_OK;
         }
         trace("flush", staged_keys);
@@ -974,13 +1041,29 @@ template <class K> struct Builder : BuilderBase {
             KTG_TRY(grow_to(need));
             moved = tab.n_sub != stage_bins || tab.sub_log2 != stage_sub_log2;
         }
-        const uint64_t n = staged_keys, spilled = staged_spilled;
+        const uint64_t n = staged_keys, spilled = staged_spilled, n_l1 = l1_keys, n_pg = pstaged_keys;
         const uint32_t bins = stage_bins;
+        const bool eager = pstage_open;
         staged_keys = staged_spilled = 0;
+        l1_keys = pstaged_keys = 0;
+        pstage_open = false;
         stage_bins = 0; // the next batch opens a new stage (sized for the table as it is then)
         // After a change of geometry the buckets no longer match the sub-tables: the keys are
         // still all there, they just lose their L2 locality for this one flush.
-        if (!moved && use_pages(n)) KTG_TRY(paged_update(bins, stage_cap1, n, stage_cursors()));
+        if (eager) {
+            const bool pmoved = moved || tab.n_pages() != pstage_pages || tab.page_log2 != pstage_page_log2 ||
+                                tab.n_sub != pstage_n_sub || tab.sub_log2 != pstage_sub_log2;
+            if (!pmoved) {
+                if (n_l1) KTG_TRY(pages_scatter(bins, stage_cap1, n_l1, stage_cursors(), (const K *)b_keys.p, 0));
+                KTG_TRY(pages_update(n));
+            }
+            else { // page buckets of a geometry that is gone: plain arrays of keys now
+                if (n_l1) KTG_TRY(launch_insert((const K *)b_keys.p, n_l1, stage_cursors(), stage_cap1, bins));
+                if (n_pg) KTG_TRY(launch_insert((const K *)b_pkeys.p, n_pg, (const unsigned long long *)b_pcur.p, pg_cap2, (uint32_t)pstage_pages));
+                KTG_TRY(launch_insert((const K *)b_pspill.p, pg_spill_cap, nullptr, 0, 0, d_page_spill));
+            }
+        }
+        else if (!moved && use_pages(n)) KTG_TRY(paged_update(bins, stage_cap1, n, stage_cursors()));
         else KTG_TRY(launch_insert((const K *)b_keys.p, n, stage_cursors(), stage_cap1, bins));
         if (spilled) KTG_TRY(launch_insert_keys((const K *)b_spill.p, spilled));
         return KTG_OK;
@@ -1049,6 +1132,9 @@ template <class K> struct Builder : BuilderBase {
 
     int flush_hint() override {
         if (deferred_error != KTG_OK || 4 * staged_keys < tab.capacity()) return KTG_OK;
+        // a call that does not fit one stage is flushed whenever the stage is full: one more sweep
+        // of the table on the way would only add its cost (C3 at k = 63: 30 GB per sweep)
+        if (call_keys_hint > stage_max_keys()) return KTG_OK;
         return flush_staged();
     }
 
@@ -1070,6 +1156,8 @@ template <class K> struct Builder : BuilderBase {
     int reset() override {
         trace("reset");
         staged_keys = staged_spilled = 0;
+        l1_keys = pstaged_keys = 0;
+        pstage_open = false;
         stage_bins = 0;
         fresh = true; // the next user of the table memory initialises it (ensure_init / page update)
         KTG_TRY(init_special_slot(tab));

@@ -1,6 +1,9 @@
 // ktg_api.cu -- the extern "C" boundary declared in include/katome_gpu.h.
 #include <fstream>
 #include <memory>
+#include <atomic>
+#include <system_error>
+#include <thread>
 
 #include "builder.cuh"
 #include "fastq_device.cuh"
@@ -12,7 +15,9 @@ struct ktg_builder {
     std::unique_ptr<BuilderBase> impl;
     // device staging for host batches: two buffers for the full chunks, four small ones for the
     // short chunks a large batch ends in (all of those are copied while the last flush runs)
-    static constexpr int N_STAGE = 6;
+    // staging buffers of the host batcher: up to N_FULL rotate under the full chunks, the short
+    // chunks at the end of a large batch have one each
+    static constexpr int N_FULL = 6, N_TAIL = 4, N_STAGE = N_FULL + N_TAIL;
     DeviceBuf st_bases[N_STAGE], st_offs[N_STAGE];
     cudaEvent_t st_free[N_STAGE] = {}; // staging buffer consumed by the compute stream
     cudaEvent_t st_ready[N_STAGE] = {};
@@ -151,7 +156,18 @@ int ktg_add_reads(ktg_builder *b, const uint8_t *bases, const uint64_t *offsets,
     std::vector<char> flush_here(n_chunks, 0);
     if (large) {
         const size_t last_full = tail_first != (size_t)-1 ? tail_first - 1 : n_chunks - 1;
-        for (uint64_t pct : {55u}) {
+        std::vector<uint64_t> pcts{55};
+        if (const char *e = getenv("KTG_FLUSH_PCT")) { // tuning knob: comma separated percentages of the bytes
+            pcts.clear();
+            for (const char *q = e; *q;) {
+                char *end = nullptr;
+                const long v = strtol(q, &end, 10);
+                if (end == q) break;
+                if (v >= 1 && v <= 100) pcts.push_back((uint64_t)v);
+                q = *end == ',' ? end + 1 : end;
+            }
+        }
+        for (uint64_t pct : pcts) {
             size_t c = 0;
             while (c + 1 < n_chunks && offsets[cut[c + 1]] - offsets[0] < total / 100 * pct) ++c;
             flush_here[std::min(c, last_full)] = 1;
@@ -165,32 +181,68 @@ int ktg_add_reads(ktg_builder *b, const uint8_t *bases, const uint64_t *offsets,
         impl->hold_flush = true;
         impl->call_keys_hint = total > n_reads * (uint64_t)(impl->k - 1) ? total - n_reads * (uint64_t)(impl->k - 1) : 0;
     }
-    // staging buffer of chunk c: the full chunks alternate between 0 and 1, the short ones at
-    // the end have one each
+    // staging buffer of chunk c: the full chunks rotate over n_full buffers, the short ones at the
+    // end have one each.  Two are enough: a buffer is free as soon as its chunk is packed, and a large
+    // call ends in short chunks with buffers of their own, so the copy engine does not wait for a
+    // flush (measured on C2: 3, 4 or 6 buffers change nothing; KTG_STAGE_BUFS to try).
+    size_t n_full = 2;
+    if (const char *e = getenv("KTG_STAGE_BUFS")) n_full = (size_t)atoi(e); // tuning knob
+    n_full = std::min<size_t>(std::max<size_t>(n_full, 2), ktg_builder::N_FULL);
     auto slot_of = [&](size_t c) -> int {
-        return c >= tail_first ? 2 + (int)std::min<size_t>(c - tail_first, ktg_builder::N_STAGE - 3) : (int)(c & 1);
+        return c >= tail_first ? ktg_builder::N_FULL + (int)std::min<size_t>(c - tail_first, ktg_builder::N_TAIL - 1)
+                               : (int)(c % n_full);
     };
     // What the offsets on the host already tell about a chunk: one read length or ragged, and how
     // many windows at most; with that the chunk is queued without a device round trip, and the
     // offsets of a uniform chunk are generated on the device instead of copied (8 bytes per read:
     // 8 % of the PCIe traffic of 100 bp reads).
+    // (the pass over the offsets takes ~0.6 ms of host time per 64 MiB of 100 bp reads; on the issuing
+    // thread that made the host the pace setter of the whole call, so a helper thread runs ahead with it)
     std::vector<BatchHint> hints(n_chunks);
-    std::vector<char> have_hint(n_chunks, 0);
-    auto hint_of = [&](size_t c) -> const BatchHint & {
-        if (have_hint[c]) return hints[c];
+    std::atomic<size_t> hints_done{0};
+    auto compute_hint = [&](size_t c) {
         BatchHint &h = hints[c];
         const uint64_t r = cut[c], r1 = cut[c + 1], kk = impl->k, len0 = offsets[r + 1] - offsets[r];
-        bool uniform = true;
+        uint64_t diff = 0; // one length?  (branch free; the window count needs its own pass only for a ragged chunk)
+        for (uint64_t i = r; i < r1; ++i) diff |= (offsets[i + 1] - offsets[i]) ^ len0;
+        const bool uniform = diff == 0;
         uint64_t wub = 0;
-        for (uint64_t i = r; i < r1; ++i) {
-            const uint64_t len = offsets[i + 1] - offsets[i];
-            uniform &= len == len0;
-            wub += len >= kk ? len - kk + 1 : 0;
-        }
+        if (uniform) wub = len0 >= kk ? (r1 - r) * (len0 - kk + 1) : 0;
+        else
+            for (uint64_t i = r; i < r1; ++i) {
+                const uint64_t len = offsets[i + 1] - offsets[i];
+                wub += len >= kk ? len - kk + 1 : 0;
+            }
         h.ulen = (uniform && len0 <= 0xFFFFFFFFull) ? (uint32_t)len0 : 0;
         h.windows_ub = wub;
-        have_hint[c] = 1;
-        return h;
+    };
+    struct Helper { // joined on every way out of this function
+        std::thread t;
+        ~Helper() {
+            if (t.joinable()) t.join();
+        }
+    } helper;
+    if (n_chunks >= 3) {
+        try {
+            helper.t = std::thread([&] {
+                for (size_t c = 0; c < n_chunks; ++c) {
+                    compute_hint(c);
+                    hints_done.store(c + 1, std::memory_order_release);
+                }
+            });
+        } catch (const std::system_error &) { // no thread to be had: do it here
+        }
+    }
+    auto hint_of = [&](size_t c) -> const BatchHint & {
+        if (!helper.t.joinable()) {
+            for (size_t d = hints_done.load(std::memory_order_relaxed); d <= c; ++d) {
+                compute_hint(d);
+                hints_done.store(d + 1, std::memory_order_relaxed);
+            }
+        }
+        else
+            while (hints_done.load(std::memory_order_acquire) <= c) std::this_thread::yield();
+        return hints[c];
     };
     auto issue_copy = [&](size_t c) -> int {
         const uint64_t r = cut[c], r1 = cut[c + 1], nb = offsets[r1] - offsets[r], nr = r1 - r;
@@ -200,11 +252,10 @@ int ktg_add_reads(ktg_builder *b, const uint8_t *bases, const uint64_t *offsets,
         if (b->st_bases[s].cap < nb + 64 || b->st_offs[s].cap < (nr + 1) * 8) {
             KTG_CUDA(cudaStreamSynchronize(impl->stream)); // reallocation frees the old buffer
             KTG_CUDA(cudaStreamSynchronize(impl->copy_stream));
-            KTG_TRY(b->st_bases[s].ensure((s < 2 ? std::max<uint64_t>(nb, CHUNK) : nb + nb / 4) + 64));
+            KTG_TRY(b->st_bases[s].ensure((s < ktg_builder::N_FULL ? std::max<uint64_t>(nb, CHUNK) : nb + nb / 4) + 64));
             KTG_TRY(b->st_offs[s].ensure((nr + 1) * 8));
         }
         KTG_CUDA(cudaMemcpyAsync(b->st_bases[s].p, bases + offsets[r], nb, cudaMemcpyHostToDevice, impl->copy_stream));
-        // (the pass over the offsets is 0.6-0.8 ms of host time per 64 MiB of 100 bp reads: behind the copy)
         const uint32_t ulen = hint_of(c).ulen;
         if (ulen) {
             const int g = (int)std::min<uint64_t>((nr + 1 + 255) / 256, 4096);
@@ -222,7 +273,7 @@ int ktg_add_reads(ktg_builder *b, const uint8_t *bases, const uint64_t *offsets,
     KTG_TRY(issue_copy(0));
     size_t issued = 1;
     for (size_t c = 0; c < n_chunks; ++c) {
-        const size_t ahead = (tail_first != (size_t)-1 && c + 1 >= tail_first) ? n_chunks : std::min(c + 2, n_chunks);
+        const size_t ahead = (tail_first != (size_t)-1 && c + 1 >= tail_first) ? n_chunks : std::min(c + n_full, n_chunks);
         for (; issued < ahead; ++issued) KTG_TRY(issue_copy(issued));
         const uint64_t r = cut[c], r1 = cut[c + 1], nb = offsets[r1] - offsets[r], nr = r1 - r;
         const int s = slot_of(c);

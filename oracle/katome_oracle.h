@@ -98,6 +98,14 @@ void ko_digest(const ko_gir *g, uint64_t out[4]);
  * k-mer.  Returns bytes needed; writes at most cap bytes. */
 uint64_t ko_dump(const ko_gir *g, char *buf, uint64_t cap);
 
+/* ---- "optimistic CPU" (katome_oracle_mt.c): NOT the reference's work shape.  The same edge
+ * multiset counted with rolling extraction, canonical keys, an edge-keyed table and n_threads host
+ * threads (hash-sharded); returns ko_digest()'s four numbers for the batch.  bench.py reports it
+ * beside the faithful single-thread port, tests check it against ko_digest(). */
+int ko_mt_build_digest(int k, const uint8_t *bases, const uint64_t *offsets, uint64_t n_reads,
+                       int reverse_complement, int n_threads, uint64_t out[4],
+                       uint64_t *accepted_reads, uint64_t *accepted_bytes);
+
 /* ---- codec (compress.rs) ---- */
 uint8_t ko_encode_fasta_symbol(uint8_t symbol, uint8_t carrier);                /* :347-378 */
 size_t ko_compress_node(const uint8_t *s, size_t len, uint8_t *out);            /* :55-73  */

@@ -25,8 +25,8 @@ class OracleError(RuntimeError):
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "katome_oracle.c")
-    stale = (not os.path.exists(_SO)) or os.path.getmtime(_SO) < os.path.getmtime(src)
+    srcs = [os.path.join(_HERE, f) for f in ("katome_oracle.c", "katome_oracle_mt.c", "katome_oracle.h")]
+    stale = (not os.path.exists(_SO)) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs)
     if force or stale:
         subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
     return _SO
@@ -76,6 +76,7 @@ def lib():
         L.ko_splitmix64.argtypes = [C.c_uint64]
         L.ko_synth_reads.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p]
         L.ko_synth_genome.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
+        L.ko_mt_build_digest.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, u64p, u64p, u64p]
         _lib = L
     return _lib
 
@@ -268,3 +269,15 @@ def synth_genome(seed_g: int, pos0: int, n: int) -> np.ndarray:
     out = np.empty(n, np.uint8)
     lib().ko_synth_genome(seed_g, pos0, n, out.ctypes.data)
     return out
+
+
+def mt_build_digest(k: int, bases: np.ndarray, offsets: np.ndarray, reverse_complement: bool, n_threads: int):
+    """The "optimistic CPU" counter (katome_oracle_mt.c): hash-sharded over n_threads host threads.
+    Returns (digest tuple as OracleGIR.digest(), accepted_reads, accepted_bytes)."""
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    out = (C.c_uint64 * 4)()
+    nr, nb = C.c_uint64(0), C.c_uint64(0)
+    _check(lib().ko_mt_build_digest(k, bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1,
+                                    int(reverse_complement), int(n_threads), out, C.byref(nr), C.byref(nb)))
+    return tuple(int(x) for x in out), nr.value, nb.value

@@ -224,6 +224,60 @@ def test_paged_and_atomic_paths_agree_at_scale(K):
     assert res[0] == res[1] and res[0][0][2] == 2 * n * (L - 63 + 1)
 
 
+@pytest.mark.parametrize("k,rc", [(31, True), (32, False), (40, True), (63, True)])
+def test_host_batcher_large_call(K, k, rc):
+    """ktg_add_reads on a call of many chunks (KTG_CHUNK_MB=1 makes a 5 MB batch "large"): tapered last
+    chunks, held-back flush with one flush on the way, and the eager page stage (every chunk's keys are
+    moved on to page buckets at once, a flush is only the page sweep) -- against the oracle, with the
+    eager stage off, with a table that has to grow at the flush (page buckets of a geometry that is
+    gone fall back to L2 atomics), with ragged reads, and over two calls into one stage."""
+    import os
+    rng = np.random.default_rng(1000 + k)
+    genome = "".join(rng.choice(list("ACGT"), size=60000))
+    uniform = [genome[i:i + 100] for i in rng.integers(0, len(genome) - 100, size=50000)]
+    uniform[17] = uniform[17][:40] + "N" + uniform[17][41:]
+    uniform += ["T" * 100, "A" * 100, "AT" * 50, "ACGT" * 25]
+    ragged = H.random_reads(rng, 30000, max(k, 70), 190, genome=genome, n_rate=0.02)
+    cases = []
+    for name, seqs in (("uniform", uniform), ("ragged", ragged)):
+        cases.append((name, seqs, _oracle(seqs, k, rc)))
+    distinct = 2 * len(genome) * 2
+    os.environ["KTG_CHUNK_MB"] = "1"
+    try:
+        for name, seqs, cpu in cases:
+            bases, offsets = H.batch_of(seqs)
+            for kw, env in (({"force_pages": True, "sub_table_log2_bytes": 18, "edges_count": distinct}, {}),
+                            ({"force_pages": True, "sub_table_log2_bytes": 18, "edges_count": distinct}, {"KTG_NO_EAGER": "1"}),
+                            ({"force_pages": True, "sub_table_log2_bytes": 18, "edges_count": distinct}, {"KTG_FLUSH_PCT": "30", "KTG_STAGE_BUFS": "3"}),
+                            ({"force_pages": True, "sub_table_log2_bytes": 16, "edges_count": 3000}, {}),  # must grow
+                            ({"force_pages": True, "sub_table_log2_bytes": 16}, {})):                     # no hint at all
+                os.environ.update(env)
+                try:
+                    g = K.GpuGIR(k, rc, profile=True, **kw)
+                    nr, nb = g.add_reads(bases, offsets)
+                    assert (nr, nb) == (cpu.accepted_reads, cpu.accepted_bytes), (name, kw, env)
+                    _assert_same(g, cpu, full_stats=False)
+                    if kw.get("edges_count") == distinct:
+                        sweeps, scatters = g.info()["page_updates"], g.profile()["scatter_pages"]["launches"]
+                        assert sweeps >= 2, (name, g.info())  # the flush on the way + the final one
+                        # eager: one level-2 scatter per chunk; otherwise one per sweep
+                        assert (scatters == sweeps) if "KTG_NO_EAGER" in env else (scatters >= 4 > sweeps), (scatters, sweeps)
+                    g.close()
+                finally:
+                    for key in env:
+                        os.environ.pop(key, None)
+        # two large calls into one builder; the second finds the first one's stage open
+        name, seqs, cpu2 = cases[0][0], cases[0][1] + cases[1][1], None
+        cpu2 = _oracle(seqs, k, rc)
+        g = K.GpuGIR(k, rc, force_pages=True, sub_table_log2_bytes=18, edges_count=distinct)
+        g.add_reads(*H.batch_of(cases[0][1]))
+        g.add_reads(*H.batch_of(cases[1][1]))
+        _assert_same(g, cpu2, full_stats=False)
+        g.close()
+    finally:
+        os.environ.pop("KTG_CHUNK_MB", None)
+
+
 @pytest.mark.parametrize("k,rc", [(4, True), (31, True), (32, False), (33, True), (34, False), (40, True), (63, True), (64, True)])
 def test_graph_export_for_convert(K, k, rc):
     """SURVEY 8f-1: the hand-off to Convert::create_from -- sorted node set, edges with the indices

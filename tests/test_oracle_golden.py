@@ -205,3 +205,25 @@ def test_bfcounter_input_matches_the_set_level_twin(tmp_path):
         assert e.value.code == code
     with pytest.raises(O.OracleError):
         O.OracleGIR.create_bfc(31, [str(tmp_path / "missing.txt")], True, 0)
+
+
+@pytest.mark.parametrize("k,rc", [(4, True), (5, True), (31, True), (31, False), (32, True), (32, False), (33, True),
+                                  (40, True), (63, True), (64, True), (64, False)])
+def test_optimistic_cpu_counter_equals_the_faithful_oracle(k, rc):
+    """katome_oracle_mt.c (rolling, canonical, edge keyed, hash-sharded over threads: the "optimistic CPU"
+    line of the bench) produces the digest of the faithful restatement, whatever the thread count."""
+    rng = np.random.default_rng(7 * k + rc)
+    seqs = H.random_reads(rng, 120, k, k + 90, n_rate=0.1)
+    seqs += ["T" * (k + 7), "A" * (k + 3), "AT" * k, "ACGT" * k]  # all-ones key, palindromes (even k)
+    bases, offsets = H.batch_of(seqs)
+    g = O.OracleGIR(k)
+    g.add_reads(bases, offsets, rc)
+    for threads in (1, 2, 5):
+        d, nr, nb = O.mt_build_digest(k, bases, offsets, rc, threads)
+        assert d == g.digest()
+        assert (nr, nb) == (g.accepted_reads, g.accepted_bytes)
+    # a read shorter than k voids the build in both (hm_gir.rs:40)
+    bases, offsets = H.batch_of(seqs + ["ACG"[: min(3, k - 1)]])
+    with pytest.raises(O.OracleError) as e:
+        O.mt_build_digest(k, bases, offsets, rc, 3)
+    assert e.value.code == O.KO_ERR_SHORT_READ
