@@ -99,7 +99,7 @@ pack_flat_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restrict__
 
 // One thread per read: accept / reject (any bad byte rejects the whole read), counters, and
 // valid[r] = 1 iff the read contributes windows (accepted and len >= k).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 check_reads_kernel(const uint64_t *__restrict__ offsets, uint64_t n_reads,
                    const uint8_t *__restrict__ bases, uint32_t k, const uint32_t *__restrict__ bad,
                    uint8_t *__restrict__ valid, PackCounters *ctr) {
@@ -1271,22 +1271,50 @@ __device__ __forceinline__ uint64_t digest_term(uint64_t hi, uint64_t lo, uint32
     return splitmix64(splitmix64(hi) ^ lo) * (2ull * w + 1ull);
 }
 
+// Less than half of the slots are occupied and an occupied one costs ~130 instructions (four
+// splitmix64 rounds and a reverse complement), so lanes do not digest "their" slots: a warp
+// compacts the occupied slots it streams past into a small shared-memory queue and digests them in
+// full rows of 32 (the scan was 45 % divergence-idle and instruction bound at 3.2 TB/s before).
 template <class K, bool RC>
 __global__ void __launch_bounds__(256)
 edge_stats_kernel(const typename KeyTraits<K>::Slot *slots, uint64_t n_slots, uint32_t k,
                   uint32_t threshold, EdgeStats *out) {
     typedef KeyTraits<K> T;
     typedef typename T::Slot Slot;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    constexpr int U = 4, QCAP = 64; // < 32 left over + <= 32 pushed per step
+    __shared__ uint64_t q_lo[8][QCAP];
+    __shared__ uint64_t q_hi[sizeof(Slot) == 32 ? 8 : 1][QCAP];
+    __shared__ uint32_t q_w[8][QCAP];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint64_t acc[4] = {0, 0, 0, 0}; // edges, sum_w, sum_w_below, digest
     uint64_t mx = 0;
-    // whole slots with 16-byte loads, four in flight per thread (a pure HBM stream)
-    constexpr int U = 4;
-    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n_slots; i0 += U * stride) {
+    uint32_t qn = 0; // warp-uniform
+    auto digest_one = [&](uint64_t hi, uint64_t lo, uint32_t w) {
+        const K key = T::make(hi, lo);
+        uint64_t mult = 1;
+        uint64_t d = digest_term(T::hi(key), T::lo(key), w);
+        if (RC) {
+            K r = revcomp(key, k);
+            if (r != key) {
+                mult = 2;
+                d += digest_term(T::hi(r), T::lo(r), w);
+            }
+        }
+        acc[0] += mult;
+        acc[1] += mult * w;
+        if (w < threshold) acc[2] += mult * w;
+        acc[3] += d;
+        if (w > mx) mx = w;
+    };
+    // whole slots with 16-byte loads, U in flight per lane (a pure HBM stream); a warp covers
+    // 32 * U consecutive slots per step
+    const uint64_t warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    const uint64_t gw = (uint64_t)blockIdx.x * (blockDim.x >> 5) + wid;
+    for (uint64_t base = gw * (32 * U); base < n_slots; base += warps * (32 * U)) {
         uint4 v[U], v2[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const uint64_t i = i0 + u * stride;
+            const uint64_t i = base + u * 32 + lane;
             v[u] = make_uint4(0, 0, 0, 0);
             v2[u] = make_uint4(0, 0, 0, 0);
             if (i < n_slots) {
@@ -1297,26 +1325,24 @@ edge_stats_kernel(const typename KeyTraits<K>::Slot *slots, uint64_t n_slots, ui
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const uint32_t w = sizeof(Slot) == 32 ? v2[u].x : v[u].z;
-            if (w == 0) continue;
-            const uint64_t lo = ((uint64_t)v[u].y << 32) | v[u].x;
-            const uint64_t hi = sizeof(Slot) == 32 ? (((uint64_t)v[u].w << 32) | v[u].z) : 0;
-            const K key = T::make(hi, lo);
-            uint64_t mult = 1;
-            uint64_t d = digest_term(T::hi(key), T::lo(key), w);
-            if (RC) {
-                K r = revcomp(key, k);
-                if (r != key) {
-                    mult = 2;
-                    d += digest_term(T::hi(r), T::lo(r), w);
-                }
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, w != 0);
+            if (m == 0) continue;
+            if (w != 0) {
+                const uint32_t pos = qn + __popc(m & ((1u << lane) - 1u));
+                q_lo[wid][pos] = ((uint64_t)v[u].y << 32) | v[u].x;
+                if (sizeof(Slot) == 32) q_hi[wid][pos] = ((uint64_t)v[u].w << 32) | v[u].z;
+                q_w[wid][pos] = w;
             }
-            acc[0] += mult;
-            acc[1] += mult * w;
-            if (w < threshold) acc[2] += mult * w;
-            acc[3] += d;
-            if (w > mx) mx = w;
+            qn += __popc(m);
+            __syncwarp();
+            if (qn >= 32) {
+                qn -= 32;
+                digest_one(sizeof(Slot) == 32 ? q_hi[wid][qn + lane] : 0, q_lo[wid][qn + lane], q_w[wid][qn + lane]);
+                __syncwarp();
+            }
         }
     }
+    if (lane < qn) digest_one(sizeof(Slot) == 32 ? q_hi[wid][lane] : 0, q_lo[wid][lane], q_w[wid][lane]);
     uint64_t a4[4] = {acc[0], acc[1], acc[2], acc[3]};
     // EdgeStats layout: edges, sum_w, sum_w_below, max_w, digest
     __shared__ unsigned long long sh[5];
