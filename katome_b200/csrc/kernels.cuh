@@ -9,6 +9,7 @@
 //
 // Reference code each one replaces is cited at the kernel.
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 
 namespace ktg {
@@ -850,22 +851,38 @@ scatter_buckets_kernel(const K *__restrict__ keys1, const unsigned long long *__
     for (uint32_t i = threadIdx.x; i < 2 * n2; i += L2S_THREADS) sm.cnt[i] = 0;
     __syncthreads();
     uint32_t parity = 0;
+    const uint32_t tpb = (uint32_t)tiles_per_bin;
     for (uint32_t tile = blockIdx.x; tile < (uint32_t)n_tiles; tile += gridDim.x) {
-        const uint64_t q = tile / (uint32_t)tiles_per_bin;
-        const uint64_t b = LEVEL == 2 ? (sub_mod ? q % sub_mod : q) : 0;
-        const uint64_t lim = (q + 1) * cap1, fill = fill1[q];
-        const uint64_t base = q * cap1 + (uint64_t)(tile - (uint32_t)q * (uint32_t)tiles_per_bin) * L2S_TILE;
+        const uint32_t q = tile / tpb; // (32-bit: as 64-bit division and modulo these two lines were 6 % of the kernel)
+        const uint32_t b = LEVEL == 2 ? (sub_mod ? q % sub_mod : q) : 0;
+        const uint64_t lim = ((uint64_t)q + 1) * cap1, fill = fill1[q];
+        const uint64_t base = (uint64_t)q * cap1 + (uint64_t)(tile - q * tpb) * L2S_TILE;
         const uint64_t end = fill < lim ? fill : lim;
         if (base >= end) continue;
         K key[L2S_PER];
         uint32_t bin[L2S_PER];
-        uint32_t vmask = 0, sampled = 0;
         KTG_PHASE_BEGIN();
+        if (!skip_empty && !HLL && base + L2S_TILE <= end) {
+            // a whole tile (all but the last of a bucket): no per-key bounds, every key is valid
+#pragma unroll
+            for (int j = 0; j < L2S_PER; ++j) {
+                key[j] = KeyTraits<K>::load_stream(&keys1[base + (uint32_t)(j * L2S_THREADS) + threadIdx.x]);
+                if (LEVEL == 2) bin[j] = (KeyTraits<K>::slot_hash(key[j]) & t.sub_mask) >> t.page_log2;
+                else bin[j] = place_of(KeyTraits<K>::hash(key[j]), t.world, t.n_sub).part;
+            }
+            KTG_PHASE(0);
+            tile_scatter<K, L2S_THREADS, L2S_PER>(key, bin, (1u << L2S_PER) - 1u, sm, n2, o.cursors + (uint64_t)b * n2,
+                                                  (uint64_t)b * n2, o, parity);
+            parity ^= 1u;
+            continue;
+        }
+        uint32_t vmask = 0, sampled = 0;
+        const uint32_t rem = (uint32_t)(end - base < L2S_TILE ? end - base : L2S_TILE);
 #pragma unroll
         for (int j = 0; j < L2S_PER; ++j) {
-            const uint64_t i = base + (uint64_t)j * L2S_THREADS + threadIdx.x;
-            const bool in = i < end;
-            key[j] = in ? KeyTraits<K>::load_stream(&keys1[i]) : (K)0;
+            const uint32_t o32 = (uint32_t)(j * L2S_THREADS) + threadIdx.x;
+            const bool in = o32 < rem;
+            key[j] = in ? KeyTraits<K>::load_stream(&keys1[base + o32]) : (K)0;
             if (LEVEL == 2) bin[j] = (KeyTraits<K>::slot_hash(key[j]) & t.sub_mask) >> t.page_log2;
             else {
                 const uint64_t h = KeyTraits<K>::hash(key[j]);
@@ -879,7 +896,7 @@ scatter_buckets_kernel(const K *__restrict__ keys1, const unsigned long long *__
         if (threadIdx.x == 0 && key[L2S_PER - 1] == (K)12345) g_phase_cycles[7] = 1; // wait for the loads
 #endif
         KTG_PHASE(0);
-        tile_scatter<K, L2S_THREADS, L2S_PER>(key, bin, vmask, sm, n2, o.cursors + b * n2, b * n2, o, parity);
+        tile_scatter<K, L2S_THREADS, L2S_PER>(key, bin, vmask, sm, n2, o.cursors + (uint64_t)b * n2, (uint64_t)b * n2, o, parity);
         parity ^= 1u;
     }
 }
@@ -1032,13 +1049,16 @@ __device__ __forceinline__ void smem_to_slot(KeyTraits<u128>::Slot *g, const u12
     ((uint4 *)g)[1] = make_uint4(*sw, 0u, 0u, 0u);
 }
 
-template <class K, int THREADS, int PAGE_UNROLL = ktg::PAGE_UNROLL>
+// FIXED_LOG2 != 0: the page size is a compile-time constant (the usual geometry, PageGeom<K>::LOG2), so
+// the shared-memory carve-up and the page mask cost no registers (the kernel runs at 40 per thread
+// and recomputed them inside the probe loops otherwise)
+template <class K, int THREADS, int PAGE_UNROLL = ktg::PAGE_UNROLL, int FIXED_LOG2 = 0, bool FULL_ROWS = false>
 __global__ void __launch_bounds__(THREADS, 2)
 update_pages_kernel(const K *__restrict__ keys2, const unsigned long long *__restrict__ cursors2,
                     uint64_t cap2, uint32_t k, bool check_palindrome, bool has_special, Table<K> t, bool fresh) {
     typedef KeyTraits<K> T;
     extern __shared__ __align__(16) unsigned char smem[];
-    const uint32_t P = 1u << t.page_log2;
+    const uint32_t P = FIXED_LOG2 ? (1u << FIXED_LOG2) : (1u << t.page_log2);
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     PageCtx<K> c;
     c.sk = (K *)smem;
@@ -1046,7 +1066,7 @@ update_pages_kernel(const K *__restrict__ keys2, const unsigned long long *__res
     c.sw = (uint32_t *)(c.sk + P + (THREADS / 32) * PQ_CAP);
     c.qi = c.sw + P + wid * PQ_CAP;
     c.qn = 0;
-    c.page_mask = t.page_mask;
+    c.page_mask = FIXED_LOG2 ? ((1u << FIXED_LOG2) - 1u) : t.page_mask;
     const uint64_t n_pages = t.n_pages();
     for (uint64_t g = blockIdx.x; g < n_pages; g += gridDim.x) {
         typename T::Slot *gs = t.slots + g * P;
@@ -1063,13 +1083,15 @@ update_pages_kernel(const K *__restrict__ keys2, const unsigned long long *__res
         const uint64_t beg = g * cap2, lim = beg + cap2, cur = cursors2[g];
         const uint32_t n = (uint32_t)((cur < lim ? cur : lim) - beg);
         const K *src = keys2 + beg;
-        // a warp takes PAGE_UNROLL consecutive rows of 32 keys at a time
-        for (uint32_t r0 = wid * 32 * PAGE_UNROLL; r0 < n; r0 += THREADS * PAGE_UNROLL) {
+        // a warp takes PAGE_UNROLL consecutive rows of 32 keys at a time; FULL: all of them inside
+        // the bucket (all but its last rows), so no per-key bounds
+        auto rows = [&](uint32_t r0, auto full_tag) {
+            constexpr bool FULL = decltype(full_tag)::value;
             K my[PAGE_UNROLL];
 #pragma unroll
             for (int q = 0; q < PAGE_UNROLL; ++q) {
                 const uint32_t i = r0 + q * 32 + lane;
-                my[q] = i < n ? T::load_stream(&src[i]) : T::empty();
+                my[q] = (FULL || i < n) ? T::load_stream(&src[i]) : T::empty();
             }
             // first probes of the PAGE_UNROLL keys: independent shared-memory loads in flight together
             uint32_t st[PAGE_UNROLL];
@@ -1077,7 +1099,7 @@ update_pages_kernel(const K *__restrict__ keys2, const unsigned long long *__res
             bool active[PAGE_UNROLL];
 #pragma unroll
             for (int q = 0; q < PAGE_UNROLL; ++q) {
-                active[q] = r0 + q * 32 + lane < n;
+                active[q] = FULL || r0 + q * 32 + lane < n;
                 if (has_special && active[q] && my[q] == T::empty()) { // all-T at full key width, no canonicalisation
                     atomicAdd(&t.slots[t.capacity()].w, 1u);
                     active[q] = false;
@@ -1092,6 +1114,10 @@ update_pages_kernel(const K *__restrict__ keys2, const unsigned long long *__res
                 page_push(c, my[q], st[q], pending);
                 page_retry_rows(c, t);
             }
+        };
+        for (uint32_t r0 = wid * 32 * PAGE_UNROLL; r0 < n; r0 += THREADS * PAGE_UNROLL) {
+            if (FULL_ROWS && r0 + 32 * PAGE_UNROLL <= n) rows(r0, std::true_type{});
+            else rows(r0, std::false_type{});
         }
         page_drain(c, t);
         __syncthreads();
