@@ -20,9 +20,10 @@ sys.path.insert(0, ROOT)
 _OUT = sys.stdout
 METRIC = "kmers_inserted_per_sec"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed `ncu --set full`
-# capture of this command at N=1 on workload c2 (profiles/r01_ncu_full_c2_final2.txt)
-NCU_TRAFFIC_C2 = {"scatter_reads": 0.121311e9 + 2.520613e9, "scatter_pages": 2.578176e9 + 2.522128e9,
-                  "update_pages": 2.600737e9 + 1.686935e9, "pack_reads": 0.460008e9 + 0.121134e9}
+# capture of this command at N=1 on workload c2 (profiles/r01_ncu_full_c2_final3.txt)
+NCU_SOURCE = "profiles/r01_ncu_full_c2_final3.txt"
+NCU_TRAFFIC_C2 = {"scatter_reads": 0.122055e9 + 2.519546e9, "scatter_pages": 2.577942e9 + 2.520448e9,
+                  "update_pages": 2.599678e9 + 1.687045e9, "pack_reads": 0.460009e9 + 0.117671e9}
 UNIT = "k-mers/s"
 
 
@@ -309,7 +310,7 @@ def run_ours(args):
         ach = alg / (avg_ms * 1e-3) / 1e9
         traffic = NCU_TRAFFIC_C2.get(top) if (args.workload == "c2" and world == 1) else None
         roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": traffic, "traffic_source": "profiles/r01_ncu_full_c2_final2.txt" if traffic else None,
+                "traffic": traffic, "traffic_source": NCU_SOURCE if traffic else None,
                 "peak_source": peak_src, "avg_launch_ms": avg_ms,
                 "algorithmic_bytes_per_launch": alg,
                 "kernel_share_of_step": kern[top]["ms"] / args.steps / ms_step}
