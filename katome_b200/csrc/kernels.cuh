@@ -862,7 +862,7 @@ scatter_buckets_kernel(const K *__restrict__ keys1, const unsigned long long *__
         K key[L2S_PER];
         uint32_t bin[L2S_PER];
         KTG_PHASE_BEGIN();
-        if (LEVEL == 2 && base + L2S_TILE <= end) {
+        if (LEVEL == 2 && !skip_empty && base + L2S_TILE <= end) {
             // a whole tile (all but the last of a bucket): no per-key bounds, every key is valid.
             // (Level 1, the receive side of the multi-GPU exchange, keeps the general path: with the
             // filler test inside, this variant made its 512-thread kernel slower, 1.65 -> 1.76 ms.)
