@@ -313,7 +313,10 @@ def run_ours(args):
                 "traffic": traffic, "traffic_source": NCU_SOURCE if traffic else None,
                 "peak_source": peak_src, "avg_launch_ms": avg_ms,
                 "algorithmic_bytes_per_launch": alg,
-                "kernel_share_of_step": kern[top]["ms"] / args.steps / ms_step}
+                "kernel_share_of_step": kern[top]["ms"] / args.steps / ms_step,
+                # the same algorithmic bytes over the WHOLE step (every kernel of the build), for scale
+                "step": {"achieved": alg / (ms_step * 1e-3) / 1e9, "frac": alg / (ms_step * 1e-3) / 1e9 / peak,
+                         "unit": "GB/s"}}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if args.workload == "c5" else "weak",

@@ -200,6 +200,10 @@ struct BuilderBase {
     // will offer, and "keep staging until flush_hint() or the stage is full"
     uint64_t call_keys_hint = 0;
     bool hold_flush = false;
+    // set by the host batcher for the duration of any ktg_add_reads call: input arrives at PCIe pace,
+    // so flushes hide behind the following copies and should be small; device-resident input is
+    // better served by as few sweeps of the table as memory allows
+    bool host_paced = false;
 
     virtual ~BuilderBase() {}
     virtual int init() = 0;
@@ -939,11 +943,32 @@ template <class K> struct Builder : BuilderBase {
     unsigned long long *stage_cursors() { return (unsigned long long *)b_stage_cur.p; }
     unsigned long long *stage_spill_cursor() { return stage_cursors() + stage_bins; }
 
+    // Most keys one stage may hold.  Two limits: bucket positions are 32-bit (2^31 keys plus the
+    // slack of the buckets stay below 4e9), and memory: level-1 buckets, their spill list (as large as
+    // the stage) and the page buckets make ~3.3 keys of memory per staged key; the stage may take 70 %
+    // of what is free now plus what its own buffers already hold (180 GB of HBM: C3 stages all of its
+    // 1.84 G keys, 46 GB, beside the 10.6 GB table and is swept once).
     uint64_t stage_max_keys() const {
         const char *e = getenv("KTG_STAGE_MAX_KEYS"); // tuning knob
         if (e) return std::max<uint64_t>(1u << 16, strtoull(e, nullptr, 10));
-        return sizeof(K) == 8 ? (1ull << 30) : (1ull << 29); // 8 GiB of staged keys
+        uint64_t lim = 1ull << 31;
+        // (cudaMemGetInfo takes ~1.5 ms on this driver: asked once per table allocation, not per stage)
+        if (stage_mem_for != (const void *)tab.slots) {
+            size_t free_b = 0, total_b = 0;
+            stage_mem_keys = ~0ull;
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+                const uint64_t held = b_keys.cap + b_spill.cap + b_pkeys.cap + b_pspill.cap;
+                const uint64_t budget = ((uint64_t)free_b + held) / 10 * 7;
+                stage_mem_keys = budget / (uint64_t)(3.3 * sizeof(K));
+            }
+            else (void)cudaGetLastError();
+            stage_mem_for = (const void *)tab.slots;
+        }
+        lim = std::min<uint64_t>(lim, stage_mem_keys);
+        return std::max<uint64_t>(lim, 1u << 20);
     }
+    mutable uint64_t stage_mem_keys = ~0ull;
+    mutable const void *stage_mem_for = nullptr; // the table allocation the memory budget was taken beside
 
     int stage_open(uint64_t batch_keys) {
         if (!sketch_complete) { // keys went in unsketched (direct path): restart from the exact count
@@ -954,10 +979,14 @@ template <class K> struct Builder : BuilderBase {
             KTG_CUDA(cudaMemsetAsync(b_hll.p, 0, HLL_M * 4, stream));
         }
         const uint32_t n_bins = tab.n_sub;
-        double factor = 0.75; // with host input: flushes small enough to hide under the following copies
+        // host input: flushes small enough to hide under the following copies (a sweep per 0.75 x capacity
+        // keys).  Device-resident input: every sweep reads and writes the whole table, so as many keys per
+        // sweep as fit (C3 in 5 batches: three sweeps of the 10.6 GB table were 17.9 of 41 ms, one is 9.6)
+        double factor = host_paced ? 0.75 : 3.0;
         if (const char *e = getenv("KTG_STAGE_FACTOR")) factor = atof(e); // tuning knob
         stage_target = std::min<uint64_t>((uint64_t)(factor * (double)tab.capacity()), stage_max_keys());
-        stage_room = batch_keys >= stage_target ? batch_keys : stage_target + batch_keys;
+        if (host_paced) stage_room = batch_keys >= stage_target ? batch_keys : stage_target + batch_keys;
+        else stage_room = std::max(batch_keys, stage_target);
         const bool eager = eager_pages();
         if (eager) { // level-1 buckets are drained after every chunk; the page stage takes the whole call
             stage_room = batch_keys;

@@ -107,6 +107,11 @@ int ktg_add_reads(ktg_builder *b, const uint8_t *bases, const uint64_t *offsets,
     if (n_reads == 0) return KTG_OK;
     if (!bases || !offsets) return fail(KTG_ERR_INVALID, "null argument");
     BuilderBase *impl = b->impl.get();
+    struct Paced { // input at PCIe pace for the duration of this call (the builder's flush cadence)
+        BuilderBase *p;
+        explicit Paced(BuilderBase *q) : p(q) { p->host_paced = true; }
+        ~Paced() { p->host_paced = false; }
+    } paced{impl};
     uint64_t r0c = 0, b0c = 0;
     if (accepted_reads || accepted_bytes) KTG_TRY(impl->read_counters(&r0c, &b0c));
     // bytes of bases per chunk: small enough that the H2D copy of chunk i+1 hides the kernels of
