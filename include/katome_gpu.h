@@ -290,6 +290,9 @@ typedef struct ktg_kernel_profile {
 } ktg_kernel_profile;
 int ktg_get_profile(ktg_builder *b, ktg_kernel_profile *out, uint32_t cap, uint32_t *n);
 int ktg_reset_profile(ktg_builder *b);
+/* Switch the per-launch timing on or off for the launches that follow (the events around every
+ * kernel cost ~20 us of GPU time per launch: 0.8 ms of an 11 ms host-fed C2 build). */
+int ktg_set_profile(ktg_builder *b, int enabled);
 
 typedef struct ktg_info {
     uint64_t capacity_slots, occupied_slots;

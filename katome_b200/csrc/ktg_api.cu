@@ -968,6 +968,14 @@ int ktg_reset_profile(ktg_builder *b) {
     return KTG_OK;
 }
 
+int ktg_set_profile(ktg_builder *b, int enabled) {
+    KTG_ENTER(b);
+    KTG_CUDA(cudaStreamSynchronize(b->impl->stream));
+    b->impl->prof.resolve(); // what was timed so far stays in the table
+    b->impl->prof.enabled = enabled != 0;
+    return KTG_OK;
+}
+
 int ktg_get_info(ktg_builder *b, ktg_info *out) {
     KTG_ENTER(b);
     if (!out) return fail(KTG_ERR_INVALID, "null argument");

@@ -426,6 +426,10 @@ class GpuGIR:
     def reset_profile(self):
         _check(self._L.ktg_reset_profile(self._h))
 
+    def set_profile(self, enabled: bool):
+        """Per-launch timing on / off for the launches that follow (ktg_set_profile)."""
+        _check(self._L.ktg_set_profile(self._h, int(bool(enabled))))
+
     def info(self) -> dict:
         i = L.KtgInfo()
         _check(self._L.ktg_get_info(self._h, C.byref(i)))

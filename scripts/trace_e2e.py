@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Host timeline (KTG_TRACE) of one end-to-end build from pinned host memory: trace_e2e.py [c2|c3|c3k63] [--no-trace]"""
+"""Host timeline (KTG_TRACE) of one end-to-end build from pinned host memory: trace_e2e.py [c2|c3|c3k63] [--no-trace] [--no-profile]"""
 import os
 import sys
 
@@ -19,8 +19,9 @@ synth_reads_device(d, wl.seed, wl.genome_len, L, wl.err_ppm, 0, n, stream=stream
 h = torch.empty(n * L, dtype=torch.uint8).pin_memory()
 h.copy_(d[: n * L])
 offs = torch.arange(0, (n + 1) * L, L, dtype=torch.int64).pin_memory()
-g = GpuGIR(wl.k, True, device=0, stream=stream, profile=True, edges_count=wl.expected_distinct_edges())
-for i in range(3):
+PROFILE = "--no-profile" not in sys.argv
+g = GpuGIR(wl.k, True, device=0, stream=stream, profile=PROFILE, edges_count=wl.expected_distinct_edges())
+for i in range(6 if "--no-trace" in sys.argv else 3):
     torch.cuda.synchronize()
     print(f"=== step {i}", file=sys.stderr, flush=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
