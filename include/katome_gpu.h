@@ -294,6 +294,15 @@ int ktg_reset_profile(ktg_builder *b);
  * kernel cost ~20 us of GPU time per launch: 0.8 ms of an 11 ms host-fed C2 build). */
 int ktg_set_profile(ktg_builder *b, int enabled);
 
+/* ---- test hook (no GPU needed): the plan ktg_add_reads follows for a batch with these offsets and
+ * this chunk size -- cuts[0..n_chunks] (chunk c = reads [cuts[c], cuts[c+1])), flush_after[c] != 0 where
+ * the stage is flushed on the way (after the given percentages of the bytes), *tail_first = index of the
+ * first of the short chunks a large call ends in, or -1.  cuts needs cap + 1 entries, flush_after cap.
+ * The per-read loop this batches is create_fastq, algorithms/builder.rs:152-160. */
+int ktg_plan_chunks(const uint64_t *offsets, uint64_t n_reads, uint64_t chunk_bytes, const uint32_t *flush_pcts,
+                    uint32_t n_pcts, uint64_t *cuts, uint8_t *flush_after, uint32_t cap, uint32_t *n_chunks,
+                    int64_t *tail_first);
+
 typedef struct ktg_info {
     uint64_t capacity_slots, occupied_slots;
     uint64_t table_bytes;

@@ -7,6 +7,7 @@
 
 #include "builder.cuh"
 #include "fastq_device.cuh"
+#include "host_plan.h"
 #include "host_reader.h"
 
 using namespace ktg;
@@ -124,60 +125,26 @@ int ktg_add_reads(ktg_builder *b, const uint8_t *bases, const uint64_t *offsets,
             KTG_CUDA(cudaEventCreateWithFlags(&b->st_ready[i], cudaEventDisableTiming));
         }
     }
-    // chunk boundaries: largest r1 with offsets[r1] - offsets[r] <= CHUNK (at least one read)
-    // Only what cannot start before the LAST copy has landed is exposed: the last chunk's kernels,
-    // the flush of whatever is staged then, the caller's first query.  So a large batch (>= 3 chunks)
-    //   * ends in four short chunks (the last 0.5-1.5 CHUNK), each with its own staging buffer, all
-    //     queued on the copy engine as soon as the last full chunk is;
-    //   * is flushed once on the way, after ~55 % of its bytes (the builder's own cadence, a flush per
-    //     0.75 x capacity keys, is held back: every extra sweep of the table is GPU time that queues
-    //     up behind the copies), which leaves the final flush ~40 % of the keys.
-    std::vector<uint64_t> cut{0};
+    // where the batch is cut and after which chunks the stage is flushed: host_plan.h
+    // (measured on C2, 8.3 ms of copies, before the eager page stage: the builder's own cadence, 4 flushes,
+    // 12.55 ms per build, one flush at 73 % 12.8, at 58 % 11.8, two (44 %, 73 %) 11.9)
+    std::vector<uint64_t> pcts{55};
+    if (const char *e = getenv("KTG_FLUSH_PCT")) { // tuning knob: comma separated percentages of the bytes
+        pcts.clear();
+        for (const char *q = e; *q;) {
+            char *end = nullptr;
+            const long v = strtol(q, &end, 10);
+            if (end == q) break;
+            if (v >= 1 && v <= 100) pcts.push_back((uint64_t)v);
+            q = *end == ',' ? end + 1 : end;
+        }
+    }
+    const ChunkPlan plan = plan_chunks(offsets, n_reads, CHUNK, pcts, !getenv("KTG_NO_TAPER"));
+    const std::vector<uint64_t> &cut = plan.cut;
+    const std::vector<char> &flush_here = plan.flush_here;
+    const size_t n_chunks = plan.n_chunks(), tail_first = plan.tail_first;
+    const bool large = plan.large;
     const uint64_t total = offsets[n_reads] - offsets[0];
-    const bool large = total >= 3 * CHUNK && !getenv("KTG_NO_TAPER");
-    size_t tail_first = (size_t)-1; // first of the short chunks
-    while (cut.back() < n_reads) {
-        const uint64_t r = cut.back();
-        uint64_t limit = CHUNK;
-        if (large) {
-            const uint64_t left = offsets[n_reads] - offsets[r];
-            if (left <= CHUNK + CHUNK / 2) {
-                if (tail_first == (size_t)-1) tail_first = cut.size() - 1;
-                limit = std::max<uint64_t>(left / (4 - std::min<size_t>(3, cut.size() - 1 - tail_first)), 1u << 20);
-            }
-        }
-        uint64_t lo = r + 1, hi = n_reads;
-        while (lo < hi) {
-            uint64_t mid = (lo + hi + 1) / 2;
-            if (offsets[mid] - offsets[r] <= limit) lo = mid;
-            else hi = mid - 1;
-        }
-        cut.push_back(lo);
-    }
-    const size_t n_chunks = cut.size() - 1;
-    // One flush on the way, after ~55 % of the bytes: it hides behind the remaining copies and leaves
-    // the final one ~40 % of the keys.  Measured on C2 (8.3 ms of copies): the builder's own cadence
-    // (4 flushes) 12.55 ms per build, one flush at 73 % 12.8, at 58 % 11.8, two (44 %, 73 %) 11.9.
-    std::vector<char> flush_here(n_chunks, 0);
-    if (large) {
-        const size_t last_full = tail_first != (size_t)-1 ? tail_first - 1 : n_chunks - 1;
-        std::vector<uint64_t> pcts{55};
-        if (const char *e = getenv("KTG_FLUSH_PCT")) { // tuning knob: comma separated percentages of the bytes
-            pcts.clear();
-            for (const char *q = e; *q;) {
-                char *end = nullptr;
-                const long v = strtol(q, &end, 10);
-                if (end == q) break;
-                if (v >= 1 && v <= 100) pcts.push_back((uint64_t)v);
-                q = *end == ',' ? end + 1 : end;
-            }
-        }
-        for (uint64_t pct : pcts) {
-            size_t c = 0;
-            while (c + 1 < n_chunks && offsets[cut[c + 1]] - offsets[0] < total / 100 * pct) ++c;
-            flush_here[std::min(c, last_full)] = 1;
-        }
-    }
     struct Hold { // the builder keeps its stage until flush_hint() / the end of this call
         BuilderBase *p;
         ~Hold() { p->hold_flush = false; p->call_keys_hint = 0; }
@@ -965,6 +932,22 @@ int ktg_reset_profile(ktg_builder *b) {
     KTG_ENTER(b);
     KTG_CUDA(cudaStreamSynchronize(b->impl->stream));
     b->impl->prof.reset();
+    return KTG_OK;
+}
+
+int ktg_plan_chunks(const uint64_t *offsets, uint64_t n_reads, uint64_t chunk_bytes, const uint32_t *flush_pcts,
+                    uint32_t n_pcts, uint64_t *cuts, uint8_t *flush_after, uint32_t cap, uint32_t *n_chunks,
+                    int64_t *tail_first) {
+    if (!offsets || !n_chunks || chunk_bytes == 0 || n_reads == 0) return fail(KTG_ERR_INVALID, "bad plan request");
+    std::vector<uint64_t> pcts(flush_pcts, flush_pcts + (flush_pcts ? n_pcts : 0));
+    const ChunkPlan p = plan_chunks(offsets, n_reads, chunk_bytes, pcts, true);
+    *n_chunks = (uint32_t)p.n_chunks();
+    if (tail_first) *tail_first = p.tail_first == (size_t)-1 ? -1 : (int64_t)p.tail_first;
+    if (p.n_chunks() > cap) return fail(KTG_ERR_INVALID, "plan has %zu chunks, room for %u", p.n_chunks(), cap);
+    for (size_t c = 0; c <= p.n_chunks(); ++c)
+        if (cuts) cuts[c] = p.cut[c];
+    for (size_t c = 0; c < p.n_chunks(); ++c)
+        if (flush_after) flush_after[c] = (uint8_t)p.flush_here[c];
     return KTG_OK;
 }
 
