@@ -85,7 +85,7 @@ def run_reference(args):
     n = args.cpu_sample_reads
     vals = []
     for i in range(args.warmup + args.steps):
-        v, dt = cpu_sample(wl, n)
+        v, dt = cpu_sample(wl, n, args.rc)
         if i >= args.warmup:
             vals.append((v, dt))
     v = sum(x for x, _ in vals) / len(vals)
@@ -95,12 +95,12 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic",
-        "config": {"workload": wl.name, "k": wl.k, "reverse_complement": True,
+        "config": {"workload": wl.name, "k": wl.k, "reverse_complement": args.rc,
                    "note": "the Rust reference cannot be built here (no rustc/cargo); this is the C port"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "reads_per_sec": v / wl.windows_per_read,
-        "cpu_optimistic": cpu_optimistic(wl, args.cpu_opt_reads),
+        "cpu_optimistic": cpu_optimistic(wl, args.cpu_opt_reads, args.rc),
     }
     _OUT.write(json.dumps(line) + "\n")
     _OUT.flush()
@@ -186,7 +186,7 @@ def run_ours(args):
 
     exchange = None
     if world == 1:
-        g = GpuGIR(k, True, device=local, stream=stream, profile=True, edges_count=hint,
+        g = GpuGIR(k, args.rc, device=local, stream=stream, profile=True, edges_count=hint,
                    sub_table_log2_bytes=args.sub_log2)
         def step():
             g.reset()
@@ -195,7 +195,7 @@ def run_ours(args):
         digest = g.digest
         builder = g
     else:
-        sg = ShardedGIR(k, True, edges_count=hint, profile=True, sub_table_log2_bytes=args.sub_log2)
+        sg = ShardedGIR(k, args.rc, edges_count=hint, profile=True, sub_table_log2_bytes=args.sub_log2)
         exchange = sg.exchange
         def step():
             sg.reset()
@@ -231,7 +231,7 @@ def run_ours(args):
     launches = info["kernel_launches"] - launches0 - 1  # info() itself launches one scan
     dig = digest()
     # weight conservation: every window adds 1 to each strand (2 to a palindrome)
-    assert dig[2] == 2 * windows_total, (dig, windows_total)
+    assert dig[2] == (2 if args.rc else 1) * windows_total, (dig, windows_total)
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -335,13 +335,13 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "u64" if k <= 32 else "u128",
         "data": "synthetic",
         "config": {"workload": wl.name, "genome_len": wl.genome_len, "read_len": L, "coverage": wl.coverage,
-                   "err_ppm": wl.err_ppm, "k": k, "reverse_complement": True, "reads": n_total,
+                   "err_ppm": wl.err_ppm, "k": k, "reverse_complement": args.rc, "reads": n_total,
                    "windows": windows_total, "parallelism": f"hash-shard x{world}", "exchange": exchange,
                    "batches_per_step": n_batches,
                    "l2": "inputs (460 MB of reads per GPU) and table exceed the 126 MB L2; no explicit flush",
                    "capacity_hint": bool(args.hint)},
         "reads_per_sec": n_total / (ms_step * 1e-3),
-        "edge_inserts_per_sec_reference_equivalent": 2 * value,
+        "edge_inserts_per_sec_reference_equivalent": (2 if args.rc else 1) * value,
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
         "kernels": {n: {"launches": p["launches"], "ms_per_step": p["ms"] / args.steps} for n, p in kern.items()},
         "table": {"bytes": info["table_bytes"], "sub_tables": info["n_sub_tables"], "slot_bytes": info["slot_bytes"],
@@ -349,12 +349,12 @@ def run_ours(args):
         "digest": {"D": dig[0], "edges": dig[1], "sum_w": dig[2], "max_w": dig[3]},
     }
     if world == 1 and not args.no_cpu:
-        v, dt = cpu_sample(wl, args.cpu_sample_reads)
+        v, dt = cpu_sample(wl, args.cpu_sample_reads, args.rc)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                                 "sample": f"first {args.cpu_sample_reads} reads of the workload "
                                           f"({args.cpu_sample_reads * wl.windows_per_read} windows, {dt:.1f} s), "
                                           "oracle port of hm_gir.rs:39-153, 1 thread"}
-        line["cpu_optimistic"] = cpu_optimistic(wl, args.cpu_opt_reads)
+        line["cpu_optimistic"] = cpu_optimistic(wl, args.cpu_opt_reads, args.rc)
     if not args.no_probe and world == 1:
         # the random-access roofline of SURVEY 8(d): uniformly random "load key + atomicAdd weight" over an
         # array as large as this build's table (and over one that fits in L2), measured on this GPU now
@@ -390,6 +390,8 @@ def main():
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--cpu-sample-reads", type=int, default=200_000)
     ap.add_argument("--no-hint", dest="hint", action="store_false")
+    ap.add_argument("--no-rc", dest="rc", action="store_false",
+                    help="reverse_complement=false (SURVEY 8d asks for one such run of C2); the default is the settings default, true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-opt-reads", type=int, default=1_000_000,
