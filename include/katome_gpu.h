@@ -303,6 +303,15 @@ int ktg_plan_chunks(const uint64_t *offsets, uint64_t n_reads, uint64_t chunk_by
                     uint32_t n_pcts, uint64_t *cuts, uint8_t *flush_after, uint32_t cap, uint32_t *n_chunks,
                     int64_t *tail_first);
 
+/* ---- test hook (no GPU needed): the host FASTQ / FASTA reader behind ktg_create_from_files alone
+ * (csrc/host_reader.h: check_files, builder.rs:57-77, and the record semantics of rust-bio 0.10 that
+ * create_fastq / create_fasta rely on, builder.rs:118-165): records read, bases in their sequences
+ * (before the ACGT filter, which runs on the device) and an FNV-1a checksum over every sequence
+ * followed by '\n'.  batch_bytes: bases per internal batch (0 = 64 MiB).  KTG_ERR_IO / KTG_ERR_BAD_RECORD
+ * as ktg_create_from_files returns them. */
+int ktg_host_parse_file(const char *path, int file_type, uint64_t batch_bytes, uint64_t *n_records,
+                        uint64_t *total_bases, uint64_t *checksum);
+
 typedef struct ktg_info {
     uint64_t capacity_slots, occupied_slots;
     uint64_t table_bytes;

@@ -951,6 +951,31 @@ int ktg_plan_chunks(const uint64_t *offsets, uint64_t n_reads, uint64_t chunk_by
     return KTG_OK;
 }
 
+int ktg_host_parse_file(const char *path, int file_type, uint64_t batch_bytes, uint64_t *n_records,
+                        uint64_t *total_bases, uint64_t *checksum) {
+    if (!path || (file_type != KTG_FASTQ && file_type != KTG_FASTA)) return fail(KTG_ERR_INVALID, "bad argument");
+    ReadFile f;
+    std::string why;
+    if (!f.open(path, file_type == KTG_FASTA, &why)) return fail(KTG_ERR_IO, "%s", why.c_str());
+    ReadBatch batch;
+    uint64_t n = 0, bases = 0, h = 0xcbf29ce484222325ull; // FNV-1a over every sequence followed by '\n'
+    for (;;) {
+        const int st = f.next_batch(&batch, batch_bytes ? batch_bytes : (64u << 20), &why);
+        if (st < 0) return fail(KTG_ERR_BAD_RECORD, "%s", why.c_str());
+        for (uint64_t r = 0; r < batch.n_reads(); ++r) {
+            for (uint64_t i = batch.offsets[r]; i < batch.offsets[r + 1]; ++i) h = (h ^ batch.bases[i]) * 0x100000001b3ull;
+            h = (h ^ (uint64_t)'\n') * 0x100000001b3ull;
+        }
+        n += batch.n_reads();
+        bases += batch.size;
+        if (st == 0) break;
+    }
+    if (n_records) *n_records = n;
+    if (total_bases) *total_bases = bases;
+    if (checksum) *checksum = h;
+    return KTG_OK;
+}
+
 int ktg_set_profile(ktg_builder *b, int enabled) {
     KTG_ENTER(b);
     KTG_CUDA(cudaStreamSynchronize(b->impl->stream));
