@@ -105,6 +105,21 @@ uint64_t ko_dump(const ko_gir *g, char *buf, uint64_t cap);
 int ko_mt_build_digest(int k, const uint8_t *bases, const uint64_t *offsets, uint64_t n_reads,
                        int reverse_complement, int n_threads, uint64_t out[4],
                        uint64_t *accepted_reads, uint64_t *accepted_bytes);
+/* The same counter as an object, so that the BASELINE-size GPU builds can be checked in full: reads
+ * are taken batch by batch (memory follows the distinct keys), and the filter
+ * (edges.rs:51-58, pruner.rs:109-118) and standardize_edges (standardizer.rs:42-70,123-127) are
+ * applied to its tables; ko_mt_digest is ko_digest's four numbers at any point. */
+typedef struct ko_mt ko_mt;
+ko_mt *ko_mt_new(int k, int reverse_complement, int n_threads);
+void ko_mt_free(ko_mt *j);
+int ko_mt_add_reads(ko_mt *j, const uint8_t *bases, const uint64_t *offsets, uint64_t n_reads);
+void ko_mt_counters(const ko_mt *j, uint64_t *accepted_reads, uint64_t *accepted_bytes);
+int ko_mt_digest(ko_mt *j, uint64_t out[4]);
+int ko_mt_remove_weak_edges(ko_mt *j, uint32_t threshold);
+int ko_mt_standardize_edges(ko_mt *j, uint64_t genome_len, uint64_t k, uint32_t threshold);
+/* ko_synth_reads over n_threads host threads (same bytes) */
+void ko_synth_reads_mt(uint64_t seed_g, uint64_t G, uint32_t L, uint32_t err_ppm, uint64_t r0, uint64_t r1,
+                       uint8_t *out, int n_threads);
 
 /* ---- codec (compress.rs) ---- */
 uint8_t ko_encode_fasta_symbol(uint8_t symbol, uint8_t carrier);                /* :347-378 */

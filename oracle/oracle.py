@@ -77,6 +77,15 @@ def lib():
         L.ko_synth_reads.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p]
         L.ko_synth_genome.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
         L.ko_mt_build_digest.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, u64p, u64p, u64p]
+        L.ko_mt_new.restype = C.c_void_p
+        L.ko_mt_new.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.ko_mt_free.argtypes = [C.c_void_p]
+        L.ko_mt_add_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.ko_mt_counters.argtypes = [C.c_void_p, u64p, u64p]
+        L.ko_mt_digest.argtypes = [C.c_void_p, u64p]
+        L.ko_mt_remove_weak_edges.argtypes = [C.c_void_p, C.c_uint32]
+        L.ko_mt_standardize_edges.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32]
+        L.ko_synth_reads_mt.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int]
         _lib = L
     return _lib
 
@@ -265,6 +274,17 @@ def synth_reads(seed_g: int, G: int, L: int, err_ppm: int, r0: int, r1: int) -> 
     return out
 
 
+def host_threads() -> int:
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def synth_reads_mt(seed_g: int, G: int, L: int, err_ppm: int, r0: int, r1: int, n_threads: int = 0) -> np.ndarray:
+    """synth_reads over every host thread (counter based generator: the same bytes)"""
+    out = np.empty((r1 - r0) * L, np.uint8)
+    lib().ko_synth_reads_mt(seed_g, G, L, err_ppm, r0, r1, out.ctypes.data, n_threads or host_threads())
+    return out
+
+
 def synth_genome(seed_g: int, pos0: int, n: int) -> np.ndarray:
     out = np.empty(n, np.uint8)
     lib().ko_synth_genome(seed_g, pos0, n, out.ctypes.data)
@@ -281,3 +301,45 @@ def mt_build_digest(k: int, bases: np.ndarray, offsets: np.ndarray, reverse_comp
     _check(lib().ko_mt_build_digest(k, bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1,
                                     int(reverse_complement), int(n_threads), out, C.byref(nr), C.byref(nb)))
     return tuple(int(x) for x in out), nr.value, nb.value
+
+
+class MtCounter:
+    """katome_oracle_mt.c as an object: the multi-threaded CPU counter that finishes the BASELINE
+    configurations in seconds and is digest-equal to the faithful OracleGIR (tests/test_oracle_golden.py).
+    The checker of the full-size GPU builds: reads batch by batch, remove_weak_edges, standardize_edges,
+    digest = OracleGIR.digest()'s four numbers."""
+
+    def __init__(self, k: int, reverse_complement: bool, n_threads: int = 0):
+        self._h = lib().ko_mt_new(int(k), int(bool(reverse_complement)), int(n_threads or host_threads()))
+        if not self._h:
+            raise OracleError(KO_ERR_BAD_K, "bad k")
+        self.k = int(k)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            lib().ko_mt_free(h)
+
+    def add_reads(self, bases: np.ndarray, offsets: np.ndarray):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        _check(lib().ko_mt_add_reads(self._h, bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1))
+
+    def add_reads_ptr(self, bases_ptr: int, offsets_ptr: int, n_reads: int):
+        _check(lib().ko_mt_add_reads(self._h, bases_ptr, offsets_ptr, n_reads))
+
+    def counters(self):
+        nr, nb = C.c_uint64(0), C.c_uint64(0)
+        lib().ko_mt_counters(self._h, C.byref(nr), C.byref(nb))
+        return nr.value, nb.value
+
+    def digest(self):
+        out = (C.c_uint64 * 4)()
+        _check(lib().ko_mt_digest(self._h, out))
+        return tuple(int(x) for x in out)
+
+    def remove_weak_edges(self, threshold: int):
+        _check(lib().ko_mt_remove_weak_edges(self._h, int(threshold)))
+
+    def standardize_edges(self, genome_len: int, k: int, threshold: int):
+        _check(lib().ko_mt_standardize_edges(self._h, int(genome_len), int(k), int(threshold)))

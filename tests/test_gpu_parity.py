@@ -724,6 +724,62 @@ def test_baseline_config2_full_size(K):
     g.close(), g2.close()
 
 
+def _gpu_and_oracle_stages(K, wl, n_reads, rc=True, **kw):
+    """The three stages of tests/golden/make_baseline_digests.py on the GPU (resident input, ONE call) and on
+    the multi-threaded CPU oracle (oracle/katome_oracle_mt.c, digest-equal to the faithful port:
+    tests/test_oracle_golden.py) fed with the very bytes the device generator wrote."""
+    import sys
+    sys.path.insert(0, H.ROOT)
+    from oracle import oracle as O
+    L = wl.read_len
+    d = torch.empty(n_reads * L + 64, dtype=torch.uint8, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    K.synth_reads_device(d, wl.seed, wl.genome_len, L, wl.err_ppm, 0, n_reads, stream=s)
+    offs = torch.arange(0, (n_reads + 1) * L, L, dtype=torch.int64, device="cuda")
+    g = K.GpuGIR(wl.k, rc, stream=s, **kw)
+    assert g.add_reads_device(d, offs, n_reads, n_reads * L, want_counts=True) == (n_reads, n_reads * L)
+    m = O.MtCounter(wl.k, rc)
+    step = (256 << 20) // L
+    for r0 in range(0, n_reads, step):
+        r1 = min(n_reads, r0 + step)
+        m.add_reads(d[r0 * L: r1 * L].cpu().numpy(), np.arange(r1 - r0 + 1, dtype=np.uint64) * L)
+    assert m.counters() == (n_reads, n_reads * L)
+    gpu, cpu = {}, {}
+    gpu["built"], cpu["built"] = list(g.digest()), list(m.digest())
+    g.remove_weak_edges(2), m.remove_weak_edges(2)
+    gpu["filtered"], cpu["filtered"] = list(g.digest()), list(m.digest())
+    g.standardize_edges(64 * wl.genome_len, wl.k, 3), m.standardize_edges(64 * wl.genome_len, wl.k, 3)
+    gpu["standardized"], cpu["standardized"] = list(g.digest()), list(m.digest())
+    info = g.info()
+    g.close()
+    return gpu, cpu, info
+
+
+def test_baseline_config2_against_the_oracle_at_full_size(K):
+    """ALL of BASELINE config 2 (322 M windows, k=31, reverse_complement=true -- the bench workload): the GPU
+    digest equals the CPU oracle's after the build, after remove_weak_edges(2) and after
+    standardize_edges(64 G, k, 3), and both equal the committed golden digests."""
+    import json, os
+    from katome_b200.workloads import C2 as wl
+    gpu, cpu, info = _gpu_and_oracle_stages(K, wl, wl.n_reads)
+    assert gpu == cpu
+    gold = json.load(open(os.path.join(H.ROOT, "tests", "golden", "baseline_digests.json")))["workloads"]["c2"]
+    for stage in ("built", "filtered", "standardized"):
+        assert gpu[stage] == gold[stage], stage
+    assert info["page_updates"] >= 1  # the two-level partition + page sweep is what ran
+
+
+@pytest.mark.parametrize("name,n_reads", [("c3k63", 2_000_000), ("c3", 1_500_000)])
+def test_baseline_config3_slice_against_the_oracle(K, name, n_reads):
+    """The first reads of BASELINE config 3 (46 Mbp, 150 bp; k=63 = u128 keys, and k=31): 176 M / 180 M windows
+    through the paged path, stage by stage against the CPU oracle."""
+    from katome_b200.workloads import BY_NAME
+    wl = BY_NAME[name]
+    gpu, cpu, info = _gpu_and_oracle_stages(K, wl, n_reads)
+    assert gpu == cpu
+    assert gpu["built"][2] == 2 * n_reads * wl.windows_per_read and info["page_updates"] >= 1
+
+
 def _both_fastq_parsers(K, path, k, rc, chunk_kb=None):
     """Build::create through the device-side FASTQ parser and through the host reader (its twin)."""
     import os

@@ -227,3 +227,47 @@ def test_optimistic_cpu_counter_equals_the_faithful_oracle(k, rc):
     with pytest.raises(O.OracleError) as e:
         O.mt_build_digest(k, bases, offsets, rc, 3)
     assert e.value.code == O.KO_ERR_SHORT_READ
+
+
+@pytest.mark.parametrize("k,rc", [(4, True), (6, True), (31, True), (31, False), (32, False), (33, True), (40, False),
+                                  (63, True), (64, True), (64, False)])
+def test_mt_counter_object_follows_the_faithful_oracle_through_filter_and_standardize(k, rc):
+    """MtCounter (the checker of the BASELINE-size GPU builds) == OracleGIR at every stage: batches added one by
+    one (tables grow with the distinct keys), remove_weak_edges (edges.rs:51-58), more reads after the filter,
+    standardize_edges (standardizer.rs:42-70), and the degenerate ratio."""
+    rng = np.random.default_rng(11 * k + rc)
+    genome = "".join(rng.choice(list("ACGT"), 3000))
+    batches = [H.random_reads(rng, 400, k, k + 60, genome=genome, n_rate=0.05) for _ in range(3)]
+    batches[1] += ["T" * (k + 9), "AT" * k, "ACGT" * k, "A" * k]
+    g = O.OracleGIR(k)
+    for threads in (1, 3, 8):
+        g = O.OracleGIR(k)
+        m = O.MtCounter(k, rc, threads)
+        for seqs in batches[:2]:
+            bases, offsets = H.batch_of(seqs)
+            g.add_reads(bases, offsets, rc)
+            m.add_reads(bases, offsets)
+            assert m.digest() == g.digest()
+        assert m.counters() == (g.accepted_reads, g.accepted_bytes)
+        g.remove_weak_edges(3)
+        m.remove_weak_edges(3)
+        assert m.digest() == g.digest() and g.digest()[1] > 0
+        bases, offsets = H.batch_of(batches[2])  # a removed edge that comes back starts from weight 0 again
+        g.add_reads(bases, offsets, rc)
+        m.add_reads(bases, offsets)
+        assert m.digest() == g.digest()
+        g.standardize_edges(2 * len(genome), k, 2)
+        m.standardize_edges(2 * len(genome), k, 2)
+        assert m.digest() == g.digest() and g.digest()[1] > 0
+        g.remove_weak_edges(1 << 30)
+        m.remove_weak_edges(1 << 30)
+        assert m.digest() == g.digest() == (0, 0, 0, 0)
+        with pytest.raises(O.OracleError) as e:
+            m.standardize_edges(1000, k, 1)
+        assert e.value.code == O.KO_ERR_DEGENERATE
+
+
+def test_synth_reads_mt_writes_the_same_bytes():
+    a = O.synth_reads(0x6B61746F6D65 + 1, 50_000, 100, 5000, 17, 1017)
+    for threads in (1, 3, 7):
+        assert np.array_equal(O.synth_reads_mt(0x6B61746F6D65 + 1, 50_000, 100, 5000, 17, 1017, threads), a)
