@@ -239,7 +239,10 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = None
     if world > 1:
+        from katome_b200.dist import bind_to_gpu_numa
+        numa = bind_to_gpu_numa(local)  # before any pinned allocation
         dist.init_process_group("nccl", device_id=dev)
     wl = workload_for(args.workload, world, args.weak)
     L, k = wl.read_len, wl.k
@@ -270,7 +273,7 @@ def run_ours(args):
     exchange = None
     if world == 1:
         g = GpuGIR(k, args.rc, device=local, stream=stream, profile=True, edges_count=hint,
-                   sub_table_log2_bytes=args.sub_log2)
+                   sub_table_log2_bytes=args.sub_log2, options=args.options)
         sg = None
         def step():
             g.reset()
@@ -278,7 +281,8 @@ def run_ours(args):
             g.finalize()
         top, builder = g, g
     else:
-        sg = ShardedGIR(k, args.rc, edges_count=hint, profile=True, sub_table_log2_bytes=args.sub_log2)
+        sg = ShardedGIR(k, args.rc, edges_count=hint, profile=True, sub_table_log2_bytes=args.sub_log2,
+                        exchange=args.exchange, options=args.options)
         exchange = sg.exchange
         def step():
             sg.reset()
@@ -445,7 +449,7 @@ def run_ours(args):
                    "batches_per_step": n_batches,
                    "l2": f"inputs ({n_local * L / 1e6:.0f} MB of reads per GPU) and table exceed the 126 MB L2; "
                          "no explicit flush",
-                   "capacity_hint": bool(args.hint)},
+                   "capacity_hint": bool(args.hint), "options": args.options or None, "numa_node_rank0": numa},
         "reads_per_sec": n_total / (ms_step * 1e-3),
         "edge_inserts_per_sec_reference_equivalent": (2 if args.rc else 1) * value,
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
@@ -659,8 +663,13 @@ def main():
                     help="sample of the multi-threaded optimistic CPU counter")
     ap.add_argument("--no-probe", action="store_true", help="skip the random-access roofline probe")
     ap.add_argument("--sub-log2", type=int, default=0)
+    ap.add_argument("--exchange", default=None, choices=["fused", "skm", "keys", "nccl"],
+                    help="N > 1: which exchange (default: the measured winner for this world size and k)")
     ap.add_argument("--batches", type=int, default=0, help="add_reads calls per step (0: one)")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
+                    help="ktg_set_option on the builder (measurements; include/katome_gpu.h lists the names)")
     args = ap.parse_args()
+    args.options = {kv.split("=")[0]: int(kv.split("=")[1]) for kv in args.opt}
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define KTG_ABI_VERSION 1
+#define KTG_ABI_VERSION 2
 
 enum {
     KTG_OK = 0,
@@ -63,6 +63,16 @@ typedef struct ktg_config {
                                     cudaStreamLegacy for the legacy default stream) */
     uint32_t sub_table_log2_bytes; /* 0 = default (L2-resident partition size) */
     uint32_t flags;              /* KTG_FLAG_* */
+    /* ONE handle over several GPUs of this process: n_devices > 1 builds a table that is
+     * hash-sharded over device_ids[0..n_devices) -- the reads of every ktg_add_reads call are split over
+     * the devices, each extracts its share and writes the k-mers (or super-k-mer records) straight into
+     * the owning device's HBM over NVLink peer memory, and every query / export below answers for the
+     * whole graph (the export gathers the shards on device_ids[0] and numbers nodes globally).  The
+     * caller changes nothing else: Build::create (builder.rs:42-54) stays one call.  world_size / rank /
+     * device / stream are ignored then.  A device may be listed more than once (shards then share a
+     * GPU; the tests run 2-4 shards on the one GPU of a test box this way).  n_devices <= 1: one GPU. */
+    uint32_t n_devices;
+    const int32_t *device_ids;
 } ktg_config;
 
 #define KTG_FLAG_PROFILE 1u      /* time every kernel launch with CUDA events */
@@ -85,7 +95,7 @@ int ktg_device_count(void);
 int ktg_add_reads(ktg_builder *b, const uint8_t *bases, const uint64_t *offsets, uint64_t n_reads,
                   uint64_t *accepted_reads, uint64_t *accepted_bytes);
 
-/* Same, inputs already resident in device memory (d_offsets: n_reads+1 u64).
+/* Same, inputs already resident in device memory (d_offsets: n_reads+1 u64); single-device handles only.
  * total_bases == offsets[n_reads] - offsets[0].  The packer reads whole aligned 32-byte
  * chunks: d_bases must be readable from the 32-byte boundary at or below its first base to
  * the one at or above its end (true for any sub-range of a cudaMalloc allocation). */
@@ -150,6 +160,15 @@ int ktg_export_edges(ktg_builder *b, uint64_t *key_hi, uint64_t *key_lo, uint32_
 int ktg_export_graph(ktg_builder *b, uint64_t *node_hi, uint64_t *node_lo, uint64_t n_nodes, uint64_t *src,
                      uint64_t *dst, uint32_t *weight, uint8_t *edge_bytes, uint64_t n_edges);
 uint32_t ktg_edge_record_bytes(const ktg_builder *b);
+
+/* The seeds of remove_dead_paths (pruner.rs:165-195, the `Externals` iterator): in ascending
+ * node index -- the numbering of ktg_export_graph -- every node without an incoming edge as
+ * VertexType::Input (kinds[i] = KTG_EXTERNAL_INPUT), else every node without an outgoing edge as
+ * VertexType::Output (KTG_EXTERNAL_OUTPUT).  The walk along the dead paths is pointer chasing and stays on
+ * the host; this is its degree-0 seeding.  Returns the count in *n, copies at most cap entries
+ * (node_ids / kinds may be NULL for a size query). */
+enum { KTG_EXTERNAL_INPUT = 0, KTG_EXTERNAL_OUTPUT = 1 };
+int ktg_export_externals(ktg_builder *b, uint64_t *node_ids, uint8_t *kinds, uint64_t cap, uint64_t *n);
 
 /* ---- BFCounter input (builder.rs:79-115, pt_graph.rs:201-213,318-329).  The
  * reference implements it for PtGraph only (add_read_bfc is unreachable!() on its GIR types,
@@ -311,6 +330,13 @@ int ktg_plan_chunks(const uint64_t *offsets, uint64_t n_reads, uint64_t chunk_by
  * as ktg_create_from_files returns them. */
 int ktg_host_parse_file(const char *path, int file_type, uint64_t batch_bytes, uint64_t *n_records,
                         uint64_t *total_bases, uint64_t *checksum);
+
+/* ---- options (tests and measurements; the defaults are the measured winners and nothing in the
+ * library reads the environment).  Names: page_threads, page_nbuf, page_log2, l2s_variant, l1_ctas,
+ * p2p_ctas, chunk_mb, stage_bufs, flush_pct, flush_pct2, taper, eager_pages, stage_factor_milli,
+ * stage_max_keys, host_parse (ktg_create_from_files: records cut by the host reader instead of the
+ * device), fastq_chunk_kb, mg_pad, trace (host timeline on stderr).  Unknown names: KTG_ERR_INVALID. */
+int ktg_set_option(ktg_builder *b, const char *name, int64_t value);
 
 typedef struct ktg_info {
     uint64_t capacity_slots, occupied_slots;

@@ -52,6 +52,16 @@ struct Graph {
 
 class GpuGIR {
   public:
+    // The GPUs every collection created afterwards is built on -- katome's settings are process
+    // globals too (config.rs, prelude.rs:21-25).  Empty or one entry: one GPU.  Several: ONE table
+    // hash-sharded over them (ktg_config.n_devices); create / add_read_fastaq / stats / to_graph are
+    // called exactly as before, which is the point: Build::create (builder.rs:42-54) stays one call.
+    static std::vector<int32_t> &devices() {
+        static std::vector<int32_t> d;
+        return d;
+    }
+    static void set_devices(const std::vector<int32_t> &ids) { devices() = ids; }
+
     // set_global_k_sizes (prelude.rs:34-43) + Init::init: k is per collection, not a process global
     static GpuGIR init(uint32_t k, bool reverse_complement, uint64_t edges_count = 0, int device = -1) {
         return GpuGIR(k, reverse_complement, edges_count, device);
@@ -170,6 +180,17 @@ class GpuGIR {
                                g.edge_bytes.data(), ne));
         return g;
     }
+    // the edges sorted by k-mer with their weights (the dump that must be byte-identical
+    // on 1, 2, 4 and 8 GPUs); key_hi is all zero for k <= 32
+    void sorted_edges(std::vector<uint64_t> &key_hi, std::vector<uint64_t> &key_lo, std::vector<uint32_t> &weight) {
+        flush();
+        uint64_t n = 0;
+        check(ktg_export_edges(h_, nullptr, nullptr, nullptr, 0, 1, &n));
+        key_hi.assign(n, 0);
+        key_lo.assign(n, 0);
+        weight.assign(n, 0);
+        if (n) check(ktg_export_edges(h_, key_hi.data(), key_lo.data(), weight.data(), n, 1, &n));
+    }
     ktg_builder *handle() { return h_; }
 
   private:
@@ -182,6 +203,11 @@ class GpuGIR {
         cfg.capacity_hint_edges = edges_count;
         cfg.world_size = 1;
         cfg.rank = 0;
+        const std::vector<int32_t> ids = devices(); // a copy: the handle reads it during ktg_create only
+        if (!ids.empty()) {
+            cfg.n_devices = (uint32_t)ids.size();
+            cfg.device_ids = ids.data();
+        }
         const int rc = ktg_create(&cfg, &h_);
         if (rc != KTG_OK) {
             h_ = nullptr;

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "lib", "libkatome_gpu.so")
 CSRC = os.path.join(_HERE, "csrc")
 
-KTG_ABI_VERSION = 1
+KTG_ABI_VERSION = 2
 (KTG_OK, KTG_ERR_SHORT_READ, KTG_ERR_BAD_K, KTG_ERR_IO, KTG_ERR_BAD_RECORD, KTG_ERR_DEGENERATE,
  KTG_ERR_TABLE_FULL, KTG_ERR_CUDA, KTG_ERR_INVALID, KTG_ERR_NO_DEVICE) = range(10)
 KTG_FASTQ, KTG_FASTA = 0, 1
@@ -28,7 +28,7 @@ SYMBOLS = (
     "ktg_standardize_edges", "ktg_export_edges", "ktg_digest", "ktg_key_words", "ktg_owner_of",
     "ktg_partition_reads_device", "ktg_insert_keys_device", "ktg_host_alloc", "ktg_host_free",
     "ktg_synth_reads_device", "ktg_random_access_probe", "ktg_get_profile", "ktg_reset_profile", "ktg_set_profile", "ktg_plan_chunks", "ktg_host_parse_file",
-    "ktg_get_info", "ktg_partition_keys_device", "ktg_mg_plan", "ktg_mg_prepare",
+    "ktg_get_info", "ktg_set_option", "ktg_export_externals", "ktg_partition_keys_device", "ktg_mg_plan", "ktg_mg_prepare",
     "ktg_mg_scatter_reads_device", "ktg_mg_insert_buckets", "ktg_mg_sketch", "ktg_mg_merge_sketch", "ktg_mg_spill", "ktg_mg_insert_spill", "ktg_ipc_get_handle", "ktg_ipc_open", "ktg_ipc_close",
     "ktg_mg_skm_supported", "ktg_mg_skm_plan", "ktg_mg_skm_prepare", "ktg_mg_skm_scatter_reads_device",
     "ktg_mg_skm_insert_buckets", "ktg_mg_skm_spill", "ktg_mg_skm_partition_records", "ktg_mg_skm_insert_records",
@@ -43,7 +43,7 @@ class KtgConfig(C.Structure):
         ("abi_version", C.c_uint32), ("k", C.c_uint32), ("reverse_complement", C.c_uint32),
         ("device", C.c_int32), ("capacity_hint_edges", C.c_uint64), ("world_size", C.c_uint32),
         ("rank", C.c_uint32), ("stream", C.c_void_p), ("sub_table_log2_bytes", C.c_uint32),
-        ("flags", C.c_uint32),
+        ("flags", C.c_uint32), ("n_devices", C.c_uint32), ("device_ids", C.POINTER(C.c_int32)),
     ]
 
 
@@ -113,6 +113,7 @@ def lib():
     L.ktg_export_edges.argtypes = [vp, vp, vp, vp, C.c_uint64, C.c_int, u64p]
     L.ktg_digest.argtypes = [vp, u64p]
     L.ktg_export_graph.argtypes = [vp, vp, vp, C.c_uint64, vp, vp, vp, vp, C.c_uint64]
+    L.ktg_export_externals.argtypes = [vp, vp, vp, C.c_uint64, u64p]
     L.ktg_edge_record_bytes.argtypes = [vp]
     L.ktg_edge_record_bytes.restype = C.c_uint32
     L.ktg_key_words.argtypes = [vp]
@@ -132,6 +133,7 @@ def lib():
     L.ktg_host_parse_file.argtypes = [C.c_char_p, C.c_int, C.c_uint64, u64p, u64p, u64p]
     L.ktg_plan_chunks.argtypes = [vp, C.c_uint64, C.c_uint64, vp, C.c_uint32, vp, vp, C.c_uint32, vp, vp]
     L.ktg_get_info.argtypes = [vp, C.POINTER(KtgInfo)]
+    L.ktg_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     intp = C.POINTER(C.c_int)
     L.ktg_partition_keys_device.argtypes = [vp, vp, C.c_uint64, C.POINTER(vp), u64p]
     L.ktg_mg_plan.argtypes = [vp, C.c_uint64, intp]

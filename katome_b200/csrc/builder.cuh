@@ -49,9 +49,12 @@ inline int fail(int code, const char *fmt, ...) {
 namespace ktg {
 
 // host-side timeline for tuning (KTG_TRACE=1): label + microseconds since the first event
+inline bool &trace_enabled() {
+    static bool on = false;
+    return on;
+}
 inline void trace(const char *label, uint64_t v = 0) {
-    static const bool on = getenv("KTG_TRACE") != nullptr;
-    if (!on) return;
+    if (!trace_enabled()) return;
     static timespec t0{};
     timespec t;
     clock_gettime(CLOCK_MONOTONIC, &t);
@@ -179,8 +182,32 @@ struct BatchHint {
     uint64_t windows_ub = 0; // windows if every read is accepted
 };
 
+// Options a caller may change through ktg_set_option (tests and measurements; the defaults are the
+// measured winners).  Nothing in the library reads the environment.
+struct Tuning {
+    int page_threads = 0;    // update_pages: threads per CTA (0: the default of the key width)
+    int page_nbuf = 0;       // update_pages: 1 = two CTAs per SM, 2 = one pipelined CTA per SM (0: default)
+    int page_log2 = 0;       // slots per page, log2 (0: PageGeom)
+    int l2s_variant = -1;    // level-2 scatter geometry (-1: the default of the key width)
+    int l1_ctas = 0;         // cap on the level-1 scatter's CTAs per SM (0: occupancy)
+    int p2p_ctas = 0;        // same for the fused exchange kernels
+    int chunk_mb = 64;       // host batcher: bytes of bases per chunk
+    int stage_bufs = 2;      // host batcher: staging buffers under the full chunks
+    int flush_pct = 55;      // host batcher: flush on the way after this share of a large call (0: never)
+    int flush_pct2 = 0;      //   and a second one
+    int taper = 1;           // host batcher: a large call ends in short chunks
+    int eager_pages = 1;     // host batcher: level-2 scatter chunk by chunk
+    int stage_factor_milli = 0; // keys per flush in thousandths of the capacity (0: 750 host paced, 3000 resident)
+    long long stage_max_keys = 0; // most keys one stage may hold (0: what memory allows)
+    int host_parse = 0;      // ktg_create_from_files: FASTQ / FASTA records cut by the host reader
+    int fastq_chunk_kb = 16 << 10; // device parser: raw bytes per chunk
+    int mg_pad = 1;          // fused exchange: runs padded to 128-byte lines
+    int trace = 0;           // host timeline on stderr
+};
+
 // ------------------------------------------------------------ abstract base
 struct BuilderBase {
+    Tuning tune;
     ktg_config cfg{};
     uint32_t k = 0;
     bool rc = false;
@@ -226,6 +253,17 @@ struct BuilderBase {
                              uint64_t *n) = 0;
     virtual int export_graph(uint64_t *node_hi, uint64_t *node_lo, uint64_t n_nodes, uint64_t *src, uint64_t *dst,
                              uint32_t *weight, uint8_t *edge_bytes, uint64_t n_edges) = 0;
+    // the export in steps, for a sharded handle (multi.cuh)
+    virtual int compact_edges_into(uint64_t *d_hi, uint64_t *d_lo, uint32_t *d_w, uint64_t cap) = 0;
+    virtual int edges_to_host(uint64_t *d_hi, uint64_t *d_lo, uint32_t *d_w, uint64_t ne, int sorted, uint64_t *hi,
+                              uint64_t *lo, uint32_t *w, uint64_t cap) = 0;
+    virtual int graph_to_host(uint64_t *d_ehi, uint64_t *d_elo, uint32_t *d_w, uint64_t ne, uint64_t *node_hi,
+                              uint64_t *node_lo, uint64_t n_nodes, uint64_t *src, uint64_t *dst, uint32_t *weight,
+                              uint8_t *edge_bytes, uint64_t n_edges) = 0;
+    virtual int externals_to_host(uint64_t *d_ehi, uint64_t *d_elo, uint32_t *d_w, uint64_t ne, uint64_t *ids,
+                                  uint8_t *kinds, uint64_t cap, uint64_t *n_out) = 0;
+    virtual int export_externals(uint64_t *ids, uint8_t *kinds, uint64_t cap, uint64_t *n_out) = 0;
+    virtual int sync_stream() = 0;
     virtual int partition_reads(const uint8_t *d_bases, const uint64_t *d_offsets,
                                 uint64_t n_reads, uint64_t total_bases, void **d_keys,
                                 uint64_t *counts) = 0;
@@ -269,7 +307,6 @@ template <class F> inline int grid_for(F kernel, int block, size_t smem, const D
 // ---------------------------------------------------------------- the builder
 template <class K> struct Builder : BuilderBase {
     typedef KeyTraits<K> T;
-    typedef typename T::Slot Slot;
 
     Table<K> tab{};
     bool fresh = true;        // the table is logically empty and its memory undefined (see ensure_init)
@@ -280,12 +317,12 @@ template <class K> struct Builder : BuilderBase {
     DeviceBuf b_hll;
     DeviceBuf b_spill;
     DeviceBuf b_packed, b_keys, b_keys2, b_hist, b_ovf_keys, b_ovf_inc, b_small;
-    DeviceBuf b_pkeys, b_pcur, b_pspill; // level-2 (page) buckets, their cursors, their spill list
+    DeviceBuf b_pkeys, b_pcur; // level-2 (page) buckets and their cursors
     PackCounters *d_ctr = nullptr;        // accumulates over the whole build
     unsigned long long *d_ovf_count = nullptr;
     unsigned long long *d_scratch = nullptr; // 16 u64 of scratch (stats, cursors)
     unsigned long long *d_lost = nullptr;    // keys dropped because a spill list overflowed (voids the build)
-    unsigned long long *d_page_spill = nullptr; // cursor of the page spill list
+    unsigned long long *d_stage_spill = nullptr; // cursor of the stage's spill list (level-1 and page overflow)
     // lazily built node ((k-1)-mer) table
     bool nodes_valid = false;
     NodeStats node_cache{};
@@ -293,11 +330,12 @@ template <class K> struct Builder : BuilderBase {
     ~Builder() override {
         cudaSetDevice(device);
         if (stream) cudaStreamSynchronize(stream);
-        if (tab.slots) cudaFree(tab.slots);
+        if (tab.base) cudaFree(tab.base);
+        b_empty_page.release();
         b_packed.release(); b_bad.release(); b_valid.release(); b_wstart.release(); b_keys.release(); b_keys2.release();
         b_hist.release(); b_hll.release(); b_spill.release(); b_ovf_keys.release(); b_ovf_inc.release(); b_small.release();
-        b_pkeys.release(); b_pcur.release(); b_pspill.release(); b_stage_cur.release();
-        b_rx.release(); b_mg_cur.release(); b_mg_spill.release(); b_skm_cnt.release(); b_skm_part.release(); b_skm_keys.release(); b_bfc_ctr.release(); b_node_keys.release(); b_node_deg.release();
+        b_pkeys.release(); b_pcur.release(); b_stage_cur.release();
+        b_rx.release(); b_mg_cur.release(); b_mg_spill.release(); b_skm_cnt.release(); b_skm_part.release(); b_bfc_ctr.release(); b_node_keys.release(); b_node_deg.release();
         if (copy_stream) cudaStreamDestroy(copy_stream);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
@@ -310,7 +348,7 @@ template <class K> struct Builder : BuilderBase {
     // to a few keys (C3: 632 sub-tables made the level-1 scatter 3x slower per key).
     static void geometry(uint64_t need_slots, uint32_t sub_log2_bytes, bool balance, uint32_t *n_sub,
                          uint32_t *sub_log2) {
-        uint32_t slot_log2 = sizeof(Slot) == 16 ? 4 : 5;
+        uint32_t slot_log2 = sizeof(K) == 8 ? 4 : 5; // sub-table sizes are quoted for 16 / 32-byte slots (12 / 20 now)
         uint32_t sl = sub_log2_bytes - slot_log2; // slots per sub-table (log2)
         if (balance) {
             while (sl < 28 && sl > PageGeom<K>::LOG2) {
@@ -343,11 +381,11 @@ template <class K> struct Builder : BuilderBase {
         geometry(need_slots, slb, cfg.sub_table_log2_bytes == 0, &t.n_sub, &t.sub_log2);
         t.sub_mask = (uint32_t)((1ull << t.sub_log2) - 1);
         uint32_t pl = PageGeom<K>::LOG2;
-        if (const char *e = getenv("KTG_PAGE_LOG2")) pl = std::min<uint32_t>(pl, std::max(8, atoi(e))); // tuning knob
+        if (tune.page_log2) pl = std::min<uint32_t>(pl, (uint32_t)std::max(8, tune.page_log2));
         t.page_log2 = std::min<uint32_t>(pl, t.sub_log2);
         t.page_mask = (1u << t.page_log2) - 1;
         t.max_probe = std::min<uint32_t>(1u << t.page_log2, 2048);
-        size_t bytes = (t.capacity() + 1) * sizeof(Slot);
+        size_t bytes = t.bytes();
         void *p = nullptr;
         cudaError_t e = cudaMalloc(&p, bytes);
         if (e != cudaSuccess) {
@@ -355,22 +393,33 @@ template <class K> struct Builder : BuilderBase {
             return fail(KTG_ERR_TABLE_FULL, "cannot allocate a %zu byte table: %s", bytes,
                         cudaGetErrorString(e));
         }
-        t.slots = (Slot *)p;
+        t.base = (unsigned char *)p;
         if (do_init) {
             prof.begin("init_table", t.capacity() + 1, stream);
-            init_table_kernel<K><<<props.sms * 8, 256, 0, stream>>>(t.slots, t.capacity() + 1);
+            init_table_kernel<K><<<props.sms * 8, 256, 0, stream>>>(t);
             prof.end(stream);
         }
         else KTG_TRY(init_special_slot(t));
+        KTG_TRY(make_empty_page(t));
         *out = t;
+        return KTG_OK;
+    }
+
+    // one page of empty slots: what the page update loads instead of a page of a fresh table
+    DeviceBuf b_empty_page;
+    uint32_t empty_page_log2 = 0;
+    int make_empty_page(const Table<K> &t) {
+        if (b_empty_page.p && empty_page_log2 == t.page_log2) return KTG_OK;
+        KTG_TRY(b_empty_page.ensure(t.page_bytes()));
+        KTG_CUDA(cudaMemsetAsync(b_empty_page.p, 0xFF, (size_t)sizeof(K) << t.page_log2, stream));
+        KTG_CUDA(cudaMemsetAsync((char *)b_empty_page.p + ((size_t)sizeof(K) << t.page_log2), 0, (size_t)4 << t.page_log2, stream));
+        empty_page_log2 = t.page_log2;
         return KTG_OK;
     }
 
     // the one slot past the end (all-ones key at full width) is always kept defined
     int init_special_slot(const Table<K> &t) {
-        Slot *sp = t.slots + t.capacity();
-        KTG_CUDA(cudaMemsetAsync(sp, 0, sizeof(Slot), stream));
-        KTG_CUDA(cudaMemsetAsync(sp, 0xFF, sizeof(K), stream));
+        KTG_CUDA(cudaMemsetAsync(t.special_w(), 0, 16, stream));
         return KTG_OK;
     }
 
@@ -380,7 +429,7 @@ template <class K> struct Builder : BuilderBase {
     int ensure_init() {
         if (!fresh) return KTG_OK;
         prof.begin("init_table", tab.capacity() + 1, stream);
-        init_table_kernel<K><<<props.sms * 8, 256, 0, stream>>>(tab.slots, tab.capacity() + 1);
+        init_table_kernel<K><<<props.sms * 8, 256, 0, stream>>>(tab);
         prof.end(stream);
         fresh = false;
         return KTG_OK;
@@ -403,7 +452,7 @@ template <class K> struct Builder : BuilderBase {
         d_ovf_count = (unsigned long long *)((char *)b_small.p + 256);
         d_scratch = (unsigned long long *)((char *)b_small.p + 512);
         d_lost = (unsigned long long *)((char *)b_small.p + 1024);
-        d_page_spill = d_lost + 1;
+        d_stage_spill = d_lost + 1;
         KTG_TRY(b_hll.ensure(HLL_M * 4));
         KTG_CUDA(cudaMemsetAsync(b_hll.p, 0, HLL_M * 4, stream));
         KTG_TRY(b_ovf_keys.ensure(OVF_CAP * sizeof(K)));
@@ -429,26 +478,11 @@ template <class K> struct Builder : BuilderBase {
     template <class F> static void allow_smem(F kernel, size_t bytes) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     }
+    static size_t mx_scatter_smem() { return ScatterSmem<K, SCATTER_TILE>::bytes(MAX_BINS, true); }
     void set_smem_attrs() {
         const size_t mx = ScatterSmem<K, SCATTER_TILE>::bytes(MAX_BINS, true);
         allow_smem(scatter_buckets_kernel<K, 2>, ScatterSmem<K, L2S_TILE>::bytes(MAX_PAGES_PER_SUB, false));
         allow_smem(scatter_buckets_kernel<K, 1>, ScatterSmem<K, L2S_TILE>::bytes(MAX_BINS, false));
-        allow_smem(update_pages_kernel<K, 512>, page_smem_bytes(512));
-        allow_smem(update_pages_kernel<K, 640>, page_smem_bytes(640));
-        allow_smem(update_pages_kernel<K, 704>, page_smem_bytes(704));
-        allow_smem(update_pages_kernel<K, 704, PAGE_UNROLL, PageGeom<K>::LOG2>, page_smem_bytes(704));
-        allow_smem(update_pages_kernel<K, 704, PAGE_UNROLL, 0, true>, page_smem_bytes(704));
-        allow_smem(update_pages_kernel<K, 704, 2>, page_smem_bytes(704));
-        allow_smem(update_pages_kernel<K, 704, 6>, page_smem_bytes(704));
-        allow_smem(update_pages_kernel<K, 704, 8>, page_smem_bytes(704));
-        allow_smem(scatter_reads_kernel<K, true, BIN_PART, true>, mx);
-        allow_smem(scatter_reads_kernel<K, false, BIN_PART, true>, mx);
-        allow_smem(scatter_reads_kernel<K, true, BIN_PART, false>, mx);
-        allow_smem(scatter_reads_kernel<K, false, BIN_PART, false>, mx);
-        allow_smem(scatter_reads_kernel<K, true, BIN_OWNER, false>, mx);
-        allow_smem(scatter_reads_kernel<K, false, BIN_OWNER, false>, mx);
-        allow_smem(scatter_reads_kernel<K, true, BIN_OWNER, true>, mx);
-        allow_smem(scatter_reads_kernel<K, false, BIN_OWNER, true>, mx);
         allow_smem(scatter_keys_kernel<K, true, false>, mx);
         allow_smem(scatter_keys_kernel<K, false, true>, mx);
         allow_smem(scatter_keys_kernel<K, false, false>, mx);
@@ -458,9 +492,6 @@ template <class K> struct Builder : BuilderBase {
         if (cfg.flags & KTG_FLAG_FORCE_DIRECT) return false;
         if (cfg.flags & (KTG_FLAG_FORCE_PARTITION | KTG_FLAG_FORCE_PAGES)) return true;
         return tab.n_sub > 3; // up to ~48 MB of table is L2 resident as a whole
-    }
-    static size_t page_smem_bytes(int threads, uint32_t page_log2 = PageGeom<K>::LOG2) {
-        return (((size_t)1 << page_log2) + (threads / 32) * PQ_CAP) * (sizeof(K) + 4);
     }
     // Streaming page update or L2 atomics?  The sweep reads and writes every slot
     // (32 B per slot of traffic) and then absorbs ~120 G keys/s, the atomic path runs at
@@ -473,6 +504,7 @@ template <class K> struct Builder : BuilderBase {
         return 4 * n_keys >= tab.capacity();
     }
 
+    int sync_stream() override { return sync(); }
     int sync() {
         trace("sync>");
         KTG_CUDA(cudaStreamSynchronize(stream));
@@ -489,7 +521,7 @@ template <class K> struct Builder : BuilderBase {
         }
         KTG_CUDA(cudaMemsetAsync(d_scratch, 0, 8, stream));
         prof.begin("count_occupied", tab.capacity(), stream);
-        count_occupied_kernel<K><<<props.sms * 8, 256, 0, stream>>>(tab.slots, tab.capacity(), d_scratch);
+        count_occupied_kernel<K><<<props.sms * 8, 256, 0, stream>>>(tab, d_scratch);
         prof.end(stream);
         unsigned long long v = 0;
         KTG_CUDA(cudaMemcpyAsync(&v, d_scratch, 8, cudaMemcpyDeviceToHost, stream));
@@ -503,17 +535,17 @@ template <class K> struct Builder : BuilderBase {
         if (fresh) { // nothing to move
             KTG_TRY(alloc_table(need_slots, &nt, false));
             KTG_TRY(sync());
-            cudaFree(tab.slots);
+            cudaFree(tab.base);
             tab = nt;
             ++grow_events;
             return KTG_OK;
         }
         KTG_TRY(alloc_table(need_slots, &nt, true));
         prof.begin("rehash", tab.capacity(), stream);
-        rehash_kernel<K><<<props.sms * 8, 256, 0, stream>>>(tab.slots, tab.capacity(), nt);
+        rehash_kernel<K><<<props.sms * 8, 256, 0, stream>>>(tab, nt);
         prof.end(stream);
         KTG_TRY(sync());
-        cudaFree(tab.slots);
+        cudaFree(tab.base);
         tab = nt;
         ++grow_events;
         return KTG_OK;
@@ -754,24 +786,22 @@ template <class K> struct Builder : BuilderBase {
 
     template <int BINS, bool HLL>
     int scatter_reads_pass(const Batch &bt, uint32_t n_bins, const ScatterOut &o, const PeerOut *po = nullptr) {
-        size_t ss = ScatterSmem<K, SCATTER_TILE>::bytes(n_bins, HLL);
         uint64_t n_tiles = std::max<uint64_t>(1, (bt.v.n_items + SCATTER_THREADS - 1) / SCATTER_THREADS);
         PeerOut peers{};
         if (po) peers = *po;
         // tuning knobs: CTAs per SM (the fused exchange kernel may share the SMs with the
         // owner-side kernels of the previous chunk when a batch is sent in chunks)
-        int cap_ctas = 0;
-        if (const char *e = getenv(po ? "KTG_P2P_CTAS" : "KTG_L1_CTAS")) cap_ctas = atoi(e);
+        const int cap_ctas = po ? tune.p2p_ctas : tune.l1_ctas;
         prof.begin(po ? "scatter_reads_p2p" : "scatter_reads", bt.windows, stream);
         if (cap_ctas > 0) n_tiles = std::min<uint64_t>(n_tiles, (uint64_t)props.sms * cap_ctas);
-        if (rc) {
-            int g = (int)std::min<uint64_t>(grid_for(scatter_reads_kernel<K, true, BINS, HLL>, SCATTER_THREADS, ss, props), n_tiles);
-            scatter_reads_kernel<K, true, BINS, HLL><<<g, SCATTER_THREADS, ss, stream>>>(bt.v, k, tab, n_bins, o, (uint32_t *)b_hll.p, peers);
-        }
-        else {
-            int g = (int)std::min<uint64_t>(grid_for(scatter_reads_kernel<K, false, BINS, HLL>, SCATTER_THREADS, ss, props), n_tiles);
-            scatter_reads_kernel<K, false, BINS, HLL><<<g, SCATTER_THREADS, ss, stream>>>(bt.v, k, tab, n_bins, o, (uint32_t *)b_hll.p, peers);
-        }
+        auto launch = [&](auto kern, int per) {
+            const size_t sb = (size_t)SCATTER_THREADS * per * (sizeof(K) + 2) + (size_t)n_bins * 28 + (HLL ? HLL_M * 4 : 0);
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(sb, mx_scatter_smem()));
+            int g = (int)std::min<uint64_t>(grid_for(kern, SCATTER_THREADS, sb, props), n_tiles);
+            kern<<<g, SCATTER_THREADS, sb, stream>>>(bt.v, k, tab, n_bins, o, (uint32_t *)b_hll.p, peers);
+        };
+        if (rc) launch(scatter_reads_kernel<K, true, BINS, HLL>, ScatterGeom<K>::PER);
+        else launch(scatter_reads_kernel<K, false, BINS, HLL>, ScatterGeom<K>::PER);
         prof.end(stream);
         return KTG_OK;
     }
@@ -815,16 +845,12 @@ template <class K> struct Builder : BuilderBase {
     //                 sub_mod != 0: bucket q belongs to sub-table q % sub_mod (receive buckets,
     //                 one set per source rank)
     //   pages_update  the sweep + the spill list
-    uint64_t pg_cap2 = 0, pg_spill_cap = 0;
+    uint64_t pg_cap2 = 0;
     int pages_open(uint64_t room) {
         const uint64_t n_pages = tab.n_pages();
         pg_cap2 = page_bucket_cap_for(room, n_pages);
-        pg_spill_cap = std::max<uint64_t>(1u << 20, room / 32);
-        if ((double)n_pages * (double)pg_cap2 >= 4.0e9) return fail(KTG_ERR_INVALID, "batch too large for 32-bit bucket positions");
         KTG_TRY(b_pkeys.ensure(n_pages * pg_cap2 * sizeof(K) + 64));
         KTG_TRY(b_pcur.ensure(n_pages * 8));
-        KTG_TRY(b_pspill.ensure(pg_spill_cap * sizeof(K) + 64));
-        KTG_CUDA(cudaMemsetAsync(d_page_spill, 0, 8, stream));
         init_cursors_kernel<<<(int)std::min<uint64_t>((n_pages + 255) / 256, props.sms * 8), 256, 0, stream>>>(
             (unsigned long long *)b_pcur.p, n_pages, pg_cap2);
         return KTG_OK;
@@ -835,19 +861,21 @@ template <class K> struct Builder : BuilderBase {
         o.cursors = (unsigned long long *)b_pcur.p;
         o.bucket_cap = pg_cap2;
         o.out = b_pkeys.p;
-        o.spill_out = b_pspill.p;
-        o.spill_cursor = d_page_spill;
-        o.spill_cap = pg_spill_cap;
+        // a page bucket that overflows (a heavy hitter: poly-A reads, satellite repeats) spills into the
+        // stage's own list, which is as large as the stage: nothing can be lost whatever the skew
+        o.spill_out = b_spill.p;
+        o.spill_cursor = stage_spill_cursor();
+        o.spill_cap = stage_spill_cap;
         const uint64_t tiles_per_bin = cap1 / L2S_TILE, n_tiles = tiles_per_bin * n_bins;
         const size_t ss = ScatterSmem<K, L2S_TILE>::bytes(tab.pages_per_sub(), false);
         // 256-thread CTAs (four per SM) overlap the phases of a tile better than 512-thread ones
         // (1.51 vs 1.60 ms on C2); u128 keys need the registers of the larger block
-        int variant = sizeof(K) == 8 ? 1 : 0;
-        if (const char *e = getenv("KTG_L2S_VARIANT")) variant = atoi(e); // tuning knob
+        int variant = (sizeof(K) == 8 && tab.pages_per_sub() <= 256) ? 1 : 0; // at most one bin per thread
+        if (tune.l2s_variant >= 0) variant = tune.l2s_variant;
         prof.begin("scatter_pages", n_keys, stream);
         auto launch_v = [&](auto kern, int threads, int per) {
             const uint64_t tile = (uint64_t)threads * per, tpb = cap1 / tile, nt = tpb * n_bins;
-            const size_t sb = (size_t)tile * (sizeof(K) + 4) + (size_t)tab.pages_per_sub() * 32;
+            const size_t sb = (size_t)tile * (sizeof(K) + 2) + (size_t)tab.pages_per_sub() * 28;
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);
             int gg = (int)std::min<uint64_t>(grid_for(kern, threads, sb, props), nt);
             kern<<<gg, threads, sb, stream>>>(keys1, fill1, cap1, tpb, nt, sub_mod, false, tab, o, nullptr);
@@ -869,35 +897,30 @@ template <class K> struct Builder : BuilderBase {
     int pages_update(uint64_t n_keys) {
         const uint64_t n_pages = tab.n_pages(), cap2 = pg_cap2;
         unsigned long long *cur2 = (unsigned long long *)b_pcur.p;
-        int pt = sizeof(K) == 8 ? 704 : 512; // u128 keys need the registers of the smaller block
-        if (const char *e = getenv("KTG_PAGE_THREADS")) pt = atoi(e); // tuning knob: 512, 640 or 704
         const bool palin = rc && (k % 2 == 0), special = !rc && 2 * k == 8 * sizeof(K);
+        // geometry (two CTAs per SM): u64 keys 640 threads at 46 registers (C2: 1.397 ms, 704 threads 1.425,
+        // one pipelined CTA of 1024 threads with two page buffers 1.56); u128 keys need the registers of
+        // the smaller block (512 threads 14.2 ms on C3 k=63, 640 threads 15.7)
+        int pt = tune.page_threads ? tune.page_threads : (sizeof(K) == 8 ? 640 : 512);
+        const int nbuf = tune.page_nbuf ? tune.page_nbuf : 1;
+        KTG_TRY(make_empty_page(tab));
+        const unsigned char *empty = fresh ? (const unsigned char *)b_empty_page.p : nullptr;
         prof.begin("update_pages", n_keys, stream);
-        auto launch_p = [&](auto kern, int threads) {
-            const size_t ps = page_smem_bytes(threads, tab.page_log2);
+        auto launch_p = [&](auto kern, int threads, int nb) {
+            const size_t ps = page_kernel_smem<K>(threads, nb, tab.page_log2);
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps);
             int g = (int)std::min<uint64_t>(grid_for(kern, threads, ps, props), n_pages);
-            kern<<<g, threads, ps, stream>>>((const K *)b_pkeys.p, cur2, cap2, k, palin, special, tab, fresh);
+            kern<<<g, threads, ps, stream>>>((const K *)b_pkeys.p, cur2, cap2, k, palin, special, tab, empty);
         };
-        int pu = 4;
-        if (const char *e = getenv("KTG_PAGE_UNROLL")) pu = atoi(e); // tuning knob: 2, 4, 6, 8 (704 threads)
-        if (pt == 704 && pu == 2) launch_p(update_pages_kernel<K, 704, 2>, 704);
-        else if (pt == 704 && pu == 6) launch_p(update_pages_kernel<K, 704, 6>, 704);
-        else if (pt == 704 && pu == 8) launch_p(update_pages_kernel<K, 704, 8>, 704);
-        else if (pt == 640) launch_p(update_pages_kernel<K, 640>, 640);
-        // (a variant with the page size as a compile-time constant has 3 % fewer instructions and is 5 % slower)
-        else if (pt == 704 && tab.page_log2 == PageGeom<K>::LOG2 && getenv("KTG_PAGE_FIXED")) // tuning knob
-            launch_p(update_pages_kernel<K, 704, PAGE_UNROLL, PageGeom<K>::LOG2>, 704);
-        // rows that lie wholly inside their bucket skip the per-key bounds (1.61 -> 1.59 ms on C2)
-        else if (pt == 704 && !getenv("KTG_PAGE_NO_FULLROWS")) launch_p(update_pages_kernel<K, 704, PAGE_UNROLL, 0, true>, 704); // (tuning knob)
-        else if (pt == 704) launch_p(update_pages_kernel<K, 704>, 704);
-        else launch_p(update_pages_kernel<K, 512>, 512);
+        if (nbuf == 2 && pt >= 1024) launch_p(update_pages_kernel<K, 1024, 2>, 1024, 2);
+        else if (nbuf == 2) launch_p(update_pages_kernel<K, 768, 2>, 768, 2);
+        else if (pt >= 704) launch_p(update_pages_kernel<K, 704, 1>, 704, 1);
+        else if (pt >= 640) launch_p(update_pages_kernel<K, 640, 1>, 640, 1);
+        else launch_p(update_pages_kernel<K, 512, 1>, 512, 1);
         prof.end(stream);
         fresh = false;
         nodes_valid = false;
         ++page_updates;
-        // page-bucket spill (if any): the kernel reads the count from the device
-        // (keys beyond spill_cap are counted in *d_lost by the kernel and void the build in finalize)
-        KTG_TRY(launch_insert((const K *)b_pspill.p, pg_spill_cap, nullptr, 0, 0, d_page_spill));
         return KTG_OK;
     }
     int paged_update(uint32_t n_bins, uint64_t cap1, uint64_t n_keys, const unsigned long long *fill1,
@@ -922,7 +945,6 @@ template <class K> struct Builder : BuilderBase {
     uint64_t stage_target = 0;    // flush once this many keys are staged
     uint64_t stage_spill_cap = 0;
     uint64_t staged_keys = 0;     // keys in the buckets + spill list (+ page buckets, see below)
-    uint64_t staged_spilled = 0;  // of which in the spill list
     // Eager page stage (host batcher, large batches).  With hold_flush the batcher has announced how
     // many keys its call will offer (call_keys_hint) and flushes on its own schedule.  Then every
     // chunk's level-1 buckets are moved on to page buckets right away (pages_drain): the level-2
@@ -936,12 +958,12 @@ template <class K> struct Builder : BuilderBase {
     uint32_t pstage_n_sub = 0, pstage_sub_log2 = 0, pstage_page_log2 = 0;
     uint64_t pstage_pages = 0;
     bool eager_pages() const {
-        if (!hold_flush || !call_keys_hint || getenv("KTG_NO_EAGER")) return false; // (tuning knob)
+        if (!hold_flush || !call_keys_hint || !tune.eager_pages) return false;
         return use_partition() && use_pages(call_keys_hint);
     }
     DeviceBuf b_stage_cur;        // cursors[n_bins] | spill cursor | backup of both
     unsigned long long *stage_cursors() { return (unsigned long long *)b_stage_cur.p; }
-    unsigned long long *stage_spill_cursor() { return stage_cursors() + stage_bins; }
+    unsigned long long *stage_spill_cursor() { return d_stage_spill; }
 
     // Most keys one stage may hold.  Two limits: bucket positions are 32-bit (2^31 keys plus the
     // slack of the buckets stay below 4e9), and memory: level-1 buckets, their spill list (as large as
@@ -949,20 +971,19 @@ template <class K> struct Builder : BuilderBase {
     // of what is free now plus what its own buffers already hold (180 GB of HBM: C3 stages all of its
     // 1.84 G keys, 46 GB, beside the 10.6 GB table and is swept once).
     uint64_t stage_max_keys() const {
-        const char *e = getenv("KTG_STAGE_MAX_KEYS"); // tuning knob
-        if (e) return std::max<uint64_t>(1u << 16, strtoull(e, nullptr, 10));
-        uint64_t lim = 1ull << 31;
+        if (tune.stage_max_keys > 0) return std::max<uint64_t>(1u << 16, (uint64_t)tune.stage_max_keys);
+        uint64_t lim = ~0ull;
         // (cudaMemGetInfo takes ~1.5 ms on this driver: asked once per table allocation, not per stage)
-        if (stage_mem_for != (const void *)tab.slots) {
+        if (stage_mem_for != (const void *)tab.base) {
             size_t free_b = 0, total_b = 0;
             stage_mem_keys = ~0ull;
             if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-                const uint64_t held = b_keys.cap + b_spill.cap + b_pkeys.cap + b_pspill.cap;
+                const uint64_t held = b_keys.cap + b_spill.cap + b_pkeys.cap;
                 const uint64_t budget = ((uint64_t)free_b + held) / 10 * 7;
                 stage_mem_keys = budget / (uint64_t)(3.3 * sizeof(K));
             }
             else (void)cudaGetLastError();
-            stage_mem_for = (const void *)tab.slots;
+            stage_mem_for = (const void *)tab.base;
         }
         lim = std::min<uint64_t>(lim, stage_mem_keys);
         return std::max<uint64_t>(lim, 1u << 20);
@@ -983,7 +1004,7 @@ template <class K> struct Builder : BuilderBase {
         // keys).  Device-resident input: every sweep reads and writes the whole table, so as many keys per
         // sweep as fit (C3 in 5 batches: three sweeps of the 10.6 GB table were 17.9 of 41 ms, one is 9.6)
         double factor = host_paced ? 0.75 : 3.0;
-        if (const char *e = getenv("KTG_STAGE_FACTOR")) factor = atof(e); // tuning knob
+        if (tune.stage_factor_milli > 0) factor = tune.stage_factor_milli / 1000.0;
         stage_target = std::min<uint64_t>((uint64_t)(factor * (double)tab.capacity()), stage_max_keys());
         if (host_paced) stage_room = batch_keys >= stage_target ? batch_keys : stage_target + batch_keys;
         else stage_room = std::max(batch_keys, stage_target);
@@ -998,7 +1019,6 @@ template <class K> struct Builder : BuilderBase {
         // as large as the stage itself: even a batch made of one key cannot overflow it, so a
         // batch is staged without looking at the spill cursor (it is read when the stage is flushed)
         stage_spill_cap = (eager ? pstage_room + batch_keys : stage_room) + 64;
-        if ((double)stage_cap1 * n_bins >= 4.0e9) return fail(KTG_ERR_INVALID, "batch too large: split it (32-bit bucket positions)");
         KTG_TRY(b_keys.ensure(stage_cap1 * n_bins * sizeof(K) + 64));
         KTG_TRY(b_spill.ensure(stage_spill_cap * sizeof(K) + 64));
         KTG_TRY(b_stage_cur.ensure(((size_t)n_bins + 1) * 8));
@@ -1006,7 +1026,7 @@ template <class K> struct Builder : BuilderBase {
         stage_sub_log2 = tab.sub_log2;
         init_cursors_kernel<<<(n_bins + 255) / 256, 256, 0, stream>>>(stage_cursors(), n_bins, stage_cap1);
         KTG_CUDA(cudaMemsetAsync(stage_spill_cursor(), 0, 8, stream));
-        staged_keys = staged_spilled = 0;
+        staged_keys = 0;
         l1_keys = pstaged_keys = 0;
         pstage_open = false;
         if (eager) {
@@ -1064,11 +1084,8 @@ template <class K> struct Builder : BuilderBase {
             return KTG_OK;
         }
         trace("flush", staged_keys);
-        unsigned long long spilled_now = 0;
-        KTG_CUDA(cudaMemcpyAsync(&spilled_now, stage_spill_cursor(), 8, cudaMemcpyDeviceToHost, stream));
         double est = 0;
         KTG_TRY(hll_estimate(&est)); // synchronises the stream
-        staged_spilled = std::min<uint64_t>(spilled_now, stage_spill_cap);
         // fused multi-GPU mode: the sketch was all-reduced, it describes the keys of ALL ranks
         // (super-k-mer exchange: the owner sketches what it receives, i.e. its own shard)
         const uint64_t distinct = hll_base + (uint64_t)(est * (mg_mode && !mg_local_sketch ? 1.10 / tab.world : 1.08)) + 64;
@@ -1080,10 +1097,10 @@ template <class K> struct Builder : BuilderBase {
             KTG_TRY(grow_to(need));
             moved = tab.n_sub != stage_bins || tab.sub_log2 != stage_sub_log2;
         }
-        const uint64_t n = staged_keys, spilled = staged_spilled, n_l1 = l1_keys, n_pg = pstaged_keys;
+        const uint64_t n = staged_keys, n_l1 = l1_keys, n_pg = pstaged_keys;
         const uint32_t bins = stage_bins;
         const bool eager = pstage_open;
-        staged_keys = staged_spilled = 0;
+        staged_keys = 0;
         l1_keys = pstaged_keys = 0;
         pstage_open = false;
         stage_bins = 0; // the next batch opens a new stage (sized for the table as it is then)
@@ -1099,12 +1116,13 @@ template <class K> struct Builder : BuilderBase {
             else { // page buckets of a geometry that is gone: plain arrays of keys now
                 if (n_l1) KTG_TRY(launch_insert((const K *)b_keys.p, n_l1, stage_cursors(), stage_cap1, bins));
                 if (n_pg) KTG_TRY(launch_insert((const K *)b_pkeys.p, n_pg, (const unsigned long long *)b_pcur.p, pg_cap2, (uint32_t)pstage_pages));
-                KTG_TRY(launch_insert((const K *)b_pspill.p, pg_spill_cap, nullptr, 0, 0, d_page_spill));
             }
         }
         else if (!moved && use_pages(n)) KTG_TRY(paged_update(bins, stage_cap1, n, stage_cursors()));
         else KTG_TRY(launch_insert((const K *)b_keys.p, n, stage_cursors(), stage_cap1, bins));
-        if (spilled) KTG_TRY(launch_insert_keys((const K *)b_spill.p, spilled));
+        // the spill list (level-1 buckets and page buckets that overflowed; usually empty): the kernel
+        // reads the count from the device
+        KTG_TRY(launch_insert((const K *)b_spill.p, stage_spill_cap, nullptr, 0, 0, stage_spill_cursor()));
         return KTG_OK;
     }
 
@@ -1194,7 +1212,7 @@ template <class K> struct Builder : BuilderBase {
 
     int reset() override {
         trace("reset");
-        staged_keys = staged_spilled = 0;
+        staged_keys = 0;
         l1_keys = pstaged_keys = 0;
         pstage_open = false;
         stage_bins = 0;
@@ -1222,14 +1240,14 @@ template <class K> struct Builder : BuilderBase {
         KTG_CUDA(cudaMemsetAsync(d_scratch, 0, sizeof(EdgeStats), stream));
         uint64_t n = tab.capacity() + 1;
         prof.begin("edge_stats", n, stream);
-        if (rc) edge_stats_kernel<K, true><<<props.sms * 8, 256, 0, stream>>>(tab.slots, n, k, threshold, (EdgeStats *)d_scratch);
-        else edge_stats_kernel<K, false><<<props.sms * 8, 256, 0, stream>>>(tab.slots, n, k, threshold, (EdgeStats *)d_scratch);
+        if (rc) edge_stats_kernel<K, true><<<props.sms * 8, 256, 0, stream>>>(tab, k, threshold, (EdgeStats *)d_scratch);
+        else edge_stats_kernel<K, false><<<props.sms * 8, 256, 0, stream>>>(tab, k, threshold, (EdgeStats *)d_scratch);
         prof.end(stream);
         KTG_CUDA(cudaMemcpyAsync(out, d_scratch, sizeof(EdgeStats), cudaMemcpyDeviceToHost, stream));
         return sync();
     }
 
-    // an empty node table for up to max_entries canonical (k-1)-mers (the caller frees nt->slots)
+    // an empty node table for up to max_entries canonical (k-1)-mers (the caller frees nt->base)
     template <class KN> int make_node_table(uint64_t max_entries, Table<KN> *out) {
         Table<KN> nt{};
         uint64_t need = (uint64_t)((double)(max_entries + 1) / 0.8) + 1024;
@@ -1247,18 +1265,17 @@ template <class K> struct Builder : BuilderBase {
         nt.ovf_inc = nullptr;
         nt.ovf_count = d_scratch + 15; // count only; nothing is stored (ovf_cap = 0)
         nt.ovf_cap = 0;
-        typedef typename KeyTraits<KN>::Slot NSlot;
         void *p = nullptr;
-        size_t bytes = (nt.capacity() + 1) * sizeof(NSlot);
+        size_t bytes = nt.bytes();
         cudaError_t e = cudaMalloc(&p, bytes);
         if (e != cudaSuccess) {
             (void)cudaGetLastError();
             return fail(KTG_ERR_CUDA, "cannot allocate %zu bytes for the node table: %s", bytes, cudaGetErrorString(e));
         }
-        nt.slots = (NSlot *)p;
+        nt.base = (unsigned char *)p;
         KTG_CUDA(cudaMemsetAsync(d_scratch, 0, 128, stream));
         prof.begin("init_table", nt.capacity() + 1, stream);
-        init_table_kernel<KN><<<props.sms * 8, 256, 0, stream>>>(nt.slots, nt.capacity() + 1);
+        init_table_kernel<KN><<<props.sms * 8, 256, 0, stream>>>(nt);
         prof.end(stream);
         *out = nt;
         return KTG_OK;
@@ -1272,21 +1289,21 @@ template <class K> struct Builder : BuilderBase {
         KTG_TRY(make_node_table<KN>(2 * occ, nt)); // distinct canonical nodes <= 2 x live canonical edges
         uint64_t n = tab.capacity() + 1;
         prof.begin("build_nodes", n, stream);
-        if (rc) build_nodes_kernel<K, KN, true><<<props.sms * 8, 256, 0, stream>>>(tab.slots, n, k, *nt);
-        else build_nodes_kernel<K, KN, false><<<props.sms * 8, 256, 0, stream>>>(tab.slots, n, k, *nt);
+        if (rc) build_nodes_kernel<K, KN, true><<<props.sms * 8, 256, 0, stream>>>(tab, k, *nt);
+        else build_nodes_kernel<K, KN, false><<<props.sms * 8, 256, 0, stream>>>(tab, k, *nt);
         prof.end(stream);
         return KTG_OK;
     }
 
     template <class KN> int node_table_stats(const Table<KN> &nt, NodeStats *out) {
         prof.begin("node_stats", nt.capacity() + 1, stream);
-        if (rc) node_stats_kernel<KN, true><<<props.sms * 8, 256, 0, stream>>>(nt.slots, nt.capacity() + 1, (NodeStats *)d_scratch);
-        else node_stats_kernel<KN, false><<<props.sms * 8, 256, 0, stream>>>(nt.slots, nt.capacity() + 1, (NodeStats *)d_scratch);
+        if (rc) node_stats_kernel<KN, true><<<props.sms * 8, 256, 0, stream>>>(nt, (NodeStats *)d_scratch);
+        else node_stats_kernel<KN, false><<<props.sms * 8, 256, 0, stream>>>(nt, (NodeStats *)d_scratch);
         prof.end(stream);
         unsigned long long host[16];
         KTG_CUDA(cudaMemcpyAsync(host, d_scratch, sizeof host, cudaMemcpyDeviceToHost, stream));
         int rc_ = sync();
-        cudaFree(nt.slots);
+        cudaFree(nt.base);
         KTG_TRY(rc_);
         if (host[15]) return fail(KTG_ERR_TABLE_FULL, "node table overflow (%llu)", host[15]);
         memcpy(out, host, sizeof(NodeStats));
@@ -1307,25 +1324,24 @@ template <class K> struct Builder : BuilderBase {
         uint64_t occ = 0; // exact number of entries: one more scan, this is not a hot path
         {
             KTG_CUDA(cudaMemsetAsync(d_scratch, 0, 8, stream));
-            count_occupied_kernel<KN><<<props.sms * 8, 256, 0, stream>>>(nt.slots, nt.capacity() + 1, d_scratch);
+            count_occupied_kernel<KN><<<props.sms * 8, 256, 0, stream>>>(nt, d_scratch);
             unsigned long long v = 0;
             KTG_CUDA(cudaMemcpyAsync(&v, d_scratch, 8, cudaMemcpyDeviceToHost, stream));
             int rc_ = sync();
-            if (rc_ != KTG_OK) { cudaFree(nt.slots); return rc_; }
+            if (rc_ != KTG_OK) { cudaFree(nt.base); return rc_; }
             occ = v;
         }
         int rc_ = b_node_keys.ensure(occ * sizeof(KN) + 64);
         if (rc_ == KTG_OK) rc_ = b_node_deg.ensure(occ * 4 + 64);
-        if (rc_ != KTG_OK) { cudaFree(nt.slots); return rc_; }
+        if (rc_ != KTG_OK) { cudaFree(nt.base); return rc_; }
         KTG_CUDA(cudaMemsetAsync(d_scratch, 0, 8, stream));
         prof.begin("compact_nodes", nt.capacity() + 1, stream);
-        compact_nodes_kernel<KN><<<props.sms * 8, 256, 0, stream>>>(nt.slots, nt.capacity() + 1, (KN *)b_node_keys.p,
-                                                                    (uint32_t *)b_node_deg.p, d_scratch);
+        compact_nodes_kernel<KN><<<props.sms * 8, 256, 0, stream>>>(nt, (KN *)b_node_keys.p, (uint32_t *)b_node_deg.p, d_scratch);
         prof.end(stream);
         unsigned long long host[16];
         KTG_CUDA(cudaMemcpyAsync(host, d_scratch, sizeof host, cudaMemcpyDeviceToHost, stream));
         rc_ = sync();
-        cudaFree(nt.slots);
+        cudaFree(nt.base);
         KTG_TRY(rc_);
         if (host[15]) return fail(KTG_ERR_TABLE_FULL, "node table overflow (%llu)", host[15]);
         *d_keys = b_node_keys.p;
@@ -1368,7 +1384,7 @@ template <class K> struct Builder : BuilderBase {
         KTG_TRY(ensure_init());
         uint64_t n = tab.capacity() + 1;
         prof.begin("standardize", n, stream);
-        standardize_kernel<K><<<props.sms * 8, 256, 0, stream>>>(tab.slots, n, p, t);
+        standardize_kernel<K><<<props.sms * 8, 256, 0, stream>>>(tab, p, t);
         prof.end(stream);
         nodes_valid = false;
         KTG_CUDA(cudaGetLastError());
@@ -1393,7 +1409,7 @@ template <class K> struct Builder : BuilderBase {
         KTG_TRY(ensure_init());
         uint64_t n = tab.capacity() + 1;
         prof.begin("filter", n, stream);
-        filter_kernel<K><<<props.sms * 8, 256, 0, stream>>>(tab.slots, n, t);
+        filter_kernel<K><<<props.sms * 8, 256, 0, stream>>>(tab, t);
         prof.end(stream);
         nodes_valid = false;
         KTG_CUDA(cudaGetLastError());
@@ -1409,48 +1425,79 @@ template <class K> struct Builder : BuilderBase {
         double p = (double)(G - k_) / (double)(es.sum_w - es.sum_w_below); // standardizer.rs:123-127
         uint64_t n = tab.capacity() + 1;
         prof.begin("standardize", n, stream);
-        standardize_kernel<K><<<props.sms * 8, 256, 0, stream>>>(tab.slots, n, p, t);
+        standardize_kernel<K><<<props.sms * 8, 256, 0, stream>>>(tab, p, t);
         prof.end(stream);
         nodes_valid = false;
         KTG_CUDA(cudaGetLastError());
         return KTG_OK;
     }
 
-    // both-strand expanded (key, weight) arrays on the device, optionally sorted by k-mer
+    // ---- export: what Convert::create_from consumes (hm_gir.rs:156-226) ------------------------------
+    // Three steps that a sharded handle (multi.cuh) runs on different devices: every shard compacts its
+    // both-strand expanded edges into arrays that may live on another GPU (peer memory), the gathering
+    // device sorts them and derives the graph.
+    int compact_edges_into(uint64_t *d_hi, uint64_t *d_lo, uint32_t *d_w, uint64_t cap) override {
+        KTG_TRY(finalize());
+        KTG_TRY(ensure_init());
+        KTG_CUDA(cudaMemsetAsync(d_scratch, 0, 8, stream));
+        prof.begin("compact_edges", tab.capacity() + 1, stream);
+        if (rc) compact_edges_kernel<K, true><<<props.sms * 8, 256, 0, stream>>>(tab, k, 1, d_hi, d_lo, d_w, cap, d_scratch);
+        else compact_edges_kernel<K, false><<<props.sms * 8, 256, 0, stream>>>(tab, k, 1, d_hi, d_lo, d_w, cap, d_scratch);
+        prof.end(stream);
+        KTG_CUDA(cudaGetLastError());
+        return KTG_OK;
+    }
+
+    // ne unsorted edges in device arrays of THIS device -> sorted by k-mer (arrays owned by sc)
+    int sort_device_edges(Scratch &sc, KeyArr *keys, uint32_t **weights, uint64_t ne) {
+        if (!ne) return KTG_OK;
+        uint32_t *perm;
+        KeyArr s_;
+        prof.begin("sort_edges", ne, stream);
+        KTG_TRY(sort_keys(*keys, ne, 2 * k, sc, stream, &perm, &s_));
+        uint32_t *w_s;
+        KTG_TRY(sc.alloc(&w_s, ne));
+        gather_kernel<uint32_t><<<export_grid(ne), 256, 0, stream>>>(*weights, perm, w_s, ne);
+        prof.end(stream);
+        *keys = s_;
+        *weights = w_s;
+        KTG_CUDA(cudaGetLastError());
+        return KTG_OK;
+    }
+
+    // this handle's edges: count, allocate, compact (+ sort)
     int device_edges(bool sorted, Scratch &sc, KeyArr *keys, uint32_t **weights, uint64_t *n_out) {
         EdgeStats es;
         KTG_TRY(edge_stats(0, &es));
         const uint64_t ne = es.edges;
         *n_out = ne;
-        const bool wide = T::WORDS == 2;
         uint64_t *d_hi = nullptr, *d_lo;
         uint32_t *d_w;
         KTG_TRY(sc.alloc(&d_lo, ne));
         KTG_TRY(sc.alloc(&d_w, ne));
-        if (wide) KTG_TRY(sc.alloc(&d_hi, ne));
-        KTG_CUDA(cudaMemsetAsync(d_scratch, 0, 8, stream));
-        const uint64_t n = tab.capacity() + 1;
-        prof.begin("compact_edges", n, stream);
-        if (rc) compact_edges_kernel<K, true><<<props.sms * 8, 256, 0, stream>>>(tab.slots, n, k, 1, d_hi, d_lo, d_w, ne, d_scratch);
-        else compact_edges_kernel<K, false><<<props.sms * 8, 256, 0, stream>>>(tab.slots, n, k, 1, d_hi, d_lo, d_w, ne, d_scratch);
-        prof.end(stream);
+        if (T::WORDS == 2) KTG_TRY(sc.alloc(&d_hi, ne));
+        KTG_TRY(compact_edges_into(d_hi, d_lo, d_w, ne));
         keys->hi = d_hi;
         keys->lo = d_lo;
         *weights = d_w;
-        if (sorted && ne) {
-            uint32_t *perm;
-            KeyArr s;
-            prof.begin("sort_edges", ne, stream);
-            KTG_TRY(sort_keys(*keys, ne, 2 * k, sc, stream, &perm, &s));
-            uint32_t *w_s;
-            KTG_TRY(sc.alloc(&w_s, ne));
-            gather_kernel<uint32_t><<<export_grid(ne), 256, 0, stream>>>(d_w, perm, w_s, ne);
-            prof.end(stream);
-            *keys = s;
-            *weights = w_s;
-        }
-        KTG_CUDA(cudaGetLastError());
+        if (sorted) KTG_TRY(sort_device_edges(sc, keys, weights, ne));
         return KTG_OK;
+    }
+
+    int edges_to_host(uint64_t *d_hi, uint64_t *d_lo, uint32_t *d_w, uint64_t ne, int sorted, uint64_t *hi, uint64_t *lo,
+                      uint32_t *w, uint64_t cap) override {
+        Scratch sc;
+        KeyArr keys{d_hi, d_lo};
+        if (sorted) KTG_TRY(sort_device_edges(sc, &keys, &d_w, ne));
+        const uint64_t m = std::min(ne, cap);
+        if (m == 0) return sync();
+        KTG_CUDA(cudaMemcpyAsync(lo, keys.lo, m * 8, cudaMemcpyDeviceToHost, stream));
+        KTG_CUDA(cudaMemcpyAsync(w, d_w, m * 4, cudaMemcpyDeviceToHost, stream));
+        if (hi) {
+            if (keys.hi) KTG_CUDA(cudaMemcpyAsync(hi, keys.hi, m * 8, cudaMemcpyDeviceToHost, stream));
+            else memset(hi, 0, m * 8);
+        }
+        return sync(); // before the scratch buffers are freed
     }
 
     int export_edges(uint64_t *hi, uint64_t *lo, uint32_t *w, uint64_t cap, int sorted,
@@ -1465,57 +1512,57 @@ template <class K> struct Builder : BuilderBase {
         KeyArr keys;
         uint32_t *d_w;
         uint64_t ne = 0;
-        KTG_TRY(device_edges(sorted != 0, sc, &keys, &d_w, &ne));
+        KTG_TRY(device_edges(false, sc, &keys, &d_w, &ne));
         if (n_out) *n_out = ne;
-        const uint64_t m = std::min(ne, cap);
-        if (m == 0) return sync();
-        KTG_CUDA(cudaMemcpyAsync(lo, keys.lo, m * 8, cudaMemcpyDeviceToHost, stream));
-        KTG_CUDA(cudaMemcpyAsync(w, d_w, m * 4, cudaMemcpyDeviceToHost, stream));
-        if (hi) {
-            if (keys.hi) KTG_CUDA(cudaMemcpyAsync(hi, keys.hi, m * 8, cudaMemcpyDeviceToHost, stream));
-            else memset(hi, 0, m * 8);
-        }
-        return sync();
+        return edges_to_host(keys.hi, keys.lo, d_w, ne, sorted, hi, lo, w, cap);
     }
 
     // The input of Convert::create_from in a canonical numbering (export.cuh): sorted nodes,
     // sorted edges with the node indices of their prefix and suffix, edges as compress_edge bytes.
-    int export_graph(uint64_t *node_hi, uint64_t *node_lo, uint64_t n_nodes, uint64_t *src, uint64_t *dst,
-                     uint32_t *weight, uint8_t *edge_bytes, uint64_t n_edges) override {
-        Scratch sc;
-        KeyArr edges;
-        uint32_t *d_w;
-        uint64_t ne = 0;
-        KTG_TRY(device_edges(true, sc, &edges, &d_w, &ne));
-        if (ne != n_edges) return fail(KTG_ERR_INVALID, "n_edges is %llu, the graph has %llu edges (ktg_counts)",
-                                       (unsigned long long)n_edges, (unsigned long long)ne);
+    // From ne unsorted edges in device arrays of THIS device.  n_nodes / n_edges: what the caller
+    // allocated for (checked); *got_nodes / *got_edges (optional): what the graph has.
+    // sorted edges -> sorted distinct nodes and, if wanted, every edge's (prefix, suffix) node indices
+    int device_graph(Scratch &sc, const KeyArr &edges, uint64_t ne, KeyArr *nodes, uint64_t *nn, uint64_t **d_src, uint64_t **d_dst) {
         const bool wide_nodes = k - 1 > 32;
-        KeyArr nodes{nullptr, nullptr};
-        uint64_t nn = 0;
-        if (ne) {
-            KeyArr cand{nullptr, nullptr}, cand_sorted;
-            KTG_TRY(sc.alloc(&cand.lo, 2 * ne));
-            if (wide_nodes) KTG_TRY(sc.alloc(&cand.hi, 2 * ne));
-            prof.begin("graph_nodes", ne, stream);
-            split_nodes_kernel<<<export_grid(ne), 256, 0, stream>>>(edges.hi, edges.lo, ne, k, cand.hi, cand.lo);
-            uint32_t *perm;
-            KTG_TRY(sort_keys(cand, 2 * ne, 2 * (k - 1), sc, stream, &perm, &cand_sorted));
-            KTG_TRY(unique_sorted(cand_sorted, 2 * ne, sc, stream, &nodes, &nn));
+        *nodes = KeyArr{nullptr, nullptr};
+        *nn = 0;
+        if (!ne) return KTG_OK;
+        KeyArr cand{nullptr, nullptr}, cand_sorted;
+        KTG_TRY(sc.alloc(&cand.lo, 2 * ne));
+        if (wide_nodes) KTG_TRY(sc.alloc(&cand.hi, 2 * ne));
+        prof.begin("graph_nodes", ne, stream);
+        split_nodes_kernel<<<export_grid(ne), 256, 0, stream>>>(edges.hi, edges.lo, ne, k, cand.hi, cand.lo);
+        uint32_t *perm;
+        KTG_TRY(sort_keys(cand, 2 * ne, 2 * (k - 1), sc, stream, &perm, &cand_sorted));
+        KTG_TRY(unique_sorted(cand_sorted, 2 * ne, sc, stream, nodes, nn));
+        prof.end(stream);
+        if (d_src) {
+            KTG_TRY(sc.alloc(d_src, ne));
+            KTG_TRY(sc.alloc(d_dst, ne));
+            prof.begin("graph_ids", ne, stream);
+            node_ids_kernel<<<export_grid(ne), 256, 0, stream>>>(edges.hi, edges.lo, ne, k, nodes->hi, nodes->lo, *nn, *d_src, *d_dst);
             prof.end(stream);
         }
+        KTG_CUDA(cudaGetLastError());
+        return KTG_OK;
+    }
+
+    int graph_to_host(uint64_t *d_ehi, uint64_t *d_elo, uint32_t *d_w, uint64_t ne, uint64_t *node_hi, uint64_t *node_lo,
+                      uint64_t n_nodes, uint64_t *src, uint64_t *dst, uint32_t *weight, uint8_t *edge_bytes,
+                      uint64_t n_edges) override {
+        Scratch sc;
+        KeyArr edges{d_ehi, d_elo};
+        KTG_TRY(sort_device_edges(sc, &edges, &d_w, ne));
+        if (ne != n_edges) return fail(KTG_ERR_INVALID, "n_edges is %llu, the graph has %llu edges (ktg_counts)",
+                                       (unsigned long long)n_edges, (unsigned long long)ne);
+        KeyArr nodes{nullptr, nullptr};
+        uint64_t nn = 0, *d_src = nullptr, *d_dst = nullptr;
+        KTG_TRY(device_graph(sc, edges, ne, &nodes, &nn, (src || dst) ? &d_src : nullptr, &d_dst));
         if (nn != n_nodes) return fail(KTG_ERR_INVALID, "n_nodes is %llu, the graph has %llu nodes (ktg_counts)",
                                        (unsigned long long)n_nodes, (unsigned long long)nn);
         if (ne == 0) return sync();
-        if (src || dst) {
-            uint64_t *d_src, *d_dst;
-            KTG_TRY(sc.alloc(&d_src, ne));
-            KTG_TRY(sc.alloc(&d_dst, ne));
-            prof.begin("graph_ids", ne, stream);
-            node_ids_kernel<<<export_grid(ne), 256, 0, stream>>>(edges.hi, edges.lo, ne, k, nodes.hi, nodes.lo, nn, d_src, d_dst);
-            prof.end(stream);
-            if (src) KTG_CUDA(cudaMemcpyAsync(src, d_src, ne * 8, cudaMemcpyDeviceToHost, stream));
-            if (dst) KTG_CUDA(cudaMemcpyAsync(dst, d_dst, ne * 8, cudaMemcpyDeviceToHost, stream));
-        }
+        if (src) KTG_CUDA(cudaMemcpyAsync(src, d_src, ne * 8, cudaMemcpyDeviceToHost, stream));
+        if (dst) KTG_CUDA(cudaMemcpyAsync(dst, d_dst, ne * 8, cudaMemcpyDeviceToHost, stream));
         if (edge_bytes) {
             const size_t rec = (k + 3) / 4 + 1;
             uint8_t *d_b;
@@ -1533,6 +1580,70 @@ template <class K> struct Builder : BuilderBase {
         }
         KTG_CUDA(cudaGetLastError());
         return sync(); // before the scratch buffers are freed
+    }
+
+    // The seeds of remove_dead_paths (pruner.rs:165-195, `Externals`): in ascending node index (the
+    // numbering of graph_to_host), every node without an incoming edge as Input (kind 0), else every
+    // node without an outgoing edge as Output (kind 1).
+    int externals_to_host(uint64_t *d_ehi, uint64_t *d_elo, uint32_t *d_w, uint64_t ne, uint64_t *ids, uint8_t *kinds,
+                          uint64_t cap, uint64_t *n_out) override {
+        Scratch sc;
+        KeyArr edges{d_ehi, d_elo};
+        KTG_TRY(sort_device_edges(sc, &edges, &d_w, ne));
+        KeyArr nodes{nullptr, nullptr};
+        uint64_t nn = 0, *d_src = nullptr, *d_dst = nullptr;
+        KTG_TRY(device_graph(sc, edges, ne, &nodes, &nn, &d_src, &d_dst));
+        if (n_out) *n_out = 0;
+        if (nn == 0) return sync();
+        uint32_t *deg, *flag, *pos;
+        KTG_TRY(sc.alloc(&deg, nn));
+        KTG_TRY(sc.alloc(&flag, nn + 1));
+        KTG_TRY(sc.alloc(&pos, nn + 1));
+        KTG_CUDA(cudaMemsetAsync(deg, 0, nn * 4, stream));
+        prof.begin("externals", nn, stream);
+        mark_degrees_kernel<<<export_grid(ne), 256, 0, stream>>>(d_src, d_dst, ne, deg);
+        external_flags_kernel<<<export_grid(nn + 1), 256, 0, stream>>>(deg, nn, flag);
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, flag, pos, (int)(nn + 1), stream);
+        void *tmp;
+        KTG_TRY(sc.alloc((uint8_t **)&tmp, tb));
+        KTG_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, flag, pos, (int)(nn + 1), stream));
+        uint32_t total = 0;
+        KTG_CUDA(cudaMemcpyAsync(&total, pos + nn, 4, cudaMemcpyDeviceToHost, stream));
+        KTG_TRY(sync());
+        if (n_out) *n_out = total;
+        const uint64_t m = std::min<uint64_t>(total, cap);
+        if (m && ids && kinds) {
+            uint64_t *d_ids;
+            uint8_t *d_kinds;
+            KTG_TRY(sc.alloc(&d_ids, total));
+            KTG_TRY(sc.alloc(&d_kinds, total));
+            scatter_externals_kernel<<<export_grid(nn), 256, 0, stream>>>(deg, flag, pos, nn, d_ids, d_kinds);
+            KTG_CUDA(cudaMemcpyAsync(ids, d_ids, m * 8, cudaMemcpyDeviceToHost, stream));
+            KTG_CUDA(cudaMemcpyAsync(kinds, d_kinds, m, cudaMemcpyDeviceToHost, stream));
+        }
+        prof.end(stream);
+        KTG_CUDA(cudaGetLastError());
+        return sync();
+    }
+
+    int export_externals(uint64_t *ids, uint8_t *kinds, uint64_t cap, uint64_t *n_out) override {
+        Scratch sc;
+        KeyArr edges;
+        uint32_t *d_w;
+        uint64_t ne = 0;
+        KTG_TRY(device_edges(false, sc, &edges, &d_w, &ne));
+        return externals_to_host(edges.hi, edges.lo, d_w, ne, ids, kinds, cap, n_out);
+    }
+
+    int export_graph(uint64_t *node_hi, uint64_t *node_lo, uint64_t n_nodes, uint64_t *src, uint64_t *dst,
+                     uint32_t *weight, uint8_t *edge_bytes, uint64_t n_edges) override {
+        Scratch sc;
+        KeyArr edges;
+        uint32_t *d_w;
+        uint64_t ne = 0;
+        KTG_TRY(device_edges(false, sc, &edges, &d_w, &ne));
+        return graph_to_host(edges.hi, edges.lo, d_w, ne, node_hi, node_lo, n_nodes, src, dst, weight, edge_bytes, n_edges);
     }
 
     // ---- multi-GPU phases -------------------------------------------------------------------
@@ -1663,7 +1774,7 @@ template <class K> struct Builder : BuilderBase {
     // run padding of the exchange (PeerOut::pad), in keys: 128 bytes, unless all-ones is a real key
     uint32_t mg_pad() const {
         if (!rc && 2 * k == 8 * sizeof(K)) return 1;
-        if (getenv("KTG_MG_NOPAD")) return 1; // tuning knob
+        if (!tune.mg_pad) return 1;
         return 128 / sizeof(K);
     }
     unsigned long long *mg_cursors(uint32_t slot) { return (unsigned long long *)b_mg_cur.p + (size_t)slot * tab.world; }
@@ -1675,7 +1786,6 @@ template <class K> struct Builder : BuilderBase {
         // every (tile, owner) run may be rounded up by pad - 1 filler keys
         const uint64_t fillers = (max_windows / SCATTER_TILE + 1) * W * (mg_pad() - 1);
         *cap = bucket_cap_for(std::max<uint64_t>(max_windows + fillers, 1), W);
-        if ((double)*cap * W >= 4.0e9) return fail(KTG_ERR_INVALID, "batch too large: split it (32-bit bucket positions)");
         return KTG_OK;
     }
     // would mg_prepare(max_windows) replace the receive buffer?  (peers must unmap it first)
@@ -1842,7 +1952,6 @@ template <class K> struct Builder : BuilderBase {
         // spill route.  Every (tile, owner) run may be rounded up by SKM_PAD - 1 fillers.
         const uint64_t fillers = (max_windows / (SKM_W * SCATTER_THREADS) + 1) * W * (SKM_PAD - 1);
         *cap = bucket_cap_for(std::max<uint64_t>(max_windows / 4 + fillers, 1), W);
-        if ((double)*cap * W >= 4.0e9) return fail(KTG_ERR_INVALID, "batch too large: split it (32-bit bucket positions)");
         return KTG_OK;
     }
     int mg_skm_plan(uint64_t max_windows, int *needs_realloc) override {
@@ -1921,8 +2030,7 @@ template <class K> struct Builder : BuilderBase {
         const size_t ss = ScatterSmem<u128, SCATTER_TILE>::bytes(W, false);
         const uint64_t n_tiles = std::max<uint64_t>(1, (sv.n_items + SCATTER_THREADS * SKM_IPL - 1) / (SCATTER_THREADS * SKM_IPL));
         int g = (int)std::min<uint64_t>(grid_for(scatter_superkmers_kernel, SCATTER_THREADS, ss, props), n_tiles);
-        if (const char *e = getenv("KTG_P2P_CTAS")) // tuning knob
-            if (atoi(e) > 0) g = (int)std::min<uint64_t>(g, (uint64_t)props.sms * atoi(e));
+        if (tune.p2p_ctas > 0) g = (int)std::min<uint64_t>(g, (uint64_t)props.sms * tune.p2p_ctas);
         prof.begin("scatter_superkmers_p2p", bt.windows, stream);
         scatter_superkmers_kernel<<<g, SCATTER_THREADS, ss, stream>>>(sv, k, W, so, po, kc);
         prof.end(stream);
@@ -1932,38 +2040,22 @@ template <class K> struct Builder : BuilderBase {
         return KTG_OK;
     }
 
-    // records [q*cap, ends[q]) for q < n_buckets -> flat keys -> staged by sub-table (+ sketch)
-    DeviceBuf b_skm_keys;
+    // records [q*cap, ends[q]) for q < n_buckets -> canonical k-mers -> staged by sub-table (+ sketch),
+    // one kernel (superkmer.cuh: scatter_records_kernel)
     int skm_unroll(const u128 *rx, const unsigned long long *ends, uint64_t cap, uint32_t n_buckets, uint64_t n_keys_ub) {
         if constexpr (sizeof(K) == 8) {
-            const uint64_t tiles_per_bucket = cap / UNROLL_THREADS, n_rtiles = tiles_per_bucket * n_buckets;
+            const uint64_t n_rtiles = (cap / SREC_THREADS + 1) * n_buckets;
             if ((double)n_rtiles >= 4.0e9) return fail(KTG_ERR_INVALID, "batch too large: split it");
-            // every warp leaves half a chunk of fillers behind on average: no more CTAs than it takes
-            int ug = (int)std::min<uint64_t>((uint64_t)props.sms * 8, std::max<uint64_t>(n_rtiles, 1));
-            // fillers included (see unroll_records_kernel), in whole tiles of the scatter
-            const uint64_t cap1 = (unroll_out_cap(n_keys_ub, (uint64_t)ug * (UNROLL_THREADS / 32)) + L2S_TILE - 1) / L2S_TILE * L2S_TILE;
-            if ((double)cap1 >= 4.0e9) return fail(KTG_ERR_INVALID, "batch too large: split it (32-bit bucket positions)");
-            KTG_TRY(b_skm_keys.ensure(cap1 * sizeof(K) + 64));
-            unsigned long long *n_keys = skm_scalar(2);
-            KTG_CUDA(cudaMemsetAsync(n_keys, 0, 8, stream));
-            prof.begin("unroll_records", n_keys_ub, stream);
-            if (rc)
-                unroll_records_kernel<true><<<ug, UNROLL_THREADS, 0, stream>>>(rx, ends, cap, n_buckets, k,
-                                                                              (uint64_t *)b_skm_keys.p, n_keys, cap1);
-            else
-                unroll_records_kernel<false><<<ug, UNROLL_THREADS, 0, stream>>>(rx, ends, cap, n_buckets, k,
-                                                                               (uint64_t *)b_skm_keys.p, n_keys, cap1);
-            prof.end(stream);
             KTG_TRY(stage_add(n_keys_ub, [&](uint32_t n_bins, const ScatterOut &o) -> int {
-                // the flat array is ONE level-1 bucket whose fill is the device-side key count
-                const uint64_t n_tiles = cap1 / L2S_TILE;
-                const size_t ss = ScatterSmem<K, L2S_TILE>::bytes(n_bins, false);
-                auto kern = scatter_buckets_kernel<K, 1, L2S_THREADS, L2S_PER, 2, true>;
-                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ScatterSmem<K, L2S_TILE>::bytes(MAX_BINS, false));
-                int g = (int)std::min<uint64_t>(grid_for(kern, L2S_THREADS, ss, props), n_tiles);
-                prof.begin("scatter_received", n_keys_ub, stream);
-                kern<<<g, L2S_THREADS, ss, stream>>>((const K *)b_skm_keys.p, n_keys, cap1, n_tiles, n_tiles, 0, true, tab, o,
-                                                     (uint32_t *)b_hll.p);
+                const size_t ss = ScatterSmem<K, SREC_TILE>::bytes(n_bins, false);
+                auto launch = [&](auto kern) {
+                    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ScatterSmem<K, SREC_TILE>::bytes(MAX_BINS, false));
+                    int g = (int)std::min<uint64_t>(grid_for(kern, SREC_THREADS, ss, props), std::max<uint64_t>(n_rtiles, 1));
+                    kern<<<g, SREC_THREADS, ss, stream>>>(rx, ends, cap, n_buckets, k, tab, o, (uint32_t *)b_hll.p);
+                };
+                prof.begin("scatter_records", n_keys_ub, stream);
+                if (rc) launch(scatter_records_kernel<true>);
+                else launch(scatter_records_kernel<false>);
                 prof.end(stream);
                 return KTG_OK;
             }));
@@ -2044,7 +2136,7 @@ template <class K> struct Builder : BuilderBase {
         const unsigned long long end = n;
         KTG_CUDA(cudaMemcpyAsync(skm_scalar(1), &end, 8, cudaMemcpyHostToDevice, stream));
         KTG_TRY(sync()); // `end` is on this stack frame
-        const uint64_t cap = (n + UNROLL_THREADS - 1) / UNROLL_THREADS * UNROLL_THREADS;
+        const uint64_t cap = (n + SREC_THREADS - 1) / SREC_THREADS * SREC_THREADS;
         KTG_TRY(skm_unroll((const u128 *)d_records, skm_scalar(1), cap, 1, n * SKM_W));
         KTG_TRY(sync()); // the caller may free the records
         return KTG_OK;
@@ -2063,7 +2155,7 @@ template <class K> struct Builder : BuilderBase {
             K r = revcomp(key, k);
             if (r < key) key = r;
         }
-        return place_of(T::hash(key), tab.world, tab.n_sub).owner;
+        return place_of(T::place_hash(key), tab.world, tab.n_sub).owner;
     }
 
     int info(ktg_info *out) override {
@@ -2073,9 +2165,9 @@ template <class K> struct Builder : BuilderBase {
         KTG_TRY(count_occupied(&occ));
         out->capacity_slots = tab.capacity();
         out->occupied_slots = occ;
-        out->table_bytes = (tab.capacity() + 1) * sizeof(Slot);
+        out->table_bytes = tab.bytes();
         out->n_sub_tables = tab.n_sub;
-        out->slot_bytes = sizeof(Slot);
+        out->slot_bytes = Table<K>::SLOT_BYTES;
         out->windows_inserted = windows_inserted;
         out->kernel_launches = prof.total_launches;
         out->grow_events = grow_events;

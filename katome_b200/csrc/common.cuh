@@ -25,11 +25,7 @@ __host__ __device__ __forceinline__ uint64_t fmix64(uint64_t z) {
 __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
     return fmix64(x + 0x9E3779B97F4A7C15ull);
 }
-// Placement hash: two multiply / fold rounds (a shift by 32 is a register move,
-// so this is ~8 SASS instructions against ~20 for fmix64, and the hash is
-// computed three times per window: L1 scatter, L2 scatter, page update).  It only
-// decides WHERE a key lives, never a result; its uniformity on sequential, shifted,
-// low-complexity and tandem-repeat key sets is checked in tests/test_hashing.py.
+// 64-bit mixer of the multi-GPU control paths and tests (two multiply / fold rounds)
 __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
     x *= 0x9E3779B97F4A7C15ull;
     x ^= x >> 32;
@@ -64,16 +60,28 @@ __host__ __device__ __forceinline__ u128 revcomp(u128 x, uint32_t k) {
     return r >> (128 - 2 * k);
 }
 
-// Slot hash: murmur3's 32-bit finalizer over a multiplicative fold of the key
-// words.  Owner rank and sub-table come from the top bits of mix64; the slot
-// (and with it the page) comes from this cheaper, independent function, because
-// the level-2 scatter and the page update need nothing else (9 instructions
-// instead of 17 per key and pass).
-__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
+// Two independent 32-bit hashes of a key place it (they only decide WHERE a key lives, never a
+// result; uniformity on sequential, shifted, low-complexity and tandem-repeat key sets is checked
+// in tests/test_hashing.py against the numpy mirror katome_b200/hashing.py):
+//   place_hash  owner rank and sub-table (level-1 bin), through place_of;
+//   slot_hash   home slot inside the sub-table; its high bits are the PAGE (level-2 bin).
+// Each is a 32-bit finalizer over a multiplicative fold of the key words: 9 instructions, against
+// ~20 for a 64-bit mixer (the level-1 scatter spent 15 % of its instructions on two 64-bit
+// multiplies per window in round 1).  The folds are different linear forms of the words, so that
+// keys that collide under one do not collide under the other.
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) { // murmur3 finalizer
     x ^= x >> 16;
     x *= 0x85EBCA6Bu;
     x ^= x >> 13;
     x *= 0xC2B2AE35u;
+    x ^= x >> 16;
+    return x;
+}
+__host__ __device__ __forceinline__ uint32_t mix32b(uint32_t x) { // "lowbias32" constants
+    x ^= x >> 16;
+    x *= 0x7FEB352Du;
+    x ^= x >> 15;
+    x *= 0x846CA68Bu;
     x ^= x >> 16;
     return x;
 }
@@ -82,49 +90,43 @@ template <class K> struct KeyTraits;
 
 template <> struct KeyTraits<uint64_t> {
     static constexpr int WORDS = 1;
-    struct alignas(16) Slot {
-        uint64_t key;
-        uint32_t w;
-        uint32_t aux;
-    };
     __host__ __device__ static __forceinline__ uint64_t empty() { return ~0ull; }
-    __host__ __device__ static __forceinline__ uint64_t hash(uint64_t k) { return mix64(k); }
+    __host__ __device__ static __forceinline__ uint32_t place_hash(uint64_t k) {
+        return mix32b((uint32_t)(k >> 32) + (uint32_t)k * 0x85EBCA77u);
+    }
     __host__ __device__ static __forceinline__ uint32_t slot_hash(uint64_t k) {
         return mix32((uint32_t)k + (uint32_t)(k >> 32) * 0x9E3779B1u);
     }
+    // 64 well mixed bits (cardinality sketch, sampled keys only)
+    __host__ __device__ static __forceinline__ uint64_t hash64(uint64_t k) { return fmix64(k ^ 0x9E3779B97F4A7C15ull); }
     __host__ __device__ static __forceinline__ uint64_t hi(uint64_t) { return 0; }
     __host__ __device__ static __forceinline__ uint64_t lo(uint64_t k) { return k; }
     __host__ __device__ static __forceinline__ uint64_t make(uint64_t, uint64_t lo_) { return lo_; }
 #ifdef __CUDACC__
-    __device__ static __forceinline__ uint64_t load(const Slot *s) {
-        return __ldcg((const unsigned long long *)&s->key);
-    }
+    __device__ static __forceinline__ uint64_t load(const uint64_t *p) { return __ldcg((const unsigned long long *)p); }
     __device__ static __forceinline__ uint64_t load_stream(const uint64_t *p) { // read once
         return __ldcs((const unsigned long long *)p);
     }
     __device__ static __forceinline__ bool maybe_torn(uint64_t) { return false; }
-    __device__ static __forceinline__ uint64_t cas(Slot *s, uint64_t cmp, uint64_t val) {
-        return atomicCAS((unsigned long long *)&s->key, (unsigned long long)cmp,
-                         (unsigned long long)val);
+    __device__ static __forceinline__ uint64_t cas(uint64_t *p, uint64_t cmp, uint64_t val) {
+        return atomicCAS((unsigned long long *)p, (unsigned long long)cmp, (unsigned long long)val);
     }
-    __device__ static __forceinline__ void store_key(Slot *s, uint64_t k) { s->key = k; }
 #endif
 };
 
 template <> struct KeyTraits<u128> {
     static constexpr int WORDS = 2;
-    struct alignas(32) Slot {
-        uint64_t lo, hi;
-        uint32_t w;
-        uint32_t aux[3];
-    };
     __host__ __device__ static __forceinline__ u128 empty() { return ~(u128)0; }
-    __host__ __device__ static __forceinline__ uint64_t hash(u128 k) {
-        return mix64((uint64_t)k ^ ((uint64_t)(k >> 64) * 0xA24BAED4963EE407ull));
+    __host__ __device__ static __forceinline__ uint32_t place_hash(u128 k) {
+        return mix32b((uint32_t)(k >> 96) + (uint32_t)(k >> 64) * 0x85EBCA77u + (uint32_t)(k >> 32) * 0xC2B2AE3Du +
+                      (uint32_t)k * 0x27D4EB2Fu);
     }
     __host__ __device__ static __forceinline__ uint32_t slot_hash(u128 k) {
         return mix32((uint32_t)k + (uint32_t)(k >> 32) * 0x9E3779B1u + (uint32_t)(k >> 64) * 0x85EBCA77u +
                      (uint32_t)(k >> 96) * 0xC2B2AE3Du);
+    }
+    __host__ __device__ static __forceinline__ uint64_t hash64(u128 k) {
+        return fmix64((uint64_t)k ^ ((uint64_t)(k >> 64) * 0xA24BAED4963EE407ull) ^ 0x9E3779B97F4A7C15ull);
     }
     __host__ __device__ static __forceinline__ uint64_t hi(u128 k) { return (uint64_t)(k >> 64); }
     __host__ __device__ static __forceinline__ uint64_t lo(u128 k) { return (uint64_t)k; }
@@ -132,8 +134,8 @@ template <> struct KeyTraits<u128> {
         return ((u128)hi_ << 64) | lo_;
     }
 #ifdef __CUDACC__
-    __device__ static __forceinline__ u128 load(const Slot *s) {
-        ulonglong2 v = __ldcg((const ulonglong2 *)s);
+    __device__ static __forceinline__ u128 load(const u128 *p) {
+        ulonglong2 v = __ldcg((const ulonglong2 *)p);
         return ((u128)v.y << 64) | v.x;
     }
     __device__ static __forceinline__ u128 load_stream(const u128 *p) {
@@ -146,7 +148,7 @@ template <> struct KeyTraits<u128> {
     __device__ static __forceinline__ bool maybe_torn(u128 k) {
         return (uint64_t)k == ~0ull || (uint64_t)(k >> 64) == ~0ull;
     }
-    __device__ static __forceinline__ u128 cas(Slot *s, u128 cmp, u128 val) {
+    __device__ static __forceinline__ u128 cas(u128 *p, u128 cmp, u128 val) {
         uint64_t olo, ohi;
         asm volatile(
             "{\n\t"
@@ -158,13 +160,9 @@ template <> struct KeyTraits<u128> {
             "}\n"
             : "=l"(olo), "=l"(ohi)
             : "l"((uint64_t)cmp), "l"((uint64_t)(cmp >> 64)), "l"((uint64_t)val),
-              "l"((uint64_t)(val >> 64)), "l"(s)
+              "l"((uint64_t)(val >> 64)), "l"(p)
             : "memory");
         return ((u128)ohi << 64) | olo;
-    }
-    __device__ static __forceinline__ void store_key(Slot *s, u128 k) {
-        s->lo = (uint64_t)k;
-        s->hi = (uint64_t)(k >> 64);
     }
 #endif
 };
@@ -173,22 +171,28 @@ template <> struct KeyTraits<u128> {
 // L2-resident partition, = level-1 bin of the partitioner) and home slot inside
 // it (slot_hash & sub_mask); the high bits of the slot select the PAGE (the shared-memory sized unit of
 // the streaming update, = level-2 bin) and linear probing wraps inside the page.
-// Disjoint pieces of one 64-bit hash, range-reduced by multiply-shift so that
-// world and n_sub need not be powers of two.
+// Owner and sub-table are disjoint pieces of place_hash, range-reduced by multiply-shift so that
+// world and n_sub need not be powers of two; its low 9 bits pick the keys the sketch samples.
 struct Place {
     uint32_t owner, part;
 };
-__host__ __device__ __forceinline__ Place place_of(uint64_t h, uint32_t world, uint32_t n_sub) {
-    uint32_t hi = (uint32_t)(h >> 32);
-    uint64_t t = (uint64_t)hi * world;
+__host__ __device__ __forceinline__ Place place_of(uint32_t h, uint32_t world, uint32_t n_sub) {
+    uint64_t t = (uint64_t)h * world;
     Place p;
     p.owner = (uint32_t)(t >> 32);
     p.part = (uint32_t)(((uint64_t)(uint32_t)t * n_sub) >> 32);
     return p;
 }
 
+// The edge table in HBM: open addressing, linear probing inside a page.  Structure of arrays PER
+// PAGE -- page g is [2^page_log2 keys | 2^page_log2 u32 weights], 12 bytes per slot for u64 keys and
+// 20 for u128 -- which is exactly the image the page update keeps in shared memory, so a page
+// moves between HBM and an SM as ONE bulk copy each way (cp.async.bulk), the weight-only passes
+// (filter, standardize, node statistics) read 4 bytes per slot, and nothing is spent on padding
+// (round 1 had 16 / 32-byte array-of-structs slots).  One "special" entry past the last page holds
+// the weight of the all-ones key (T...T at full key width without canonicalisation).
 template <class K> struct Table {
-    typename KeyTraits<K>::Slot *slots; // n_sub << sub_log2 slots + 1 special slot
+    unsigned char *base; // n_pages() pages, then the special weight (16 bytes)
     uint32_t n_sub, sub_log2, sub_mask;
     uint32_t page_log2, page_mask; // page_log2 <= sub_log2; probing wraps inside a page
     uint32_t world, rank;
@@ -198,9 +202,20 @@ template <class K> struct Table {
     uint32_t *ovf_inc;
     unsigned long long *ovf_count;
     uint64_t ovf_cap;
+    static constexpr uint32_t SLOT_BYTES = sizeof(K) + 4;
     __host__ __device__ uint64_t capacity() const { return (uint64_t)n_sub << sub_log2; }
     __host__ __device__ uint32_t pages_per_sub() const { return 1u << (sub_log2 - page_log2); }
     __host__ __device__ uint64_t n_pages() const { return (uint64_t)n_sub << (sub_log2 - page_log2); }
+    __host__ __device__ uint64_t page_bytes() const { return (uint64_t)SLOT_BYTES << page_log2; }
+    __host__ __device__ uint64_t bytes() const { return n_pages() * page_bytes() + 16; }
+    __host__ __device__ K *page_keys(uint64_t g) const { return (K *)(base + g * page_bytes()); }
+    __host__ __device__ uint32_t *page_weights(uint64_t g) const {
+        return (uint32_t *)(base + g * page_bytes() + ((uint64_t)sizeof(K) << page_log2));
+    }
+    // slot i of the whole table, i < capacity()
+    __host__ __device__ K *key_ptr(uint64_t i) const { return page_keys(i >> page_log2) + (i & page_mask); }
+    __host__ __device__ uint32_t *w_ptr(uint64_t i) const { return page_weights(i >> page_log2) + (i & page_mask); }
+    __host__ __device__ uint32_t *special_w() const { return (uint32_t *)(base + n_pages() * page_bytes()); }
 };
 
 #ifdef __CUDACC__
@@ -209,22 +224,22 @@ template <class K> struct Table {
 template <class K>
 __device__ __forceinline__ void table_add(const Table<K> &t, K key, uint32_t inc) {
     typedef KeyTraits<K> T;
-    typedef typename T::Slot Slot;
     const K EMPTY = T::empty();
     if (key == EMPTY) { // all-T at full key width (only without canonicalisation)
-        atomicAdd(&t.slots[t.capacity()].w, inc);
+        atomicAdd(t.special_w(), inc);
         return;
     }
-    const Place p = place_of(T::hash(key), t.world, t.n_sub);
+    const Place p = place_of(T::place_hash(key), t.world, t.n_sub);
     const uint32_t slot = T::slot_hash(key) & t.sub_mask;
-    Slot *page = t.slots + ((uint64_t)p.part << t.sub_log2) + (slot & ~t.page_mask);
+    const uint64_t g = (((uint64_t)p.part << t.sub_log2) + slot) >> t.page_log2;
+    K *pk = t.page_keys(g);
+    uint32_t *pw = t.page_weights(g);
     uint32_t i = slot & t.page_mask;
     for (uint32_t n = 0; n < t.max_probe; ++n) {
-        Slot *s = page + i;
-        K cur = T::load(s);
-        if (cur != key && (cur == EMPTY || T::maybe_torn(cur))) cur = T::cas(s, EMPTY, key);
+        K cur = T::load(pk + i);
+        if (cur != key && (cur == EMPTY || T::maybe_torn(cur))) cur = T::cas(pk + i, EMPTY, key);
         if (cur == key || cur == EMPTY) {
-            atomicAdd(&s->w, inc);
+            atomicAdd(pw + i, inc);
             return;
         }
         i = (i + 1) & t.page_mask;

@@ -105,6 +105,32 @@ __global__ void edge_bytes_kernel(const uint64_t *__restrict__ e_hi, const uint6
     }
 }
 
+// ---- Externals (pruner.rs:165-195): nodes without an incoming edge (Input), else without an outgoing
+// edge (Output), in node index order.  deg[v] bit 0: v has an outgoing edge, bit 1: an incoming one.
+__global__ void mark_degrees_kernel(const uint64_t *__restrict__ src, const uint64_t *__restrict__ dst, uint64_t n_edges,
+                                    uint32_t *__restrict__ deg) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += stride) {
+        atomicOr(&deg[src[e]], 1u);
+        atomicOr(&deg[dst[e]], 2u);
+    }
+}
+__global__ void external_flags_kernel(const uint32_t *__restrict__ deg, uint64_t n_nodes, uint32_t *__restrict__ flag) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v <= n_nodes; v += stride)
+        flag[v] = v < n_nodes && deg[v] != 3u;
+}
+__global__ void scatter_externals_kernel(const uint32_t *__restrict__ deg, const uint32_t *__restrict__ flag,
+                                         const uint32_t *__restrict__ pos, uint64_t n_nodes, uint64_t *__restrict__ ids,
+                                         uint8_t *__restrict__ kinds) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_nodes; v += stride)
+        if (flag[v]) {
+            ids[pos[v]] = v;
+            kinds[pos[v]] = (deg[v] & 2u) ? 1 : 0; // no incoming edge: Input, whatever goes out (pruner.rs:181-186)
+        }
+}
+
 // ---- host helpers -------------------------------------------------------------------------
 struct Scratch { // device allocations of one export, freed together
     std::vector<void *> ptrs;

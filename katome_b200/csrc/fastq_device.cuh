@@ -1,4 +1,4 @@
-// fastq_device.cuh -- FASTQ record parsing on the device.
+// fastq_device.cuh -- FASTQ and FASTA record parsing on the device.
 //
 // Replaces the record iteration of create_fastq (algorithms/builder.rs:142-160), i.e. rust-bio
 // 0.10's fastq::Reader (Cargo.lock:22-25; restated for the host in host_reader.h): strict 4-line
@@ -129,6 +129,89 @@ fq_gather_kernel(const uint8_t *__restrict__ raw, const uint32_t *__restrict__ s
         const uint64_t o = offsets[r], len = offsets[r + 1] - o;
         const uint8_t *src = raw + seq_start[r];
         for (uint64_t i = lane; i < len; i += 32) dense[o + i] = src[i];
+    }
+}
+
+// ---- FASTA (create_fasta, builder.rs:118-140; rust-bio 0.10's fasta::Reader restated in host_reader.h):
+// a line that starts with '>' opens a record, every other line is appended to the open record after
+// trimming trailing whitespace; the first line of a file must be a header.  A record is one read.
+// Lines are cut with the same newline index as FASTQ; two scans turn the per-line facts into the dense
+// batch: rec_idx = headers before the line, base_off = sequence bytes before the line.
+
+// one thread per line: hdr[i] (starts with '>'), len[i] (trimmed length, 0 for a header)
+__global__ void __launch_bounds__(256)
+fa_lines_kernel(const uint8_t *__restrict__ raw, const uint32_t *__restrict__ nl, uint64_t n_lines,
+                uint32_t *__restrict__ hdr, uint64_t *__restrict__ len) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n_lines; i += stride) {
+        if (i == n_lines) { // scan sentinels
+            hdr[i] = 0;
+            len[i] = 0;
+            continue;
+        }
+        const uint32_t s = i ? nl[i - 1] + 1 : 0;
+        uint32_t e = nl[i];
+        const bool h = raw[s] == '>';
+        while (e > s && fq_space(raw[e - 1])) --e;
+        hdr[i] = h;
+        len[i] = h ? 0 : e - s;
+    }
+}
+
+// offsets[r] = sequence bytes before record r, r <= n_rec; consumed = where the first record that is
+// NOT part of this batch starts (the header after the last complete record)
+__global__ void __launch_bounds__(256)
+fa_offsets_kernel(const uint32_t *__restrict__ nl, const uint32_t *__restrict__ hdr, const uint32_t *__restrict__ rec_idx,
+                  const uint64_t *__restrict__ base_off, uint64_t n_lines, uint64_t n_rec, uint64_t *__restrict__ offsets,
+                  FastqChunkInfo *info) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n_lines; i += stride) {
+        if (i == n_lines) {
+            if (rec_idx[i] == n_rec) offsets[n_rec] = base_off[i]; // the chunk ends with the file
+        }
+        else if (hdr[i] && rec_idx[i] <= n_rec) {
+            offsets[rec_idx[i]] = base_off[i];
+            if (rec_idx[i] == n_rec) info->consumed = i ? (unsigned long long)nl[i - 1] + 1 : 0ull;
+        }
+    }
+}
+
+// one warp per sequence line of a complete record
+__global__ void __launch_bounds__(256)
+fa_gather_kernel(const uint8_t *__restrict__ raw, const uint32_t *__restrict__ nl, const uint32_t *__restrict__ hdr,
+                 const uint32_t *__restrict__ rec_idx, const uint64_t *__restrict__ base_off, uint64_t n_lines, uint64_t n_rec,
+                 uint8_t *__restrict__ dense) {
+    const uint64_t warps = (uint64_t)gridDim.x * blockDim.x / 32;
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32; i < n_lines; i += warps) {
+        if (hdr[i] || rec_idx[i] == 0 || rec_idx[i] - 1 >= n_rec) continue;
+        const uint64_t o = base_off[i], len = base_off[i + 1] - o;
+        const uint8_t *src = raw + (i ? nl[i - 1] + 1 : 0);
+        for (uint64_t j = lane; j < len; j += 32) dense[o + j] = src[j];
+    }
+}
+
+// batch hint of the records: one length or ragged, windows if every read is accepted
+__global__ void __launch_bounds__(256)
+fa_hint_kernel(const uint64_t *__restrict__ offsets, uint64_t n_rec, uint32_t k, FastqChunkInfo *info) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long lmin = ~0ull, lmax = 0, wub = 0;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += stride) {
+        const unsigned long long len = offsets[r + 1] - offsets[r];
+        lmin = len < lmin ? len : lmin;
+        lmax = len > lmax ? len : lmax;
+        wub += len >= k ? len - k + 1 : 0;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long a = __shfl_xor_sync(0xFFFFFFFFu, lmin, o), b = __shfl_xor_sync(0xFFFFFFFFu, lmax, o);
+        lmin = a < lmin ? a : lmin;
+        lmax = b > lmax ? b : lmax;
+        wub += __shfl_xor_sync(0xFFFFFFFFu, wub, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&info->min_len, lmin);
+        atomicMax(&info->max_len, lmax);
+        if (wub) atomicAdd(&info->windows_ub, wub);
     }
 }
 

@@ -231,8 +231,8 @@ template <class K> struct Roller {
 // the scatter kernel's instructions).
 constexpr uint32_t HLL_P = 12, HLL_M = 1u << HLL_P, HLL_SAMPLE = 512;
 
-__device__ __forceinline__ void hll_insert(uint32_t *regs, uint64_t h) {
-    uint64_t g = fmix64(h ^ 0x9E3779B97F4A7C15ull);
+// g: 64 well mixed bits of the key (KeyTraits::hash64), independent of the bits that place it
+__device__ __forceinline__ void hll_insert(uint32_t *regs, uint64_t g) {
     uint32_t idx = (uint32_t)(g >> (64 - HLL_P));
     uint64_t rest = g << HLL_P;
     uint32_t rank = rest ? (uint32_t)__clzll((long long)rest) + 1u : 64u - HLL_P + 1u;
@@ -242,11 +242,12 @@ __global__ void hll_merge_kernel(uint32_t *__restrict__ dst, const uint32_t *__r
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < HLL_M && src[i] > dst[i]) atomicMax(&dst[i], src[i]);
 }
-__device__ __forceinline__ bool hll_sampled(uint64_t h) { return ((uint32_t)h >> 23) == 0; } // 1 / HLL_SAMPLE
-__device__ __forceinline__ void hll_update(uint32_t *regs, uint64_t h, bool valid = true) {
-    const bool s = valid && hll_sampled(h);
+// ph: the key's place_hash; owner and sub-table come from its high bits, the sample from its low 9
+__device__ __forceinline__ bool hll_sampled(uint32_t ph) { return (ph & (HLL_SAMPLE - 1u)) == 0; }
+template <class K> __device__ __forceinline__ void hll_update(uint32_t *regs, K key, uint32_t ph, bool valid = true) {
+    const bool s = valid && hll_sampled(ph);
     if (__any_sync(__activemask(), s)) {
-        if (s) hll_insert(regs, h);
+        if (s) hll_insert(regs, KeyTraits<K>::hash64(key));
     }
 }
 // one vote for the PER keys a lane handles in a tile; mask bit j = key j is sampled
@@ -255,7 +256,7 @@ __device__ __forceinline__ void hll_update_tile(uint32_t *regs, const K (&key)[P
     if (__any_sync(0xFFFFFFFFu, mask != 0)) {
 #pragma unroll
         for (int j = 0; j < PER; ++j)
-            if (mask & (1u << j)) hll_insert(regs, KeyTraits<K>::hash(key[j]));
+            if (mask & (1u << j)) hll_insert(regs, KeyTraits<K>::hash64(key[j]));
     }
 }
 
@@ -386,7 +387,10 @@ hll_reads_kernel(ReadView v, uint32_t k, uint32_t *__restrict__ g_regs) {
         iw.load(v, it, k);
 #pragma unroll
         for (int j = 0; j < GRAN; ++j) {
-            hll_update(regs, KeyTraits<K>::hash(iw.template key<RC>()), (iw.mask >> j) & 1u);
+            {
+                const K key = iw.template key<RC>();
+                hll_update(regs, key, KeyTraits<K>::place_hash(key), (iw.mask >> j) & 1u);
+            }
             iw.r.step();
         }
     }
@@ -403,7 +407,7 @@ hll_keys_kernel(const K *__restrict__ keys, uint64_t n, uint32_t *__restrict__ g
     __syncthreads();
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        hll_update(regs, KeyTraits<K>::hash(keys[i]));
+        hll_update(regs, keys[i], KeyTraits<K>::place_hash(keys[i]));
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < HLL_M; i += blockDim.x)
         if (regs[i]) atomicMax(&g_regs[i], regs[i]);
@@ -429,10 +433,11 @@ hist_reads_kernel(ReadView v, uint32_t k, Table<K> t, uint32_t n_bins,
 #pragma unroll
         for (int j = 0; j < GRAN; ++j) {
             if (iw.mask & (1u << j)) {
-                uint64_t h = KeyTraits<K>::hash(iw.template key<RC>());
+                const K key = iw.template key<RC>();
+                const uint32_t h = KeyTraits<K>::place_hash(key);
                 Place p = place_of(h, t.world, t.n_sub);
                 atomicAdd(&sh_hist[BY_OWNER ? p.owner : p.part], 1u);
-                if (HLL) hll_update(regs, h);
+                if (HLL) hll_update(regs, key, h);
             }
             iw.r.step();
         }
@@ -455,10 +460,10 @@ hist_keys_kernel(const K *__restrict__ keys, uint64_t n, Table<K> t, uint32_t n_
     __syncthreads();
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        uint64_t h = KeyTraits<K>::hash(keys[i]);
+        const uint32_t h = KeyTraits<K>::place_hash(keys[i]);
         Place p = place_of(h, t.world, t.n_sub);
         atomicAdd(&sh_hist[BY_OWNER ? p.owner : p.part], 1u);
-        if (HLL) hll_update(regs, h);
+        if (HLL) hll_update(regs, keys[i], h);
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < n_bins; i += blockDim.x)
@@ -545,24 +550,24 @@ __device__ unsigned long long g_phase_cycles[8];
 #endif
 
 template <class K, int TILE> struct ScatterSmem {
-    K *keys;                   // TILE
-    uint32_t *delta;           // TILE: output position minus position in the sorted tile
-    uint32_t *cnt;             // 2 x n_bins (double buffered)
-    uint2 *ld;                 // n_bins: {start in the sorted tile, output position minus that start}
-    unsigned long long *glob;  // n_bins: reserved start in the bin's HBM range
-    unsigned long long *spill; // n_bins: reserved start in the overflow array
-    uint32_t *regs;            // HLL_M (only with HLL)
-    __device__ __forceinline__ void carve(unsigned char *base, uint32_t n_bins) {
+    K *keys;                    // TILE: the tile sorted by bin
+    unsigned long long *gdelta; // n_bins: output position of the bin's run minus its start in the sorted tile
+    unsigned long long *spill;  // n_bins: reserved start in the overflow array
+    uint32_t *start;            // n_bins: start of the bin's run in the sorted tile
+    uint32_t *cnt;              // 2 x n_bins (double buffered)
+    uint32_t *regs;             // HLL_M (only with HLL)
+    uint16_t *binof;            // TILE: bin of every key of the sorted tile
+    __device__ __forceinline__ void carve(unsigned char *base, uint32_t n_bins, bool hll) {
         keys = (K *)base;
-        glob = (unsigned long long *)(keys + TILE);
-        spill = glob + n_bins;
-        ld = (uint2 *)(spill + n_bins);
-        delta = (uint32_t *)(ld + n_bins);
-        cnt = delta + TILE;
+        gdelta = (unsigned long long *)(keys + TILE);
+        spill = gdelta + n_bins;
+        start = (uint32_t *)(spill + n_bins);
+        cnt = start + n_bins;
         regs = cnt + 2 * n_bins;
+        binof = (uint16_t *)(regs + (hll ? HLL_M : 0));
     }
     static size_t bytes(uint32_t n_bins, bool hll) {
-        return (size_t)TILE * (sizeof(K) + 4) + (size_t)n_bins * 32 + (hll ? HLL_M * 4 : 0);
+        return (size_t)TILE * (sizeof(K) + 2) + (size_t)n_bins * 28 + (hll ? HLL_M * 4 : 0);
     }
 };
 
@@ -591,8 +596,11 @@ struct ScatterOut {
     unsigned long long spill_cap;
 };
 
-// Preconditions: sm.cnt[parity] is zero, s_ovf == 0, the block is synchronised.
+// Preconditions: sm.cnt[parity] is zero, the block is synchronised.
 // Leaves sm.cnt[parity ^ 1] zeroed and the block synchronised.
+// Output positions are 64-bit (a stage may hold any number of keys): the sorted tile keeps the BIN of
+// every key (16 bits) and the copy-out adds the bin's 64-bit `gdelta`; neighbouring lanes mostly share
+// a bin, so that load is a broadcast.
 template <class K, int THREADS, int PER>
 __device__ __forceinline__ void tile_scatter(const K (&key)[PER], const uint32_t (&bin)[PER],
                                              uint32_t vmask, ScatterSmem<K, THREADS * PER> &sm,
@@ -617,6 +625,8 @@ __device__ __forceinline__ void tile_scatter(const K (&key)[PER], const uint32_t
         const uint32_t per = (n_bins + THREADS - 1) / THREADS;
         const uint32_t b0 = threadIdx.x * per;
         const bool one = per == 1; // the usual case: at most one bin per thread
+        // (a fast path for two bins per thread as well made the one-bin case 4 % slower and did not help at
+        // 316 bins: what makes the level-1 scatter twice as slow there is the run length, not the scan)
         uint32_t s = 0, c1 = 0;
         unsigned long long base1 = 0;
         const uint32_t padm = po ? po->pad - 1u : 0u; // reservations are rounded up to pad keys
@@ -651,7 +661,7 @@ __device__ __forceinline__ void tile_scatter(const K (&key)[PER], const uint32_t
             unsigned long long base = base1;
             if (c) {
                 if (!one) base = atomicAdd(&cursors[i], (unsigned long long)((c + padm) & ~padm));
-                sm.glob[i] = base;
+                sm.gdelta[i] = base - run;
                 if (o.bucket_cap) {
                     const unsigned long long lim = (bin_off + i + 1) * o.bucket_cap;
                     if (base + c > lim) {
@@ -661,7 +671,7 @@ __device__ __forceinline__ void tile_scatter(const K (&key)[PER], const uint32_t
                     }
                 }
             }
-            sm.ld[i] = make_uint2(run, (uint32_t)base - run);
+            sm.start[i] = run;
             run += c;
         }
     }
@@ -670,10 +680,9 @@ __device__ __forceinline__ void tile_scatter(const K (&key)[PER], const uint32_t
 #pragma unroll
     for (int j = 0; j < PER; ++j)
         if (vmask & (1u << j)) {
-            const uint2 v = sm.ld[bin[j]];
-            const uint32_t pos = v.x + rank[j];
+            const uint32_t pos = sm.start[bin[j]] + rank[j];
             sm.keys[pos] = key[j];
-            sm.delta[pos] = v.y;
+            sm.binof[pos] = (uint16_t)bin[j];
         }
     {   // the other counter buffer is free now: zero it for the next tile
         uint32_t *nxt = sm.cnt + (parity ^ 1u) * n_bins;
@@ -685,30 +694,24 @@ __device__ __forceinline__ void tile_scatter(const K (&key)[PER], const uint32_t
     K *out = (K *)o.out;
     if (!s_ovf && po) { // bins are owner-major: one contiguous range of the sorted tile per destination GPU
         for (uint32_t w = 0; w < po->world; ++w) {
-            const uint32_t beg = sm.ld[w * po->bins_per_owner].x;
-            const uint32_t end = w + 1 < po->world ? sm.ld[(w + 1) * po->bins_per_owner].x : total;
+            const uint32_t beg = sm.start[w * po->bins_per_owner];
+            const uint32_t end = w + 1 < po->world ? sm.start[(w + 1) * po->bins_per_owner] : total;
             K *dst = (K *)po->rxb[w];
-            for (uint32_t i = beg + threadIdx.x; i < end; i += THREADS) dst[(uint32_t)(sm.delta[i] + i)] = sm.keys[i];
+            for (uint32_t i = beg + threadIdx.x; i < end; i += THREADS) dst[sm.gdelta[sm.binof[i]] + i] = sm.keys[i];
         }
     }
     else if (!s_ovf) {
-        for (uint32_t i = threadIdx.x; i < total; i += THREADS) out[(uint32_t)(sm.delta[i] + i)] = sm.keys[i];
+        for (uint32_t i = threadIdx.x; i < total; i += THREADS) out[sm.gdelta[sm.binof[i]] + i] = sm.keys[i];
     }
-    else { // some bin of this tile ran past its bucket: find each key's bin again (rare)
+    else { // some bin of this tile ran past its bucket (rare)
         for (uint32_t i = threadIdx.x; i < total; i += THREADS) {
-            uint32_t lo = 0, hi = n_bins - 1; // last bin with loc <= i and a non-empty count
-            while (lo < hi) {
-                uint32_t mid = (lo + hi + 1) >> 1;
-                if (sm.ld[mid].x <= i) lo = mid;
-                else hi = mid - 1;
-            }
-            const uint32_t b = lo;
+            const uint32_t b = sm.binof[i];
             const unsigned long long lim = (bin_off + b + 1) * o.bucket_cap;
-            const unsigned long long dst = sm.glob[b] + (i - sm.ld[b].x);
+            const unsigned long long dst = sm.gdelta[b] + i, base = sm.gdelta[b] + sm.start[b];
             if (po) out = (K *)po->rxb[b / po->bins_per_owner];
             if (dst < lim) out[dst] = sm.keys[i];
             else {
-                const unsigned long long first = sm.glob[b] > lim ? sm.glob[b] : lim;
+                const unsigned long long first = base > lim ? base : lim;
                 const unsigned long long so = sm.spill[b] + (dst - first);
                 if (so < o.spill_cap) ((K *)o.spill_out)[so] = sm.keys[i];
             }
@@ -719,7 +722,7 @@ __device__ __forceinline__ void tile_scatter(const K (&key)[PER], const uint32_t
         for (uint32_t b = 0; b < n_bins; ++b) {
             const uint32_t c = cnt[b];
             if (c == 0 || (c & padm) == 0) continue;
-            const unsigned long long base = sm.glob[b], lim = (bin_off + b + 1) * o.bucket_cap;
+            const unsigned long long base = sm.gdelta[b] + sm.start[b], lim = (bin_off + b + 1) * o.bucket_cap;
             K *dst = (K *)po->rxb[b / po->bins_per_owner];
             for (uint32_t j = c + threadIdx.x; j < ((c + padm) & ~padm); j += THREADS)
                 if (base + j < lim) dst[base + j] = KeyTraits<K>::empty();
@@ -735,13 +738,20 @@ constexpr int SCATTER_THREADS = 256, SCATTER_PER = 8, SCATTER_TILE = SCATTER_THR
 // rank -- into a local array for an NCCL exchange (po.world == 0) or straight into the
 // owners' receive buckets over NVLink (po).
 constexpr int BIN_PART = 0, BIN_OWNER = 1;
-template <class K, bool RC, int BINS, bool HLL>
-__global__ void __launch_bounds__(SCATTER_THREADS, (BINS == BIN_OWNER || sizeof(K) == 8) ? 4 : 3)
+// PER: keys per lane and tile.  A work item is GRAN = 8 window starts; with PER = 4 it is partitioned in
+// two passes of 4 keys (the rolling state survives the tile scatter in between).  That keeps the u128
+// kernel's keys in registers (64 registers, no spill, against 80 and 28 bytes of spill) but halves the
+// tile, and the per-tile costs (scan, barriers, reservations) decide: measured on C3 k=63 it takes
+// 30.2 ms against 16.3, on C2 3.31 against 1.75 (profiles/r02_sweeps.md), so PER stays 8.
+template <class K> struct ScatterGeom { static constexpr int PER = 8; };
+template <class K, bool RC, int BINS, bool HLL, int PER = ScatterGeom<K>::PER>
+__global__ void __launch_bounds__(SCATTER_THREADS, (BINS == BIN_OWNER || sizeof(K) == 8 || PER == 4) ? 4 : 3)
 scatter_reads_kernel(ReadView v, uint32_t k, Table<K> t, uint32_t n_bins, ScatterOut o,
                      uint32_t *__restrict__ g_regs, PeerOut po) {
     extern __shared__ __align__(16) unsigned char smem[];
-    ScatterSmem<K, SCATTER_TILE> sm;
-    sm.carve(smem, n_bins);
+    static_assert(GRAN % PER == 0, "a work item is a whole number of passes");
+    ScatterSmem<K, SCATTER_THREADS * PER> sm;
+    sm.carve(smem, n_bins, HLL);
     if (HLL) {
         for (uint32_t i = threadIdx.x; i < HLL_M; i += SCATTER_THREADS) sm.regs[i] = 0;
     }
@@ -749,24 +759,28 @@ scatter_reads_kernel(ReadView v, uint32_t k, Table<K> t, uint32_t n_bins, Scatte
     __syncthreads();
     const uint64_t n_tiles = (v.n_items + SCATTER_THREADS - 1) / SCATTER_THREADS;
     uint32_t parity = 0;
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, parity ^= 1u) {
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         ItemWindows<K> iw;
         iw.load(v, tile * SCATTER_THREADS + threadIdx.x, k);
-        K key[SCATTER_PER];
-        uint32_t bin[SCATTER_PER];
-        uint32_t sampled = 0;
 #pragma unroll
-        for (int j = 0; j < SCATTER_PER; ++j) {
-            key[j] = iw.template key<RC>();
-            uint64_t h = KeyTraits<K>::hash(key[j]);
-            Place p = place_of(h, t.world, t.n_sub);
-            bin[j] = BINS == BIN_OWNER ? p.owner : p.part;
-            if (HLL && hll_sampled(h)) sampled |= 1u << j;
-            iw.r.step();
+        for (int pass = 0; pass < GRAN / PER; ++pass, parity ^= 1u) {
+            K key[PER];
+            uint32_t bin[PER];
+            uint32_t sampled = 0;
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                key[j] = iw.template key<RC>();
+                const uint32_t h = KeyTraits<K>::place_hash(key[j]);
+                Place p = place_of(h, t.world, t.n_sub);
+                bin[j] = BINS == BIN_OWNER ? p.owner : p.part;
+                if (HLL && hll_sampled(h)) sampled |= 1u << j;
+                iw.r.step();
+            }
+            const uint32_t vmask = (iw.mask >> (pass * PER)) & ((1u << PER) - 1u);
+            if (HLL) hll_update_tile<K, PER>(sm.regs, key, sampled & vmask);
+            tile_scatter<K, SCATTER_THREADS, PER>(key, bin, vmask, sm, n_bins, o.cursors, 0, o, parity,
+                                                  (BINS == BIN_OWNER && po.world) ? &po : nullptr);
         }
-        if (HLL) hll_update_tile<K, SCATTER_PER>(sm.regs, key, sampled & iw.mask);
-        tile_scatter<K, SCATTER_THREADS, SCATTER_PER>(key, bin, iw.mask, sm, n_bins, o.cursors, 0, o, parity,
-                                                      (BINS == BIN_OWNER && po.world) ? &po : nullptr);
     }
     if (HLL) {
         __syncthreads();
@@ -782,7 +796,7 @@ scatter_keys_kernel(const K *__restrict__ keys, uint64_t n, Table<K> t, uint32_t
                     ScatterOut o, uint32_t *__restrict__ g_regs) {
     extern __shared__ __align__(16) unsigned char smem[];
     ScatterSmem<K, SCATTER_TILE> sm;
-    sm.carve(smem, n_bins);
+    sm.carve(smem, n_bins, HLL);
     if (HLL) {
         for (uint32_t i = threadIdx.x; i < HLL_M; i += SCATTER_THREADS) sm.regs[i] = 0;
     }
@@ -800,7 +814,7 @@ scatter_keys_kernel(const K *__restrict__ keys, uint64_t n, Table<K> t, uint32_t
             const uint64_t i = base + (uint64_t)j * SCATTER_THREADS + threadIdx.x;
             const bool in = i < n;
             key[j] = in ? KeyTraits<K>::load_stream(&keys[i]) : (K)0;
-            uint64_t h = KeyTraits<K>::hash(key[j]);
+            const uint32_t h = KeyTraits<K>::place_hash(key[j]);
             Place p = place_of(h, t.world, t.n_sub);
             bin[j] = BY_OWNER ? p.owner : p.part;
             if (HLL && hll_sampled(h) && in) sampled |= 1u << j;
@@ -847,7 +861,7 @@ scatter_buckets_kernel(const K *__restrict__ keys1, const unsigned long long *__
     constexpr int L2S_TILE = L2S_THREADS * L2S_PER;
     const uint32_t n2 = LEVEL == 2 ? t.pages_per_sub() : t.n_sub;
     ScatterSmem<K, L2S_TILE> sm;
-    sm.carve(smem, n2);
+    sm.carve(smem, n2, false);
     for (uint32_t i = threadIdx.x; i < 2 * n2; i += L2S_THREADS) sm.cnt[i] = 0;
     __syncthreads();
     uint32_t parity = 0;
@@ -886,7 +900,7 @@ scatter_buckets_kernel(const K *__restrict__ keys1, const unsigned long long *__
             key[j] = in ? KeyTraits<K>::load_stream(&keys1[base + o32]) : (K)0;
             if (LEVEL == 2) bin[j] = (KeyTraits<K>::slot_hash(key[j]) & t.sub_mask) >> t.page_log2;
             else {
-                const uint64_t h = KeyTraits<K>::hash(key[j]);
+                const uint32_t h = KeyTraits<K>::place_hash(key[j]);
                 bin[j] = place_of(h, t.world, t.n_sub).part;
                 if (HLL && hll_sampled(h)) sampled |= 1u << j;
             }
@@ -903,17 +917,62 @@ scatter_buckets_kernel(const K *__restrict__ keys1, const unsigned long long *__
 }
 
 // ======================================================================= K3
-// Streaming page update: the table is swept once, page by page.  A CTA loads
-// one page (2^page_log2 slots) into shared memory, inserts the page's keys with
-// shared-memory CAS / atomicAdd (add_single_edge + create_or_modify_edge,
-// hm_gir.rs:91-153, hs_gir.rs:192-203), and writes the page back.  No L2
-// atomics: HBM sees one coalesced read of the keys and one read + write of the
-// table.  `fresh`: the table is logically empty and its memory undefined (right
-// after ktg_reset), so pages are initialised in shared memory instead of loaded.
-constexpr int PAGE_THREADS = 512, PAGE_UNROLL = 4;
+// Streaming page update: the table is swept once, page by page.  A page is [P keys | P weights] in
+// HBM and the same bytes in shared memory, so it arrives as ONE bulk copy (cp.async.bulk, the 1-D TMA
+// path: an elected thread issues it, an mbarrier counts the bytes, SASS UBLKCP / SYNCS) and leaves as
+// one bulk store; no thread spends instructions on moving the table.  The CTA inserts the page's
+// keys with shared-memory CAS / atomicAdd (add_single_edge + create_or_modify_edge,
+// hm_gir.rs:91-153, hs_gir.rs:192-203).  No L2 atomics: HBM sees one coalesced read of the keys
+// and one read + write of the table.  A table that is logically empty (right after ktg_reset, its
+// memory undefined) loads every page from a 1-page template of empty slots instead (L2 resident).
+// NBUF == 2: one persistent CTA per SM holds two page buffers and pipelines them -- page g+1 is
+// loading and page g-1 is being stored while page g is probed.  NBUF == 1: two CTAs per SM cover
+// each other's copies.
+constexpr int PAGE_UNROLL = 4;
 template <class K> struct PageGeom;
 template <> struct PageGeom<uint64_t> { static constexpr uint32_t LOG2 = 13; }; // 8192 x (8+4) B =  96 KB
 template <> struct PageGeom<u128> { static constexpr uint32_t LOG2 = 12; };     // 4096 x (16+4) B = 80 KB
+
+// ---- mbarrier / bulk-copy PTX (sm_90+; the 1-D flavour of TMA needs no tensor map)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared, completion counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// shared -> global, tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void bulk_s2g(void *gdst, const void *smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// orders this thread's generic-proxy writes to shared memory before later async-proxy (bulk copy) reads
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ uint64_t smem_cas(uint64_t *p, uint64_t cmp, uint64_t val) {
     return atomicCAS((unsigned long long *)p, (unsigned long long)cmp, (unsigned long long)val);
@@ -1031,59 +1090,53 @@ template <class K> __device__ __forceinline__ void page_drain(PageCtx<K> &c, con
     }
 }
 
-__device__ __forceinline__ void slot_to_smem(const KeyTraits<uint64_t>::Slot *g, uint64_t *sk, uint32_t *sw) {
-    uint4 v = __ldcs((const uint4 *)g);
-    *sk = ((uint64_t)v.y << 32) | v.x;
-    *sw = v.z;
-}
-__device__ __forceinline__ void slot_to_smem(const KeyTraits<u128>::Slot *g, u128 *sk, uint32_t *sw) {
-    uint4 a = __ldcs((const uint4 *)g), b = __ldcs((const uint4 *)g + 1);
-    *(uint4 *)sk = a;
-    *sw = b.x;
-}
-__device__ __forceinline__ void smem_to_slot(KeyTraits<uint64_t>::Slot *g, const uint64_t *sk, const uint32_t *sw) {
-    const uint64_t key = *sk;
-    *(uint4 *)g = make_uint4((uint32_t)key, (uint32_t)(key >> 32), *sw, 0u);
-}
-__device__ __forceinline__ void smem_to_slot(KeyTraits<u128>::Slot *g, const u128 *sk, const uint32_t *sw) {
-    ((uint4 *)g)[0] = *(const uint4 *)sk;
-    ((uint4 *)g)[1] = make_uint4(*sw, 0u, 0u, 0u);
+// shared memory of update_pages_kernel: NBUF page images | the warps' retry queues | NBUF mbarriers
+template <class K> __host__ __device__ constexpr size_t page_kernel_smem(int threads, int nbuf, uint32_t page_log2) {
+    return (size_t)nbuf * ((sizeof(K) + 4) << page_log2) + (size_t)(threads / 32) * PQ_CAP * (sizeof(K) + 4) + 16;
 }
 
-// FIXED_LOG2 != 0: the page size is a compile-time constant (the usual geometry, PageGeom<K>::LOG2), so
-// the shared-memory carve-up and the page mask cost no registers (the kernel runs at 40 per thread
-// and recomputed them inside the probe loops otherwise)
-template <class K, int THREADS, int PAGE_UNROLL = ktg::PAGE_UNROLL, int FIXED_LOG2 = 0, bool FULL_ROWS = false>
-__global__ void __launch_bounds__(THREADS, 2)
+template <class K, int THREADS, int NBUF, int PAGE_UNROLL = ktg::PAGE_UNROLL>
+__global__ void __launch_bounds__(THREADS, NBUF == 1 ? 2 : 1)
 update_pages_kernel(const K *__restrict__ keys2, const unsigned long long *__restrict__ cursors2,
-                    uint64_t cap2, uint32_t k, bool check_palindrome, bool has_special, Table<K> t, bool fresh) {
+                    uint64_t cap2, uint32_t k, bool check_palindrome, bool has_special, Table<K> t,
+                    const unsigned char *__restrict__ empty_page) {
     typedef KeyTraits<K> T;
     extern __shared__ __align__(16) unsigned char smem[];
-    const uint32_t P = FIXED_LOG2 ? (1u << FIXED_LOG2) : (1u << t.page_log2);
+    const uint32_t P = 1u << t.page_log2;
+    const uint32_t pbytes = (uint32_t)t.page_bytes();
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     PageCtx<K> c;
-    c.sk = (K *)smem;
-    c.qk = c.sk + P + wid * PQ_CAP;
-    c.sw = (uint32_t *)(c.sk + P + (THREADS / 32) * PQ_CAP);
-    c.qi = c.sw + P + wid * PQ_CAP;
+    K *qk_all = (K *)(smem + (size_t)NBUF * pbytes);
+    uint32_t *qi_all = (uint32_t *)(qk_all + (THREADS / 32) * PQ_CAP);
+    uint64_t *bars = (uint64_t *)(qi_all + (THREADS / 32) * PQ_CAP);
+    c.qk = qk_all + wid * PQ_CAP;
+    c.qi = qi_all + wid * PQ_CAP;
     c.qn = 0;
-    c.page_mask = FIXED_LOG2 ? ((1u << FIXED_LOG2) - 1u) : t.page_mask;
+    c.page_mask = t.page_mask;
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < NBUF; ++b) mbar_init(&bars[b], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
     const uint64_t n_pages = t.n_pages();
-    for (uint64_t g = blockIdx.x; g < n_pages; g += gridDim.x) {
-        typename T::Slot *gs = t.slots + g * P;
-        if (fresh) {
-            for (uint32_t i = threadIdx.x; i < P; i += THREADS) {
-                c.sk[i] = T::empty();
-                c.sw[i] = 0;
-            }
+    auto issue_load = [&](uint64_t g, uint32_t buf) { // one thread
+        mbar_expect_tx(&bars[buf], pbytes);
+        bulk_g2s(smem + (size_t)buf * pbytes, empty_page ? empty_page : t.base + g * pbytes, pbytes, &bars[buf]);
+    };
+    if (threadIdx.x == 0 && blockIdx.x < n_pages) issue_load(blockIdx.x, 0);
+    uint32_t it = 0;
+    for (uint64_t g = blockIdx.x; g < n_pages; g += gridDim.x, ++it) {
+        const uint32_t buf = NBUF == 1 ? 0u : (it & 1u);
+        if (NBUF == 2 && threadIdx.x == 0 && g + gridDim.x < n_pages) {
+            bulk_wait_read_all(); // the store of page g - gridDim.x has finished reading the other buffer
+            issue_load(g + gridDim.x, buf ^ 1u);
         }
-        else {
-            for (uint32_t i = threadIdx.x; i < P; i += THREADS) slot_to_smem(gs + i, c.sk + i, c.sw + i);
-        }
-        __syncthreads();
+        c.sk = (K *)(smem + (size_t)buf * pbytes);
+        c.sw = (uint32_t *)(smem + (size_t)buf * pbytes + ((size_t)sizeof(K) << t.page_log2));
         const uint64_t beg = g * cap2, lim = beg + cap2, cur = cursors2[g];
         const uint32_t n = (uint32_t)((cur < lim ? cur : lim) - beg);
         const K *src = keys2 + beg;
+        mbar_wait(&bars[buf], (it / NBUF) & 1u);
         // a warp takes PAGE_UNROLL consecutive rows of 32 keys at a time; FULL: all of them inside
         // the bucket (all but its last rows), so no per-key bounds
         auto rows = [&](uint32_t r0, auto full_tag) {
@@ -1102,7 +1155,7 @@ update_pages_kernel(const K *__restrict__ keys2, const unsigned long long *__res
             for (int q = 0; q < PAGE_UNROLL; ++q) {
                 active[q] = FULL || r0 + q * 32 + lane < n;
                 if (has_special && active[q] && my[q] == T::empty()) { // all-T at full key width, no canonicalisation
-                    atomicAdd(&t.slots[t.capacity()].w, 1u);
+                    atomicAdd(t.special_w(), 1u);
                     active[q] = false;
                 }
                 st[q] = T::slot_hash(my[q]) & c.page_mask;
@@ -1117,14 +1170,22 @@ update_pages_kernel(const K *__restrict__ keys2, const unsigned long long *__res
             }
         };
         for (uint32_t r0 = wid * 32 * PAGE_UNROLL; r0 < n; r0 += THREADS * PAGE_UNROLL) {
-            if (FULL_ROWS && r0 + 32 * PAGE_UNROLL <= n) rows(r0, std::true_type{});
+            if (r0 + 32 * PAGE_UNROLL <= n) rows(r0, std::true_type{});
             else rows(r0, std::false_type{});
         }
         page_drain(c, t);
+        fence_proxy_async(); // this thread's shared-memory writes, before the bulk store reads them
         __syncthreads();
-        for (uint32_t i = threadIdx.x; i < P; i += THREADS) smem_to_slot(gs + i, c.sk + i, c.sw + i);
-        __syncthreads();
+        if (threadIdx.x == 0) {
+            bulk_s2g(t.base + g * pbytes, smem + (size_t)buf * pbytes, pbytes);
+            if (NBUF == 1 && g + gridDim.x < n_pages) {
+                bulk_wait_read_all();
+                issue_load(g + gridDim.x, 0); // the other threads wait on the mbarrier
+            }
+        }
     }
+    if (threadIdx.x == 0) bulk_wait_all();
+    (void)P;
 }
 
 // K3 with L2 atomics over an array of canonical keys (small batches against a
@@ -1244,46 +1305,43 @@ __global__ void replay_overflow_kernel(const K *__restrict__ keys, const uint32_
 }
 
 // ================================================================ table scans
-template <class K>
-__global__ void init_table_kernel(typename KeyTraits<K>::Slot *slots, uint64_t n) {
-    typedef typename KeyTraits<K>::Slot Slot;
+// All scans walk the slots in index order: slot i lives in page i >> page_log2 (Table::key_ptr /
+// w_ptr), so a warp reads 32 consecutive weights (128 bytes) and, where it needs them, 32
+// consecutive keys.  Index capacity() is the special entry (all-ones key, weight only).
+template <class K> __device__ __forceinline__ uint32_t *slot_weight(const Table<K> &t, uint64_t i) {
+    return i < t.capacity() ? t.w_ptr(i) : t.special_w();
+}
+template <class K> __device__ __forceinline__ K slot_key(const Table<K> &t, uint64_t i) {
+    return i < t.capacity() ? KeyTraits<K>::load(t.key_ptr(i)) : KeyTraits<K>::empty();
+}
+
+// every 16 bytes of an empty table: keys all-ones, weights zero
+template <class K> __global__ void init_table_kernel(Table<K> t) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    // every 16 bytes of an empty slot: key halves all-ones, weight/aux zero
-    if (sizeof(Slot) == 16) {
-        uint4 e = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
-        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-            ((uint4 *)slots)[i] = e;
-    }
-    else {
-        uint4 e0 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-        uint4 e1 = make_uint4(0u, 0u, 0u, 0u);
-        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n; i += stride)
-            ((uint4 *)slots)[i] = (i & 1) ? e1 : e0;
+    const uint64_t per_page = t.page_bytes() / 16, key_chunks = ((uint64_t)sizeof(K) << t.page_log2) / 16;
+    const uint64_t total = t.n_pages() * per_page;
+    const uint4 ones = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), zero = make_uint4(0u, 0u, 0u, 0u);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= total; i += stride) {
+        const uint64_t c = i % per_page;
+        ((uint4 *)t.base)[i] = (i < total && c < key_chunks) ? ones : zero; // i == total: the special entry
     }
 }
 
-template <class K>
-__global__ void count_occupied_kernel(const typename KeyTraits<K>::Slot *slots, uint64_t n,
-                                      unsigned long long *out) {
+template <class K> __global__ void count_occupied_kernel(Table<K> t, unsigned long long *out) {
     typedef KeyTraits<K> T;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, n = t.capacity();
     uint64_t acc[1] = {0};
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        acc[0] += T::load(&slots[i]) != T::empty();
+        acc[0] += T::load(t.key_ptr(i)) != T::empty();
     block_accumulate<1>(acc, out);
 }
 
-template <class K>
-__global__ void rehash_kernel(const typename KeyTraits<K>::Slot *old_slots, uint64_t n_old,
-                              Table<K> t) {
-    typedef KeyTraits<K> T;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    // slot n_old is the special all-ones-key slot
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n_old; i += stride) {
-        uint32_t w = old_slots[i].w;
+template <class K> __global__ void rehash_kernel(Table<K> old, Table<K> t) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, n = old.capacity();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += stride) {
+        const uint32_t w = *slot_weight(old, i);
         if (w == 0) continue; // empty, or an edge removed by the filter
-        K key = i == n_old ? T::empty() : T::load(&old_slots[i]);
-        table_add(t, key, w);
+        table_add(t, slot_key(old, i), w);
     }
 }
 
@@ -1304,20 +1362,16 @@ __device__ __forceinline__ uint64_t digest_term(uint64_t hi, uint64_t lo, uint32
 // full rows of 32 (the scan was 45 % divergence-idle and instruction bound at 3.2 TB/s before).
 template <class K, bool RC>
 __global__ void __launch_bounds__(256)
-edge_stats_kernel(const typename KeyTraits<K>::Slot *slots, uint64_t n_slots, uint32_t k,
-                  uint32_t threshold, EdgeStats *out) {
+edge_stats_kernel(Table<K> t, uint32_t k, uint32_t threshold, EdgeStats *out) {
     typedef KeyTraits<K> T;
-    typedef typename T::Slot Slot;
     constexpr int U = 4, QCAP = 64; // < 32 left over + <= 32 pushed per step
-    __shared__ uint64_t q_lo[8][QCAP];
-    __shared__ uint64_t q_hi[sizeof(Slot) == 32 ? 8 : 1][QCAP];
+    __shared__ K q_key[8][QCAP];
     __shared__ uint32_t q_w[8][QCAP];
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint64_t acc[4] = {0, 0, 0, 0}; // edges, sum_w, sum_w_below, digest
     uint64_t mx = 0;
     uint32_t qn = 0; // warp-uniform
-    auto digest_one = [&](uint64_t hi, uint64_t lo, uint32_t w) {
-        const K key = T::make(hi, lo);
+    auto digest_one = [&](K key, uint32_t w) {
         uint64_t mult = 1;
         uint64_t d = digest_term(T::hi(key), T::lo(key), w);
         if (RC) {
@@ -1333,43 +1387,42 @@ edge_stats_kernel(const typename KeyTraits<K>::Slot *slots, uint64_t n_slots, ui
         acc[3] += d;
         if (w > mx) mx = w;
     };
-    // whole slots with 16-byte loads, U in flight per lane (a pure HBM stream); a warp covers
-    // 32 * U consecutive slots per step
+    // weights first (4 bytes per slot, U rows in flight per lane), keys of the occupied slots only
+    const uint64_t n_slots = t.capacity() + 1;
     const uint64_t warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
     const uint64_t gw = (uint64_t)blockIdx.x * (blockDim.x >> 5) + wid;
     for (uint64_t base = gw * (32 * U); base < n_slots; base += warps * (32 * U)) {
-        uint4 v[U], v2[U];
+        uint32_t w[U];
+        K key[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const uint64_t i = base + u * 32 + lane;
-            v[u] = make_uint4(0, 0, 0, 0);
-            v2[u] = make_uint4(0, 0, 0, 0);
-            if (i < n_slots) {
-                v[u] = __ldcs((const uint4 *)&slots[i]);
-                if (sizeof(Slot) == 32) v2[u] = __ldcs((const uint4 *)&slots[i] + 1);
-            }
+            w[u] = i < n_slots ? __ldcs(slot_weight(t, i)) : 0u;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const uint32_t w = sizeof(Slot) == 32 ? v2[u].x : v[u].z;
-            const uint32_t m = __ballot_sync(0xFFFFFFFFu, w != 0);
+            const uint64_t i = base + u * 32 + lane;
+            key[u] = w[u] ? slot_key(t, i) : (K)0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, w[u] != 0);
             if (m == 0) continue;
-            if (w != 0) {
+            if (w[u] != 0) {
                 const uint32_t pos = qn + __popc(m & ((1u << lane) - 1u));
-                q_lo[wid][pos] = ((uint64_t)v[u].y << 32) | v[u].x;
-                if (sizeof(Slot) == 32) q_hi[wid][pos] = ((uint64_t)v[u].w << 32) | v[u].z;
-                q_w[wid][pos] = w;
+                q_key[wid][pos] = key[u];
+                q_w[wid][pos] = w[u];
             }
             qn += __popc(m);
             __syncwarp();
             if (qn >= 32) {
                 qn -= 32;
-                digest_one(sizeof(Slot) == 32 ? q_hi[wid][qn + lane] : 0, q_lo[wid][qn + lane], q_w[wid][qn + lane]);
+                digest_one(q_key[wid][qn + lane], q_w[wid][qn + lane]);
                 __syncwarp();
             }
         }
     }
-    if (lane < qn) digest_one(sizeof(Slot) == 32 ? q_hi[wid][lane] : 0, q_lo[wid][lane], q_w[wid][lane]);
+    if (lane < qn) digest_one(q_key[wid][lane], q_w[wid][lane]);
     uint64_t a4[4] = {acc[0], acc[1], acc[2], acc[3]};
     // EdgeStats layout: edges, sum_w, sum_w_below, max_w, digest
     __shared__ unsigned long long sh[5];
@@ -1391,14 +1444,13 @@ edge_stats_kernel(const typename KeyTraits<K>::Slot *slots, uint64_t n_slots, ui
 // ======================================================================= K4
 // Clean::remove_weak_edges (pruner.rs:109-118, edges.rs:51-58): keep w >= t.
 // In place: a removed edge keeps its slot (probe chains stay intact) with
-// weight 0 == "not in E".
-template <class K>
-__global__ void filter_kernel(typename KeyTraits<K>::Slot *slots, uint64_t n_slots,
-                              uint32_t threshold) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += stride) {
-        uint32_t w = slots[i].w;
-        if (w != 0 && w < threshold) slots[i].w = 0;
+// weight 0 == "not in E".  Reads (and rarely writes) the weights only: 4 bytes per slot.
+template <class K> __global__ void filter_kernel(Table<K> t, uint32_t threshold) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, n = t.capacity();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += stride) {
+        uint32_t *wp = slot_weight(t, i);
+        const uint32_t w = *wp;
+        if (w != 0 && w < threshold) *wp = 0;
     }
 }
 
@@ -1415,13 +1467,12 @@ __device__ __forceinline__ uint32_t scale_weight(uint32_t w, double p, uint32_t 
     return nw;
 }
 
-template <class K>
-__global__ void standardize_kernel(typename KeyTraits<K>::Slot *slots, uint64_t n_slots, double p,
-                                   uint32_t threshold) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += stride) {
-        uint32_t w = slots[i].w;
-        if (w != 0) slots[i].w = scale_weight(w, p, threshold);
+template <class K> __global__ void standardize_kernel(Table<K> t, double p, uint32_t threshold) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, n = t.capacity();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += stride) {
+        uint32_t *wp = slot_weight(t, i);
+        const uint32_t w = *wp;
+        if (w != 0) *wp = scale_weight(w, p, threshold);
     }
 }
 
@@ -1429,25 +1480,27 @@ __global__ void standardize_kernel(typename KeyTraits<K>::Slot *slots, uint64_t 
 // into dense arrays, expanding both strands.  Block-aggregated: one atomicAdd
 // on the output cursor per CTA iteration.  This is the export that
 // Convert::create_from (hm_gir.rs:156-226) consumes and, with threshold > 1,
-// the fused "filter + compact" of north_star kernel (4).
+// the fused "filter + compact" of north_star kernel (4).  The output arrays may live on
+// another GPU (peer memory): a sharded export compacts every shard straight into the
+// gathering device's arrays over NVLink.
 template <class K, bool RC>
 __global__ void __launch_bounds__(256)
-compact_edges_kernel(const typename KeyTraits<K>::Slot *slots, uint64_t n_slots, uint32_t k,
-                     uint32_t threshold, uint64_t *__restrict__ out_hi,
+compact_edges_kernel(Table<K> t, uint32_t k, uint32_t threshold, uint64_t *__restrict__ out_hi,
                      uint64_t *__restrict__ out_lo, uint32_t *__restrict__ out_w, uint64_t cap,
                      unsigned long long *cursor) {
     typedef KeyTraits<K> T;
     __shared__ uint32_t s_warp[8];
     __shared__ unsigned long long s_base;
+    const uint64_t n_slots = t.capacity() + 1;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t n_round = (n_slots + blockDim.x - 1) / blockDim.x * blockDim.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-        uint32_t w = i < n_slots ? slots[i].w : 0;
+        uint32_t w = i < n_slots ? *slot_weight(t, i) : 0;
         uint32_t cnt = 0;
         K key = 0, r = 0;
         if (w != 0 && w >= threshold) {
-            key = T::load(&slots[i]);
+            key = slot_key(t, i);
             cnt = 1;
             if (RC) {
                 r = revcomp(key, k);
@@ -1495,15 +1548,13 @@ compact_edges_kernel(const typename KeyTraits<K>::Slot *slots, uint64_t n_slots,
 // out/in of the reverse-complement orientation (each <= 4).
 template <class KE, class KN, bool RC>
 __global__ void __launch_bounds__(256)
-build_nodes_kernel(const typename KeyTraits<KE>::Slot *slots, uint64_t n_slots, uint32_t k,
-                   Table<KN> nt) {
-    typedef KeyTraits<KE> TE;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+build_nodes_kernel(Table<KE> t, uint32_t k, Table<KN> nt) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, n = t.capacity();
     const uint32_t k1 = k - 1;
     const KE nmask = (k1 == 8 * sizeof(KE) / 2) ? ~(KE)0 : (KE)((((KE)1) << (2 * k1)) - 1);
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += stride) {
-        if (slots[i].w == 0) continue;
-        KE e = TE::load(&slots[i]);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += stride) {
+        if (*slot_weight(t, i) == 0) continue;
+        KE e = slot_key(t, i);
         KE er = RC ? revcomp(e, k) : e;
         const int n_exp = (RC && er != e) ? 2 : 1;
         for (int x = 0; x < n_exp; ++x) {
@@ -1511,16 +1562,16 @@ build_nodes_kernel(const typename KeyTraits<KE>::Slot *slots, uint64_t n_slots, 
             KN pre = (KN)(edge >> 2), suf = (KN)(edge & nmask);
 #pragma unroll
             for (int side = 0; side < 2; ++side) { // 0: prefix gains an out-edge, 1: suffix an in-edge
-                KN n = side ? suf : pre;
+                KN nd = side ? suf : pre;
                 uint32_t field = side;
                 if (RC) {
-                    KN nr = revcomp(n, k1);
-                    if (nr < n) {
-                        n = nr;
+                    KN nr = revcomp(nd, k1);
+                    if (nr < nd) {
+                        nd = nr;
                         field += 2;
                     }
                 }
-                table_add(nt, n, 1u << (8 * field));
+                table_add(nt, nd, 1u << (8 * field));
             }
         }
     }
@@ -1534,13 +1585,12 @@ struct NodeStats {
 // sends to the owners of its nodes when the table is sharded over GPUs
 template <class KN>
 __global__ void __launch_bounds__(256)
-compact_nodes_kernel(const typename KeyTraits<KN>::Slot *slots, uint64_t n_slots, KN *__restrict__ out_keys,
-                     uint32_t *__restrict__ out_deg, unsigned long long *cursor) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+compact_nodes_kernel(Table<KN> nt, KN *__restrict__ out_keys, uint32_t *__restrict__ out_deg, unsigned long long *cursor) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, n_slots = nt.capacity() + 1;
     const uint64_t n_round = (n_slots + 31) & ~(uint64_t)31;
     const uint32_t lane = threadIdx.x & 31;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-        const uint32_t w = i < n_slots ? slots[i].w : 0;
+        const uint32_t w = i < n_slots ? *slot_weight(nt, i) : 0;
         const uint32_t m = __ballot_sync(0xFFFFFFFFu, w != 0);
         if (m == 0) continue;
         unsigned long long base = 0;
@@ -1548,7 +1598,7 @@ compact_nodes_kernel(const typename KeyTraits<KN>::Slot *slots, uint64_t n_slots
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         if (w) {
             const unsigned long long pos = base + __popc(m & ((1u << lane) - 1u));
-            out_keys[pos] = KeyTraits<KN>::load(&slots[i]);
+            out_keys[pos] = slot_key(nt, i);
             out_deg[pos] = w;
         }
     }
@@ -1566,12 +1616,12 @@ merge_nodes_kernel(const KN *__restrict__ keys, const uint32_t *__restrict__ deg
 
 template <class KN, bool RC>
 __global__ void __launch_bounds__(256)
-node_stats_kernel(const typename KeyTraits<KN>::Slot *slots, uint64_t n_slots, NodeStats *out) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+node_stats_kernel(Table<KN> nt, NodeStats *out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, n = nt.capacity();
     uint64_t acc[3] = {0, 0, 0};
     uint64_t mi = 0, mo = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += stride) {
-        uint32_t w = slots[i].w;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += stride) {
+        uint32_t w = *slot_weight(nt, i);
         if (w == 0) continue;
 #pragma unroll
         for (int o = 0; o < (RC ? 2 : 1); ++o) {

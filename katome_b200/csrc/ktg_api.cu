@@ -9,11 +9,14 @@
 #include "fastq_device.cuh"
 #include "host_plan.h"
 #include "host_reader.h"
+#include "multi.cuh"
 
 using namespace ktg;
 
 struct ktg_builder {
-    std::unique_ptr<BuilderBase> impl;
+    std::unique_ptr<BuilderBase> impl;   // one GPU
+    std::unique_ptr<MultiBuilder> multi; // or ktg_config.n_devices > 1 (multi.cuh)
+    uint32_t k = 0;
     // device staging for host batches: two buffers for the full chunks, four small ones for the
     // short chunks a large batch ends in (all of those are copied while the last flush runs)
     // staging buffers of the host batcher: up to N_FULL rotate under the full chunks, the short
@@ -48,7 +51,17 @@ int ktg_create(const ktg_config *cfg, ktg_builder **out) {
     if (cfg->sub_table_log2_bytes && (cfg->sub_table_log2_bytes < 16 || cfg->sub_table_log2_bytes > 34))
         return fail(KTG_ERR_INVALID, "sub_table_log2_bytes out of range");
     if (ktg_device_count() < 1) return fail(KTG_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
+    if (cfg->n_devices > 1) {
+        std::unique_ptr<MultiBuilder> m(new MultiBuilder());
+        KTG_TRY(m->init(*cfg));
+        ktg_builder *b = new ktg_builder();
+        b->multi = std::move(m);
+        b->k = cfg->k;
+        *out = b;
+        return KTG_OK;
+    }
     int dev = cfg->device;
+    if (cfg->n_devices == 1 && cfg->device_ids) dev = cfg->device_ids[0];
     if (dev < 0) KTG_CUDA(cudaGetDevice(&dev));
     std::unique_ptr<BuilderBase> impl;
     if (cfg->k <= 32) impl.reset(new Builder<uint64_t>());
@@ -62,12 +75,17 @@ int ktg_create(const ktg_config *cfg, ktg_builder **out) {
     KTG_TRY(impl->init());
     ktg_builder *b = new ktg_builder();
     b->impl = std::move(impl);
+    b->k = cfg->k;
     *out = b;
     return KTG_OK;
 }
 
 void ktg_destroy(ktg_builder *b) {
     if (!b) return;
+    if (b->multi) {
+        delete b;
+        return;
+    }
     cudaSetDevice(b->impl->device);
     cudaStreamSynchronize(b->impl->stream);
     cudaStreamSynchronize(b->impl->copy_stream);
@@ -82,12 +100,16 @@ void ktg_destroy(ktg_builder *b) {
 
 #define KTG_ENTER(b)                                                                           \
     if (!(b)) return fail(KTG_ERR_INVALID, "null builder");                                    \
-    KTG_CUDA(cudaSetDevice((b)->impl->device));
+    KTG_CUDA(cudaSetDevice((b)->multi ? (b)->multi->dev[0] : (b)->impl->device));
+// entry points that address one shard's device memory: single-device handles only
+#define KTG_SINGLE(b)                                                                          \
+    if ((b)->multi) return fail(KTG_ERR_INVALID, "%s is not available on a multi-device handle", __func__);
 
 int ktg_add_reads_device(ktg_builder *b, const void *d_bases, const void *d_offsets,
                          uint64_t n_reads, uint64_t total_bases, uint64_t *accepted_reads,
                          uint64_t *accepted_bytes) {
     KTG_ENTER(b);
+    KTG_SINGLE(b);
     uint64_t r0 = 0, b0 = 0;
     if (accepted_reads || accepted_bytes) KTG_TRY(b->impl->read_counters(&r0, &b0));
     KTG_TRY(b->impl->ingest_device((const uint8_t *)d_bases, (const uint64_t *)d_offsets, n_reads, total_bases));
@@ -107,6 +129,7 @@ int ktg_add_reads(ktg_builder *b, const uint8_t *bases, const uint64_t *offsets,
     KTG_ENTER(b);
     if (n_reads == 0) return KTG_OK;
     if (!bases || !offsets) return fail(KTG_ERR_INVALID, "null argument");
+    if (b->multi) return b->multi->add_reads(bases, offsets, n_reads, accepted_reads, accepted_bytes);
     BuilderBase *impl = b->impl.get();
     struct Paced { // input at PCIe pace for the duration of this call (the builder's flush cadence)
         BuilderBase *p;
@@ -117,8 +140,7 @@ int ktg_add_reads(ktg_builder *b, const uint8_t *bases, const uint64_t *offsets,
     if (accepted_reads || accepted_bytes) KTG_TRY(impl->read_counters(&r0c, &b0c));
     // bytes of bases per chunk: small enough that the H2D copy of chunk i+1 hides the kernels of
     // chunk i and only one chunk's kernels are exposed at the end
-    uint64_t CHUNK = 64ull << 20;
-    if (const char *e = getenv("KTG_CHUNK_MB")) CHUNK = (uint64_t)std::max(1, atoi(e)) << 20; // tuning knob
+    const uint64_t CHUNK = (uint64_t)std::max(1, impl->tune.chunk_mb) << 20;
     for (int i = 0; i < ktg_builder::N_STAGE; ++i) {
         if (!b->st_free[i]) {
             KTG_CUDA(cudaEventCreateWithFlags(&b->st_free[i], cudaEventDisableTiming));
@@ -128,18 +150,10 @@ int ktg_add_reads(ktg_builder *b, const uint8_t *bases, const uint64_t *offsets,
     // where the batch is cut and after which chunks the stage is flushed: host_plan.h
     // (measured on C2, 8.3 ms of copies, before the eager page stage: the builder's own cadence, 4 flushes,
     // 12.55 ms per build, one flush at 73 % 12.8, at 58 % 11.8, two (44 %, 73 %) 11.9)
-    std::vector<uint64_t> pcts{55};
-    if (const char *e = getenv("KTG_FLUSH_PCT")) { // tuning knob: comma separated percentages of the bytes
-        pcts.clear();
-        for (const char *q = e; *q;) {
-            char *end = nullptr;
-            const long v = strtol(q, &end, 10);
-            if (end == q) break;
-            if (v >= 1 && v <= 100) pcts.push_back((uint64_t)v);
-            q = *end == ',' ? end + 1 : end;
-        }
-    }
-    const ChunkPlan plan = plan_chunks(offsets, n_reads, CHUNK, pcts, !getenv("KTG_NO_TAPER"));
+    std::vector<uint64_t> pcts;
+    for (int v : {impl->tune.flush_pct, impl->tune.flush_pct2})
+        if (v >= 1 && v <= 100) pcts.push_back((uint64_t)v);
+    const ChunkPlan plan = plan_chunks(offsets, n_reads, CHUNK, pcts, impl->tune.taper != 0);
     const std::vector<uint64_t> &cut = plan.cut;
     const std::vector<char> &flush_here = plan.flush_here;
     const size_t n_chunks = plan.n_chunks(), tail_first = plan.tail_first;
@@ -157,9 +171,7 @@ int ktg_add_reads(ktg_builder *b, const uint8_t *bases, const uint64_t *offsets,
     // end have one each.  Two are enough: a buffer is free as soon as its chunk is packed, and a large
     // call ends in short chunks with buffers of their own, so the copy engine does not wait for a
     // flush (measured on C2: 3, 4 or 6 buffers change nothing; KTG_STAGE_BUFS to try).
-    size_t n_full = 2;
-    if (const char *e = getenv("KTG_STAGE_BUFS")) n_full = (size_t)atoi(e); // tuning knob
-    n_full = std::min<size_t>(std::max<size_t>(n_full, 2), ktg_builder::N_FULL);
+    const size_t n_full = std::min<size_t>(std::max<size_t>((size_t)impl->tune.stage_bufs, 2), ktg_builder::N_FULL);
     auto slot_of = [&](size_t c) -> int {
         return c >= tail_first ? ktg_builder::N_FULL + (int)std::min<size_t>(c - tail_first, ktg_builder::N_TAIL - 1)
                                : (int)(c % n_full);
@@ -277,7 +289,7 @@ struct FastqDeviceParser {
     BuilderBase *impl;
     size_t chunk;                     // raw bytes per chunk
     uint8_t *pinned[2] = {nullptr, nullptr};
-    DeviceBuf raw[2], dense[2], offs[2], nl, bcount, bstart, sstart, slen, tmp, info;
+    DeviceBuf raw[2], dense[2], offs[2], nl, bcount, bstart, sstart, slen, tmp, info, hdr, recidx, baseoff;
     cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
     bool used[2] = {false, false};
 
@@ -292,6 +304,7 @@ struct FastqDeviceParser {
             raw[i].release(); dense[i].release(); offs[i].release();
         }
         nl.release(); bcount.release(); bstart.release(); sstart.release(); slen.release(); tmp.release(); info.release();
+        hdr.release(); recidx.release(); baseoff.release();
     }
     int init() {
         for (int i = 0; i < 2; ++i) {
@@ -301,6 +314,137 @@ struct FastqDeviceParser {
             KTG_TRY(raw[i].ensure(chunk + 64));
         }
         KTG_TRY(info.ensure(sizeof(FastqChunkInfo)));
+        return KTG_OK;
+    }
+
+    // newline index of n raw bytes on the device -> nl (positions), *n_lines
+    int index_lines(const uint8_t *d_raw, size_t n, uint32_t *n_lines) {
+        cudaStream_t st = impl->stream;
+        const uint32_t n_blocks = (uint32_t)((n + FQ_BLOCK_BYTES - 1) / FQ_BLOCK_BYTES);
+        KTG_TRY(bcount.ensure(((size_t)n_blocks + 1) * 4));
+        KTG_TRY(bstart.ensure(((size_t)n_blocks + 1) * 4));
+        KTG_CUDA(cudaMemsetAsync((uint32_t *)bcount.p + n_blocks, 0, 4, st));
+        fq_count_kernel<<<n_blocks, 256, 0, st>>>(d_raw, n, (uint32_t *)bcount.p);
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, (uint32_t *)bcount.p, (uint32_t *)bstart.p, (int)n_blocks + 1, st);
+        KTG_TRY(tmp.ensure(tb));
+        KTG_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, (uint32_t *)bcount.p, (uint32_t *)bstart.p, (int)n_blocks + 1, st));
+        KTG_CUDA(cudaMemcpyAsync(n_lines, (uint32_t *)bstart.p + n_blocks, 4, cudaMemcpyDeviceToHost, st));
+        KTG_CUDA(cudaStreamSynchronize(st));
+        if (*n_lines) {
+            KTG_TRY(nl.ensure((size_t)*n_lines * 4));
+            fq_positions_kernel<<<n_blocks, 256, 0, st>>>(d_raw, n, (const uint32_t *)bstart.p, (uint32_t *)nl.p);
+        }
+        return KTG_OK;
+    }
+
+    // a record that does not fit the chunk: double the pinned and the raw buffers, keeping what
+    // pinned[cur] holds (a FASTA record may be a whole chromosome)
+    int grow(int cur, size_t keep) {
+        if (chunk >= ((size_t)2 << 30)) return fail(KTG_ERR_BAD_RECORD, "a record is larger than %zu bytes", chunk);
+        KTG_CUDA(cudaStreamSynchronize(impl->stream));
+        KTG_CUDA(cudaStreamSynchronize(impl->copy_stream));
+        const size_t bigger = chunk * 2;
+        for (int i = 0; i < 2; ++i) {
+            uint8_t *p = nullptr;
+            KTG_CUDA(cudaHostAlloc((void **)&p, bigger + 64, cudaHostAllocDefault));
+            if (i == cur && keep) memcpy(p, pinned[i], keep);
+            cudaFreeHost(pinned[i]);
+            pinned[i] = p;
+            KTG_TRY(raw[i].ensure(bigger + 64));
+        }
+        chunk = bigger;
+        return KTG_OK;
+    }
+
+    // One FASTA file.  Mirrors next_fasta of host_reader.h record for record.
+    int parse_fasta(ReadFile &f) {
+        cudaStream_t st = impl->stream;
+        size_t carry = 0; // bytes of an unfinished record at the front of pinned[cur]
+        int cur = 0;
+        bool eof = false, first = true;
+        while (!eof) {
+            if (used[cur]) KTG_CUDA(cudaEventSynchronize(copied[cur]));
+            if (carry >= chunk) KTG_TRY(grow(cur, carry));
+            uint8_t *h = pinned[cur];
+            size_t got = f.read_raw(h + carry, chunk - carry);
+            size_t n = carry + got;
+            eof = got < chunk - carry;
+            if (eof && n && h[n - 1] != '\n') h[n++] = '\n'; // a last line without newline is a line
+            if (n == 0) break;
+            if (first && h[0] != '>') return fail(KTG_ERR_BAD_RECORD, "Expected > at record start.");
+            first = false;
+            if (used[cur]) KTG_CUDA(cudaStreamWaitEvent(impl->copy_stream, consumed[cur], 0));
+            KTG_CUDA(cudaMemcpyAsync(raw[cur].p, h, n, cudaMemcpyHostToDevice, impl->copy_stream));
+            KTG_CUDA(cudaEventRecord(copied[cur], impl->copy_stream));
+            KTG_CUDA(cudaStreamWaitEvent(st, copied[cur], 0));
+            used[cur] = true;
+            const uint8_t *d_raw = (const uint8_t *)raw[cur].p;
+            uint32_t n_lines = 0;
+            KTG_TRY(index_lines(d_raw, n, &n_lines));
+            // per-line facts and their scans
+            KTG_TRY(hdr.ensure(((size_t)n_lines + 1) * 4));
+            KTG_TRY(recidx.ensure(((size_t)n_lines + 1) * 4));
+            KTG_TRY(slen.ensure(((size_t)n_lines + 1) * 8));
+            KTG_TRY(baseoff.ensure(((size_t)n_lines + 1) * 8));
+            const int lgrid = (int)std::min<uint64_t>(((uint64_t)n_lines + 256) / 256, 148 * 8);
+            fa_lines_kernel<<<lgrid, 256, 0, st>>>(d_raw, (const uint32_t *)nl.p, n_lines, (uint32_t *)hdr.p, (uint64_t *)slen.p);
+            size_t tb = 0, tb2 = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, tb, (uint32_t *)hdr.p, (uint32_t *)recidx.p, (int)n_lines + 1, st);
+            cub::DeviceScan::ExclusiveSum(nullptr, tb2, (uint64_t *)slen.p, (uint64_t *)baseoff.p, (int)n_lines + 1, st);
+            KTG_TRY(tmp.ensure(std::max(tb, tb2)));
+            KTG_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, (uint32_t *)hdr.p, (uint32_t *)recidx.p, (int)n_lines + 1, st));
+            KTG_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb2, (uint64_t *)slen.p, (uint64_t *)baseoff.p, (int)n_lines + 1, st));
+            uint32_t n_hdr = 0;
+            KTG_CUDA(cudaMemcpyAsync(&n_hdr, (uint32_t *)recidx.p + n_lines, 4, cudaMemcpyDeviceToHost, st));
+            KTG_CUDA(cudaStreamSynchronize(st));
+            // the last record of a chunk may continue in the next one
+            const uint64_t n_rec = eof ? n_hdr : (n_hdr ? n_hdr - 1 : 0);
+            FastqChunkInfo ci{};
+            ci.consumed = eof ? n : 0;
+            if (n_rec) {
+                KTG_TRY(offs[cur].ensure((n_rec + 1) * 8));
+                FastqChunkInfo init{};
+                init.bad_header = ~0ull;
+                init.min_len = ~0ull;
+                init.consumed = eof ? n : 0;
+                KTG_CUDA(cudaMemcpyAsync(info.p, &init, sizeof init, cudaMemcpyHostToDevice, st));
+                fa_offsets_kernel<<<lgrid, 256, 0, st>>>((const uint32_t *)nl.p, (const uint32_t *)hdr.p, (const uint32_t *)recidx.p,
+                                                        (const uint64_t *)baseoff.p, n_lines, n_rec, (uint64_t *)offs[cur].p,
+                                                        (FastqChunkInfo *)info.p);
+                const int rgrid = (int)std::min<uint64_t>((n_rec + 255) / 256, 148 * 8);
+                fa_hint_kernel<<<rgrid, 256, 0, st>>>((const uint64_t *)offs[cur].p, n_rec, impl->k, (FastqChunkInfo *)info.p);
+                uint64_t total_bases = 0;
+                KTG_CUDA(cudaMemcpyAsync(&ci, info.p, sizeof ci, cudaMemcpyDeviceToHost, st));
+                KTG_CUDA(cudaMemcpyAsync(&total_bases, (uint64_t *)offs[cur].p + n_rec, 8, cudaMemcpyDeviceToHost, st));
+                KTG_CUDA(cudaStreamSynchronize(st));
+                KTG_TRY(dense[cur].ensure(total_bases + 64));
+                fa_gather_kernel<<<148 * 8, 256, 0, st>>>(d_raw, (const uint32_t *)nl.p, (const uint32_t *)hdr.p, (const uint32_t *)recidx.p,
+                                                         (const uint64_t *)baseoff.p, n_lines, n_rec, (uint8_t *)dense[cur].p);
+                BatchHint hint;
+                hint.ulen = (ci.min_len == ci.max_len && ci.max_len <= 0xFFFFFFFFull) ? (uint32_t)ci.max_len : 0;
+                hint.windows_ub = ci.windows_ub;
+                impl->hint_shift0 = (uint32_t)((uintptr_t)dense[cur].p & 31);
+                impl->input_consumed = consumed[cur];
+                int rc_ = impl->ingest_device((const uint8_t *)dense[cur].p, (const uint64_t *)offs[cur].p, n_rec, total_bases, &hint);
+                impl->input_consumed = nullptr;
+                KTG_TRY(rc_);
+            }
+            else KTG_CUDA(cudaEventRecord(consumed[cur], st));
+            if (eof) break;
+            // what follows the last complete record goes to the front of the other buffer
+            const size_t done = n_rec ? (size_t)ci.consumed : 0, rest = n - done;
+            if (rest >= chunk) { // one record fills the whole chunk: read on into a larger one
+                KTG_TRY(grow(cur, n));
+                carry = n;
+                continue;
+            }
+            const int nxt = cur ^ 1;
+            if (used[nxt]) KTG_CUDA(cudaEventSynchronize(copied[nxt]));
+            memcpy(pinned[nxt], h + done, rest);
+            carry = rest;
+            cur = nxt;
+        }
         return KTG_OK;
     }
 
@@ -413,13 +557,13 @@ int ktg_create_from_files(ktg_builder *b, const char *const *paths, uint32_t n_p
         if (!f->open(paths[i], file_type == KTG_FASTA, &why)) return fail(KTG_ERR_IO, "%s", why.c_str());
         files.push_back(std::move(f));
     }
-    // FASTQ: records are cut on the device (KTG_HOST_PARSE=1 keeps the host reader, its twin)
-    if (file_type == KTG_FASTQ && !getenv("KTG_HOST_PARSE")) {
-        size_t chunk = 16u << 20; // small: the two pinned buffers are allocated per call (0.3 ms / MiB)
-        if (const char *e = getenv("KTG_FASTQ_CHUNK_KB")) chunk = (size_t)std::max(1, atoi(e)) << 10; // test knob
+    // records are cut on the device (option host_parse keeps the host reader, its twin)
+    if (!b->multi && !b->impl->tune.host_parse) {
+        // small: the two pinned buffers are allocated per call (0.3 ms / MiB)
+        const size_t chunk = (size_t)std::max(1, b->impl->tune.fastq_chunk_kb) << 10;
         FastqDeviceParser parser(b, chunk);
         KTG_TRY(parser.init());
-        for (auto &f : files) KTG_TRY(parser.parse(*f));
+        for (auto &f : files) KTG_TRY(file_type == KTG_FASTA ? parser.parse_fasta(*f) : parser.parse(*f));
         KTG_TRY(b->impl->read_counters(&reads, &bytes));
         if (total_bytes) *total_bytes = bytes;
         return ktg_finalize(b);
@@ -442,19 +586,21 @@ int ktg_create_from_files(ktg_builder *b, const char *const *paths, uint32_t n_p
             if (batch[cur].n_reads()) {
                 rc_ = ktg_add_reads(b, batch[cur].bases, batch[cur].offsets.data(), batch[cur].n_reads(), nullptr, nullptr);
                 if (rc_ != KTG_OK) break;
-                if (!copied[cur]) cudaEventCreateWithFlags(&copied[cur], cudaEventDisableTiming);
-                cudaEventRecord(copied[cur], b->impl->copy_stream);
+                if (!b->multi) { // (a multi-device add_reads returns with its copies done)
+                    if (!copied[cur]) cudaEventCreateWithFlags(&copied[cur], cudaEventDisableTiming);
+                    cudaEventRecord(copied[cur], b->impl->copy_stream);
+                }
                 cur ^= 1;
             }
             if (st == 0) break;
         }
         if (rc_ != KTG_OK) break;
     }
-    cudaStreamSynchronize(b->impl->copy_stream); // the batches are freed below
+    if (!b->multi) cudaStreamSynchronize(b->impl->copy_stream); // the batches are freed below
     for (int i = 0; i < 2; ++i)
         if (copied[i]) cudaEventDestroy(copied[i]);
     KTG_TRY(rc_);
-    KTG_TRY(b->impl->read_counters(&reads, &bytes));
+    KTG_TRY(b->multi ? b->multi->read_counters(&reads, &bytes) : b->impl->read_counters(&reads, &bytes));
     if (total_bytes) *total_bytes = bytes;
     return ktg_finalize(b);
 }
@@ -466,6 +612,7 @@ int ktg_add_weighted_kmers(ktg_builder *b, const uint8_t *kmers, const uint32_t 
     KTG_ENTER(b);
     if (n == 0) return KTG_OK;
     if (!kmers || !weights) return fail(KTG_ERR_INVALID, "null argument");
+    KTG_SINGLE(b);
     BuilderBase *impl = b->impl.get();
     const uint64_t k = impl->k, step = std::max<uint64_t>(1, (64ull << 20) / k); // 64 MiB of bases at a time
     DeviceBuf d_k, d_w;
@@ -497,6 +644,7 @@ int ktg_create_from_bfc_files(ktg_builder *b, const char *const *paths, uint32_t
                               uint32_t minimal_weight_threshold, uint64_t *total_bytes) {
     KTG_ENTER(b);
     if (!paths && n_paths) return fail(KTG_ERR_INVALID, "null argument");
+    KTG_SINGLE(b);
     const uint64_t k = b->impl->k;
     std::vector<FILE *> fs;
     auto close_all = [&]() { for (FILE *f : fs) if (f) fclose(f); };
@@ -552,24 +700,33 @@ int ktg_create_from_bfc_files(ktg_builder *b, const char *const *paths, uint32_t
 
 int ktg_reset(ktg_builder *b) {
     KTG_ENTER(b);
+    if (b->multi) return b->multi->reset();
     return b->impl->reset();
 }
 
 int ktg_finalize(ktg_builder *b) {
     KTG_ENTER(b);
+    if (b->multi) return b->multi->finalize();
     return b->impl->finalize();
+}
+
+static int edge_stats_of(ktg_builder *b, uint32_t threshold, EdgeStats *es) {
+    return b->multi ? b->multi->edge_stats(threshold, es) : b->impl->edge_stats(threshold, es);
+}
+static int node_stats_of(ktg_builder *b, NodeStats *ns) {
+    return b->multi ? b->multi->node_stats(ns) : b->impl->node_stats(ns);
 }
 
 int ktg_counts(ktg_builder *b, uint64_t *nodes, uint64_t *edges) {
     KTG_ENTER(b);
     if (edges) {
         EdgeStats es;
-        KTG_TRY(b->impl->edge_stats(0, &es));
+        KTG_TRY(edge_stats_of(b, 0, &es));
         *edges = es.edges;
     }
     if (nodes) {
         NodeStats ns;
-        KTG_TRY(b->impl->node_stats(&ns));
+        KTG_TRY(node_stats_of(b, &ns));
         *nodes = ns.nodes;
     }
     return KTG_OK;
@@ -580,8 +737,8 @@ int ktg_collection_stats(ktg_builder *b, ktg_stats *out) {
     if (!out) return fail(KTG_ERR_INVALID, "null argument");
     EdgeStats es;
     NodeStats ns;
-    KTG_TRY(b->impl->edge_stats(0, &es));
-    KTG_TRY(b->impl->node_stats(&ns));
+    KTG_TRY(edge_stats_of(b, 0, &es));
+    KTG_TRY(node_stats_of(b, &ns));
     out->node_count = ns.nodes;
     out->edge_count = es.edges;
     out->max_edge_weight = es.max_w;
@@ -595,12 +752,14 @@ int ktg_collection_stats(ktg_builder *b, ktg_stats *out) {
 
 int ktg_nodes_export_device(ktg_builder *b, void **d_keys, void **d_degrees, uint64_t *n, uint32_t *key_words) {
     KTG_ENTER(b);
+    KTG_SINGLE(b);
     if (!d_keys || !d_degrees || !n || !key_words) return fail(KTG_ERR_INVALID, "null argument");
     return b->impl->nodes_export(d_keys, d_degrees, n, key_words);
 }
 
 int ktg_nodes_stats_from_device(ktg_builder *b, const void *d_keys, const void *d_degrees, uint64_t n, ktg_stats *out) {
     KTG_ENTER(b);
+    KTG_SINGLE(b);
     if (!out) return fail(KTG_ERR_INVALID, "null argument");
     NodeStats ns;
     KTG_TRY(b->impl->nodes_stats_from(d_keys, d_degrees, n, &ns));
@@ -615,48 +774,61 @@ int ktg_nodes_stats_from_device(ktg_builder *b, const void *d_keys, const void *
 
 int ktg_edge_sums(ktg_builder *b, uint32_t threshold, uint64_t *sum_w, uint64_t *sum_w_below) {
     KTG_ENTER(b);
+    KTG_SINGLE(b);
     if (!sum_w || !sum_w_below) return fail(KTG_ERR_INVALID, "null argument");
     return b->impl->edge_sums(threshold, sum_w, sum_w_below);
 }
 
 int ktg_scale_weights(ktg_builder *b, double ratio, uint32_t threshold) {
     KTG_ENTER(b);
+    KTG_SINGLE(b);
     return b->impl->scale_weights(ratio, threshold);
 }
 
 int ktg_remove_weak_edges(ktg_builder *b, uint32_t threshold) {
     KTG_ENTER(b);
+    if (b->multi) return b->multi->remove_weak_edges(threshold);
     return b->impl->remove_weak_edges(threshold);
 }
 
 int ktg_remove_single_vertices(ktg_builder *b) {
     KTG_ENTER(b);
+    if (b->multi) return b->multi->finalize();
     return b->impl->finalize(); // nodes are implicit: nothing to remove
 }
 
 int ktg_standardize_edges(ktg_builder *b, uint64_t genome_len, uint64_t k, uint32_t threshold) {
     KTG_ENTER(b);
+    if (b->multi) return b->multi->standardize(genome_len, k, threshold);
     return b->impl->standardize(genome_len, k, threshold);
 }
 
 int ktg_export_edges(ktg_builder *b, uint64_t *key_hi, uint64_t *key_lo, uint32_t *weight,
                      uint64_t cap, int sorted, uint64_t *n) {
     KTG_ENTER(b);
+    if (b->multi) return b->multi->export_edges(key_hi, key_lo, weight, cap, sorted, n);
     return b->impl->export_edges(key_hi, key_lo, weight, cap, sorted, n);
 }
 
 int ktg_export_graph(ktg_builder *b, uint64_t *node_hi, uint64_t *node_lo, uint64_t n_nodes, uint64_t *src,
                      uint64_t *dst, uint32_t *weight, uint8_t *edge_bytes, uint64_t n_edges) {
     KTG_ENTER(b);
+    if (b->multi) return b->multi->export_graph(node_hi, node_lo, n_nodes, src, dst, weight, edge_bytes, n_edges);
     return b->impl->export_graph(node_hi, node_lo, n_nodes, src, dst, weight, edge_bytes, n_edges);
 }
 
-uint32_t ktg_edge_record_bytes(const ktg_builder *b) { return b ? (b->impl->k + 3) / 4 + 1 : 0; }
+int ktg_export_externals(ktg_builder *b, uint64_t *node_ids, uint8_t *kinds, uint64_t cap, uint64_t *n) {
+    KTG_ENTER(b);
+    if (b->multi) return b->multi->export_externals(node_ids, kinds, cap, n);
+    return b->impl->export_externals(node_ids, kinds, cap, n);
+}
+
+uint32_t ktg_edge_record_bytes(const ktg_builder *b) { return b ? (b->k + 3) / 4 + 1 : 0; }
 
 int ktg_digest(ktg_builder *b, uint64_t out[4]) {
     KTG_ENTER(b);
     EdgeStats es;
-    KTG_TRY(b->impl->edge_stats(0, &es));
+    KTG_TRY(edge_stats_of(b, 0, &es));
     out[0] = es.digest;
     out[1] = es.edges;
     out[2] = es.sum_w;
@@ -664,10 +836,12 @@ int ktg_digest(ktg_builder *b, uint64_t out[4]) {
     return KTG_OK;
 }
 
-uint32_t ktg_key_words(const ktg_builder *b) { return b && b->impl->k > 32 ? 2u : 1u; }
+uint32_t ktg_key_words(const ktg_builder *b) { return b && b->k > 32 ? 2u : 1u; }
 
 uint32_t ktg_owner_of(const ktg_builder *b, uint64_t key_hi, uint64_t key_lo) {
-    return b ? b->impl->owner_of(key_hi, key_lo) : 0;
+    if (!b) return 0;
+    if (b->multi) return b->multi->use_skm ? b->multi->sh[0]->skm_owner_of(key_hi, key_lo) : b->multi->sh[0]->owner_of(key_hi, key_lo);
+    return b->impl->owner_of(key_hi, key_lo);
 }
 
 int ktg_partition_reads_device(ktg_builder *b, const void *d_bases, const void *d_offsets,
@@ -675,6 +849,7 @@ int ktg_partition_reads_device(ktg_builder *b, const void *d_bases, const void *
                                uint64_t *counts, uint64_t *accepted_reads,
                                uint64_t *accepted_bytes) {
     KTG_ENTER(b);
+    KTG_SINGLE(b);
     if (!d_keys || !counts) return fail(KTG_ERR_INVALID, "null argument");
     uint64_t r0 = 0, b0 = 0;
     if (accepted_reads || accepted_bytes) KTG_TRY(b->impl->read_counters(&r0, &b0));
@@ -690,17 +865,20 @@ int ktg_partition_reads_device(ktg_builder *b, const void *d_bases, const void *
 
 int ktg_insert_keys_device(ktg_builder *b, const void *d_keys, uint64_t n) {
     KTG_ENTER(b);
+    KTG_SINGLE(b);
     return b->impl->insert_keys(d_keys, n);
 }
 
 int ktg_partition_keys_device(ktg_builder *b, const void *d_keys, uint64_t n, void **d_out, uint64_t *counts) {
     KTG_ENTER(b);
+    KTG_SINGLE(b);
     if (!d_out || !counts) return fail(KTG_ERR_INVALID, "null argument");
     return b->impl->partition_keys(d_keys, n, d_out, counts);
 }
 
 int ktg_mg_plan(ktg_builder *b, uint64_t max_windows, int *needs_realloc) {
     KTG_ENTER(b);
+    KTG_SINGLE(b);
     if (!needs_realloc) return fail(KTG_ERR_INVALID, "null argument");
     return b->impl->mg_plan(max_windows, needs_realloc);
 }
@@ -708,6 +886,7 @@ int ktg_mg_plan(ktg_builder *b, uint64_t max_windows, int *needs_realloc) {
 int ktg_mg_prepare(ktg_builder *b, uint64_t max_windows, void **rx_base, uint64_t *rx_bytes,
                    uint64_t *bucket_cap, uint32_t *n_sub) {
     KTG_ENTER(b);
+    KTG_SINGLE(b);
     if (!rx_base || !rx_bytes || !bucket_cap || !n_sub) return fail(KTG_ERR_INVALID, "null argument");
     return b->impl->mg_prepare(max_windows, rx_base, rx_bytes, bucket_cap, n_sub);
 }
@@ -716,6 +895,7 @@ int ktg_mg_scatter_reads_device(ktg_builder *b, const void *d_bases, const void 
                                 uint64_t total_bases, void *const *peer_rx, uint32_t slot, int first_of_batch,
                                 void *send_stream, void **d_cursors) {
     KTG_ENTER(b);
+    KTG_SINGLE(b);
     if (!peer_rx || !d_cursors) return fail(KTG_ERR_INVALID, "null argument");
     return b->impl->mg_scatter_reads((const uint8_t *)d_bases, (const uint64_t *)d_offsets, n_reads, total_bases,
                                      peer_rx, slot, first_of_batch, (cudaStream_t)send_stream, d_cursors);
@@ -723,29 +903,34 @@ int ktg_mg_scatter_reads_device(ktg_builder *b, const void *d_bases, const void 
 
 int ktg_mg_insert_buckets(ktg_builder *b, const void *d_bucket_ends, uint64_t n_keys, uint32_t slot) {
     KTG_ENTER(b);
+    KTG_SINGLE(b);
     return b->impl->mg_insert_buckets(d_bucket_ends, n_keys, slot);
 }
 
 int ktg_mg_sketch(ktg_builder *b, void **d_regs, uint32_t *n_regs) {
     KTG_ENTER(b);
+    KTG_SINGLE(b);
     if (!d_regs || !n_regs) return fail(KTG_ERR_INVALID, "null argument");
     return b->impl->mg_sketch(d_regs, n_regs);
 }
 
 int ktg_mg_merge_sketch(ktg_builder *b, const void *d_regs) {
     KTG_ENTER(b);
+    KTG_SINGLE(b);
     if (!d_regs) return fail(KTG_ERR_INVALID, "null argument");
     return b->impl->mg_merge_sketch(d_regs);
 }
 
 int ktg_mg_spill(ktg_builder *b, void **d_keys, uint64_t *n) {
     KTG_ENTER(b);
+    KTG_SINGLE(b);
     if (!d_keys || !n) return fail(KTG_ERR_INVALID, "null argument");
     return b->impl->mg_spill(d_keys, n);
 }
 
 int ktg_mg_insert_spill(ktg_builder *b, const void *d_keys, uint64_t n) {
     KTG_ENTER(b);
+    KTG_SINGLE(b);
     return b->impl->mg_insert_spill(d_keys, n);
 }
 
@@ -754,12 +939,14 @@ int ktg_mg_skm_supported(uint32_t k) { return ktg::skm_supported(k) ? 1 : 0; }
 
 int ktg_mg_skm_plan(ktg_builder *b, uint64_t max_windows, int *needs_realloc) {
     KTG_ENTER(b);
+    KTG_SINGLE(b);
     if (!needs_realloc) return fail(KTG_ERR_INVALID, "null argument");
     return b->impl->mg_skm_plan(max_windows, needs_realloc);
 }
 
 int ktg_mg_skm_prepare(ktg_builder *b, uint64_t max_windows, void **rx_base, uint64_t *rx_bytes, uint64_t *bucket_cap) {
     KTG_ENTER(b);
+    KTG_SINGLE(b);
     if (!rx_base || !rx_bytes || !bucket_cap) return fail(KTG_ERR_INVALID, "null argument");
     return b->impl->mg_skm_prepare(max_windows, rx_base, rx_bytes, bucket_cap);
 }
@@ -768,6 +955,7 @@ int ktg_mg_skm_scatter_reads_device(ktg_builder *b, const void *d_bases, const v
                                     uint64_t total_bases, void *const *peer_rx, uint32_t slot, int first_of_batch,
                                     void *send_stream, void **d_cursors, void **d_key_counts) {
     KTG_ENTER(b);
+    KTG_SINGLE(b);
     if (!peer_rx || !d_cursors || !d_key_counts) return fail(KTG_ERR_INVALID, "null argument");
     return b->impl->mg_skm_scatter_reads((const uint8_t *)d_bases, (const uint64_t *)d_offsets, n_reads, total_bases,
                                          peer_rx, slot, first_of_batch, (cudaStream_t)send_stream, d_cursors,
@@ -776,24 +964,28 @@ int ktg_mg_skm_scatter_reads_device(ktg_builder *b, const void *d_bases, const v
 
 int ktg_mg_skm_insert_buckets(ktg_builder *b, const void *d_bucket_ends, uint64_t n_keys_ub, uint32_t slot) {
     KTG_ENTER(b);
+    KTG_SINGLE(b);
     if (!d_bucket_ends) return fail(KTG_ERR_INVALID, "null argument");
     return b->impl->mg_skm_insert_buckets(d_bucket_ends, n_keys_ub, slot);
 }
 
 int ktg_mg_skm_spill(ktg_builder *b, void **d_records, uint64_t *n) {
     KTG_ENTER(b);
+    KTG_SINGLE(b);
     if (!d_records || !n) return fail(KTG_ERR_INVALID, "null argument");
     return b->impl->mg_skm_spill(d_records, n);
 }
 
 int ktg_mg_skm_partition_records(ktg_builder *b, const void *d_records, uint64_t n, void **d_out, uint64_t *counts) {
     KTG_ENTER(b);
+    KTG_SINGLE(b);
     if (!d_out || !counts) return fail(KTG_ERR_INVALID, "null argument");
     return b->impl->mg_skm_partition_records(d_records, n, d_out, counts);
 }
 
 int ktg_mg_skm_insert_records(ktg_builder *b, const void *d_records, uint64_t n) {
     KTG_ENTER(b);
+    KTG_SINGLE(b);
     return b->impl->mg_skm_insert_records(d_records, n);
 }
 
@@ -903,9 +1095,12 @@ int ktg_random_access_probe(uint64_t bytes, uint64_t n_updates, uint32_t slot_by
     return KTG_OK;
 }
 
+// profile of a multi-device handle: the first shard's (every shard runs the same schedule)
+static BuilderBase *profiled(ktg_builder *b) { return b->multi ? b->multi->sh[0].get() : b->impl.get(); }
+
 int ktg_get_profile(ktg_builder *b, ktg_kernel_profile *out, uint32_t cap, uint32_t *n) {
     KTG_ENTER(b);
-    KTG_CUDA(cudaStreamSynchronize(b->impl->stream));
+    KTG_CUDA(cudaStreamSynchronize(profiled(b)->stream));
 #ifdef KTG_PHASE_TIMERS
     {
         unsigned long long h[8];
@@ -915,8 +1110,8 @@ int ktg_get_profile(ktg_builder *b, ktg_kernel_profile *out, uint32_t cap, uint3
         cudaMemcpyToSymbol(g_phase_cycles, h, sizeof h);
     }
 #endif
-    b->impl->prof.resolve();
-    const auto &es = b->impl->prof.entries;
+    profiled(b)->prof.resolve();
+    const auto &es = profiled(b)->prof.entries;
     if (n) *n = (uint32_t)es.size();
     for (uint32_t i = 0; i < es.size() && i < cap; ++i) {
         memset(&out[i], 0, sizeof out[i]);
@@ -930,6 +1125,12 @@ int ktg_get_profile(ktg_builder *b, ktg_kernel_profile *out, uint32_t cap, uint3
 
 int ktg_reset_profile(ktg_builder *b) {
     KTG_ENTER(b);
+    if (b->multi)
+        return b->multi->parallel([&](uint32_t i) -> int {
+            KTG_TRY(b->multi->sh[i]->sync_stream());
+            b->multi->sh[i]->prof.reset();
+            return KTG_OK;
+        });
     KTG_CUDA(cudaStreamSynchronize(b->impl->stream));
     b->impl->prof.reset();
     return KTG_OK;
@@ -978,15 +1179,52 @@ int ktg_host_parse_file(const char *path, int file_type, uint64_t batch_bytes, u
 
 int ktg_set_profile(ktg_builder *b, int enabled) {
     KTG_ENTER(b);
+    if (b->multi)
+        return b->multi->parallel([&](uint32_t i) -> int {
+            KTG_TRY(b->multi->sh[i]->sync_stream());
+            b->multi->sh[i]->prof.enabled = enabled != 0;
+            return KTG_OK;
+        });
     KTG_CUDA(cudaStreamSynchronize(b->impl->stream));
     b->impl->prof.resolve(); // what was timed so far stays in the table
     b->impl->prof.enabled = enabled != 0;
     return KTG_OK;
 }
 
+static int set_option_on(BuilderBase *impl, const char *name, int64_t value) {
+    Tuning &t = impl->tune;
+    const struct { const char *n; int *p; } ints[] = {
+        {"page_threads", &t.page_threads}, {"page_nbuf", &t.page_nbuf}, {"page_log2", &t.page_log2},
+        {"l2s_variant", &t.l2s_variant}, {"l1_ctas", &t.l1_ctas}, {"p2p_ctas", &t.p2p_ctas},
+        {"chunk_mb", &t.chunk_mb}, {"stage_bufs", &t.stage_bufs}, {"flush_pct", &t.flush_pct},
+        {"flush_pct2", &t.flush_pct2}, {"taper", &t.taper}, {"eager_pages", &t.eager_pages},
+        {"stage_factor_milli", &t.stage_factor_milli}, {"host_parse", &t.host_parse},
+        {"fastq_chunk_kb", &t.fastq_chunk_kb}, {"mg_pad", &t.mg_pad}, {"trace", &t.trace},
+    };
+    if (!strcmp(name, "stage_max_keys")) {
+        t.stage_max_keys = value;
+        return KTG_OK;
+    }
+    for (const auto &o : ints)
+        if (!strcmp(name, o.n)) {
+            *o.p = (int)value;
+            if (o.p == &t.trace) trace_enabled() = value != 0;
+            return KTG_OK;
+        }
+    return fail(KTG_ERR_INVALID, "unknown option %s", name);
+}
+
+int ktg_set_option(ktg_builder *b, const char *name, int64_t value) {
+    KTG_ENTER(b);
+    if (!name) return fail(KTG_ERR_INVALID, "null argument");
+    if (b->multi) return b->multi->set_option(name, value, set_option_on);
+    return set_option_on(b->impl.get(), name, value);
+}
+
 int ktg_get_info(ktg_builder *b, ktg_info *out) {
     KTG_ENTER(b);
     if (!out) return fail(KTG_ERR_INVALID, "null argument");
+    if (b->multi) return b->multi->info(out);
     return b->impl->info(out);
 }
 

@@ -229,7 +229,7 @@ scatter_superkmers_kernel(SkmView sv, uint32_t k, uint32_t world, ScatterOut o, 
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint32_t s_kc[MAX_P2P_WORLD];
     ScatterSmem<u128, SCATTER_TILE> sm;
-    sm.carve(smem, world);
+    sm.carve(smem, world, false);
     u128 *stage = sm.keys; // dead between two tile_scatter calls
     for (uint32_t i = threadIdx.x; i < 2 * world; i += SCATTER_THREADS) sm.cnt[i] = 0;
     if (threadIdx.x < MAX_P2P_WORLD) s_kc[threadIdx.x] = 0;
@@ -325,36 +325,32 @@ scatter_superkmers_kernel(SkmView sv, uint32_t k, uint32_t world, ScatterOut o, 
     if (threadIdx.x < world && s_kc[threadIdx.x]) atomicAdd(&key_counts[threadIdx.x], (unsigned long long)s_kc[threadIdx.x]);
 }
 
-// ---- owner: received records -> canonical k-mers, as a flat array (any order).  Bucket q of
+// ---- owner: received records -> canonical k-mers -> level-1 buckets, in ONE kernel.  Bucket q of
 // the receive slot holds what source rank q wrote: records [q*cap, min(ends[q], (q+1)*cap)).
-// Pure streaming, no block barriers: a warp takes 32 records, scans their k-mer counts, unrolls
-// every record into a warp-private shared-memory buffer (rolling fw/rc like the read
-// extraction) and copies that out coalesced.  Output space is handed out in chunks of
-// UNROLL_CHUNK keys per warp (one global atomicAdd per chunk: a cursor bumped once per warp row
-// serialised the whole kernel on one L2 address); what a warp leaves unused in a chunk is
-// filled with all-ones keys, which the level-1 scatter skips (k <= 31: never a real key).
-// *cursor ends up as the length of the array, fillers included.
-constexpr int UNROLL_THREADS = 256;
-constexpr uint32_t UNROLL_CHUNK = 2048;
-// out_cap that n_keys keys unrolled by n_warps warps can never exceed
-__host__ __device__ __forceinline__ uint64_t unroll_out_cap(uint64_t n_keys, uint64_t n_warps) {
-    return (uint64_t)UNROLL_CHUNK * (n_keys / (UNROLL_CHUNK - 32 * SKM_W + 1) + n_warps + 2);
-}
+// (Round 1 unrolled the records into a flat array in HBM and partitioned that array with a second
+// kernel: 8 bytes per key written and read again, 1.4 ms of a 8.8 ms step at N = 8.)
+// A warp takes 32 records, which hold T <= 512 k-mers; k-mer s belongs to the record whose first
+// k-mer is the last "head" at or before s.  The heads are a 512-bit map (16 words of shared memory per
+// warp); lane l produces k-mers s = 32*it + l: it finds its record with two popcounts, fetches that
+// record and its first index from the owning lane with shuffles and cuts the k-mer out of the 128
+// bits directly (no rolling state), so the lanes stay balanced whatever the record lengths (a
+// lane-per-record loop runs to the longest record of the row, 16 iterations against 5.5 on average).
+// The k-mers never leave the registers: 8 iterations fill one tile of the partitioner (tile_scatter,
+// bins = sub-tables), which also feeds the cardinality sketch; rows with more than 256 k-mers (records
+// longer than 8 windows on average: low-complexity reads) take a second tile.
+constexpr int SREC_THREADS = 256, SREC_PER = 8, SREC_TILE = SREC_THREADS * SREC_PER;
 template <bool RC>
-__global__ void __launch_bounds__(UNROLL_THREADS)
-unroll_records_kernel(const u128 *__restrict__ rx, const unsigned long long *__restrict__ ends, uint64_t cap,
-                      uint32_t n_buckets, uint32_t k, uint64_t *__restrict__ out,
-                      unsigned long long *__restrict__ cursor, uint64_t out_cap) {
-    // Balanced lanes: the 32 records of a warp row hold T <= 512 k-mers; k-mer s belongs to the
-    // record whose first k-mer is the last "head" at or before s.  The heads are a 512-bit map
-    // (16 words in shared memory per warp); in iteration it, lane l produces k-mer s = 32*it + l:
-    // it finds its record with two popcounts, fetches that record and its first index from the
-    // owning lane with shuffles, cuts the k-mer out of the 128 bits directly (no rolling state)
-    // and stores it coalesced.  A lane-per-record loop runs to the longest record of the row
-    // (16 iterations against 5.5 on average) and was 3x slower.
-    __shared__ uint32_t s_heads[UNROLL_THREADS / 32][16];
+__global__ void __launch_bounds__(SREC_THREADS, 3)
+scatter_records_kernel(const u128 *__restrict__ rx, const unsigned long long *__restrict__ ends, uint64_t cap,
+                       uint32_t n_buckets, uint32_t k, Table<uint64_t> t, ScatterOut o, uint32_t *__restrict__ g_regs) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ uint32_t s_heads[SREC_THREADS / 32][16];
     __shared__ unsigned long long s_end[MAX_P2P_WORLD];
     __shared__ uint32_t s_tbase[MAX_P2P_WORLD + 1]; // data tiles before bucket q (tiles past a bucket's fill are not visited)
+    const uint32_t n_bins = t.n_sub;
+    ScatterSmem<uint64_t, SREC_TILE> sm;
+    sm.carve(smem, n_bins, false);
+    for (uint32_t i = threadIdx.x; i < 2 * n_bins; i += SREC_THREADS) sm.cnt[i] = 0;
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t *heads = s_heads[wid];
     const uint64_t kmask = (1ull << (2 * k)) - 1ull;
@@ -365,21 +361,19 @@ unroll_records_kernel(const u128 *__restrict__ rx, const unsigned long long *__r
             const unsigned long long e = fill < lim ? fill : lim;
             s_end[q] = e;
             s_tbase[q] = run;
-            run += e > beg ? (uint32_t)((e - beg + UNROLL_THREADS - 1) / UNROLL_THREADS) : 0u;
+            run += e > beg ? (uint32_t)((e - beg + SREC_THREADS - 1) / SREC_THREADS) : 0u;
         }
         s_tbase[n_buckets] = run;
     }
     __syncthreads();
     const uint32_t n_tiles = s_tbase[n_buckets];
-    unsigned long long pos = 0, chunk_end = 0; // warp-uniform
-    // the records of the NEXT tile are loaded before this one is processed (the kernel is a chain of
-    // dependent latencies per warp otherwise: DRAM, scan, cursor, stores)
+    // the records of the NEXT tile are loaded before this one is processed
     auto fetch = [&](uint32_t tile, uint64_t &hi, uint64_t &lo) {
         hi = lo = ~0ull;
         if (tile >= n_tiles) return;
         uint32_t q = 0;
         while (q + 1 < n_buckets && tile >= s_tbase[q + 1]) ++q;
-        const uint64_t i = (uint64_t)q * cap + (uint64_t)(tile - s_tbase[q]) * UNROLL_THREADS + threadIdx.x;
+        const uint64_t i = (uint64_t)q * cap + (uint64_t)(tile - s_tbase[q]) * SREC_THREADS + threadIdx.x;
         if (i < s_end[q]) {
             const ulonglong2 raw = __ldcs((const ulonglong2 *)(rx + i));
             lo = raw.x;
@@ -388,6 +382,7 @@ unroll_records_kernel(const u128 *__restrict__ rx, const unsigned long long *__r
     };
     uint64_t nhi, nlo;
     fetch(blockIdx.x, nhi, nlo);
+    uint32_t parity = 0;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint64_t rhi = nhi, rlo = nlo;
         fetch(tile + gridDim.x, nhi, nlo);
@@ -399,17 +394,6 @@ unroll_records_kernel(const u128 *__restrict__ rx, const unsigned long long *__r
             if (lane >= (uint32_t)d) incl += x;
         }
         const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-        if (total == 0) continue; // warp-uniform
-        if (pos + total > chunk_end) {
-            for (unsigned long long s = pos + lane; s < chunk_end; s += 32)
-                if (s < out_cap) out[s] = ~0ull;
-            unsigned long long c = 0;
-            if (lane == 0) c = atomicAdd(cursor, (unsigned long long)UNROLL_CHUNK);
-            pos = __shfl_sync(0xFFFFFFFFu, c, 0);
-            chunk_end = pos + UNROLL_CHUNK;
-        }
-        const unsigned long long base = pos;
-        pos += total;
         const uint32_t excl = incl - n;
         if (lane < 16) heads[lane] = 0;
         __syncwarp();
@@ -426,32 +410,47 @@ unroll_records_kernel(const u128 *__restrict__ rx, const unsigned long long *__r
         before -= __popc(my_word); // exclusive
         // the h-th head (in index order) belongs to the h-th lane with n > 0
         const uint32_t nz = __ballot_sync(0xFFFFFFFFu, n != 0);
-        const uint32_t n_it = (total + 31) >> 5;
-        for (uint32_t it = 0; it < n_it; ++it) {
-            const uint32_t word = __shfl_sync(0xFFFFFFFFu, my_word, it);
-            const uint32_t wb = __shfl_sync(0xFFFFFFFFu, before, it);
-            const uint32_t s = 32 * it + lane;
-            const uint32_t h = wb + __popc(word & (0xFFFFFFFFu >> (31 - lane))) - 1u; // head index, valid if s < total
-            const uint32_t src = nz == 0xFFFFFFFFu ? h : __fns(nz, 0, (int)h + 1);    // lane of the h-th non-empty record
-            const uint32_t sl = src & 31u; // (s >= total: garbage in, nothing stored)
-            const uint64_t hi = __shfl_sync(0xFFFFFFFFu, rhi, sl), lo = __shfl_sync(0xFFFFFFFFu, rlo, sl);
-            const uint32_t first = __shfl_sync(0xFFFFFFFFu, excl, sl);
-            if (s < total) {
-                const uint32_t j = s - first;
-                const uint32_t sh = 128 - 2 * (k + j); // 36 .. 82
-                const uint64_t fw = (sh >= 64 ? hi >> (sh - 64) : (hi << (64 - sh)) | (lo >> sh)) & kmask;
-                uint64_t key = fw;
-                if (RC) {
-                    const uint64_t rc = revcomp(fw, k);
-                    if (rc < fw) key = rc;
+        for (uint32_t half = 0; half < 2; ++half) {
+            if (half && !__syncthreads_or(total > 32u * SREC_PER)) break; // block-uniform
+            uint64_t key[SREC_PER];
+            uint32_t bin[SREC_PER];
+            uint32_t vmask = 0, sampled = 0;
+#pragma unroll
+            for (int q = 0; q < SREC_PER; ++q) {
+                const uint32_t it = half * SREC_PER + q;
+                key[q] = 0;
+                bin[q] = 0;
+                if (32u * it >= total) continue; // warp-uniform
+                const uint32_t word = __shfl_sync(0xFFFFFFFFu, my_word, it);
+                const uint32_t wb = __shfl_sync(0xFFFFFFFFu, before, it);
+                const uint32_t s = 32 * it + lane;
+                const uint32_t h = wb + __popc(word & (0xFFFFFFFFu >> (31 - lane))) - 1u; // head index, valid if s < total
+                const uint32_t src = nz == 0xFFFFFFFFu ? h : __fns(nz, 0, (int)h + 1);    // lane of the h-th non-empty record
+                const uint32_t sl = src & 31u; // (s >= total: garbage in, nothing kept)
+                const uint64_t hi = __shfl_sync(0xFFFFFFFFu, rhi, sl), lo = __shfl_sync(0xFFFFFFFFu, rlo, sl);
+                const uint32_t first = __shfl_sync(0xFFFFFFFFu, excl, sl);
+                if (s < total) {
+                    const uint32_t j = s - first;
+                    const uint32_t sh = 128 - 2 * (k + j); // 36 .. 82
+                    const uint64_t fw = (sh >= 64 ? hi >> (sh - 64) : (hi << (64 - sh)) | (lo >> sh)) & kmask;
+                    uint64_t kk = fw;
+                    if (RC) {
+                        const uint64_t rc = revcomp(fw, k);
+                        if (rc < fw) kk = rc;
+                    }
+                    key[q] = kk;
+                    const uint32_t ph = KeyTraits<uint64_t>::place_hash(kk);
+                    bin[q] = place_of(ph, t.world, t.n_sub).part;
+                    vmask |= 1u << q;
+                    if (hll_sampled(ph)) sampled |= 1u << q;
                 }
-                if (base + s < out_cap) out[base + s] = key;
             }
+            hll_update_tile<uint64_t, SREC_PER>(g_regs, key, sampled);
+            tile_scatter<uint64_t, SREC_THREADS, SREC_PER>(key, bin, vmask, sm, n_bins, o.cursors, 0, o, parity);
+            parity ^= 1u;
         }
         __syncwarp();
     }
-    for (unsigned long long s = pos + lane; s < chunk_end; s += 32)
-        if (s < out_cap) out[s] = ~0ull;
 }
 
 // ---- spill route (records that did not fit a receive bucket): group by owner with plain

@@ -79,7 +79,8 @@ class GpuGIR:
     def __init__(self, k: int = 40, reverse_complement: bool = True, *, edges_count: Optional[int] = None,
                  device: int = -1, stream: Optional[int] = None, world_size: int = 1, rank: int = 0,
                  profile: bool = False, force_direct: bool = False, force_partition: bool = False,
-                 force_pages: bool = False, no_pages: bool = False, sub_table_log2_bytes: int = 0):
+                 force_pages: bool = False, no_pages: bool = False, sub_table_log2_bytes: int = 0,
+                 options: Optional[dict] = None, device_ids: Optional[Sequence[int]] = None):
         self._L = L.lib()
         flags = (L.KTG_FLAG_PROFILE if profile else 0) | (L.KTG_FLAG_FORCE_DIRECT if force_direct else 0) | \
                 (L.KTG_FLAG_FORCE_PARTITION if force_partition else 0) | \
@@ -88,9 +89,12 @@ class GpuGIR:
         # legacy default stream, which the C ABI spells cudaStreamLegacy (0x1), since NULL = "own".
         if stream is not None and int(stream) == 0:
             stream = 1
+        # device_ids: ONE handle over several GPUs (hash-sharded table, fused NVLink exchange); a device
+        # may be listed more than once (shards sharing a GPU)
+        ids = (C.c_int32 * len(device_ids))(*[int(d) for d in device_ids]) if device_ids else None
         cfg = L.KtgConfig(L.KTG_ABI_VERSION, int(k), int(bool(reverse_complement)), int(device),
                           int(edges_count or 0), int(world_size), int(rank), C.c_void_p(stream),
-                          int(sub_table_log2_bytes), flags)
+                          int(sub_table_log2_bytes), flags, len(device_ids) if device_ids else 0, ids)
         h = C.c_void_p()
         self._h = None
         _check(self._L.ktg_create(C.byref(cfg), C.byref(h)))
@@ -98,6 +102,13 @@ class GpuGIR:
         self.k = int(k)
         self.reverse_complement = bool(reverse_complement)
         self.world_size, self.rank = int(world_size), int(rank)
+        self.device_ids = [int(d) for d in device_ids] if device_ids else None
+        for name, value in (options or {}).items():
+            self.set_option(name, value)
+
+    def set_option(self, name: str, value: int):
+        """ktg_set_option: test / measurement options (include/katome_gpu.h lists them)"""
+        _check(self._L.ktg_set_option(self._h, name.encode(), int(value)))
 
     # ---- Init (builder.rs:19-25) -------------------------------------------------
     @classmethod
@@ -269,6 +280,16 @@ class GpuGIR:
                                         out["src"].ctypes.data, out["dst"].ctypes.data, out["weight"].ctypes.data,
                                         out["edge_bytes"].ctypes.data, ne))
         return out
+
+    def export_externals(self):
+        """`Externals` of remove_dead_paths (pruner.rs:165-195): (node indices ascending, kinds) with kind 0 =
+        Input (no incoming edge), 1 = Output (no outgoing edge); indices are those of export_graph."""
+        n = C.c_uint64(0)
+        _check(self._L.ktg_export_externals(self._h, None, None, 0, C.byref(n)))
+        ids, kinds = np.zeros(n.value, np.uint64), np.zeros(n.value, np.uint8)
+        if n.value:
+            _check(self._L.ktg_export_externals(self._h, ids.ctypes.data, kinds.ctypes.data, n.value, C.byref(n)))
+        return ids, kinds
 
     def digest(self) -> Tuple[int, int, int, int]:
         out = (C.c_uint64 * 4)()

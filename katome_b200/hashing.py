@@ -1,5 +1,5 @@
 """Host-side (numpy) mirror of the device key functions in csrc/common.cuh: canonical form,
-the 64-bit key hash and the owner rank of a k-mer.  Used by the host routing logic and its
+the two 32-bit placement hashes and the owner rank of a k-mer.  Used by the host routing logic and its
 CPU tests; the insert path itself only exists on the GPU."""
 from __future__ import annotations
 
@@ -52,7 +52,7 @@ def canonical(hi, lo, k: int):
 
 
 def mix64(x: np.ndarray) -> np.ndarray:
-    """placement hash of common.cuh: two multiply / fold-by-32 rounds"""
+    """common.cuh mix64: two multiply / fold-by-32 rounds (control paths, node owners)"""
     x = np.asarray(x, dtype=np.uint64).copy()
     with np.errstate(over="ignore"):
         x *= np.uint64(0x9E3779B97F4A7C15)
@@ -62,17 +62,49 @@ def mix64(x: np.ndarray) -> np.ndarray:
     return x
 
 
-def key_hash(hi, lo, k: int) -> np.ndarray:
+_M32 = np.uint64(0xFFFFFFFF)
+
+
+def _mix32(x: np.ndarray, c1: int, s2: int, c2: int) -> np.ndarray:
+    """32-bit finalizer on u64 lanes holding 32-bit values"""
+    x = x & _M32
+    x = x ^ (x >> np.uint64(16))
+    x = (x * np.uint64(c1)) & _M32
+    x = x ^ (x >> np.uint64(s2))
+    x = (x * np.uint64(c2)) & _M32
+    return x ^ (x >> np.uint64(16))
+
+
+def _words(hi, lo):
+    hi = np.asarray(hi, dtype=np.uint64)
     lo = np.asarray(lo, dtype=np.uint64)
-    if k <= 32:
-        return mix64(lo)
+    return lo & _M32, lo >> np.uint64(32), hi & _M32, hi >> np.uint64(32)
+
+
+def place_hash(hi, lo, k: int) -> np.ndarray:
+    """KeyTraits<K>::place_hash of common.cuh: owner rank and sub-table come from it"""
+    w0, w1, w2, w3 = _words(hi, lo)
     with np.errstate(over="ignore"):
-        return mix64(lo ^ (np.asarray(hi, dtype=np.uint64) * np.uint64(0xA24BAED4963EE407)))
+        if k <= 32:
+            f = w1 + w0 * np.uint64(0x85EBCA77)
+        else:
+            f = w3 + w2 * np.uint64(0x85EBCA77) + w1 * np.uint64(0xC2B2AE3D) + w0 * np.uint64(0x27D4EB2F)
+    return _mix32(f, 0x7FEB352D, 15, 0x846CA68B)
+
+
+def slot_hash(hi, lo, k: int) -> np.ndarray:
+    """KeyTraits<K>::slot_hash of common.cuh: home slot inside the sub-table (its high bits: the page)"""
+    w0, w1, w2, w3 = _words(hi, lo)
+    with np.errstate(over="ignore"):
+        f = w0 + w1 * np.uint64(0x9E3779B1)
+        if k > 32:
+            f = f + w2 * np.uint64(0x85EBCA77) + w3 * np.uint64(0xC2B2AE3D)
+    return _mix32(f, 0x85EBCA6B, 13, 0xC2B2AE35)
 
 
 def owner_of(hi, lo, k: int, world: int, reverse_complement: bool = True) -> np.ndarray:
-    """owner rank = top 32 hash bits range-reduced to [0, world) (place_of in common.cuh)"""
+    """owner rank = place_hash range-reduced to [0, world) (place_of in common.cuh)"""
     if reverse_complement:
         hi, lo = canonical(hi, lo, k)
-    h = key_hash(hi, lo, k)
-    return (((h >> np.uint64(32)) * np.uint64(world)) >> np.uint64(32)).astype(np.int64)
+    h = place_hash(hi, lo, k)
+    return ((h * np.uint64(world)) >> np.uint64(32)).astype(np.int64)

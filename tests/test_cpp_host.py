@@ -57,3 +57,33 @@ def test_cpp_host_reproduces_the_reference_fixtures(exe, golden, tmp_path):
     # a missing file (builder.rs:57-77)
     r = run(exe, 40, 0, 0, 0, str(tmp_path / "nope.fastq"))
     assert r.returncode == 3
+
+
+@pytest.mark.gpu
+def test_cpp_host_on_several_shards_writes_the_same_dump(exe, tmp_path):
+    """One table sharded over 1, 2, 3, 4 and 8 devices (here: shards of one GPU, `--devices 0,0,...`; on a
+    multi-GPU box scripts/r02_multi.sh runs the same with distinct devices): the sorted edge dump of SURVEY
+    Appendix A.12 and the line of graph statistics are byte-identical, and Build::create stays one call."""
+    import numpy as np
+    rng = np.random.default_rng(12)
+    genome = "".join(rng.choice(list("ACGT"), size=40_000))
+    seqs = H.random_reads(rng, 6000, 70, 150, genome=genome, n_rate=0.02) + ["T" * 90, "AT" * 45, "ACGT" * 30]
+    fq = H.write_fastq(tmp_path / "reads.fastq", seqs)
+    for k, rc in ((31, 1), (40, 0), (63, 1)):
+        ref_line = ref_dump = None
+        for devices in (None, "0,0", "0,0,0", "0,0,0,0", "0,0,0,0,0,0,0,0"):
+            dump = tmp_path / f"dump_{k}_{devices}.txt"
+            args = (["--devices", devices] if devices else []) + ["--dump", dump, k, rc, 0, 0, fq]
+            r = run(exe, *args)
+            assert r.returncode == 0, (devices, r.stderr)
+            text = open(dump).read()
+            if ref_line is None:
+                ref_line, ref_dump = r.stdout, text
+                assert text.count("\n") == int(r.stdout.split()[2]) + 1
+            else:
+                assert r.stdout == ref_line, (k, devices)
+                assert text == ref_dump, (k, devices)
+    # the panics of the reference arrive through a sharded handle as well (hm_gir.rs:40)
+    short = H.write_fastq(tmp_path / "short.fastq", seqs[:50] + ["ACGTACGT"] + seqs[50:100])
+    r = run(exe, "--devices", "0,0", 31, 1, 0, 0, short)
+    assert r.returncode == 3 and "Read is too short!" in r.stderr

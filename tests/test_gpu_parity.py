@@ -176,24 +176,49 @@ def test_paged_update_path(K, k, rc):
     seqs += ["T" * (k + 20), "A" * (k + 7), "AT" * 60, "ACGT" * 40]
     cpu = _oracle(seqs, k, rc)
     import os
-    for kw, factor in (({}, None), ({"sub_table_log2_bytes": 18}, "0.001"), ({"edges_count": 2 * 30000 * 3}, "0.001")):
-        # KTG_STAGE_FACTOR: flush the staged buckets after every batch instead of once at the end
+    for kw, factor in (({}, None), ({"sub_table_log2_bytes": 18}, 1), ({"edges_count": 2 * 30000 * 3}, 1),
+                       ({"options": {"page_nbuf": 2}}, 1), ({"options": {"page_nbuf": 2, "page_threads": 1024}}, None)):
+        # stage_factor_milli = 1: flush the staged buckets after every batch instead of once at the end
+        g = K.GpuGIR(k, rc, force_pages=True, **kw)
         if factor:
-            os.environ["KTG_STAGE_FACTOR"] = factor
-        try:
-            g = K.GpuGIR(k, rc, force_pages=True, **kw)
-            third = len(seqs) // 3
-            for part in (seqs[:third], seqs[third:2 * third], seqs[2 * third:]):
-                g.add_reads(*H.batch_of(part))
-            _assert_same(g, cpu)
-            info = g.info()
-            assert info["page_updates"] == (3 if factor else 1) and info["partitioned"] == 1
-            g.reset()
-            g.add_reads(*H.batch_of(seqs))
-            _assert_same(g, cpu, full_stats=False)
-            g.close()
-        finally:
-            os.environ.pop("KTG_STAGE_FACTOR", None)
+            g.set_option("stage_factor_milli", factor)
+        third = len(seqs) // 3
+        for part in (seqs[:third], seqs[third:2 * third], seqs[2 * third:]):
+            g.add_reads(*H.batch_of(part))
+        _assert_same(g, cpu)
+        info = g.info()
+        assert info["page_updates"] == (3 if factor else 1) and info["partitioned"] == 1
+        g.reset()
+        g.add_reads(*H.batch_of(seqs))
+        _assert_same(g, cpu, full_stats=False)
+        g.close()
+
+
+@pytest.mark.parametrize("k,rc", [(31, True), (32, False), (63, True)])
+def test_heavy_hitters_overflow_the_page_buckets_without_loss(K, k, rc):
+    """Skewed input on the page path: 10 % homopolymer and dinucleotide reads put millions of windows on a
+    handful of canonical k-mers, far beyond what their pages' buckets hold (1.125 x mean + 1024).  The
+    overflow goes to the stage's spill list, which is as large as the stage, so the build neither fails
+    nor loses a key (the reference builds such inputs: hm_gir.rs:39-87 has no capacity anywhere)."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(5 * k + rc)
+    genome = "".join(rng.choice(list("ACGT"), size=200_000))
+    n = 60_000
+    seqs = [genome[i:i + 100] for i in rng.integers(0, len(genome) - 100, size=n)]
+    for i in range(0, n, 10):
+        seqs[i] = ("A" * 100, "T" * 100, "AC" * 50, "G" * 100, "ACGT" * 25)[(i // 10) % 5]
+    bases, offsets = H.batch_of(seqs)
+    m = O.MtCounter(k, rc)
+    m.add_reads(bases, offsets)
+    for kw in ({"force_pages": True, "sub_table_log2_bytes": 20, "edges_count": 900_000},
+               {"force_pages": True, "sub_table_log2_bytes": 20, "edges_count": 900_000, "options": {"chunk_mb": 1}},
+               {"force_pages": True}):
+        g = K.GpuGIR(k, rc, **kw)
+        assert g.add_reads(bases, offsets) == m.counters()
+        assert g.digest() == m.digest(), kw
+        assert g.info()["page_updates"] >= 1
+        g.close()
+    assert m.digest()[3] >= 1_200 * (100 - k + 1)  # one homopolymer k-mer alone: far more than a page bucket holds
 
 
 def test_paged_and_atomic_paths_agree_at_scale(K):
@@ -226,7 +251,7 @@ def test_paged_and_atomic_paths_agree_at_scale(K):
 
 @pytest.mark.parametrize("k,rc", [(31, True), (32, False), (40, True), (63, True)])
 def test_host_batcher_large_call(K, k, rc):
-    """ktg_add_reads on a call of many chunks (KTG_CHUNK_MB=1 makes a 5 MB batch "large"): tapered last
+    """ktg_add_reads on a call of many chunks (option chunk_mb=1 makes a 5 MB batch "large"): tapered last
     chunks, held-back flush with one flush on the way, and the eager page stage (every chunk's keys are
     moved on to page buckets at once, a flush is only the page sweep) -- against the oracle, with the
     eager stage off, with a table that has to grow at the flush (page buckets of a geometry that is
@@ -242,18 +267,16 @@ def test_host_batcher_large_call(K, k, rc):
     for name, seqs in (("uniform", uniform), ("ragged", ragged)):
         cases.append((name, seqs, _oracle(seqs, k, rc)))
     distinct = 2 * len(genome) * 2
-    os.environ["KTG_CHUNK_MB"] = "1"
     try:
         for name, seqs, cpu in cases:
             bases, offsets = H.batch_of(seqs)
             for kw, env in (({"force_pages": True, "sub_table_log2_bytes": 18, "edges_count": distinct}, {}),
-                            ({"force_pages": True, "sub_table_log2_bytes": 18, "edges_count": distinct}, {"KTG_NO_EAGER": "1"}),
-                            ({"force_pages": True, "sub_table_log2_bytes": 18, "edges_count": distinct}, {"KTG_FLUSH_PCT": "30", "KTG_STAGE_BUFS": "3"}),
+                            ({"force_pages": True, "sub_table_log2_bytes": 18, "edges_count": distinct}, {"eager_pages": 0}),
+                            ({"force_pages": True, "sub_table_log2_bytes": 18, "edges_count": distinct}, {"flush_pct": 30, "stage_bufs": 3}),
                             ({"force_pages": True, "sub_table_log2_bytes": 16, "edges_count": 3000}, {}),  # must grow
                             ({"force_pages": True, "sub_table_log2_bytes": 16}, {})):                     # no hint at all
-                os.environ.update(env)
                 try:
-                    g = K.GpuGIR(k, rc, profile=True, **kw)
+                    g = K.GpuGIR(k, rc, profile=True, options=dict(env, chunk_mb=1), **kw)
                     nr, nb = g.add_reads(bases, offsets)
                     assert (nr, nb) == (cpu.accepted_reads, cpu.accepted_bytes), (name, kw, env)
                     _assert_same(g, cpu, full_stats=False)
@@ -261,21 +284,20 @@ def test_host_batcher_large_call(K, k, rc):
                         sweeps, scatters = g.info()["page_updates"], g.profile()["scatter_pages"]["launches"]
                         assert sweeps >= 2, (name, g.info())  # the flush on the way + the final one
                         # eager: one level-2 scatter per chunk; otherwise one per sweep
-                        assert (scatters == sweeps) if "KTG_NO_EAGER" in env else (scatters >= 4 > sweeps), (scatters, sweeps)
+                        assert (scatters == sweeps) if "eager_pages" in env else (scatters >= 4 > sweeps), (scatters, sweeps)
                     g.close()
                 finally:
-                    for key in env:
-                        os.environ.pop(key, None)
+                    pass
         # two large calls into one builder; the second finds the first one's stage open
         name, seqs, cpu2 = cases[0][0], cases[0][1] + cases[1][1], None
         cpu2 = _oracle(seqs, k, rc)
-        g = K.GpuGIR(k, rc, force_pages=True, sub_table_log2_bytes=18, edges_count=distinct)
+        g = K.GpuGIR(k, rc, force_pages=True, sub_table_log2_bytes=18, edges_count=distinct, options={"chunk_mb": 1})
         g.add_reads(*H.batch_of(cases[0][1]))
         g.add_reads(*H.batch_of(cases[1][1]))
         _assert_same(g, cpu2, full_stats=False)
         g.close()
     finally:
-        os.environ.pop("KTG_CHUNK_MB", None)
+        pass
 
 
 @pytest.mark.parametrize("k,rc", [(4, True), (31, True), (32, False), (33, True), (34, False), (40, True), (63, True), (64, True)])
@@ -304,6 +326,46 @@ def test_graph_export_for_convert(K, k, rc):
             text = "".join("ACGT"[(edge >> (2 * (k - 1 - j))) & 3] for j in range(k)).encode()
             assert bytes(out["edge_bytes"][e]) == O.compress_edge(text)
     assert O.compress_edge(b"AGGTCG") == bytes([2, 0b00101011, 0b01100000])  # compress.rs:244-248
+    g.close()
+
+
+@pytest.mark.parametrize("k,rc,shards", [(5, True, 0), (31, True, 0), (31, False, 3), (40, False, 0), (63, True, 2)])
+def test_externals_seed_the_dead_path_search(K, k, rc, shards):
+    """ktg_export_externals == the `Externals` iterator of remove_dead_paths (pruner.rs:165-195) over the graph
+    Convert::create_from would build from the oracle's edges: node index ascending (sorted nodes), Input when
+    the node has no incoming edge, else Output when it has no outgoing edge.  Also after the filter, and on a
+    sharded handle."""
+    rng = np.random.default_rng(9 * k + rc)
+    genome = "".join(rng.choice(list("ACGT"), size=3000))
+    seqs = H.random_reads(rng, 300, max(k, 40), 120, genome=genome, n_rate=0.02) + ["ACGT" * 30, "T" * (k + 4)]
+    cpu = _oracle(seqs, k, rc)
+    g = K.GpuGIR(k, rc, **({"device_ids": [0] * shards} if shards else {}))
+    g.add_reads(*H.batch_of(seqs))
+
+    def twin(cpu):
+        ehi, elo, _ = cpu.export_edges()
+        edges = [(int(h) << 64) | int(l) for h, l in zip(ehi.tolist(), elo.tolist())]
+        mask = (1 << (2 * (k - 1))) - 1
+        nodes = sorted({e >> 2 for e in edges} | {e & mask for e in edges})
+        idx = {v: i for i, v in enumerate(nodes)}
+        has_out, has_in = set(idx[e >> 2] for e in edges), set(idx[e & mask] for e in edges)
+        ids, kinds = [], []
+        for v in range(len(nodes)):
+            if v not in has_in:
+                ids.append(v), kinds.append(0)
+            elif v not in has_out:
+                ids.append(v), kinds.append(1)
+        return np.array(ids, np.uint64), np.array(kinds, np.uint8)
+
+    for t in (0, 2):
+        if t:
+            g.remove_weak_edges(t), cpu.remove_weak_edges(t)
+        ids, kinds = g.export_externals()
+        want_ids, want_kinds = twin(cpu)
+        assert np.array_equal(ids, want_ids) and np.array_equal(kinds, want_kinds), (t, len(ids), len(want_ids))
+        st = g.collection_stats()  # sources + the sinks that are not sources
+        assert int((kinds == 0).sum()) == st["incoming_vert_count"]
+        assert len(ids) > 0 or k == 5  # (the 4^4 nodes of k = 5 all have edges both ways)
     g.close()
 
 
@@ -639,6 +701,90 @@ def test_superkmer_exchange_spill_route(K):
         g.close()
 
 
+@pytest.mark.parametrize("k,shards,rc", [(31, 2, True), (31, 4, True), (27, 8, True), (40, 3, False), (63, 2, True),
+                                          (32, 4, False), (23, 5, False)])
+def test_one_handle_over_several_shards(K, k, shards, rc, tmp_path):
+    """ktg_config.n_devices: ONE handle whose table is hash-sharded over `shards` devices (here all on GPU 0),
+    fed through the same ktg_add_reads / ktg_create_from_files, answering every query for the whole graph.
+    Keys exchange below 4 shards and for k outside 23..31, super-k-mer records otherwise.  Against the oracle:
+    counters, digest, sorted edges, node / degree statistics, the exported graph (identical to a one-GPU
+    handle's, node numbering included), filter, standardize, reset, several calls, file input, the short read."""
+    rng = np.random.default_rng(100 * k + shards)
+    genome = "".join(rng.choice(list("ACGT"), size=50_000))
+    seqs = H.random_reads(rng, 9000, max(k, 50), 170, genome=genome, n_rate=0.02)
+    seqs += ["T" * (k + 30), "A" * (k + 9), "AT" * 70, "ACGT" * 40] * 3
+    cpu = _oracle(seqs, k, rc)
+    bases, offsets = H.batch_of(seqs)
+    ids = [0] * shards
+    g = K.GpuGIR(k, rc, device_ids=ids, options={"chunk_mb": 1})  # several rounds per call
+    assert g.add_reads(bases, offsets) == (cpu.accepted_reads, cpu.accepted_bytes)
+    _assert_same(g, cpu)
+    one = K.GpuGIR(k, rc)
+    one.add_reads(bases, offsets)
+    ga, gb = g.export_graph(), one.export_graph()
+    assert sorted(ga) == sorted(gb)
+    for name in ga:
+        assert np.array_equal(ga[name], gb[name]), name
+    assert g.info()["windows_inserted"] == one.info()["windows_inserted"]
+    g.remove_weak_edges(2), cpu.remove_weak_edges(2)
+    _assert_same(g, cpu)
+    g.standardize_edges(40 * len(genome), k, 3), cpu.standardize_edges(40 * len(genome), k, 3)
+    _assert_same(g, cpu, full_stats=False)
+    with pytest.raises(K.KatomeError):
+        g.standardize_edges(k - 1, k, 1)  # G < k: degenerate (standardizer.rs:123-127)
+    # reset, then the same reads in three calls
+    g.reset()
+    cpu = _oracle(seqs, k, rc)
+    third = len(seqs) // 3
+    for part in (seqs[:third], seqs[third:2 * third], seqs[2 * third:]):
+        g.add_reads(*H.batch_of(part))
+    _assert_same(g, cpu, full_stats=False)
+    g.close(), one.close()
+    # Build::create from files on a sharded handle (builder.rs:42-54)
+    fq = H.write_fastq(tmp_path / "r.fastq", seqs)
+    g, nbytes = K.GpuGIR.create([fq], "fastq", rc, 0, k=k, device_ids=ids)
+    assert nbytes == cpu.accepted_bytes
+    _assert_same(g, cpu, full_stats=False)
+    g.close()
+    # an accepted read shorter than k voids the whole build (hm_gir.rs:40), whichever shard meets it
+    g = K.GpuGIR(k, rc, device_ids=ids)
+    with pytest.raises(K.ReadTooShort):
+        g.add_reads(*H.batch_of(seqs[:500] + ["ACGTA"] + seqs[500:900]))
+        g.finalize()
+    with pytest.raises(K.KatomeError):
+        g.digest()
+    g.reset()
+    g.add_reads(*H.batch_of(seqs[:100]))
+    assert g.digest() == _oracle(seqs[:100], k, rc).digest()
+    g.close()
+    # per-shard primitives are not offered on such a handle; bad device lists fail loudly
+    g = K.GpuGIR(k, rc, device_ids=ids)
+    with pytest.raises(K.KatomeError):
+        g.mg_plan(1000)
+    g.close()
+    with pytest.raises(K.KatomeError):
+        K.GpuGIR(k, rc, device_ids=[0, 99])
+
+
+def test_sharded_handle_with_skewed_input_takes_the_spill_route(K):
+    """poly-A reads send most windows to one owner: its receive bucket overflows and the rest travels by the
+    slow route (grouped by owner, through the host); nothing is lost, in either exchange"""
+    from oracle import oracle as O
+    rng = np.random.default_rng(77)
+    genome = "".join(rng.choice(list("ACGT"), size=30_000))
+    seqs = [genome[i:i + 120] for i in rng.integers(0, len(genome) - 120, size=20_000)]
+    for i in range(0, len(seqs), 2):
+        seqs[i] = "A" * 120 if i % 4 else "ACACACAC" * 15
+    bases, offsets = H.batch_of(seqs)
+    for k, shards in ((31, 2), (31, 4), (40, 4)):
+        m = O.MtCounter(k, True)
+        m.add_reads(bases, offsets)
+        g = K.GpuGIR(k, True, device_ids=[0] * shards)
+        assert g.add_reads(bases, offsets) == m.counters()
+        assert g.digest() == m.digest(), (k, shards)
+        g.close()
+
+
 def test_host_mirror_of_owner_matches_device(K):
     from katome_b200 import hashing
     rng = np.random.default_rng(9)
@@ -782,21 +928,15 @@ def test_baseline_config3_slice_against_the_oracle(K, name, n_reads):
 
 def _both_fastq_parsers(K, path, k, rc, chunk_kb=None):
     """Build::create through the device-side FASTQ parser and through the host reader (its twin)."""
-    import os
     out = []
     for host in (False, True):
-        env = {"KTG_HOST_PARSE": "1"} if host else ({"KTG_FASTQ_CHUNK_KB": str(chunk_kb)} if chunk_kb else {})
-        os.environ.update(env)
+        opts = {"host_parse": 1} if host else ({"fastq_chunk_kb": chunk_kb} if chunk_kb else {})
         try:
-            try:
-                g, nbytes = K.GpuGIR.create([path] if isinstance(path, str) else path, "fastq", rc, 0, k=k)
-                out.append(("ok", nbytes, g.digest(), g.counts()))
-                g.close()
-            except K.KatomeError as e:
-                out.append(("error", str(e)))
-        finally:
-            for key in env:
-                os.environ.pop(key, None)
+            g, nbytes = K.GpuGIR.create([path] if isinstance(path, str) else path, "fastq", rc, 0, k=k, options=opts)
+            out.append(("ok", nbytes, g.digest(), g.counts()))
+            g.close()
+        except K.KatomeError as e:
+            out.append(("error", str(e)))
     return out
 
 
@@ -837,6 +977,60 @@ def test_device_fastq_parser_matches_host_reader(K, tmp_path):
     cpu = _oracle(seqs + ragged, 40, True)
     p1, p2 = tmp_path / "plain.fastq", tmp_path / "ragged.fastq"
     dev, host = _both_fastq_parsers(K, [str(p1), str(p2)], 40, True, 2)
+    assert dev == host and dev[2] == cpu.digest() and dev[1] == cpu.accepted_bytes and dev[3] == cpu.counts()
+
+
+def test_device_fasta_parser_matches_host_reader(K, tmp_path):
+    """create_fasta (builder.rs:118-140) with the records cut on the device == the host reader (rust-bio 0.10
+    semantics: '>' opens a record, the other lines are appended after trimming trailing whitespace, the first
+    line must be a header): wrapped and unwrapped sequences, CRLF, blank lines, no final newline, a record
+    that is larger than a chunk (the chunk grows), empty files, errors."""
+    rng = np.random.default_rng(78)
+    seqs = H.golden_seqs("data2")
+    ragged = H.random_reads(rng, 300, 45, 400, n_rate=0.05)
+
+    def fasta(reads, width=60, nl="\n", final_nl=True, pad=""):
+        out = []
+        for i, sq in enumerate(reads):
+            out.append(f">read{i} some description{nl}")
+            w = width if width else max(1, len(sq))
+            out.extend(sq[j:j + w] + pad + nl for j in range(0, len(sq), w))
+        text = "".join(out)
+        return text if final_nl else text[: -len(nl)]
+
+    long_read = "".join(rng.choice(list("ACGT"), size=9000))
+    files = {
+        "wrapped": fasta(seqs), "one_line": fasta(seqs, width=0), "crlf": fasta(seqs, nl="\r\n"),
+        "no_final_newline": fasta(seqs, final_nl=False), "trailing_blanks": fasta(seqs, pad=" \t"),
+        "ragged": fasta(ragged, width=70), "empty": "", "one_record": fasta(seqs[:1]),
+        "blank_lines_inside": fasta(seqs[:20]).replace("\nA", "\n\nA", 5),
+        "larger_than_a_chunk": fasta([long_read] + seqs[:10] + [long_read[:5000]], width=80),
+    }
+    bad = {
+        "no_header_first": "ACGT\n>r\nACGT\n", "blank_first": "\n" + fasta(seqs[:3]),
+        "header_only_at_end": fasta(seqs[:4]) + ">lonely\n",  # an empty read: "Read is too short!" (hm_gir.rs:40)
+    }
+
+    def both(path, chunk_kb):
+        out = []
+        for opts in ({"fastq_chunk_kb": chunk_kb} if chunk_kb else {}, {"host_parse": 1}):
+            try:
+                g, nbytes = K.GpuGIR.create([path] if isinstance(path, str) else path, "fasta", True, 0, k=40, options=opts)
+                out.append(("ok", nbytes, g.digest(), g.counts()))
+                g.close()
+            except K.KatomeError as e:
+                out.append(("error", e.code))
+        return out
+
+    for name, text in {**files, **bad}.items():
+        p = tmp_path / f"{name}.fasta"
+        p.write_bytes(text.encode())
+        for chunk_kb in (None, 1, 3):
+            dev, host = both(str(p), chunk_kb)
+            assert dev == host, (name, chunk_kb, dev, host)
+            assert (dev[0] == "error") == (name in bad), (name, dev)
+    cpu = _oracle(seqs + ragged, 40, True)
+    dev, host = both([str(tmp_path / "wrapped.fasta"), str(tmp_path / "ragged.fasta")], 2)
     assert dev == host and dev[2] == cpu.digest() and dev[1] == cpu.accepted_bytes and dev[3] == cpu.counts()
 
 
