@@ -574,7 +574,7 @@ def consumer_legs(args, wl, g, h_bases, h_offs, n_local, dig, dev, stream):
         g.reset()
         g.add_reads_host_ptr(h_bases.data_ptr(), h_offs.data_ptr(), n_local)
         g.remove_weak_edges(3)
-        return g.export_graph()
+        return g.export_graph(pinned=True)
     try:
         dt, graph = best_of(export_step)
         d2h = sum(int(v.nbytes) for v in graph.values())
@@ -582,7 +582,7 @@ def consumer_legs(args, wl, g, h_bases, h_offs, n_local, dig, dev, stream):
                          "h2d_bytes_per_step": n_local * L, "d2h_bytes_per_step": d2h,
                          "nodes": int(len(graph["node_lo"])), "edges": int(len(graph["weight"])),
                          "what": "reset -> add_reads(host) -> remove_weak_edges(3) -> export_graph (sorted nodes, "
-                                 "src/dst/weight, compress_edge bytes) in host memory; sorts are cub (library)"}
+                                 "src/dst/weight, compress_edge bytes) in page-locked host memory from ktg_host_alloc; sorts are cub (library)"}
         del graph
     except Exception as e:  # noqa: BLE001 -- a leg that fails is reported, the headline stands
         out["export"] = {"error": repr(e)}

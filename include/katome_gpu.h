@@ -157,6 +157,11 @@ int ktg_export_edges(ktg_builder *b, uint64_t *key_hi, uint64_t *key_lo, uint32_
  *   edge_bytes  every edge in compress_edge format (compress.rs:250-271), ktg_edge_record_bytes()
  *               = 1 + ceil(k/4) bytes each: what SEQUENCES holds after kmer_to_edge
  * n_nodes / n_edges must be the values of ktg_counts; any output pointer may be NULL. */
+/* Builds that graph on the device and reports its sizes, so that the caller can allocate: the following
+ * ktg_export_graph / ktg_export_externals only copy (the device copy is dropped when the table changes).
+ * Optional -- both compute it on demand -- but it saves the separate node count of ktg_counts.  Buffers
+ * from ktg_host_alloc (pinned) take the copies at PCIe speed; pageable memory is several times slower. */
+int ktg_graph_prepare(ktg_builder *b, uint64_t *n_nodes, uint64_t *n_edges);
 int ktg_export_graph(ktg_builder *b, uint64_t *node_hi, uint64_t *node_lo, uint64_t n_nodes, uint64_t *src,
                      uint64_t *dst, uint32_t *weight, uint8_t *edge_bytes, uint64_t n_edges);
 uint32_t ktg_edge_record_bytes(const ktg_builder *b);

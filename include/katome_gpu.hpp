@@ -167,7 +167,9 @@ class GpuGIR {
     }
     // the input of Convert::create_from (girs/mod.rs:26-29)
     Graph to_graph() {
-        auto [nn, ne] = counts();
+        flush();
+        uint64_t nn = 0, ne = 0;
+        check(ktg_graph_prepare(h_, &nn, &ne)); // built on the device once; the export below only copies
         Graph g;
         g.edge_record_bytes = ktg_edge_record_bytes(h_);
         g.node_hi.resize(nn);

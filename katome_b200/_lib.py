@@ -28,7 +28,7 @@ SYMBOLS = (
     "ktg_standardize_edges", "ktg_export_edges", "ktg_digest", "ktg_key_words", "ktg_owner_of",
     "ktg_partition_reads_device", "ktg_insert_keys_device", "ktg_host_alloc", "ktg_host_free",
     "ktg_synth_reads_device", "ktg_random_access_probe", "ktg_get_profile", "ktg_reset_profile", "ktg_set_profile", "ktg_plan_chunks", "ktg_host_parse_file",
-    "ktg_get_info", "ktg_set_option", "ktg_export_externals", "ktg_partition_keys_device", "ktg_mg_plan", "ktg_mg_prepare",
+    "ktg_get_info", "ktg_set_option", "ktg_export_externals", "ktg_graph_prepare", "ktg_partition_keys_device", "ktg_mg_plan", "ktg_mg_prepare",
     "ktg_mg_scatter_reads_device", "ktg_mg_insert_buckets", "ktg_mg_sketch", "ktg_mg_merge_sketch", "ktg_mg_spill", "ktg_mg_insert_spill", "ktg_ipc_get_handle", "ktg_ipc_open", "ktg_ipc_close",
     "ktg_mg_skm_supported", "ktg_mg_skm_plan", "ktg_mg_skm_prepare", "ktg_mg_skm_scatter_reads_device",
     "ktg_mg_skm_insert_buckets", "ktg_mg_skm_spill", "ktg_mg_skm_partition_records", "ktg_mg_skm_insert_records",
@@ -114,6 +114,7 @@ def lib():
     L.ktg_digest.argtypes = [vp, u64p]
     L.ktg_export_graph.argtypes = [vp, vp, vp, C.c_uint64, vp, vp, vp, vp, C.c_uint64]
     L.ktg_export_externals.argtypes = [vp, vp, vp, C.c_uint64, u64p]
+    L.ktg_graph_prepare.argtypes = [vp, u64p, u64p]
     L.ktg_edge_record_bytes.argtypes = [vp]
     L.ktg_edge_record_bytes.restype = C.c_uint32
     L.ktg_key_words.argtypes = [vp]

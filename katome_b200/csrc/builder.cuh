@@ -257,11 +257,13 @@ struct BuilderBase {
     virtual int compact_edges_into(uint64_t *d_hi, uint64_t *d_lo, uint32_t *d_w, uint64_t cap) = 0;
     virtual int edges_to_host(uint64_t *d_hi, uint64_t *d_lo, uint32_t *d_w, uint64_t ne, int sorted, uint64_t *hi,
                               uint64_t *lo, uint32_t *w, uint64_t cap) = 0;
-    virtual int graph_to_host(uint64_t *d_ehi, uint64_t *d_elo, uint32_t *d_w, uint64_t ne, uint64_t *node_hi,
-                              uint64_t *node_lo, uint64_t n_nodes, uint64_t *src, uint64_t *dst, uint32_t *weight,
-                              uint8_t *edge_bytes, uint64_t n_edges) = 0;
-    virtual int externals_to_host(uint64_t *d_ehi, uint64_t *d_elo, uint32_t *d_w, uint64_t ne, uint64_t *ids,
-                                  uint8_t *kinds, uint64_t cap, uint64_t *n_out) = 0;
+    virtual int graph_build(Scratch &from, uint64_t *d_ehi, uint64_t *d_elo, uint32_t *d_w, uint64_t ne) = 0;
+    virtual int graph_prepare(uint64_t *n_nodes, uint64_t *n_edges) = 0;
+    virtual bool graph_ready() const = 0;
+    virtual void touch() = 0;
+    virtual int graph_to_host(uint64_t *node_hi, uint64_t *node_lo, uint64_t n_nodes, uint64_t *src, uint64_t *dst,
+                              uint32_t *weight, uint8_t *edge_bytes, uint64_t n_edges) = 0;
+    virtual int externals_to_host(uint64_t *ids, uint8_t *kinds, uint64_t cap, uint64_t *n_out) = 0;
     virtual int export_externals(uint64_t *ids, uint8_t *kinds, uint64_t cap, uint64_t *n_out) = 0;
     virtual int sync_stream() = 0;
     virtual int partition_reads(const uint8_t *d_bases, const uint64_t *d_offsets,
@@ -326,6 +328,24 @@ template <class K> struct Builder : BuilderBase {
     // lazily built node ((k-1)-mer) table
     bool nodes_valid = false;
     NodeStats node_cache{};
+    // The graph Convert::create_from loads, kept on the device between ktg_graph_prepare (which reports its
+    // sizes) and ktg_export_graph / ktg_export_externals (which copy it out); any change of the table drops it.
+    struct GraphCache {
+        Scratch sc;
+        KeyArr edges{nullptr, nullptr}, nodes{nullptr, nullptr};
+        uint32_t *w = nullptr;
+        uint64_t *src = nullptr, *dst = nullptr, ne = 0, nn = 0;
+        bool valid = false;
+        void clear() {
+            Scratch empty;
+            std::swap(sc.ptrs, empty.ptrs); // frees what the cache held
+            valid = false;
+        }
+    } graph;
+    void touch() override { // the table changed
+        nodes_valid = false;
+        if (graph.valid) graph.clear();
+    }
 
     ~Builder() override {
         cudaSetDevice(device);
@@ -678,7 +698,7 @@ template <class K> struct Builder : BuilderBase {
                                                          (uint8_t *)b_valid.p, d_ctr);
         }
         prof.end(stream);
-        nodes_valid = false;
+        touch();
         PackCounters c{};
         if (hint) { // no round trip: an upper bound on the windows is all the staging needs
             counters_stale = true;
@@ -830,7 +850,7 @@ template <class K> struct Builder : BuilderBase {
         insert_keys_kernel<K><<<g, 256, 0, stream>>>(keys, n, n_dev, d_lost, k, rc && (k % 2 == 0), skip_empty, tab, d_scratch + 14, bin_end,
                                                       bucket_cap, tiles_per_bin, n_tiles);
         prof.end(stream);
-        nodes_valid = false;
+        touch();
         return KTG_OK;
     }
     int launch_insert_keys(const K *keys, uint64_t n) { return launch_insert(keys, n, nullptr, 0, 0); }
@@ -919,7 +939,7 @@ template <class K> struct Builder : BuilderBase {
         else launch_p(update_pages_kernel<K, 512, 1>, 512, 1);
         prof.end(stream);
         fresh = false;
-        nodes_valid = false;
+        touch();
         ++page_updates;
         return KTG_OK;
     }
@@ -1070,7 +1090,7 @@ template <class K> struct Builder : BuilderBase {
         KTG_TRY(scatter(stage_bins, o));
         staged_keys += n_keys;
         l1_keys += n_keys;
-        nodes_valid = false;
+        touch();
         KTG_TRY(pages_drain());
         if (staged_keys >= stage_target && !hold_flush) KTG_TRY(flush_staged());
         return KTG_OK;
@@ -1226,7 +1246,7 @@ template <class K> struct Builder : BuilderBase {
         deferred_error = KTG_OK;
         windows_inserted = 0;
         windows_seen = 0;
-        nodes_valid = false;
+        touch();
         page_updates = 0;
         KTG_CUDA(cudaGetLastError());
         return KTG_OK;
@@ -1386,7 +1406,7 @@ template <class K> struct Builder : BuilderBase {
         prof.begin("standardize", n, stream);
         standardize_kernel<K><<<props.sms * 8, 256, 0, stream>>>(tab, p, t);
         prof.end(stream);
-        nodes_valid = false;
+        touch();
         KTG_CUDA(cudaGetLastError());
         return KTG_OK;
     }
@@ -1411,7 +1431,7 @@ template <class K> struct Builder : BuilderBase {
         prof.begin("filter", n, stream);
         filter_kernel<K><<<props.sms * 8, 256, 0, stream>>>(tab, t);
         prof.end(stream);
-        nodes_valid = false;
+        touch();
         KTG_CUDA(cudaGetLastError());
         return KTG_OK;
     }
@@ -1427,7 +1447,7 @@ template <class K> struct Builder : BuilderBase {
         prof.begin("standardize", n, stream);
         standardize_kernel<K><<<props.sms * 8, 256, 0, stream>>>(tab, p, t);
         prof.end(stream);
-        nodes_valid = false;
+        touch();
         KTG_CUDA(cudaGetLastError());
         return KTG_OK;
     }
@@ -1547,61 +1567,83 @@ template <class K> struct Builder : BuilderBase {
         return KTG_OK;
     }
 
-    int graph_to_host(uint64_t *d_ehi, uint64_t *d_elo, uint32_t *d_w, uint64_t ne, uint64_t *node_hi, uint64_t *node_lo,
-                      uint64_t n_nodes, uint64_t *src, uint64_t *dst, uint32_t *weight, uint8_t *edge_bytes,
-                      uint64_t n_edges) override {
-        Scratch sc;
-        KeyArr edges{d_ehi, d_elo};
-        KTG_TRY(sort_device_edges(sc, &edges, &d_w, ne));
+    // ne unsorted edges in device arrays of THIS device (owned by `from`, which the cache takes over) ->
+    // the device graph: sorted edges, sorted nodes, every edge's node indices
+    int graph_build(Scratch &from, uint64_t *d_ehi, uint64_t *d_elo, uint32_t *d_w, uint64_t ne) override {
+        graph.clear();
+        std::swap(graph.sc.ptrs, from.ptrs);
+        graph.edges = KeyArr{d_ehi, d_elo};
+        graph.w = d_w;
+        graph.ne = ne;
+        int rc_ = sort_device_edges(graph.sc, &graph.edges, &graph.w, ne);
+        if (rc_ == KTG_OK) rc_ = device_graph(graph.sc, graph.edges, ne, &graph.nodes, &graph.nn, &graph.src, &graph.dst);
+        if (rc_ != KTG_OK) {
+            graph.clear();
+            return rc_;
+        }
+        graph.valid = true;
+        return KTG_OK;
+    }
+    int graph_prepare(uint64_t *n_nodes, uint64_t *n_edges) override {
+        if (!graph.valid) {
+            Scratch sc;
+            KeyArr edges;
+            uint32_t *d_w;
+            uint64_t ne = 0;
+            KTG_TRY(device_edges(false, sc, &edges, &d_w, &ne));
+            KTG_TRY(graph_build(sc, edges.hi, edges.lo, d_w, ne));
+        }
+        if (n_nodes) *n_nodes = graph.nn;
+        if (n_edges) *n_edges = graph.ne;
+        return KTG_OK;
+    }
+    bool graph_ready() const override { return graph.valid; }
+
+    int graph_to_host(uint64_t *node_hi, uint64_t *node_lo, uint64_t n_nodes, uint64_t *src, uint64_t *dst, uint32_t *weight,
+                      uint8_t *edge_bytes, uint64_t n_edges) override {
+        const uint64_t ne = graph.ne, nn = graph.nn;
         if (ne != n_edges) return fail(KTG_ERR_INVALID, "n_edges is %llu, the graph has %llu edges (ktg_counts)",
                                        (unsigned long long)n_edges, (unsigned long long)ne);
-        KeyArr nodes{nullptr, nullptr};
-        uint64_t nn = 0, *d_src = nullptr, *d_dst = nullptr;
-        KTG_TRY(device_graph(sc, edges, ne, &nodes, &nn, (src || dst) ? &d_src : nullptr, &d_dst));
         if (nn != n_nodes) return fail(KTG_ERR_INVALID, "n_nodes is %llu, the graph has %llu nodes (ktg_counts)",
                                        (unsigned long long)n_nodes, (unsigned long long)nn);
         if (ne == 0) return sync();
-        if (src) KTG_CUDA(cudaMemcpyAsync(src, d_src, ne * 8, cudaMemcpyDeviceToHost, stream));
-        if (dst) KTG_CUDA(cudaMemcpyAsync(dst, d_dst, ne * 8, cudaMemcpyDeviceToHost, stream));
+        Scratch sc;
+        if (src) KTG_CUDA(cudaMemcpyAsync(src, graph.src, ne * 8, cudaMemcpyDeviceToHost, stream));
+        if (dst) KTG_CUDA(cudaMemcpyAsync(dst, graph.dst, ne * 8, cudaMemcpyDeviceToHost, stream));
         if (edge_bytes) {
             const size_t rec = (k + 3) / 4 + 1;
             uint8_t *d_b;
             KTG_TRY(sc.alloc(&d_b, ne * rec));
             prof.begin("edge_bytes", ne, stream);
-            edge_bytes_kernel<<<export_grid(ne), 256, 0, stream>>>(edges.hi, edges.lo, ne, k, d_b);
+            edge_bytes_kernel<<<export_grid(ne), 256, 0, stream>>>(graph.edges.hi, graph.edges.lo, ne, k, d_b);
             prof.end(stream);
             KTG_CUDA(cudaMemcpyAsync(edge_bytes, d_b, ne * rec, cudaMemcpyDeviceToHost, stream));
         }
-        if (weight) KTG_CUDA(cudaMemcpyAsync(weight, d_w, ne * 4, cudaMemcpyDeviceToHost, stream));
-        if (node_lo) KTG_CUDA(cudaMemcpyAsync(node_lo, nodes.lo, nn * 8, cudaMemcpyDeviceToHost, stream));
+        if (weight) KTG_CUDA(cudaMemcpyAsync(weight, graph.w, ne * 4, cudaMemcpyDeviceToHost, stream));
+        if (node_lo) KTG_CUDA(cudaMemcpyAsync(node_lo, graph.nodes.lo, nn * 8, cudaMemcpyDeviceToHost, stream));
         if (node_hi) {
-            if (nodes.hi) KTG_CUDA(cudaMemcpyAsync(node_hi, nodes.hi, nn * 8, cudaMemcpyDeviceToHost, stream));
+            if (graph.nodes.hi) KTG_CUDA(cudaMemcpyAsync(node_hi, graph.nodes.hi, nn * 8, cudaMemcpyDeviceToHost, stream));
             else memset(node_hi, 0, nn * 8);
         }
         KTG_CUDA(cudaGetLastError());
-        return sync(); // before the scratch buffers are freed
+        return sync(); // before the scratch buffer is freed
     }
 
     // The seeds of remove_dead_paths (pruner.rs:165-195, `Externals`): in ascending node index (the
     // numbering of graph_to_host), every node without an incoming edge as Input (kind 0), else every
     // node without an outgoing edge as Output (kind 1).
-    int externals_to_host(uint64_t *d_ehi, uint64_t *d_elo, uint32_t *d_w, uint64_t ne, uint64_t *ids, uint8_t *kinds,
-                          uint64_t cap, uint64_t *n_out) override {
-        Scratch sc;
-        KeyArr edges{d_ehi, d_elo};
-        KTG_TRY(sort_device_edges(sc, &edges, &d_w, ne));
-        KeyArr nodes{nullptr, nullptr};
-        uint64_t nn = 0, *d_src = nullptr, *d_dst = nullptr;
-        KTG_TRY(device_graph(sc, edges, ne, &nodes, &nn, &d_src, &d_dst));
+    int externals_to_host(uint64_t *ids, uint8_t *kinds, uint64_t cap, uint64_t *n_out) override {
+        const uint64_t ne = graph.ne, nn = graph.nn;
         if (n_out) *n_out = 0;
         if (nn == 0) return sync();
+        Scratch sc;
         uint32_t *deg, *flag, *pos;
         KTG_TRY(sc.alloc(&deg, nn));
         KTG_TRY(sc.alloc(&flag, nn + 1));
         KTG_TRY(sc.alloc(&pos, nn + 1));
         KTG_CUDA(cudaMemsetAsync(deg, 0, nn * 4, stream));
         prof.begin("externals", nn, stream);
-        mark_degrees_kernel<<<export_grid(ne), 256, 0, stream>>>(d_src, d_dst, ne, deg);
+        mark_degrees_kernel<<<export_grid(ne), 256, 0, stream>>>(graph.src, graph.dst, ne, deg);
         external_flags_kernel<<<export_grid(nn + 1), 256, 0, stream>>>(deg, nn, flag);
         size_t tb = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tb, flag, pos, (int)(nn + 1), stream);
@@ -1627,23 +1669,16 @@ template <class K> struct Builder : BuilderBase {
         return sync();
     }
 
-    int export_externals(uint64_t *ids, uint8_t *kinds, uint64_t cap, uint64_t *n_out) override {
-        Scratch sc;
-        KeyArr edges;
-        uint32_t *d_w;
-        uint64_t ne = 0;
-        KTG_TRY(device_edges(false, sc, &edges, &d_w, &ne));
-        return externals_to_host(edges.hi, edges.lo, d_w, ne, ids, kinds, cap, n_out);
-    }
-
     int export_graph(uint64_t *node_hi, uint64_t *node_lo, uint64_t n_nodes, uint64_t *src, uint64_t *dst,
                      uint32_t *weight, uint8_t *edge_bytes, uint64_t n_edges) override {
-        Scratch sc;
-        KeyArr edges;
-        uint32_t *d_w;
-        uint64_t ne = 0;
-        KTG_TRY(device_edges(false, sc, &edges, &d_w, &ne));
-        return graph_to_host(edges.hi, edges.lo, d_w, ne, node_hi, node_lo, n_nodes, src, dst, weight, edge_bytes, n_edges);
+        KTG_TRY(finalize());
+        KTG_TRY(graph_prepare(nullptr, nullptr));
+        return graph_to_host(node_hi, node_lo, n_nodes, src, dst, weight, edge_bytes, n_edges);
+    }
+    int export_externals(uint64_t *ids, uint8_t *kinds, uint64_t cap, uint64_t *n_out) override {
+        KTG_TRY(finalize());
+        KTG_TRY(graph_prepare(nullptr, nullptr));
+        return externals_to_host(ids, kinds, cap, n_out);
     }
 
     // ---- multi-GPU phases -------------------------------------------------------------------
@@ -1722,7 +1757,7 @@ template <class K> struct Builder : BuilderBase {
         else insert_weighted_kmers_kernel<K, false><<<g, 256, 0, stream>>>(d_kmers, d_weights, n, k, threshold, tab, (unsigned long long *)b_bfc_ctr.p);
         prof.end(stream);
         KTG_CUDA(cudaGetLastError());
-        nodes_valid = false;
+        touch();
         unsigned long long c[2] = {0, 0};
         KTG_CUDA(cudaMemcpyAsync(c, b_bfc_ctr.p, 16, cudaMemcpyDeviceToHost, stream));
         KTG_TRY(sync());

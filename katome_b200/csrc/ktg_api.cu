@@ -817,6 +817,13 @@ int ktg_export_graph(ktg_builder *b, uint64_t *node_hi, uint64_t *node_lo, uint6
     return b->impl->export_graph(node_hi, node_lo, n_nodes, src, dst, weight, edge_bytes, n_edges);
 }
 
+int ktg_graph_prepare(ktg_builder *b, uint64_t *n_nodes, uint64_t *n_edges) {
+    KTG_ENTER(b);
+    if (b->multi) return b->multi->graph_prepare(n_nodes, n_edges);
+    KTG_TRY(b->impl->finalize());
+    return b->impl->graph_prepare(n_nodes, n_edges);
+}
+
 int ktg_export_externals(ktg_builder *b, uint64_t *node_ids, uint8_t *kinds, uint64_t cap, uint64_t *n) {
     KTG_ENTER(b);
     if (b->multi) return b->multi->export_externals(node_ids, kinds, cap, n);

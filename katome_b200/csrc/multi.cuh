@@ -195,6 +195,7 @@ struct MultiBuilder {
     int add_reads(const uint8_t *bases, const uint64_t *offsets, uint64_t n_reads, uint64_t *acc_reads, uint64_t *acc_bytes) {
         KTG_TRY(check_state());
         if (n_reads == 0) return KTG_OK;
+        touch();
         uint64_t r0c = 0, b0c = 0;
         if (acc_reads || acc_bytes) KTG_TRY(read_counters(&r0c, &b0c));
         // shares: contiguous blocks of reads with about the same number of bases
@@ -445,6 +446,7 @@ struct MultiBuilder {
         deferred_error = KTG_OK;
         deferred_msg.clear();
         exchanged_bytes = 0;
+        touch();
         return parallel([&](uint32_t i) -> int { return sh[i]->reset(); });
     }
     int set_option(const char *name, int64_t value, int (*apply)(BuilderBase *, const char *, int64_t)) {
@@ -485,10 +487,12 @@ struct MultiBuilder {
         int rc_ = keys.ensure(total * kb + 64);
         if (rc_ == KTG_OK) rc_ = deg.ensure(total * 4 + 64);
         uint64_t off = 0;
+        // on the first shard's stream, which the merge kernels follow (a device-to-device cudaMemcpyPeer
+        // does not wait on the host side, and that stream does not synchronise with the default stream)
         for (uint32_t i = 0; i < n && rc_ == KTG_OK; ++i) {
             if (cnt[i]) {
-                if (cudaMemcpyPeer((char *)keys.p + off * kb, dev[0], pk[i], dev[i], cnt[i] * kb) != cudaSuccess ||
-                    cudaMemcpyPeer((char *)deg.p + off * 4, dev[0], pd[i], dev[i], cnt[i] * 4) != cudaSuccess)
+                if (cudaMemcpyPeerAsync((char *)keys.p + off * kb, dev[0], pk[i], dev[i], cnt[i] * kb, sh[0]->stream) != cudaSuccess ||
+                    cudaMemcpyPeerAsync((char *)deg.p + off * 4, dev[0], pd[i], dev[i], cnt[i] * 4, sh[0]->stream) != cudaSuccess)
                     rc_ = fail(KTG_ERR_CUDA, "gathering the shards' nodes failed: %s", cudaGetErrorString(cudaGetLastError()));
             }
             off += cnt[i];
@@ -501,6 +505,7 @@ struct MultiBuilder {
 
     int remove_weak_edges(uint32_t t) {
         KTG_TRY(check_state());
+        touch();
         return parallel([&](uint32_t i) -> int { return sh[i]->remove_weak_edges(t); });
     }
 
@@ -512,6 +517,7 @@ struct MultiBuilder {
             return fail(KTG_ERR_DEGENERATE, "degenerate standardization ratio (G=%llu k=%llu s=%llu l=%llu)",
                         (unsigned long long)G, (unsigned long long)k_, es.sum_w, es.sum_w_below);
         const double p = (double)(G - k_) / (double)(es.sum_w - es.sum_w_below);
+        touch();
         return parallel([&](uint32_t i) -> int { return sh[i]->scale_weights(p, t); });
     }
 
@@ -556,23 +562,31 @@ struct MultiBuilder {
         return sh[0]->edges_to_host(d_hi, d_lo, d_w, ne, sorted, hi, lo, w, cap);
     }
 
+    // the device graph of the whole table lives on the first device (its builder's cache)
+    int graph_prepare(uint64_t *n_nodes, uint64_t *n_edges) {
+        KTG_TRY(check_state());
+        if (!sh[0]->graph_ready()) {
+            Scratch sc;
+            uint64_t *d_hi, *d_lo, ne = 0;
+            uint32_t *d_w;
+            KTG_TRY(gather_edges(sc, &d_hi, &d_lo, &d_w, &ne));
+            KTG_CUDA(cudaSetDevice(dev[0]));
+            KTG_TRY(sh[0]->graph_build(sc, d_hi, d_lo, d_w, ne));
+        }
+        KTG_CUDA(cudaSetDevice(dev[0]));
+        return sh[0]->graph_prepare(n_nodes, n_edges);
+    }
     int export_graph(uint64_t *node_hi, uint64_t *node_lo, uint64_t n_nodes, uint64_t *src, uint64_t *dst, uint32_t *weight,
                      uint8_t *edge_bytes, uint64_t n_edges) {
-        Scratch sc;
-        uint64_t *d_hi, *d_lo, ne = 0;
-        uint32_t *d_w;
-        KTG_TRY(gather_edges(sc, &d_hi, &d_lo, &d_w, &ne));
-        KTG_CUDA(cudaSetDevice(dev[0]));
-        return sh[0]->graph_to_host(d_hi, d_lo, d_w, ne, node_hi, node_lo, n_nodes, src, dst, weight, edge_bytes, n_edges);
+        KTG_TRY(graph_prepare(nullptr, nullptr));
+        return sh[0]->graph_to_host(node_hi, node_lo, n_nodes, src, dst, weight, edge_bytes, n_edges);
     }
-
     int export_externals(uint64_t *ids, uint8_t *kinds, uint64_t cap, uint64_t *n_out) {
-        Scratch sc;
-        uint64_t *d_hi, *d_lo, ne = 0;
-        uint32_t *d_w;
-        KTG_TRY(gather_edges(sc, &d_hi, &d_lo, &d_w, &ne));
-        KTG_CUDA(cudaSetDevice(dev[0]));
-        return sh[0]->externals_to_host(d_hi, d_lo, d_w, ne, ids, kinds, cap, n_out);
+        KTG_TRY(graph_prepare(nullptr, nullptr));
+        return sh[0]->externals_to_host(ids, kinds, cap, n_out);
+    }
+    void touch() { // any shard changed: the gathered graph is stale
+        if (!sh.empty() && sh[0]) sh[0]->touch();
     }
 
     int info(ktg_info *out) {

@@ -69,6 +69,20 @@ class DeviceArray:
 _FILE_TYPES = {"fastq": L.KTG_FASTQ, "fasta": L.KTG_FASTA}
 
 
+def _pinned_empty(shape, dtype) -> np.ndarray:
+    """numpy array over page-locked host memory (ktg_host_alloc), freed with the array"""
+    import weakref
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) if not isinstance(shape, int) else int(shape)
+    nbytes = max(n * dt.itemsize, 1)
+    p = C.c_void_p()
+    _check(L.lib().ktg_host_alloc(C.byref(p), nbytes))
+    buf = (C.c_uint8 * nbytes).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dt, count=n).reshape(shape)
+    weakref.finalize(buf, L.lib().ktg_host_free, p.value)
+    return arr
+
+
 class GpuGIR:
     """De Bruijn graph intermediate representation built on one B200.
 
@@ -268,14 +282,18 @@ class GpuGIR:
         assert n.value == ne
         return hi, lo, w
 
-    def export_graph(self) -> dict:
+    def export_graph(self, pinned: bool = False) -> dict:
         """What Convert::create_from builds (hm_gir.rs:156-226), canonical numbering: sorted
-        nodes, sorted edges as (src index, dst index, weight) and in compress_edge bytes."""
-        nn, ne = self.counts()
+        nodes, sorted edges as (src index, dst index, weight) and in compress_edge bytes.
+        pinned: the arrays live in page-locked memory (ktg_host_alloc), which takes the copies at PCIe speed."""
+        n, e = C.c_uint64(0), C.c_uint64(0)
+        _check(self._L.ktg_graph_prepare(self._h, C.byref(n), C.byref(e)))
+        nn, ne = n.value, e.value
         rec = int(self._L.ktg_edge_record_bytes(self._h))
-        out = {"node_hi": np.zeros(nn, np.uint64), "node_lo": np.zeros(nn, np.uint64),
-               "src": np.zeros(ne, np.uint64), "dst": np.zeros(ne, np.uint64), "weight": np.zeros(ne, np.uint32),
-               "edge_bytes": np.zeros((ne, rec), np.uint8)}
+        new = _pinned_empty if pinned else (lambda shape, dt: np.zeros(shape, dt))
+        out = {"node_hi": new(nn, np.uint64), "node_lo": new(nn, np.uint64),
+               "src": new(ne, np.uint64), "dst": new(ne, np.uint64), "weight": new(ne, np.uint32),
+               "edge_bytes": new((ne, rec), np.uint8)}
         _check(self._L.ktg_export_graph(self._h, out["node_hi"].ctypes.data, out["node_lo"].ctypes.data, nn,
                                         out["src"].ctypes.data, out["dst"].ctypes.data, out["weight"].ctypes.data,
                                         out["edge_bytes"].ctypes.data, ne))

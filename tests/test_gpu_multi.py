@@ -81,3 +81,39 @@ def test_two_gpu_sharded_build_matches_oracle(tmp_path):
                        env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("ok") == 2
+
+
+def test_one_handle_over_two_real_gpus(tmp_path):
+    """ktg_config.n_devices over DISTINCT devices (peer memory over NVLink, no torch.distributed, one
+    process): against the oracle and against the same build on one GPU, exports included."""
+    import numpy as np
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import katome_b200 as K
+    from oracle import oracle as O
+    from tests import helpers as H
+    n_dev = min(torch.cuda.device_count(), 8)
+    for k, ids in ((31, [0, 1]), (63, [1, 0]), (31, list(range(n_dev))), (40, list(range(n_dev)))):
+        n, L, G = 40_000, 150, 300_000
+        reads = O.synth_reads(1234 + k, G, L, 5000, 0, n)
+        offsets = np.arange(n + 1, dtype=np.uint64) * L
+        cpu = O.OracleGIR(k)
+        cpu.add_reads(reads, offsets, True)
+        g = K.GpuGIR(k, True, device_ids=ids, options={"chunk_mb": 1})
+        assert g.add_reads(reads, offsets) == (cpu.accepted_reads, cpu.accepted_bytes)
+        assert g.digest() == cpu.digest() and g.counts() == cpu.counts()
+        one = K.GpuGIR(k, True, device=0)
+        one.add_reads(reads, offsets)
+        ga, gb = g.export_graph(), one.export_graph()
+        for name in ga:
+            assert np.array_equal(ga[name], gb[name]), (k, ids, name)
+        for a, b in zip(g.export_externals(), one.export_externals()):
+            assert np.array_equal(a, b)
+        a, b = g.collection_stats(), cpu.collection_stats()
+        for key in b:
+            assert a[key] == b[key] or (a[key] != a[key] and b[key] != b[key]), (k, ids, key)
+        g.remove_weak_edges(3), cpu.remove_weak_edges(3)
+        g.standardize_edges(G, k, 3), cpu.standardize_edges(G, k, 3)
+        assert g.digest() == cpu.digest() and g.counts() == cpu.counts()
+        g.close(), one.close()
