@@ -283,7 +283,6 @@ def run_ours(args):
     else:
         sg = ShardedGIR(k, args.rc, edges_count=hint, profile=True, sub_table_log2_bytes=args.sub_log2,
                         exchange=args.exchange, options=args.options)
-        exchange = sg.exchange
         def step():
             sg.reset()
             feed(sg.add_reads_device)
@@ -327,6 +326,8 @@ def run_ours(args):
     assert dig[2] == (2 if args.rc else 1) * windows_total, (dig, windows_total)
     ms_step = ms / args.steps
     value = windows_total / (ms_step * 1e-3)
+    if sg is not None:
+        exchange = sg.last_exchange
 
     # ---- end to end: pinned host reads -> H2D -> build -> D2H of the digest, every step
     e2e = None
@@ -663,7 +664,7 @@ def main():
                     help="sample of the multi-threaded optimistic CPU counter")
     ap.add_argument("--no-probe", action="store_true", help="skip the random-access roofline probe")
     ap.add_argument("--sub-log2", type=int, default=0)
-    ap.add_argument("--exchange", default=None, choices=["fused", "skm", "keys", "nccl"],
+    ap.add_argument("--exchange", default=None, choices=["fused", "direct", "skm", "keys", "nccl"],
                     help="N > 1: which exchange (default: the measured winner for this world size and k)")
     ap.add_argument("--batches", type=int, default=0, help="add_reads calls per step (0: one)")
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",

@@ -91,7 +91,12 @@ int ktg_device_count(void);
  * bases: concatenated ASCII reads on the HOST, read r = [offsets[r], offsets[r+1]).
  * A read with any byte outside "ACGT" is dropped whole; an accepted read
  * shorter than k returns KTG_ERR_SHORT_READ and voids the build.
- * accepted_* are incremented (not overwritten) when non-NULL. */
+ * accepted_* are incremented (not overwritten) when non-NULL.
+ * BUFFER LIFETIME: with page-locked buffers (ktg_host_alloc) and both accepted_* NULL the call returns while the
+ * copies of `bases` / `offsets` to the device may still be in flight, so that the caller can prepare its next
+ * batch meanwhile.  The buffers must stay valid and untouched until ktg_wait_input, ktg_finalize or any query
+ * (ktg_counts, ktg_digest, ...) has returned; with accepted_* non-NULL, or pageable memory, they are free on
+ * return.  (Multi-device handles always return with the copies done.) */
 int ktg_add_reads(ktg_builder *b, const uint8_t *bases, const uint64_t *offsets, uint64_t n_reads,
                   uint64_t *accepted_reads, uint64_t *accepted_bytes);
 
@@ -107,6 +112,9 @@ int ktg_add_reads_device(ktg_builder *b, const void *d_bases, const void *d_offs
  * total_bytes = second element of the reference's return tuple. */
 int ktg_create_from_files(ktg_builder *b, const char *const *paths, uint32_t n_paths,
                           int file_type, uint64_t *total_bytes);
+
+/* Waits until the device has its own copy of everything passed to ktg_add_reads so far (see BUFFER LIFETIME). */
+int ktg_wait_input(ktg_builder *b);
 
 /* Default::default() again (builder.rs:145): empties the collection but keeps the
  * device allocations, so that repeated builds do not pay cudaMalloc. */
@@ -182,6 +190,10 @@ int ktg_export_externals(ktg_builder *b, uint64_t *node_ids, uint8_t *kinds, uin
  * weight[kmer] += count, and weight[revcomp(kmer)] += count with reverse_complement.
  * *accepted_bytes += k per accepted k-mer (builder.rs:109).  BFCounter's k-mers are unique
  * (pt_graph.rs:78); a repeated one adds up here where petgraph would hold parallel edges.
+ * DEVIATION: weight 0 means "not an edge" in this table.  A line with count 0 (only reachable with
+ * minimal_weight_threshold == 0; BFCounter never writes one) is accepted and counted in accepted_* like the
+ * reference does, but adds no edge, where the reference would add an edge of weight 0; likewise an edge whose
+ * u32 weight wraps to exactly 0 (2^32 occurrences) disappears.
  * Single GPU.  ktg_create_from_bfc_files reads "<k-mer>\t<count>" lines and finalizes. */
 int ktg_add_weighted_kmers(ktg_builder *b, const uint8_t *kmers, const uint32_t *weights, uint64_t n,
                            uint32_t minimal_weight_threshold, uint64_t *accepted_kmers, uint64_t *accepted_bytes);
@@ -256,6 +268,27 @@ int ktg_mg_sketch(ktg_builder *b, void **d_regs, uint32_t *n_regs);
 int ktg_mg_merge_sketch(ktg_builder *b, const void *d_regs);
 int ktg_mg_spill(ktg_builder *b, void **d_keys, uint64_t *n);
 int ktg_mg_insert_spill(ktg_builder *b, const void *d_keys, uint64_t n);
+/* ---- the DIRECT exchange: the sender does the owner's level-1 partition as well.  Its extraction kernel bins
+ * every key by (owner, sub-table of the owner) -- world x n_sub bins, as many as the one-GPU build of the same
+ * table has -- and writes the runs into the owner's receive bucket for (this sender, that sub-table); the owner
+ * goes straight to its page level (ktg_mg_direct_insert: level-2 scatter + page sweep), without the extra pass
+ * over the received keys that ktg_mg_insert_buckets needs.  Every shard must have the same geometry:
+ *   ktg_mg_direct_plan      n_sub / sub_log2 of this shard (all-reduce them: use this exchange only when all
+ *                           ranks agree) and whether ktg_mg_direct_prepare would replace the receive buffer;
+ *   ktg_mg_direct_prepare   bucket_cap keys per (source, sub-table) bucket, world * n_sub buckets per slot;
+ *   ktg_mg_direct_scatter_reads_device   *d_cursors: world * n_sub u64 bucket ends, owner-major
+ *                           ((owner * n_sub + sub) * bucket_cap + fill); send n_sub of them to every owner.
+ *                           A batch may be scattered in several calls (chunks of a host batch, copied while
+ *                           the previous chunk is scattered): only the first passes first_of_batch, the
+ *                           others append to the same buckets, and the owners insert once at the end;
+ *   the sketch is all-reduced as above; ktg_mg_direct_insert(ends[source * n_sub + sub] = (source * n_sub +
+ *   sub) * bucket_cap + fill, exact key count); spills: ktg_mg_spill and on as above. */
+int ktg_mg_direct_plan(ktg_builder *b, uint64_t max_windows, int *needs_realloc, uint32_t *n_sub, uint32_t *sub_log2);
+int ktg_mg_direct_prepare(ktg_builder *b, uint64_t max_windows, void **rx_base, uint64_t *rx_bytes, uint64_t *bucket_cap);
+int ktg_mg_direct_scatter_reads_device(ktg_builder *b, const void *d_bases, const void *d_offsets, uint64_t n_reads,
+                                       uint64_t total_bases, void *const *peer_rx, uint32_t slot, int first_of_batch,
+                                       void *send_stream, void **d_cursors);
+int ktg_mg_direct_insert(ktg_builder *b, const void *d_bucket_ends, uint64_t n_keys, uint32_t slot);
 /* ---- the fused exchange in SUPER-K-MER records (23 <= k <= 31).  The owner of a k-mer is a
  * function of its minimizer (smallest hashed canonical (k-15)-mer inside it); consecutive windows
  * of a read mostly share it, so a run of n <= 16 windows travels over NVLink as ONE 16-byte
@@ -340,7 +373,7 @@ int ktg_host_parse_file(const char *path, int file_type, uint64_t batch_bytes, u
  * library reads the environment).  Names: page_threads, page_nbuf, page_log2, l2s_variant, l1_ctas,
  * p2p_ctas, chunk_mb, stage_bufs, flush_pct, flush_pct2, taper, eager_pages, stage_factor_milli,
  * stage_max_keys, host_parse (ktg_create_from_files: records cut by the host reader instead of the
- * device), fastq_chunk_kb, mg_pad, trace (host timeline on stderr).  Unknown names: KTG_ERR_INVALID. */
+ * device), fastq_chunk_kb, mg_pad, mg_direct, trace (host timeline on stderr).  Unknown names: KTG_ERR_INVALID. */
 int ktg_set_option(ktg_builder *b, const char *name, int64_t value);
 
 typedef struct ktg_info {

@@ -28,8 +28,9 @@ SYMBOLS = (
     "ktg_standardize_edges", "ktg_export_edges", "ktg_digest", "ktg_key_words", "ktg_owner_of",
     "ktg_partition_reads_device", "ktg_insert_keys_device", "ktg_host_alloc", "ktg_host_free",
     "ktg_synth_reads_device", "ktg_random_access_probe", "ktg_get_profile", "ktg_reset_profile", "ktg_set_profile", "ktg_plan_chunks", "ktg_host_parse_file",
-    "ktg_get_info", "ktg_set_option", "ktg_export_externals", "ktg_graph_prepare", "ktg_partition_keys_device", "ktg_mg_plan", "ktg_mg_prepare",
-    "ktg_mg_scatter_reads_device", "ktg_mg_insert_buckets", "ktg_mg_sketch", "ktg_mg_merge_sketch", "ktg_mg_spill", "ktg_mg_insert_spill", "ktg_ipc_get_handle", "ktg_ipc_open", "ktg_ipc_close",
+    "ktg_get_info", "ktg_set_option", "ktg_export_externals", "ktg_graph_prepare", "ktg_wait_input", "ktg_partition_keys_device", "ktg_mg_plan", "ktg_mg_prepare",
+    "ktg_mg_scatter_reads_device", "ktg_mg_direct_plan", "ktg_mg_direct_prepare", "ktg_mg_direct_scatter_reads_device",
+    "ktg_mg_direct_insert", "ktg_mg_insert_buckets", "ktg_mg_sketch", "ktg_mg_merge_sketch", "ktg_mg_spill", "ktg_mg_insert_spill", "ktg_ipc_get_handle", "ktg_ipc_open", "ktg_ipc_close",
     "ktg_mg_skm_supported", "ktg_mg_skm_plan", "ktg_mg_skm_prepare", "ktg_mg_skm_scatter_reads_device",
     "ktg_mg_skm_insert_buckets", "ktg_mg_skm_spill", "ktg_mg_skm_partition_records", "ktg_mg_skm_insert_records",
     "ktg_mg_skm_owner_of", "ktg_skm_items_host", "ktg_skm_owner_of_kmer",
@@ -104,6 +105,7 @@ def lib():
     L.ktg_add_weighted_kmers.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint32, u64p, u64p]
     L.ktg_create_from_bfc_files.argtypes = [vp, C.POINTER(C.c_char_p), C.c_uint32, C.c_uint32, u64p]
     L.ktg_finalize.argtypes = [vp]
+    L.ktg_wait_input.argtypes = [vp]
     L.ktg_reset.argtypes = [vp]
     L.ktg_counts.argtypes = [vp, u64p, u64p]
     L.ktg_collection_stats.argtypes = [vp, C.POINTER(KtgStats)]
@@ -142,6 +144,11 @@ def lib():
     L.ktg_mg_scatter_reads_device.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, C.POINTER(vp), C.c_uint32, C.c_int,
                                               vp, C.POINTER(vp)]
     L.ktg_mg_insert_buckets.argtypes = [vp, vp, C.c_uint64, C.c_uint32]
+    L.ktg_mg_direct_plan.argtypes = [vp, C.c_uint64, intp, u32p, u32p]
+    L.ktg_mg_direct_prepare.argtypes = [vp, C.c_uint64, C.POINTER(vp), u64p, u64p]
+    L.ktg_mg_direct_scatter_reads_device.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, C.POINTER(vp), C.c_uint32, C.c_int,
+                                                     vp, C.POINTER(vp)]
+    L.ktg_mg_direct_insert.argtypes = [vp, vp, C.c_uint64, C.c_uint32]
     L.ktg_mg_sketch.argtypes = [vp, C.POINTER(vp), u32p]
     L.ktg_mg_merge_sketch.argtypes = [vp, vp]
     L.ktg_mg_spill.argtypes = [vp, C.POINTER(vp), u64p]

@@ -202,6 +202,7 @@ struct Tuning {
     int host_parse = 0;      // ktg_create_from_files: FASTQ / FASTA records cut by the host reader
     int fastq_chunk_kb = 16 << 10; // device parser: raw bytes per chunk
     int mg_pad = 1;          // fused exchange: runs padded to 128-byte lines
+    int mg_direct = 0;       // multi-device handle: the direct exchange (sender bins by owner and sub-table) where the shards agree on their geometry
     int trace = 0;           // host timeline on stderr
 };
 
@@ -281,6 +282,13 @@ struct BuilderBase {
                                  uint64_t total_bases, void *const *peer_rx, uint32_t slot, int first_of_batch,
                                  cudaStream_t send_stream, void **d_cursors) = 0;
     virtual int mg_insert_buckets(const void *d_bucket_ends, uint64_t n_keys, uint32_t slot) = 0;
+    // the direct exchange: the sender partitions by (owner, sub-table), the owner goes straight to the page level
+    virtual int mgd_plan(uint64_t max_windows, int *needs_realloc, uint32_t *n_sub, uint32_t *sub_log2) = 0;
+    virtual int mgd_prepare(uint64_t max_windows, void **rx_base, uint64_t *rx_bytes, uint64_t *bucket_cap) = 0;
+    virtual int mgd_scatter_reads(const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t n_reads, uint64_t total_bases,
+                                  void *const *peer_rx, uint32_t slot, int first_of_batch, cudaStream_t send_stream,
+                                  void **d_cursors, const BatchHint *hint = nullptr) = 0;
+    virtual int mgd_insert(const void *d_bucket_ends, uint64_t n_keys, uint32_t slot) = 0;
     virtual int mg_sketch(void **d_regs, uint32_t *n_regs) = 0;
     virtual int mg_merge_sketch(const void *d_regs) = 0;
     virtual int mg_spill(void **d_keys, uint64_t *n) = 0;
@@ -366,14 +374,16 @@ template <class K> struct Builder : BuilderBase {
     // than pages per sub-table (level-2 bins).  A table of P pages then costs two scatter passes
     // with about sqrt(P) bins each instead of one pass with P / 128 bins, whose runs would shrink
     // to a few keys (C3: 632 sub-tables made the level-1 scatter 3x slower per key).
-    static void geometry(uint64_t need_slots, uint32_t sub_log2_bytes, bool balance, uint32_t *n_sub,
+    // world > 1: this is one shard of `world`; the sender of the direct exchange bins by (owner, sub-table),
+    // so it is world x n_sub that must stay within what one scatter pass handles well
+    static void geometry(uint64_t need_slots, uint32_t sub_log2_bytes, bool balance, uint32_t world, uint32_t *n_sub,
                          uint32_t *sub_log2) {
         uint32_t slot_log2 = sizeof(K) == 8 ? 4 : 5; // sub-table sizes are quoted for 16 / 32-byte slots (12 / 20 now)
         uint32_t sl = sub_log2_bytes - slot_log2; // slots per sub-table (log2)
         if (balance) {
             while (sl < 28 && sl > PageGeom<K>::LOG2) {
                 const uint64_t ns = (need_slots + (1ull << sl) - 1) >> sl;
-                if (ns <= 128 || ns <= (1ull << (sl - PageGeom<K>::LOG2))) break;
+                if (ns * world <= 128 || ns * world <= (1ull << (sl - PageGeom<K>::LOG2))) break;
                 ++sl;
             }
         }
@@ -398,7 +408,7 @@ template <class K> struct Builder : BuilderBase {
     int alloc_table(uint64_t need_slots, Table<K> *out, bool do_init) {
         Table<K> t = tab;
         uint32_t slb = cfg.sub_table_log2_bytes ? cfg.sub_table_log2_bytes : 24;
-        geometry(need_slots, slb, cfg.sub_table_log2_bytes == 0, &t.n_sub, &t.sub_log2);
+        geometry(need_slots, slb, cfg.sub_table_log2_bytes == 0, std::max<uint32_t>(1, tab.world), &t.n_sub, &t.sub_log2);
         t.sub_mask = (uint32_t)((1ull << t.sub_log2) - 1);
         uint32_t pl = PageGeom<K>::LOG2;
         if (tune.page_log2) pl = std::min<uint32_t>(pl, (uint32_t)std::max(8, tune.page_log2));
@@ -1840,7 +1850,7 @@ template <class K> struct Builder : BuilderBase {
             b_rx.release();
             KTG_TRY(b_rx.ensure((size_t)cap * W * MG_SLOTS * sizeof(K) + 64));
             mg_cap = cap;
-            skm_cap = 0; // the super-k-mer exchange has to size the buffer again
+            skm_cap = mgd_cap = 0; // the other exchanges have to size the buffer again
             mg_spill_cap = std::max<uint64_t>(1u << 20, max_windows / 4); // per batch of several chunks
             KTG_TRY(b_mg_spill.ensure(mg_spill_cap * sizeof(K) + 64));
             KTG_TRY(b_mg_cur.ensure(((size_t)W * MG_SLOTS + 2) * 8));
@@ -1875,6 +1885,7 @@ template <class K> struct Builder : BuilderBase {
         const uint32_t W = tab.world;
         mg_mode = true;
         mg_local_sketch = false;
+        mgd_active = false;
         unsigned long long *cur = mg_cursors(slot);
         *d_cursors = cur;
         init_cursors_kernel<<<1, 32, 0, stream>>>(cur, W, mg_cap);
@@ -1930,6 +1941,142 @@ template <class K> struct Builder : BuilderBase {
         return KTG_OK;
     }
 
+    // ---- multi-GPU, direct: the sender does the owner's level-1 partition too -------------------------
+    // The fused exchange above leaves the owner one more pass than a single GPU has (scatter_received:
+    // 4.6 of 20.1 ms per step on C3 at N = 2).  Here the extraction kernel bins every key by (owner,
+    // sub-table of the owner) -- world x n_sub bins, as many as the one-GPU build of the same table has,
+    // because a shard is 1/world of it -- and writes the runs into the owner's receive bucket for
+    // (this sender, that sub-table).  The owner's receive buffer then IS its level-1 stage: it goes
+    // straight to the level-2 scatter (bucket q holds keys of sub-table q % n_sub) and the page sweep.
+    // Needs the same geometry (n_sub, sub_log2) on every shard: they are sized from the same all-reduced
+    // sketch, and the caller checks it per batch (mgd_plan) and falls back to the exchange above otherwise.
+    uint64_t mgd_cap = 0;
+    uint32_t mgd_n_sub = 0, mgd_sub_log2 = 0;
+    bool mgd_active = false; // the last exchange was the direct one (which spill cursor mg_spill reads)
+    size_t mgd_bins() const { return (size_t)tab.world * mgd_n_sub; }
+    size_t mgd_slot_keys() const { return (size_t)mgd_cap * mgd_bins(); }
+    int mgd_check() {
+        if (tab.world > (uint32_t)MAX_P2P_WORLD) return fail(KTG_ERR_INVALID, "fused exchange needs world <= %d", MAX_P2P_WORLD);
+        if ((uint64_t)tab.world * tab.n_sub > MAX_BINS) return fail(KTG_ERR_INVALID, "too many sub-tables for the direct exchange");
+        return KTG_OK;
+    }
+    int mgd_plan(uint64_t max_windows, int *needs_realloc, uint32_t *n_sub, uint32_t *sub_log2) override {
+        KTG_TRY(mgd_check());
+        const uint64_t cap = bucket_cap_for(std::max<uint64_t>(max_windows, 1), tab.world * tab.n_sub);
+        *needs_realloc = cap > mgd_cap || tab.n_sub != mgd_n_sub || !b_rx.p;
+        *n_sub = tab.n_sub;
+        *sub_log2 = tab.sub_log2;
+        return KTG_OK;
+    }
+    int mgd_prepare(uint64_t max_windows, void **rx_base, uint64_t *rx_bytes, uint64_t *bucket_cap) override {
+        KTG_TRY(mgd_check());
+        const uint32_t W = tab.world;
+        const uint64_t cap = bucket_cap_for(std::max<uint64_t>(max_windows, 1), W * tab.n_sub);
+        if (cap > mgd_cap || tab.n_sub != mgd_n_sub || !b_rx.p) {
+            KTG_TRY(sync());
+            b_rx.release();
+            mgd_cap = cap;
+            mgd_n_sub = tab.n_sub;
+            KTG_TRY(b_rx.ensure(mgd_slot_keys() * MG_SLOTS * sizeof(K) + 64));
+            mg_cap = skm_cap = 0; // the other exchanges have to size the buffer again
+            mg_spill_cap = std::max<uint64_t>(1u << 20, max_windows / 4);
+            KTG_TRY(b_mg_spill.ensure(mg_spill_cap * sizeof(K) + 64));
+            KTG_TRY(b_mg_cur.ensure((mgd_bins() * MG_SLOTS + 2) * 8));
+        }
+        mgd_sub_log2 = tab.sub_log2;
+        *rx_base = b_rx.p;
+        *rx_bytes = mgd_slot_keys() * sizeof(K); // of ONE slot
+        *bucket_cap = mgd_cap;
+        return KTG_OK;
+    }
+    unsigned long long *mgd_cursors(uint32_t slot) { return (unsigned long long *)b_mg_cur.p + (size_t)slot * mgd_bins(); }
+    unsigned long long *mgd_spill_cursor() { return (unsigned long long *)b_mg_cur.p + (size_t)MG_SLOTS * mgd_bins(); }
+
+    int mgd_scatter_reads(const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t n_reads, uint64_t total_bases,
+                          void *const *peer_rx, uint32_t slot, int first_of_batch, cudaStream_t send_stream,
+                          void **d_cursors, const BatchHint *hint = nullptr) override {
+        if (deferred_error != KTG_OK) return fail(deferred_error, "build is void after an earlier error");
+        if (!b_rx.p || !mgd_cap) return fail(KTG_ERR_INVALID, "ktg_mg_direct_prepare first");
+        if (slot >= MG_SLOTS) return fail(KTG_ERR_INVALID, "slot out of range");
+        if (tab.n_sub != mgd_n_sub) return fail(KTG_ERR_INVALID, "the table geometry changed since ktg_mg_direct_prepare");
+        struct StreamSwap {
+            cudaStream_t &ref, saved;
+            StreamSwap(cudaStream_t &r, cudaStream_t s_) : ref(r), saved(r) { if (s_) ref = s_; }
+            ~StreamSwap() { ref = saved; }
+        } swap(stream, send_stream);
+        const uint32_t W = tab.world, n_bins = (uint32_t)mgd_bins();
+        mg_mode = true;
+        mg_local_sketch = false;
+        mgd_active = true;
+        unsigned long long *cur = mgd_cursors(slot);
+        *d_cursors = cur;
+        // a batch may arrive in several calls (chunks of a host batch): the later ones append to the same buckets
+        if (first_of_batch) {
+            init_cursors_kernel<<<(n_bins + 255) / 256, 256, 0, stream>>>(cur, n_bins, mgd_cap);
+            KTG_CUDA(cudaMemsetAsync(mgd_spill_cursor(), 0, 8, stream));
+        }
+        if (n_reads == 0) return KTG_OK;
+        Batch bt;
+        KTG_TRY(pack(d_bases, d_offsets, n_reads, total_bases, &bt, hint, hint_shift0));
+        if (bt.windows == 0) return KTG_OK;
+        PeerOut po{};
+        po.world = W;
+        po.bins_per_owner = mgd_n_sub;
+        po.pad = 1; // runs are a dozen keys: padding them to 128 bytes would be a fifth of the traffic
+        // the sender's virtual position is v = (owner * n_sub + sub) * cap + fill; in the owner's slot the
+        // bucket of (this sender, sub) starts at (rank * n_sub + sub) * cap
+        for (uint32_t o = 0; o < W; ++o)
+            po.rxb[o] = (K *)peer_rx[o] + (int64_t)slot * (int64_t)mgd_slot_keys() +
+                        ((int64_t)tab.rank - (int64_t)o) * (int64_t)mgd_n_sub * (int64_t)mgd_cap;
+        ScatterOut so;
+        so.cursors = cur;
+        so.bucket_cap = mgd_cap;
+        so.out = nullptr;
+        so.spill_out = b_mg_spill.p;
+        so.spill_cursor = mgd_spill_cursor();
+        so.spill_cap = mg_spill_cap;
+        KTG_TRY((scatter_reads_pass<BIN_OWNER_PART, true>(bt, n_bins, so, &po)));
+        KTG_CUDA(cudaGetLastError());
+        return KTG_OK;
+    }
+
+    // d_bucket_ends[q], q = source * n_sub + sub: absolute end (in keys, inside the slot) of that bucket,
+    // q * cap + fill; n_keys: the exact total.  The caller has all-reduced (max) the sketch.
+    int mgd_insert(const void *d_bucket_ends, uint64_t n_keys, uint32_t slot) override {
+        if (deferred_error != KTG_OK) return fail(deferred_error, "build is void after an earlier error");
+        if (slot >= MG_SLOTS) return fail(KTG_ERR_INVALID, "slot out of range");
+        if (n_keys == 0) return KTG_OK;
+        const unsigned long long *ends = (const unsigned long long *)d_bucket_ends;
+        const K *rx = (const K *)b_rx.p + (size_t)slot * mgd_slot_keys();
+        const uint32_t n_bins = (uint32_t)mgd_bins();
+        KTG_TRY(flush_staged()); // (keys staged by another route go first; usually nothing)
+        // size the table for everything offered so far, as flush_staged does
+        double est = 0;
+        KTG_TRY(hll_estimate(&est));
+        const uint64_t distinct = hll_base + (uint64_t)(est * 1.10 / tab.world) + 64;
+        occupied_ub = distinct;
+        if ((double)distinct > LOAD_MAX * (double)tab.capacity()) {
+            const uint64_t need = std::max<uint64_t>((uint64_t)((double)distinct / LOAD_TARGET) + 1, 2 * tab.capacity());
+            KTG_TRY(grow_to(need));
+        }
+        touch();
+        const bool same = tab.n_sub == mgd_n_sub && tab.sub_log2 == mgd_sub_log2;
+        if (same && use_pages(n_keys)) {
+            // page-bucket overflow goes to the stage's spill list
+            stage_spill_cap = n_keys + 64;
+            KTG_TRY(b_spill.ensure(stage_spill_cap * sizeof(K) + 64));
+            KTG_CUDA(cudaMemsetAsync(stage_spill_cursor(), 0, 8, stream));
+            KTG_TRY(pages_open(n_keys));
+            KTG_TRY(pages_scatter(n_bins, mgd_cap, n_keys, ends, rx, mgd_n_sub));
+            KTG_TRY(pages_update(n_keys));
+            KTG_TRY(launch_insert((const K *)b_spill.p, stage_spill_cap, nullptr, 0, 0, stage_spill_cursor()));
+        }
+        else KTG_TRY(launch_insert(rx, n_keys, ends, mgd_cap, n_bins)); // plain arrays of keys, any geometry
+        KTG_TRY(sync()); // the receive slot may be written again
+        KTG_CUDA(cudaGetLastError());
+        return KTG_OK;
+    }
+
     int mg_sketch(void **d_regs, uint32_t *n_regs) override {
         *d_regs = b_hll.p;
         *n_regs = HLL_M;
@@ -1948,7 +2095,7 @@ template <class K> struct Builder : BuilderBase {
         *d_keys = b_mg_spill.p;
         *n = 0;
         if (!b_mg_cur.p) return KTG_OK;
-        KTG_CUDA(cudaMemcpyAsync(&v, mg_spill_cursor(), 8, cudaMemcpyDeviceToHost, stream));
+        KTG_CUDA(cudaMemcpyAsync(&v, mgd_active ? mgd_spill_cursor() : mg_spill_cursor(), 8, cudaMemcpyDeviceToHost, stream));
         KTG_TRY(sync());
         if (v > mg_spill_cap) {
             deferred_error = KTG_ERR_TABLE_FULL;
@@ -2004,7 +2151,7 @@ template <class K> struct Builder : BuilderBase {
             b_rx.release();
             KTG_TRY(b_rx.ensure((size_t)cap * W * MG_SLOTS * sizeof(u128) + 64));
             skm_cap = cap;
-            mg_cap = 0; // the key exchange has to size the buffer again
+            mg_cap = mgd_cap = 0; // the key exchanges have to size the buffer again
             skm_spill_cap = std::max<uint64_t>(1u << 20, max_windows / 16);
             KTG_TRY(b_mg_spill.ensure(skm_spill_cap * sizeof(u128) + 64));
             KTG_TRY(b_mg_cur.ensure(((size_t)W * MG_SLOTS + 2) * 8));

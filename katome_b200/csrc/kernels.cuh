@@ -737,7 +737,9 @@ constexpr int SCATTER_THREADS = 256, SCATTER_PER = 8, SCATTER_TILE = SCATTER_THR
 // Level 1 from packed reads: extraction (K2) + partition.  BINS: by sub-table, or by owner
 // rank -- into a local array for an NCCL exchange (po.world == 0) or straight into the
 // owners' receive buckets over NVLink (po).
-constexpr int BIN_PART = 0, BIN_OWNER = 1;
+// BIN_OWNER_PART: (owner rank, sub-table of that owner), owner-major -- the sender of the direct exchange does
+// the owner's level-1 partition as well, so that what arrives is already grouped by sub-table
+constexpr int BIN_PART = 0, BIN_OWNER = 1, BIN_OWNER_PART = 2;
 // PER: keys per lane and tile.  A work item is GRAN = 8 window starts; with PER = 4 it is partitioned in
 // two passes of 4 keys (the rolling state survives the tile scatter in between).  That keeps the u128
 // kernel's keys in registers (64 registers, no spill, against 80 and 28 bytes of spill) but halves the
@@ -745,7 +747,7 @@ constexpr int BIN_PART = 0, BIN_OWNER = 1;
 // 30.2 ms against 16.3, on C2 3.31 against 1.75 (profiles/r02_sweeps.md), so PER stays 8.
 template <class K> struct ScatterGeom { static constexpr int PER = 8; };
 template <class K, bool RC, int BINS, bool HLL, int PER = ScatterGeom<K>::PER>
-__global__ void __launch_bounds__(SCATTER_THREADS, (BINS == BIN_OWNER || sizeof(K) == 8 || PER == 4) ? 4 : 3)
+__global__ void __launch_bounds__(SCATTER_THREADS, (BINS != BIN_PART || sizeof(K) == 8 || PER == 4) ? 4 : 3)
 scatter_reads_kernel(ReadView v, uint32_t k, Table<K> t, uint32_t n_bins, ScatterOut o,
                      uint32_t *__restrict__ g_regs, PeerOut po) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -772,14 +774,14 @@ scatter_reads_kernel(ReadView v, uint32_t k, Table<K> t, uint32_t n_bins, Scatte
                 key[j] = iw.template key<RC>();
                 const uint32_t h = KeyTraits<K>::place_hash(key[j]);
                 Place p = place_of(h, t.world, t.n_sub);
-                bin[j] = BINS == BIN_OWNER ? p.owner : p.part;
+                bin[j] = BINS == BIN_OWNER ? p.owner : BINS == BIN_PART ? p.part : p.owner * t.n_sub + p.part;
                 if (HLL && hll_sampled(h)) sampled |= 1u << j;
                 iw.r.step();
             }
             const uint32_t vmask = (iw.mask >> (pass * PER)) & ((1u << PER) - 1u);
             if (HLL) hll_update_tile<K, PER>(sm.regs, key, sampled & vmask);
             tile_scatter<K, SCATTER_THREADS, PER>(key, bin, vmask, sm, n_bins, o.cursors, 0, o, parity,
-                                                  (BINS == BIN_OWNER && po.world) ? &po : nullptr);
+                                                  (BINS != BIN_PART && po.world) ? &po : nullptr);
         }
     }
     if (HLL) {
@@ -1267,6 +1269,10 @@ insert_weighted_kmers_kernel(const uint8_t *__restrict__ kmers, const uint32_t *
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const uint32_t w = weights[i];
         if (w < threshold) continue;
+        if (w == 0) { // weight 0 means "not an edge" in this table (a removed edge keeps its slot that way): a
+            ++ok;     // count-0 line is accepted and counted like the reference does, but adds no edge
+            continue;
+        }
         const uint8_t *p = kmers + i * k;
         K key = 0;
         bool valid = true;

@@ -308,12 +308,17 @@ struct FastqDeviceParser {
     }
     int init() {
         for (int i = 0; i < 2; ++i) {
-            KTG_CUDA(cudaHostAlloc((void **)&pinned[i], chunk + 64, cudaHostAllocDefault));
             KTG_CUDA(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
             KTG_CUDA(cudaEventCreateWithFlags(&consumed[i], cudaEventDisableTiming));
             KTG_TRY(raw[i].ensure(chunk + 64));
         }
         KTG_TRY(info.ensure(sizeof(FastqChunkInfo)));
+        return KTG_OK;
+    }
+    // the two page-locked buffers of the serial paths (the block reader brings its own)
+    int ensure_pinned() {
+        for (int i = 0; i < 2; ++i)
+            if (!pinned[i]) KTG_CUDA(cudaHostAlloc((void **)&pinned[i], chunk + 64, cudaHostAllocDefault));
         return KTG_OK;
     }
 
@@ -359,6 +364,7 @@ struct FastqDeviceParser {
 
     // One FASTA file.  Mirrors next_fasta of host_reader.h record for record.
     int parse_fasta(ReadFile &f) {
+        KTG_TRY(ensure_pinned());
         cudaStream_t st = impl->stream;
         size_t carry = 0; // bytes of an unfinished record at the front of pinned[cur]
         int cur = 0;
@@ -448,9 +454,78 @@ struct FastqDeviceParser {
         return KTG_OK;
     }
 
-    // One file.  Mirrors next_fastq of host_reader.h record for record.
-    int parse(ReadFile &f) {
+    // One chunk of FASTQ text at h[0, n) (page-locked), starting at a record boundary: to the device,
+    // records cut, complete records ingested.  *rest_at = where the unfinished record at its end starts.
+    int fastq_chunk(const uint8_t *h, size_t n, int cur, bool eof, size_t *rest_at) {
         cudaStream_t st = impl->stream;
+        // raw bytes to the device (the device buffer of two chunks ago has been consumed)
+        if (used[cur]) KTG_CUDA(cudaStreamWaitEvent(impl->copy_stream, consumed[cur], 0));
+        KTG_TRY(raw[cur].ensure(n + 64));
+        KTG_CUDA(cudaMemcpyAsync(raw[cur].p, h, n, cudaMemcpyHostToDevice, impl->copy_stream));
+        KTG_CUDA(cudaEventRecord(copied[cur], impl->copy_stream));
+        KTG_CUDA(cudaStreamWaitEvent(st, copied[cur], 0));
+        used[cur] = true;
+        const uint8_t *d_raw = (const uint8_t *)raw[cur].p;
+        uint32_t n_lines = 0;
+        KTG_TRY(index_lines(d_raw, n, &n_lines));
+        const uint64_t n_rec = n_lines / 4;
+        FastqChunkInfo ci{};
+        ci.bad_header = ~0ull;
+        if (n_rec) {
+            KTG_TRY(sstart.ensure(n_rec * 4));
+            KTG_TRY(slen.ensure((n_rec + 1) * 8));
+            KTG_TRY(offs[cur].ensure((n_rec + 1) * 8));
+            FastqChunkInfo init{};
+            init.bad_header = ~0ull;
+            init.min_len = ~0ull;
+            KTG_CUDA(cudaMemcpyAsync(info.p, &init, sizeof init, cudaMemcpyHostToDevice, st));
+            KTG_CUDA(cudaMemsetAsync((uint64_t *)slen.p + n_rec, 0, 8, st));
+            const int grid = (int)std::min<uint64_t>((n_rec + 255) / 256, 148 * 8);
+            fq_records_kernel<<<grid, 256, 0, st>>>(d_raw, (const uint32_t *)nl.p, n_rec, impl->k, (uint32_t *)sstart.p,
+                                                   (uint64_t *)slen.p, (FastqChunkInfo *)info.p);
+            size_t tb2 = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, tb2, (uint64_t *)slen.p, (uint64_t *)offs[cur].p, (int)n_rec + 1, st);
+            KTG_TRY(tmp.ensure(tb2));
+            KTG_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb2, (uint64_t *)slen.p, (uint64_t *)offs[cur].p, (int)n_rec + 1, st));
+            uint64_t total_bases = 0;
+            KTG_CUDA(cudaMemcpyAsync(&ci, info.p, sizeof ci, cudaMemcpyDeviceToHost, st));
+            KTG_CUDA(cudaMemcpyAsync(&total_bases, (uint64_t *)offs[cur].p + n_rec, 8, cudaMemcpyDeviceToHost, st));
+            KTG_CUDA(cudaStreamSynchronize(st));
+            if (ci.bad_header != ~0ull) return fail(KTG_ERR_BAD_RECORD, "Expected @ at record start.");
+            KTG_TRY(dense[cur].ensure(total_bases + 64));
+            fq_gather_kernel<<<148 * 8, 256, 0, st>>>(d_raw, (const uint32_t *)sstart.p, (const uint64_t *)offs[cur].p,
+                                                     n_rec, (uint8_t *)dense[cur].p);
+            BatchHint hint;
+            hint.ulen = (ci.min_len == ci.max_len && ci.max_len <= 0xFFFFFFFFull) ? (uint32_t)ci.max_len : 0;
+            hint.windows_ub = ci.windows_ub;
+            impl->hint_shift0 = (uint32_t)((uintptr_t)dense[cur].p & 31);
+            impl->input_consumed = consumed[cur]; // dense, offsets and raw of this slot are free after the pack
+            int rc_ = impl->ingest_device((const uint8_t *)dense[cur].p, (const uint64_t *)offs[cur].p, n_rec, total_bases, &hint);
+            impl->input_consumed = nullptr;
+            KTG_TRY(rc_);
+        }
+        else KTG_CUDA(cudaEventRecord(consumed[cur], st));
+        // what follows the last complete record
+        const size_t done = n_rec ? (size_t)ci.consumed : 0;
+        *rest_at = done;
+        if (eof && n - done) { // lines of an unfinished record: the reader fails on its header or on its missing lines
+            if (h[done] != '@') return fail(KTG_ERR_BAD_RECORD, "Expected @ at record start.");
+            return fail(KTG_ERR_BAD_RECORD, "Incomplete record. Each FastQ record has to consist of 4 lines.");
+        }
+        return KTG_OK;
+    }
+
+    // One FASTQ file.  Mirrors next_fastq of host_reader.h record for record.  A regular file is read in
+    // blocks by reader threads that run ahead (BlockReader); anything else serially.
+    int parse(ReadFile &f) {
+        const long long fsize = f.regular_size();
+        if (fsize >= 0 && chunk >= (64u << 10)) {
+            if (fsize == 0) return KTG_OK;
+            BlockReader rd(f.fd(), (size_t)fsize, chunk, 4, 3);
+            if (rd.init()) return parse_blocks(rd);
+            // (no page-locked memory or no thread to be had: the serial path below)
+        }
+        KTG_TRY(ensure_pinned());
         size_t carry = 0; // bytes of an unfinished record at the front of pinned[cur]
         int cur = 0;
         bool eof = false;
@@ -462,80 +537,39 @@ struct FastqDeviceParser {
             eof = got < chunk - carry;
             if (eof && n && h[n - 1] != '\n') h[n++] = '\n'; // a last line without newline is a line
             if (n == 0) break;
-            // raw bytes to the device (the device buffer of two chunks ago has been consumed)
-            if (used[cur]) KTG_CUDA(cudaStreamWaitEvent(impl->copy_stream, consumed[cur], 0));
-            KTG_CUDA(cudaMemcpyAsync(raw[cur].p, h, n, cudaMemcpyHostToDevice, impl->copy_stream));
-            KTG_CUDA(cudaEventRecord(copied[cur], impl->copy_stream));
-            KTG_CUDA(cudaStreamWaitEvent(st, copied[cur], 0));
-            used[cur] = true;
-            const uint8_t *d_raw = (const uint8_t *)raw[cur].p;
-            // newline index
-            const uint32_t n_blocks = (uint32_t)((n + FQ_BLOCK_BYTES - 1) / FQ_BLOCK_BYTES);
-            KTG_TRY(bcount.ensure(((size_t)n_blocks + 1) * 4));
-            KTG_TRY(bstart.ensure(((size_t)n_blocks + 1) * 4));
-            KTG_CUDA(cudaMemsetAsync((uint32_t *)bcount.p + n_blocks, 0, 4, st));
-            fq_count_kernel<<<n_blocks, 256, 0, st>>>(d_raw, n, (uint32_t *)bcount.p);
-            size_t tb = 0;
-            cub::DeviceScan::ExclusiveSum(nullptr, tb, (uint32_t *)bcount.p, (uint32_t *)bstart.p, (int)n_blocks + 1, st);
-            KTG_TRY(tmp.ensure(tb));
-            KTG_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, (uint32_t *)bcount.p, (uint32_t *)bstart.p, (int)n_blocks + 1, st));
-            uint32_t n_lines = 0;
-            KTG_CUDA(cudaMemcpyAsync(&n_lines, (uint32_t *)bstart.p + n_blocks, 4, cudaMemcpyDeviceToHost, st));
-            KTG_CUDA(cudaStreamSynchronize(st));
-            const uint64_t n_rec = n_lines / 4;
-            FastqChunkInfo ci{};
-            ci.bad_header = ~0ull;
-            if (n_rec) {
-                KTG_TRY(nl.ensure((size_t)n_lines * 4));
-                fq_positions_kernel<<<n_blocks, 256, 0, st>>>(d_raw, n, (const uint32_t *)bstart.p, (uint32_t *)nl.p);
-                KTG_TRY(sstart.ensure(n_rec * 4));
-                KTG_TRY(slen.ensure((n_rec + 1) * 8));
-                KTG_TRY(offs[cur].ensure((n_rec + 1) * 8));
-                FastqChunkInfo init{};
-                init.bad_header = ~0ull;
-                init.min_len = ~0ull;
-                KTG_CUDA(cudaMemcpyAsync(info.p, &init, sizeof init, cudaMemcpyHostToDevice, st));
-                KTG_CUDA(cudaMemsetAsync((uint64_t *)slen.p + n_rec, 0, 8, st));
-                const int grid = (int)std::min<uint64_t>((n_rec + 255) / 256, 148 * 8);
-                fq_records_kernel<<<grid, 256, 0, st>>>(d_raw, (const uint32_t *)nl.p, n_rec, impl->k, (uint32_t *)sstart.p,
-                                                       (uint64_t *)slen.p, (FastqChunkInfo *)info.p);
-                size_t tb2 = 0;
-                cub::DeviceScan::ExclusiveSum(nullptr, tb2, (uint64_t *)slen.p, (uint64_t *)offs[cur].p, (int)n_rec + 1, st);
-                KTG_TRY(tmp.ensure(tb2));
-                KTG_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb2, (uint64_t *)slen.p, (uint64_t *)offs[cur].p, (int)n_rec + 1, st));
-                uint64_t total_bases = 0;
-                KTG_CUDA(cudaMemcpyAsync(&ci, info.p, sizeof ci, cudaMemcpyDeviceToHost, st));
-                KTG_CUDA(cudaMemcpyAsync(&total_bases, (uint64_t *)offs[cur].p + n_rec, 8, cudaMemcpyDeviceToHost, st));
-                KTG_CUDA(cudaStreamSynchronize(st));
-                if (ci.bad_header != ~0ull) return fail(KTG_ERR_BAD_RECORD, "Expected @ at record start.");
-                KTG_TRY(dense[cur].ensure(total_bases + 64));
-                fq_gather_kernel<<<148 * 8, 256, 0, st>>>(d_raw, (const uint32_t *)sstart.p, (const uint64_t *)offs[cur].p,
-                                                         n_rec, (uint8_t *)dense[cur].p);
-                BatchHint hint;
-                hint.ulen = (ci.min_len == ci.max_len && ci.max_len <= 0xFFFFFFFFull) ? (uint32_t)ci.max_len : 0;
-                hint.windows_ub = ci.windows_ub;
-                impl->hint_shift0 = (uint32_t)((uintptr_t)dense[cur].p & 31);
-                impl->input_consumed = consumed[cur]; // dense, offsets and raw of this slot are free after the pack
-                int rc_ = impl->ingest_device((const uint8_t *)dense[cur].p, (const uint64_t *)offs[cur].p, n_rec, total_bases, &hint);
-                impl->input_consumed = nullptr;
-                KTG_TRY(rc_);
-            }
-            // what follows the last complete record
-            const size_t done = n_rec ? (size_t)ci.consumed : 0;
+            size_t done = 0;
+            KTG_TRY(fastq_chunk(h, n, cur, eof, &done));
+            if (eof) break;
             const size_t rest = n - done;
-            if (eof) {
-                if (rest) { // lines of an unfinished record: the reader fails on its header or on its missing lines
-                    if (h[done] != '@') return fail(KTG_ERR_BAD_RECORD, "Expected @ at record start.");
-                    return fail(KTG_ERR_BAD_RECORD, "Incomplete record. Each FastQ record has to consist of 4 lines.");
-                }
-                break;
-            }
             if (rest >= chunk) return fail(KTG_ERR_BAD_RECORD, "a FASTQ record is larger than %zu bytes", chunk);
             const int nxt = cur ^ 1;
             if (used[nxt]) KTG_CUDA(cudaEventSynchronize(copied[nxt]));
             memcpy(pinned[nxt], h + done, rest);
             carry = rest;
             cur = nxt;
+        }
+        return KTG_OK;
+    }
+
+    int parse_blocks(BlockReader &rd) {
+        std::vector<uint8_t> carry;
+        const size_t nb = rd.n_blocks();
+        for (size_t j = 0; j < nb; ++j) {
+            uint8_t *p = nullptr;
+            size_t got = 0;
+            if (!rd.acquire(j, &p, &got)) return fail(KTG_ERR_IO, "reading the file failed");
+            if (carry.size() > BlockReader::HEAD) return fail(KTG_ERR_BAD_RECORD, "a FASTQ record is larger than %zu bytes", BlockReader::HEAD);
+            uint8_t *h = p - carry.size();
+            if (!carry.empty()) memcpy(h, carry.data(), carry.size());
+            size_t n = carry.size() + got;
+            const bool eof = j + 1 == nb;
+            if (eof && n && h[n - 1] != '\n') h[n++] = '\n'; // a last line without newline is a line
+            size_t done = 0;
+            if (n) KTG_TRY(fastq_chunk(h, n, (int)(j & 1), eof, &done));
+            carry.assign(h + done, h + n);
+            // the copy of this block to the device must have finished before its buffer is read into again
+            KTG_CUDA(cudaEventSynchronize(copied[j & 1]));
+            rd.release(j);
         }
         return KTG_OK;
     }
@@ -696,6 +730,13 @@ int ktg_create_from_bfc_files(ktg_builder *b, const char *const *paths, uint32_t
     KTG_TRY(rc_);
     if (total_bytes) *total_bytes = total;
     return ktg_finalize(b);
+}
+
+int ktg_wait_input(ktg_builder *b) {
+    KTG_ENTER(b);
+    if (b->multi) return KTG_OK; // its ktg_add_reads returns with the copies done
+    KTG_CUDA(cudaStreamSynchronize(b->impl->copy_stream));
+    return KTG_OK;
 }
 
 int ktg_reset(ktg_builder *b) {
@@ -912,6 +953,37 @@ int ktg_mg_insert_buckets(ktg_builder *b, const void *d_bucket_ends, uint64_t n_
     KTG_ENTER(b);
     KTG_SINGLE(b);
     return b->impl->mg_insert_buckets(d_bucket_ends, n_keys, slot);
+}
+
+int ktg_mg_direct_plan(ktg_builder *b, uint64_t max_windows, int *needs_realloc, uint32_t *n_sub, uint32_t *sub_log2) {
+    KTG_ENTER(b);
+    KTG_SINGLE(b);
+    if (!needs_realloc || !n_sub || !sub_log2) return fail(KTG_ERR_INVALID, "null argument");
+    return b->impl->mgd_plan(max_windows, needs_realloc, n_sub, sub_log2);
+}
+
+int ktg_mg_direct_prepare(ktg_builder *b, uint64_t max_windows, void **rx_base, uint64_t *rx_bytes, uint64_t *bucket_cap) {
+    KTG_ENTER(b);
+    KTG_SINGLE(b);
+    if (!rx_base || !rx_bytes || !bucket_cap) return fail(KTG_ERR_INVALID, "null argument");
+    return b->impl->mgd_prepare(max_windows, rx_base, rx_bytes, bucket_cap);
+}
+
+int ktg_mg_direct_scatter_reads_device(ktg_builder *b, const void *d_bases, const void *d_offsets, uint64_t n_reads,
+                                       uint64_t total_bases, void *const *peer_rx, uint32_t slot, int first_of_batch,
+                                       void *send_stream, void **d_cursors) {
+    KTG_ENTER(b);
+    KTG_SINGLE(b);
+    if (!peer_rx || !d_cursors) return fail(KTG_ERR_INVALID, "null argument");
+    return b->impl->mgd_scatter_reads((const uint8_t *)d_bases, (const uint64_t *)d_offsets, n_reads, total_bases, peer_rx,
+                                      slot, first_of_batch, (cudaStream_t)send_stream, d_cursors);
+}
+
+int ktg_mg_direct_insert(ktg_builder *b, const void *d_bucket_ends, uint64_t n_keys, uint32_t slot) {
+    KTG_ENTER(b);
+    KTG_SINGLE(b);
+    if (!d_bucket_ends) return fail(KTG_ERR_INVALID, "null argument");
+    return b->impl->mgd_insert(d_bucket_ends, n_keys, slot);
 }
 
 int ktg_mg_sketch(ktg_builder *b, void **d_regs, uint32_t *n_regs) {
@@ -1206,7 +1278,7 @@ static int set_option_on(BuilderBase *impl, const char *name, int64_t value) {
         {"chunk_mb", &t.chunk_mb}, {"stage_bufs", &t.stage_bufs}, {"flush_pct", &t.flush_pct},
         {"flush_pct2", &t.flush_pct2}, {"taper", &t.taper}, {"eager_pages", &t.eager_pages},
         {"stage_factor_milli", &t.stage_factor_milli}, {"host_parse", &t.host_parse},
-        {"fastq_chunk_kb", &t.fastq_chunk_kb}, {"mg_pad", &t.mg_pad}, {"trace", &t.trace},
+        {"fastq_chunk_kb", &t.fastq_chunk_kb}, {"mg_pad", &t.mg_pad}, {"mg_direct", &t.mg_direct}, {"trace", &t.trace},
     };
     if (!strcmp(name, "stage_max_keys")) {
         t.stage_max_keys = value;

@@ -214,8 +214,8 @@ struct MultiBuilder {
             std::vector<BatchHint> hint; // one read length or ragged, windows if every read is accepted
         };
         std::vector<Plan> plan(n);
-        std::vector<uint64_t> max_win(n, 0);
-        std::vector<uint32_t> rounds_of(n, 0);
+        std::vector<uint64_t> max_win(n, 0), sum_win(n, 0);
+        std::vector<uint32_t> rounds_of(n, 0), geo_sub(n, 0), geo_log2(n, 0);
         // published between barriers
         std::vector<void *> rx(n, nullptr);
         std::vector<uint64_t> cap(n, 0);
@@ -255,21 +255,120 @@ struct MultiBuilder {
                     h.windows_ub = wub;
                     p.hint.push_back(h);
                     max_win[i] = std::max(max_win[i], wub);
+                    sum_win[i] += wub;
                     p.c.push_back(e);
                     r = e;
                 }
                 rounds_of[i] = (uint32_t)p.hint.size();
+                int needs = 0;
+                step(b->mgd_plan(1, &needs, &geo_sub[i], &geo_log2[i]));
             }
-            if (!gate.wait()) return PEER_FAILED;
-            uint64_t gmax = 0;
+            if (!gate.wait(err == KTG_OK)) return err != KTG_OK ? err : PEER_FAILED;
+            uint64_t gmax = 0, gsum = 0;
             uint32_t rounds = 0;
+            bool same_geo = true;
             for (uint32_t j = 0; j < n; ++j) {
                 gmax = std::max(gmax, max_win[j]);
+                gsum = std::max(gsum, sum_win[j]);
                 rounds = std::max(rounds, rounds_of[j]);
+                same_geo = same_geo && geo_sub[j] == geo_sub[0] && geo_log2[j] == geo_log2[0];
             }
             if (gmax == 0) return KTG_OK; // nothing to insert anywhere (everybody sees the same gmax)
+            // The direct exchange (every shard has the same geometry, no super-k-mers): the senders stream
+            // all their chunks into the owners' (sender, sub-table) buckets without any barrier in between,
+            // and the owners go straight to their page level, once, at the end.
+            if (!skm && same_geo && b->tune.mg_direct && (uint64_t)n * geo_sub[0] <= 1024) {
+                const uint32_t n_sub = geo_sub[0];
+                {
+                    void *base = nullptr;
+                    uint64_t bytes = 0, bc = 0;
+                    step(b->mgd_prepare(gsum, &base, &bytes, &bc));
+                    rx[i] = base;
+                    cap[i] = bc;
+                }
+                if (!gate.wait(err == KTG_OK)) return err != KTG_OK ? err : PEER_FAILED;
+                const Plan &p = plan[i];
+                std::vector<unsigned long long> cur_host((size_t)n * n_sub, 0);
+                void *d_cur = nullptr;
+                auto copy_chunk = [&](uint32_t c) -> int {
+                    if (c >= p.hint.size()) return KTG_OK;
+                    const int s = (int)(c & 1);
+                    const uint64_t r = p.c[c], r1 = p.c[c + 1], nb = offsets[r1] - offsets[r], nr = r1 - r;
+                    if (st.used[s]) KTG_CUDA(cudaStreamWaitEvent(b->copy_stream, st.consumed[s], 0));
+                    if (st.bases[s].cap < nb + 64 || st.offs[s].cap < (nr + 1) * 8) {
+                        KTG_TRY(b->sync_stream());
+                        KTG_CUDA(cudaStreamSynchronize(b->copy_stream));
+                        KTG_TRY(st.bases[s].ensure(std::max<uint64_t>(nb, CHUNK) + 64));
+                        KTG_TRY(st.offs[s].ensure((nr + 1) * 8));
+                    }
+                    KTG_CUDA(cudaMemcpyAsync(st.bases[s].p, bases + offsets[r], nb, cudaMemcpyHostToDevice, b->copy_stream));
+                    if (p.hint[c].ulen) {
+                        const int g = (int)std::min<uint64_t>((nr + 1 + 255) / 256, 4096);
+                        fill_offsets_kernel<<<g, 256, 0, b->copy_stream>>>((uint64_t *)st.offs[s].p, nr + 1, offsets[r], p.hint[c].ulen);
+                        KTG_CUDA(cudaGetLastError());
+                    }
+                    else KTG_CUDA(cudaMemcpyAsync(st.offs[s].p, offsets + r, (nr + 1) * 8, cudaMemcpyHostToDevice, b->copy_stream));
+                    KTG_CUDA(cudaEventRecord(st.ready[s], b->copy_stream));
+                    st.used[s] = true;
+                    return KTG_OK;
+                };
+                step(copy_chunk(0));
+                if (p.hint.empty() && err == KTG_OK) // nothing of mine: my cursors still have to say so
+                    step(b->mgd_scatter_reads(nullptr, nullptr, 0, 0, rx.data(), 0, 1, nullptr, &d_cur));
+                for (uint32_t c = 0; c < p.hint.size() && err == KTG_OK; ++c) {
+                    step(copy_chunk(c + 1)); // the next chunk's copy runs under this chunk's kernels
+                    const int s = (int)(c & 1);
+                    const uint64_t r = p.c[c], r1 = p.c[c + 1];
+                    step(cudaStreamWaitEvent(b->stream, st.ready[s], 0) == cudaSuccess ? KTG_OK : fail(KTG_ERR_CUDA, "cudaStreamWaitEvent failed"));
+                    b->input_consumed = st.consumed[s];
+                    b->hint_shift0 = (uint32_t)((uintptr_t)st.bases[s].p & 31);
+                    if (err == KTG_OK)
+                        step(b->mgd_scatter_reads((const uint8_t *)st.bases[s].p - offsets[r], (const uint64_t *)st.offs[s].p, r1 - r,
+                                                  offsets[r1] - offsets[r], rx.data(), 0, c == 0, nullptr, &d_cur, &p.hint[c]));
+                    b->input_consumed = nullptr;
+                }
+                if (err == KTG_OK) {
+                    step(cudaMemcpyAsync(cur_host.data(), d_cur, cur_host.size() * 8, cudaMemcpyDeviceToHost, b->stream) == cudaSuccess ? KTG_OK : fail(KTG_ERR_CUDA, "copying the bucket cursors failed"));
+                    void *regs = nullptr;
+                    uint32_t nregs = 0;
+                    step(b->mg_sketch(&regs, &nregs));
+                    if (err == KTG_OK)
+                        step(cudaMemcpyAsync(sketches[i].data(), regs, HLL_M * 4, cudaMemcpyDeviceToHost, b->stream) == cudaSuccess ? KTG_OK : fail(KTG_ERR_CUDA, "copying the sketch failed"));
+                    step(b->sync_stream()); // my writes into the peers' buckets have landed
+                }
+                cursors[i].assign(cur_host.begin(), cur_host.end());
+                // -- every writer is done; cursors and sketches are published
+                if (!gate.wait(err == KTG_OK)) return err != KTG_OK ? err : PEER_FAILED;
+                std::vector<unsigned long long> ends((size_t)n * n_sub);
+                uint64_t n_keys = 0;
+                for (uint32_t s = 0; s < n; ++s)
+                    for (uint32_t q = 0; q < n_sub; ++q) {
+                        const unsigned long long lo = ((unsigned long long)i * n_sub + q) * cap[i]; // the sender's virtual position
+                        const unsigned long long v = cursors[s][(size_t)i * n_sub + q];
+                        unsigned long long fill = v > lo ? v - lo : 0;
+                        if (fill > cap[i]) fill = cap[i];
+                        ends[(size_t)s * n_sub + q] = ((unsigned long long)s * n_sub + q) * cap[i] + fill;
+                        n_keys += fill;
+                    }
+                {
+                    std::vector<uint32_t> merged(sketches[0]);
+                    for (uint32_t s = 1; s < n; ++s)
+                        for (uint32_t q = 0; q < HLL_M; ++q) merged[q] = std::max(merged[q], sketches[s][q]);
+                    step(cudaMemcpyAsync(st.sketch.p, merged.data(), HLL_M * 4, cudaMemcpyHostToDevice, b->stream) == cudaSuccess ? KTG_OK : fail(KTG_ERR_CUDA, "copying the merged sketch failed"));
+                    if (err == KTG_OK) step(b->sync_stream()); // `merged` is a local
+                    if (err == KTG_OK) step(b->mg_merge_sketch(st.sketch.p));
+                }
+                if (err == KTG_OK) {
+                    step(st.ends.ensure(ends.size() * 8));
+                    if (err == KTG_OK)
+                        step(cudaMemcpyAsync(st.ends.p, ends.data(), ends.size() * 8, cudaMemcpyHostToDevice, b->stream) == cudaSuccess ? KTG_OK : fail(KTG_ERR_CUDA, "copying the bucket ends failed"));
+                    if (err == KTG_OK) step(b->sync_stream());
+                    if (err == KTG_OK) step(b->mgd_insert(st.ends.p, n_keys, 0));
+                }
+                rounds = 0; // (the rounds of the other exchanges below are skipped)
+            }
             // -- receive buffers (one bucket per source shard, two slots)
-            {
+            if (rounds) {
                 void *base = nullptr;
                 uint64_t bytes = 0, bc = 0;
                 uint32_t ns = 0;
@@ -277,7 +376,7 @@ struct MultiBuilder {
                 rx[i] = base;
                 cap[i] = bc;
             }
-            if (!gate.wait(err == KTG_OK)) return err != KTG_OK ? err : PEER_FAILED;
+            if (rounds && !gate.wait(err == KTG_OK)) return err != KTG_OK ? err : PEER_FAILED;
             const Plan &p = plan[i];
             auto issue_copy = [&](uint32_t c) -> int {
                 if (c >= p.hint.size()) return KTG_OK;
@@ -301,7 +400,7 @@ struct MultiBuilder {
                 st.used[s] = true;
                 return KTG_OK;
             };
-            step(issue_copy(0));
+            if (rounds) step(issue_copy(0));
             std::vector<unsigned long long> my_ends(n);
             for (uint32_t c = 0; c < rounds; ++c) {
                 const uint32_t slot = c & 1;

@@ -4,7 +4,11 @@ The table is sharded by owner(key) = hash(canonical k-mer) range-reduced to [0, 
 (SURVEY 8e).  Shards are disjoint by construction, so the merged GIR is their
 concatenation and all whole-graph statistics are plain reductions.
 
-Three data paths:
+Data paths:
+  direct (opt-in, exchange="direct"; needs the same table geometry on every shard): the extraction kernel of
+      every rank bins its keys by (owner, sub-table of the owner) and writes the runs straight into the owner's
+      HBM over NVLink; what arrives is already the owner's level-1 stage, so the owner goes on with its level-2
+      scatter and page sweep.  Measured slower than the key exchange on 2 B200s (short runs over NVLink).
   fused, super-k-mers (default on one node, world <= 8, 23 <= k <= 31): owner(k-mer) is a
       function of its minimizer; the sending kernel cuts every read into runs of windows that
       share a minimizer and writes each run as ONE 16-byte record straight into the owner's HBM
@@ -104,7 +108,7 @@ class ShardedGIR:
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.device = torch.device("cuda", torch.cuda.current_device())
-        mode = exchange or "fused"  # fused | skm | keys | nccl
+        mode = exchange or "fused"  # fused | direct | skm | keys | nccl
         if fused is None:
             fused = self.world <= 8 and mode != "nccl"
         self.fused = bool(fused)
@@ -115,7 +119,15 @@ class ShardedGIR:
         # is the default from SKM_MIN_WORLD ranks on ("skm" / "keys" force one).
         want_skm = mode == "skm" or (mode == "fused" and self.world >= self.SKM_MIN_WORLD)
         self.exchange = "nccl" if not self.fused else ("skm" if skm_supported(k) and want_skm else "keys")
+        # the direct exchange replaces the key exchange whenever every shard has the same geometry (checked per
+        # batch); "keys" forces the older one
+        # opt-in: measured on 2 B200s (C3, profiles/r02_mg_n2_*.json) the sender's 100-byte runs reach only
+        # ~320 GB/s over NVLink and its 11.6 ms cost more than the owner's pass it saves (5.9 + 4.4 ms)
+        self.direct = self.fused and mode == "direct"
+        if mode == "direct":
+            self.exchange = "keys"
         self._mapped_for = None
+        self.last_exchange = self.exchange
         if self.fused:
             kw.setdefault("force_partition", True)  # the fused path has no unpartitioned mode
         self.gir = GpuGIR(k, reverse_complement, edges_count=edges_count, world_size=self.world, rank=self.rank,
@@ -183,6 +195,7 @@ class ShardedGIR:
         gmax, n_chunks_all = (int(x) for x in t.tolist())
         if gmax == 0:
             return
+        self.last_exchange = "keys"
         if not self._peers or self._mapped_for != "keys" or self.gir.mg_plan(gmax):
             self._map_peers(gmax)
         cap = self._cap
@@ -248,6 +261,83 @@ class ShardedGIR:
             self.gir.mg_insert_spill(recv, sum(rcounts))
             self._keep = (keep, recv)
 
+    # The direct exchange in three steps, so that a host batch can be scattered chunk by chunk (every chunk's
+    # H2D copy under the previous chunk's kernels) and inserted once:
+    def _direct_begin(self, windows_ub: int) -> bool:
+        """collective; False (nothing done) when the shards' geometries differ: the caller takes the key exchange"""
+        W, dev = self.world, self.device
+        _, n_sub, sub_log2 = self.gir.mg_direct_plan(max(windows_ub, 1))
+        geo = (n_sub << 8) | sub_log2
+        t = torch.tensor([windows_ub, geo, -geo], dtype=torch.int64, device=dev)
+        # also orders "every rank has finished reading its receive buffer" before anybody writes again
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        gmax, gmx, gmn = (int(x) for x in t.tolist())
+        self._d_n_sub, self._d_any = n_sub, gmax > 0
+        if gmax == 0:
+            return True
+        if gmx != -gmn or W * n_sub > 1024:
+            return False
+        if not self._peers or self._mapped_for != ("direct", n_sub) or self.gir.mg_direct_plan(gmax)[0]:
+            self._unmap_peers()
+            dist.barrier(self.group)
+            base, self._slot_bytes, self._cap = self.gir.mg_direct_prepare(gmax)
+            self._mapped_for = ("direct", n_sub)
+            mine = torch.frombuffer(bytearray(ipc_get_handle(base)), dtype=torch.uint8).to(dev)
+            allh = [torch.empty_like(mine) for _ in range(W)]
+            dist.all_gather(allh, mine, group=self.group)
+            self._peers = [base if r == self.rank else ipc_open(bytes(allh[r].cpu().numpy().tobytes())) for r in range(W)]
+        self._d_cur = None
+        self._d_ub = 0
+        self.last_exchange = "direct"
+        return True
+
+    def _direct_scatter(self, d_bases, d_offsets, n_reads: int, total_bases: int, first: bool):
+        if not self._d_any:
+            return
+        self._d_cur = self.gir.mg_direct_scatter_reads_device(d_bases, d_offsets, n_reads, total_bases, self._peers, 0, first)
+        self._d_ub += max(int(total_bases) - n_reads * (self.k - 1), 0)
+
+    def _direct_finish(self):
+        if not self._d_any:
+            return
+        W, dev, n_sub, cap = self.world, self.device, self._d_n_sub, self._cap
+        if self._d_cur is None:  # nothing of mine: my cursors still have to say so
+            empty = torch.empty(1, dtype=torch.int64, device=dev)
+            self._d_cur = self.gir.mg_direct_scatter_reads_device(0, empty, 0, 0, self._peers, 0, True)
+        cur = torch.as_tensor(DeviceArray(self._d_cur, W * n_sub), device=dev)
+        got = torch.empty_like(cur)
+        dist.all_to_all_single(got, cur, group=self.group)  # n_sub cursors per owner; also: the writers' kernels have completed
+        sk_ptr, sk_n = self.gir.mg_sketch()
+        regs = torch.as_tensor(DeviceArray(sk_ptr, sk_n, "<i4"), device=dev).clone()
+        dist.all_reduce(regs, op=dist.ReduceOp.MAX, group=self.group)  # every shard sizes itself from it
+        self.gir.mg_merge_sketch(regs)
+        # got[s * n_sub + p]: where sender s stopped in its bucket for (owner = me, sub-table p)
+        lo = (self.rank * n_sub + torch.arange(n_sub, dtype=torch.int64, device=dev)).repeat(W) * cap
+        fill = (got - lo).clamp_(min=0, max=cap)
+        ends = torch.arange(W * n_sub, dtype=torch.int64, device=dev) * cap + fill
+        self.gir.mg_direct_insert(ends, int(fill.sum().item()), 0)
+        self._keep = (cur, got, regs, ends)
+        self.exchanged_bytes += int(self._d_ub * 8 * self.words * (W - 1) / W)
+        sp_ptr, n_sp = self.gir.mg_spill()  # keys that did not fit their bucket (skew): routed the slow way
+        tot = torch.tensor([n_sp], dtype=torch.int64, device=dev)
+        dist.all_reduce(tot, group=self.group)
+        if int(tot.item()):
+            ptr, counts = self.gir.partition_keys_device(sp_ptr, n_sp)
+            n = sum(counts)
+            keys = torch.as_tensor(DeviceArray(ptr, n * self.words), device=dev) if n else \
+                torch.empty(0, dtype=torch.int64, device=dev)
+            recv, rcounts = exchange_keys(keys, counts, self.words, self.group)
+            self.gir.mg_insert_spill(recv, sum(rcounts))
+            self._keep = (self._keep, recv)
+
+    def _add_reads_direct(self, d_bases, d_offsets, n_reads: int, total_bases: int) -> bool:
+        """One device-resident batch through the direct exchange; False when the geometries differ."""
+        if not self._direct_begin(max(int(total_bases) - n_reads * (self.k - 1), 0)):
+            return False
+        self._direct_scatter(d_bases, d_offsets, n_reads, total_bases, True)
+        self._direct_finish()
+        return True
+
     def _add_reads_skm(self, d_bases, d_offsets, n_reads: int, total_bases: int):
         """One batch through the super-k-mer exchange (one chunk, everything on the current stream)."""
         W, dev, k = self.world, self.device, self.k
@@ -291,6 +381,8 @@ class ShardedGIR:
             self._copy_stream = torch.cuda.Stream()
         copy = self._copy_stream
         offs = h_offsets[: n_reads + 1]
+        if self.direct and self.fused and chunks == 4:
+            chunks = 16  # chunks cost nothing in the direct exchange: small ones hide the first copy better
         n_chunks = max(1, min(chunks, n_reads // self.MIN_CHUNK_READS)) if n_reads else 1
         per = -(-n_reads // n_chunks) if n_reads else 0
         bounds = [min(i * per, n_reads) for i in range(n_chunks + 1)]
@@ -314,6 +406,8 @@ class ShardedGIR:
                 self._stage[s][1][: hi - lo + 1].copy_(offs[lo: hi + 1], non_blocking=True)
                 self._stage_ev[s][0].record(copy)
 
+        # direct exchange: the chunks are scattered as they arrive (no collective in between) and inserted once
+        direct = self.direct and self.fused and self._direct_begin(max(ob[-1] - ob[0] - n_reads * (self.k - 1), 0))
         issue(0)
         for c in range(n_chunks):
             if c + 1 < n_chunks:
@@ -322,15 +416,22 @@ class ShardedGIR:
             lo, hi = bounds[c], bounds[c + 1]
             main.wait_event(self._stage_ev[s][0])
             # the offsets stay absolute: bias the base pointer instead
-            self.add_reads_device(int(self._stage[s][0].data_ptr()) - ob[c], self._stage[s][1][: hi - lo + 1],
-                                  hi - lo, ob[c + 1] - ob[c])
+            args = (int(self._stage[s][0].data_ptr()) - ob[c], self._stage[s][1][: hi - lo + 1], hi - lo, ob[c + 1] - ob[c])
+            if direct:
+                self._direct_scatter(*args, first=c == 0)
+            else:
+                self.add_reads_device(*args)
             self._stage_ev[s][1].record(main)
             self._stage_used[s] = True
+        if direct:
+            self._direct_finish()
 
     def add_reads_device(self, d_bases, d_offsets, n_reads: int, total_bases: int):
         if self.exchange == "skm":
             return self._add_reads_skm(d_bases, d_offsets, n_reads, total_bases)
         if self.fused:
+            if self.direct and self._add_reads_direct(d_bases, d_offsets, n_reads, total_bases):
+                return None
             return self._add_reads_fused(d_bases, d_offsets, n_reads, total_bases)
         ptr, counts = self.gir.partition_reads_device(d_bases, d_offsets, n_reads, total_bases)
         n = sum(counts)

@@ -396,6 +396,30 @@ class GpuGIR:
     def mg_insert_buckets(self, d_bucket_ends, n_keys: int, slot: int = 0):
         _check(self._L.ktg_mg_insert_buckets(self._h, _ptr(d_bucket_ends), int(n_keys), int(slot)))
 
+    # ---- the direct exchange (sender partitions by (owner, sub-table)) ----
+    def mg_direct_plan(self, max_windows: int):
+        """-> (needs_realloc, n_sub, sub_log2) of this shard"""
+        r, ns, sl = C.c_int(0), C.c_uint32(0), C.c_uint32(0)
+        _check(self._L.ktg_mg_direct_plan(self._h, int(max_windows), C.byref(r), C.byref(ns), C.byref(sl)))
+        return bool(r.value), int(ns.value), int(sl.value)
+
+    def mg_direct_prepare(self, max_windows: int):
+        base, nbytes, cap = C.c_void_p(), C.c_uint64(), C.c_uint64()
+        _check(self._L.ktg_mg_direct_prepare(self._h, int(max_windows), C.byref(base), C.byref(nbytes), C.byref(cap)))
+        return int(base.value), int(nbytes.value), int(cap.value)
+
+    def mg_direct_scatter_reads_device(self, d_bases, d_offsets, n_reads: int, total_bases: int, peer_rx, slot: int = 0,
+                                       first_of_batch: bool = True, send_stream: Optional[int] = None) -> int:
+        arr = (C.c_void_p * self.world_size)(*[C.c_void_p(int(p)) for p in peer_rx])
+        cur = C.c_void_p()
+        _check(self._L.ktg_mg_direct_scatter_reads_device(self._h, _ptr(d_bases), _ptr(d_offsets), int(n_reads),
+                                                          int(total_bases), arr, int(slot), int(bool(first_of_batch)),
+                                                          C.c_void_p(send_stream or None), C.byref(cur)))
+        return int(cur.value)
+
+    def mg_direct_insert(self, d_bucket_ends, n_keys: int, slot: int = 0):
+        _check(self._L.ktg_mg_direct_insert(self._h, _ptr(d_bucket_ends), int(n_keys), int(slot)))
+
     def mg_sketch(self):
         p, n = C.c_void_p(), C.c_uint32()
         _check(self._L.ktg_mg_sketch(self._h, C.byref(p), C.byref(n)))

@@ -716,9 +716,14 @@ def test_one_handle_over_several_shards(K, k, shards, rc, tmp_path):
     cpu = _oracle(seqs, k, rc)
     bases, offsets = H.batch_of(seqs)
     ids = [0] * shards
-    g = K.GpuGIR(k, rc, device_ids=ids, options={"chunk_mb": 1})  # several rounds per call
+    g = K.GpuGIR(k, rc, device_ids=ids, options={"chunk_mb": 1})  # several chunks per call
     assert g.add_reads(bases, offsets) == (cpu.accepted_reads, cpu.accepted_bytes)
     _assert_same(g, cpu)
+    # the direct exchange (the sender does the owner's level-1 partition too; opt-in)
+    g2 = K.GpuGIR(k, rc, device_ids=ids, options={"chunk_mb": 1, "mg_direct": 1})
+    assert g2.add_reads(bases, offsets) == (cpu.accepted_reads, cpu.accepted_bytes)
+    assert g2.digest() == cpu.digest() and g2.counts() == cpu.counts()
+    g2.close()
     one = K.GpuGIR(k, rc)
     one.add_reads(bases, offsets)
     ga, gb = g.export_graph(), one.export_graph()
@@ -958,7 +963,7 @@ def test_device_fastq_parser_matches_host_reader(K, tmp_path):
     files = {
         "plain": fastq(seqs), "crlf": fastq(seqs, nl="\r\n"), "no_final_newline": fastq(seqs, final_nl=False),
         "trailing_blanks": fastq(seqs, pad=" \t"), "ragged": fastq(ragged), "empty": "",
-        "one_record": fastq(seqs[:1]),
+        "one_record": fastq(seqs[:1]), "many_blocks": fastq(ragged * 12),
     }
     bad = {
         "no_at_first": "read0\nACGT\n+\nIIII\n", "no_at_later": fastq(seqs[:5]) + "read5\nACGT\n+\nIIII\n",
@@ -969,7 +974,8 @@ def test_device_fastq_parser_matches_host_reader(K, tmp_path):
     for name, text in {**files, **bad}.items():
         p = tmp_path / f"{name}.fastq"
         p.write_bytes(text.encode())
-        for chunk_kb in (None, 1, 3):  # tiny chunks: records carried across chunk boundaries
+        # tiny chunks: records carried across chunk boundaries; 64 KiB: the threaded block reader with a carry
+        for chunk_kb in (None, 1, 3, 64):
             dev, host = _both_fastq_parsers(K, str(p), 40, True, chunk_kb)
             assert dev == host, (name, chunk_kb, dev, host)
             assert (dev[0] == "error") == (name in bad), (name, dev)
