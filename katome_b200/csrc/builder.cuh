@@ -200,7 +200,8 @@ struct Tuning {
     int stage_factor_milli = 0; // keys per flush in thousandths of the capacity (0: 750 host paced, 3000 resident)
     long long stage_max_keys = 0; // most keys one stage may hold (0: what memory allows)
     int host_parse = 0;      // ktg_create_from_files: FASTQ / FASTA records cut by the host reader
-    int fastq_chunk_kb = 16 << 10; // device parser: raw bytes per chunk
+    int fastq_chunk_kb = 8 << 10; // device parser: raw bytes per chunk (page-locked memory costs ~1 ms per MiB to allocate:
+                                  // four 16 MiB blocks were 74 ms of a 157 ms Build::create from a 950 MB FASTQ file)
     int mg_pad = 1;          // fused exchange: runs padded to 128-byte lines
     int mg_direct = 0;       // multi-device handle: the direct exchange (sender bins by owner and sub-table) where the shards agree on their geometry
     int trace = 0;           // host timeline on stderr

@@ -557,7 +557,9 @@ struct FastqDeviceParser {
         for (size_t j = 0; j < nb; ++j) {
             uint8_t *p = nullptr;
             size_t got = 0;
+            trace("block wanted", j);
             if (!rd.acquire(j, &p, &got)) return fail(KTG_ERR_IO, "reading the file failed");
+            trace("block there", j);
             if (carry.size() > BlockReader::HEAD) return fail(KTG_ERR_BAD_RECORD, "a FASTQ record is larger than %zu bytes", BlockReader::HEAD);
             uint8_t *h = p - carry.size();
             if (!carry.empty()) memcpy(h, carry.data(), carry.size());
@@ -570,6 +572,7 @@ struct FastqDeviceParser {
             // the copy of this block to the device must have finished before its buffer is read into again
             KTG_CUDA(cudaEventSynchronize(copied[j & 1]));
             rd.release(j);
+            trace("block done", j);
         }
         return KTG_OK;
     }
@@ -592,12 +595,15 @@ int ktg_create_from_files(ktg_builder *b, const char *const *paths, uint32_t n_p
         files.push_back(std::move(f));
     }
     // records are cut on the device (option host_parse keeps the host reader, its twin)
+    trace("create_from_files", n_paths);
     if (!b->multi && !b->impl->tune.host_parse) {
         // small: the two pinned buffers are allocated per call (0.3 ms / MiB)
         const size_t chunk = (size_t)std::max(1, b->impl->tune.fastq_chunk_kb) << 10;
         FastqDeviceParser parser(b, chunk);
         KTG_TRY(parser.init());
+        trace("parser ready");
         for (auto &f : files) KTG_TRY(file_type == KTG_FASTA ? parser.parse_fasta(*f) : parser.parse(*f));
+        trace("files parsed");
         KTG_TRY(b->impl->read_counters(&reads, &bytes));
         if (total_bytes) *total_bytes = bytes;
         return ktg_finalize(b);

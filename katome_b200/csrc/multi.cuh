@@ -404,6 +404,7 @@ struct MultiBuilder {
             std::vector<unsigned long long> my_ends(n);
             for (uint32_t c = 0; c < rounds; ++c) {
                 const uint32_t slot = c & 1;
+                trace("mh round>", i * 1000 + c);
                 step(issue_copy(c + 1)); // the next chunk's copy runs under this round
                 // -- sender: pack + extract + scatter into the owners' buckets
                 void *d_cur = nullptr, *d_kc = nullptr;
@@ -437,8 +438,10 @@ struct MultiBuilder {
                     }
                     step(b->sync_stream()); // my writes into the peers' buckets have landed
                 }
+                trace("mh scattered", i * 1000 + c);
                 // -- every writer is done; cursors (and sketches) are published
                 if (!gate.wait(err == KTG_OK)) return err != KTG_OK ? err : PEER_FAILED;
+                trace("mh barrier<", i * 1000 + c);
                 // -- owner: what the shards wrote into my buckets
                 uint64_t n_keys = 0;
                 for (uint32_t s = 0; s < n; ++s) {
@@ -462,6 +465,7 @@ struct MultiBuilder {
                     if (err == KTG_OK) step(b->sync_stream());
                     if (err == KTG_OK) step(skm ? b->mg_skm_insert_buckets(st.ends.p, n_keys, slot) : b->mg_insert_buckets(st.ends.p, n_keys, slot));
                 }
+                trace("mh inserted", i * 1000 + c);
                 // (the insert ends with a stream synchronisation: when the next barrier is passed, every
                 // shard has consumed this slot, which is written again two rounds from now)
             }

@@ -282,22 +282,32 @@ class GpuGIR:
         assert n.value == ne
         return hi, lo, w
 
-    def export_graph(self, pinned: bool = False) -> dict:
+    def export_graph(self, pinned: bool = False, out: Optional[dict] = None) -> dict:
         """What Convert::create_from builds (hm_gir.rs:156-226), canonical numbering: sorted
         nodes, sorted edges as (src index, dst index, weight) and in compress_edge bytes.
-        pinned: the arrays live in page-locked memory (ktg_host_alloc), which takes the copies at PCIe speed."""
+        pinned: the arrays live in page-locked memory (ktg_host_alloc), which takes the copies at PCIe speed;
+        out: arrays of an earlier call to write into again (reused when large enough: page-locked memory is
+        slow to allocate, ~0.3 ms per MiB)."""
         n, e = C.c_uint64(0), C.c_uint64(0)
         _check(self._L.ktg_graph_prepare(self._h, C.byref(n), C.byref(e)))
         nn, ne = n.value, e.value
         rec = int(self._L.ktg_edge_record_bytes(self._h))
         new = _pinned_empty if pinned else (lambda shape, dt: np.zeros(shape, dt))
-        out = {"node_hi": new(nn, np.uint64), "node_lo": new(nn, np.uint64),
-               "src": new(ne, np.uint64), "dst": new(ne, np.uint64), "weight": new(ne, np.uint32),
-               "edge_bytes": new((ne, rec), np.uint8)}
-        _check(self._L.ktg_export_graph(self._h, out["node_hi"].ctypes.data, out["node_lo"].ctypes.data, nn,
-                                        out["src"].ctypes.data, out["dst"].ctypes.data, out["weight"].ctypes.data,
-                                        out["edge_bytes"].ctypes.data, ne))
-        return out
+        want = {"node_hi": (nn, np.uint64), "node_lo": (nn, np.uint64), "src": (ne, np.uint64), "dst": (ne, np.uint64),
+                "weight": (ne, np.uint32), "edge_bytes": (ne * rec, np.uint8)}
+        store = out if out is not None else {}
+        res = {}
+        for name, (cnt, dt) in want.items():
+            base = store.get("_" + name)
+            if base is None or base.size < cnt or base.dtype != dt:
+                base = new(max(cnt + cnt // 8, 1), dt)
+                store["_" + name] = base
+            res[name] = base[:cnt]
+        res["edge_bytes"] = res["edge_bytes"].reshape(ne, rec)
+        _check(self._L.ktg_export_graph(self._h, res["node_hi"].ctypes.data, res["node_lo"].ctypes.data, nn,
+                                        res["src"].ctypes.data, res["dst"].ctypes.data, res["weight"].ctypes.data,
+                                        res["edge_bytes"].ctypes.data, ne))
+        return res
 
     def export_externals(self):
         """`Externals` of remove_dead_paths (pruner.rs:165-195): (node indices ascending, kinds) with kind 0 =

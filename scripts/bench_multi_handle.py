@@ -24,6 +24,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--export", action="store_true", help="also time remove_weak_edges(3) + export_graph")
+    ap.add_argument("--trace", action="store_true", help="host timeline of the last step on stderr (option trace)")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE")
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -45,9 +47,12 @@ def main():
     del d
     offs = torch.arange(0, (n + 1) * L, L, dtype=torch.int64).pin_memory()
     kw = {"device_ids": ids} if len(ids) > 1 else {"device": ids[0]}
+    kw["options"] = {kv.split("=")[0]: int(kv.split("=")[1]) for kv in args.opt}
     g = GpuGIR(wl.k, True, edges_count=wl.expected_distinct_edges(), **kw)
     times, dig = [], None
     for i in range(args.warmup + args.steps):
+        if args.trace and i == args.warmup + args.steps - 1:
+            g.set_option("trace", 1)
         t0 = time.perf_counter()
         g.reset()
         g.add_reads_host_ptr(h.data_ptr(), offs.data_ptr(), n)
