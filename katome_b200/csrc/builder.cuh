@@ -281,7 +281,7 @@ struct BuilderBase {
     virtual int mg_insert_spill(const void *d_keys, uint64_t n) = 0;
     virtual int mg_scatter_reads(const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t n_reads,
                                  uint64_t total_bases, void *const *peer_rx, uint32_t slot, int first_of_batch,
-                                 cudaStream_t send_stream, void **d_cursors) = 0;
+                                 cudaStream_t send_stream, void **d_cursors, const BatchHint *hint = nullptr) = 0;
     virtual int mg_insert_buckets(const void *d_bucket_ends, uint64_t n_keys, uint32_t slot) = 0;
     // the direct exchange: the sender partitions by (owner, sub-table), the owner goes straight to the page level
     virtual int mgd_plan(uint64_t max_windows, int *needs_realloc, uint32_t *n_sub, uint32_t *sub_log2) = 0;
@@ -298,7 +298,8 @@ struct BuilderBase {
     virtual int mg_skm_prepare(uint64_t max_windows, void **rx_base, uint64_t *rx_bytes, uint64_t *bucket_cap) = 0;
     virtual int mg_skm_scatter_reads(const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t n_reads,
                                      uint64_t total_bases, void *const *peer_rx, uint32_t slot, int first_of_batch,
-                                     cudaStream_t send_stream, void **d_cursors, void **d_key_counts) = 0;
+                                     cudaStream_t send_stream, void **d_cursors, void **d_key_counts,
+                                     const BatchHint *hint = nullptr) = 0;
     virtual int mg_skm_insert_buckets(const void *d_bucket_ends, uint64_t n_keys_ub, uint32_t slot) = 0;
     virtual int mg_skm_spill(void **d_records, uint64_t *n) = 0;
     virtual int mg_skm_partition_records(const void *d_records, uint64_t n, void **d_out, uint64_t *counts) = 0;
@@ -1874,7 +1875,7 @@ template <class K> struct Builder : BuilderBase {
     // work of the previous chunk; peer_rx are the slot-0 bases of all ranks.
     int mg_scatter_reads(const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t n_reads,
                          uint64_t total_bases, void *const *peer_rx, uint32_t slot, int first_of_batch,
-                         cudaStream_t send_stream, void **d_cursors) override {
+                         cudaStream_t send_stream, void **d_cursors, const BatchHint *hint = nullptr) override {
         if (deferred_error != KTG_OK) return fail(deferred_error, "build is void after an earlier error");
         if (!b_rx.p) return fail(KTG_ERR_INVALID, "ktg_mg_prepare first");
         if (slot >= MG_SLOTS) return fail(KTG_ERR_INVALID, "slot out of range");
@@ -1893,7 +1894,7 @@ template <class K> struct Builder : BuilderBase {
         if (first_of_batch) KTG_CUDA(cudaMemsetAsync(mg_spill_cursor(), 0, 8, stream));
         if (n_reads == 0) return KTG_OK;
         Batch bt;
-        KTG_TRY(pack(d_bases, d_offsets, n_reads, total_bases, &bt));
+        KTG_TRY(pack(d_bases, d_offsets, n_reads, total_bases, &bt, hint, hint_shift0));
         if (bt.windows == 0) return KTG_OK;
         PeerOut po{};
         po.world = W;
@@ -2166,7 +2167,8 @@ template <class K> struct Builder : BuilderBase {
 
     int mg_skm_scatter_reads(const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t n_reads,
                              uint64_t total_bases, void *const *peer_rx, uint32_t slot, int first_of_batch,
-                             cudaStream_t send_stream, void **d_cursors, void **d_key_counts) override {
+                             cudaStream_t send_stream, void **d_cursors, void **d_key_counts,
+                             const BatchHint *hint = nullptr) override {
         if (deferred_error != KTG_OK) return fail(deferred_error, "build is void after an earlier error");
         KTG_TRY(skm_check());
         if (!b_rx.p || !skm_cap) return fail(KTG_ERR_INVALID, "ktg_mg_skm_prepare first");
@@ -2187,7 +2189,7 @@ template <class K> struct Builder : BuilderBase {
         if (first_of_batch) KTG_CUDA(cudaMemsetAsync(mg_spill_cursor(), 0, 8, stream));
         if (n_reads == 0) return KTG_OK;
         Batch bt;
-        KTG_TRY(pack(d_bases, d_offsets, n_reads, total_bases, &bt));
+        KTG_TRY(pack(d_bases, d_offsets, n_reads, total_bases, &bt, hint, hint_shift0));
         if (bt.windows == 0) return KTG_OK;
         SkmView sv{};
         sv.v = bt.v;
