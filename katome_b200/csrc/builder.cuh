@@ -2232,9 +2232,10 @@ template <class K> struct Builder : BuilderBase {
             const uint64_t n_rtiles = (cap / SREC_THREADS + 1) * n_buckets;
             if ((double)n_rtiles >= 4.0e9) return fail(KTG_ERR_INVALID, "batch too large: split it");
             KTG_TRY(stage_add(n_keys_ub, [&](uint32_t n_bins, const ScatterOut &o) -> int {
-                const size_t ss = ScatterSmem<K, SREC_TILE>::bytes(n_bins, false);
+                const size_t ss = ((ScatterSmem<K, SREC_TILE>::bytes(n_bins, false) + 15) & ~(size_t)15) + (size_t)SREC_STAGE * 8;
                 auto launch = [&](auto kern) {
-                    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ScatterSmem<K, SREC_TILE>::bytes(MAX_BINS, false));
+                    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(((ScatterSmem<K, SREC_TILE>::bytes(MAX_BINS, false) + 15) & ~(size_t)15) + (size_t)SREC_STAGE * 8));
                     int g = (int)std::min<uint64_t>(grid_for(kern, SREC_THREADS, ss, props), std::max<uint64_t>(n_rtiles, 1));
                     kern<<<g, SREC_THREADS, ss, stream>>>(rx, ends, cap, n_buckets, k, tab, o, (uint32_t *)b_hll.p);
                 };

@@ -566,7 +566,7 @@ template <class K, int TILE> struct ScatterSmem {
         regs = cnt + 2 * n_bins;
         binof = (uint16_t *)(regs + (hll ? HLL_M : 0));
     }
-    static size_t bytes(uint32_t n_bins, bool hll) {
+    __host__ __device__ static size_t bytes(uint32_t n_bins, bool hll) {
         return (size_t)TILE * (sizeof(K) + 2) + (size_t)n_bins * 28 + (hll ? HLL_M * 4 : 0);
     }
 };

@@ -328,32 +328,35 @@ scatter_superkmers_kernel(SkmView sv, uint32_t k, uint32_t world, ScatterOut o, 
 // ---- owner: received records -> canonical k-mers -> level-1 buckets, in ONE kernel.  Bucket q of
 // the receive slot holds what source rank q wrote: records [q*cap, min(ends[q], (q+1)*cap)).
 // (Round 1 unrolled the records into a flat array in HBM and partitioned that array with a second
-// kernel: 8 bytes per key written and read again, 1.4 ms of a 8.8 ms step at N = 8.)
-// A warp takes 32 records, which hold T <= 512 k-mers; k-mer s belongs to the record whose first
-// k-mer is the last "head" at or before s.  The heads are a 512-bit map (16 words of shared memory per
-// warp); lane l produces k-mers s = 32*it + l: it finds its record with two popcounts, fetches that
-// record and its first index from the owning lane with shuffles and cuts the k-mer out of the 128
-// bits directly (no rolling state), so the lanes stay balanced whatever the record lengths (a
-// lane-per-record loop runs to the longest record of the row, 16 iterations against 5.5 on average).
-// The k-mers never leave the registers: 8 iterations fill one tile of the partitioner (tile_scatter,
-// bins = sub-tables), which also feeds the cardinality sketch; rows with more than 256 k-mers (records
-// longer than 8 windows on average: low-complexity reads) take a second tile.
+// kernel: 8 bytes per key written and read again.)
+// Two stages inside the CTA, both in shared memory:
+//   A  a lane unrolls ITS record with the rolling fw / rc of the read extraction (a dozen
+//      instructions per k-mer) into a dense staging array -- the warp reserves the room of its 32
+//      records with one shared atomicAdd.  Records are 1..16 windows long (5.5 on average), so the
+//      lanes of a warp finish at different times; that is cheap here because the loop body is, and
+//      the k-mers land in shared memory, not in HBM (the balanced scheme -- lane l makes k-mer
+//      32 it + l, finds its record with two popcounts and four shuffles -- cost 3x the instructions
+//      per k-mer and left the partitioner's tiles 69 % full);
+//   B  whenever 2048 k-mers are staged they go through the tile scatter (bins = sub-tables) as one
+//      full tile, which also feeds the cardinality sketch.
 constexpr int SREC_THREADS = 256, SREC_PER = 8, SREC_TILE = SREC_THREADS * SREC_PER;
+constexpr int SREC_STAGE = SREC_TILE + SREC_THREADS * (int)SKM_W; // what is left over + one round of records at their longest
 template <bool RC>
 __global__ void __launch_bounds__(SREC_THREADS, 3)
 scatter_records_kernel(const u128 *__restrict__ rx, const unsigned long long *__restrict__ ends, uint64_t cap,
                        uint32_t n_buckets, uint32_t k, Table<uint64_t> t, ScatterOut o, uint32_t *__restrict__ g_regs) {
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ uint32_t s_heads[SREC_THREADS / 32][16];
     __shared__ unsigned long long s_end[MAX_P2P_WORLD];
     __shared__ uint32_t s_tbase[MAX_P2P_WORLD + 1]; // data tiles before bucket q (tiles past a bucket's fill are not visited)
+    __shared__ uint32_t s_count;                    // k-mers in the staging array
     const uint32_t n_bins = t.n_sub;
     ScatterSmem<uint64_t, SREC_TILE> sm;
     sm.carve(smem, n_bins, false);
+    uint64_t *stage = (uint64_t *)(smem + ((ScatterSmem<uint64_t, SREC_TILE>::bytes(n_bins, false) + 15) & ~(size_t)15));
     for (uint32_t i = threadIdx.x; i < 2 * n_bins; i += SREC_THREADS) sm.cnt[i] = 0;
-    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t *heads = s_heads[wid];
+    const uint32_t lane = threadIdx.x & 31;
     const uint64_t kmask = (1ull << (2 * k)) - 1ull;
+    const uint32_t rc_shift = 2 * (k - 1);
     if (threadIdx.x == 0) {
         uint32_t run = 0;
         for (uint32_t q = 0; q < n_buckets; ++q) {
@@ -364,6 +367,7 @@ scatter_records_kernel(const u128 *__restrict__ rx, const unsigned long long *__
             run += e > beg ? (uint32_t)((e - beg + SREC_THREADS - 1) / SREC_THREADS) : 0u;
         }
         s_tbase[n_buckets] = run;
+        s_count = 0;
     }
     __syncthreads();
     const uint32_t n_tiles = s_tbase[n_buckets];
@@ -380,12 +384,37 @@ scatter_records_kernel(const u128 *__restrict__ rx, const unsigned long long *__
             hi = raw.y;
         }
     };
+    uint32_t parity = 0;
+    // stage B: the last `take` staged k-mers as one tile of the partitioner
+    auto drain = [&](uint32_t count) {
+        const uint32_t take = count < (uint32_t)SREC_TILE ? count : (uint32_t)SREC_TILE, from = count - take;
+        uint64_t key[SREC_PER];
+        uint32_t bin[SREC_PER];
+        uint32_t vmask = 0, sampled = 0;
+#pragma unroll
+        for (int q = 0; q < SREC_PER; ++q) {
+            const uint32_t i = q * SREC_THREADS + threadIdx.x;
+            const bool in = i < take;
+            key[q] = in ? stage[from + i] : 0ull;
+            const uint32_t ph = KeyTraits<uint64_t>::place_hash(key[q]);
+            bin[q] = place_of(ph, t.world, t.n_sub).part;
+            if (in) {
+                vmask |= 1u << q;
+                if (hll_sampled(ph)) sampled |= 1u << q;
+            }
+        }
+        hll_update_tile<uint64_t, SREC_PER>(g_regs, key, sampled);
+        tile_scatter<uint64_t, SREC_THREADS, SREC_PER>(key, bin, vmask, sm, n_bins, o.cursors, 0, o, parity);
+        parity ^= 1u;
+        if (threadIdx.x == 0) s_count = from;
+        __syncthreads();
+    };
     uint64_t nhi, nlo;
     fetch(blockIdx.x, nhi, nlo);
-    uint32_t parity = 0;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint64_t rhi = nhi, rlo = nlo;
         fetch(tile + gridDim.x, nhi, nlo);
+        // stage A
         const uint32_t n = (rhi & rlo) == ~0ull ? 0u : ((uint32_t)rlo & 63u) + 1u; // all-ones: filler of a padded run
         uint32_t incl = n;
 #pragma unroll
@@ -394,63 +423,30 @@ scatter_records_kernel(const u128 *__restrict__ rx, const unsigned long long *__
             if (lane >= (uint32_t)d) incl += x;
         }
         const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-        const uint32_t excl = incl - n;
-        if (lane < 16) heads[lane] = 0;
-        __syncwarp();
-        if (n) atomicOr(&heads[excl >> 5], 1u << (excl & 31u));
-        __syncwarp();
-        // lane w < 16: heads in the words before word w; lanes with n == 0 own no head
-        const uint32_t my_word = lane < 16 ? heads[lane] : 0u;
-        uint32_t before = __popc(my_word);
-#pragma unroll
-        for (int d = 1; d < 16; d <<= 1) {
-            const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, before, d);
-            if (lane >= (uint32_t)d) before += x;
-        }
-        before -= __popc(my_word); // exclusive
-        // the h-th head (in index order) belongs to the h-th lane with n > 0
-        const uint32_t nz = __ballot_sync(0xFFFFFFFFu, n != 0);
-        for (uint32_t half = 0; half < 2; ++half) {
-            if (half && !__syncthreads_or(total > 32u * SREC_PER)) break; // block-uniform
-            uint64_t key[SREC_PER];
-            uint32_t bin[SREC_PER];
-            uint32_t vmask = 0, sampled = 0;
-#pragma unroll
-            for (int q = 0; q < SREC_PER; ++q) {
-                const uint32_t it = half * SREC_PER + q;
-                key[q] = 0;
-                bin[q] = 0;
-                if (32u * it >= total) continue; // warp-uniform
-                const uint32_t word = __shfl_sync(0xFFFFFFFFu, my_word, it);
-                const uint32_t wb = __shfl_sync(0xFFFFFFFFu, before, it);
-                const uint32_t s = 32 * it + lane;
-                const uint32_t h = wb + __popc(word & (0xFFFFFFFFu >> (31 - lane))) - 1u; // head index, valid if s < total
-                const uint32_t src = nz == 0xFFFFFFFFu ? h : __fns(nz, 0, (int)h + 1);    // lane of the h-th non-empty record
-                const uint32_t sl = src & 31u; // (s >= total: garbage in, nothing kept)
-                const uint64_t hi = __shfl_sync(0xFFFFFFFFu, rhi, sl), lo = __shfl_sync(0xFFFFFFFFu, rlo, sl);
-                const uint32_t first = __shfl_sync(0xFFFFFFFFu, excl, sl);
-                if (s < total) {
-                    const uint32_t j = s - first;
-                    const uint32_t sh = 128 - 2 * (k + j); // 36 .. 82
-                    const uint64_t fw = (sh >= 64 ? hi >> (sh - 64) : (hi << (64 - sh)) | (lo >> sh)) & kmask;
-                    uint64_t kk = fw;
-                    if (RC) {
-                        const uint64_t rc = revcomp(fw, k);
-                        if (rc < fw) kk = rc;
-                    }
-                    key[q] = kk;
-                    const uint32_t ph = KeyTraits<uint64_t>::place_hash(kk);
-                    bin[q] = place_of(ph, t.world, t.n_sub).part;
-                    vmask |= 1u << q;
-                    if (hll_sampled(ph)) sampled |= 1u << q;
-                }
+        uint32_t base = 0;
+        if (lane == 0 && total) base = atomicAdd(&s_count, total);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0) + incl - n;
+        if (n) {
+            // the record's bases, first base in bits 127:126: the first k-mer is its top 2k bits (k <= 31),
+            // the up to 15 bases that follow are the next bits
+            uint64_t fw = rhi >> (64 - 2 * k);
+            uint64_t rest = (rhi << (2 * k)) | (rlo >> (64 - 2 * k));
+            uint64_t rc = RC ? revcomp(fw, k) : 0ull;
+            for (uint32_t j = 0; j < n; ++j) {
+                stage[base + j] = (RC && rc < fw) ? rc : fw;
+                const uint64_t b = rest >> 62;
+                rest <<= 2;
+                fw = ((fw << 2) | b) & kmask;
+                if (RC) rc = (rc >> 2) | ((3ull - b) << rc_shift);
             }
-            hll_update_tile<uint64_t, SREC_PER>(g_regs, key, sampled);
-            tile_scatter<uint64_t, SREC_THREADS, SREC_PER>(key, bin, vmask, sm, n_bins, o.cursors, 0, o, parity);
-            parity ^= 1u;
         }
-        __syncwarp();
+        __syncthreads();
+        uint32_t staged = s_count; // every thread reads the same value: nobody adds to it before the next barrier
+        __syncthreads();
+        for (; staged >= (uint32_t)SREC_TILE; staged -= SREC_TILE) drain(staged);
     }
+    __syncthreads();
+    if (s_count) drain(s_count);
 }
 
 // ---- spill route (records that did not fit a receive bucket): group by owner with plain

@@ -41,7 +41,7 @@ def main():
                 g.finalize()
             torch.cuda.synchronize()
         prof0 = gs[0].profile()
-        owner_ms = [sum(g.profile().get(n, {"ms": 0})["ms"] for n in ("unroll_records", "scatter_received")) for g in gs]
+        owner_ms = [sum(g.profile().get(n, {"ms": 0})["ms"] for n in ("unroll_records", "scatter_received", "scatter_records")) for g in gs]
         digs = [g.digest() for g in gs]
         assert sum(x[2] for x in digs) == 2 * windows, (digs, windows)
         print(json.dumps({"world": W, "workload": wl.name, "windows": windows, "records": n_rec,
