@@ -1,10 +1,8 @@
 #!/usr/bin/env python3
-"""Host timeline (KTG_TRACE) of one end-to-end build from pinned host memory: trace_e2e.py [c2|c3|c3k63] [--no-trace] [--no-profile]"""
+"""Host timeline (option `trace`) of one end-to-end build from pinned host memory: trace_e2e.py [c2|c3|c3k63] [--no-trace] [--no-profile]"""
 import os
 import sys
 
-if "--no-trace" not in sys.argv:
-    os.environ["KTG_TRACE"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from katome_b200 import GpuGIR, synth_reads_device
@@ -20,7 +18,8 @@ h = torch.empty(n * L, dtype=torch.uint8).pin_memory()
 h.copy_(d[: n * L])
 offs = torch.arange(0, (n + 1) * L, L, dtype=torch.int64).pin_memory()
 PROFILE = "--no-profile" not in sys.argv
-g = GpuGIR(wl.k, True, device=0, stream=stream, profile=PROFILE, edges_count=wl.expected_distinct_edges())
+g = GpuGIR(wl.k, True, device=0, stream=stream, profile=PROFILE, edges_count=wl.expected_distinct_edges(),
+           options={"trace": 0 if "--no-trace" in sys.argv else 1})
 for i in range(6 if "--no-trace" in sys.argv else 3):
     torch.cuda.synchronize()
     print(f"=== step {i}", file=sys.stderr, flush=True)
