@@ -738,7 +738,7 @@ template <class K> struct Builder : BuilderBase {
         if (c.min_len == c.max_len) { // every read has the same length: closed-form item map
             const uint32_t L = (uint32_t)c.max_len;
             v.ulen = L;
-            v.ipr = L >= k ? (L - k + 1 + GRAN - 1) / GRAN : 0;
+            v.set_ipr(L >= k ? (L - k + 1 + GRAN - 1) / GRAN : 0);
             v.n_items = n_reads * v.ipr;
         }
         else if (bt->windows) { // ragged: mark the window starts, items are (word, granule) pairs
@@ -750,7 +750,8 @@ template <class K> struct Builder : BuilderBase {
                                                          (uint32_t *)b_wstart.p);
             prof.end(stream);
             v.wstart = (const uint32_t *)b_wstart.p;
-            v.ulen = v.ipr = 0;
+            v.ulen = 0;
+            v.set_ipr(0);
             v.n_items = v.n_words * ITEMS_PER_WORD;
         }
         // nothing after this point reads the caller's bases or offsets
@@ -827,7 +828,7 @@ template <class K> struct Builder : BuilderBase {
         prof.begin(po ? "scatter_reads_p2p" : "scatter_reads", bt.windows, stream);
         if (cap_ctas > 0) n_tiles = std::min<uint64_t>(n_tiles, (uint64_t)props.sms * cap_ctas);
         auto launch = [&](auto kern, int per) {
-            const size_t sb = (size_t)SCATTER_THREADS * per * (sizeof(K) + 2) + (size_t)n_bins * 28 + (HLL ? HLL_M * 4 : 0);
+            const size_t sb = scatter_smem_bytes((size_t)SCATTER_THREADS * per, sizeof(K), n_bins, HLL);
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(sb, mx_scatter_smem()));
             int g = (int)std::min<uint64_t>(grid_for(kern, SCATTER_THREADS, sb, props), n_tiles);
             kern<<<g, SCATTER_THREADS, sb, stream>>>(bt.v, k, tab, n_bins, o, (uint32_t *)b_hll.p, peers);
@@ -907,7 +908,7 @@ template <class K> struct Builder : BuilderBase {
         prof.begin("scatter_pages", n_keys, stream);
         auto launch_v = [&](auto kern, int threads, int per) {
             const uint64_t tile = (uint64_t)threads * per, tpb = cap1 / tile, nt = tpb * n_bins;
-            const size_t sb = (size_t)tile * (sizeof(K) + 2) + (size_t)tab.pages_per_sub() * 28;
+            const size_t sb = scatter_smem_bytes(tile, sizeof(K), tab.pages_per_sub(), false);
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);
             int gg = (int)std::min<uint64_t>(grid_for(kern, threads, sb, props), nt);
             kern<<<gg, threads, sb, stream>>>(keys1, fill1, cap1, tpb, nt, sub_mod, false, tab, o, nullptr);
@@ -942,13 +943,19 @@ template <class K> struct Builder : BuilderBase {
             const size_t ps = page_kernel_smem<K>(threads, nb, tab.page_log2);
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps);
             int g = (int)std::min<uint64_t>(grid_for(kern, threads, ps, props), n_pages);
-            kern<<<g, threads, ps, stream>>>((const K *)b_pkeys.p, cur2, cap2, k, palin, special, tab, empty);
+            kern<<<g, threads, ps, stream>>>((const K *)b_pkeys.p, cur2, cap2, k, tab, empty);
         };
-        if (nbuf == 2 && pt >= 1024) launch_p(update_pages_kernel<K, 1024, 2>, 1024, 2);
-        else if (nbuf == 2) launch_p(update_pages_kernel<K, 768, 2>, 768, 2);
-        else if (pt >= 704) launch_p(update_pages_kernel<K, 704, 1>, 704, 1);
-        else if (pt >= 640) launch_p(update_pages_kernel<K, 640, 1>, 640, 1);
-        else launch_p(update_pages_kernel<K, 512, 1>, 512, 1);
+        auto launch_m = [&](auto mode) { // the kernel is specialised for what a key may need besides the plain update
+            constexpr int M = decltype(mode)::value;
+            if (nbuf == 2 && pt >= 1024) launch_p(update_pages_kernel<K, 1024, 2, M>, 1024, 2);
+            else if (nbuf == 2) launch_p(update_pages_kernel<K, 768, 2, M>, 768, 2);
+            else if (pt >= 704) launch_p(update_pages_kernel<K, 704, 1, M>, 704, 1);
+            else if (pt >= 640) launch_p(update_pages_kernel<K, 640, 1, M>, 640, 1);
+            else launch_p(update_pages_kernel<K, 512, 1, M>, 512, 1);
+        };
+        if (palin) launch_m(std::integral_constant<int, PAGE_PALIN>{});
+        else if (special) launch_m(std::integral_constant<int, PAGE_SPECIAL>{});
+        else launch_m(std::integral_constant<int, PAGE_PLAIN>{});
         prof.end(stream);
         fresh = false;
         touch();

@@ -15,6 +15,7 @@
 namespace ktg {
 
 // ------------------------------------------------------------------ helpers
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint64_t warp_sum(uint64_t v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
     return v;
@@ -282,7 +283,21 @@ struct ReadView {
     uint32_t shift0; // flat position of the first base of the batch
     uint32_t ulen;   // 0: ragged
     uint32_t ipr;    // items per read (uniform)
+    uint64_t ipr_magic; // floor(2^64 / ipr) + 1, or 0 when ipr == 1: item / ipr without a division
+    __host__ void set_ipr(uint32_t v) {
+        ipr = v;
+        // (2^64 - 1) / v == floor(2^64 / v) unless v is a power of two, where it is one less
+        ipr_magic = v > 1 ? ~0ull / v + ((v & (v - 1)) == 0 ? 2 : 1) : 0;
+    }
 };
+
+// n / d for n < 2^32 and d < 2^32 with m = floor(2^64 / d) + 1: hi64(n * m) (exact because n * d < 2^64);
+// a 32-bit division is ~20 instructions, this is two wide multiplies
+__device__ __forceinline__ uint32_t div_magic(uint32_t n, uint64_t m) {
+    const uint64_t lo = (uint64_t)n * (uint32_t)m;
+    const uint64_t hi = (uint64_t)n * (uint32_t)(m >> 32) + (lo >> 32);
+    return (uint32_t)(hi >> 32);
+}
 
 template <class K> struct ItemWindows {
     Roller<K> r;
@@ -296,7 +311,7 @@ template <class K> struct ItemWindows {
             uint64_t rd, pos;
             uint32_t u;
             if (v.n_items <= 0xFFFFFFFFull) {
-                rd = (uint32_t)item / v.ipr;
+                rd = v.ipr_magic ? div_magic((uint32_t)item, v.ipr_magic) : (uint32_t)item;
                 u = (uint32_t)item - (uint32_t)rd * v.ipr;
             }
             else {
@@ -549,26 +564,42 @@ __device__ unsigned long long g_phase_cycles[8];
 #define KTG_PHASE_RESET()
 #endif
 
+// dynamic shared memory of a tile scatter: the sorted tile | per bin: gaddr 8, spill 8, start 4, cnt 2 x 4 | sketch
+__host__ __device__ constexpr size_t scatter_smem_bytes(size_t tile, size_t key_bytes, size_t n_bins, bool hll) {
+    return tile * key_bytes + n_bins * 28 + (hll ? (size_t)4096 * 4 : 0);
+}
 template <class K, int TILE> struct ScatterSmem {
     K *keys;                    // TILE: the tile sorted by bin
-    unsigned long long *gdelta; // n_bins: output position of the bin's run minus its start in the sorted tile
+    unsigned long long *gaddr;  // n_bins: byte address of the bin's destination minus its start in the sorted tile
     unsigned long long *spill;  // n_bins: reserved start in the overflow array
     uint32_t *start;            // n_bins: start of the bin's run in the sorted tile
     uint32_t *cnt;              // 2 x n_bins (double buffered)
     uint32_t *regs;             // HLL_M (only with HLL)
-    uint16_t *binof;            // TILE: bin of every key of the sorted tile
     __device__ __forceinline__ void carve(unsigned char *base, uint32_t n_bins, bool hll) {
         keys = (K *)base;
-        gdelta = (unsigned long long *)(keys + TILE);
-        spill = gdelta + n_bins;
+        gaddr = (unsigned long long *)(keys + TILE);
+        spill = gaddr + n_bins;
         start = (uint32_t *)(spill + n_bins);
         cnt = start + n_bins;
         regs = cnt + 2 * n_bins;
-        binof = (uint16_t *)(regs + (hll ? HLL_M : 0));
     }
-    __host__ __device__ static size_t bytes(uint32_t n_bins, bool hll) {
-        return (size_t)TILE * (sizeof(K) + 2) + (size_t)n_bins * 28 + (hll ? HLL_M * 4 : 0);
+    __host__ __device__ static size_t bytes(uint32_t n_bins, bool hll) { return scatter_smem_bytes(TILE, sizeof(K), n_bins, hll); }
+};
+
+// The bin of a key as a function object: the copy-out of the tile scatter recomputes it from the key
+// (a dozen ALU instructions) instead of keeping a 16-bit bin per position in shared memory.  Both
+// partition levels are bound by shared-memory wavefronts, not by issue slots (level 2: LSU data pipe at
+// 78 %, 22 wavefronts per 32 keys of which the randomly placed 16-bit store and its load were 4.5).
+template <class K, int BINS> struct BinByPlace { // BIN_PART / BIN_OWNER / BIN_OWNER_PART of place_hash
+    uint32_t world, n_sub;
+    __device__ __forceinline__ uint32_t operator()(K key) const {
+        const Place p = place_of(KeyTraits<K>::place_hash(key), world, n_sub);
+        return BINS == 1 ? p.owner : BINS == 0 ? p.part : p.owner * n_sub + p.part;
     }
+};
+template <class K> struct BinByPage { // level 2: the page inside the sub-table
+    uint32_t sub_mask, page_log2;
+    __device__ __forceinline__ uint32_t operator()(K key) const { return (KeyTraits<K>::slot_hash(key) & sub_mask) >> page_log2; }
 };
 
 // Multi-GPU fused scatter: bins are owner ranks and the bucket of owner o lives in the
@@ -598,25 +629,41 @@ struct ScatterOut {
 
 // Preconditions: sm.cnt[parity] is zero, the block is synchronised.
 // Leaves sm.cnt[parity ^ 1] zeroed and the block synchronised.
-// Output positions are 64-bit (a stage may hold any number of keys): the sorted tile keeps the BIN of
-// every key (16 bits) and the copy-out adds the bin's 64-bit `gdelta`; neighbouring lanes mostly share
-// a bin, so that load is a broadcast.
-template <class K, int THREADS, int PER>
+// Output positions are 64-bit (a stage may hold any number of keys): every bin of the tile has the
+// bin's 64-bit `gaddr` (the byte address its run would have at tile position 0) which the copy-out adds
+// to the position; it finds the bin by `bin_of(key)`; neighbouring lanes mostly share a bin, so the
+// gaddr load is a broadcast.
+// ALL: every key of the tile is valid (vmask is ignored).  Bins must be < n_bins for invalid keys too.
+// SYNC_END = false: no barrier after the copy-out.  The next call's first writes to what the copy-out reads
+// (the sorted tile, gaddr, start, s_total, s_ovf) all come after its own first barrier, so a caller that
+// does not touch the tile's shared memory between two calls may let its warps run ahead into the next
+// tile's loads and hashing while the others still copy out (6 -> 4 barriers per tile with the scan below).
+template <class K, int THREADS, int PER, bool ALL = false, bool SYNC_END = true, class BinFn>
 __device__ __forceinline__ void tile_scatter(const K (&key)[PER], const uint32_t (&bin)[PER],
                                              uint32_t vmask, ScatterSmem<K, THREADS * PER> &sm,
                                              uint32_t n_bins, unsigned long long *cursors,
                                              uint64_t bin_off, const ScatterOut &o, uint32_t parity,
-                                             const PeerOut *po = nullptr) {
+                                             const BinFn &bin_of, const PeerOut *po = nullptr) {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_total, s_ovf;
+    static_assert(THREADS * PER <= 65536, "ranks are kept in 16 bits");
     uint32_t *cnt = sm.cnt + parity * n_bins;
-    uint32_t rank[PER];
+    // bin (low 16 bits) and rank inside the bin's run (high 16 bits) of every key in ONE register.  As two
+    // values the bin did not survive the 64-register cap: the compiler recomputed the key's hash and its
+    // range reduction for the placement (14 of the level-1 kernel's 118 instructions per key, 11 of the
+    // 85 of level 2; profiles/r02_sass_tile_scatter.md).  The rank comes out of the atomic, so the packed
+    // word cannot be rematerialised.
+    uint32_t br[PER];
     KTG_PHASE_BEGIN();
 #pragma unroll
-    for (int j = 0; j < PER; ++j)
-        if (vmask & (1u << j)) rank[j] = atomicAdd(&cnt[bin[j]], 1u);
-    if (threadIdx.x == 0) s_ovf = 0;
+    for (int j = 0; j < PER; ++j) {
+        // an invalid key adds 0 to its (in-range) bin: no branch around the atomic
+        uint32_t w = bin[j] | (atomicAdd(&cnt[bin[j]], ALL ? 1u : ((vmask >> j) & 1u)) << 16);
+        asm volatile("" : "+r"(w)); // opaque: keeps the compiler from splitting the word again and recomputing the bin later
+        br[j] = w;
+    }
     __syncthreads();
+    if (threadIdx.x == 0) s_ovf = 0; // (after the barrier: a warp of the previous call may still have been reading it)
     KTG_PHASE(1);
     // block-wide exclusive scan of the bin counts; reserve HBM ranges.  The global atomicAdd
     // that reserves a bin's range is issued BEFORE the scan so that its round trip to L2
@@ -661,7 +708,8 @@ __device__ __forceinline__ void tile_scatter(const K (&key)[PER], const uint32_t
             unsigned long long base = base1;
             if (c) {
                 if (!one) base = atomicAdd(&cursors[i], (unsigned long long)((c + padm) & ~padm));
-                sm.gdelta[i] = base - run;
+                const unsigned long long dst0 = (unsigned long long)(po ? po->rxb[i / po->bins_per_owner] : o.out);
+                sm.gaddr[i] = dst0 + (base - run) * sizeof(K);
                 if (o.bucket_cap) {
                     const unsigned long long lim = (bin_off + i + 1) * o.bucket_cap;
                     if (base + c > lim) {
@@ -678,12 +726,14 @@ __device__ __forceinline__ void tile_scatter(const K (&key)[PER], const uint32_t
     __syncthreads();
     KTG_PHASE(2);
 #pragma unroll
-    for (int j = 0; j < PER; ++j)
-        if (vmask & (1u << j)) {
-            const uint32_t pos = sm.start[bin[j]] + rank[j];
-            sm.keys[pos] = key[j];
-            sm.binof[pos] = (uint16_t)bin[j];
-        }
+    for (int j = 0; j < PER; ++j) {
+        const uint32_t b = br[j] & 0xFFFFu;
+        uint32_t pos = sm.start[b] + (br[j] >> 16);
+        // an invalid key goes to the last position of the tile, which no valid key can have then and
+        // which the copy-out does not reach: no branch around the stores
+        if (!ALL && !((vmask >> j) & 1u)) pos = THREADS * PER - 1;
+        sm.keys[pos] = key[j];
+    }
     {   // the other counter buffer is free now: zero it for the next tile
         uint32_t *nxt = sm.cnt + (parity ^ 1u) * n_bins;
         for (uint32_t i = threadIdx.x; i < n_bins; i += THREADS) nxt[i] = 0;
@@ -691,24 +741,24 @@ __device__ __forceinline__ void tile_scatter(const K (&key)[PER], const uint32_t
     __syncthreads();
     KTG_PHASE(3);
     const uint32_t total = s_total;
-    K *out = (K *)o.out;
-    if (!s_ovf && po) { // bins are owner-major: one contiguous range of the sorted tile per destination GPU
-        for (uint32_t w = 0; w < po->world; ++w) {
-            const uint32_t beg = sm.start[w * po->bins_per_owner];
-            const uint32_t end = w + 1 < po->world ? sm.start[(w + 1) * po->bins_per_owner] : total;
-            K *dst = (K *)po->rxb[w];
-            for (uint32_t i = beg + threadIdx.x; i < end; i += THREADS) dst[sm.gdelta[sm.binof[i]] + i] = sm.keys[i];
+    if (!s_ovf) { // runs of the sorted tile to their buckets (local HBM, or a peer's over NVLink)
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const uint32_t i = threadIdx.x + (uint32_t)(j * THREADS);
+            if (ALL || i < total) {
+                const K kk = sm.keys[i];
+                *(K *)(sm.gaddr[bin_of(kk)] + (unsigned long long)i * sizeof(K)) = kk;
+            }
         }
-    }
-    else if (!s_ovf) {
-        for (uint32_t i = threadIdx.x; i < total; i += THREADS) out[sm.gdelta[sm.binof[i]] + i] = sm.keys[i];
     }
     else { // some bin of this tile ran past its bucket (rare)
         for (uint32_t i = threadIdx.x; i < total; i += THREADS) {
-            const uint32_t b = sm.binof[i];
+            const uint32_t b = bin_of(sm.keys[i]);
+            K *out = (K *)(po ? po->rxb[b / po->bins_per_owner] : o.out);
+            // position of the bin's run in `out` minus its start in the tile (may be negative)
+            const long long gdelta = (long long)(sm.gaddr[b] - (unsigned long long)out) / (long long)sizeof(K);
             const unsigned long long lim = (bin_off + b + 1) * o.bucket_cap;
-            const unsigned long long dst = sm.gdelta[b] + i, base = sm.gdelta[b] + sm.start[b];
-            if (po) out = (K *)po->rxb[b / po->bins_per_owner];
+            const unsigned long long dst = (unsigned long long)(gdelta + i), base = (unsigned long long)(gdelta + sm.start[b]);
             if (dst < lim) out[dst] = sm.keys[i];
             else {
                 const unsigned long long first = base > lim ? base : lim;
@@ -722,13 +772,14 @@ __device__ __forceinline__ void tile_scatter(const K (&key)[PER], const uint32_t
         for (uint32_t b = 0; b < n_bins; ++b) {
             const uint32_t c = cnt[b];
             if (c == 0 || (c & padm) == 0) continue;
-            const unsigned long long base = sm.gdelta[b] + sm.start[b], lim = (bin_off + b + 1) * o.bucket_cap;
             K *dst = (K *)po->rxb[b / po->bins_per_owner];
+            const long long gdelta = (long long)(sm.gaddr[b] - (unsigned long long)dst) / (long long)sizeof(K);
+            const unsigned long long base = (unsigned long long)(gdelta + sm.start[b]), lim = (bin_off + b + 1) * o.bucket_cap;
             for (uint32_t j = c + threadIdx.x; j < ((c + padm) & ~padm); j += THREADS)
                 if (base + j < lim) dst[base + j] = KeyTraits<K>::empty();
         }
     }
-    __syncthreads();
+    if (SYNC_END) __syncthreads();
     KTG_PHASE(4);
 }
 
@@ -781,7 +832,7 @@ scatter_reads_kernel(ReadView v, uint32_t k, Table<K> t, uint32_t n_bins, Scatte
             const uint32_t vmask = (iw.mask >> (pass * PER)) & ((1u << PER) - 1u);
             if (HLL) hll_update_tile<K, PER>(sm.regs, key, sampled & vmask);
             tile_scatter<K, SCATTER_THREADS, PER>(key, bin, vmask, sm, n_bins, o.cursors, 0, o, parity,
-                                                  (BINS != BIN_PART && po.world) ? &po : nullptr);
+                                                  BinByPlace<K, BINS>{t.world, t.n_sub}, (BINS != BIN_PART && po.world) ? &po : nullptr);
         }
     }
     if (HLL) {
@@ -823,7 +874,8 @@ scatter_keys_kernel(const K *__restrict__ keys, uint64_t n, Table<K> t, uint32_t
             if (in) vmask |= 1u << j;
         }
         if (HLL) hll_update_tile<K, SCATTER_PER>(sm.regs, key, sampled);
-        tile_scatter<K, SCATTER_THREADS, SCATTER_PER>(key, bin, vmask, sm, n_bins, o.cursors, 0, o, parity);
+        tile_scatter<K, SCATTER_THREADS, SCATTER_PER>(key, bin, vmask, sm, n_bins, o.cursors, 0, o, parity,
+                                                      BinByPlace<K, BY_OWNER ? BIN_OWNER : BIN_PART>{t.world, t.n_sub});
     }
     if (HLL) {
         __syncthreads();
@@ -868,11 +920,51 @@ scatter_buckets_kernel(const K *__restrict__ keys1, const unsigned long long *__
     __syncthreads();
     uint32_t parity = 0;
     const uint32_t tpb = (uint32_t)tiles_per_bin;
-    for (uint32_t tile = blockIdx.x; tile < (uint32_t)n_tiles; tile += gridDim.x) {
-        const uint32_t q = tile / tpb; // (32-bit: as 64-bit division and modulo these two lines were 6 % of the kernel)
-        const uint32_t b = LEVEL == 2 ? (sub_mod ? q % sub_mod : q) : 0;
+    // bucket q = tile / tpb, tile inside it tq = tile % tpb, sub-table b = q % sub_mod, all advanced without
+    // dividing: a division per tile and thread is ~25 instructions that every lane repeats (as tile / tpb
+    // and q % sub_mod they were 10 % of this kernel's instructions)
+    uint32_t q = blockIdx.x / tpb, tq = blockIdx.x - q * tpb;
+    uint32_t b = LEVEL == 2 ? (sub_mod ? q % sub_mod : q) : 0;
+    const uint32_t dq = gridDim.x / tpb, dt = gridDim.x - dq * tpb;
+    auto advance = [&]() {
+        uint32_t adv = dq;
+        tq += dt;
+        if (tq >= tpb) {
+            tq -= tpb;
+            ++adv;
+        }
+        q += adv;
+        if (LEVEL == 2) {
+            b += adv;
+            if (sub_mod) while (b >= sub_mod) b -= sub_mod;
+        }
+    };
+    for (uint32_t tile = blockIdx.x; tile < (uint32_t)n_tiles; tile += gridDim.x, advance()) {
         const uint64_t lim = ((uint64_t)q + 1) * cap1, fill = fill1[q];
-        const uint64_t base = (uint64_t)q * cap1 + (uint64_t)(tile - q * tpb) * L2S_TILE;
+        const uint64_t base = (uint64_t)q * cap1 + (uint64_t)tq * L2S_TILE;
+        // This CTA's next tile: its keys would come straight from HBM into the registers that hash them
+        // (long scoreboard was this kernel's first stall reason), so every thread asks L2 for its share of
+        // them once this tile's own loads are out (C2: 1.27 -> 1.18 ms).  Only up to the bucket's fill: a
+        // stage sized for more keys than it holds has whole tiles of unused capacity.
+        uint64_t nbase = 0, nfill = 0;
+        if (tile + gridDim.x < (uint32_t)n_tiles) {
+            uint32_t qn = q + dq, tn = tq + dt;
+            if (tn >= tpb) {
+                tn -= tpb;
+                ++qn;
+            }
+            nbase = (uint64_t)qn * cap1 + (uint64_t)tn * L2S_TILE;
+            const uint64_t nlim = ((uint64_t)qn + 1) * cap1, f = fill1[qn];
+            nfill = f < nlim ? f : nlim;
+        }
+        auto prefetch_next = [&]() {
+            const uint64_t first = nbase + (uint64_t)threadIdx.x * L2S_PER; // the thread's L2S_PER consecutive keys
+            if (first < nfill) {
+                const unsigned char *nx = (const unsigned char *)(keys1 + first);
+#pragma unroll
+                for (int h = 0; h < (int)(L2S_PER * sizeof(K) / 32); ++h) prefetch_l2(nx + h * 32);
+            }
+        };
         const uint64_t end = fill < lim ? fill : lim;
         if (base >= end) continue;
         K key[L2S_PER];
@@ -888,8 +980,9 @@ scatter_buckets_kernel(const K *__restrict__ keys1, const unsigned long long *__
                 bin[j] = (KeyTraits<K>::slot_hash(key[j]) & t.sub_mask) >> t.page_log2;
             }
             KTG_PHASE(0);
-            tile_scatter<K, L2S_THREADS, L2S_PER>(key, bin, (1u << L2S_PER) - 1u, sm, n2, o.cursors + (uint64_t)b * n2,
-                                                  (uint64_t)b * n2, o, parity);
+            prefetch_next();
+            tile_scatter<K, L2S_THREADS, L2S_PER, true, false>(key, bin, (1u << L2S_PER) - 1u, sm, n2, o.cursors + (uint64_t)b * n2,
+                                                               (uint64_t)b * n2, o, parity, BinByPage<K>{t.sub_mask, t.page_log2});
             parity ^= 1u;
             continue;
         }
@@ -913,7 +1006,13 @@ scatter_buckets_kernel(const K *__restrict__ keys1, const unsigned long long *__
         if (threadIdx.x == 0 && key[L2S_PER - 1] == (K)12345) g_phase_cycles[7] = 1; // wait for the loads
 #endif
         KTG_PHASE(0);
-        tile_scatter<K, L2S_THREADS, L2S_PER>(key, bin, vmask, sm, n2, o.cursors + (uint64_t)b * n2, (uint64_t)b * n2, o, parity);
+        prefetch_next();
+        if (LEVEL == 2)
+            tile_scatter<K, L2S_THREADS, L2S_PER, false, false>(key, bin, vmask, sm, n2, o.cursors + (uint64_t)b * n2, (uint64_t)b * n2, o,
+                                                                parity, BinByPage<K>{t.sub_mask, t.page_log2});
+        else
+            tile_scatter<K, L2S_THREADS, L2S_PER, false, false>(key, bin, vmask, sm, n2, o.cursors, 0, o, parity,
+                                                                BinByPlace<K, BIN_PART>{t.world, t.n_sub});
         parity ^= 1u;
     }
 }
@@ -1036,7 +1135,7 @@ __device__ __forceinline__ bool page_probe_once(PageCtx<K> &c, const Table<K> &t
         return false;
     }
     st = (st + PQ_STEP) & (0xFFFF0000u | c.page_mask); // next slot (wraps inside the page), one more probe
-    if (((st & ~PQ_INC2) >> PQ_PROBE_SHIFT) > c.page_mask) { // every slot holds another key
+    if (st & ((c.page_mask + 1u) << PQ_PROBE_SHIFT)) { // 2^page_log2 probes: every slot holds another key
         unsigned long long pos = atomicAdd(t.ovf_count, 1ull); // replayed after a grow
         if (pos < t.ovf_cap) {
             t.ovf_keys[pos] = key;
@@ -1097,11 +1196,16 @@ template <class K> __host__ __device__ constexpr size_t page_kernel_smem(int thr
     return (size_t)nbuf * ((sizeof(K) + 4) << page_log2) + (size_t)(threads / 32) * PQ_CAP * (sizeof(K) + 4) + 16;
 }
 
-template <class K, int THREADS, int NBUF, int PAGE_UNROLL = ktg::PAGE_UNROLL>
+// MODE: what a key may need besides the plain update (mutually exclusive, fixed per build):
+//   PAGE_PALIN    reverse_complement with even k: a k-mer equal to its reverse complement counts twice;
+//   PAGE_SPECIAL  no canonicalisation at full key width: the all-ones key (T...T) lives in the special weight.
+// As run-time flags the two tests were 4 % of the kernel's instructions for every build.
+constexpr int PAGE_PLAIN = 0, PAGE_PALIN = 1, PAGE_SPECIAL = 2;
+template <class K, int THREADS, int NBUF, int MODE = PAGE_PLAIN, int PAGE_UNROLL = ktg::PAGE_UNROLL>
 __global__ void __launch_bounds__(THREADS, NBUF == 1 ? 2 : 1)
 update_pages_kernel(const K *__restrict__ keys2, const unsigned long long *__restrict__ cursors2,
-                    uint64_t cap2, uint32_t k, bool check_palindrome, bool has_special, Table<K> t,
-                    const unsigned char *__restrict__ empty_page) {
+                    uint64_t cap2, uint32_t k, Table<K> t, const unsigned char *__restrict__ empty_page) {
+    constexpr bool check_palindrome = MODE == PAGE_PALIN, has_special = MODE == PAGE_SPECIAL;
     typedef KeyTraits<K> T;
     extern __shared__ __align__(16) unsigned char smem[];
     const uint32_t P = 1u << t.page_log2;
@@ -1164,14 +1268,40 @@ update_pages_kernel(const K *__restrict__ keys2, const unsigned long long *__res
                 if (check_palindrome && revcomp(my[q], k) == my[q]) st[q] |= PQ_INC2;
                 cur[q] = smem_load(&c.sk[st[q] & 0xFFFFu]);
             }
+            // The first probe only takes the hit -- the slot already holds the key, 30 of 32 lanes on C2 --
+            // with one compare and one atomicAdd.  Everything else (an empty slot to claim, another key
+            // to step over) goes to the warp's queue with the slot NOT advanced and is handled there in
+            // full rows of 32 by page_probe_once: the claim / collision code, which the whole warp used
+            // to walk through for the 2-6 lanes that needed it, now runs with every lane busy
+            // (57 -> 37 warp instructions per row of 32 keys on C2).
 #pragma unroll
             for (int q = 0; q < PAGE_UNROLL; ++q) {
-                const bool pending = active[q] && page_probe_once(c, t, my[q], st[q], cur[q]);
-                page_push(c, my[q], st[q], pending);
+                const bool hit = active[q] && cur[q] == my[q];
+                if (hit) atomicAdd(&c.sw[st[q] & 0xFFFFu], 1u + (st[q] >> 31));
+                page_push(c, my[q], st[q], active[q] && !hit);
                 page_retry_rows(c, t);
             }
         };
+        // The keys are read once, straight from HBM (~800 cycles) into the registers that hash them, and a
+        // warp has nothing else to do meanwhile (long scoreboard was the first stall reason).  Every lane
+        // asks L2 for one 32-byte sector of the rows its warp takes NEXT (32 lanes cover 1 KB: the
+        // PAGE_UNROLL rows of u64 keys, half of them for u128), and the warp's first rows of the CTA's
+        // next page are requested when this page starts.
+        constexpr uint32_t PF_GROUPS = PAGE_UNROLL * 32 * sizeof(K) / 1024; // 1 KB requests per group of rows
+        auto prefetch_rows = [&](const K *p, uint32_t r, uint32_t cnt) {
+#pragma unroll
+            for (uint32_t h = 0; h < PF_GROUPS; ++h) {
+                const uint32_t off = h * 1024 + lane * 32; // bytes from the first key of the group
+                if (r * (uint32_t)sizeof(K) + off < cnt * (uint32_t)sizeof(K)) prefetch_l2((const unsigned char *)(p + r) + off);
+            }
+        };
+        if (g + gridDim.x < n_pages) {
+            const uint64_t gn = g + gridDim.x, begn = gn * cap2, curn = cursors2[gn];
+            const uint32_t nn = (uint32_t)((curn < begn + cap2 ? curn : begn + cap2) - begn);
+            prefetch_rows(keys2 + begn, wid * 32 * PAGE_UNROLL, nn);
+        }
         for (uint32_t r0 = wid * 32 * PAGE_UNROLL; r0 < n; r0 += THREADS * PAGE_UNROLL) {
+            prefetch_rows(src, r0 + THREADS * PAGE_UNROLL, n);
             if (r0 + 32 * PAGE_UNROLL <= n) rows(r0, std::true_type{});
             else rows(r0, std::false_type{});
         }

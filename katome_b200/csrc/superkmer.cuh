@@ -138,6 +138,9 @@ __host__ __device__ __forceinline__ uint32_t skm_record_count(u128 rec) { return
 __host__ __device__ __forceinline__ uint32_t skm_record_owner_field(u128 rec) {
     return ((uint32_t)rec >> SKM_OWNER_SHIFT) & 15u;
 }
+struct SkmRecordOwner { // the bin of a record in the sender's tile scatter
+    __device__ __forceinline__ uint32_t operator()(u128 rec) const { return skm_record_owner_field(rec); }
+};
 // the j-th k-mer of a record, forward strand
 __host__ __device__ __forceinline__ uint64_t skm_record_kmer(u128 rec, uint32_t k, uint32_t j) {
     return (uint64_t)(rec >> (128 - 2 * (k + j))) & ((1ull << (2 * k)) - 1ull);
@@ -317,7 +320,7 @@ scatter_superkmers_kernel(SkmView sv, uint32_t k, uint32_t world, ScatterOut o, 
                 if (in) vmask |= 1u << q;
             }
             // (tile_scatter's first barrier orders these reads before it rewrites sm.keys)
-            tile_scatter<u128, SCATTER_THREADS, SCATTER_PER>(rec, bin, vmask, sm, world, o.cursors, 0, o, parity, &po);
+            tile_scatter<u128, SCATTER_THREADS, SCATTER_PER>(rec, bin, vmask, sm, world, o.cursors, 0, o, parity, SkmRecordOwner{}, &po);
             parity ^= 1u;
         }
     }
@@ -404,7 +407,8 @@ scatter_records_kernel(const u128 *__restrict__ rx, const unsigned long long *__
             }
         }
         hll_update_tile<uint64_t, SREC_PER>(g_regs, key, sampled);
-        tile_scatter<uint64_t, SREC_THREADS, SREC_PER>(key, bin, vmask, sm, n_bins, o.cursors, 0, o, parity);
+        tile_scatter<uint64_t, SREC_THREADS, SREC_PER>(key, bin, vmask, sm, n_bins, o.cursors, 0, o, parity,
+                                                       BinByPlace<uint64_t, BIN_PART>{t.world, t.n_sub});
         parity ^= 1u;
         if (threadIdx.x == 0) s_count = from;
         __syncthreads();
