@@ -190,6 +190,7 @@ struct Tuning {
     int page_log2 = 0;       // slots per page, log2 (0: PageGeom)
     int l2s_variant = -1;    // level-2 scatter geometry (-1: the default of the key width)
     int l1_ctas = 0;         // cap on the level-1 scatter's CTAs per SM (0: occupancy)
+    int l1_big = -1;         // level-1 scatter with the big tile (two extraction passes): -1 = when a thread of the one-pass kernel would have more than one bin, 0 / 1 = never / always
     int p2p_ctas = 0;        // same for the fused exchange kernels
     int chunk_mb = 64;       // host batcher: bytes of bases per chunk
     int stage_bufs = 2;      // host batcher: staging buffers under the full chunks
@@ -833,7 +834,21 @@ template <class K> struct Builder : BuilderBase {
             int g = (int)std::min<uint64_t>(grid_for(kern, SCATTER_THREADS, sb, props), n_tiles);
             kern<<<g, SCATTER_THREADS, sb, stream>>>(bt.v, k, tab, n_bins, o, (uint32_t *)b_hll.p, peers);
         };
-        if (rc) launch(scatter_reads_kernel<K, true, BINS, HLL>, ScatterGeom<K>::PER);
+        // more bins than the one-pass kernel has threads: the big-tile kernel (two extraction passes, 64 KB tiles)
+        const bool big = tune.l1_big < 0 ? n_bins > (uint32_t)SCATTER_THREADS : tune.l1_big != 0;
+        auto launch_big = [&](auto kern) {
+            const size_t sb = big_scatter_smem(BigGeom<K>::TILE, sizeof(K), n_bins, HLL);
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);
+            uint64_t nt = std::max<uint64_t>(1, (bt.v.n_items + BIG_THREADS * BigGeom<K>::IPT - 1) / (BIG_THREADS * BigGeom<K>::IPT));
+            if (cap_ctas > 0) nt = std::min<uint64_t>(nt, (uint64_t)props.sms * cap_ctas);
+            int g = (int)std::min<uint64_t>(grid_for(kern, BIG_THREADS, sb, props), nt);
+            kern<<<g, BIG_THREADS, sb, stream>>>(bt.v, k, tab, n_bins, o, (uint32_t *)b_hll.p, peers);
+        };
+        if (big && n_bins <= 2 * BIG_THREADS && big_scatter_smem(BigGeom<K>::TILE, sizeof(K), n_bins, HLL) <= 113 * 1024) {
+            if (rc) launch_big(scatter_reads_big_kernel<K, true, BINS, HLL>);
+            else launch_big(scatter_reads_big_kernel<K, false, BINS, HLL>);
+        }
+        else if (rc) launch(scatter_reads_kernel<K, true, BINS, HLL>, ScatterGeom<K>::PER);
         else launch(scatter_reads_kernel<K, false, BINS, HLL>, ScatterGeom<K>::PER);
         prof.end(stream);
         return KTG_OK;

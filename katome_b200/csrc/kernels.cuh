@@ -356,6 +356,18 @@ template <class K> struct ItemWindows {
     template <bool RC> __device__ __forceinline__ K key() const {
         return (RC && r.rc < r.fw) ? r.rc : r.fw;
     }
+    // asks L2 for the packed words a later load(v, item, k) of a uniform batch will read.  (Loading them
+    // into registers one tile ahead instead was slower: 1.85 against 1.73 ms on C2, the kernel sits at
+    // its 64-register cap.)
+    static __device__ __forceinline__ void prefetch(const ReadView &v, uint64_t item) {
+        if (!v.ulen || item >= v.n_items || v.n_items > 0xFFFFFFFFull) return;
+        const uint32_t rd = v.ipr_magic ? div_magic((uint32_t)item, v.ipr_magic) : (uint32_t)item;
+        const uint32_t u = (uint32_t)item - rd * v.ipr;
+        const uint64_t pos = (uint64_t)rd * v.ulen + GRAN * u + v.shift0;
+        const uint64_t *p = v.packed + (pos >> 5);
+        prefetch_l2(p);
+        prefetch_l2(p + (sizeof(K) == 16 ? 3 : 2)); // the span may cross into the next 32-byte sector
+    }
 };
 
 // ======================================================================= K3 (direct)
@@ -815,6 +827,7 @@ scatter_reads_kernel(ReadView v, uint32_t k, Table<K> t, uint32_t n_bins, Scatte
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         ItemWindows<K> iw;
         iw.load(v, tile * SCATTER_THREADS + threadIdx.x, k);
+        ItemWindows<K>::prefetch(v, (tile + gridDim.x) * SCATTER_THREADS + threadIdx.x); // this CTA's next tile
 #pragma unroll
         for (int pass = 0; pass < GRAN / PER; ++pass, parity ^= 1u) {
             K key[PER];
@@ -839,6 +852,179 @@ scatter_reads_kernel(ReadView v, uint32_t k, Table<K> t, uint32_t n_bins, Scatte
         __syncthreads();
         for (uint32_t i = threadIdx.x; i < HLL_M; i += SCATTER_THREADS)
             if (sm.regs[i]) atomicMax(&g_regs[i], sm.regs[i]);
+    }
+}
+
+// ---- Level 1 with a BIG tile, for many bins (more than one per thread of the kernel above).
+// The one-pass kernel keeps a tile's keys in registers across its scan, which caps the tile at 2048
+// keys; with 450 bins (C3 at k = 63) that is 4.5 keys = 73 bytes per run and 450 cursor reservations
+// (64-bit L2 atomics) per 2048 keys, and the kernel takes 12 ps per key where 104 bins cost 5.4.
+// This one extracts every window TWICE -- once to count the bins, once more, after the scan, to put the
+// key where it belongs in the sorted tile -- so that a thread holds one key at a time and the tile is as
+// large as shared memory: 64 KB of keys (8192 u64 / 4096 u128) under 512 threads, two CTAs per SM.
+// Extraction is the cheap part (30-40 ALU instructions per window against the shared-memory sort), the
+// per-bin work is spread over 2-4 times as many keys and the runs are that much longer.
+constexpr int BIG_THREADS = 512;
+template <class K> struct BigGeom {
+    static constexpr int IPT = sizeof(K) == 8 ? 2 : 1;      // work items (of GRAN windows) per thread and tile
+    static constexpr int TILE = BIG_THREADS * IPT * GRAN;   // keys
+};
+__host__ __device__ constexpr size_t big_scatter_smem(size_t tile, size_t key_bytes, size_t n_bins, bool hll) {
+    return tile * key_bytes + n_bins * 24 + (hll ? (size_t)4096 * 4 : 0); // per bin: gaddr 8, spill 8, start 4, count / cursor 4
+}
+
+template <class K, bool RC, int BINS, bool HLL>
+__global__ void __launch_bounds__(BIG_THREADS, 2)
+scatter_reads_big_kernel(ReadView v, uint32_t k, Table<K> t, uint32_t n_bins, ScatterOut o,
+                         uint32_t *__restrict__ g_regs, PeerOut po_) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int IPT = BigGeom<K>::IPT, TILE = BigGeom<K>::TILE, THREADS = BIG_THREADS;
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_total, s_ovf;
+    K *keys = (K *)smem;
+    unsigned long long *gaddr = (unsigned long long *)(keys + TILE);
+    unsigned long long *spill = gaddr + n_bins;
+    uint32_t *start = (uint32_t *)(spill + n_bins);
+    uint32_t *cnt = start + n_bins; // the bins' counts (pass A), then their running cursors in the sorted tile (pass B)
+    uint32_t *regs = cnt + n_bins;
+    const PeerOut *po = (BINS != BIN_PART && po_.world) ? &po_ : nullptr;
+    const BinByPlace<K, BINS> bin_of{t.world, t.n_sub};
+    for (uint32_t i = threadIdx.x; i < n_bins + (HLL ? HLL_M : 0); i += THREADS) cnt[i] = 0; // counts and sketch are adjacent
+    __syncthreads();
+    const uint64_t n_tiles = (v.n_items + THREADS * IPT - 1) / (THREADS * IPT);
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        // pass A: count
+#pragma unroll
+        for (int a = 0; a < IPT; ++a) {
+            ItemWindows<K> iw;
+            iw.load(v, (tile * IPT + a) * THREADS + threadIdx.x, k);
+#pragma unroll
+            for (int j = 0; j < GRAN; ++j) {
+                const K key = iw.template key<RC>();
+                const uint32_t h = KeyTraits<K>::place_hash(key);
+                const Place p = place_of(h, t.world, t.n_sub);
+                const uint32_t b = BINS == BIN_OWNER ? p.owner : BINS == BIN_PART ? p.part : p.owner * t.n_sub + p.part;
+                const uint32_t valid = (iw.mask >> j) & 1u;
+                atomicAdd(&cnt[b], valid); // an invalid key adds 0 to its (in-range) bin: no branch
+                if (HLL) hll_update(regs, key, h, valid != 0);
+                iw.r.step();
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_ovf = 0;
+        {   // scan of the counts, reservation of the output ranges (as in tile_scatter), counts -> cursors
+            // (n_bins <= 2 * THREADS: at most two bins per thread, both reservations go out before the scan so
+            // that their round trips to L2 overlap its barriers)
+            const uint32_t b0 = threadIdx.x * 2;
+            const uint32_t padm = po ? po->pad - 1u : 0u;
+            uint32_t c2[2] = {0, 0};
+            unsigned long long base2[2] = {0, 0};
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                if (b0 + q < n_bins) c2[q] = cnt[b0 + q];
+                if (c2[q]) base2[q] = atomicAdd(&o.cursors[b0 + q], (unsigned long long)((c2[q] + padm) & ~padm));
+            }
+            const uint32_t s = c2[0] + c2[1];
+            uint32_t incl = s;
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t x = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if ((threadIdx.x & 31) >= d) incl += x;
+            }
+            if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                uint32_t w = threadIdx.x < THREADS / 32 ? s_warp[threadIdx.x] : 0, iv = w;
+                for (int d = 1; d < 32; d <<= 1) {
+                    uint32_t x = __shfl_up_sync(0xFFFFFFFFu, iv, d);
+                    if (threadIdx.x >= d) iv += x;
+                }
+                s_warp[threadIdx.x] = iv - w;
+                if (threadIdx.x == 31) s_total = iv;
+            }
+            __syncthreads();
+            uint32_t run = s_warp[threadIdx.x >> 5] + incl - s;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const uint32_t i = b0 + q, c = c2[q];
+                if (i >= n_bins) break;
+                if (c) {
+                    const unsigned long long base = base2[q];
+                    const unsigned long long dst0 = (unsigned long long)(po ? po->rxb[i / po->bins_per_owner] : o.out);
+                    gaddr[i] = dst0 + (base - run) * sizeof(K);
+                    if (o.bucket_cap) {
+                        const unsigned long long lim = ((unsigned long long)i + 1) * o.bucket_cap;
+                        if (base + c > lim) {
+                            const unsigned long long over = base + c - (base > lim ? base : lim);
+                            spill[i] = atomicAdd(o.spill_cursor, over);
+                            s_ovf = 1;
+                        }
+                    }
+                }
+                start[i] = run;
+                cnt[i] = run;
+                run += c;
+            }
+        }
+        __syncthreads();
+        // pass B: the same windows again, every key to its place in the sorted tile
+#pragma unroll
+        for (int a = 0; a < IPT; ++a) {
+            ItemWindows<K> iw;
+            iw.load(v, (tile * IPT + a) * THREADS + threadIdx.x, k);
+#pragma unroll
+            for (int j = 0; j < GRAN; ++j) {
+                const K key = iw.template key<RC>();
+                const Place p = place_of(KeyTraits<K>::place_hash(key), t.world, t.n_sub);
+                const uint32_t b = BINS == BIN_OWNER ? p.owner : BINS == BIN_PART ? p.part : p.owner * t.n_sub + p.part;
+                const uint32_t valid = (iw.mask >> j) & 1u;
+                uint32_t pos = atomicAdd(&cnt[b], valid);
+                if (!valid) pos = TILE - 1; // the last position is free whenever a key is invalid, and never copied out then
+                keys[pos] = key;
+                iw.r.step();
+            }
+        }
+        __syncthreads();
+        const uint32_t total = s_total;
+        if (!s_ovf) {
+            for (uint32_t i = threadIdx.x; i < total; i += THREADS) {
+                const K kk = keys[i];
+                *(K *)(gaddr[bin_of(kk)] + (unsigned long long)i * sizeof(K)) = kk;
+            }
+        }
+        else { // some bin of this tile ran past its bucket (rare)
+            for (uint32_t i = threadIdx.x; i < total; i += THREADS) {
+                const uint32_t b = bin_of(keys[i]);
+                K *out = (K *)(po ? po->rxb[b / po->bins_per_owner] : o.out);
+                const long long gdelta = (long long)(gaddr[b] - (unsigned long long)out) / (long long)sizeof(K);
+                const unsigned long long lim = ((unsigned long long)b + 1) * o.bucket_cap;
+                const unsigned long long dst = (unsigned long long)(gdelta + i), base = (unsigned long long)(gdelta + start[b]);
+                if (dst < lim) out[dst] = keys[i];
+                else {
+                    const unsigned long long first = base > lim ? base : lim;
+                    const unsigned long long so = spill[b] + (dst - first);
+                    if (so < o.spill_cap) ((K *)o.spill_out)[so] = keys[i];
+                }
+            }
+        }
+        if (po && po->pad > 1) { // the rounded-up tail of every run (inside the bucket) is filled with all-ones keys
+            const uint32_t padm = po->pad - 1u;
+            for (uint32_t b = 0; b < n_bins; ++b) {
+                const uint32_t c = (b + 1 < n_bins ? start[b + 1] : total) - start[b];
+                if (c == 0 || (c & padm) == 0) continue;
+                K *dst = (K *)po->rxb[b / po->bins_per_owner];
+                const long long gdelta = (long long)(gaddr[b] - (unsigned long long)dst) / (long long)sizeof(K);
+                const unsigned long long base = (unsigned long long)(gdelta + start[b]), lim = ((unsigned long long)b + 1) * o.bucket_cap;
+                for (uint32_t j = c + threadIdx.x; j < ((c + padm) & ~padm); j += THREADS)
+                    if (base + j < lim) dst[base + j] = KeyTraits<K>::empty();
+            }
+        }
+        __syncthreads(); // the copy-out has read the tile, the cursors are dead: counts back to zero for the next tile
+        for (uint32_t i = threadIdx.x; i < n_bins; i += THREADS) cnt[i] = 0;
+        __syncthreads();
+    }
+    if (HLL) {
+        for (uint32_t i = threadIdx.x; i < HLL_M; i += THREADS)
+            if (regs[i]) atomicMax(&g_regs[i], regs[i]);
     }
 }
 

@@ -1280,7 +1280,7 @@ static int set_option_on(BuilderBase *impl, const char *name, int64_t value) {
     Tuning &t = impl->tune;
     const struct { const char *n; int *p; } ints[] = {
         {"page_threads", &t.page_threads}, {"page_nbuf", &t.page_nbuf}, {"page_log2", &t.page_log2},
-        {"l2s_variant", &t.l2s_variant}, {"l1_ctas", &t.l1_ctas}, {"p2p_ctas", &t.p2p_ctas},
+        {"l2s_variant", &t.l2s_variant}, {"l1_ctas", &t.l1_ctas}, {"l1_big", &t.l1_big}, {"p2p_ctas", &t.p2p_ctas},
         {"chunk_mb", &t.chunk_mb}, {"stage_bufs", &t.stage_bufs}, {"flush_pct", &t.flush_pct},
         {"flush_pct2", &t.flush_pct2}, {"taper", &t.taper}, {"eager_pages", &t.eager_pages},
         {"stage_factor_milli", &t.stage_factor_milli}, {"host_parse", &t.host_parse},

@@ -221,6 +221,41 @@ def test_heavy_hitters_overflow_the_page_buckets_without_loss(K, k, rc):
     assert m.digest()[3] >= 1_200 * (100 - k + 1)  # one homopolymer k-mer alone: far more than a page bucket holds
 
 
+@pytest.mark.parametrize("k,rc", [(21, True), (31, True), (32, False), (33, True), (40, False), (63, True), (64, False)])
+def test_big_tile_level1_scatter(K, k, rc):
+    """The level-1 scatter with the big tile (two extraction passes, 64 KB of keys per tile; the default when
+    a table has more than 256 sub-tables, forced here with the l1_big option on tables of many small
+    sub-tables): uniform and ragged reads with N / lowercase, T...T at full key width, and homopolymer
+    reads that overflow their level-1 buckets into the spill list -- against the oracle, and bin for bin
+    against the one-pass kernel."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(77 * k + rc)
+    genome = "".join(rng.choice(list("ACGT"), size=150_000))
+    uniform = [genome[i:i + 100] for i in rng.integers(0, len(genome) - 100, size=40_000)]
+    uniform[5] = uniform[5][:50] + "N" + uniform[5][51:]
+    uniform[6] = uniform[6].lower()
+    for i in range(0, len(uniform), 9):  # 11 % low-complexity reads: a few bins get far more than their bucket holds
+        uniform[i] = ("T" * 100, "A" * 100, "GT" * 50, "ACGT" * 25)[(i // 9) % 4]
+    ragged = H.random_reads(rng, 20_000, max(k, 66), 180, genome=genome, n_rate=0.02) + ["T" * (k + 3), "A" * k]
+    for name, seqs in (("uniform", uniform), ("ragged", ragged)):
+        bases, offsets = H.batch_of(seqs)
+        m = O.MtCounter(k, rc)
+        m.add_reads(bases, offsets)
+        got = []
+        for big in (1, 0):
+            for kw in ({"force_pages": True, "sub_table_log2_bytes": 16, "edges_count": 600_000},   # hundreds of sub-tables
+                       {"force_partition": True, "no_pages": True, "sub_table_log2_bytes": 17, "edges_count": 600_000},
+                       {"force_pages": True, "sub_table_log2_bytes": 18, "edges_count": 600_000, "options": {"chunk_mb": 1}}):
+                kw = dict(kw)
+                kw["options"] = dict(kw.get("options", {}), l1_big=big)
+                g = K.GpuGIR(k, rc, **kw)
+                assert g.add_reads(bases, offsets) == m.counters(), (name, kw)
+                assert g.digest() == m.digest(), (name, kw)
+                got.append(g.counts())
+                g.close()
+        assert len(set(got)) == 1, got
+
+
 def test_paged_and_atomic_paths_agree_at_scale(K):
     """mini-C2 shape, default path selection (page update) against L2 atomics only"""
     from katome_b200.workloads import Workload
