@@ -835,7 +835,9 @@ template <class K> struct Builder : BuilderBase {
             kern<<<g, SCATTER_THREADS, sb, stream>>>(bt.v, k, tab, n_bins, o, (uint32_t *)b_hll.p, peers);
         };
         // more bins than the one-pass kernel has threads: the big-tile kernel (two extraction passes, 64 KB tiles)
-        const bool big = tune.l1_big < 0 ? n_bins > (uint32_t)SCATTER_THREADS : tune.l1_big != 0;
+        // (and the sender of the direct exchange, whose bins are owner x sub-table: NVLink wants the longer runs --
+        // 100-byte runs reached ~320 GB/s, C3 at N = 2: 20.4 ms with the one-pass sender, 17.3 with this one)
+        const bool big = tune.l1_big < 0 ? (n_bins > (uint32_t)SCATTER_THREADS || (po && BINS == BIN_OWNER_PART)) : tune.l1_big != 0;
         auto launch_big = [&](auto kern) {
             const size_t sb = big_scatter_smem(BigGeom<K>::TILE, sizeof(K), n_bins, HLL);
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);

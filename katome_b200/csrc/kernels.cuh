@@ -217,6 +217,47 @@ template <class K> struct Roller {
     }
 };
 
+// ---- mbarrier / bulk-copy PTX (sm_90+; the 1-D flavour of TMA needs no tensor map)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared, completion counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// shared -> global, tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void bulk_s2g(void *gdst, const void *smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// orders this thread's generic-proxy writes to shared memory before later async-proxy (bulk copy) reads
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // ============================================================ cardinality
 // HyperLogLog sketch (2^12 registers) of the keys offered to the table, merged
 // into a persistent sketch with atomicMax.  The host sizes / grows the table
@@ -639,6 +680,33 @@ struct ScatterOut {
     unsigned long long spill_cap;
 };
 
+// Copy-out of a sorted tile into PEER memory (NVLink): every run is written from its own start, so that a
+// warp's store covers whole 128-byte lines of the destination (the runs start on line boundaries there,
+// PeerOut::pad) -- lanes that straddle two runs split lines between two stores, and NVLink carries partial
+// packets (7.2 against 5.9 ms for the sender of the key exchange on C3 at N = 2).  Few bins (owners): all
+// threads walk one run after the other; many bins (owner x sub-table): a warp per run.
+template <class K, int THREADS>
+__device__ __forceinline__ void copy_out_runs(const K *keys, const uint32_t *start, const unsigned long long *gaddr,
+                                              uint32_t n_bins, uint32_t total) {
+    constexpr uint32_t NW = THREADS / 32;
+    if (n_bins <= 2 * NW) {
+        for (uint32_t b = 0; b < n_bins; ++b) {
+            const uint32_t beg = start[b], end = b + 1 < n_bins ? start[b + 1] : total;
+            const unsigned long long ga = gaddr[b];
+            for (uint32_t i = beg + threadIdx.x; i < end; i += THREADS) *(K *)(ga + (unsigned long long)i * sizeof(K)) = keys[i];
+        }
+    }
+    else {
+        const uint32_t lane = threadIdx.x & 31;
+        for (uint32_t b = threadIdx.x >> 5; b < n_bins; b += NW) {
+            const uint32_t beg = start[b], end = b + 1 < n_bins ? start[b + 1] : total;
+            if (beg == end) continue;
+            const unsigned long long ga = gaddr[b];
+            for (uint32_t i = beg + lane; i < end; i += 32) *(K *)(ga + (unsigned long long)i * sizeof(K)) = keys[i];
+        }
+    }
+}
+
 // Preconditions: sm.cnt[parity] is zero, the block is synchronised.
 // Leaves sm.cnt[parity ^ 1] zeroed and the block synchronised.
 // Output positions are 64-bit (a stage may hold any number of keys): every bin of the tile has the
@@ -753,7 +821,8 @@ __device__ __forceinline__ void tile_scatter(const K (&key)[PER], const uint32_t
     __syncthreads();
     KTG_PHASE(3);
     const uint32_t total = s_total;
-    if (!s_ovf) { // runs of the sorted tile to their buckets (local HBM, or a peer's over NVLink)
+    if (!s_ovf && po) copy_out_runs<K, THREADS>(sm.keys, sm.start, sm.gaddr, n_bins, total);
+    else if (!s_ovf) { // runs of the sorted tile to their buckets
 #pragma unroll
         for (int j = 0; j < PER; ++j) {
             const uint32_t i = threadIdx.x + (uint32_t)(j * THREADS);
@@ -985,7 +1054,12 @@ scatter_reads_big_kernel(ReadView v, uint32_t k, Table<K> t, uint32_t n_bins, Sc
         }
         __syncthreads();
         const uint32_t total = s_total;
-        if (!s_ovf) {
+        // (Leaving by bulk copies instead -- cp.async.bulk shared -> global, one per run, issued by the thread
+        // that owns the bin, the next tile's counting pass running meanwhile -- was implemented and measured:
+        // 14.5 against 13.5 ms on C3 k = 63, 7.97 against 8.04 ms for the sender of the direct exchange at
+        // N = 2; a few hundred bytes per copy is too little for the copy engine.)
+        if (!s_ovf && po) copy_out_runs<K, THREADS>(keys, start, gaddr, n_bins, total);
+        else if (!s_ovf) {
             for (uint32_t i = threadIdx.x; i < total; i += THREADS) {
                 const K kk = keys[i];
                 *(K *)(gaddr[bin_of(kk)] + (unsigned long long)i * sizeof(K)) = kk;
@@ -1219,47 +1293,6 @@ constexpr int PAGE_UNROLL = 4;
 template <class K> struct PageGeom;
 template <> struct PageGeom<uint64_t> { static constexpr uint32_t LOG2 = 13; }; // 8192 x (8+4) B =  96 KB
 template <> struct PageGeom<u128> { static constexpr uint32_t LOG2 = 12; };     // 4096 x (16+4) B = 80 KB
-
-// ---- mbarrier / bulk-copy PTX (sm_90+; the 1-D flavour of TMA needs no tensor map)
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-// global -> shared, completion counted in bytes on the mbarrier
-__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(smem_dst)),
-                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-// shared -> global, tracked by the issuing thread's bulk async-group
-__device__ __forceinline__ void bulk_s2g(void *gdst, const void *smem_src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
-                 "r"(bytes)
-                 : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-// orders this thread's generic-proxy writes to shared memory before later async-proxy (bulk copy) reads
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ uint64_t smem_cas(uint64_t *p, uint64_t cmp, uint64_t val) {
     return atomicCAS((unsigned long long *)p, (unsigned long long)cmp, (unsigned long long)val);

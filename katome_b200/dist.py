@@ -119,12 +119,15 @@ class ShardedGIR:
         # is the default from SKM_MIN_WORLD ranks on ("skm" / "keys" force one).
         want_skm = mode == "skm" or (mode == "fused" and self.world >= self.SKM_MIN_WORLD)
         self.exchange = "nccl" if not self.fused else ("skm" if skm_supported(k) and want_skm else "keys")
-        # the direct exchange replaces the key exchange whenever every shard has the same geometry (checked per
-        # batch); "keys" forces the older one
-        # opt-in: measured on 2 B200s (C3, profiles/r02_mg_n2_*.json) the sender's 100-byte runs reach only
-        # ~320 GB/s over NVLink and its 11.6 ms cost more than the owner's pass it saves (5.9 + 4.4 ms)
-        self.direct = self.fused and mode == "direct"
-        if mode == "direct":
+        # The direct exchange (the sender bins by owner AND sub-table with the big-tile level-1 kernel, the
+        # owner goes straight to its level-2 scatter) replaces the key exchange below SKM_MIN_WORLD ranks
+        # whenever every shard has the same geometry (checked per batch; "keys" forces the key exchange).
+        # Measured on B200s, C3 as one job (profiles/r02e_*): N = 2 17.2 ms against 18.5 for the key exchange;
+        # N = 8 6.5 ms against 5.8 for super-k-mers -- its sender is NVLink bound (8 bytes per window against
+        # 2.9), so from 4 ranks on it stays opt-in ("direct").  With the one-pass sender of the first version
+        # (2048-key tiles, ~100-byte runs reached ~320 GB/s over NVLink) it lost at N = 2 as well (20.4 ms).
+        self.direct = self.fused and (mode == "direct" or (mode == "fused" and self.world < self.SKM_MIN_WORLD))
+        if self.direct:
             self.exchange = "keys"
         self._mapped_for = None
         self.last_exchange = self.exchange
