@@ -939,7 +939,8 @@ template <class K> struct BigGeom {
     static constexpr int TILE = BIG_THREADS * IPT * GRAN;   // keys
 };
 __host__ __device__ constexpr size_t big_scatter_smem(size_t tile, size_t key_bytes, size_t n_bins, bool hll) {
-    return tile * key_bytes + n_bins * 24 + (hll ? (size_t)4096 * 4 : 0); // per bin: gaddr 8, spill 8, start 4, count / cursor 4
+    // per bin: gaddr 8, spill 8, start 4, count / cursor 4; 128-bit keys: the bin of every tile position, 2 bytes
+    return tile * key_bytes + n_bins * 24 + (hll ? (size_t)4096 * 4 : 0) + (key_bytes == 16 ? tile * 2 : 0);
 }
 
 template <class K, bool RC, int BINS, bool HLL>
@@ -956,6 +957,13 @@ scatter_reads_big_kernel(ReadView v, uint32_t k, Table<K> t, uint32_t n_bins, Sc
     uint32_t *start = (uint32_t *)(spill + n_bins);
     uint32_t *cnt = start + n_bins; // the bins' counts (pass A), then their running cursors in the sorted tile (pass B)
     uint32_t *regs = cnt + n_bins;
+    // The bins found in pass A stay in registers (16 bits each) for pass B, and for 128-bit keys pass B also
+    // leaves the bin of every tile position in shared memory for the copy-out: this kernel is bound by the
+    // math pipes (its extraction runs twice), and the hash of a u128 key is 14 instructions.  For u64 keys
+    // the copy-out recomputes the bin like the one-pass kernel (no room for the array beside 8192 keys).
+    constexpr bool BINOF = sizeof(K) == 16;
+    uint16_t *binof = (uint16_t *)(regs + (HLL ? HLL_M : 0));
+    uint32_t bins2[IPT * GRAN / 2];
     const PeerOut *po = (BINS != BIN_PART && po_.world) ? &po_ : nullptr;
     const BinByPlace<K, BINS> bin_of{t.world, t.n_sub};
     for (uint32_t i = threadIdx.x; i < n_bins + (HLL ? HLL_M : 0); i += THREADS) cnt[i] = 0; // counts and sketch are adjacent
@@ -976,6 +984,8 @@ scatter_reads_big_kernel(ReadView v, uint32_t k, Table<K> t, uint32_t n_bins, Sc
                 const uint32_t valid = (iw.mask >> j) & 1u;
                 atomicAdd(&cnt[b], valid); // an invalid key adds 0 to its (in-range) bin: no branch
                 if (HLL) hll_update(regs, key, h, valid != 0);
+                if (j & 1) bins2[(a * GRAN + j) / 2] |= b << 16;
+                else bins2[(a * GRAN + j) / 2] = b;
                 iw.r.step();
             }
         }
@@ -1043,12 +1053,12 @@ scatter_reads_big_kernel(ReadView v, uint32_t k, Table<K> t, uint32_t n_bins, Sc
 #pragma unroll
             for (int j = 0; j < GRAN; ++j) {
                 const K key = iw.template key<RC>();
-                const Place p = place_of(KeyTraits<K>::place_hash(key), t.world, t.n_sub);
-                const uint32_t b = BINS == BIN_OWNER ? p.owner : BINS == BIN_PART ? p.part : p.owner * t.n_sub + p.part;
+                const uint32_t b = (bins2[(a * GRAN + j) / 2] >> (16 * (j & 1))) & 0xFFFFu;
                 const uint32_t valid = (iw.mask >> j) & 1u;
                 uint32_t pos = atomicAdd(&cnt[b], valid);
                 if (!valid) pos = TILE - 1; // the last position is free whenever a key is invalid, and never copied out then
                 keys[pos] = key;
+                if (BINOF) binof[pos] = (uint16_t)b;
                 iw.r.step();
             }
         }
@@ -1062,12 +1072,12 @@ scatter_reads_big_kernel(ReadView v, uint32_t k, Table<K> t, uint32_t n_bins, Sc
         else if (!s_ovf) {
             for (uint32_t i = threadIdx.x; i < total; i += THREADS) {
                 const K kk = keys[i];
-                *(K *)(gaddr[bin_of(kk)] + (unsigned long long)i * sizeof(K)) = kk;
+                *(K *)(gaddr[BINOF ? (uint32_t)binof[i] : bin_of(kk)] + (unsigned long long)i * sizeof(K)) = kk;
             }
         }
         else { // some bin of this tile ran past its bucket (rare)
             for (uint32_t i = threadIdx.x; i < total; i += THREADS) {
-                const uint32_t b = bin_of(keys[i]);
+                const uint32_t b = BINOF ? (uint32_t)binof[i] : bin_of(keys[i]);
                 K *out = (K *)(po ? po->rxb[b / po->bins_per_owner] : o.out);
                 const long long gdelta = (long long)(gaddr[b] - (unsigned long long)out) / (long long)sizeof(K);
                 const unsigned long long lim = ((unsigned long long)b + 1) * o.bucket_cap;
