@@ -373,7 +373,9 @@ int ktg_host_parse_file(const char *path, int file_type, uint64_t batch_bytes, u
  * library reads the environment).  Names: page_threads, page_nbuf, page_log2, l2s_variant, l1_ctas,
  * l1_big (level-1 scatter with the big tile: -1 when there are more than 256 bins, 0 never, 1 always), p2p_ctas, chunk_mb, stage_bufs, flush_pct, flush_pct2, taper, eager_pages, stage_factor_milli,
  * stage_max_keys, host_parse (ktg_create_from_files: records cut by the host reader instead of the
- * device), fastq_chunk_kb, mg_pad, mg_direct, trace (host timeline on stderr).  Unknown names: KTG_ERR_INVALID. */
+ * device), fastq_chunk_kb, mg_pad, mg_direct (a handle over several devices: the direct exchange; -1 below 4
+ * devices, 0 never, 1 whenever the shards' geometries agree), trace (host timeline on stderr).  Unknown names:
+ * KTG_ERR_INVALID. */
 int ktg_set_option(ktg_builder *b, const char *name, int64_t value);
 
 typedef struct ktg_info {

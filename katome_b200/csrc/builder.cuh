@@ -204,7 +204,8 @@ struct Tuning {
     int fastq_chunk_kb = 8 << 10; // device parser: raw bytes per chunk (page-locked memory costs ~1 ms per MiB to allocate:
                                   // four 16 MiB blocks were 74 ms of a 157 ms Build::create from a 950 MB FASTQ file)
     int mg_pad = 1;          // fused exchange: runs padded to 128-byte lines
-    int mg_direct = 0;       // multi-device handle: the direct exchange (sender bins by owner and sub-table) where the shards agree on their geometry
+    int mg_direct = -1;      // multi-device handle: the direct exchange (sender bins by owner and sub-table) where the shards agree on
+                             // their geometry: -1 = below 4 devices, 0 = never, 1 = whenever possible
     int trace = 0;           // host timeline on stderr
 };
 

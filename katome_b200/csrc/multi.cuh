@@ -290,7 +290,11 @@ struct MultiBuilder {
             // The direct exchange (every shard has the same geometry, no super-k-mers): the senders stream
             // all their chunks into the owners' (sender, sub-table) buckets without any barrier in between,
             // and the owners go straight to their page level, once, at the end.
-            if (!skm && same_geo && b->tune.mg_direct && (uint64_t)n * geo_sub[0] <= 1024) {
+            // Default below 4 devices (mg_direct = -1; 0 / 1 = never / whenever possible), like the per-rank
+            // processes: C3 over 2 B200s end to end 31.7 ms against 34.4 with the key exchange; from 4 devices on
+            // the super-k-mer exchange is faster (the direct sender is NVLink bound).
+            const bool want_direct = b->tune.mg_direct < 0 ? n < 4 : b->tune.mg_direct != 0;
+            if (!skm && same_geo && want_direct && (uint64_t)n * geo_sub[0] <= 1024) {
                 const uint32_t n_sub = geo_sub[0];
                 {
                     void *base = nullptr;

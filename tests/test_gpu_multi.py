@@ -27,13 +27,15 @@ for k, n, L, G in ((31, 6000, 150, 200_000), (63, 3000, 150, 100_000)):
     half = n // world
     mine = torch.from_numpy(reads[rank * half * L:(rank + 1) * half * L]).cuda()
     offs = torch.arange(0, (half + 1) * L, L, dtype=torch.int64, device="cuda")
-    for kw in ({}, {"exchange": "direct"}, {"exchange": "skm"}, {"fused": False}, {"force_pages": True, "exchange": "skm"},
-               {"force_pages": True, "exchange": "direct"},
+    for kw in ({}, {"exchange": "direct"}, {"exchange": "keys"}, {"exchange": "skm"}, {"fused": False},
+               {"force_pages": True, "exchange": "skm"}, {"force_pages": True, "exchange": "direct"},
+               {"force_pages": True, "exchange": "keys"},
                {"fused": False, "force_partition": True, "sub_table_log2_bytes": 16}):
         sg = ShardedGIR(k, True, **kw)
         # super-k-mer records need 23 <= k <= 31; below 8 ranks they are opt-in
         assert sg.exchange == ("nccl" if kw.get("fused") is False else "skm" if k <= 31 and kw.get("exchange") == "skm" else "keys")
-        assert sg.direct == (kw.get("exchange") == "direct")
+        # the direct exchange is the default below 4 ranks; "keys" / "skm" / fused=False ask for another one
+        assert sg.direct == (kw.get("exchange") == "direct" or (kw.get("exchange") is None and kw.get("fused") is not False))
         for _ in range(2):  # reset + rebuild gives the same table
             sg.reset()
             sg.add_reads_device(mine[: (half // 2) * L], offs[: half // 2 + 1], half // 2, (half // 2) * L)

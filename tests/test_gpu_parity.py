@@ -741,7 +741,7 @@ def test_superkmer_exchange_spill_route(K):
 def test_one_handle_over_several_shards(K, k, shards, rc, tmp_path):
     """ktg_config.n_devices: ONE handle whose table is hash-sharded over `shards` devices (here all on GPU 0),
     fed through the same ktg_add_reads / ktg_create_from_files, answering every query for the whole graph.
-    Keys exchange below 4 shards and for k outside 23..31, super-k-mer records otherwise.  Against the oracle:
+    Direct or key exchange below 4 shards and for k outside 23..31, super-k-mer records otherwise.  Against the oracle:
     counters, digest, sorted edges, node / degree statistics, the exported graph (identical to a one-GPU
     handle's, node numbering included), filter, standardize, reset, several calls, file input, the short read."""
     rng = np.random.default_rng(100 * k + shards)
@@ -754,11 +754,13 @@ def test_one_handle_over_several_shards(K, k, shards, rc, tmp_path):
     g = K.GpuGIR(k, rc, device_ids=ids, options={"chunk_mb": 1})  # several chunks per call
     assert g.add_reads(bases, offsets) == (cpu.accepted_reads, cpu.accepted_bytes)
     _assert_same(g, cpu)
-    # the direct exchange (the sender does the owner's level-1 partition too; opt-in)
-    g2 = K.GpuGIR(k, rc, device_ids=ids, options={"chunk_mb": 1, "mg_direct": 1})
-    assert g2.add_reads(bases, offsets) == (cpu.accepted_reads, cpu.accepted_bytes)
-    assert g2.digest() == cpu.digest() and g2.counts() == cpu.counts()
-    g2.close()
+    # the direct exchange (the sender does the owner's level-1 partition too: the default below 4 shards where
+    # the geometries agree) forced on and off
+    for direct in (1, 0):
+        g2 = K.GpuGIR(k, rc, device_ids=ids, options={"chunk_mb": 1, "mg_direct": direct})
+        assert g2.add_reads(bases, offsets) == (cpu.accepted_reads, cpu.accepted_bytes)
+        assert g2.digest() == cpu.digest() and g2.counts() == cpu.counts(), direct
+        g2.close()
     one = K.GpuGIR(k, rc)
     one.add_reads(bases, offsets)
     ga, gb = g.export_graph(), one.export_graph()
