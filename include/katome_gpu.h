@@ -360,6 +360,10 @@ int ktg_plan_chunks(const uint64_t *offsets, uint64_t n_reads, uint64_t chunk_by
                     uint32_t n_pcts, uint64_t *cuts, uint8_t *flush_after, uint32_t cap, uint32_t *n_chunks,
                     int64_t *tail_first);
 
+/* ---- test hook (no GPU needed): item / items_per_read the way the extraction kernels compute it for a batch
+ * of equally long reads (a multiplication by floor(2^64 / d) + 1 instead of a division): out[i] for items[i]. */
+int ktg_item_reads(const uint32_t *items, uint64_t n, uint32_t items_per_read, uint32_t *out);
+
 /* ---- test hook (no GPU needed): the host FASTQ / FASTA reader behind ktg_create_from_files alone
  * (csrc/host_reader.h: check_files, builder.rs:57-77, and the record semantics of rust-bio 0.10 that
  * create_fastq / create_fasta rely on, builder.rs:118-165): records read, bases in their sequences

@@ -27,7 +27,7 @@ SYMBOLS = (
     "ktg_collection_stats", "ktg_remove_weak_edges", "ktg_remove_single_vertices",
     "ktg_standardize_edges", "ktg_export_edges", "ktg_digest", "ktg_key_words", "ktg_owner_of",
     "ktg_partition_reads_device", "ktg_insert_keys_device", "ktg_host_alloc", "ktg_host_free",
-    "ktg_synth_reads_device", "ktg_random_access_probe", "ktg_get_profile", "ktg_reset_profile", "ktg_set_profile", "ktg_plan_chunks", "ktg_host_parse_file",
+    "ktg_synth_reads_device", "ktg_random_access_probe", "ktg_get_profile", "ktg_reset_profile", "ktg_set_profile", "ktg_plan_chunks", "ktg_item_reads", "ktg_host_parse_file",
     "ktg_get_info", "ktg_set_option", "ktg_export_externals", "ktg_graph_prepare", "ktg_wait_input", "ktg_partition_keys_device", "ktg_mg_plan", "ktg_mg_prepare",
     "ktg_mg_scatter_reads_device", "ktg_mg_direct_plan", "ktg_mg_direct_prepare", "ktg_mg_direct_scatter_reads_device",
     "ktg_mg_direct_insert", "ktg_mg_insert_buckets", "ktg_mg_sketch", "ktg_mg_merge_sketch", "ktg_mg_spill", "ktg_mg_insert_spill", "ktg_ipc_get_handle", "ktg_ipc_open", "ktg_ipc_close",
@@ -135,6 +135,7 @@ def lib():
     L.ktg_set_profile.argtypes = [vp, C.c_int]
     L.ktg_host_parse_file.argtypes = [C.c_char_p, C.c_int, C.c_uint64, u64p, u64p, u64p]
     L.ktg_plan_chunks.argtypes = [vp, C.c_uint64, C.c_uint64, vp, C.c_uint32, vp, vp, C.c_uint32, vp, vp]
+    L.ktg_item_reads.argtypes = [vp, C.c_uint64, C.c_uint32, vp]
     L.ktg_get_info.argtypes = [vp, C.POINTER(KtgInfo)]
     L.ktg_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     intp = C.POINTER(C.c_int)

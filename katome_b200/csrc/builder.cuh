@@ -921,7 +921,9 @@ template <class K> struct Builder : BuilderBase {
         const size_t ss = ScatterSmem<K, L2S_TILE>::bytes(tab.pages_per_sub(), false);
         // 256-thread CTAs (four per SM) overlap the phases of a tile better than 512-thread ones
         // (1.51 vs 1.60 ms on C2); u128 keys need the registers of the larger block
-        int variant = (sizeof(K) == 8 && tab.pages_per_sub() <= 256) ? 1 : 0; // at most one bin per thread
+        // u128 keys: 256 threads x 16 keys (126 registers, no spill; the 512 x 8 geometry spills 128 bytes at its
+        // 64-register cap): 10.7 against 10.9 ms on C3 k = 63
+        int variant = sizeof(K) == 16 ? 4 : tab.pages_per_sub() <= 256 ? 1 : 0; // u64: at most one bin per thread
         if (tune.l2s_variant >= 0) variant = tune.l2s_variant;
         prof.begin("scatter_pages", n_keys, stream);
         auto launch_v = [&](auto kern, int threads, int per) {

@@ -334,7 +334,7 @@ struct ReadView {
 
 // n / d for n < 2^32 and d < 2^32 with m = floor(2^64 / d) + 1: hi64(n * m) (exact because n * d < 2^64);
 // a 32-bit division is ~20 instructions, this is two wide multiplies
-__device__ __forceinline__ uint32_t div_magic(uint32_t n, uint64_t m) {
+__host__ __device__ __forceinline__ uint32_t div_magic(uint32_t n, uint64_t m) {
     const uint64_t lo = (uint64_t)n * (uint32_t)m;
     const uint64_t hi = (uint64_t)n * (uint32_t)(m >> 32) + (lo >> 32);
     return (uint32_t)(hi >> 32);

@@ -1221,6 +1221,14 @@ int ktg_reset_profile(ktg_builder *b) {
     return KTG_OK;
 }
 
+int ktg_item_reads(const uint32_t *items, uint64_t n, uint32_t items_per_read, uint32_t *out) {
+    if (!items || !out || items_per_read == 0) return fail(KTG_ERR_INVALID, "bad request");
+    ReadView v{};
+    v.set_ipr(items_per_read);
+    for (uint64_t i = 0; i < n; ++i) out[i] = v.ipr_magic ? div_magic(items[i], v.ipr_magic) : items[i];
+    return KTG_OK;
+}
+
 int ktg_plan_chunks(const uint64_t *offsets, uint64_t n_reads, uint64_t chunk_bytes, const uint32_t *flush_pcts,
                     uint32_t n_pcts, uint64_t *cuts, uint8_t *flush_after, uint32_t cap, uint32_t *n_chunks,
                     int64_t *tail_first) {

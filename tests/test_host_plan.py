@@ -101,3 +101,21 @@ def test_ragged_reads_and_a_read_longer_than_a_chunk():
     big = int(np.searchsorted(cuts, 1234, side="right")) - 1
     assert cuts[big] == 1234 and cuts[big + 1] == 1235
     assert total >= 3 * MB and flush.sum() == 1 and n - tail <= 4
+
+
+def test_item_to_read_without_a_division():
+    """The extraction kernels turn an item index into (read, granule) with a multiplication by
+    floor(2^64 / items_per_read) + 1 (kernels.cuh: ReadView::set_ipr, div_magic): exact for every 32-bit item."""
+    from katome_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(7)
+    edge = np.array([0, 1, 2, 3, 2**16 - 1, 2**16, 2**31 - 1, 2**31, 2**32 - 2, 2**32 - 1], dtype=np.uint64)
+    for d in [1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 63, 64, 65, 100, 255, 256, 1023, 1024, 1250, 4097, 65535, 65536,
+              99991, 2**20, 2**20 + 1, 2**31 - 1, 2**31, 2**32 - 1]:
+        top = (2**32 - 1) // d * d  # the largest multiple of d, and the ones just below it
+        mult = np.array([m for m in (top, top - d, top - 2 * d, d, 2 * d) if m > 0], dtype=np.uint64)
+        near = np.concatenate([mult - 1, mult, (mult + 1) % 2**32, edge * d % 2**32, np.arange(0, min(4 * d + 2, 4000), dtype=np.uint64)])
+        items = np.concatenate([rng.integers(0, 2**32, size=20000, dtype=np.uint64), edge, near]).astype(np.uint32)
+        out = np.empty(len(items), dtype=np.uint32)
+        assert L.ktg_item_reads(items.ctypes.data, len(items), d, out.ctypes.data) == 0
+        assert np.array_equal(out, (items.astype(np.uint64) // d).astype(np.uint32)), d
