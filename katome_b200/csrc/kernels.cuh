@@ -680,6 +680,13 @@ struct ScatterOut {
     unsigned long long spill_cap;
 };
 
+// a key stored once and read by a later kernel: evict-first, so that it does not push the tables' and the
+// buckets' live lines out of L2
+__device__ __forceinline__ void store_stream(uint64_t *p, uint64_t v) { __stcs((unsigned long long *)p, (unsigned long long)v); }
+__device__ __forceinline__ void store_stream(u128 *p, u128 v) {
+    __stcs((ulonglong2 *)p, make_ulonglong2((unsigned long long)v, (unsigned long long)(v >> 64)));
+}
+
 // Copy-out of a sorted tile into PEER memory (NVLink): every run is written from its own start, so that a
 // warp's store covers whole 128-byte lines of the destination (the runs start on line boundaries there,
 // PeerOut::pad) -- lanes that straddle two runs split lines between two stores, and NVLink carries partial
@@ -718,7 +725,10 @@ __device__ __forceinline__ void copy_out_runs(const K *keys, const uint32_t *sta
 // (the sorted tile, gaddr, start, s_total, s_ovf) all come after its own first barrier, so a caller that
 // does not touch the tile's shared memory between two calls may let its warps run ahead into the next
 // tile's loads and hashing while the others still copy out (6 -> 4 barriers per tile with the scan below).
-template <class K, int THREADS, int PER, bool ALL = false, bool SYNC_END = true, class BinFn>
+// STREAM: the copy-out's stores are evict-first (st.global.cs).  Measured per kernel: it helps the level-2
+// scatter of the large tables (512 pages per sub-table, u128 keys: C3 8.71 -> 8.35 ms, C3 k = 63 10.7 -> 10.2)
+// and hurts level 1 and the 256-thread level-2 geometry of C2 (1.14 -> 1.22 ms).
+template <class K, int THREADS, int PER, bool ALL = false, bool SYNC_END = true, bool STREAM = false, class BinFn>
 __device__ __forceinline__ void tile_scatter(const K (&key)[PER], const uint32_t (&bin)[PER],
                                              uint32_t vmask, ScatterSmem<K, THREADS * PER> &sm,
                                              uint32_t n_bins, unsigned long long *cursors,
@@ -828,7 +838,9 @@ __device__ __forceinline__ void tile_scatter(const K (&key)[PER], const uint32_t
             const uint32_t i = threadIdx.x + (uint32_t)(j * THREADS);
             if (ALL || i < total) {
                 const K kk = sm.keys[i];
-                *(K *)(sm.gaddr[bin_of(kk)] + (unsigned long long)i * sizeof(K)) = kk;
+                K *dst = (K *)(sm.gaddr[bin_of(kk)] + (unsigned long long)i * sizeof(K));
+                if (STREAM) store_stream(dst, kk);
+                else *dst = kk;
             }
         }
     }
@@ -1183,6 +1195,7 @@ scatter_buckets_kernel(const K *__restrict__ keys1, const unsigned long long *__
                        bool skip_empty, Table<K> t, ScatterOut o, uint32_t *__restrict__ g_regs = nullptr) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int L2S_TILE = L2S_THREADS * L2S_PER;
+    constexpr bool L2_STREAM = LEVEL == 2 && !(L2S_THREADS == 256 && L2S_PER == 8); // the geometries of the large tables
     const uint32_t n2 = LEVEL == 2 ? t.pages_per_sub() : t.n_sub;
     ScatterSmem<K, L2S_TILE> sm;
     sm.carve(smem, n2, false);
@@ -1251,7 +1264,7 @@ scatter_buckets_kernel(const K *__restrict__ keys1, const unsigned long long *__
             }
             KTG_PHASE(0);
             prefetch_next();
-            tile_scatter<K, L2S_THREADS, L2S_PER, true, false>(key, bin, (1u << L2S_PER) - 1u, sm, n2, o.cursors + (uint64_t)b * n2,
+            tile_scatter<K, L2S_THREADS, L2S_PER, true, false, L2_STREAM>(key, bin, (1u << L2S_PER) - 1u, sm, n2, o.cursors + (uint64_t)b * n2,
                                                                (uint64_t)b * n2, o, parity, BinByPage<K>{t.sub_mask, t.page_log2});
             parity ^= 1u;
             continue;
@@ -1278,7 +1291,7 @@ scatter_buckets_kernel(const K *__restrict__ keys1, const unsigned long long *__
         KTG_PHASE(0);
         prefetch_next();
         if (LEVEL == 2)
-            tile_scatter<K, L2S_THREADS, L2S_PER, false, false>(key, bin, vmask, sm, n2, o.cursors + (uint64_t)b * n2, (uint64_t)b * n2, o,
+            tile_scatter<K, L2S_THREADS, L2S_PER, false, false, L2_STREAM>(key, bin, vmask, sm, n2, o.cursors + (uint64_t)b * n2, (uint64_t)b * n2, o,
                                                                 parity, BinByPage<K>{t.sub_mask, t.page_log2});
         else
             tile_scatter<K, L2S_THREADS, L2S_PER, false, false>(key, bin, vmask, sm, n2, o.cursors, 0, o, parity,
