@@ -715,7 +715,7 @@ __device__ __forceinline__ void copy_out_runs(const K *keys, const uint32_t *sta
 }
 
 // Preconditions: sm.cnt[parity] is zero, the block is synchronised.
-// Leaves sm.cnt[parity ^ 1] zeroed and the block synchronised.
+// Leaves sm.cnt[parity ^ 1] zeroed and (SYNC_END) the block synchronised.
 // Output positions are 64-bit (a stage may hold any number of keys): every bin of the tile has the
 // bin's 64-bit `gaddr` (the byte address its run would have at tile position 0) which the copy-out adds
 // to the position; it finds the bin by `bin_of(key)`; neighbouring lanes mostly share a bin, so the
@@ -724,7 +724,8 @@ __device__ __forceinline__ void copy_out_runs(const K *keys, const uint32_t *sta
 // SYNC_END = false: no barrier after the copy-out.  The next call's first writes to what the copy-out reads
 // (the sorted tile, gaddr, start, s_total, s_ovf) all come after its own first barrier, so a caller that
 // does not touch the tile's shared memory between two calls may let its warps run ahead into the next
-// tile's loads and hashing while the others still copy out (6 -> 4 barriers per tile with the scan below).
+// tile's loads and hashing while the others still copy out (5 barriers per tile instead of 6).  Used by the
+// level-2 kernel (1.35 -> 1.32 ms on C2); the level-1 kernel was a little slower without the barrier.
 // STREAM: the copy-out's stores are evict-first (st.global.cs).  Measured per kernel: it helps the level-2
 // scatter of the large tables (512 pages per sub-table, u128 keys: C3 8.71 -> 8.35 ms, C3 k = 63 10.7 -> 10.2)
 // and hurts level 1 and the 256-thread level-2 geometry of C2 (1.14 -> 1.22 ms).
